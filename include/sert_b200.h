@@ -1,0 +1,174 @@
+/*
+ * sert_b200.h -- C-ABI of the B200-native SERT hot path (libsert_b200.so).
+ *
+ * The reference (cvangysel/SERT) has no FFI: its hot path is a Theano graph
+ * reached through the Python class surface of sert/models.py and four compiled
+ * callables (train_fn / test_fn / validate_fn / predict_fn).  Every entry point
+ * below replaces one of those callables or the numpy/sklearn ranking code of
+ * bin/query.py; the reference interface it stands in for is cited (file:line,
+ * relative to the reference checkout).  The Python mirror of the class surface
+ * (sert_b200/models.py, sert_b200/inference.py, sert_b200/ranking.py) binds these
+ * symbols with ctypes (sert_b200/_native.py); INTEGRATION.md shows the stub.
+ *
+ * Conventions
+ *   - plain C types only; no torch / CUDA types in signatures.  `stream` is a
+ *     cudaStream_t passed as void* (NULL = legacy default stream).
+ *   - every function returns 0 on success, non-zero on failure;
+ *     sert_last_error() returns the message of the calling thread's last failure
+ *     (the Python layer raises RuntimeError with it, matching the reference's
+ *     error behaviour, sert/models.py:372-379,624-628).
+ *   - "dev" pointers are device (HBM) addresses owned by the caller (the Python
+ *     layer allocates them as torch tensors: torch is the HBM allocator, nothing
+ *     else); "host" pointers are ordinary host memory (pinned memory makes the
+ *     copies asynchronous).
+ *   - one host thread per model; calls enqueue work on the model's stream and only
+ *     the *_fetch / *_host / get_* calls synchronise.
+ *   - all floating point is IEEE float32 (the reference aborts on float64,
+ *     sert/models.py:610-628); indices are int32 on the device.
+ */
+#ifndef SERT_B200_H_
+#define SERT_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SERT_ABI_VERSION 1
+
+#if defined(__GNUC__)
+#define SERT_API __attribute__((visibility("default")))
+#else
+#define SERT_API
+#endif
+
+/* model kinds: bin/train.py:21-24 MODELS */
+#define SERT_KIND_LOGLINEAR   0   /* sert.models.LanguageModel          (sert/models.py:804)  */
+#define SERT_KIND_VECTORSPACE 1   /* sert.models.VectorSpaceLanguageModel (sert/models.py:1024) */
+
+/* dataset splits: ModelInterface.TRAIN / VALIDATE (sert/models.py:312) */
+#define SERT_SPLIT_TRAIN    0
+#define SERT_SPLIT_VALIDATE 1
+
+/* parameter tensor ids for get/set */
+#define SERT_PARAM_WORD_REPR   0  /* R    (V,dw)   SparseProjectionLayer.representations, sert/models.py:167-171 */
+#define SERT_PARAM_DENSE_W     1  /* W    (dw,E) log-linear | (dw,de) vector space; DenseLayer.W, :846-849,1057-1061 */
+#define SERT_PARAM_DENSE_B     2  /* b    (E,) | (de,)      DenseLayer.b */
+#define SERT_PARAM_ENTITY_REPR 3  /* Eemb (E,de)  "Class representations", sert/models.py:940-941 (vector space only) */
+/* optimiser state slots (Adadelta: accu, delta_accu; Adam: m, v) */
+#define SERT_STATE_PARAM 0
+#define SERT_STATE_S1    1
+#define SERT_STATE_S2    2
+
+typedef struct sert_config {
+  int32_t kind;            /* SERT_KIND_* */
+  int32_t batch;           /* B: --batch_size, bin/train.py:41-42 */
+  int32_t window;          /* W: data_args.window_size, bin/prepare.py:54 */
+  int32_t num_negatives;   /* k: --num_negative_samples (vector space), bin/train.py:50-51 */
+  int64_t vocab;           /* V */
+  int64_t entities;        /* E */
+  int32_t word_dim;        /* dw: --word_representation_size */
+  int32_t entity_dim;      /* de: --entity_representation_size (vector space) */
+  float   lambda;          /* --regularization_lambda, bin/train.py:58-59 */
+  int32_t loss_slots;      /* capacity of the device-side per-batch loss buffer */
+  uint64_t seed;           /* negative-sampler seed (reference: unseeded RandomStreams, sert/models.py:958-959) */
+  int64_t entity_begin;    /* first entity column/row owned by this rank (0 when not sharded) */
+  int64_t entity_count;    /* entities owned by this rank (== entities when not sharded) */
+} sert_config;
+
+typedef struct sert_model sert_model;     /* opaque */
+typedef struct sert_scorer sert_scorer;   /* opaque */
+
+/* ---- library --------------------------------------------------------------------------- */
+SERT_API int         sert_abi_version(void);
+SERT_API const char *sert_last_error(void);
+/* number of kernels this library has launched since load (bench.py's gpu_launches) */
+SERT_API uint64_t    sert_launch_count(void);
+
+/* ---- model life cycle: replaces the model constructors, sert/models.py:806-878,1026-1105 -- */
+/* HBM bytes the model needs for parameters, optimiser state, gradients and workspaces. */
+SERT_API int sert_model_arena_bytes(const sert_config *cfg, size_t *bytes);
+/* `arena_dev` must hold sert_model_arena_bytes() bytes, 256-byte aligned; it is zero-filled by create. */
+SERT_API int sert_model_create(const sert_config *cfg, void *arena_dev, size_t arena_bytes, void *stream,
+                      sert_model **out);
+SERT_API int sert_model_destroy(sert_model *m);
+
+/* Parameter / optimiser-state transfer (host float32, row-major).  Replaces representations_init /
+ * entity_representations_init (sert/models.py:699-713,940-941) and get_representations()/get_state()
+ * (sert/models.py:670-680,797-801,943-945).  `which` = SERT_PARAM_*, `slot` = SERT_STATE_*. */
+SERT_API int sert_model_set_tensor(sert_model *m, int which, int slot, const float *host, size_t count);
+SERT_API int sert_model_get_tensor(sert_model *m, int which, int slot, float *host, size_t count);
+/* Adam's shared step counter t (lasagne.updates.adam t_prev; sert/models.py:922). */
+SERT_API int sert_model_set_step(sert_model *m, int64_t t);
+SERT_API int sert_model_get_step(sert_model *m, int64_t *t);
+
+/* ---- device-resident data set: replaces the theano.shared X/Y/W variables, sert/models.py:470-480 -- */
+/* x_dev (N,W) int32; labels either one-hot y_dev (N,) int32 (vector space, bin/train.py:186-245) or CSR
+ * (indptr_dev int64 (N+1), indices_dev int32, data_dev f32; bin/prepare.py:593-597); w_dev (N,) f32 or NULL
+ * (validation has no weights).  Pointers are borrowed until the model is destroyed. */
+SERT_API int sert_model_attach_dataset(sert_model *m, int split, int64_t n, const int32_t *x_dev,
+                              const int32_t *y_dev, const int64_t *indptr_dev, const int32_t *indices_dev,
+                              const float *data_dev, const float *w_dev);
+
+/* ---- train_fn(batch_index): sert/models.py:581-588, driven by _iterate_batches :351-399 ------- */
+/* Runs n training batches in the given order (host int64 batch indices; the shuffled order of
+ * sert/models.py:363-367).  neg_dev: (n,B,k) int32 device negatives or NULL = sample on device
+ * (sert/models.py:947-979).  Per-batch train losses go to loss slots [first_slot, first_slot+n). */
+SERT_API int sert_train_batches(sert_model *m, const int64_t *order_host, int64_t n, const int32_t *neg_dev,
+                       int32_t first_slot);
+/* test_fn / validate_fn (sert/models.py:593-608): eval loss of n batches of `split`. */
+SERT_API int sert_eval_batches(sert_model *m, int split, const int64_t *order_host, int64_t n,
+                      const int32_t *neg_dev, int32_t first_slot);
+/* Synchronises, copies loss slots to the host and fails with the reference's message if any is NaN/Inf
+ * (sert/models.py:372-379). */
+SERT_API int sert_losses_fetch(sert_model *m, int32_t first_slot, int64_t n, float *out_host);
+
+/* End-to-end variant of train_fn for callers that stream batches from the host: copies one batch
+ * (x (B,W) int32, labels, w (B,), negatives (B,k) or NULL) host->device, runs the step, reads the loss back. */
+SERT_API int sert_train_batch_host(sert_model *m, const int32_t *x_host, const int32_t *y_host,
+                          const int64_t *indptr_host, const int32_t *indices_host, const float *data_host,
+                          const float *w_host, const int32_t *neg_host, float *loss_host);
+
+/* ---- parity hooks (no reference counterpart; expose the graph's intermediate tensors) ---------- */
+/* vector space: forward of one attached batch; out_scores_host (B,1+k) = [u.E[y], u.E[n_j]] logits,
+ * out_proj_host (B,de) = clipped tanh projection u, out_ell_host (B,) instance losses. Any may be NULL. */
+SERT_API int sert_vs_forward_host(sert_model *m, int split, int64_t batch_index, const int32_t *neg_dev,
+                         float *out_scores_host, float *out_proj_host, float *out_ell_host);
+/* log-linear: z (B*W,E) per-word logits, s (B,E) joint logits, ell (B,). Any may be NULL. */
+SERT_API int sert_ll_forward_host(sert_model *m, int split, int64_t batch_index, float *out_z_host,
+                         float *out_s_host, float *out_ell_host);
+
+/* ---- predict_fn ------------------------------------------------------------------------------ */
+/* log-linear predict_fn(batch, mask) -> (rows,W,E) per-word softmax (sert/models.py:880-890; the mask is
+ * accepted and unused there).  rows <= B. Host in, host out. */
+SERT_API int sert_predict_loglinear(sert_model *m, const int32_t *batch_host, int32_t rows, float *out_host);
+/* vector-space predict_fn(avg) -> tanh(avg.W+b), no clip (sert/models.py:1107-1118), batched over q rows. */
+SERT_API int sert_project_queries(sert_model *m, const float *avg_host, int32_t q, float *out_host);
+
+/* ---- entity scoring: replaces VectorSpaceCallback's sklearn kNN / cdist, bin/query.py:241-318 -- */
+/* Builds a scorer over `rows` entity vectors of dimension d (host float32, row-major).  normalise!=0
+ * L2-normalises rows first (bin/query.py:270-274).  The rows are this rank's shard
+ * [row_begin, row_begin+rows) of the global matrix.  arena as for models. */
+SERT_API int sert_scorer_arena_bytes(int64_t rows, int32_t d, int32_t max_queries, int32_t max_k, size_t *bytes);
+SERT_API int sert_scorer_create(const float *entities_host, int64_t rows, int32_t d, int64_t row_begin,
+                       int32_t normalise, int32_t max_queries, int32_t max_k, void *arena_dev,
+                       size_t arena_bytes, void *stream, sert_scorer **out);
+SERT_API int sert_scorer_destroy(sert_scorer *s);
+/* Top-k by inner product of q query vectors (host f32 (q,d); normalise_q!=0 L2-normalises them,
+ * bin/query.py:333-336) against the shard.  Outputs (q,k) global row ids and float32 inner products,
+ * sorted by score descending (ties: lower row id first). */
+SERT_API int sert_scorer_topk_host(sert_scorer *s, const float *queries_host, int32_t q, int32_t normalise_q,
+                          int32_t k, int32_t *out_idx_host, float *out_score_host);
+/* Same, device in / device out, asynchronous on the scorer's stream (used under NCCL sharding). */
+SERT_API int sert_scorer_topk_dev(sert_scorer *s, const float *queries_dev, int32_t q, int32_t normalise_q,
+                         int32_t k, int32_t *out_idx_dev, float *out_score_dev);
+/* k-way merge of `parts` gathered (q,k) candidate lists laid out [part][q][k] into one (q,k) list. */
+SERT_API int sert_topk_merge_dev(const int32_t *idx_dev, const float *score_dev, int32_t parts, int32_t q, int32_t k,
+                        int32_t *out_idx_dev, float *out_score_dev, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SERT_B200_H_ */

@@ -1,0 +1,84 @@
+// Launcher declarations for the sm_100a kernels of libsert_b200.
+// Each launcher enqueues on `st` and returns 0 / -1 (error text via sert::set_error).
+#pragma once
+
+#include "common.cuh"
+
+namespace sert {
+
+// ---- embedding gather (sert/models.py:180) fused with the window mean (sert/models.py:226,1051) ---
+// out[i,:] = (sum_w R[x[i,w],:]) / denom        (pooled, (B,d))
+int launch_gather_pool(const int32_t *x, const float *R, float *out, int B, int W, int d, float denom,
+                       cudaStream_t st);
+// out[i*W+w,:] = R[x[i,w],:]                      (unpooled rows, (B*W,d); log-linear)
+int launch_gather_rows(const int32_t *x, const float *R, float *out, int64_t rows, int d, cudaStream_t st);
+
+// ---- small fp32 GEMMs on CUDA cores (vector-space projection, sert/models.py:1057-1061, and its grads) --
+enum GemmEpilogue { EPI_STORE = 0, EPI_BIAS_TANH = 1, EPI_ATOMIC_ADD = 2, EPI_BIAS = 3 };
+// C[M,N] = epi(op(A)[M,K] * op(B)[K,N]); a_t: A stored (K,M) row-major; b_t: B stored (N,K) row-major.
+// split_k > 1 requires EPI_ATOMIC_ADD.
+int launch_gemm_f32(const float *A, const float *Bm, float *C, int M, int N, int K, bool a_t, bool b_t,
+                    int lda, int ldb, int ldc, GemmEpilogue epi, const float *bias, int split_k,
+                    cudaStream_t st);
+// out[n] += sum_m A[m,n]   (bias gradient)
+int launch_colsum_atomic(const float *A, float *out, int M, int N, cudaStream_t st);
+
+// ---- vector-space negative-sampling loss, forward + backward (sert/models.py:1072-1098,893-902) ---
+struct VsNceArgs {
+  const float *t;        // (B,de) tanh(h.Wp+bp), unclipped
+  const float *Eemb;     // (E,de)
+  const int32_t *y;      // (B,)
+  const int32_t *neg;    // (B,k)
+  const float *w;        // (B,) instance weights or nullptr (=1)
+  float *gE;             // (E,de) gradient accumulator (train) or nullptr
+  uint32_t *flagE;       // (E,) touched stamps
+  uint32_t stamp;
+  float *da;             // (B,de) d loss / d pre-activation (train)
+  double *loss_acc;      // += sum_i w_i*ell_i (train) or sum_i ell_i (eval)
+  float *dbg_scores;     // (B,1+k) logits or nullptr
+  float *dbg_u;          // (B,de) clipped projection or nullptr
+  float *dbg_ell;        // (B,) or nullptr
+  int B, k, de;
+  float inv_B;
+  bool train;
+};
+int launch_vs_nce(const VsNceArgs &a, cudaStream_t st);
+
+// scatter-add of dh/denom into the word-gradient rows (autodiff of the gather, AdvancedIncSubtensor)
+int launch_scatter_rows(const int32_t *x, const float *dh, float *gR, uint32_t *flagR, uint32_t stamp,
+                        int B, int W, int d, float denom, cudaStream_t st);
+
+// uniform negatives with replacement over [0,E) (sert/models.py:956-973); Philox4x32-10
+int launch_sample_negatives(int32_t *out, int64_t n, int64_t E, uint64_t seed, uint64_t step,
+                            cudaStream_t st);
+
+// ---- dense optimisers with L2 (lasagne.updates.adam / adadelta; sert/models.py:764-795,820,922) -----
+struct ParamSegment {
+  long long offset;      // float offset inside the arena arrays
+  long long count;       // number of floats (multiple of 4, zero padded)
+  int row_len;           // floats per row for flag lookup
+  int regularised;       // contributes to the L2 term (bias does not)
+  const uint32_t *flags; // per-row touched stamps or nullptr (= always read the gradient)
+};
+constexpr int kMaxSegments = 4;
+struct OptimArgs {
+  float *theta, *s1, *s2, *grad;   // arena arrays of `total` floats
+  long long total;                 // multiple of 4
+  ParamSegment seg[kMaxSegments];
+  int num_segments;
+  uint32_t stamp;
+  float l2_scale;                  // lambda / B
+  // Adam: c0 = a_t, c1 = beta1, c2 = beta2, c3 = eps.  Adadelta: c0 = lr, c1 = rho, c3 = eps.
+  float c0, c1, c2, c3;
+  // loss finalisation by the last block: loss[slot] = data_acc*inv_B + reg_coeff * sum(theta^2)
+  double *acc;                     // acc[0] = data loss sum, acc[1] = sumsq
+  unsigned int *ticket;
+  float *loss_out;
+  float inv_B, reg_coeff;
+};
+int launch_adam(const OptimArgs &a, cudaStream_t st);
+int launch_adadelta(const OptimArgs &a, cudaStream_t st);
+// eval loss finalisation: loss_out = acc[0]*inv_B ; acc[0] = 0
+int launch_finalize_eval(double *acc, float *loss_out, float inv_B, cudaStream_t st);
+
+}  // namespace sert

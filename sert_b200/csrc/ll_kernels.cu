@@ -1,0 +1,195 @@
+// Row kernels of the log-linear model (sert.models.LanguageModel, sert/models.py:804-878):
+// per-word softmax statistics, ProductTimestepsLayer (sum_w log clip(p) then softmax, :186-212),
+// clipped categorical cross-entropy against CSR labels (:289-292) and the backward of all of it in
+// the general (clipped) regime.  The (B*W,E) logits Z come from the
+// word x entity projection GEMM; everything here is a streaming pass over Z / S with block-per-row
+// reductions (warp shuffles + one smem hop).
+#include "ll_kernels.cuh"
+
+namespace sert {
+
+__device__ __forceinline__ float block_max(float v, float *sm) {
+  v = warp_max(v);
+  if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = v;
+  __syncthreads();
+  float r = (threadIdx.x < (blockDim.x >> 5)) ? sm[threadIdx.x] : -INFINITY;
+  r = warp_max(r);
+  __syncthreads();
+  return r;   // valid in every thread of warp 0; broadcast below
+}
+__device__ __forceinline__ float block_sum(float v, float *sm) {
+  v = warp_sum(v);
+  if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = v;
+  __syncthreads();
+  float r = (threadIdx.x < (blockDim.x >> 5)) ? sm[threadIdx.x] : 0.f;
+  r = warp_sum(r);
+  __syncthreads();
+  return r;
+}
+__device__ __forceinline__ float block_bcast(float v, float *sm) {
+  if (threadIdx.x == 0) sm[0] = v;
+  __syncthreads();
+  const float r = sm[0];
+  __syncthreads();
+  return r;
+}
+
+// ---- per-row softmax statistics: rmax[r] = max_e Z[r,e], rsum[r] = sum_e exp(Z[r,e]-rmax[r]) ----
+__global__ void __launch_bounds__(256) ll_row_stats_kernel(const float *__restrict__ Z, long long rows,
+                                                           int E, long long ldz, float *__restrict__ rmax,
+                                                           float *__restrict__ rsum) {
+  __shared__ float sm[32];
+  for (long long r = blockIdx.x; r < rows; r += gridDim.x) {
+    const float *z = Z + r * ldz;
+    float m = -INFINITY;
+    for (int e = threadIdx.x; e < E; e += blockDim.x) m = fmaxf(m, z[e]);
+    m = block_bcast(block_max(m, sm), sm);
+    float s = 0.f;
+    for (int e = threadIdx.x; e < E; e += blockDim.x) s += expf(z[e] - m);
+    s = block_sum(s, sm);
+    if (threadIdx.x == 0) { rmax[r] = m; rsum[r] = s; }
+  }
+}
+
+int launch_ll_row_stats(const float *Z, int64_t rows, int E, int64_t ldz, float *rmax, float *rsum,
+                        cudaStream_t st) {
+  if (rows == 0) return 0;
+  const int threads = E >= 1024 ? 256 : 128;
+  ll_row_stats_kernel<<<(int)std::min<int64_t>(rows, 148 * 64), threads, 0, st>>>(Z, rows, E, ldz, rmax, rsum);
+  SERT_LAUNCH_CHECK();
+  return 0;
+}
+
+// ---- in-place row softmax (predict_fn: unclipped per-word distributions, sert/models.py:868,880-890) --
+__global__ void __launch_bounds__(256) ll_softmax_inplace_kernel(float *__restrict__ Z, long long rows, int E,
+                                                                 long long ldz, const float *__restrict__ rmax,
+                                                                 const float *__restrict__ rsum) {
+  for (long long r = blockIdx.x; r < rows; r += gridDim.x) {
+    float *z = Z + r * ldz;
+    const float m = rmax[r], s = rsum[r];
+    for (int e = threadIdx.x; e < E; e += blockDim.x) z[e] = expf(z[e] - m) / s;
+  }
+}
+
+int launch_ll_softmax_inplace(float *Z, int64_t rows, int E, int64_t ldz, const float *rmax,
+                              const float *rsum, cudaStream_t st) {
+  if (rows == 0) return 0;
+  ll_softmax_inplace_kernel<<<(int)std::min<int64_t>(rows, 148 * 64), 256, 0, st>>>(Z, rows, E, ldz, rmax, rsum);
+  SERT_LAUNCH_CHECK();
+  return 0;
+}
+
+// ---- joint logits S[i,e] = sum_w log clip(p[i,w,e]) ------------------------------------------------
+__global__ void __launch_bounds__(256) ll_joint_kernel(const float *__restrict__ Z,
+                                                       const float *__restrict__ rmax,
+                                                       const float *__restrict__ rsum, float *__restrict__ S,
+                                                       int B, int W, int E, long long ldz, long long lds) {
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  const int i = blockIdx.y;
+  if (e >= E) return;
+  float acc = 0.f;
+  for (int w = 0; w < W; ++w) {
+    const long long r = (long long)i * W + w;
+    const float p = expf(Z[r * ldz + e] - rmax[r]) / rsum[r];
+    acc += logf(clipf_(p, SERT_CLIP_LO, SERT_CLIP_HI));
+  }
+  S[(long long)i * lds + e] = acc;
+}
+
+int launch_ll_joint(const float *Z, const float *rmax, const float *rsum, float *S, int B, int W, int E,
+                    int64_t ldz, int64_t lds, cudaStream_t st) {
+  if (B == 0) return 0;
+  dim3 grid(cdiv(E, 256), B);
+  ll_joint_kernel<<<grid, 256, 0, st>>>(Z, rmax, rsum, S, B, W, E, ldz, lds);
+  SERT_LAUNCH_CHECK();
+  return 0;
+}
+
+// ---- per-instance softmax over S, CSR cross-entropy and (train) ds = dL/dS ------------------------
+__global__ void __launch_bounds__(256) ll_instance_kernel(LlInstanceArgs a) {
+  __shared__ float sm[32];
+  const int i = blockIdx.x;
+  const float *s = a.S + (long long)i * a.lds;
+  float m = -INFINITY;
+  for (int e = threadIdx.x; e < a.E; e += blockDim.x) m = fmaxf(m, s[e]);
+  m = block_bcast(block_max(m, sm), sm);
+  float sum = 0.f;
+  for (int e = threadIdx.x; e < a.E; e += blockDim.x) sum += expf(s[e] - m);
+  sum = block_bcast(block_sum(sum, sm), sm);
+
+  const long long p0 = a.indptr[i] - a.nnz_base, p1 = a.indptr[i + 1] - a.nnz_base;
+  const float wi = a.w ? a.w[i] : 1.0f;
+  const float cw = a.train ? wi * a.inv_B : 0.f;
+  float ell = 0.f, adot = 0.f;
+  for (long long p = p0 + threadIdx.x; p < p1; p += blockDim.x) {
+    const int e = a.indices[p];
+    const float y = a.data[p];
+    const float o = expf(s[e] - m) / sum;
+    const float c = clipf_(o, SERT_CLIP_LO, SERT_CLIP_HI);
+    ell -= y * logf(c);
+    if (o >= SERT_CLIP_LO && o <= SERT_CLIP_HI) adot += (-cw * y / c) * o;   // sum_e do*o
+  }
+  ell = block_sum(ell, sm);
+  adot = block_bcast(block_sum(adot, sm), sm);
+  if (threadIdx.x == 0) {
+    if (a.ell_out) a.ell_out[i] = ell;
+    atomicAdd(a.loss_acc, (double)(a.train ? wi * ell : ell));
+  }
+  if (!a.train) return;
+  // ds = o * (do - sum_e do*o); do is non-zero only on the label columns
+  float *ds = a.DS + (long long)i * a.lds;
+  for (int e = threadIdx.x; e < a.E; e += blockDim.x) ds[e] = -(expf(s[e] - m) / sum) * adot;
+  __syncthreads();
+  for (long long p = p0 + threadIdx.x; p < p1; p += blockDim.x) {
+    const int e = a.indices[p];
+    const float y = a.data[p];
+    const float o = expf(s[e] - m) / sum;
+    const float c = clipf_(o, SERT_CLIP_LO, SERT_CLIP_HI);
+    if (o >= SERT_CLIP_LO && o <= SERT_CLIP_HI) atomicAdd(ds + e, o * (-cw * y / c));
+  }
+}
+
+int launch_ll_instance(const LlInstanceArgs &a, cudaStream_t st) {
+  if (a.B == 0) return 0;
+  SERT_REQUIRE(!a.train || a.DS != nullptr, "training needs a dS buffer");
+  ll_instance_kernel<<<a.B, a.E >= 1024 ? 256 : 128, 0, st>>>(a);
+  SERT_LAUNCH_CHECK();
+  return 0;
+}
+
+// ---- dZ in place: one block per (i,w) row ---------------------------------------------------------
+__global__ void __launch_bounds__(256) ll_dz_kernel(float *__restrict__ Z, const float *__restrict__ rmax,
+                                                    const float *__restrict__ rsum,
+                                                    const float *__restrict__ DS, long long rows, int W, int E,
+                                                    long long ldz, long long lds) {
+  __shared__ float sm[32];
+  for (long long r = blockIdx.x; r < rows; r += gridDim.x) {
+    float *z = Z + r * ldz;
+    const float *ds = DS + (r / W) * lds;
+    const float m = rmax[r], s = rsum[r];
+    float acc = 0.f;
+    for (int e = threadIdx.x; e < E; e += blockDim.x) {
+      const float p = expf(z[e] - m) / s;
+      if (p >= SERT_CLIP_LO && p <= SERT_CLIP_HI) acc += ds[e];   // dp*p = ds/clip(p)*p = ds when unclipped
+    }
+    acc = block_bcast(block_sum(acc, sm), sm);
+    for (int e = threadIdx.x; e < E; e += blockDim.x) {
+      const float p = expf(z[e] - m) / s;
+      const float dpp = (p >= SERT_CLIP_LO && p <= SERT_CLIP_HI) ? ds[e] : 0.f;
+      z[e] = dpp - p * acc;
+    }
+    __syncthreads();
+  }
+}
+
+int launch_ll_dz(float *Z, const float *rmax, const float *rsum, const float *DS, int B, int W, int E,
+                 int64_t ldz, int64_t lds, cudaStream_t st) {
+  const long long rows = (long long)B * W;
+  if (rows == 0) return 0;
+  ll_dz_kernel<<<(int)std::min<long long>(rows, 148 * 64), E >= 1024 ? 256 : 128, 0, st>>>(
+      Z, rmax, rsum, DS, rows, W, E, ldz, lds);
+  SERT_LAUNCH_CHECK();
+  return 0;
+}
+
+}  // namespace sert

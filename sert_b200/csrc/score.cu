@@ -1,0 +1,387 @@
+// Entity scoring: query x all-entities inner products with a fused running top-k.
+// Replaces VectorSpaceCallback's sklearn k-NN / cdist + argsort (bin/query.py:241-318): on
+// L2-normalised vectors, Euclidean k-NN order == inner-product order, so the device returns the
+// top-k rows by inner product and the host callback re-scores them exactly like the reference.
+//
+// The (Q,E) score matrix is never materialised.  Entities are swept in chunks; the score-tile
+// kernel compares each score with its query's running threshold tau_q (the k-th best so far) and
+// appends survivors to a per-query candidate list; a prune kernel re-selects the best k whenever
+// a list is more than half full and raises tau_q.  Chunk size == half the list capacity, so a list
+// can never overflow (worst case: every score of a chunk survives) and the result is exact.
+// Keys are 64-bit (order-preserving score bits << 32 | ~row id): larger key == better score, ties
+// broken by lower row id, so selection and the final order are deterministic.
+#include "score.cuh"
+
+namespace sert {
+
+__device__ __forceinline__ unsigned int orderable(float f) {
+  const unsigned int u = __float_as_uint(f);
+  return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+__device__ __forceinline__ float unorderable(unsigned int o) {
+  const unsigned int u = (o & 0x80000000u) ? (o & 0x7fffffffu) : ~o;
+  return __uint_as_float(u);
+}
+__device__ __forceinline__ unsigned long long make_key(float score, unsigned int row) {
+  return ((unsigned long long)orderable(score) << 32) | (unsigned long long)(0xffffffffu - row);
+}
+
+// ---- row L2 normalisation (bin/query.py:270-274, 333-336) --------------------------------------
+__global__ void __launch_bounds__(256) normalise_rows_kernel(const float *__restrict__ in, float *__restrict__ out,
+                                                             long long rows, int d) {
+  const long long r = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (r >= rows) return;
+  const float *x = in + r * d;
+  float s = 0.f;
+  for (int c = lane; c < d; c += 32) s += x[c] * x[c];
+  s = sqrtf(warp_sum(s));
+  for (int c = lane; c < d; c += 32) out[r * d + c] = x[c] / s;
+}
+
+int launch_normalise_rows(const float *in, float *out, int64_t rows, int d, cudaStream_t st) {
+  if (rows == 0) return 0;
+  normalise_rows_kernel<<<cdiv(rows, 8), 256, 0, st>>>(in, out, rows, d);
+  SERT_LAUNCH_CHECK();
+  return 0;
+}
+
+// ---- score tile + threshold filter (fp32 FMA tile; the tcgen05 variant shares the epilogue) ------
+constexpr int TQ = 64, TN = 64, TK = 16;
+
+__global__ void __launch_bounds__(256) score_filter_kernel(const float *__restrict__ Qm,   // (Q,d)
+                                                           const float *__restrict__ En,   // (rows,d)
+                                                           int Q, long long n_begin, long long n_end, int d,
+                                                           long long row_offset,
+                                                           const unsigned long long *__restrict__ tau,
+                                                           int *__restrict__ count,
+                                                           unsigned long long *__restrict__ cand, int cap) {
+  __shared__ float Qs[TK][TQ + 4];
+  __shared__ float Es[TK][TN + 4];
+  const int tid = threadIdx.x;
+  const int q0 = blockIdx.y * TQ;
+  const long long n0 = n_begin + (long long)blockIdx.x * TN;
+  const int tx = tid & 15, ty = tid >> 4;
+  float acc[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+  for (int k0 = 0; k0 < d; k0 += TK) {
+#pragma unroll
+    for (int l = 0; l < (TQ * TK) / 256; ++l) {
+      const int e = tid + l * 256;
+      const int k = e % TK, m = e / TK;
+      const int gq = q0 + m, gk = k0 + k;
+      Qs[k][m] = (gq < Q && gk < d) ? Qm[(size_t)gq * d + gk] : 0.f;
+    }
+#pragma unroll
+    for (int l = 0; l < (TN * TK) / 256; ++l) {
+      const int e = tid + l * 256;
+      const int k = e % TK, n = e / TK;
+      const long long gn = n0 + n;
+      const int gk = k0 + k;
+      Es[k][n] = (gn < n_end && gk < d) ? En[(size_t)gn * d + gk] : 0.f;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < TK; ++k) {
+      const float4 av = *reinterpret_cast<const float4 *>(&Qs[k][ty * 4]);
+      const float4 bv = *reinterpret_cast<const float4 *>(&Es[k][tx * 4]);
+      const float a_[4] = {av.x, av.y, av.z, av.w};
+      const float b_[4] = {bv.x, bv.y, bv.z, bv.w};
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a_[i], b_[j], acc[i][j]);
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int gq = q0 + ty * 4 + i;
+    if (gq >= Q) continue;
+    const unsigned long long t = tau[gq];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const long long gn = n0 + tx * 4 + j;
+      if (gn >= n_end) continue;
+      const unsigned long long key = make_key(acc[i][j], (unsigned int)(gn + row_offset));
+      if (key > t) {
+        const int pos = atomicAdd(count + gq, 1);
+        if (pos < cap) cand[(size_t)gq * cap + pos] = key;
+      }
+    }
+  }
+}
+
+// ---- block-wide bitonic sort (descending) of n_pow2 keys in shared memory -------------------------
+__device__ void bitonic_sort_desc(unsigned long long *keys, int n_pow2) {
+  for (int size = 2; size <= n_pow2; size <<= 1) {
+    for (int stride = size >> 1; stride > 0; stride >>= 1) {
+      __syncthreads();
+      for (int t = threadIdx.x; t < (n_pow2 >> 1); t += blockDim.x) {
+        const int lo = 2 * t - (t & (stride - 1));
+        const int hi = lo + stride;
+        const bool desc = ((lo & size) == 0);
+        const unsigned long long a = keys[lo], b = keys[hi];
+        if ((a < b) == desc) { keys[lo] = b; keys[hi] = a; }
+      }
+    }
+  }
+  __syncthreads();
+}
+
+// Re-selects the best k candidates of every query whose list is more than half full (or of every
+// query when `final`), raises tau, and on `final` writes the sorted (row id, score) outputs.
+__global__ void __launch_bounds__(256) prune_kernel(unsigned long long *__restrict__ cand, int *__restrict__ count,
+                                                    unsigned long long *__restrict__ tau, int cap, int k, int final,
+                                                    int32_t *__restrict__ out_idx, float *__restrict__ out_score) {
+  extern __shared__ unsigned long long keys[];
+  const int q = blockIdx.x;
+  const int n = min(count[q], cap);
+  if (!final && n <= cap / 2) return;
+  int n_pow2 = 1;
+  while (n_pow2 < n) n_pow2 <<= 1;
+  if (n_pow2 < 2) n_pow2 = 2;
+  unsigned long long *mine = cand + (size_t)q * cap;
+  for (int i = threadIdx.x; i < n_pow2; i += blockDim.x) keys[i] = (i < n) ? mine[i] : 0ull;
+  bitonic_sort_desc(keys, n_pow2);
+  const int keep = min(n, k);
+  for (int i = threadIdx.x; i < keep; i += blockDim.x) mine[i] = keys[i];
+  if (threadIdx.x == 0) {
+    count[q] = keep;
+    if (keep == k) tau[q] = keys[k - 1];
+  }
+  if (final) {
+    for (int i = threadIdx.x; i < k; i += blockDim.x) {
+      if (i < keep) {
+        out_idx[(size_t)q * k + i] = (int32_t)(0xffffffffu - (unsigned int)(keys[i] & 0xffffffffull));
+        out_score[(size_t)q * k + i] = unorderable((unsigned int)(keys[i] >> 32));
+      } else {                               // fewer than k rows in the shard
+        out_idx[(size_t)q * k + i] = -1;
+        out_score[(size_t)q * k + i] = -INFINITY;
+      }
+    }
+  }
+}
+
+__global__ void reset_topk_state_kernel(unsigned long long *tau, int *count, int Q) {
+  const int q = blockIdx.x * blockDim.x + threadIdx.x;
+  if (q < Q) { tau[q] = 0ull; count[q] = 0; }
+}
+
+int topk_sweep(const TopkState &s, const float *queries_dev, int Q, int k, int32_t *out_idx, float *out_score,
+               cudaStream_t st) {
+  SERT_REQUIRE(k >= 1 && k <= s.cap / 2, "k exceeds the scorer's max_k");
+  SERT_REQUIRE(Q >= 0 && Q <= s.max_queries, "more queries than the scorer's max_queries");
+  if (Q == 0) return 0;
+  reset_topk_state_kernel<<<cdiv(Q, 256), 256, 0, st>>>(s.tau, s.count, Q);
+  SERT_LAUNCH_CHECK();
+  const long long chunk = s.cap / 2;
+  const size_t smem = (size_t)s.cap * sizeof(unsigned long long);
+  for (long long n0 = 0; n0 < s.rows; n0 += chunk) {
+    const long long n1 = std::min<long long>(s.rows, n0 + chunk);
+    dim3 grid(cdiv(n1 - n0, TN), cdiv(Q, TQ));
+    score_filter_kernel<<<grid, 256, 0, st>>>(queries_dev, s.entities, Q, n0, n1, s.d, s.row_begin, s.tau, s.count,
+                                              s.cand, s.cap);
+    SERT_LAUNCH_CHECK();
+    const bool last = (n1 == s.rows);
+    prune_kernel<<<Q, 256, smem, st>>>(s.cand, s.count, s.tau, s.cap, k, last ? 1 : 0, out_idx, out_score);
+    SERT_LAUNCH_CHECK();
+  }
+  if (s.rows == 0) {
+    prune_kernel<<<Q, 256, smem, st>>>(s.cand, s.count, s.tau, s.cap, k, 1, out_idx, out_score);
+    SERT_LAUNCH_CHECK();
+  }
+  return 0;
+}
+
+int topk_prepare(int cap) {
+  static int configured = 0;
+  const int smem = cap * (int)sizeof(unsigned long long);
+  if (smem > configured) {
+    SERT_CUDA(cudaFuncSetAttribute(prune_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    configured = smem;
+  }
+  return 0;
+}
+
+// ---- merge of gathered per-shard lists: [parts][q][k] -> (q,k) ------------------------------------
+__global__ void __launch_bounds__(256) merge_kernel(const int32_t *__restrict__ idx, const float *__restrict__ score,
+                                                    int parts, int Q, int k, int32_t *__restrict__ out_idx,
+                                                    float *__restrict__ out_score, int n_pow2) {
+  extern __shared__ unsigned long long keys[];
+  const int q = blockIdx.x;
+  const int n = parts * k;
+  for (int i = threadIdx.x; i < n_pow2; i += blockDim.x) {
+    unsigned long long key = 0ull;
+    if (i < n) {
+      const int p = i / k, j = i % k;
+      const size_t src = ((size_t)p * Q + q) * k + j;
+      const int32_t id = idx[src];
+      if (id >= 0) key = make_key(score[src], (unsigned int)id);
+    }
+    keys[i] = key;
+  }
+  bitonic_sort_desc(keys, n_pow2);
+  for (int i = threadIdx.x; i < k; i += blockDim.x) {
+    const unsigned long long key = keys[i];
+    if (key != 0ull) {
+      out_idx[(size_t)q * k + i] = (int32_t)(0xffffffffu - (unsigned int)(key & 0xffffffffull));
+      out_score[(size_t)q * k + i] = unorderable((unsigned int)(key >> 32));
+    } else {
+      out_idx[(size_t)q * k + i] = -1;
+      out_score[(size_t)q * k + i] = -INFINITY;
+    }
+  }
+}
+
+int launch_topk_merge(const int32_t *idx, const float *score, int parts, int Q, int k, int32_t *out_idx,
+                      float *out_score, cudaStream_t st) {
+  SERT_REQUIRE(parts >= 1 && k >= 1, "bad merge shape");
+  if (Q == 0) return 0;
+  int n_pow2 = 2;
+  while (n_pow2 < parts * k) n_pow2 <<= 1;
+  const size_t smem = (size_t)n_pow2 * sizeof(unsigned long long);
+  SERT_REQUIRE(smem <= 200 * 1024, "merge fan-in too large");
+  static size_t configured = 0;
+  if (smem > configured) {
+    SERT_CUDA(cudaFuncSetAttribute(merge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    configured = smem;
+  }
+  merge_kernel<<<Q, 256, smem, st>>>(idx, score, parts, Q, k, out_idx, out_score, n_pow2);
+  SERT_LAUNCH_CHECK();
+  return 0;
+}
+
+}  // namespace sert
+
+// =================================================================================================
+using namespace sert;
+
+struct sert_scorer {
+  TopkState s;
+  cudaStream_t st = nullptr;
+  float *queries = nullptr;     // (max_queries, d) staging / normalised queries
+  int32_t *out_idx = nullptr;   // (max_queries, max_k)
+  float *out_score = nullptr;
+  int max_k = 0;
+};
+
+namespace sert {
+static size_t carve_scorer(sert_scorer &sc, void *base, int64_t rows, int d, int max_queries, int max_k) {
+  char *b = static_cast<char *>(base);
+  size_t off = 0;
+  auto take = [&](size_t bytes) {
+    off = align_up(off, 256);
+    char *p = b ? b + off : nullptr;
+    off += bytes;
+    return p;
+  };
+  int cap = 4096;
+  while (cap / 2 < max_k) cap <<= 1;
+  sc.s.cap = cap;
+  sc.s.rows = rows;
+  sc.s.d = d;
+  sc.s.max_queries = max_queries;
+  sc.max_k = max_k;
+  sc.s.entities = reinterpret_cast<float *>(take((size_t)rows * d * sizeof(float)));
+  sc.s.cand = reinterpret_cast<unsigned long long *>(take((size_t)max_queries * cap * sizeof(unsigned long long)));
+  sc.s.tau = reinterpret_cast<unsigned long long *>(take((size_t)max_queries * sizeof(unsigned long long)));
+  sc.s.count = reinterpret_cast<int *>(take((size_t)max_queries * sizeof(int)));
+  sc.queries = reinterpret_cast<float *>(take((size_t)max_queries * d * sizeof(float)));
+  sc.out_idx = reinterpret_cast<int32_t *>(take((size_t)max_queries * max_k * sizeof(int32_t)));
+  sc.out_score = reinterpret_cast<float *>(take((size_t)max_queries * max_k * sizeof(float)));
+  return align_up(off, 256);
+}
+}  // namespace sert
+
+extern "C" {
+
+int sert_scorer_arena_bytes(int64_t rows, int32_t d, int32_t max_queries, int32_t max_k, size_t *bytes) {
+  SERT_REQUIRE(bytes, "null argument");
+  SERT_REQUIRE(rows >= 0 && d > 0 && max_queries > 0 && max_k > 0, "bad scorer shape");
+  SERT_REQUIRE(max_k <= 8192, "max_k above 8192 is not supported");
+  sert_scorer tmp;
+  *bytes = carve_scorer(tmp, nullptr, rows, d, max_queries, max_k);
+  return 0;
+}
+
+int sert_scorer_create(const float *entities_host, int64_t rows, int32_t d, int64_t row_begin, int32_t normalise,
+                       int32_t max_queries, int32_t max_k, void *arena_dev, size_t arena_bytes, void *stream,
+                       sert_scorer **out) {
+  SERT_REQUIRE(out && arena_dev && (entities_host || rows == 0), "null argument");
+  SERT_REQUIRE(rows >= 0 && d > 0 && max_queries > 0 && max_k > 0 && max_k <= 8192, "bad scorer shape");
+  SERT_REQUIRE(row_begin >= 0 && row_begin + rows < (1ll << 31), "row ids must fit in int32");
+  int ndev = 0;
+  SERT_CUDA(cudaGetDeviceCount(&ndev));
+  SERT_REQUIRE(ndev > 0, "no CUDA device: libsert_b200 has no CPU fallback");
+  sert_scorer *sc = new sert_scorer();
+  const size_t need = carve_scorer(*sc, arena_dev, rows, d, max_queries, max_k);
+  if (need > arena_bytes) {
+    delete sc;
+    set_error("scorer arena too small: need " + std::to_string(need) + " bytes");
+    return -1;
+  }
+  sc->st = static_cast<cudaStream_t>(stream);
+  sc->s.row_begin = row_begin;
+  if (topk_prepare(sc->s.cap)) { delete sc; return -1; }
+  if (rows > 0) {
+    cudaError_t e = cudaMemcpyAsync(sc->s.entities, entities_host, (size_t)rows * d * sizeof(float),
+                                    cudaMemcpyHostToDevice, sc->st);
+    if (e != cudaSuccess) { delete sc; set_error(cudaGetErrorString(e)); return -1; }
+    if (normalise && launch_normalise_rows(sc->s.entities, sc->s.entities, rows, d, sc->st)) { delete sc; return -1; }
+  }
+  cudaError_t e = cudaStreamSynchronize(sc->st);
+  if (e != cudaSuccess) { delete sc; set_error(cudaGetErrorString(e)); return -1; }
+  *out = sc;
+  return 0;
+}
+
+int sert_scorer_destroy(sert_scorer *s) {
+  if (s) {
+    cudaStreamSynchronize(s->st);
+    delete s;
+  }
+  return 0;
+}
+
+int sert_scorer_topk_dev(sert_scorer *s, const float *queries_dev, int32_t q, int32_t normalise_q, int32_t k,
+                         int32_t *out_idx_dev, float *out_score_dev) {
+  SERT_REQUIRE(s && (queries_dev || q == 0) && out_idx_dev && out_score_dev, "null argument");
+  SERT_REQUIRE(q <= s->s.max_queries, "more queries than the scorer's max_queries");
+  SERT_REQUIRE(k >= 1 && k <= s->max_k, "k exceeds the scorer's max_k");
+  const float *qq = queries_dev;
+  if (normalise_q) {
+    if (launch_normalise_rows(queries_dev, s->queries, q, s->s.d, s->st)) return -1;
+    qq = s->queries;
+  }
+  return topk_sweep(s->s, qq, q, k, out_idx_dev, out_score_dev, s->st);
+}
+
+int sert_scorer_topk_host(sert_scorer *s, const float *queries_host, int32_t q, int32_t normalise_q, int32_t k,
+                          int32_t *out_idx_host, float *out_score_host) {
+  SERT_REQUIRE(s && (queries_host || q == 0) && out_idx_host && out_score_host, "null argument");
+  SERT_REQUIRE(q <= s->s.max_queries, "more queries than the scorer's max_queries");
+  SERT_REQUIRE(k >= 1 && k <= s->max_k, "k exceeds the scorer's max_k");
+  if (q == 0) return 0;
+  SERT_CUDA(cudaMemcpyAsync(s->queries, queries_host, (size_t)q * s->s.d * sizeof(float), cudaMemcpyHostToDevice,
+                            s->st));
+  if (normalise_q && launch_normalise_rows(s->queries, s->queries, q, s->s.d, s->st)) return -1;
+  if (topk_sweep(s->s, s->queries, q, k, s->out_idx, s->out_score, s->st)) return -1;
+  SERT_CUDA(cudaMemcpyAsync(out_idx_host, s->out_idx, (size_t)q * k * sizeof(int32_t), cudaMemcpyDeviceToHost, s->st));
+  SERT_CUDA(cudaMemcpyAsync(out_score_host, s->out_score, (size_t)q * k * sizeof(float), cudaMemcpyDeviceToHost,
+                            s->st));
+  SERT_CUDA(cudaStreamSynchronize(s->st));
+  return 0;
+}
+
+int sert_topk_merge_dev(const int32_t *idx_dev, const float *score_dev, int32_t parts, int32_t q, int32_t k,
+                        int32_t *out_idx_dev, float *out_score_dev, void *stream) {
+  SERT_REQUIRE(idx_dev && score_dev && out_idx_dev && out_score_dev, "null argument");
+  return launch_topk_merge(idx_dev, score_dev, parts, q, k, out_idx_dev, out_score_dev,
+                           static_cast<cudaStream_t>(stream));
+}
+
+}  // extern "C"

@@ -1,0 +1,652 @@
+// extern "C" surface of libsert_b200.so: model life cycle, device-resident data set, the
+// train / eval / predict sequences of both models.  See include/sert_b200.h for the contract and the
+// reference interfaces each entry point replaces.
+#include <math.h>
+#include <string.h>
+
+#include <atomic>
+#include <vector>
+
+#include "kernels.cuh"
+#include "ll_kernels.cuh"
+
+namespace sert {
+
+static thread_local std::string g_error;
+static std::atomic<uint64_t> g_launches{0};
+void set_error(const std::string &msg) { g_error = msg; }
+void count_launch(uint64_t n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+
+// ---- bump allocator over the caller-provided HBM arena ------------------------------------------
+struct Bump {
+  char *base;
+  size_t off = 0;
+  explicit Bump(void *b) : base(static_cast<char *>(b)) {}
+  template <typename T>
+  T *take(size_t count) {
+    off = align_up(off, 256);
+    T *p = base ? reinterpret_cast<T *>(base + off) : nullptr;
+    off += count * sizeof(T);
+    return p;
+  }
+};
+
+struct Dataset {
+  int64_t n = 0;
+  const int32_t *x = nullptr;
+  const int32_t *y = nullptr;
+  const int64_t *indptr = nullptr;
+  const int32_t *indices = nullptr;
+  const float *data = nullptr;
+  const float *w = nullptr;
+};
+
+}  // namespace sert
+
+using namespace sert;
+
+struct sert_model {
+  sert_config cfg;
+  cudaStream_t st = nullptr;
+  char *arena = nullptr;
+  size_t arena_bytes = 0;
+  // parameter arena: theta / state1 / state2 / grad share one layout
+  float *theta = nullptr, *s1 = nullptr, *s2 = nullptr, *grad = nullptr;
+  long long total = 0;
+  long long off[4] = {0, 0, 0, 0};    // by SERT_PARAM_*: float offset
+  long long cnt[4] = {0, 0, 0, 0};    // logical float count (0 = tensor absent)
+  ParamSegment seg[kMaxSegments];
+  int nseg = 0;
+  uint32_t *flagR = nullptr, *flagE = nullptr;
+  uint32_t stamp = 0;
+  int64_t step = 0;                   // Adam's t
+  uint64_t sample_calls = 0;
+  double *acc = nullptr;
+  unsigned int *ticket = nullptr;
+  float *losses = nullptr;
+  Dataset ds[2];
+  // vector-space workspaces
+  float *h = nullptr, *t = nullptr, *da = nullptr, *dh = nullptr;
+  int32_t *neg = nullptr;
+  float *dbg_scores = nullptr, *dbg_u = nullptr, *dbg_ell = nullptr;
+  // log-linear workspaces
+  float *X = nullptr, *Z = nullptr, *S = nullptr, *DS = nullptr, *dX = nullptr, *rmax = nullptr, *rsum = nullptr;
+  // host-batch staging
+  int32_t *stage_x = nullptr, *stage_y = nullptr, *stage_neg = nullptr, *stage_indices = nullptr;
+  int64_t *stage_indptr = nullptr;
+  float *stage_w = nullptr, *stage_data = nullptr, *stage_f = nullptr;
+  size_t stage_nnz_cap = 0;
+};
+
+namespace sert {
+
+static bool is_vs(const sert_config &c) { return c.kind == SERT_KIND_VECTORSPACE; }
+
+static int validate(const sert_config &c) {
+  SERT_REQUIRE(c.kind == SERT_KIND_LOGLINEAR || c.kind == SERT_KIND_VECTORSPACE, "unknown model kind");
+  SERT_REQUIRE(c.batch > 0, "batch_size must be positive");                     // sert/models.py:315
+  SERT_REQUIRE(c.window >= 1, "window_size must be >= 1");                      // sert/models.py:696
+  SERT_REQUIRE(c.vocab > 0 && c.vocab < (1ll << 31), "vocabulary size out of range");
+  SERT_REQUIRE(c.entities > 1 && c.entities < (1ll << 31), "number of entities out of range");  // bin/train.py:100
+  SERT_REQUIRE(c.word_dim > 0 && c.word_dim % 4 == 0, "word representation size must be a positive multiple of 4");
+  SERT_REQUIRE(c.loss_slots > 0, "loss_slots must be positive");
+  SERT_REQUIRE(c.lambda >= 0.f, "regularization lambda must be >= 0");
+  if (is_vs(c)) {
+    SERT_REQUIRE(c.entity_dim > 0 && c.entity_dim % 4 == 0,
+                 "entity representation size must be a positive multiple of 4");
+    SERT_REQUIRE(c.num_negatives >= 1, "num_negative_samples must be positive");  // sert/models.py:948
+  }
+  SERT_REQUIRE((long long)c.vocab * c.word_dim < (1ll << 32), "word table above 2^32 elements");
+  SERT_REQUIRE((long long)c.entities * (is_vs(c) ? c.entity_dim : c.word_dim) < (1ll << 32),
+               "entity table above 2^32 elements");
+  return 0;
+}
+
+// Lays the model out in the arena (base == nullptr: size query only).
+static size_t carve(sert_model &m, void *base) {
+  const sert_config &c = m.cfg;
+  Bump b(base);
+  const long long B = c.batch, W = c.window, V = c.vocab, E = c.entities, dw = c.word_dim;
+  const long long de = is_vs(c) ? c.entity_dim : 0;
+  // ---- parameter layout: the optimiser's parameter order, sert/models.py:542-543,1105 ----
+  long long o = 0;
+  m.nseg = 0;
+  auto add = [&](int which, long long count, int row_len, int regularised) {
+    m.off[which] = o;
+    m.cnt[which] = count;
+    ParamSegment &s = m.seg[m.nseg++];
+    s.offset = o;
+    s.count = (long long)align_up((size_t)count, 4);
+    s.row_len = row_len;
+    s.regularised = regularised;
+    s.flags = nullptr;
+    o += (long long)align_up((size_t)count, 64);   // 256-byte aligned tensors
+  };
+  if (is_vs(c)) {
+    add(SERT_PARAM_ENTITY_REPR, E * de, (int)de, 1);
+    add(SERT_PARAM_WORD_REPR, V * dw, (int)dw, 1);
+    add(SERT_PARAM_DENSE_W, dw * de, (int)de, 1);
+    add(SERT_PARAM_DENSE_B, de, (int)de, 0);
+  } else {
+    add(SERT_PARAM_WORD_REPR, V * dw, (int)dw, 1);
+    add(SERT_PARAM_DENSE_W, dw * E, (int)E, 1);
+    add(SERT_PARAM_DENSE_B, E, (int)E, 0);
+  }
+  m.total = o;
+  m.theta = b.take<float>(o);
+  m.s1 = b.take<float>(o);
+  m.s2 = b.take<float>(o);
+  m.grad = b.take<float>(o);
+  m.flagR = b.take<uint32_t>(V);
+  m.flagE = is_vs(c) ? b.take<uint32_t>(E) : nullptr;
+  m.acc = b.take<double>(4);
+  m.ticket = b.take<unsigned int>(4);
+  m.losses = b.take<float>(c.loss_slots + 1);   // last slot: scratch for parity hooks
+  if (is_vs(c)) {
+    const long long k = c.num_negatives;
+    m.h = b.take<float>(B * dw);
+    m.t = b.take<float>(B * de);
+    m.da = b.take<float>(B * de);
+    m.dh = b.take<float>(B * dw);
+    m.neg = b.take<int32_t>(B * k);
+    m.dbg_scores = b.take<float>(B * (k + 1));
+    m.dbg_u = b.take<float>(B * de);
+    m.dbg_ell = b.take<float>(B);
+    m.stage_neg = b.take<int32_t>(B * k);
+    m.stage_y = b.take<int32_t>(B);
+    m.stage_f = b.take<float>(B * std::max(dw, de));
+  } else {
+    m.X = b.take<float>(B * W * dw);
+    m.Z = b.take<float>(B * W * E);
+    m.S = b.take<float>(B * E);
+    m.DS = b.take<float>(B * E);
+    m.dX = b.take<float>(B * W * dw);
+    m.rmax = b.take<float>(B * W);
+    m.rsum = b.take<float>(B * W);
+    m.dbg_ell = b.take<float>(B);
+    m.stage_indptr = b.take<int64_t>(B + 1);
+    m.stage_nnz_cap = (size_t)B * 64;            // host-streamed batches: up to 64 labels per row on average
+    m.stage_indices = b.take<int32_t>(m.stage_nnz_cap);
+    m.stage_data = b.take<float>(m.stage_nnz_cap);
+  }
+  m.stage_x = b.take<int32_t>(B * W);
+  m.stage_w = b.take<float>(B);
+  // flags are looked up through the segment table
+  for (int s = 0; s < m.nseg; ++s) {
+    if (m.seg[s].offset == m.off[SERT_PARAM_WORD_REPR]) m.seg[s].flags = m.flagR;
+    if (is_vs(c) && m.seg[s].offset == m.off[SERT_PARAM_ENTITY_REPR]) m.seg[s].flags = m.flagE;
+  }
+  return align_up(b.off, 256);
+}
+
+static float adam_alpha_f32(int64_t t) {
+  // a_t = lr*sqrt(1-beta2^t)/(1-beta1^t) evaluated in float32 (t is a floatX scalar in the graph)
+  const float tf = (float)t;
+  const float b1 = 0.9f, b2 = 0.999f, lr = 1e-3f;
+  return lr * sqrtf(1.0f - powf(b2, tf)) / (1.0f - powf(b1, tf));
+}
+
+static OptimArgs optim_args(sert_model &m, float *loss_out) {
+  OptimArgs a;
+  a.theta = m.theta; a.s1 = m.s1; a.s2 = m.s2; a.grad = m.grad;
+  a.total = m.total;
+  for (int s = 0; s < m.nseg; ++s) a.seg[s] = m.seg[s];
+  for (int s = m.nseg; s < kMaxSegments; ++s) a.seg[s] = ParamSegment{0, 0, 1, 0, nullptr};
+  a.num_segments = m.nseg;
+  a.stamp = m.stamp;
+  const float B = (float)m.cfg.batch;
+  a.l2_scale = m.cfg.lambda > 0.f ? m.cfg.lambda / B : 0.f;
+  a.acc = m.acc; a.ticket = m.ticket; a.loss_out = loss_out;
+  a.inv_B = 1.0f / B;
+  a.reg_coeff = m.cfg.lambda > 0.f ? m.cfg.lambda / (2.0f * B) : 0.f;
+  return a;
+}
+
+static int pick_split_k(int M, int N, int K) {
+  const long long tiles = (long long)cdiv(M, 64) * cdiv(N, 64);
+  long long want = (2ll * kNumSMs + tiles - 1) / tiles;
+  const long long max_split = std::max(1, K / 64);
+  if (want > max_split) want = max_split;
+  if (want < 1) want = 1;
+  return (int)want;
+}
+
+// ---- vector space: one training step on device-resident batch pointers --------------------------
+static int vs_forward(sert_model &m, const int32_t *x, cudaStream_t st) {
+  const sert_config &c = m.cfg;
+  float *R = m.theta + m.off[SERT_PARAM_WORD_REPR];
+  float *Wp = m.theta + m.off[SERT_PARAM_DENSE_W];
+  float *bp = m.theta + m.off[SERT_PARAM_DENSE_B];
+  if (launch_gather_pool(x, R, m.h, c.batch, c.window, c.word_dim, (float)c.window, st)) return -1;
+  return launch_gemm_f32(m.h, Wp, m.t, c.batch, c.entity_dim, c.word_dim, false, false, c.word_dim,
+                         c.entity_dim, c.entity_dim, EPI_BIAS_TANH, bp, 1, st);
+}
+
+static int vs_train_step(sert_model &m, const int32_t *x, const int32_t *y, const float *w,
+                         const int32_t *neg, float *loss_out) {
+  const sert_config &c = m.cfg;
+  cudaStream_t st = m.st;
+  const int B = c.batch, dw = c.word_dim, de = c.entity_dim;
+  float *Wp = m.theta + m.off[SERT_PARAM_DENSE_W];
+  m.stamp += 1;
+  if (neg == nullptr) {
+    if (launch_sample_negatives(m.neg, (int64_t)B * c.num_negatives, c.entities, c.seed, m.sample_calls++, st))
+      return -1;
+    neg = m.neg;
+  }
+  if (vs_forward(m, x, st)) return -1;
+  VsNceArgs a;
+  a.t = m.t; a.Eemb = m.theta + m.off[SERT_PARAM_ENTITY_REPR]; a.y = y; a.neg = neg; a.w = w;
+  a.gE = m.grad + m.off[SERT_PARAM_ENTITY_REPR]; a.flagE = m.flagE; a.stamp = m.stamp; a.da = m.da;
+  a.loss_acc = m.acc; a.dbg_scores = nullptr; a.dbg_u = nullptr; a.dbg_ell = nullptr;
+  a.B = B; a.k = c.num_negatives; a.de = de; a.inv_B = 1.0f / (float)B; a.train = true;
+  if (launch_vs_nce(a, st)) return -1;
+  // dh = da . Wp^T
+  if (launch_gemm_f32(m.da, Wp, m.dh, B, dw, de, false, true, de, de, dw, EPI_STORE, nullptr, 1, st)) return -1;
+  // gWp += h^T . da   (split-K over the batch)
+  if (launch_gemm_f32(m.h, m.da, m.grad + m.off[SERT_PARAM_DENSE_W], dw, de, B, true, false, dw, de, de,
+                      EPI_ATOMIC_ADD, nullptr, pick_split_k(dw, de, B), st))
+    return -1;
+  if (launch_colsum_atomic(m.da, m.grad + m.off[SERT_PARAM_DENSE_B], B, de, st)) return -1;
+  if (launch_scatter_rows(x, m.dh, m.grad + m.off[SERT_PARAM_WORD_REPR], m.flagR, m.stamp, B, c.window, dw,
+                          (float)c.window, st))
+    return -1;
+  m.step += 1;
+  OptimArgs o = optim_args(m, loss_out);
+  o.c0 = adam_alpha_f32(m.step); o.c1 = 0.9f; o.c2 = 0.999f; o.c3 = 1e-8f;
+  return launch_adam(o, st);
+}
+
+static int vs_eval_step(sert_model &m, const int32_t *x, const int32_t *y, const int32_t *neg,
+                        float *loss_out, bool debug) {
+  const sert_config &c = m.cfg;
+  cudaStream_t st = m.st;
+  if (neg == nullptr) {
+    // the eval loss draws its own negatives (loss_fn is instantiated twice, sert/models.py:745-752)
+    if (launch_sample_negatives(m.neg, (int64_t)c.batch * c.num_negatives, c.entities, c.seed,
+                                m.sample_calls++, st))
+      return -1;
+    neg = m.neg;
+  }
+  if (vs_forward(m, x, st)) return -1;
+  VsNceArgs a;
+  a.t = m.t; a.Eemb = m.theta + m.off[SERT_PARAM_ENTITY_REPR]; a.y = y; a.neg = neg; a.w = nullptr;
+  a.gE = nullptr; a.flagE = nullptr; a.stamp = 0; a.da = nullptr; a.loss_acc = m.acc;
+  a.dbg_scores = debug ? m.dbg_scores : nullptr; a.dbg_u = debug ? m.dbg_u : nullptr;
+  a.dbg_ell = debug ? m.dbg_ell : nullptr;
+  a.B = c.batch; a.k = c.num_negatives; a.de = c.entity_dim; a.inv_B = 1.0f / (float)c.batch; a.train = false;
+  if (launch_vs_nce(a, st)) return -1;
+  return launch_finalize_eval(m.acc, loss_out, 1.0f / (float)c.batch, st);
+}
+
+// ---- log-linear ---------------------------------------------------------------------------------
+static int ll_forward(sert_model &m, const int32_t *x, int rows /* instances */, cudaStream_t st) {
+  const sert_config &c = m.cfg;
+  const int E = (int)c.entities, dw = c.word_dim;
+  const long long BW = (long long)rows * c.window;
+  float *R = m.theta + m.off[SERT_PARAM_WORD_REPR];
+  float *Wd = m.theta + m.off[SERT_PARAM_DENSE_W];
+  float *bd = m.theta + m.off[SERT_PARAM_DENSE_B];
+  if (launch_gather_rows(x, R, m.X, BW, dw, st)) return -1;
+  if (launch_gemm_f32(m.X, Wd, m.Z, (int)BW, E, dw, false, false, dw, E, E, EPI_BIAS, bd, 1, st)) return -1;
+  return launch_ll_row_stats(m.Z, BW, E, E, m.rmax, m.rsum, st);
+}
+
+static LlInstanceArgs ll_instance_args(sert_model &m, const int64_t *indptr, long long nnz_base,
+                                       const int32_t *indices, const float *data, const float *w, bool train,
+                                       float *ell_out) {
+  LlInstanceArgs a;
+  a.S = m.S; a.DS = train ? m.DS : nullptr; a.lds = m.cfg.entities; a.B = m.cfg.batch; a.E = (int)m.cfg.entities;
+  a.indptr = reinterpret_cast<const long long *>(indptr); a.nnz_base = nnz_base; a.indices = indices;
+  a.data = data; a.w = w; a.inv_B = 1.0f / (float)m.cfg.batch; a.ell_out = ell_out; a.loss_acc = m.acc;
+  a.train = train;
+  return a;
+}
+
+static int ll_train_step(sert_model &m, const int32_t *x, const int64_t *indptr, long long nnz_base,
+                         const int32_t *indices, const float *data, const float *w, float *loss_out) {
+  const sert_config &c = m.cfg;
+  cudaStream_t st = m.st;
+  const int B = c.batch, W = c.window, E = (int)c.entities, dw = c.word_dim;
+  const int BW = B * W;
+  float *Wd = m.theta + m.off[SERT_PARAM_DENSE_W];
+  m.stamp += 1;
+  if (ll_forward(m, x, B, st)) return -1;
+  if (launch_ll_joint(m.Z, m.rmax, m.rsum, m.S, B, W, E, E, E, st)) return -1;
+  if (launch_ll_instance(ll_instance_args(m, indptr, nnz_base, indices, data, w, true, nullptr), st)) return -1;
+  if (launch_ll_dz(m.Z, m.rmax, m.rsum, m.DS, B, W, E, E, E, st)) return -1;
+  // gWd += X^T . dZ ; gbd += colsum(dZ) ; dX = dZ . Wd^T
+  if (launch_gemm_f32(m.X, m.Z, m.grad + m.off[SERT_PARAM_DENSE_W], dw, E, BW, true, false, dw, E, E,
+                      EPI_ATOMIC_ADD, nullptr, pick_split_k(dw, E, BW), st))
+    return -1;
+  if (launch_colsum_atomic(m.Z, m.grad + m.off[SERT_PARAM_DENSE_B], BW, E, st)) return -1;
+  if (launch_gemm_f32(m.Z, Wd, m.dX, BW, dw, E, false, true, E, E, dw, EPI_STORE, nullptr, 1, st)) return -1;
+  if (launch_scatter_rows(x, m.dX, m.grad + m.off[SERT_PARAM_WORD_REPR], m.flagR, m.stamp, BW, 1, dw, 1.0f, st))
+    return -1;
+  m.step += 1;
+  OptimArgs o = optim_args(m, loss_out);
+  o.c0 = 1.0f; o.c1 = 0.95f; o.c2 = 0.f; o.c3 = 1e-6f;   // lasagne.updates.adadelta defaults
+  return launch_adadelta(o, st);
+}
+
+static int ll_eval_step(sert_model &m, const int32_t *x, const int64_t *indptr, long long nnz_base,
+                        const int32_t *indices, const float *data, float *loss_out, bool debug) {
+  const sert_config &c = m.cfg;
+  cudaStream_t st = m.st;
+  const int B = c.batch, W = c.window, E = (int)c.entities;
+  if (ll_forward(m, x, B, st)) return -1;
+  if (launch_ll_joint(m.Z, m.rmax, m.rsum, m.S, B, W, E, E, E, st)) return -1;
+  if (launch_ll_instance(ll_instance_args(m, indptr, nnz_base, indices, data, nullptr, false,
+                                          debug ? m.dbg_ell : nullptr), st))
+    return -1;
+  return launch_finalize_eval(m.acc, loss_out, 1.0f / (float)B, st);
+}
+
+static int check_batch(sert_model *m, int split, int64_t b) {
+  SERT_REQUIRE(split == SERT_SPLIT_TRAIN || split == SERT_SPLIT_VALIDATE, "unknown split");
+  const Dataset &d = m->ds[split];
+  SERT_REQUIRE(d.x != nullptr, "no data set attached for this split");
+  SERT_REQUIRE(b >= 0 && (b + 1) * (int64_t)m->cfg.batch <= d.n,
+               "batch index out of range (incomplete batches are ignored, sert/models.py:355-359)");
+  return 0;
+}
+
+}  // namespace sert
+
+// =================================================================================================
+// extern "C"
+// =================================================================================================
+extern "C" {
+
+int sert_abi_version(void) { return SERT_ABI_VERSION; }
+const char *sert_last_error(void) { return g_error.c_str(); }
+uint64_t sert_launch_count(void) { return g_launches.load(); }
+
+int sert_model_arena_bytes(const sert_config *cfg, size_t *bytes) {
+  SERT_REQUIRE(cfg && bytes, "null argument");
+  if (validate(*cfg)) return -1;
+  sert_model tmp;
+  tmp.cfg = *cfg;
+  *bytes = carve(tmp, nullptr);
+  return 0;
+}
+
+int sert_model_create(const sert_config *cfg, void *arena_dev, size_t arena_bytes, void *stream,
+                      sert_model **out) {
+  SERT_REQUIRE(cfg && arena_dev && out, "null argument");
+  if (validate(*cfg)) return -1;
+  SERT_REQUIRE(((uintptr_t)arena_dev & 255) == 0, "arena must be 256-byte aligned");
+  int ndev = 0;
+  SERT_CUDA(cudaGetDeviceCount(&ndev));
+  SERT_REQUIRE(ndev > 0, "no CUDA device: libsert_b200 has no CPU fallback");
+  sert_model *m = new sert_model();
+  m->cfg = *cfg;
+  const size_t need = carve(*m, arena_dev);
+  if (need > arena_bytes) {
+    delete m;
+    set_error("arena too small: need " + std::to_string(need) + " bytes");
+    return -1;
+  }
+  m->arena = static_cast<char *>(arena_dev);
+  m->arena_bytes = arena_bytes;
+  m->st = static_cast<cudaStream_t>(stream);
+  cudaError_t e = cudaMemsetAsync(arena_dev, 0, need, m->st);
+  if (e != cudaSuccess) {
+    delete m;
+    set_error(std::string("cudaMemsetAsync: ") + cudaGetErrorString(e));
+    return -1;
+  }
+  *out = m;
+  return 0;
+}
+
+int sert_model_destroy(sert_model *m) {
+  if (m) {
+    cudaStreamSynchronize(m->st);
+    delete m;
+  }
+  return 0;
+}
+
+static float *tensor_ptr(sert_model *m, int which, int slot) {
+  float *base = slot == SERT_STATE_PARAM ? m->theta : slot == SERT_STATE_S1 ? m->s1 : m->s2;
+  return base + m->off[which];
+}
+
+int sert_model_set_tensor(sert_model *m, int which, int slot, const float *host, size_t count) {
+  SERT_REQUIRE(m && host, "null argument");
+  SERT_REQUIRE(which >= 0 && which < 4 && m->cnt[which] > 0, "model has no such tensor");
+  SERT_REQUIRE(slot >= 0 && slot <= 2, "bad state slot");
+  SERT_REQUIRE((long long)count == m->cnt[which], "tensor size mismatch");
+  SERT_CUDA(cudaMemcpyAsync(tensor_ptr(m, which, slot), host, count * sizeof(float), cudaMemcpyHostToDevice, m->st));
+  SERT_CUDA(cudaStreamSynchronize(m->st));
+  return 0;
+}
+
+int sert_model_get_tensor(sert_model *m, int which, int slot, float *host, size_t count) {
+  SERT_REQUIRE(m && host, "null argument");
+  SERT_REQUIRE(which >= 0 && which < 4 && m->cnt[which] > 0, "model has no such tensor");
+  SERT_REQUIRE(slot >= 0 && slot <= 2, "bad state slot");
+  SERT_REQUIRE((long long)count == m->cnt[which], "tensor size mismatch");
+  SERT_CUDA(cudaMemcpyAsync(host, tensor_ptr(m, which, slot), count * sizeof(float), cudaMemcpyDeviceToHost, m->st));
+  SERT_CUDA(cudaStreamSynchronize(m->st));
+  return 0;
+}
+
+int sert_model_set_step(sert_model *m, int64_t t) {
+  SERT_REQUIRE(m && t >= 0, "bad argument");
+  m->step = t;
+  return 0;
+}
+int sert_model_get_step(sert_model *m, int64_t *t) {
+  SERT_REQUIRE(m && t, "null argument");
+  *t = m->step;
+  return 0;
+}
+
+int sert_model_attach_dataset(sert_model *m, int split, int64_t n, const int32_t *x_dev, const int32_t *y_dev,
+                              const int64_t *indptr_dev, const int32_t *indices_dev, const float *data_dev,
+                              const float *w_dev) {
+  SERT_REQUIRE(m, "null model");
+  SERT_REQUIRE(split == SERT_SPLIT_TRAIN || split == SERT_SPLIT_VALIDATE, "unknown split");
+  SERT_REQUIRE(n >= 0, "negative instance count");
+  SERT_REQUIRE(n == 0 || x_dev != nullptr, "x is required");
+  if (is_vs(m->cfg)) {
+    // sert/models.py:933-934: 'Only one-hot vectors supported.'
+    SERT_REQUIRE(n == 0 || y_dev != nullptr, "Only one-hot vectors supported.");
+  } else {
+    SERT_REQUIRE(n == 0 || (indptr_dev && indices_dev && data_dev), "log-linear model needs CSR labels");
+  }
+  Dataset &d = m->ds[split];
+  d.n = n; d.x = x_dev; d.y = y_dev; d.indptr = indptr_dev; d.indices = indices_dev; d.data = data_dev; d.w = w_dev;
+  return 0;
+}
+
+int sert_train_batches(sert_model *m, const int64_t *order_host, int64_t n, const int32_t *neg_dev,
+                       int32_t first_slot) {
+  SERT_REQUIRE(m && (order_host || n == 0), "null argument");
+  SERT_REQUIRE(first_slot >= 0 && first_slot + n <= m->cfg.loss_slots, "loss slots exhausted");
+  const sert_config &c = m->cfg;
+  const Dataset &d = m->ds[SERT_SPLIT_TRAIN];
+  for (int64_t j = 0; j < n; ++j) {
+    const int64_t b = order_host[j];
+    if (check_batch(m, SERT_SPLIT_TRAIN, b)) return -1;
+    const int64_t r0 = b * c.batch;
+    const float *w = d.w ? d.w + r0 : nullptr;
+    float *loss = m->losses + first_slot + j;
+    int rc;
+    if (is_vs(c)) {
+      const int32_t *neg = neg_dev ? neg_dev + j * (int64_t)c.batch * c.num_negatives : nullptr;
+      rc = vs_train_step(*m, d.x + r0 * c.window, d.y + r0, w, neg, loss);
+    } else {
+      rc = ll_train_step(*m, d.x + r0 * c.window, d.indptr + r0, 0, d.indices, d.data, w, loss);
+    }
+    if (rc) return -1;
+  }
+  return 0;
+}
+
+int sert_eval_batches(sert_model *m, int split, const int64_t *order_host, int64_t n, const int32_t *neg_dev,
+                      int32_t first_slot) {
+  SERT_REQUIRE(m && (order_host || n == 0), "null argument");
+  SERT_REQUIRE(first_slot >= 0 && first_slot + n <= m->cfg.loss_slots, "loss slots exhausted");
+  const sert_config &c = m->cfg;
+  for (int64_t j = 0; j < n; ++j) {
+    const int64_t b = order_host[j];
+    if (check_batch(m, split, b)) return -1;
+    const Dataset &d = m->ds[split];
+    const int64_t r0 = b * c.batch;
+    float *loss = m->losses + first_slot + j;
+    int rc;
+    if (is_vs(c)) {
+      const int32_t *neg = neg_dev ? neg_dev + j * (int64_t)c.batch * c.num_negatives : nullptr;
+      rc = vs_eval_step(*m, d.x + r0 * c.window, d.y + r0, neg, loss, false);
+    } else {
+      rc = ll_eval_step(*m, d.x + r0 * c.window, d.indptr + r0, 0, d.indices, d.data, loss, false);
+    }
+    if (rc) return -1;
+  }
+  return 0;
+}
+
+int sert_losses_fetch(sert_model *m, int32_t first_slot, int64_t n, float *out_host) {
+  SERT_REQUIRE(m && (out_host || n == 0), "null argument");
+  SERT_REQUIRE(first_slot >= 0 && first_slot + n <= m->cfg.loss_slots, "loss slot range out of bounds");
+  if (n > 0)
+    SERT_CUDA(cudaMemcpyAsync(out_host, m->losses + first_slot, n * sizeof(float), cudaMemcpyDeviceToHost, m->st));
+  SERT_CUDA(cudaStreamSynchronize(m->st));
+  for (int64_t j = 0; j < n; ++j) {
+    if (!isfinite(out_host[j])) {
+      // message mirrors sert/models.py:372-379
+      char buf[256];
+      snprintf(buf, sizeof(buf),
+               "Encountered NaN or infinity (%f) during batch iteration (batch %lld/%lld).",
+               (double)out_host[j], (long long)(j + 1), (long long)n);
+      set_error(buf);
+      return -2;
+    }
+  }
+  return 0;
+}
+
+int sert_train_batch_host(sert_model *m, const int32_t *x_host, const int32_t *y_host, const int64_t *indptr_host,
+                          const int32_t *indices_host, const float *data_host, const float *w_host,
+                          const int32_t *neg_host, float *loss_host) {
+  SERT_REQUIRE(m && x_host && loss_host, "null argument");
+  const sert_config &c = m->cfg;
+  cudaStream_t st = m->st;
+  const size_t B = c.batch;
+  SERT_CUDA(cudaMemcpyAsync(m->stage_x, x_host, B * c.window * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+  const float *w = nullptr;
+  if (w_host) {
+    SERT_CUDA(cudaMemcpyAsync(m->stage_w, w_host, B * sizeof(float), cudaMemcpyHostToDevice, st));
+    w = m->stage_w;
+  }
+  float *loss = m->losses + c.loss_slots;   // scratch slot
+  if (is_vs(c)) {
+    SERT_REQUIRE(y_host, "vector-space batches need one-hot labels");
+    SERT_CUDA(cudaMemcpyAsync(m->stage_y, y_host, B * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+    const int32_t *neg = nullptr;
+    if (neg_host) {
+      SERT_CUDA(cudaMemcpyAsync(m->stage_neg, neg_host, B * c.num_negatives * sizeof(int32_t),
+                                cudaMemcpyHostToDevice, st));
+      neg = m->stage_neg;
+    }
+    if (vs_train_step(*m, m->stage_x, m->stage_y, w, neg, loss)) return -1;
+  } else {
+    SERT_REQUIRE(indptr_host && indices_host && data_host, "log-linear batches need CSR labels");
+    const int64_t base = indptr_host[0];
+    const size_t nnz = (size_t)(indptr_host[B] - base);
+    SERT_REQUIRE(nnz <= m->stage_nnz_cap, "too many labels in one host batch");
+    SERT_CUDA(cudaMemcpyAsync(m->stage_indptr, indptr_host, (B + 1) * sizeof(int64_t), cudaMemcpyHostToDevice, st));
+    SERT_CUDA(cudaMemcpyAsync(m->stage_indices, indices_host + base, nnz * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+    SERT_CUDA(cudaMemcpyAsync(m->stage_data, data_host + base, nnz * sizeof(float), cudaMemcpyHostToDevice, st));
+    if (ll_train_step(*m, m->stage_x, m->stage_indptr, base, m->stage_indices, m->stage_data, w, loss)) return -1;
+  }
+  SERT_CUDA(cudaMemcpyAsync(loss_host, loss, sizeof(float), cudaMemcpyDeviceToHost, st));
+  SERT_CUDA(cudaStreamSynchronize(st));
+  if (!isfinite(*loss_host)) {
+    char buf[160];
+    snprintf(buf, sizeof(buf), "Encountered NaN or infinity (%f) during batch iteration.", (double)*loss_host);
+    set_error(buf);
+    return -2;
+  }
+  return 0;
+}
+
+int sert_vs_forward_host(sert_model *m, int split, int64_t batch_index, const int32_t *neg_dev,
+                         float *out_scores_host, float *out_proj_host, float *out_ell_host) {
+  SERT_REQUIRE(m && is_vs(m->cfg), "vector-space model required");
+  SERT_REQUIRE(neg_dev, "parity forward needs explicit negatives");
+  if (check_batch(m, split, batch_index)) return -1;
+  const sert_config &c = m->cfg;
+  const Dataset &d = m->ds[split];
+  const int64_t r0 = batch_index * c.batch;
+  if (vs_eval_step(*m, d.x + r0 * c.window, d.y + r0, neg_dev, m->losses + c.loss_slots, true)) return -1;
+  const size_t B = c.batch;
+  if (out_scores_host)
+    SERT_CUDA(cudaMemcpyAsync(out_scores_host, m->dbg_scores, B * (c.num_negatives + 1) * sizeof(float),
+                              cudaMemcpyDeviceToHost, m->st));
+  if (out_proj_host)
+    SERT_CUDA(cudaMemcpyAsync(out_proj_host, m->dbg_u, B * c.entity_dim * sizeof(float), cudaMemcpyDeviceToHost, m->st));
+  if (out_ell_host)
+    SERT_CUDA(cudaMemcpyAsync(out_ell_host, m->dbg_ell, B * sizeof(float), cudaMemcpyDeviceToHost, m->st));
+  SERT_CUDA(cudaStreamSynchronize(m->st));
+  return 0;
+}
+
+int sert_ll_forward_host(sert_model *m, int split, int64_t batch_index, float *out_z_host, float *out_s_host,
+                         float *out_ell_host) {
+  SERT_REQUIRE(m && !is_vs(m->cfg), "log-linear model required");
+  if (check_batch(m, split, batch_index)) return -1;
+  const sert_config &c = m->cfg;
+  const Dataset &d = m->ds[split];
+  const int64_t r0 = batch_index * c.batch;
+  if (ll_eval_step(*m, d.x + r0 * c.window, d.indptr + r0, 0, d.indices, d.data, m->losses + c.loss_slots, true))
+    return -1;
+  const size_t B = c.batch, E = c.entities;
+  if (out_z_host)
+    SERT_CUDA(cudaMemcpyAsync(out_z_host, m->Z, B * c.window * E * sizeof(float), cudaMemcpyDeviceToHost, m->st));
+  if (out_s_host) SERT_CUDA(cudaMemcpyAsync(out_s_host, m->S, B * E * sizeof(float), cudaMemcpyDeviceToHost, m->st));
+  if (out_ell_host)
+    SERT_CUDA(cudaMemcpyAsync(out_ell_host, m->dbg_ell, B * sizeof(float), cudaMemcpyDeviceToHost, m->st));
+  SERT_CUDA(cudaStreamSynchronize(m->st));
+  return 0;
+}
+
+int sert_predict_loglinear(sert_model *m, const int32_t *batch_host, int32_t rows, float *out_host) {
+  SERT_REQUIRE(m && batch_host && out_host, "null argument");
+  SERT_REQUIRE(!is_vs(m->cfg), "log-linear model required");
+  const sert_config &c = m->cfg;
+  SERT_REQUIRE(rows >= 0 && rows <= c.batch, "more rows than the model's batch size");
+  if (rows == 0) return 0;
+  const size_t BW = (size_t)rows * c.window, E = c.entities;
+  SERT_CUDA(cudaMemcpyAsync(m->stage_x, batch_host, BW * sizeof(int32_t), cudaMemcpyHostToDevice, m->st));
+  if (ll_forward(*m, m->stage_x, rows, m->st)) return -1;
+  if (launch_ll_softmax_inplace(m->Z, BW, (int)E, E, m->rmax, m->rsum, m->st)) return -1;
+  SERT_CUDA(cudaMemcpyAsync(out_host, m->Z, BW * E * sizeof(float), cudaMemcpyDeviceToHost, m->st));
+  SERT_CUDA(cudaStreamSynchronize(m->st));
+  return 0;
+}
+
+int sert_project_queries(sert_model *m, const float *avg_host, int32_t q, float *out_host) {
+  SERT_REQUIRE(m && avg_host && out_host, "null argument");
+  SERT_REQUIRE(is_vs(m->cfg), "vector-space model required");
+  const sert_config &c = m->cfg;
+  const float *Wp = m->theta + m->off[SERT_PARAM_DENSE_W];
+  const float *bp = m->theta + m->off[SERT_PARAM_DENSE_B];
+  for (int32_t q0 = 0; q0 < q; q0 += c.batch) {
+    const int n = std::min<int32_t>(c.batch, q - q0);
+    SERT_CUDA(cudaMemcpyAsync(m->h, avg_host + (size_t)q0 * c.word_dim, (size_t)n * c.word_dim * sizeof(float),
+                              cudaMemcpyHostToDevice, m->st));
+    if (launch_gemm_f32(m->h, Wp, m->t, n, c.entity_dim, c.word_dim, false, false, c.word_dim, c.entity_dim,
+                        c.entity_dim, EPI_BIAS_TANH, bp, 1, m->st))
+      return -1;
+    SERT_CUDA(cudaMemcpyAsync(out_host + (size_t)q0 * c.entity_dim, m->t, (size_t)n * c.entity_dim * sizeof(float),
+                              cudaMemcpyDeviceToHost, m->st));
+    SERT_CUDA(cudaStreamSynchronize(m->st));
+  }
+  return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,602 @@
+"""B200-native drop-in for the class surface of the reference's ``sert/models.py``.
+
+Same class tree, constructor keywords and method contracts as the reference
+(``ModelInterface -> ModelBase -> LanguageModelBase -> {LanguageModel,
+VectorSpaceLanguageModelBase -> VectorSpaceLanguageModel}``, sert/models.py:295,414,686,
+804,905,1024), so ``bin/train.py`` / ``bin/query.py`` run unchanged.  Everything the
+reference delegates to a compiled Theano graph (train_fn / test_fn / validate_fn /
+predict_fn, sert/models.py:554-608) is executed by hand-written sm_100a kernels reached
+through the C-ABI in ``include/sert_b200.h``; PyTorch only allocates HBM and copies arrays.
+
+Differences that are deliberate (and documented in DESIGN.md):
+* ``train()`` enqueues the whole shuffled epoch with one C call and checks the per-batch losses
+  for NaN/Inf afterwards (the reference synchronises after every batch, sert/models.py:370-379);
+  the RuntimeError and its message are the same.
+* negatives are sampled on the device with Philox (the reference uses an unseeded RandomStreams,
+  sert/models.py:956-973); ``train_fn`` / ``test_fn`` / ``validate_fn`` accept explicit negatives so
+  parity runs can feed both sides the same draw.
+"""
+import logging
+import time
+
+import numpy as np
+import scipy.sparse as sparse
+
+from sert_b200 import _native as N
+
+
+def _torch():
+    import torch
+    if not torch.cuda.is_available():
+        raise RuntimeError('sert_b200 needs a CUDA device (B200, sm_100a); there is no CPU fallback.')
+    return torch
+
+
+def glorot_uniform(shape, rng=np.random):
+    """lasagne.init.GlorotUniform().sample(shape) for 2-D shapes (bin/train.py:128,170)."""
+    a = np.sqrt(6.0 / (shape[0] + shape[1]))
+    return rng.uniform(-a, a, size=shape).astype(np.float32)
+
+
+def l2_regularization(objects):
+    """Marker kept for signature compatibility (sert/models.py:92-120); the L2 term is fused into the
+    dense optimiser kernel (csrc/opt_kernels.cu)."""
+    raise NotImplementedError('the L2 term is evaluated on the device')
+
+
+class _NativeModel(object):
+    """Owns the HBM arena + the sert_model handle."""
+
+    def __init__(self, kind, batch, window, vocab, entities, word_dim, entity_dim=0, num_negatives=0,
+                 lam=0.0, loss_slots=1 << 16, seed=None, device=None):
+        torch = _torch()
+        self.lib = N.load()
+        self.device = torch.device('cuda', torch.cuda.current_device() if device is None else device)
+        if seed is None:
+            seed = int(np.random.randint(low=0, high=(1 << 30)))      # sert/models.py:958-959
+        self.cfg = N.SertConfig(kind=kind, batch=batch, window=window, num_negatives=num_negatives or 0,
+                                vocab=vocab, entities=entities, word_dim=word_dim, entity_dim=entity_dim or 0,
+                                lambda_=lam, loss_slots=loss_slots, seed=seed, entity_begin=0,
+                                entity_count=entities)
+        nbytes = N.c_size_t(0)
+        N.check(self.lib.sert_model_arena_bytes(N.ctypes.byref(self.cfg), N.ctypes.byref(nbytes)))
+        with torch.cuda.device(self.device):
+            self.arena = torch.empty(nbytes.value, dtype=torch.uint8, device=self.device)
+            self.stream = torch.cuda.current_stream(self.device)
+            handle = N.c_void_p()
+            N.check(self.lib.sert_model_create(N.ctypes.byref(self.cfg), N.dev_ptr(self.arena), nbytes.value,
+                                               N.c_void_p(self.stream.cuda_stream), N.ctypes.byref(handle)))
+        self.handle = handle
+        self.loss_slots = loss_slots
+        self._keep = []          # torch tensors borrowed by the library
+
+    def close(self):
+        if getattr(self, 'handle', None):
+            self.lib.sert_model_destroy(self.handle)
+            self.handle = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def set_tensor(self, which, array, slot=N.STATE_PARAM):
+        a = np.ascontiguousarray(array, dtype=np.float32)
+        N.check(self.lib.sert_model_set_tensor(self.handle, which, slot, N.host_ptr(a), a.size))
+
+    def get_tensor(self, which, shape, slot=N.STATE_PARAM):
+        out = np.empty(shape, dtype=np.float32)
+        N.check(self.lib.sert_model_get_tensor(self.handle, which, slot, N.host_ptr(out), out.size))
+        return out
+
+    def attach(self, split, x, y, w):
+        torch = _torch()
+        n = int(x.shape[0])
+        x_dev = torch.from_numpy(np.ascontiguousarray(x, dtype=np.int32)).to(self.device)
+        y_dev = indptr = indices = data = w_dev = None
+        if sparse.issparse(y):
+            y = y.tocsr()
+            indptr = torch.from_numpy(np.ascontiguousarray(y.indptr, dtype=np.int64)).to(self.device)
+            indices = torch.from_numpy(np.ascontiguousarray(y.indices, dtype=np.int32)).to(self.device)
+            data = torch.from_numpy(np.ascontiguousarray(y.data, dtype=np.float32)).to(self.device)
+        else:
+            y_dev = torch.from_numpy(np.ascontiguousarray(y, dtype=np.int32)).to(self.device)
+        if w is not None:
+            w_dev = torch.from_numpy(np.ascontiguousarray(w, dtype=np.float32)).to(self.device)
+        self._keep.append((x_dev, y_dev, indptr, indices, data, w_dev))
+        N.check(self.lib.sert_model_attach_dataset(
+            self.handle, split, n, N.dev_ptr(x_dev), N.dev_ptr(y_dev), N.dev_ptr(indptr), N.dev_ptr(indices),
+            N.dev_ptr(data), N.dev_ptr(w_dev)))
+
+    def _neg_dev(self, negatives, n):
+        if negatives is None:
+            return None, None
+        torch = _torch()
+        neg = np.ascontiguousarray(negatives, dtype=np.int32)
+        assert neg.size == n * self.cfg.batch * self.cfg.num_negatives, 'negatives must be (n, B, k)'
+        t = torch.from_numpy(neg).to(self.device)
+        return t, N.dev_ptr(t)
+
+    def run_batches(self, mode, order, negatives=None):
+        """mode: 'train' | 'test' (eval on train rows) | 'validate'. Returns float32 losses (len(order),)."""
+        order = np.ascontiguousarray(order, dtype=np.int64)
+        out = np.empty(order.size, dtype=np.float32)
+        done = 0
+        while done < order.size:
+            n = min(self.loss_slots, order.size - done)
+            chunk = order[done:done + n]
+            keep, negp = self._neg_dev(None if negatives is None else np.asarray(negatives)[done:done + n], n)
+            if mode == 'train':
+                N.check(self.lib.sert_train_batches(self.handle, N.host_ptr(chunk), n, negp, 0))
+            else:
+                split = N.SPLIT_TRAIN if mode == 'test' else N.SPLIT_VALIDATE
+                N.check(self.lib.sert_eval_batches(self.handle, split, N.host_ptr(chunk), n, negp, 0))
+            N.check(self.lib.sert_losses_fetch(self.handle, 0, n, N.host_ptr(out[done:done + n])))
+            del keep
+            done += n
+        return out
+
+
+class ModelInterface(object):
+    """sert/models.py:295-411."""
+
+    TRAIN, VALIDATE, TEST = range(2, 5)
+
+    def __init__(self, batch_size):
+        assert batch_size > 0
+
+        self.batch_size = batch_size
+
+        logging.debug('Batch size: %d', self.batch_size)
+
+    @classmethod
+    def _get_batch_slice(cls, batch_index, batch_size):
+        start = batch_index * batch_size
+        end = (batch_index + 1) * batch_size
+
+        return slice(start, end)
+
+    def _number_of_batches(self, num_instances):
+        return num_instances // self.batch_size
+
+    def _iterate_batches(self, fn, num_instances, report_interval=10000, shuffle=False):
+        """Per-batch host loop with the reference's contract (sert/models.py:351-399); the epoch-at-once
+        device path used by train()/train_error()/validation_error() is _run_epoch()."""
+        start = time.time()
+
+        num_batches = self._number_of_batches(num_instances)
+        incomplete_batch_size = num_instances % self.batch_size
+        if incomplete_batch_size > 0:
+            logging.warning('\tIgnoring incomplete batch of size %d.', incomplete_batch_size)
+
+        results = []
+
+        batch_indices = list(range(num_batches))
+        if shuffle:
+            logging.debug('Shuffling batches.')
+
+            np.random.shuffle(batch_indices)
+
+        for batch_idx in batch_indices:
+            results.append(fn(batch_idx))
+
+            if not np.all(np.isfinite(results[-1])):
+                raise RuntimeError(
+                    'Encountered NaN or infinity ({error}) '
+                    'during batch iteration '
+                    '(batch {batches_finished}/{num_batches}).'.format(
+                        error=results[-1],
+                        batches_finished=len(results),
+                        num_batches=len(batch_indices)))
+
+            if results and (len(results) % report_interval == 0 or len(results) == num_batches):
+                self._report(len(results), num_batches, start)
+
+        return num_batches, results
+
+    @staticmethod
+    def _report(finished, num_batches, start):
+        elapsed = max(float(time.time() - start), 1e-9)
+        batches_per_second = finished / elapsed
+        remaining = (num_batches - finished) / batches_per_second
+        logging.info('\tProcessed %d batches; %.2f batches per second; '
+                     '%d minutes %d seconds remaining.',
+                     finished, batches_per_second, remaining / 60, remaining % 60)
+
+    def train(self):
+        raise NotImplementedError()
+
+    def train_error(self):
+        raise NotImplementedError()
+
+    def validation_error(self):
+        raise NotImplementedError()
+
+    def get_state(self):
+        raise NotImplementedError()
+
+
+class ModelBase(ModelInterface):
+    """sert/models.py:414-683: owns the device-resident data set and the four callables."""
+
+    def __init__(self, batch_size, training_set, validation_set, learning_method):
+        super(ModelBase, self).__init__(batch_size)
+
+        self.learning_method = learning_method
+
+        self.training_num_instances = training_set[1].shape[0]
+        self.validation_num_instances = validation_set[1].shape[0]
+
+        # Determine number of instance features.
+        self.num_instance_features = np.prod(training_set[0].shape[1:])
+
+        assert self.num_instance_features == training_set[0].shape[1]
+
+        if np.prod(validation_set[0].shape):
+            assert self.num_instance_features == validation_set[0].shape[1]
+        else:
+            validation_set = (
+                validation_set[0].reshape(0, self.num_instance_features),
+                validation_set[1])
+
+        logging.info('Data set contains %d training instances '
+                     'and %d validation instances',
+                     self.training_num_instances,
+                     self.validation_num_instances)
+
+        assert training_set[0].dtype == validation_set[0].dtype
+        assert training_set[1].dtype == validation_set[1].dtype
+
+        self.input_dtype = training_set[0].dtype
+        self.output_dtype = training_set[1].dtype
+
+        is_training_y_sparse = sparse.isspmatrix_csr(training_set[1])
+        is_validation_y_sparse = sparse.isspmatrix_csr(validation_set[1])
+
+        if is_training_y_sparse != is_validation_y_sparse:     # sert/models.py:566-571
+            raise RuntimeError('Either training or validation truths are '
+                               'sparse while the other is dense.')
+
+        self.training_set = training_set
+        self.validation_set = validation_set
+
+    # -- native plumbing ------------------------------------------------------------------
+    def _attach_datasets(self):
+        x, y, w = self.training_set
+        xv, yv = self.validation_set
+        if self._native.cfg.kind == N.KIND_LOGLINEAR:
+            if not sparse.issparse(y):
+                y, yv = sparse.csr_matrix(np.asarray(y, dtype=np.float32)), \
+                    sparse.csr_matrix(np.asarray(yv, dtype=np.float32))
+        for name, idx in (('training', x), ('validation', xv)):
+            if idx.size and (int(idx.max()) >= self.vocabulary_size or int(idx.min()) < 0):
+                raise AssertionError('%s word indices out of range' % name)
+        self._native.attach(N.SPLIT_TRAIN, x, y, w)
+        self._native.attach(N.SPLIT_VALIDATE, xv, yv, None)
+
+    def _create_functions(self):
+        """train_fn / test_fn / validate_fn(batch_index) -> float32 loss (sert/models.py:581-608)."""
+        native = self._native
+
+        def make(mode):
+            def fn(batch_index, negatives=None):
+                neg = None if negatives is None else np.asarray(negatives)[np.newaxis]
+                return native.run_batches(mode, [int(batch_index)], neg)[0]
+            fn.__name__ = mode + '_fn'
+            return fn
+
+        self.train_fn = make('train')
+        self.test_fn = make('test')
+        self.validate_fn = make('validate')
+
+    def _run_epoch(self, mode, num_instances, shuffle=False, report_interval=10000, negatives=None,
+                   order=None):
+        start = time.time()
+        num_batches = self._number_of_batches(num_instances)
+        incomplete_batch_size = num_instances % self.batch_size
+        if incomplete_batch_size > 0:
+            logging.warning('\tIgnoring incomplete batch of size %d.', incomplete_batch_size)
+        if order is None:
+            order = list(range(num_batches))
+            if shuffle:
+                logging.debug('Shuffling batches.')
+                np.random.shuffle(order)
+        results = self._native.run_batches(mode, order, negatives)
+        if num_batches:
+            self._report(len(results), num_batches, start)
+        return num_batches, results
+
+    def train(self, order=None, negatives=None):
+        logging.info('Training on %d training instances (%d batches).',
+                     self.training_num_instances,
+                     self._number_of_batches(self.training_num_instances))
+
+        num_batches, errors = self._run_epoch(
+            'train', self.training_num_instances, report_interval=1000, shuffle=True,
+            order=order, negatives=negatives)
+
+        return num_batches, np.mean(errors)
+
+    def train_error(self, negatives=None):
+        logging.info('Measuring error on %d training instances (%d batches).',
+                     self.training_num_instances,
+                     self._number_of_batches(self.training_num_instances))
+
+        num_batches, errors = self._run_epoch('test', self.training_num_instances, negatives=negatives)
+
+        return np.mean(errors), np.std(errors)
+
+    def validation_error(self, negatives=None):
+        logging.info('Measuring error on %d validation instances '
+                     '(%d batches).',
+                     self.validation_num_instances,
+                     self._number_of_batches(self.validation_num_instances))
+
+        num_batches, errors = self._run_epoch('validate', self.validation_num_instances, negatives=negatives)
+
+        return np.mean(errors), np.std(errors)
+
+    def get_state(self):
+        state = [self.predict_fn]
+
+        all_representations = self.get_representations()
+        if not isinstance(all_representations, (tuple, list)):
+            all_representations = (all_representations, )
+
+        for representations in all_representations:
+            state.append(representations)
+
+        return state
+
+    def get_representations(self):
+        raise RuntimeError()
+
+
+class LanguageModelBase(ModelBase):
+    """sert/models.py:686-801."""
+
+    def __init__(self, window_size, representations_init, regularization_lambda, regularization_fn, **kwargs):
+        super(LanguageModelBase, self).__init__(**kwargs)
+
+        assert window_size >= 1
+        self.window_size = window_size
+
+        self.initial_representations = representations_init
+
+        self.vocabulary_size = representations_init.shape[0]
+        self.representation_size = representations_init.shape[1]
+
+        self.regularization_lambda = regularization_lambda
+
+        self.regularization_fn = regularization_fn
+
+    def get_representations(self):
+        return self._native.get_tensor(N.PARAM_WORD_REPR, (self.vocabulary_size, self.representation_size))
+
+
+class LogLinearPredictFn(object):
+    """Picklable predict_fn of the log-linear model: (batch uintK (B,W), mask int8 (B,W)) -> f32 (B,W,E)
+    per-word softmax (sert/models.py:880-890; the mask is accepted and unused there).  Carries host copies of
+    R, W, b (the reference pickles the compiled Theano function, which embeds them) and builds its device
+    model on first use in the process that unpickled it."""
+
+    def __init__(self, representations, dense_w, dense_b, batch_size, window_size):
+        self.representations = np.ascontiguousarray(representations, dtype=np.float32)
+        self.dense_w = np.ascontiguousarray(dense_w, dtype=np.float32)
+        self.dense_b = np.ascontiguousarray(dense_b, dtype=np.float32)
+        self.batch_size, self.window_size = int(batch_size), int(window_size)
+        self._native = None
+
+    def __getstate__(self):
+        d = dict(self.__dict__)
+        d['_native'] = None
+        return d
+
+    def _ensure(self):
+        if self._native is None:
+            V, dw = self.representations.shape
+            E = self.dense_w.shape[1]
+            nat = _NativeModel(N.KIND_LOGLINEAR, self.batch_size, self.window_size, V, E, dw, loss_slots=4)
+            nat.set_tensor(N.PARAM_WORD_REPR, self.representations)
+            nat.set_tensor(N.PARAM_DENSE_W, self.dense_w)
+            nat.set_tensor(N.PARAM_DENSE_B, self.dense_b)
+            self._native = nat
+        return self._native
+
+    def __call__(self, batch, mask=None):
+        nat = self._ensure()
+        batch = np.ascontiguousarray(batch, dtype=np.int32)
+        assert batch.ndim == 2 and batch.shape[1] == self.window_size
+        rows, E = batch.shape[0], self.dense_w.shape[1]
+        out = np.empty((rows, self.window_size, E), dtype=np.float32)
+        done = 0
+        while done < rows:
+            n = min(self.batch_size, rows - done)
+            N.check(nat.lib.sert_predict_loglinear(nat.handle, N.host_ptr(batch[done:done + n]), n,
+                                                   N.host_ptr(out[done:done + n])))
+            done += n
+        return out
+
+
+class VectorSpacePredictFn(object):
+    """Picklable predict_fn of the vector-space model: avg word embedding (dw,) -> tanh(avg.W+b) (de,),
+    no clip (sert/models.py:1107-1118).  ``project`` is the batched form used by the GPU ranker."""
+
+    def __init__(self, dense_w, dense_b):
+        self.dense_w = np.ascontiguousarray(dense_w, dtype=np.float32)
+        self.dense_b = np.ascontiguousarray(dense_b, dtype=np.float32)
+        self._native = None
+
+    def __getstate__(self):
+        d = dict(self.__dict__)
+        d['_native'] = None
+        return d
+
+    def _ensure(self):
+        if self._native is None:
+            dw, de = self.dense_w.shape
+            nat = _NativeModel(N.KIND_VECTORSPACE, 1024, 1, 4, 4, dw, entity_dim=de, num_negatives=1, loss_slots=4)
+            nat.set_tensor(N.PARAM_DENSE_W, self.dense_w)
+            nat.set_tensor(N.PARAM_DENSE_B, self.dense_b)
+            self._native = nat
+        return self._native
+
+    def project(self, avg_matrix):
+        nat = self._ensure()
+        avg = np.ascontiguousarray(avg_matrix, dtype=np.float32)
+        assert avg.ndim == 2 and avg.shape[1] == self.dense_w.shape[0]
+        out = np.empty((avg.shape[0], self.dense_w.shape[1]), dtype=np.float32)
+        N.check(nat.lib.sert_project_queries(nat.handle, N.host_ptr(avg), avg.shape[0], N.host_ptr(out)))
+        return out
+
+    def __call__(self, avg_word_embedding):
+        return self.project(np.asarray(avg_word_embedding, dtype=np.float32).reshape(1, -1))[0]
+
+
+class LanguageModel(LanguageModelBase):
+    """Log-linear expert-finding model (sert/models.py:804-890): params [R, W, b], Adadelta, dense L2."""
+
+    def __init__(self,
+                 batch_size, window_size,
+                 representations_init,
+                 output_layer_size,
+                 regularization_lambda,
+                 training_set,
+                 validation_set,
+                 dense_init=None, device=None, loss_slots=1 << 16):
+        super(LanguageModel, self).__init__(
+            batch_size=batch_size,
+            window_size=window_size,
+            representations_init=representations_init,
+            regularization_lambda=regularization_lambda,
+            regularization_fn=l2_regularization,
+            training_set=training_set, validation_set=validation_set,
+            learning_method='adadelta')
+
+        self.output_layer_size = int(output_layer_size)
+        logging.debug('Input layer has shape %s.', (self.batch_size, self.window_size))
+
+        if dense_init is None:          # lasagne DenseLayer defaults: GlorotUniform W, zero b
+            dense_init = (glorot_uniform((self.representation_size, self.output_layer_size)),
+                          np.zeros(self.output_layer_size, dtype=np.float32))
+
+        self._native = _NativeModel(
+            N.KIND_LOGLINEAR, self.batch_size, self.window_size, self.vocabulary_size,
+            self.output_layer_size, self.representation_size, lam=float(regularization_lambda),
+            loss_slots=loss_slots, device=device)
+        self._native.set_tensor(N.PARAM_WORD_REPR, representations_init)
+        self._native.set_tensor(N.PARAM_DENSE_W, dense_init[0])
+        self._native.set_tensor(N.PARAM_DENSE_B, dense_init[1])
+        self._attach_datasets()
+        self._create_functions()
+
+    def get_dense(self):
+        return (self._native.get_tensor(N.PARAM_DENSE_W, (self.representation_size, self.output_layer_size)),
+                self._native.get_tensor(N.PARAM_DENSE_B, (self.output_layer_size,)))
+
+    @property
+    def predict_fn(self):
+        w, b = self.get_dense()
+        return LogLinearPredictFn(self.get_representations(), w, b, self.batch_size, self.window_size)
+
+
+def inproduct_sigmoid_distance(target_embeddings, output):
+    """sert/models.py:893-902, numpy form (host-side helper; the training path uses csrc/vs_kernels.cu)."""
+    assert target_embeddings.ndim == output.ndim
+
+    activation = 1.0 / (1.0 + np.exp(-np.sum(target_embeddings * output, axis=target_embeddings.ndim - 1)))
+
+    return np.clip(activation, 1e-7, 1.0 - 1e-7)
+
+
+class VectorSpaceLanguageModelBase(LanguageModelBase):
+    """sert/models.py:905-1021."""
+
+    def __init__(self,
+                 batch_size, window_size,
+                 num_negative_samples,
+                 representations_init,
+                 entity_representations_init,
+                 regularization_lambda,
+                 training_set,
+                 validation_set):
+        super(VectorSpaceLanguageModelBase, self).__init__(
+            batch_size=batch_size,
+            window_size=window_size,
+            representations_init=representations_init,
+            regularization_lambda=regularization_lambda,
+            regularization_fn=l2_regularization,
+            training_set=training_set, validation_set=validation_set,
+            learning_method='adam')
+
+        self.num_entities = entity_representations_init.shape[0]
+        self.entity_representation_size = entity_representations_init.shape[1]
+
+        assert self.training_set[1].ndim == 1, \
+            'Only one-hot vectors supported.'
+
+        assert num_negative_samples is None or num_negative_samples >= 0, \
+            'Number of negative samples should be None, zero or positive ' \
+            '(currently: {0}).'.format(num_negative_samples)
+
+        self.num_negative_samples = num_negative_samples
+
+    def get_representations(self):
+        return (self._native.get_tensor(N.PARAM_WORD_REPR, (self.vocabulary_size, self.representation_size)),
+                self._native.get_tensor(N.PARAM_ENTITY_REPR, (self.num_entities, self.entity_representation_size)))
+
+
+class VectorSpaceLanguageModel(VectorSpaceLanguageModelBase):
+    """Latent vector space (LSE) model (sert/models.py:1024-1118): params [Eemb, R, W, b], Adam, dense L2."""
+
+    def __init__(self,
+                 batch_size, window_size,
+                 num_negative_samples,
+                 representations_init,
+                 entity_representations_init,
+                 regularization_lambda,
+                 training_set,
+                 validation_set,
+                 dense_init=None, device=None, seed=None, loss_slots=1 << 16):
+        super(VectorSpaceLanguageModel, self).__init__(
+            batch_size=batch_size,
+            window_size=window_size,
+            num_negative_samples=num_negative_samples,
+            representations_init=representations_init,
+            entity_representations_init=entity_representations_init,
+            regularization_lambda=regularization_lambda,
+            training_set=training_set,
+            validation_set=validation_set)
+
+        # sert/models.py:948 (_negative_sampling asserts num_negative_samples > 0 when the loss is built)
+        assert num_negative_samples is not None and num_negative_samples > 0
+
+        if dense_init is None:
+            dense_init = (glorot_uniform((self.representation_size, self.entity_representation_size)),
+                          np.zeros(self.entity_representation_size, dtype=np.float32))
+
+        y = self.training_set[1]
+        if y.size and (int(y.max()) >= self.num_entities or int(y.min()) < 0):
+            raise AssertionError('entity labels out of range')
+
+        self._native = _NativeModel(
+            N.KIND_VECTORSPACE, self.batch_size, self.window_size, self.vocabulary_size, self.num_entities,
+            self.representation_size, entity_dim=self.entity_representation_size,
+            num_negatives=int(num_negative_samples), lam=float(regularization_lambda),
+            loss_slots=loss_slots, seed=seed, device=device)
+        self._native.set_tensor(N.PARAM_WORD_REPR, representations_init)
+        self._native.set_tensor(N.PARAM_ENTITY_REPR, entity_representations_init)
+        self._native.set_tensor(N.PARAM_DENSE_W, dense_init[0])
+        self._native.set_tensor(N.PARAM_DENSE_B, dense_init[1])
+        self._attach_datasets()
+        self._create_functions()
+
+    def get_dense(self):
+        return (self._native.get_tensor(N.PARAM_DENSE_W, (self.representation_size, self.entity_representation_size)),
+                self._native.get_tensor(N.PARAM_DENSE_B, (self.entity_representation_size,)))
+
+    @property
+    def predict_fn(self):
+        w, b = self.get_dense()
+        return VectorSpacePredictFn(w, b)

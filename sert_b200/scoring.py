@@ -1,0 +1,132 @@
+"""Entity scoring on the device: query x all-entities inner products with a fused running top-k.
+
+Replaces the sklearn NearestNeighbors / cdist + argsort of VectorSpaceCallback.query
+(bin/query.py:280-318).  ``ShardedScorer`` row-shards the entity matrix over the ranks of a
+torch.distributed (NCCL) group and merges per-shard top-k lists after ONE all-gather.
+"""
+import numpy as np
+
+from sert_b200 import _native as N
+
+
+def _torch():
+    import torch
+    if not torch.cuda.is_available():
+        raise RuntimeError('sert_b200 needs a CUDA device (B200, sm_100a); there is no CPU fallback.')
+    return torch
+
+
+class EntityScorer(object):
+
+    def __init__(self, entities, normalise=False, max_queries=1024, max_k=128, row_begin=0, device=None):
+        torch = _torch()
+        self.lib = N.load()
+        entities = np.ascontiguousarray(entities, dtype=np.float32)
+        assert entities.ndim == 2
+        self.rows, self.d = entities.shape
+        self.max_queries, self.max_k = int(max_queries), int(max_k)
+        self.device = torch.device('cuda', torch.cuda.current_device() if device is None else device)
+        nbytes = N.c_size_t(0)
+        N.check(self.lib.sert_scorer_arena_bytes(self.rows, self.d, self.max_queries, self.max_k,
+                                                 N.ctypes.byref(nbytes)))
+        with torch.cuda.device(self.device):
+            self.arena = torch.empty(nbytes.value, dtype=torch.uint8, device=self.device)
+            self.stream = torch.cuda.current_stream(self.device)
+            handle = N.c_void_p()
+            N.check(self.lib.sert_scorer_create(N.host_ptr(entities), self.rows, self.d, int(row_begin),
+                                                int(bool(normalise)), self.max_queries, self.max_k,
+                                                N.dev_ptr(self.arena), nbytes.value,
+                                                N.c_void_p(self.stream.cuda_stream), N.ctypes.byref(handle)))
+        self.handle = handle
+
+    def close(self):
+        if getattr(self, 'handle', None):
+            self.lib.sert_scorer_destroy(self.handle)
+            self.handle = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def topk(self, queries, k, normalise_queries=False):
+        """queries (Q,d) host float32 -> (idx (Q,k) int32 global row ids, score (Q,k) float32), best first."""
+        queries = np.ascontiguousarray(queries, dtype=np.float32)
+        assert queries.ndim == 2 and queries.shape[1] == self.d
+        Q = queries.shape[0]
+        idx = np.empty((Q, k), dtype=np.int32)
+        score = np.empty((Q, k), dtype=np.float32)
+        done = 0
+        while done < Q:
+            n = min(self.max_queries, Q - done)
+            N.check(self.lib.sert_scorer_topk_host(self.handle, N.host_ptr(queries[done:done + n]), n,
+                                                   int(bool(normalise_queries)), k,
+                                                   N.host_ptr(idx[done:done + n]), N.host_ptr(score[done:done + n])))
+            done += n
+        return idx, score
+
+    def topk_dev(self, queries_dev, k, normalise_queries=False):
+        """Device in / device out, asynchronous on the scorer's stream."""
+        torch = _torch()
+        Q = queries_dev.shape[0]
+        assert Q <= self.max_queries
+        idx = torch.empty((Q, k), dtype=torch.int32, device=self.device)
+        score = torch.empty((Q, k), dtype=torch.float32, device=self.device)
+        N.check(self.lib.sert_scorer_topk_dev(self.handle, N.dev_ptr(queries_dev), Q, int(bool(normalise_queries)), k,
+                                              N.dev_ptr(idx), N.dev_ptr(score)))
+        return idx, score
+
+
+def shard_bounds(num_rows, world_size, rank):
+    """Contiguous row shards of (almost) equal size: SURVEY.md 8(e)."""
+    base, rem = divmod(num_rows, world_size)
+    begin = rank * base + min(rank, rem)
+    return begin, begin + base + (1 if rank < rem else 0)
+
+
+class ShardedScorer(object):
+    """Row-sharded scoring over a torch.distributed group: local GEMM + top-k, ONE all-gather of the
+    per-shard (idx, score)[Q,k] lists, k-way merge on every rank."""
+
+    def __init__(self, entities_full_or_shard, num_rows_total, group=None, is_shard=False, normalise=False,
+                 max_queries=1024, max_k=128):
+        import torch.distributed as dist
+        self.dist = dist
+        self.group = group
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        begin, end = shard_bounds(num_rows_total, self.world, self.rank)
+        shard = entities_full_or_shard if is_shard else entities_full_or_shard[begin:end]
+        assert shard.shape[0] == end - begin
+        self.local = EntityScorer(shard, normalise=normalise, max_queries=max_queries, max_k=max_k, row_begin=begin)
+
+    def topk_dev(self, queries_dev, k, normalise_queries=False):
+        torch = _torch()
+        idx, score = self.local.topk_dev(queries_dev, k, normalise_queries)
+        if self.world == 1:
+            return idx, score
+        Q = idx.shape[0]
+        # one collective: pack (idx, score bits) into a single int32 tensor [Q, k, 2]
+        packed = torch.stack([idx, score.view(torch.int32)], dim=-1).contiguous()
+        gathered = torch.empty((self.world,) + tuple(packed.shape), dtype=torch.int32, device=packed.device)
+        self.dist.all_gather_into_tensor(gathered, packed, group=self.group)
+        g_idx = gathered[..., 0].contiguous()
+        g_score = gathered[..., 1].contiguous().view(torch.float32)
+        out_idx = torch.empty_like(idx)
+        out_score = torch.empty_like(score)
+        N.check(self.local.lib.sert_topk_merge_dev(N.dev_ptr(g_idx), N.dev_ptr(g_score), self.world, Q, k,
+                                                   N.dev_ptr(out_idx), N.dev_ptr(out_score),
+                                                   N.c_void_p(torch.cuda.current_stream().cuda_stream)))
+        return out_idx, out_score
+
+    def topk(self, queries, k, normalise_queries=False):
+        torch = _torch()
+        queries = np.ascontiguousarray(queries, dtype=np.float32)
+        outs_i, outs_s = [], []
+        for done in range(0, queries.shape[0], self.local.max_queries):
+            q = torch.from_numpy(queries[done:done + self.local.max_queries]).to(self.local.device)
+            i, s = self.topk_dev(q, k, normalise_queries)
+            outs_i.append(i.cpu().numpy())
+            outs_s.append(s.cpu().numpy())
+        return np.concatenate(outs_i), np.concatenate(outs_s)

@@ -1,0 +1,82 @@
+"""Device top-k scoring vs exact CPU ranking (ranked entity lists identical)."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+def exact_topk(E, q, k):
+    s = (q.astype(np.float64) @ E.astype(np.float64).T)
+    order = np.lexsort((np.arange(E.shape[0])[None, :].repeat(q.shape[0], 0), -s), axis=1)[:, :k]
+    return order, np.take_along_axis(s, order, axis=1)
+
+
+@pytest.mark.parametrize('rows,d,Q,k', [(5000, 128, 37, 100), (12345, 256, 130, 10), (300, 64, 5, 100),
+                                        (64, 32, 3, 64), (9000, 20, 65, 128)])
+def test_topk_matches_exact(rows, d, Q, k):
+    from oracle import sert_oracle as O
+    from sert_b200.scoring import EntityScorer
+    rng = np.random.default_rng(rows + d)
+    E = O.normalise_rows(rng.standard_normal((rows, d)))
+    q = O.normalise_rows(rng.standard_normal((Q, d)))
+    sc = EntityScorer(E, normalise=False, max_queries=64, max_k=128)
+    idx, score = sc.topk(q, k)
+    ref_idx, ref_score = exact_topk(E, q, k)
+    np.testing.assert_allclose(score, ref_score, rtol=0, atol=2e-6)
+    # identical ranked lists wherever the exact scores are separated by more than fp32 noise
+    gaps = np.abs(np.diff(ref_score, axis=1)).min(axis=1) > 1e-6
+    assert gaps.mean() > 0.5
+    assert (idx[gaps] == ref_idx[gaps]).all()
+    assert all(len(set(r.tolist())) == k for r in idx)
+
+
+def test_normalisation_on_device_and_row_offset():
+    from oracle import sert_oracle as O
+    from sert_b200.scoring import EntityScorer
+    rng = np.random.default_rng(5)
+    E = rng.standard_normal((4100, 48)).astype(np.float32) * 3
+    q = rng.standard_normal((9, 48)).astype(np.float32) * 7
+    sc = EntityScorer(E, normalise=True, max_queries=16, max_k=16, row_begin=1000)
+    idx, score = sc.topk(q, 16, normalise_queries=True)
+    ref_idx, ref_score = exact_topk(O.normalise_rows(E), O.normalise_rows(q), 16)
+    np.testing.assert_allclose(score, ref_score, atol=3e-6)
+    assert (idx == ref_idx + 1000).mean() > 0.99
+
+
+def test_ties_break_on_lower_row_id_and_short_shards():
+    from sert_b200.scoring import EntityScorer
+    E = np.zeros((10, 8), np.float32)
+    E[:, 0] = 1.0                      # all rows identical: every score ties
+    q = np.zeros((2, 8), np.float32)
+    q[:, 0] = 1.0
+    sc = EntityScorer(E, max_queries=4, max_k=16)
+    idx, score = sc.topk(q, 16)
+    assert (idx[:, :10] == np.arange(10)).all() and (idx[:, 10:] == -1).all()
+    assert np.isneginf(score[:, 10:]).all()
+
+
+def test_merge_of_shards_equals_single_device():
+    import torch
+    from oracle import sert_oracle as O
+    from sert_b200 import _native as N
+    from sert_b200.scoring import EntityScorer, shard_bounds
+    rng = np.random.default_rng(77)
+    E = O.normalise_rows(rng.standard_normal((7001, 64)))
+    q = O.normalise_rows(rng.standard_normal((33, 64)))
+    k, parts = 50, 4
+    full_idx, full_score = EntityScorer(E, max_queries=64, max_k=64).topk(q, k)
+    idxs, scores = [], []
+    for r in range(parts):
+        b, e = shard_bounds(E.shape[0], parts, r)
+        i, s = EntityScorer(E[b:e], max_queries=64, max_k=64, row_begin=b).topk(q, k)
+        idxs.append(i)
+        scores.append(s)
+    gi = torch.from_numpy(np.stack(idxs)).cuda()
+    gs = torch.from_numpy(np.stack(scores)).cuda()
+    oi = torch.empty((33, k), dtype=torch.int32, device='cuda')
+    os_ = torch.empty((33, k), dtype=torch.float32, device='cuda')
+    N.check(N.load().sert_topk_merge_dev(N.dev_ptr(gi), N.dev_ptr(gs), parts, 33, k, N.dev_ptr(oi), N.dev_ptr(os_),
+                                         N.c_void_p(torch.cuda.current_stream().cuda_stream)))
+    torch.cuda.synchronize()
+    assert (oi.cpu().numpy() == full_idx).all()
+    np.testing.assert_array_equal(os_.cpu().numpy(), full_score)

@@ -1,0 +1,137 @@
+"""Parity of the CUDA vector-space path (through the C-ABI) against the CPU oracle."""
+import numpy as np
+import pytest
+
+from tests import helpers as H
+
+pytestmark = pytest.mark.gpu
+
+
+def make_model(p, lam, **kw):
+    from sert_b200 import models
+    return models.VectorSpaceLanguageModel(
+        batch_size=p['B'], window_size=p['W'], num_negative_samples=p['k'],
+        representations_init=p['R'], entity_representations_init=p['Eemb'],
+        regularization_lambda=lam, training_set=p['train'], validation_set=p['val'],
+        dense_init=(p['Wp'], p['bp']), **kw)
+
+
+def forward_host(model, split, b, neg):
+    import torch
+    from sert_b200 import _native as N
+    nat = model._native
+    B, k, de = nat.cfg.batch, nat.cfg.num_negatives, nat.cfg.entity_dim
+    scores = np.empty((B, k + 1), np.float32)
+    proj = np.empty((B, de), np.float32)
+    ell = np.empty(B, np.float32)
+    negt = torch.from_numpy(np.ascontiguousarray(neg, dtype=np.int32)).to(nat.device)
+    N.check(nat.lib.sert_vs_forward_host(nat.handle, split, b, N.dev_ptr(negt), N.host_ptr(scores),
+                                         N.host_ptr(proj), N.host_ptr(ell)))
+    return scores, proj, ell
+
+
+@pytest.mark.parametrize('dims', [
+    dict(V=500, E=200, dw=64, de=32, W=10, B=128, k=10),
+    dict(V=3000, E=777, dw=300, de=128, W=4, B=256, k=10),     # product-search.sh shapes (dw=300, de=128, window 4)
+    dict(V=1200, E=50, dw=128, de=256, W=3, B=64, k=3),
+    dict(V=70000, E=2000, dw=8, de=520, W=33, B=32, k=37),     # uint32 indices, window > 32, ragged de
+])
+def test_forward_logits_match_oracle(dims):
+    from oracle import sert_oracle as O
+    p = H.vs_problem(11, n_batches=2, **dims)
+    model = make_model(p, 0.01)
+    for b in range(2):
+        scores, proj, ell = forward_host(model, 0, b, p['neg'][b])
+        sl = slice(b * p['B'], (b + 1) * p['B'])
+        f = O.vectorspace_forward(p['R'], p['Wp'], p['bp'], p['Eemb'], p['train'][0][sl], p['train'][1][sl], p['neg'][b])
+        ref = np.concatenate([f['score_pos'][:, None], f['score_neg']], axis=1)
+        H.close(scores, ref, what='logits')          # logits within 1e-4 relative fp32
+        H.close(proj, f['u'], what='projection')
+        H.close(ell, f['ell'], what='instance loss')
+
+
+@pytest.mark.parametrize('gain,weights', [(1.0, False), (1.0, True), (40.0, True)])
+def test_training_steps_match_oracle(gain, weights):
+    """5 Adam steps + eval losses; gain=40 drives tanh / sigmoid into the 1e-7 clips."""
+    p = H.vs_problem(5, V=800, E=300, dw=64, de=48, W=5, B=128, k=6, n_batches=5, gain=gain, weights=weights)
+    lam = 0.01
+    model = make_model(p, lam)
+    oracle = H.vs_oracle(p, lam)
+    order = [3, 0, 4, 1, 2]
+    e0 = model.test_fn(1, p['neg'][1])
+    H.close(e0, oracle.eval_batch('train', 1, p['neg'][1]), what='initial eval loss')
+    v0 = model.validate_fn(0, p['neg'][0])
+    H.close(v0, oracle.eval_batch('val', 0, p['neg'][0]), what='initial validation loss')
+    for j, b in enumerate(order):
+        got = model.train_fn(b, p['neg'][j])
+        ref = oracle.train_batch(b, p['neg'][j])
+        H.close(got, ref, what='train loss step %d' % j)
+    R, Eemb = model.get_representations()
+    Wp, bp = model.get_dense()
+    H.close(R, oracle.R, rtol=2e-4, what='R')
+    H.close(Eemb, oracle.Eemb, rtol=2e-4, what='Eemb')
+    H.close(Wp, oracle.Wp, rtol=2e-4, what='Wp')
+    H.close(bp, oracle.bp, rtol=2e-4, atol_scale=1e-4, what='bp')
+    from sert_b200 import _native as N
+    m = model._native.get_tensor(N.PARAM_ENTITY_REPR, oracle.Eemb.shape, N.STATE_S1)
+    v = model._native.get_tensor(N.PARAM_WORD_REPR, oracle.R.shape, N.STATE_S2)
+    H.close(m, oracle.state['Eemb'][0], rtol=2e-4, atol_scale=1e-4, what='Adam m (Eemb)')
+    H.close(v, oracle.state['R'][1], rtol=2e-4, atol_scale=1e-4, what='Adam v (R)')
+    H.close(model.test_fn(2, p['neg'][2]), oracle.eval_batch('train', 2, p['neg'][2]), rtol=2e-4,
+            what='eval loss after training')
+
+
+def test_epoch_api_and_host_batches():
+    """train() over a whole epoch in one call == per-batch train_fn; streamed host batches == resident data."""
+    from sert_b200 import _native as N
+    p = H.vs_problem(9, V=600, E=150, dw=32, de=32, W=4, B=64, k=5, n_batches=4)
+    a, b = make_model(p, 0.01), make_model(p, 0.01)
+    order = [2, 0, 3, 1]
+    n, mean = a.train(order=order, negatives=p['neg'][:4])
+    assert n == 4
+    losses = [b.train_fn(bi, p['neg'][j]) for j, bi in enumerate(order)]
+    np.testing.assert_allclose(mean, np.mean(losses), rtol=1e-6)
+    c = make_model(p, 0.01)
+    nat = c._native
+    x, y, w = p['train']
+    for j, bi in enumerate(order):
+        sl = slice(bi * 64, (bi + 1) * 64)
+        xb = np.ascontiguousarray(x[sl], dtype=np.int32)
+        yb = np.ascontiguousarray(y[sl], dtype=np.int32)
+        wb = np.ascontiguousarray(w[sl], dtype=np.float32)
+        nb = np.ascontiguousarray(p['neg'][j], dtype=np.int32)
+        out = np.zeros(1, np.float32)
+        N.check(nat.lib.sert_train_batch_host(nat.handle, N.host_ptr(xb), N.host_ptr(yb), None, None, None,
+                                              N.host_ptr(wb), N.host_ptr(nb), N.host_ptr(out)))
+        np.testing.assert_allclose(out[0], losses[j], rtol=1e-5)
+    # errors over epochs: (mean, std) protocol, tail dropped
+    mean_e, std_e = a.train_error(negatives=p['neg'][:4])
+    assert np.isfinite(mean_e) and std_e >= 0
+
+
+def test_device_sampled_negatives_and_nan_guard():
+    p = H.vs_problem(3, V=400, E=100, dw=16, de=16, W=3, B=32, k=4, n_batches=3)
+    model = make_model(p, 0.0, seed=1234)
+    n, mean = model.train()
+    assert n == 3 and np.isfinite(mean)
+    # NaN parameters must surface as the reference's RuntimeError (sert/models.py:372-379)
+    from sert_b200 import _native as N
+    bad = p['Wp'].copy()
+    bad[0, 0] = np.nan
+    model._native.set_tensor(N.PARAM_DENSE_W, bad)
+    with pytest.raises(RuntimeError, match='NaN or infinity'):
+        model.train()
+
+
+def test_predict_fn_matches_oracle_and_pickles():
+    import pickle
+    from oracle import sert_oracle as O
+    p = H.vs_problem(21, V=300, E=64, dw=300, de=128, W=4, B=32, k=2, n_batches=1)
+    model = make_model(p, 0.01)
+    state = model.get_state()
+    assert len(state) == 3 and state[1].shape == p['R'].shape and state[2].shape == p['Eemb'].shape
+    fn = pickle.loads(pickle.dumps(state[0]))
+    rng = np.random.default_rng(0)
+    for _ in range(3):
+        avg = p['R'][rng.integers(0, 300, 5)].mean(axis=0)
+        H.close(fn(avg), O.vectorspace_predict(p['Wp'], p['bp'], avg), what='predict_fn')
