@@ -1,0 +1,355 @@
+#!/usr/bin/env python
+"""Benchmark of the SERT hot path on B200 (contract: see the task statement / DESIGN.md "Measurement").
+
+    python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
+    python bench.py --impl reference --gpus N --steps K ...   # the reference's CPU path (oracle port)
+
+Workload at every N: BASELINE.json configs[1] -- VectorSpaceLanguageModel |V|=100k |E|=50k d=128
+window=10, B=4096, k=10, lambda=0.01, float32 (the reference computes in float32; a float64 op is a
+hard error there).  A "step" is one training batch (forward, backward, dense Adam+L2 update of all
+tables).  N>1: one process per GPU, independent replicas on disjoint data shards (training has no
+exchange step in the reference; DESIGN.md "Multi-GPU"), value = total pairs / max-over-ranks time.
+The same JSON line carries the entity-scoring metric (row-sharded over the N ranks, one NCCL
+all-gather of per-shard top-k) under "scoring".
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+CFG2 = dict(V=100000, E=50000, dw=128, de=128, W=10, B=4096, k=10, lam=0.01)
+CFG3 = dict(Q=10000, E=50000, d=128, k=100)
+METRIC = '(word,entity) pairs/sec train'
+UNIT = 'pairs/s'
+
+
+def measured_peaks():
+    path = os.path.join(ROOT, 'MEASURED_PEAKS.json')
+    if os.path.exists(path):
+        with open(path) as f:
+            d = json.load(f)
+        return float(d['hbm_gbs']), 'measured (MEASURED_PEAKS.json hbm_gbs)'
+    return 6650.0, 'fallback (B200_PROFILING.md)'
+
+
+class ClockSampler(object):
+    """Samples nvidia-smi clocks / throttle reasons while the timed region runs."""
+
+    Q = ('index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,'
+         'clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,'
+         'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap')
+
+    def __init__(self, gpu_index):
+        self.gpu_index = gpu_index
+        self.samples = []
+        self.stop_flag = threading.Event()
+        self.thread = threading.Thread(target=self._run, daemon=True)
+
+    def _run(self):
+        while not self.stop_flag.is_set():
+            try:
+                out = subprocess.run(['nvidia-smi', '-i', str(self.gpu_index), '--query-gpu=' + self.Q,
+                                      '--format=csv,noheader,nounits'], stdout=subprocess.PIPE,
+                                     stderr=subprocess.DEVNULL, timeout=5).stdout.decode().strip()
+                if out:
+                    self.samples.append([c.strip() for c in out.split(',')])
+            except Exception:
+                pass
+            self.stop_flag.wait(0.1)
+
+    def __enter__(self):
+        self.thread.start()
+        return self
+
+    def __exit__(self, *a):
+        self.stop_flag.set()
+        self.thread.join(timeout=6)
+
+    def summary(self):
+        sm, mx, reasons = [], [], set()
+        names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
+        for s in self.samples:
+            try:
+                sm.append(float(s[1]))
+                mx.append(float(s[2]))
+            except Exception:
+                continue
+            for name, v in zip(names, s[5:9]):
+                if v.lower().startswith('active'):
+                    reasons.add(name)
+        if not sm:
+            return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': [], 'samples': 0}
+        return {'sm_mhz': float(np.median(sm)), 'sm_max_mhz': float(max(mx)), 'reasons': sorted(reasons),
+                'samples': len(sm)}
+
+
+def make_problem(rank, n_batches, cfg=CFG2):
+    from sert_b200 import synth
+    seed = 20160816 + 2 + 1000 * rank
+    rng = np.random.default_rng(seed)
+    B = cfg['B']
+    train, val = synth.vectorspace_corpus(seed, cfg['V'], cfg['E'], cfg['W'], B * n_batches, B)
+    R = synth.glorot(rng, (cfg['V'], cfg['dw']))
+    Eemb = synth.glorot(rng, (cfg['E'], cfg['de']))
+    Wp = synth.glorot(rng, (cfg['dw'], cfg['de']))
+    bp = np.zeros(cfg['de'], np.float32)
+    neg = rng.integers(0, cfg['E'], size=(n_batches, B, cfg['k'])).astype(np.int32)
+    return dict(train=train, val=val, R=R, Eemb=Eemb, Wp=Wp, bp=bp, neg=neg)
+
+
+def algorithmic_bytes_per_step(cfg=CFG2):
+    """dense update 24 B/param + word gather/scatter + entity rows (+ indices)."""
+    P = cfg['V'] * cfg['dw'] + cfg['E'] * cfg['de'] + cfg['dw'] * cfg['de'] + cfg['de']
+    dense = 24 * P
+    words = 2 * cfg['B'] * cfg['W'] * cfg['dw'] * 4 + cfg['B'] * cfg['W'] * 4
+    ents = 2 * cfg['B'] * (1 + cfg['k']) * cfg['de'] * 4 + cfg['B'] * (1 + cfg['k']) * 4
+    return dense, dense + words + ents
+
+
+# --------------------------------------------------------------------------------------------------
+def run_reference(args, rank, world):
+    """The reference's own CPU implementation of the path: Theano/Lasagne cannot be installed here (no
+    network; Python 3.12), so this arm times the numpy float32 restatement under oracle/ (kind: port)."""
+    if rank != 0:
+        return
+    from oracle import sert_oracle as O
+    cfg = CFG2
+    steps, warm = args.steps, args.warmup
+    sample_steps = min(steps, 8)
+    p = make_problem(0, sample_steps + min(warm, 1))
+    orc = O.VectorSpaceOracle(cfg['B'], p['R'], p['Wp'], p['bp'], p['Eemb'], cfg['lam'], p['train'], p['val'])
+    for j in range(min(warm, 1)):
+        orc.train_batch(j, p['neg'][j])
+    t0 = time.perf_counter()
+    for j in range(sample_steps):
+        orc.train_batch(min(warm, 1) + j, p['neg'][min(warm, 1) + j])
+    dt = time.perf_counter() - t0
+    value = sample_steps * cfg['B'] / dt
+    cores = len(os.sched_getaffinity(0))
+    line = {
+        'impl': 'reference', 'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': args.gpus,
+        'steps': sample_steps, 'warmup': min(warm, 1), 'ms_per_step': 1e3 * dt / sample_steps,
+        'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+        'config': {'workload': 'BASELINE.json configs[1]: VectorSpaceLanguageModel V=100k E=50k d=128 window=10 '
+                               'B=4096 k=10 lambda=0.01', 'parallelism': 'cpu'},
+        'cpu_baseline': {'value': value, 'unit': UNIT, 'cores': cores, 'kind': 'port',
+                         'sample': '%d training batches of 4096 pairs (numpy f32 oracle port of sert/models.py; '
+                                   'BLAS uses %d threads, elementwise passes are single-threaded like '
+                                   "Theano's CPU ops)" % (sample_steps, cores)},
+        'e2e': {'value': value, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+    }
+    print(json.dumps(line))
+
+
+# --------------------------------------------------------------------------------------------------
+def run_ours(args, rank, world, local_rank):
+    import torch
+    import torch.distributed as dist
+    from sert_b200 import _native as N, models
+    from sert_b200.scoring import ShardedScorer
+
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group('nccl', device_id=torch.device('cuda', local_rank))
+
+    cfg = CFG2
+    steps, warm = args.steps, max(args.warmup, 3)
+    n_batches = steps + warm
+    p = make_problem(rank, n_batches)
+    model = models.VectorSpaceLanguageModel(
+        batch_size=cfg['B'], window_size=cfg['W'], num_negative_samples=cfg['k'],
+        representations_init=p['R'], entity_representations_init=p['Eemb'], regularization_lambda=cfg['lam'],
+        training_set=p['train'], validation_set=p['val'], dense_init=(p['Wp'], p['bp']),
+        loss_slots=max(1024, n_batches))
+    nat = model._native
+    lib = nat.lib
+    neg_dev = torch.from_numpy(p['neg']).cuda()
+    order = np.arange(n_batches, dtype=np.int64)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def train(lo, hi):
+        N.check(lib.sert_train_batches(nat.handle, N.host_ptr(order[lo:hi]), hi - lo,
+                                       N.c_void_p(neg_dev.data_ptr() + lo * cfg['B'] * cfg['k'] * 4), lo))
+
+    # ---- device-resident throughput ("value") ----
+    train(0, warm)
+    barrier()
+    launches0 = N.launch_count()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with ClockSampler(local_rank) as clocks:
+        barrier()
+        ev0.record()
+        train(warm, n_batches)
+        ev1.record()
+        barrier()
+    launches = N.launch_count() - launches0
+    ms = ev0.elapsed_time(ev1)
+    losses = np.empty(n_batches, np.float32)
+    N.check(lib.sert_losses_fetch(nat.handle, 0, n_batches, N.host_ptr(losses)))
+    t = torch.tensor([ms], dtype=torch.float64, device='cuda')
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_max = float(t.item())
+    value = world * steps * cfg['B'] / (ms_max * 1e-3)
+
+    # ---- roofline of the dominant kernel (dense Adam+L2 update), CUDA events around each launch ----
+    N.check(lib.sert_model_profile(nat.handle, 1))
+    prof_steps = min(steps, 50)
+    N.check(lib.sert_train_batches(nat.handle, N.host_ptr(order[:prof_steps]), prof_steps,
+                                   N.c_void_p(neg_dev.data_ptr()), 0))
+    tot, cnt, bpl = N.ctypes.c_double(0), N.c_int64(0), N.ctypes.c_double(0)
+    N.check(lib.sert_model_profile_read(nat.handle, N.ctypes.byref(tot), N.ctypes.byref(cnt), N.ctypes.byref(bpl)))
+    N.check(lib.sert_model_profile(nat.handle, 0))
+    upd_ms = tot.value / max(cnt.value, 1)
+    peak, peak_src = measured_peaks()
+    achieved = bpl.value / (upd_ms * 1e-3) / 1e9
+    traffic = None
+    tpath = os.path.join(ROOT, 'profiles', 'dense_update_traffic.json')
+    if os.path.exists(tpath):
+        with open(tpath) as f:
+            traffic = json.load(f).get('dram_bytes_per_launch')
+    dense_bytes, step_bytes = algorithmic_bytes_per_step()
+
+    # ---- end-to-end: host batches through the C-ABI, H2D + step + D2H loss every step ----
+    x, y, w = p['train']
+    B = cfg['B']
+    pin = lambda a: torch.from_numpy(np.ascontiguousarray(a)).pin_memory()
+    xs = pin(x.astype(np.int32))
+    ys = pin(y.astype(np.int32))
+    ws = pin(w.astype(np.float32))
+    ns = pin(p['neg'])
+    loss_host = torch.zeros(1, dtype=torch.float32).pin_memory()
+
+    def e2e_step(b):
+        N.check(lib.sert_train_batch_host(
+            nat.handle, N.c_void_p(xs.data_ptr() + b * B * cfg['W'] * 4), N.c_void_p(ys.data_ptr() + b * B * 4),
+            None, None, None, N.c_void_p(ws.data_ptr() + b * B * 4), N.c_void_p(ns.data_ptr() + b * B * cfg['k'] * 4),
+            N.c_void_p(loss_host.data_ptr())))
+
+    for b in range(warm):
+        e2e_step(b)
+    barrier()
+    t0 = time.perf_counter()
+    for b in range(warm, n_batches):
+        e2e_step(b)
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t0
+    te = torch.tensor([e2e_s], dtype=torch.float64, device='cuda')
+    if world > 1:
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+    e2e_value = world * steps * B / float(te.item())
+    h2d = B * cfg['W'] * 4 + B * 4 + B * 4 + B * cfg['k'] * 4
+    model._native.close()
+    del model
+
+    # ---- entity scoring (row-sharded; one all-gather of per-shard top-k) ----
+    sc = CFG3
+    rng = np.random.default_rng(20160816 + 3)
+    ent = rng.standard_normal((sc['E'], sc['d'])).astype(np.float32)
+    ent /= np.linalg.norm(ent, axis=1)[:, None]
+    qs = rng.standard_normal((sc['Q'], sc['d'])).astype(np.float32)
+    qs /= np.linalg.norm(qs, axis=1)[:, None]
+    scorer = ShardedScorer(ent, sc['E'], max_queries=sc['Q'], max_k=128)
+    q_dev = torch.from_numpy(qs).cuda()
+    for _ in range(3):
+        scorer.topk_dev(q_dev, sc['k'])
+    barrier()
+    s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    reps = 5
+    s0.record()
+    for _ in range(reps):
+        idx, score = scorer.topk_dev(q_dev, sc['k'])
+    s1.record()
+    barrier()
+    sms = torch.tensor([s0.elapsed_time(s1) / reps], dtype=torch.float64, device='cuda')
+    if world > 1:
+        dist.all_reduce(sms, op=dist.ReduceOp.MAX)
+    score_value = sc['Q'] * sc['E'] / (float(sms.item()) * 1e-3)
+    # e2e scoring: host queries in, host lists out
+    t0 = time.perf_counter()
+    scorer.topk(qs, sc['k'])
+    score_e2e = sc['Q'] * sc['E'] / (time.perf_counter() - t0)
+
+    if rank == 0:
+        cpu = cpu_baseline_sample()
+        line = {
+            'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': steps, 'warmup': warm,
+            'ms_per_step': ms_max / steps, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
+            'dtype': 'f32', 'data': 'synthetic',
+            'config': {'workload': 'BASELINE.json configs[1]: VectorSpaceLanguageModel V=100k E=50k d=128 window=10 '
+                                   'B=4096 k=10 lambda=0.01 (Adam + dense L2, float32)',
+                       'global_batch': world * B,
+                       'parallelism': 'single' if world == 1 else 'replicas x%d (no training collective)' % world,
+                       'l2_policy': 'working set (params+Adam state+grads = 307 MB) larger than L2; no flush',
+                       'final_loss': float(losses[-1])},
+            'clocks': clocks.summary(),
+            'gpu_launches': int(launches),
+            'e2e': {'value': e2e_value, 'unit': UNIT, 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': 4,
+                    'api': 'sert_train_batch_host (pinned host batch -> loss on host, one sync per step)'},
+            'roofline': {'bound': 'hbm', 'kernel': 'dense_update_kernel<Adam> (csrc/opt_kernels.cu)',
+                         'achieved': achieved, 'peak': peak, 'unit': 'GB/s', 'frac': achieved / peak,
+                         'traffic': traffic, 'peak_source': peak_src,
+                         'algorithmic_bytes_per_launch': bpl.value, 'kernel_ms': upd_ms,
+                         'kernel_share_of_step': upd_ms / (ms_max / steps),
+                         'step_algorithmic_bytes': step_bytes,
+                         'step_frac_of_hbm_peak': step_bytes / (ms_max / steps * 1e-3) / 1e9 / peak},
+            'cpu_baseline': cpu,
+            'scoring': {'metric': 'scored entities/sec', 'value': score_value, 'unit': 'entities/s',
+                        'workload': 'BASELINE.json configs[2]: Q=10000 x E=50000 d=128 top-100, rows sharded '
+                                    'over %d GPU(s), one all-gather' % world,
+                        'ms': float(sms.item()), 'e2e_value': score_e2e,
+                        'tflops': 2.0 * sc['Q'] * sc['E'] * sc['d'] / (float(sms.item()) * 1e-3) / 1e12},
+        }
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def cpu_baseline_sample():
+    """Oracle port timed on the host cores (rank 0, N=1 semantics): a bounded sample of the same workload."""
+    from oracle import sert_oracle as O
+    cfg = CFG2
+    n = 6
+    p = make_problem(0, n + 1)
+    orc = O.VectorSpaceOracle(cfg['B'], p['R'], p['Wp'], p['bp'], p['Eemb'], cfg['lam'], p['train'], p['val'])
+    orc.train_batch(0, p['neg'][0])
+    t0 = time.perf_counter()
+    for j in range(1, n + 1):
+        orc.train_batch(j, p['neg'][j])
+    dt = time.perf_counter() - t0
+    return {'value': n * cfg['B'] / dt, 'unit': UNIT, 'cores': len(os.sched_getaffinity(0)), 'kind': 'port',
+            'sample': '%d training batches of 4096 pairs, numpy f32 oracle (oracle/sert_oracle.py)' % n}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=200)
+    ap.add_argument('--warmup', type=int, default=10)
+    ap.add_argument('--impl', choices=['ours', 'reference'], default='ours')
+    args = ap.parse_args()
+    rank = int(os.environ.get('RANK', '0'))
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    local_rank = int(os.environ.get('LOCAL_RANK', '0'))
+    if args.impl == 'reference':
+        run_reference(args, rank, world)
+        return 0
+    run_ours(args, rank, world, local_rank)
+    return 0
+
+
+if __name__ == '__main__':
+    sys.exit(main())

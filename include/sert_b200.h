@@ -104,6 +104,14 @@ SERT_API int sert_model_get_tensor(sert_model *m, int which, int slot, float *ho
 SERT_API int sert_model_set_step(sert_model *m, int64_t t);
 SERT_API int sert_model_get_step(sert_model *m, int64_t *t);
 
+/* Measurement hook (no reference counterpart): when enabled, every training step brackets its dense
+ * optimiser kernel with CUDA events on the model's stream.  profile_read synchronises and returns the
+ * summed kernel time, the launch count and the ALGORITHMIC bytes of one launch (24 B per parameter:
+ * read+write of theta and the two optimiser-state arrays; DESIGN.md "roofline"). */
+SERT_API int sert_model_profile(sert_model *m, int enable);
+SERT_API int sert_model_profile_read(sert_model *m, double *update_ms_total, int64_t *update_launches,
+                                     double *update_bytes_per_launch);
+
 /* ---- device-resident data set: replaces the theano.shared X/Y/W variables, sert/models.py:470-480 -- */
 /* x_dev (N,W) int32; labels either one-hot y_dev (N,) int32 (vector space, bin/train.py:186-245) or CSR
  * (indptr_dev int64 (N+1), indices_dev int32, data_dev f32; bin/prepare.py:593-597); w_dev (N,) f32 or NULL

@@ -45,6 +45,9 @@ SIGNATURES = {
     'sert_model_get_tensor': (c_int, [c_void_p, c_int, c_int, c_void_p, c_size_t]),
     'sert_model_set_step': (c_int, [c_void_p, c_int64]),
     'sert_model_get_step': (c_int, [c_void_p, ctypes.POINTER(c_int64)]),
+    'sert_model_profile': (c_int, [c_void_p, c_int]),
+    'sert_model_profile_read': (c_int, [c_void_p, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(c_int64),
+                                        ctypes.POINTER(ctypes.c_double)]),
     'sert_model_attach_dataset': (c_int, [c_void_p, c_int, c_int64, c_void_p, c_void_p, c_void_p, c_void_p,
                                           c_void_p, c_void_p]),
     'sert_train_batches': (c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_int32]),

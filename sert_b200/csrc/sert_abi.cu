@@ -76,6 +76,9 @@ struct sert_model {
   int64_t *stage_indptr = nullptr;
   float *stage_w = nullptr, *stage_data = nullptr, *stage_f = nullptr;
   size_t stage_nnz_cap = 0;
+  // optional per-kernel timing of the dense update (bench.py's roofline leg)
+  bool profile = false;
+  std::vector<std::pair<cudaEvent_t, cudaEvent_t>> prof_events;
 };
 
 namespace sert {
@@ -211,6 +214,19 @@ static int pick_split_k(int M, int N, int K) {
   return (int)want;
 }
 
+// dense update, optionally bracketed by CUDA events on the model's stream (profile mode)
+static int timed_update(sert_model &m, const OptimArgs &o, bool adam) {
+  if (!m.profile) return adam ? launch_adam(o, m.st) : launch_adadelta(o, m.st);
+  cudaEvent_t a, b;
+  SERT_CUDA(cudaEventCreate(&a));
+  SERT_CUDA(cudaEventCreate(&b));
+  SERT_CUDA(cudaEventRecord(a, m.st));
+  const int rc = adam ? launch_adam(o, m.st) : launch_adadelta(o, m.st);
+  SERT_CUDA(cudaEventRecord(b, m.st));
+  m.prof_events.emplace_back(a, b);
+  return rc;
+}
+
 // ---- vector space: one training step on device-resident batch pointers --------------------------
 static int vs_forward(sert_model &m, const int32_t *x, cudaStream_t st) {
   const sert_config &c = m.cfg;
@@ -254,7 +270,7 @@ static int vs_train_step(sert_model &m, const int32_t *x, const int32_t *y, cons
   m.step += 1;
   OptimArgs o = optim_args(m, loss_out);
   o.c0 = adam_alpha_f32(m.step); o.c1 = 0.9f; o.c2 = 0.999f; o.c3 = 1e-8f;
-  return launch_adam(o, st);
+  return timed_update(m, o, true);
 }
 
 static int vs_eval_step(sert_model &m, const int32_t *x, const int32_t *y, const int32_t *neg,
@@ -326,7 +342,7 @@ static int ll_train_step(sert_model &m, const int32_t *x, const int64_t *indptr,
   m.step += 1;
   OptimArgs o = optim_args(m, loss_out);
   o.c0 = 1.0f; o.c1 = 0.95f; o.c2 = 0.f; o.c3 = 1e-6f;   // lasagne.updates.adadelta defaults
-  return launch_adadelta(o, st);
+  return timed_update(m, o, false);
 }
 
 static int ll_eval_step(sert_model &m, const int32_t *x, const int64_t *indptr, long long nnz_base,
@@ -441,6 +457,33 @@ int sert_model_set_step(sert_model *m, int64_t t) {
 int sert_model_get_step(sert_model *m, int64_t *t) {
   SERT_REQUIRE(m && t, "null argument");
   *t = m->step;
+  return 0;
+}
+
+int sert_model_profile(sert_model *m, int enable) {
+  SERT_REQUIRE(m, "null model");
+  m->profile = enable != 0;
+  return 0;
+}
+
+int sert_model_profile_read(sert_model *m, double *update_ms_total, int64_t *update_launches,
+                            double *update_bytes_per_launch) {
+  SERT_REQUIRE(m && update_ms_total && update_launches && update_bytes_per_launch, "null argument");
+  SERT_CUDA(cudaStreamSynchronize(m->st));
+  double tot = 0.0;
+  for (auto &ev : m->prof_events) {
+    float ms = 0.f;
+    SERT_CUDA(cudaEventElapsedTime(&ms, ev.first, ev.second));
+    tot += ms;
+    cudaEventDestroy(ev.first);
+    cudaEventDestroy(ev.second);
+  }
+  *update_ms_total = tot;
+  *update_launches = (int64_t)m->prof_events.size();
+  long long params = 0;
+  for (int w = 0; w < 4; ++w) params += m->cnt[w];
+  *update_bytes_per_launch = 24.0 * (double)params;   // read+write of theta and two state arrays, f32
+  m->prof_events.clear();
   return 0;
 }
 

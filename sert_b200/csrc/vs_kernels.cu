@@ -20,7 +20,10 @@ __global__ void __launch_bounds__(256) gather_pool_kernel(const int32_t *__restr
   const int lane = threadIdx.x & 31;
   if (warp >= B) return;
   const int32_t *xi = x + (size_t)warp * W;
-  for (int c = lane; c < d4; c += 32) {
+  // warp-uniform trip counts: every lane takes part in the index shuffles, loads are predicated
+  for (int c0 = 0; c0 < d4; c0 += 32) {
+    const int c = c0 + lane;
+    const bool active = c < d4;
     float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
     for (int w0 = 0; w0 < W; w0 += 32) {
       const int nw = min(32, W - w0);
@@ -28,12 +31,16 @@ __global__ void __launch_bounds__(256) gather_pool_kernel(const int32_t *__restr
 #pragma unroll 5
       for (int w = 0; w < nw; ++w) {
         const int r = __shfl_sync(0xffffffffu, idx, w);
-        const float4 v = __ldg(R + (size_t)r * d4 + c);
-        acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+        if (active) {
+          const float4 v = __ldg(R + (size_t)r * d4 + c);
+          acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+        }
       }
     }
-    acc.x /= denom; acc.y /= denom; acc.z /= denom; acc.w /= denom;
-    out[(size_t)warp * d4 + c] = acc;
+    if (active) {
+      acc.x /= denom; acc.y /= denom; acc.z /= denom; acc.w /= denom;
+      out[(size_t)warp * d4 + c] = acc;
+    }
   }
 }
 
@@ -86,12 +93,17 @@ __global__ void __launch_bounds__(256) scatter_rows_kernel(const int32_t *__rest
     const int nw = min(32, W - w0);
     const int idx = (lane < nw) ? __ldg(xi + w0 + lane) : 0;
     if (lane < nw) flagR[idx] = stamp;
-    for (int c = lane; c < d4; c += 32) {
-      float4 g = dh[(size_t)warp * d4 + c];
-      g.x /= denom; g.y /= denom; g.z /= denom; g.w /= denom;
+    for (int c0 = 0; c0 < d4; c0 += 32) {
+      const int c = c0 + lane;
+      const bool active = c < d4;
+      float4 g = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (active) {
+        g = dh[(size_t)warp * d4 + c];
+        g.x /= denom; g.y /= denom; g.z /= denom; g.w /= denom;
+      }
       for (int w = 0; w < nw; ++w) {
         const int r = __shfl_sync(0xffffffffu, idx, w);
-        red_add_f4(gR + ((size_t)r * d4 + c) * 4, g);
+        if (active) red_add_f4(gR + ((size_t)r * d4 + c) * 4, g);
       }
     }
   }

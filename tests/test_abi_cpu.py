@@ -1,0 +1,67 @@
+"""The C-ABI library loads without a GPU, exports every symbol the header declares, and fails loudly
+(never falls back) when asked to compute without a device."""
+import ctypes
+import os
+import re
+import subprocess
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def header_symbols():
+    text = open(os.path.join(ROOT, 'include', 'sert_b200.h')).read()
+    return sorted(set(re.findall(r'SERT_API[^;(]*?\b(sert_\w+)\s*\(', text)))
+
+
+def test_header_declares_and_library_exports_every_symbol(native_lib):
+    from sert_b200 import _native as N
+    declared = header_symbols()
+    assert len(declared) >= 25
+    assert sorted(N.SIGNATURES) == declared, 'ctypes table and header disagree'
+    out = subprocess.run(['nm', '-D', '--defined-only', N.LIB_PATH], stdout=subprocess.PIPE).stdout.decode()
+    exported = set(re.findall(r' T (sert_\w+)', out))
+    assert set(declared) <= exported
+    assert native_lib.sert_abi_version() == 1
+
+
+def test_arena_size_and_config_validation(native_lib):
+    from sert_b200 import _native as N
+    cfg = N.SertConfig(kind=N.KIND_VECTORSPACE, batch=4096, window=10, num_negatives=10, vocab=100000,
+                       entities=50000, word_dim=128, entity_dim=128, lambda_=0.01, loss_slots=1024, seed=1,
+                       entity_begin=0, entity_count=50000)
+    nbytes = N.c_size_t(0)
+    N.check(native_lib.sert_model_arena_bytes(ctypes.byref(cfg), ctypes.byref(nbytes)))
+    params = 100000 * 128 + 50000 * 128 + 128 * 128 + 128
+    assert 16 * params <= nbytes.value <= 16 * params + (64 << 20)    # theta, m, v, grad + workspaces
+    cfg.word_dim = 130                                                 # not a multiple of 4
+    with pytest.raises(RuntimeError, match='multiple of 4'):
+        N.check(native_lib.sert_model_arena_bytes(ctypes.byref(cfg), ctypes.byref(nbytes)))
+    cfg.word_dim, cfg.batch = 128, 0
+    with pytest.raises(RuntimeError, match='batch_size'):
+        N.check(native_lib.sert_model_arena_bytes(ctypes.byref(cfg), ctypes.byref(nbytes)))
+    sbytes = N.c_size_t(0)
+    N.check(native_lib.sert_scorer_arena_bytes(1000000, 256, 10000, 128, ctypes.byref(sbytes)))
+    assert sbytes.value >= 1000000 * 256 * 4
+
+
+def test_no_cpu_fallback_without_device(native_lib):
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip('a GPU is present')
+    from sert_b200 import models
+    import numpy as np
+    with pytest.raises(RuntimeError, match='CUDA device'):
+        models._NativeModel(0, 8, 2, 16, 4, 4)
+    from sert_b200.scoring import EntityScorer
+    with pytest.raises(RuntimeError, match='CUDA device'):
+        EntityScorer(np.zeros((4, 4), np.float32))
+
+
+def test_product_does_not_import_the_oracle():
+    for dirpath, _, files in os.walk(os.path.join(ROOT, 'sert_b200')):
+        for f in files:
+            if f.endswith(('.py', '.cu', '.cuh')):
+                text = open(os.path.join(dirpath, f)).read()
+                assert 'oracle' not in text.replace('the CPU oracle', ''), f
