@@ -169,6 +169,10 @@ SERT_API int sert_scorer_destroy(sert_scorer *s);
  * sorted by score descending (ties: lower row id first). */
 SERT_API int sert_scorer_topk_host(sert_scorer *s, const float *queries_host, int32_t q, int32_t normalise_q,
                           int32_t k, int32_t *out_idx_host, float *out_score_host);
+/* Dense scores (q, rows) of every query against every row of the shard, host in / host out: the
+ * "all entities" mode of VectorSpaceCallback.query (scipy cdist over all E, bin/query.py:310-318). */
+SERT_API int sert_scorer_scores_host(sert_scorer *s, const float *queries_host, int32_t q, int32_t normalise_q,
+                                     float *out_host);
 /* Same, device in / device out, asynchronous on the scorer's stream (used under NCCL sharding). */
 SERT_API int sert_scorer_topk_dev(sert_scorer *s, const float *queries_dev, int32_t q, int32_t normalise_q,
                          int32_t k, int32_t *out_idx_dev, float *out_score_dev);

@@ -12,6 +12,8 @@
 // broken by lower row id, so selection and the final order are deterministic.
 #include "score.cuh"
 
+#include "kernels.cuh"
+
 namespace sert {
 
 __device__ __forceinline__ unsigned int orderable(float f) {
@@ -374,6 +376,32 @@ int sert_scorer_topk_host(sert_scorer *s, const float *queries_host, int32_t q, 
   SERT_CUDA(cudaMemcpyAsync(out_score_host, s->out_score, (size_t)q * k * sizeof(float), cudaMemcpyDeviceToHost,
                             s->st));
   SERT_CUDA(cudaStreamSynchronize(s->st));
+  return 0;
+}
+
+int sert_scorer_scores_host(sert_scorer *s, const float *queries_host, int32_t q, int32_t normalise_q,
+                            float *out_host) {
+  SERT_REQUIRE(s && (queries_host || q == 0) && out_host, "null argument");
+  SERT_REQUIRE(s->s.rows < (1ll << 31), "too many rows");
+  const long long rows = s->s.rows;
+  if (q == 0 || rows == 0) return 0;
+  // the candidate buffer doubles as scratch for the dense (q_chunk, rows) score block
+  float *scratch = reinterpret_cast<float *>(s->s.cand);
+  const long long cap_floats = (long long)s->s.max_queries * s->s.cap * 2;
+  long long q_chunk = std::min<long long>(std::min<long long>(q, s->s.max_queries), cap_floats / rows);
+  SERT_REQUIRE(q_chunk >= 1, "scorer arena too small for a full score row; raise max_queries");
+  for (long long q0 = 0; q0 < q; q0 += q_chunk) {
+    const int n = (int)std::min<long long>(q_chunk, q - q0);
+    SERT_CUDA(cudaMemcpyAsync(s->queries, queries_host + q0 * s->s.d, (size_t)n * s->s.d * sizeof(float),
+                              cudaMemcpyHostToDevice, s->st));
+    if (normalise_q && launch_normalise_rows(s->queries, s->queries, n, s->s.d, s->st)) return -1;
+    if (launch_gemm_f32(s->queries, s->s.entities, scratch, n, (int)rows, s->s.d, false, true, s->s.d, s->s.d,
+                        (int)rows, EPI_STORE, nullptr, 1, s->st))
+      return -1;
+    SERT_CUDA(cudaMemcpyAsync(out_host + q0 * rows, scratch, (size_t)n * rows * sizeof(float),
+                              cudaMemcpyDeviceToHost, s->st));
+    SERT_CUDA(cudaStreamSynchronize(s->st));
+  }
   return 0;
 }
 

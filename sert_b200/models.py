@@ -451,7 +451,8 @@ class VectorSpacePredictFn(object):
         return out
 
     def __call__(self, avg_word_embedding):
-        return self.project(np.asarray(avg_word_embedding, dtype=np.float32).reshape(1, -1))[0]
+        # shape (1, de): the reference's DenseLayer adds b.dimshuffle('x', 0) to the (de,) product
+        return self.project(np.asarray(avg_word_embedding, dtype=np.float32).reshape(1, -1))
 
 
 class LanguageModel(LanguageModelBase):

@@ -1,0 +1,216 @@
+"""Ranking callbacks: drop-in for the callbacks of the reference's ``bin/query.py:165-382``.
+
+``LogLinearCallback`` is host arithmetic over the per-term distributions that the device ``predict_fn``
+returns (product of experts, renormalise, rank ALL entities; bin/query.py:204-233).
+
+``VectorSpaceCallback`` keeps the reference's observable behaviour (bin/query.py:241-367) but replaces
+the sklearn k-NN / scipy cdist search by the device scorer (``sert_b200.scoring``): the device returns the
+top-(k + margin) entities by float32 inner product of the L2-normalised vectors (== Euclidean k-NN
+order), the host then
+  1. re-selects the k nearest of those by exact float64 Euclidean distance (what sklearn's tree search
+     computes), in ascending-distance order,
+  2. recomputes every candidate's relevance exactly like the reference, ``(sum(e * q) + 1) / 2`` in
+     float32 with numpy's summation order (bin/query.py:351-357), and
+  3. orders them with Python's stable descending sort (bin/query.py:361-365).
+``process_many`` does this for all submitted queries with ONE scorer call.
+"""
+import collections
+import logging
+import operator
+
+import numpy as np
+
+from sert_b200 import inference, math_utils
+
+CANDIDATE_MARGIN = 28       # extra device candidates re-ranked on the host (fp32 near-ties at the k-th place)
+
+
+class Callback(object):
+
+    def __init__(self, args, model_args, tokens, f_debug_out, rank_callback):
+        self.args = args
+        self.model_args = model_args
+
+        self.tokens = tokens
+
+        self.f_debug_out = f_debug_out
+
+        self.rank_callback = rank_callback
+
+        self.topic_projections = {}
+
+    def _register(self, result, topic_id):
+        assert topic_id not in self.topic_projections
+        self.topic_projections[topic_id] = result.ravel()
+
+    def __call__(self, payload, result, topic_id):
+        self._register(result, topic_id)
+
+        logging.debug('Result of shape %s for topic "%s".', result.shape, topic_id)
+
+        self.process(payload, result, topic_id)
+
+    def process(self, payload, distribution, topic_id):
+        raise NotImplementedError()
+
+    def should_average_input(self):
+        raise NotImplementedError()
+
+
+class LogLinearCallback(Callback):
+
+    def process(self, payload, distribution, topic_id):
+        terms = [self.tokens[token_id] for token_id in payload]
+        term_entropies = compute_normalised_entropy(distribution, base=2)
+
+        distribution = inference.aggregate_distribution(distribution, mode='product', axis=0)
+        assert distribution.ndim == 1
+
+        distribution /= distribution.sum()
+
+        if not np.isclose(distribution.sum(), 1.0):
+            logging.error('Encountered non-normalized distribution for topic "%s" (mass=%.10f).',
+                          topic_id, distribution.sum())
+
+        self.f_debug_out.write('Topic {0} {1}: {2}\n'.format(
+            topic_id, math_utils.entropy(distribution, base=2, normalize=True), zip(terms, term_entropies)))
+
+        top_ranked_indices = np.argsort(distribution)[::-1]
+
+        self.rank_callback(topic_id, top_ranked_indices, distribution[top_ranked_indices])
+
+    def should_average_input(self):
+        return False
+
+
+class VectorSpaceCallback(Callback):
+
+    def __init__(self, entity_representations, *args, **kwargs):
+        scorer_factory = kwargs.pop('scorer_factory', None)
+        super(VectorSpaceCallback, self).__init__(*args, **kwargs)
+
+        logging.info('Initializing k-NN for entity representations of shape %s.', entity_representations.shape)
+
+        num_entities = entity_representations.shape[0]
+        n_neighbors = self.args.top
+
+        if n_neighbors is None:
+            logging.warning('Parameter k not set; defaulting to all entities (k=%d).', num_entities)
+        elif n_neighbors > num_entities:
+            logging.warning('Parameter k exceeds number of entities; defaulting to all entities (k=%d).',
+                            num_entities)
+            n_neighbors = None
+
+        # cosine similarity == Euclidean distance between L2-normalised vectors (bin/query.py:262-274)
+        self.entity_representation_distance = 'euclidean'
+        self.normalize_representations = True
+
+        entity_representations /= np.linalg.norm(entity_representations, axis=1)[:, np.newaxis]
+        logging.debug('Term projections will be normalized.')
+
+        self.entity_representations = entity_representations
+        self.n_neighbors = n_neighbors
+
+        if n_neighbors:
+            self.num_candidates = min(num_entities, n_neighbors + CANDIDATE_MARGIN)
+            self.entity_avg = entity_representations.mean(axis=1)
+            logging.info('Using %s as distance metric in entity space with the device top-k scorer '
+                         '(k=%d, %d candidates re-ranked on the host).',
+                         self.entity_representation_distance, n_neighbors, self.num_candidates)
+        else:
+            self.num_candidates = None
+            logging.info('Using %s as distance metric in entity space.', self.entity_representation_distance)
+
+        if scorer_factory is None:
+            from sert_b200.scoring import EntityScorer
+            scorer_factory = EntityScorer
+        self.scorer = scorer_factory(entity_representations, normalise=False, max_queries=1024,
+                                     max_k=max(self.num_candidates or 1, 1))
+        self.entity_neighbors = self.scorer if n_neighbors else None
+
+    # -- candidate search -------------------------------------------------------------------------
+    def query(self, centroids):
+        """(distances, indices) with the reference's meaning: per row, the k nearest entities by Euclidean
+        distance in ascending order (k = --top), or all entities when --top is unset (bin/query.py:304-318)."""
+        centroids = np.ascontiguousarray(centroids, dtype=np.float32)
+        E = self.entity_representations
+        if self.n_neighbors:
+            cand_idx, _ = self.scorer.topk(centroids, self.num_candidates)
+        else:
+            scores = self.scorer.scores(centroids)
+            cand_idx = np.argsort(-scores, axis=1, kind='stable')
+        k = self.n_neighbors or E.shape[0]
+        distances = np.empty((centroids.shape[0], k), dtype=np.float64)
+        indices = np.empty((centroids.shape[0], k), dtype=np.int64)
+        for row in range(centroids.shape[0]):
+            cands = cand_idx[row]
+            cands = cands[cands >= 0]
+            diff = E[cands].astype(np.float64) - centroids[row].astype(np.float64)
+            dist = np.sqrt(np.einsum('ij,ij->i', diff, diff))
+            order = np.argsort(dist, kind='stable')[:k]
+            indices[row, :len(order)] = cands[order]
+            distances[row, :len(order)] = dist[order]
+        return distances, indices
+
+    # -- ranking ----------------------------------------------------------------------------------
+    def _normalise(self, term_projections):
+        if term_projections.ndim == 1:
+            term_projections = term_projections.reshape(1, -1)
+
+        _, entity_representation_size = term_projections.shape
+        assert entity_representation_size == self.model_args.entity_representation_size
+
+        term_projections_l2_norm = np.linalg.norm(term_projections, axis=1)[:, np.newaxis]
+        term_projections /= term_projections_l2_norm
+        return term_projections
+
+    def _rank(self, term_projection, term_indices):
+        """Relevance of every candidate exactly as bin/query.py:344-365 computes it."""
+        E = self.entity_representations
+        matching_scores = (E[term_indices, :] * term_projection).sum(axis=1)      # == np.sum(e * q) per row
+        matching_scores = (matching_scores + 1.0) / 2.0
+        candidates = collections.defaultdict(float)
+        for candidate, matching_score in zip(term_indices.tolist(), matching_scores):
+            candidates[candidate] += matching_score
+        top_ranked_indices, top_ranked_values = map(np.array, zip(
+            *sorted(candidates.items(), reverse=True, key=operator.itemgetter(1))))
+        return top_ranked_indices, top_ranked_values
+
+    def process(self, payload, result, topic_id):
+        terms = [self.tokens[token_id] for token_id in payload]
+
+        term_projections = self._normalise(inference.aggregate_distribution(result, mode='identity', axis=0))
+
+        logging.debug('Querying kneighbors for %s.', terms)
+
+        distances, indices = self.query(term_projections)
+
+        assert indices.shape[0] == term_projections.shape[0]
+        assert indices.shape[0] == 1
+
+        top_ranked_indices, top_ranked_values = self._rank(term_projections[0, :], indices[0, :])
+
+        self.rank_callback(topic_id, top_ranked_indices, top_ranked_values)
+
+    def process_many(self, payloads, projections, kwargs_list):
+        """All submitted queries with one device scorer call (EmbeddingMapper.process)."""
+        projections = np.array(projections, dtype=np.float32, copy=True)
+        for projection, kwargs in zip(projections, kwargs_list):
+            self._register(projection, kwargs['topic_id'])
+        projections = self._normalise(projections)
+        _, indices = self.query(projections)
+        for row, kwargs in enumerate(kwargs_list):
+            top_ranked_indices, top_ranked_values = self._rank(projections[row, :], indices[row, :])
+            self.rank_callback(kwargs['topic_id'], top_ranked_indices, top_ranked_values)
+
+    def should_average_input(self):
+        return True
+
+
+def compute_normalised_entropy(distribution, base=2):
+    assert distribution.ndim == 2
+
+    assert np.allclose(distribution.sum(axis=1), 1.0)
+
+    return [math_utils.entropy(distribution[i, :], base=base, normalize=True)
+            for i in range(distribution.shape[0])]

@@ -66,6 +66,15 @@ class EntityScorer(object):
             done += n
         return idx, score
 
+    def scores(self, queries, normalise_queries=False):
+        """Dense (Q, rows) float32 inner products (the "rank all entities" mode)."""
+        queries = np.ascontiguousarray(queries, dtype=np.float32)
+        assert queries.ndim == 2 and queries.shape[1] == self.d
+        out = np.empty((queries.shape[0], self.rows), dtype=np.float32)
+        N.check(self.lib.sert_scorer_scores_host(self.handle, N.host_ptr(queries), queries.shape[0],
+                                                 int(bool(normalise_queries)), N.host_ptr(out)))
+        return out
+
     def topk_dev(self, queries_dev, k, normalise_queries=False):
         """Device in / device out, asynchronous on the scorer's stream."""
         torch = _torch()

@@ -1,0 +1,206 @@
+"""Pins the oracle and the host-side mirrors to fixtures produced by the reference's OWN code
+(sert/models.py under the Theano/Lasagne shim, sert/inference.py, bin/query.py callbacks, bin/train.py,
+cvangysel trec_utils) -- see tests/golden/make_golden.py."""
+import io
+
+import numpy as np
+import pytest
+
+from oracle import sert_oracle as O
+from tests import golden_io as G
+from tests.helpers import close
+
+
+def assert_mean_std(got, ref, rtol=5e-6):
+    """(mean, std) over batches: the std of nearly equal float32 losses only carries absolute precision."""
+    np.testing.assert_allclose(got[0], ref[0], rtol=rtol)
+    np.testing.assert_allclose(got[1], ref[1], rtol=1e-3, atol=2e-6 * abs(ref[0]))
+
+
+class NumpyScorer(object):
+    """Test-side stand-in for sert_b200.scoring.EntityScorer (exact float32 inner products on the host) so the
+    host logic of VectorSpaceCallback can be checked without a GPU."""
+
+    def __init__(self, entities, normalise=False, max_queries=1024, max_k=128, row_begin=0):
+        self.E = np.asarray(entities, dtype=np.float32)
+
+    def scores(self, queries):
+        return (queries.astype(np.float32) @ self.E.T).astype(np.float32)
+
+    def topk(self, queries, k):
+        s = self.scores(queries)
+        idx = np.argsort(-s, axis=1, kind='stable')[:, :k]
+        return idx.astype(np.int32), np.take_along_axis(s, idx, axis=1)
+
+
+def test_oracle_matches_reference_loglinear_model():
+    d = G.loglinear()
+    orc = O.LogLinearOracle(int(d['B']), d['R0'], d['Wd0'], d['bd0'], float(d['lam']), d['training_set'],
+                            d['validation_set'])
+    assert_mean_std(orc.error('train'), d['train_error0'])
+    assert_mean_std(orc.error('val'), d['validation_error0'])
+    losses = [orc.train_batch(int(b)) for b in d['order']]
+    np.testing.assert_allclose(losses, d['train_losses'], rtol=2e-6)
+    close(orc.R, d['R1'], rtol=1e-5, what='R after 6 Adadelta steps')
+    close(orc.Wd, d['Wd1'], rtol=1e-5, what='Wd')
+    close(orc.bd, d['bd1'], rtol=1e-5, atol_scale=1e-5, what='bd')
+    assert_mean_std(orc.error('train'), d['train_error1'])
+    assert_mean_std(orc.error('val'), d['validation_error1'])
+    close(O.loglinear_predict(orc.R, orc.Wd, orc.bd, d['predict_batch']), d['predict_out'], rtol=1e-5,
+          what='predict_fn')
+
+
+def test_oracle_matches_reference_vectorspace_model():
+    d = G.vectorspace()
+    orc = O.VectorSpaceOracle(int(d['B']), d['R0'], d['Wp0'], d['bp0'], d['E0'], float(d['lam']),
+                              d['training_set'], d['validation_set'])
+    got = [orc.eval_batch('train', b, d['test_negs0'][b]) for b in range(6)]
+    np.testing.assert_allclose(got, d['test_losses0'], rtol=2e-6)
+    got = [orc.eval_batch('val', b, d['val_negs0'][b]) for b in range(2)]
+    np.testing.assert_allclose(got, d['val_losses0'], rtol=2e-6)
+    losses = [orc.train_batch(int(b), d['train_negs'][j]) for j, b in enumerate(d['order'])]
+    np.testing.assert_allclose(losses, d['train_losses'], rtol=2e-6)
+    for name, ref in (('R', 'R1'), ('Wp', 'Wp1'), ('Eemb', 'E1')):
+        close(getattr(orc, name), d[ref], rtol=1e-5, what=name)
+    close(orc.bp, d['bp1'], rtol=1e-5, atol_scale=1e-5, what='bp')
+    got = [orc.eval_batch('train', b, d['test_negs1'][b]) for b in range(6)]
+    np.testing.assert_allclose(got, d['test_losses1'], rtol=5e-6)
+    for avg, ref in zip(d['predict_in'], d['predict_out']):
+        assert ref.shape == (1, int(d['de']))            # DenseLayer adds b.dimshuffle('x', 0)
+        close(O.vectorspace_predict(d['Wp1'], d['bp1'], avg), ref[0], rtol=1e-5, what='predict_fn')
+
+
+def test_inference_mirror_matches_reference_batcher():
+    from sert_b200 import inference, math_utils
+    d = G.load_json('inference_ref.json')
+    table = np.asarray(d['table'], dtype=np.float32)
+    calls = []
+
+    class Recorder(object):
+        def __call__(self, payload, result, **kwargs):
+            calls.append((list(payload), np.asarray(result), kwargs))
+
+        def should_average_input(self):
+            return False
+
+    batcher = inference.create(lambda batch, mask: table[batch.astype(np.int64)], None, d['B'], d['W'], d['V'],
+                               Recorder())
+    assert str(batcher.batch.dtype) == d['instance_dtype'] and batcher.mask.dtype == np.int8
+    for i, q in enumerate(d['queries']):
+        batcher.submit(list(q), topic_id='T%d' % i)
+    batcher.process()
+    assert len(calls) == len(d['calls'])
+    for (payload, result, kwargs), ref in zip(calls, d['calls']):
+        assert payload == ref['payload'] and kwargs == ref['kwargs']
+        np.testing.assert_array_equal(result, np.asarray(ref['result'], dtype=np.float32))
+    with pytest.raises(RuntimeError):
+        batcher.submit(list(range(13)), topic_id='X')
+    dist = np.asarray(d['dist'], dtype=np.float32)
+    for mode, ref in d['aggregate'].items():
+        np.testing.assert_array_equal(np.asarray(inference.aggregate_distribution(dist, mode, 0)),
+                                      np.asarray(ref, dtype=np.asarray(inference.aggregate_distribution(dist, mode, 0)).dtype))
+    pk = np.asarray(d['pk'])
+    assert math_utils.entropy(pk) == d['entropy']['plain']
+    assert math_utils.entropy(pk, base=2, normalize=True) == d['entropy']['base2_norm']
+    assert math_utils.entropy(pk, normalize=True) == d['entropy']['norm']
+
+
+def test_embedding_mapper_batches_but_keeps_order():
+    from sert_b200 import inference
+    rng = np.random.default_rng(0)
+    R = rng.standard_normal((20, 6)).astype(np.float32)
+    Wp = rng.standard_normal((6, 4)).astype(np.float32)
+    seen = []
+
+    class Cb(object):
+        def __call__(self, payload, result, **kw):
+            seen.append((payload, result, kw['topic_id']))
+
+        def should_average_input(self):
+            return True
+
+    mapper = inference.create(lambda avg: np.tanh(avg @ Wp), R, 8, 3, 20, Cb())
+    qs = [[1, 2, 3], [4], [5, 6]]
+    for i, q in enumerate(qs):
+        mapper.submit(q, topic_id=i)
+    mapper.process()
+    assert [s[2] for s in seen] == [0, 1, 2]
+    for (payload, result, _), q in zip(seen, qs):
+        np.testing.assert_allclose(result, np.tanh(R[q].mean(axis=0) @ Wp), rtol=1e-6)
+
+
+def test_trec_shim_matches_reference():
+    from cvangysel import trec_utils
+    d = G.load_json('trec_ref.json')
+    for q, ref in zip(d['queries'], d['parsed']):
+        assert trec_utils.parse_query(q) == ref, q
+    topics = trec_utils.parse_topics([io.StringIO(d['topics_text'])])
+    assert [list(kv) for kv in topics.items()] == d['topics']
+    data = {'t1': [(np.float32(0.5), 'a'), (np.float32(0.5), 'b'), (np.float32(0.75), 'c'), (np.float32(0.25), 'd')],
+            't2': [(0.125, 'x10'), (0.125, 'x9'), (0.5, 'y')], 't3': []}
+    buf = io.StringIO()
+    trec_utils.write_run('model_1.bin', data, buf)
+    assert buf.getvalue() == d['run_text']
+    # ties break on the id string, descending (sub:trec_utils.py:560-561)
+    assert O.write_run_order([(0.5, 'a'), (0.5, 'b')]) == [(0.5, 'b'), (0.5, 'a')]
+
+
+def test_one_hot_expansion_matches_reference():
+    from sert_b200.synth import sparse_to_one_hot_multiple
+    d = G.load_npz('one_hot_ref.npz')
+    y = G.csr(d, 'y')
+    new_y, (new_x, new_w) = sparse_to_one_hot_multiple(y, d['x'], d['w'])
+    np.testing.assert_array_equal(new_y, d['new_y'])
+    assert new_y.dtype == np.int32 and new_x.dtype == d['new_x'].dtype
+    np.testing.assert_array_equal(new_x, d['new_x'])
+    np.testing.assert_array_equal(new_w, d['new_w'])
+    bad = y.tolil()
+    bad[3, :] = 0
+    with pytest.raises(RuntimeError):
+        sparse_to_one_hot_multiple(bad.tocsr(), d['x'], d['w'])
+
+
+def _run_callbacks(scorer_factory):
+    from sert_b200 import ranking
+    d = G.load_npz('query_ref.npz')
+
+    class Args(object):
+        top = 10
+
+    class ModelArgs(object):
+        entity_representation_size = 12
+
+    tokens = ['w%d' % i for i in range(30)]
+    ranked = {}
+    sink = lambda topic_id, idx, val: ranked.__setitem__(topic_id, (np.asarray(idx), np.asarray(val)))  # noqa: E731
+    debug = io.StringIO()
+    cb = ranking.LogLinearCallback(Args(), ModelArgs(), tokens, debug, sink)
+    for i in range(3):
+        dist = d['ll_dist%d' % i]
+        cb(list(range(dist.shape[0])), dist.copy(), topic_id='L%d' % i)
+        np.testing.assert_array_equal(ranked['L%d' % i][0], d['ll_idx%d' % i])
+        np.testing.assert_array_equal(ranked['L%d' % i][1], d['ll_val%d' % i])
+        idx, val = O.loglinear_rank(dist)
+        np.testing.assert_array_equal(idx, d['ll_idx%d' % i])
+    assert debug.getvalue().split(': <zip')[0] == str(d['ll_debug']).split(': <zip')[0]
+    for name, top in (('top10', 10), ('all', None)):
+        Args.top = top
+        ranked.clear()
+        cbv = ranking.VectorSpaceCallback(d['entities'].copy(), Args(), ModelArgs(), tokens, io.StringIO(), sink,
+                                          scorer_factory=scorer_factory)
+        # half through the reference's per-query path, half through the batched path
+        for i in range(4):
+            p = d['projections'][i]
+            cbv([1, 2], p.copy().reshape(1, -1) if i % 2 else p.copy(), topic_id='V%d' % i)
+        cbv.process_many([[1, 2]] * 4, d['projections'][4:].copy(), [{'topic_id': 'V%d' % i} for i in range(4, 8)])
+        for i in range(8):
+            np.testing.assert_array_equal(ranked['V%d' % i][0], d[name + '_idx'][i])      # ranked lists identical
+            np.testing.assert_array_equal(ranked['V%d' % i][1], d[name + '_val'][i])
+            assert str(ranked['V%d' % i][1].dtype) == str(d[name + '_val_dtype'])
+        E = O.normalise_rows(d['entities'])
+        idx, val = O.vectorspace_rank(E, d['projections'][0], top=top)
+        np.testing.assert_array_equal(idx, d[name + '_idx'][0])
+
+
+def test_ranking_callbacks_match_reference_on_host():
+    _run_callbacks(NumpyScorer)

@@ -134,4 +134,6 @@ def test_predict_fn_matches_oracle_and_pickles():
     rng = np.random.default_rng(0)
     for _ in range(3):
         avg = p['R'][rng.integers(0, 300, 5)].mean(axis=0)
-        H.close(fn(avg), O.vectorspace_predict(p['Wp'], p['bp'], avg), what='predict_fn')
+        out = fn(avg)
+        assert out.shape == (1, 128)
+        H.close(out[0], O.vectorspace_predict(p['Wp'], p['bp'], avg), what='predict_fn')
