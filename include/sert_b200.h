@@ -180,6 +180,12 @@ SERT_API int sert_scorer_topk_dev(sert_scorer *s, const float *queries_dev, int3
 SERT_API int sert_topk_merge_dev(const int32_t *idx_dev, const float *score_dev, int32_t parts, int32_t q, int32_t k,
                         int32_t *out_idx_dev, float *out_score_dev, void *stream);
 
+/* ---- test hook -------------------------------------------------------------------------------- */
+/* C (m,n) = A (m,k) . B (n,k)^T (+ bias (n,)) through the tcgen05/TMEM/TMA GEMM with `terms` (1 or 3) bf16
+ * split terms per operand; host in / host out.  Used by tests/test_gpu_gemm_tc.py only. */
+SERT_API int sert_debug_gemm_tc(const float *a_host, const float *b_host, int m, int n, int k, int terms,
+                                const float *bias_host, float *c_host);
+
 #ifdef __cplusplus
 }
 #endif

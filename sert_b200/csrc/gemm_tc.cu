@@ -1,0 +1,441 @@
+// tcgen05 (5th-gen tensor core) GEMM with TMEM accumulators and TMA operand staging; see gemm_tc.cuh.
+//
+// Kernel anatomy (one persistent CTA per SM, 192 threads):
+//   warp 0   TMA producer: cp.async.bulk.tensor 2D loads of the A (128 x 64) and B (256 x 64) bf16 tiles
+//            into a 4-stage 128B-swizzled shared-memory ring, completion via mbarrier expect_tx
+//   warp 1   allocates all 512 TMEM columns (two 128 x 256 fp32 accumulators), then one elected lane
+//            issues tcgen05.mma.cta_group::1.kind::f16 (M=128, N=256, K=16) x 4 per stage and
+//            tcgen05.commit's the stage's "empty" barrier / the accumulator's "full" barrier
+//   warps 2-5 epilogue: tcgen05.ld 32x32b.x32 of their 32-lane quarter, then either fp32 stores (+bias)
+//            or the running top-k filter; double-buffered against the next tile's MMAs
+#include <cuda.h>
+
+#include "gemm_tc.cuh"
+#include "topk_keys.cuh"
+
+namespace sert {
+
+namespace {
+
+constexpr int BM = 128, BN = 256, BK = 64, STAGES = 4, UMMA_K = 16;
+constexpr uint32_t A_STAGE_BYTES = BM * BK * 2;   // 16 KB
+constexpr uint32_t B_STAGE_BYTES = BN * BK * 2;   // 32 KB
+constexpr uint32_t STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
+constexpr int NUM_THREADS = 192;
+constexpr uint32_t TMEM_COLS = 512;
+constexpr size_t SMEM_BYTES = 1024 /*align slack*/ + (size_t)STAGES * STAGE_BYTES + 256 /*barriers*/;
+
+struct alignas(64) TcMap {
+  unsigned char bytes[128];
+};
+
+struct KernelArgs {
+  int M;
+  long long n_begin, n_end;
+  int num_kb;          // Kt / 64
+  TcEpilogue epi;
+};
+
+// ---- PTX wrappers -----------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t done;
+  do {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(bar), "r"(parity)
+        : "memory");
+  } while (!done);
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void tma_prefetch_desc(const void *map) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const void *map, uint32_t bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_alloc(uint32_t smem_result, uint32_t cols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_result), "r"(cols)
+               : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tc_dealloc(uint32_t taddr, uint32_t cols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(cols) : "memory");
+}
+// D[tmem] (+)= A[smem] . B[smem]^T, bf16 inputs, fp32 accumulate
+__device__ __forceinline__ void tc_mma_bf16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
+                                            uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// arrive on an mbarrier when all previously issued tcgen05.mma of this thread have completed
+__device__ __forceinline__ void tc_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tc_ld_32x32(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tc_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// Shared-memory matrix descriptor of a K-major bf16 tile stored as rows of 64 elements (128 bytes) with the
+// 128-byte swizzle TMA wrote: start address >> 4 [0,14), LBO = 1 (unused for swizzled K-major) [16,30),
+// SBO = 1024 bytes (8 rows x 128 B) >> 4 [32,46), descriptor version 1 [46,48), layout SWIZZLE_128B = 2 [61,64).
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr & 0x3ffffu) >> 4);
+  d |= (uint64_t)1 << 16;
+  d |= (uint64_t)(1024 >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+// Instruction descriptor (kind::f16): D fp32 (bits 4-5 = 1), A/B bf16 (bits 7-9, 10-12 = 1), both K-major,
+// N >> 3 at [17,23), M >> 4 at [24,29).
+constexpr uint32_t make_idesc(int m, int n) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
+}
+
+// ---- the kernel -----------------------------------------------------------------------------------
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+gemm_tc_kernel(const __grid_constant__ TcMap map_a, const __grid_constant__ TcMap map_b, const KernelArgs args) {
+  extern __shared__ unsigned char smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;   // SWIZZLE_128B needs 1024-byte alignment
+  const uint32_t smem_a = smem_base;
+  const uint32_t smem_b = smem_base + STAGES * A_STAGE_BYTES;
+  const uint32_t bars = smem_base + STAGES * STAGE_BYTES;
+  // barrier layout (8 bytes each): full[STAGES], empty[STAGES], tmem_full[2], tmem_empty[2], then tmem ptr
+  auto full_bar = [&](int s) { return bars + 8u * s; };
+  auto empty_bar = [&](int s) { return bars + 8u * (STAGES + s); };
+  auto tfull_bar = [&](int a) { return bars + 8u * (2 * STAGES + a); };
+  auto tempty_bar = [&](int a) { return bars + 8u * (2 * STAGES + 2 + a); };
+  const uint32_t tmem_ptr_smem = bars + 8u * (2 * STAGES + 4);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  const int num_m_tiles = (args.M + BM - 1) / BM;
+  const int num_n_tiles = (int)((args.n_end - args.n_begin + BN - 1) / BN);
+  const int num_tiles = num_m_tiles * num_n_tiles;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&map_a);
+    tma_prefetch_desc(&map_b);
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(full_bar(s), 1);
+      mbar_init(empty_bar(s), 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(tfull_bar(a), 1);
+      mbar_init(tempty_bar(a), 4);     // one arrive per epilogue warp
+    }
+    fence_barrier_init();
+  }
+  if (warp == 1) tc_alloc(tmem_ptr_smem, TMEM_COLS);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  uint32_t tmem_base;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_ptr_smem));
+
+  if (warp == 0) {
+    // ================= TMA producer =================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+        const int m0 = (t % num_m_tiles) * BM;
+        const int n0 = (int)(args.n_begin + (long long)(t / num_m_tiles) * BN);
+        for (int kb = 0; kb < args.num_kb; ++kb) {
+          mbar_wait(empty_bar(stage), phase ^ 1u);
+          mbar_expect_tx(full_bar(stage), STAGE_BYTES);
+          tma_load_2d(smem_a + stage * A_STAGE_BYTES, &map_a, full_bar(stage), kb * BK, m0);
+          tma_load_2d(smem_b + stage * B_STAGE_BYTES, &map_b, full_bar(stage), kb * BK, n0);
+          if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ================= MMA issuer =================
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc(BM, BN);
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+        mbar_wait(tempty_bar(acc), acc_phase ^ 1u);      // epilogue has drained this accumulator
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + (uint32_t)acc * BN;
+        for (int kb = 0; kb < args.num_kb; ++kb) {
+          mbar_wait(full_bar(stage), phase);             // TMA bytes have landed
+          tc_fence_after();
+          const uint32_t a_addr = smem_a + stage * A_STAGE_BYTES;
+          const uint32_t b_addr = smem_b + stage * B_STAGE_BYTES;
+#pragma unroll
+          for (int k = 0; k < BK / UMMA_K; ++k) {
+            // advancing K by 16 bf16 = 32 bytes inside the 128-byte swizzled row
+            tc_mma_bf16(d_tmem, make_smem_desc(a_addr + k * UMMA_K * 2), make_smem_desc(b_addr + k * UMMA_K * 2),
+                        idesc, (kb | k) != 0 ? 1u : 0u);
+          }
+          tc_commit(empty_bar(stage));                   // frees the smem slot once those MMAs retire
+          if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+        }
+        tc_commit(tfull_bar(acc));                       // accumulator complete -> epilogue
+        if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+      }
+    }
+  } else {
+    // ================= epilogue (warps 2..5) =================
+    const int quarter = warp & 3;                        // a warp may only touch TMEM lanes [32*(warp%4), +32)
+    const int row = quarter * 32 + lane;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    const TcEpilogue &ep = args.epi;
+    for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+      const int m0 = (t % num_m_tiles) * BM;
+      const long long n0 = args.n_begin + (long long)(t / num_m_tiles) * BN;
+      const int gm = m0 + row;
+      const bool row_ok = gm < args.M;
+      unsigned long long tau_key = ~0ull;
+      float tau_score = INFINITY;
+      if (ep.mode == TC_EPI_TOPK && row_ok) {
+        tau_key = ep.tau[gm];
+        tau_score = tau_key == 0ull ? -INFINITY : key_score(tau_key);
+      }
+      mbar_wait(tfull_bar(acc), acc_phase);
+      tc_fence_after();
+      const uint32_t t_row = tmem_base + (uint32_t)acc * BN + ((uint32_t)(quarter * 32) << 16);
+#pragma unroll 1
+      for (int c0 = 0; c0 < BN; c0 += 32) {
+        uint32_t v[32];
+        tc_ld_32x32(t_row + (uint32_t)c0, v);
+        tc_wait_ld();
+        const long long gn0 = n0 + c0;
+        if (ep.mode == TC_EPI_STORE) {
+          if (row_ok && gn0 < args.n_end) {
+            float *dst = ep.C + (long long)gm * ep.ldc + gn0;
+            const bool full = (gn0 + 32 <= args.n_end) && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0);
+            if (full) {
+#pragma unroll
+              for (int j = 0; j < 32; j += 4) {
+                float4 o = make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]), __uint_as_float(v[j + 2]),
+                                       __uint_as_float(v[j + 3]));
+                if (ep.bias != nullptr) {
+                  o.x += ep.bias[gn0 + j]; o.y += ep.bias[gn0 + j + 1];
+                  o.z += ep.bias[gn0 + j + 2]; o.w += ep.bias[gn0 + j + 3];
+                }
+                *reinterpret_cast<float4 *>(dst + j) = o;
+              }
+            } else {
+#pragma unroll
+              for (int j = 0; j < 32; ++j)
+                if (gn0 + j < args.n_end)
+                  dst[j] = __uint_as_float(v[j]) + (ep.bias != nullptr ? ep.bias[gn0 + j] : 0.f);
+            }
+          }
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            const float sc = __uint_as_float(v[j]);
+            if (sc >= tau_score && gn0 + j < args.n_end) {          // rare once tau has warmed up
+              const unsigned long long key = make_key(sc, (unsigned int)(gn0 + j + ep.row_offset));
+              if (key > tau_key) {
+                const int pos = atomicAdd(ep.count + gm, 1);
+                if (pos < ep.cap) ep.cand[(size_t)gm * ep.cap + pos] = key;
+              }
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(tempty_bar(acc));
+      if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tc_dealloc(tmem_base, TMEM_COLS);
+  }
+}
+
+// ---- host side ----------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                  const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+int get_encode_fn(EncodeTiledFn *out) {
+  static EncodeTiledFn fn = nullptr;
+  if (fn == nullptr) {
+    void *p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    SERT_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres));
+    SERT_REQUIRE(p != nullptr && qres == cudaDriverEntryPointSuccess, "cuTensorMapEncodeTiled is not available");
+    fn = reinterpret_cast<EncodeTiledFn>(p);
+  }
+  *out = fn;
+  return 0;
+}
+
+// 2-D bf16 tensor (rows, Kt) row-major; box = (64 elements of K) x box_rows, 128-byte swizzle, zero OOB fill.
+int make_map(const __nv_bfloat16 *base, long long rows, int Kt, int box_rows, TcMap *out) {
+  static_assert(sizeof(CUtensorMap) <= sizeof(TcMap), "CUtensorMap does not fit");
+  EncodeTiledFn encode;
+  if (get_encode_fn(&encode)) return -1;
+  SERT_REQUIRE((reinterpret_cast<uintptr_t>(base) & 15) == 0, "tensor-map base must be 16-byte aligned");
+  SERT_REQUIRE(Kt % BK == 0, "K must be padded to a multiple of 64");
+  const cuuint64_t gdim[2] = {(cuuint64_t)Kt, (cuuint64_t)std::max<long long>(rows, 1)};
+  const cuuint64_t gstride[1] = {(cuuint64_t)Kt * sizeof(__nv_bfloat16)};
+  const cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)box_rows};
+  const cuuint32_t estride[2] = {1, 1};
+  const CUresult r = encode(reinterpret_cast<CUtensorMap *>(out->bytes), CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2,
+                            const_cast<__nv_bfloat16 *>(base), gdim, gstride, box, estride,
+                            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                            CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  SERT_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed");
+  return 0;
+}
+
+}  // namespace
+
+int launch_gemm_tc(const __nv_bfloat16 *A, int M, const __nv_bfloat16 *B, long long N_total, long long n_begin,
+                   long long n_end, int Kt, const TcEpilogue &epi, cudaStream_t st) {
+  if (M == 0 || n_end <= n_begin) return 0;
+  SERT_REQUIRE(n_begin >= 0 && n_end <= N_total && N_total < (1ll << 31), "bad column range");
+  SERT_REQUIRE(Kt > 0 && Kt % BK == 0, "K must be a positive multiple of 64");
+  TcMap ma, mb;
+  if (make_map(A, M, Kt, BM, &ma)) return -1;
+  if (make_map(B, N_total, Kt, BN, &mb)) return -1;
+  static bool configured = false;
+  static int sms = kNumSMs;
+  if (!configured) {
+    SERT_CUDA(cudaFuncSetAttribute(gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
+    int dev = 0;
+    SERT_CUDA(cudaGetDevice(&dev));
+    SERT_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    configured = true;
+  }
+  KernelArgs args;
+  args.M = M;
+  args.n_begin = n_begin;
+  args.n_end = n_end;
+  args.num_kb = Kt / BK;
+  args.epi = epi;
+  const long long tiles = (long long)((M + BM - 1) / BM) * ((n_end - n_begin + BN - 1) / BN);
+  const int grid = (int)std::min<long long>(tiles, sms);
+  gemm_tc_kernel<<<grid, NUM_THREADS, SMEM_BYTES, st>>>(ma, mb, args);
+  SERT_LAUNCH_CHECK();
+  return 0;
+}
+
+// ---- fp32 -> bf16 split operand (see gemm_tc.cuh) --------------------------------------------------
+__global__ void __launch_bounds__(256) split_bf16_kernel(const float *__restrict__ src, long long rows, int K,
+                                                         long long ld_src, int Kp, int terms, int role,
+                                                         __nv_bfloat16 *__restrict__ dst) {
+  const long long total = rows * Kp;
+  const long long ld_dst = (long long)terms * Kp;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const long long r = i / Kp;
+    const int k = (int)(i - r * Kp);
+    const float x = k < K ? src[r * ld_src + k] : 0.f;
+    const __nv_bfloat16 hi = __float2bfloat16_rn(x);
+    __nv_bfloat16 *d = dst + r * ld_dst + k;
+    if (terms == 1) {
+      d[0] = hi;
+    } else {
+      const __nv_bfloat16 mid = __float2bfloat16_rn(x - __bfloat162float(hi));
+      // A'' = [hi | hi | mid],  B'' = [hi | mid | hi]
+      d[0] = hi;
+      d[Kp] = role == SPLIT_A ? hi : mid;
+      d[2 * (long long)Kp] = role == SPLIT_A ? mid : hi;
+    }
+  }
+}
+
+int launch_split_bf16(const float *src, long long rows, int K, long long ld_src, int terms, SplitRole role,
+                      __nv_bfloat16 *dst, cudaStream_t st) {
+  SERT_REQUIRE(terms == 1 || terms == 3, "split terms must be 1 or 3");
+  if (rows == 0) return 0;
+  const int Kp = tc_padded_k(K);
+  const long long total = rows * Kp;
+  const int blocks = (int)std::min<long long>((total + 255) / 256, (long long)kNumSMs * 16);
+  split_bf16_kernel<<<blocks, 256, 0, st>>>(src, rows, K, ld_src, Kp, terms, (int)role, dst);
+  SERT_LAUNCH_CHECK();
+  return 0;
+}
+
+}  // namespace sert
+
+// ---- test hook: C = A . B^T through the tcgen05 path, host in / host out ----------------------------
+extern "C" SERT_API int sert_debug_gemm_tc(const float *a_host, const float *b_host, int m, int n, int k, int terms,
+                                           const float *bias_host, float *c_host) {
+  using namespace sert;
+  SERT_REQUIRE(a_host && b_host && c_host && m > 0 && n > 0 && k > 0, "bad argument");
+  const int Kp = tc_padded_k(k);
+  const int Kt = terms * Kp;
+  float *dA = nullptr, *dB = nullptr, *dC = nullptr, *dbias = nullptr;
+  __nv_bfloat16 *sA = nullptr, *sB = nullptr;
+  SERT_CUDA(cudaMalloc(&dA, (size_t)m * k * 4));
+  SERT_CUDA(cudaMalloc(&dB, (size_t)n * k * 4));
+  SERT_CUDA(cudaMalloc(&dC, (size_t)m * n * 4));
+  SERT_CUDA(cudaMalloc(&sA, (size_t)m * Kt * 2));
+  SERT_CUDA(cudaMalloc(&sB, (size_t)n * Kt * 2));
+  SERT_CUDA(cudaMemcpy(dA, a_host, (size_t)m * k * 4, cudaMemcpyHostToDevice));
+  SERT_CUDA(cudaMemcpy(dB, b_host, (size_t)n * k * 4, cudaMemcpyHostToDevice));
+  SERT_CUDA(cudaMemset(dC, 0xff, (size_t)m * n * 4));
+  if (bias_host) {
+    SERT_CUDA(cudaMalloc(&dbias, (size_t)n * 4));
+    SERT_CUDA(cudaMemcpy(dbias, bias_host, (size_t)n * 4, cudaMemcpyHostToDevice));
+  }
+  int rc = launch_split_bf16(dA, m, k, k, terms, SPLIT_A, sA, nullptr);
+  if (!rc) rc = launch_split_bf16(dB, n, k, k, terms, SPLIT_B, sB, nullptr);
+  TcEpilogue ep;
+  ep.mode = TC_EPI_STORE;
+  ep.C = dC;
+  ep.ldc = n;
+  ep.bias = dbias;
+  if (!rc) rc = launch_gemm_tc(sA, m, sB, n, 0, n, Kt, ep, nullptr);
+  cudaError_t e = cudaDeviceSynchronize();
+  if (!rc && e != cudaSuccess) {
+    set_error(std::string("gemm_tc: ") + cudaGetErrorString(e));
+    rc = -1;
+  }
+  if (!rc) SERT_CUDA(cudaMemcpy(c_host, dC, (size_t)m * n * 4, cudaMemcpyDeviceToHost));
+  cudaFree(dA); cudaFree(dB); cudaFree(dC); cudaFree(sA); cudaFree(sB); cudaFree(dbias);
+  return rc;
+}

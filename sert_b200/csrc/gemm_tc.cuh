@@ -1,0 +1,46 @@
+// tcgen05 / TMEM / TMA GEMM for the two tensor-core-shaped ops of the SERT hot path:
+//   * the query x all-entities scoring GEMM (bin/query.py:304-318 replaced; epilogue = running top-k filter)
+//   * the word x entity projection GEMM of the log-linear model (sert/models.py:846-849) and its gradients.
+// C[M,N] (f32) = A[M,K'] . B[N,K']^T with bf16 operands, both K-major ("TN"), fp32 accumulation in TMEM.
+// fp32 accuracy comes from a 3-term bf16 split of each operand laid out along K (split_bf16 below):
+//   A'' = [A_hi | A_hi | A_mid],  B'' = [B_hi | B_mid | B_hi]   =>  A''.B''^T = hi.hi + hi.mid + mid.hi
+// (relative error ~2^-16 per product instead of 2^-8), so one plain bf16 GEMM of depth K' = 3K does it.
+#pragma once
+
+#include <cuda_bf16.h>
+
+#include "common.cuh"
+
+namespace sert {
+
+enum TcEpilogueMode { TC_EPI_STORE = 0, TC_EPI_TOPK = 1 };
+
+struct TcEpilogue {
+  int mode = TC_EPI_STORE;
+  // TC_EPI_STORE: C[m, n] = acc (+ bias[n])
+  float *C = nullptr;
+  long long ldc = 0;
+  const float *bias = nullptr;
+  // TC_EPI_TOPK: rows are queries, columns are entity rows [n_begin, n_end) of B
+  const unsigned long long *tau = nullptr;
+  int *count = nullptr;
+  unsigned long long *cand = nullptr;
+  int cap = 0;
+  long long row_offset = 0;     // global id of B row 0
+};
+
+enum SplitRole { SPLIT_A = 0, SPLIT_B = 1 };
+
+// K padded to a multiple of 64 (one 128-byte swizzle row of bf16); returns the padded K of ONE term.
+static inline int tc_padded_k(int K) { return (int)align_up((size_t)K, 64); }
+
+// dst (rows, terms * Kp) bf16 <- split of src (rows, K) f32 (row stride ld_src); terms in {1, 3}.
+int launch_split_bf16(const float *src, long long rows, int K, long long ld_src, int terms, SplitRole role,
+                      __nv_bfloat16 *dst, cudaStream_t st);
+
+// Runs the GEMM over B rows [n_begin, n_end) (columns of C).  A: (M, Kt) bf16, B: (N_total, Kt) bf16,
+// Kt = terms * Kp a multiple of 64.  For TC_EPI_STORE column n of C is B row n.
+int launch_gemm_tc(const __nv_bfloat16 *A, int M, const __nv_bfloat16 *B, long long N_total, long long n_begin,
+                   long long n_end, int Kt, const TcEpilogue &epi, cudaStream_t st);
+
+}  // namespace sert

@@ -61,6 +61,7 @@ struct ParamSegment {
   const uint32_t *flags; // per-row touched stamps or nullptr (= always read the gradient)
 };
 constexpr int kMaxSegments = 4;
+constexpr int kSumsqSlots = 64;     // acc[0] = data-loss sum, acc[1..64] = partial sums of theta^2
 struct OptimArgs {
   float *theta, *s1, *s2, *grad;   // arena arrays of `total` floats
   long long total;                 // multiple of 4
@@ -71,8 +72,8 @@ struct OptimArgs {
   // Adam: c0 = a_t, c1 = beta1, c2 = beta2, c3 = eps.  Adadelta: c0 = lr, c1 = rho, c3 = eps.
   float c0, c1, c2, c3;
   // loss finalisation by the last block: loss[slot] = data_acc*inv_B + reg_coeff * sum(theta^2)
-  double *acc;                     // acc[0] = data loss sum, acc[1] = sumsq
-  unsigned int *ticket;
+  double *acc;                     // 1 + kSumsqSlots doubles, see above
+  unsigned int *ticket;            // unused (kept for layout stability)
   float *loss_out;
   float inv_B, reg_coeff;
 };

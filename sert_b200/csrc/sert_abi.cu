@@ -142,7 +142,7 @@ static size_t carve(sert_model &m, void *base) {
   m.grad = b.take<float>(o);
   m.flagR = b.take<uint32_t>(V);
   m.flagE = is_vs(c) ? b.take<uint32_t>(E) : nullptr;
-  m.acc = b.take<double>(4);
+  m.acc = b.take<double>(1 + kSumsqSlots + 7);
   m.ticket = b.take<unsigned int>(4);
   m.losses = b.take<float>(c.loss_slots + 1);   // last slot: scratch for parity hooks
   if (is_vs(c)) {
