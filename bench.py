@@ -283,6 +283,8 @@ def run_ours(args, rank, world, local_rank):
     scorer.topk(qs, sc['k'])
     score_e2e = sc['Q'] * sc['E'] / (time.perf_counter() - t0)
 
+    loglinear = run_loglinear_cfg1(rank) if rank == 0 else None
+
     if rank == 0:
         cpu = cpu_baseline_sample()
         line = {
@@ -307,6 +309,7 @@ def run_ours(args, rank, world, local_rank):
                          'step_algorithmic_bytes': step_bytes,
                          'step_frac_of_hbm_peak': step_bytes / (ms_max / steps * 1e-3) / 1e9 / peak},
             'cpu_baseline': cpu,
+            'loglinear': loglinear,
             'scoring': {'metric': 'scored entities/sec', 'value': score_value, 'unit': 'entities/s',
                         'workload': 'BASELINE.json configs[2]: Q=10000 x E=50000 d=128 top-100, rows sharded '
                                     'over %d GPU(s), one all-gather' % world,
@@ -316,6 +319,41 @@ def run_ours(args, rank, world, local_rank):
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
+
+
+def run_loglinear_cfg1(rank):
+    """BASELINE.json configs[0]: log-linear V=5k E=200 d=64 window=10 B=1024 (the reference's CPU-runnable case)."""
+    import torch
+    from oracle import sert_oracle as O
+    from sert_b200 import _native as N, models, synth
+    V, E, dw, W, B, nb = 5000, 200, 64, 10, 1024, 60
+    rng = np.random.default_rng(20160816 + 1)
+    train, val = synth.loglinear_corpus(20160817, V, E, W, B * nb, B * 2)
+    R, Wd, bd = synth.glorot(rng, (V, dw)), synth.glorot(rng, (dw, E)), np.zeros(E, np.float32)
+    model = models.LanguageModel(batch_size=B, window_size=W, representations_init=R, output_layer_size=E,
+                                 regularization_lambda=0.01, training_set=train, validation_set=val,
+                                 dense_init=(Wd, bd))
+    nat = model._native
+    order = np.arange(nb, dtype=np.int64)
+    N.check(nat.lib.sert_train_batches(nat.handle, N.host_ptr(order[:10]), 10, None, 0))
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    N.check(nat.lib.sert_train_batches(nat.handle, N.host_ptr(order[10:]), nb - 10, None, 10))
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / (nb - 10)
+    orc = O.LogLinearOracle(B, R, Wd, bd, 0.01, train, val)
+    orc.train_batch(0)
+    t0 = time.perf_counter()
+    for b in range(1, 4):
+        orc.train_batch(b)
+    cpu_ms = (time.perf_counter() - t0) / 3 * 1e3
+    model._native.close()
+    return {'workload': 'BASELINE.json configs[0]: LanguageModel (log-linear) V=5k E=200 d=64 window=10 B=1024, '
+                        'Adadelta + dense L2, exact per-word clipped path',
+            'value': B / (ms * 1e-3), 'unit': UNIT, 'ms_per_step': ms,
+            'cpu_port_value': B / (cpu_ms * 1e-3), 'cpu_port_ms_per_step': cpu_ms}
 
 
 def cpu_baseline_sample():

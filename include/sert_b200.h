@@ -109,6 +109,9 @@ SERT_API int sert_model_get_step(sert_model *m, int64_t *t);
  * summed kernel time, the launch count and the ALGORITHMIC bytes of one launch (24 B per parameter:
  * read+write of theta and the two optimiser-state arrays; DESIGN.md "roofline"). */
 SERT_API int sert_model_profile(sert_model *m, int enable);
+/* Vector-space training step: 1 (default) = fused per-tile kernel when the shape fits in shared memory,
+ * 0 = one kernel per stage (general shapes; also what the fused kernel is tested against). */
+SERT_API int sert_model_set_fused(sert_model *m, int enable);
 SERT_API int sert_model_profile_read(sert_model *m, double *update_ms_total, int64_t *update_launches,
                                      double *update_bytes_per_launch);
 
@@ -164,6 +167,9 @@ SERT_API int sert_scorer_create(const float *entities_host, int64_t rows, int32_
                        int32_t normalise, int32_t max_queries, int32_t max_k, void *arena_dev,
                        size_t arena_bytes, void *stream, sert_scorer **out);
 SERT_API int sert_scorer_destroy(sert_scorer *s);
+/* Scoring arithmetic: 1 (default) = tcgen05 tensor cores on a 3-term bf16 split of both operands (fp32-class
+ * accuracy) followed by an exact fp32 re-scoring of the surviving candidates; 0 = fp32 FMA tiles on CUDA cores. */
+SERT_API int sert_scorer_set_mode(sert_scorer *s, int32_t mode);
 /* Top-k by inner product of q query vectors (host f32 (q,d); normalise_q!=0 L2-normalises them,
  * bin/query.py:333-336) against the shard.  Outputs (q,k) global row ids and float32 inner products,
  * sorted by score descending (ties: lower row id first). */

@@ -46,6 +46,7 @@ SIGNATURES = {
     'sert_model_set_step': (c_int, [c_void_p, c_int64]),
     'sert_model_get_step': (c_int, [c_void_p, ctypes.POINTER(c_int64)]),
     'sert_model_profile': (c_int, [c_void_p, c_int]),
+    'sert_model_set_fused': (c_int, [c_void_p, c_int]),
     'sert_model_profile_read': (c_int, [c_void_p, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(c_int64),
                                         ctypes.POINTER(ctypes.c_double)]),
     'sert_model_attach_dataset': (c_int, [c_void_p, c_int, c_int64, c_void_p, c_void_p, c_void_p, c_void_p,
@@ -63,6 +64,7 @@ SIGNATURES = {
     'sert_scorer_create': (c_int, [c_void_p, c_int64, c_int32, c_int64, c_int32, c_int32, c_int32, c_void_p,
                                    c_size_t, c_void_p, ctypes.POINTER(c_void_p)]),
     'sert_scorer_destroy': (c_int, [c_void_p]),
+    'sert_scorer_set_mode': (c_int, [c_void_p, c_int32]),
     'sert_scorer_topk_host': (c_int, [c_void_p, c_void_p, c_int32, c_int32, c_int32, c_void_p, c_void_p]),
     'sert_scorer_scores_host': (c_int, [c_void_p, c_void_p, c_int32, c_int32, c_void_p]),
     'sert_scorer_topk_dev': (c_int, [c_void_p, c_void_p, c_int32, c_int32, c_int32, c_void_p, c_void_p]),

@@ -227,22 +227,23 @@ gemm_tc_kernel(const __grid_constant__ TcMap map_a, const __grid_constant__ TcMa
       const long long n0 = args.n_begin + (long long)(t / num_m_tiles) * BN;
       const int gm = m0 + row;
       const bool row_ok = gm < args.M;
-      unsigned long long tau_key = ~0ull;
+      // Rows are swept in increasing id order and tau only moves between launches, so a later row that
+      // ties tau's score has a larger id (= a smaller key): `score > tau_score` is the exact key test.
       float tau_score = INFINITY;
       if (ep.mode == TC_EPI_TOPK && row_ok) {
-        tau_key = ep.tau[gm];
+        const unsigned long long tau_key = ep.tau[gm];
         tau_score = tau_key == 0ull ? -INFINITY : key_score(tau_key);
       }
       mbar_wait(tfull_bar(acc), acc_phase);
       tc_fence_after();
       const uint32_t t_row = tmem_base + (uint32_t)acc * BN + ((uint32_t)(quarter * 32) << 16);
+      if (ep.mode == TC_EPI_STORE) {
 #pragma unroll 1
-      for (int c0 = 0; c0 < BN; c0 += 32) {
-        uint32_t v[32];
-        tc_ld_32x32(t_row + (uint32_t)c0, v);
-        tc_wait_ld();
-        const long long gn0 = n0 + c0;
-        if (ep.mode == TC_EPI_STORE) {
+        for (int c0 = 0; c0 < BN; c0 += 32) {
+          uint32_t v[32];
+          tc_ld_32x32(t_row + (uint32_t)c0, v);
+          tc_wait_ld();
+          const long long gn0 = n0 + c0;
           if (row_ok && gn0 < args.n_end) {
             float *dst = ep.C + (long long)gm * ep.ldc + gn0;
             const bool full = (gn0 + 32 <= args.n_end) && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0);
@@ -264,15 +265,48 @@ gemm_tc_kernel(const __grid_constant__ TcMap map_a, const __grid_constant__ TcMa
                   dst[j] = __uint_as_float(v[j]) + (ep.bias != nullptr ? ep.bias[gn0 + j] : 0.f);
             }
           }
-        } else {
+        }
+      } else {
+        // ---- running top-k filter.  Pass 1: survivor bitmask per 32-column chunk (one compare per score).
+        uint32_t masks[BN / 32];
+        int total = 0;
 #pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            const float sc = __uint_as_float(v[j]);
-            if (sc >= tau_score && gn0 + j < args.n_end) {          // rare once tau has warmed up
-              const unsigned long long key = make_key(sc, (unsigned int)(gn0 + j + ep.row_offset));
-              if (key > tau_key) {
-                const int pos = atomicAdd(ep.count + gm, 1);
-                if (pos < ep.cap) ep.cand[(size_t)gm * ep.cap + pos] = key;
+        for (int ci = 0; ci < BN / 32; ++ci) {
+          uint32_t v[32];
+          tc_ld_32x32(t_row + (uint32_t)(ci * 32), v);
+          tc_wait_ld();
+          const long long left = args.n_end - (n0 + ci * 32);          // valid columns in this chunk
+          const uint32_t valid = left >= 32 ? 0xffffffffu : (left <= 0 ? 0u : ((1u << (int)left) - 1u));
+          uint32_t m = 0;
+#pragma unroll
+          for (int j = 0; j < 32; ++j) m |= (__uint_as_float(v[j]) > tau_score ? 1u : 0u) << j;
+          m &= valid;
+          masks[ci] = m;
+          total += __popc(m);
+        }
+        // Pass 2 (rare once tau has warmed up): ONE atomic per thread reserves its slots, then TMEM is read
+        // again.  tcgen05.ld is warp-collective (.sync.aligned), so the chunk loop and its skip test are
+        // warp-uniform (__any_sync); only the per-lane key stores diverge.
+        if (__any_sync(0xffffffffu, total > 0)) {
+          int pos = 0;
+          unsigned long long *list = ep.cand + (size_t)(row_ok ? gm : 0) * ep.cap;
+          if (total > 0) {
+            pos = atomicAdd(ep.count + gm, total);
+            if (pos + total > ep.cap) *ep.overflow = 1;
+          }
+#pragma unroll
+          for (int ci = 0; ci < BN / 32; ++ci) {
+            const uint32_t m = masks[ci];
+            if (!__any_sync(0xffffffffu, m != 0u)) continue;
+            uint32_t v[32];
+            tc_ld_32x32(t_row + (uint32_t)(ci * 32), v);
+            tc_wait_ld();
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              if ((m >> j) & 1u) {
+                if (pos < ep.cap)
+                  list[pos] = make_key(__uint_as_float(v[j]), (unsigned int)(n0 + ci * 32 + j + ep.row_offset));
+                ++pos;
               }
             }
           }

@@ -27,6 +27,7 @@ struct TcEpilogue {
   unsigned long long *cand = nullptr;
   int cap = 0;
   long long row_offset = 0;     // global id of B row 0
+  int *overflow = nullptr;      // set to 1 when a candidate list is full
 };
 
 enum SplitRole { SPLIT_A = 0, SPLIT_B = 1 };

@@ -44,6 +44,28 @@ struct VsNceArgs {
 };
 int launch_vs_nce(const VsNceArgs &a, cudaStream_t st);
 
+// fused gather -> tanh projection -> loss fwd/bwd -> back-projection -> scatter for one instance tile per CTA
+// (csrc/vs_fused.cu).  Returns 0 = launched, 1 = shape not supported (use the unfused kernels), -1 = error.
+struct VsFusedArgs {
+  const int32_t *x;       // (B,W)
+  const float *R;         // (V,dw)
+  const float *Wp;        // (dw,de)
+  const float *bp;        // (de,)
+  const float *Eemb;      // (E,de)
+  const int32_t *y;       // (B,)
+  const int32_t *neg;     // (B,k)
+  const float *w;         // (B,) or nullptr
+  float *gE; uint32_t *flagE;
+  float *gR; uint32_t *flagR;
+  uint32_t stamp;
+  float *h;               // (B,dw) out (for dW = h^T.da)
+  float *da;              // (B,de) out
+  double *loss_acc;
+  int B, W, k, dw, de;
+  float inv_B;
+};
+int launch_vs_fused(const VsFusedArgs &a, cudaStream_t st);
+
 // scatter-add of dh/denom into the word-gradient rows (autodiff of the gather, AdvancedIncSubtensor)
 int launch_scatter_rows(const int32_t *x, const float *dh, float *gR, uint32_t *flagR, uint32_t stamp,
                         int B, int W, int d, float denom, cudaStream_t st);

@@ -12,21 +12,11 @@
 // broken by lower row id, so selection and the final order are deterministic.
 #include "score.cuh"
 
+#include "gemm_tc.cuh"
 #include "kernels.cuh"
+#include "topk_keys.cuh"
 
 namespace sert {
-
-__device__ __forceinline__ unsigned int orderable(float f) {
-  const unsigned int u = __float_as_uint(f);
-  return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
-}
-__device__ __forceinline__ float unorderable(unsigned int o) {
-  const unsigned int u = (o & 0x80000000u) ? (o & 0x7fffffffu) : ~o;
-  return __uint_as_float(u);
-}
-__device__ __forceinline__ unsigned long long make_key(float score, unsigned int row) {
-  return ((unsigned long long)orderable(score) << 32) | (unsigned long long)(0xffffffffu - row);
-}
 
 // ---- row L2 normalisation (bin/query.py:270-274, 333-336) --------------------------------------
 __global__ void __launch_bounds__(256) normalise_rows_kernel(const float *__restrict__ in, float *__restrict__ out,
@@ -57,7 +47,8 @@ __global__ void __launch_bounds__(256) score_filter_kernel(const float *__restri
                                                            long long row_offset,
                                                            const unsigned long long *__restrict__ tau,
                                                            int *__restrict__ count,
-                                                           unsigned long long *__restrict__ cand, int cap) {
+                                                           unsigned long long *__restrict__ cand, int cap,
+                                                           int *__restrict__ overflow) {
   __shared__ float Qs[TK][TQ + 4];
   __shared__ float Es[TK][TN + 4];
   const int tid = threadIdx.x;
@@ -103,15 +94,21 @@ __global__ void __launch_bounds__(256) score_filter_kernel(const float *__restri
   for (int i = 0; i < 4; ++i) {
     const int gq = q0 + ty * 4 + i;
     if (gq >= Q) continue;
+    // rows are swept in increasing id order, so `score > tau_score` is the exact key test (see gemm_tc.cu)
     const unsigned long long t = tau[gq];
+    const float tau_score = t == 0ull ? -INFINITY : key_score(t);
+    int n_pass = 0;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) n_pass += (n0 + tx * 4 + j < n_end && acc[i][j] > tau_score) ? 1 : 0;
+    if (n_pass == 0) continue;
+    int pos = atomicAdd(count + gq, n_pass);               // one reservation per (thread, query row)
+    if (pos + n_pass > cap) *overflow = 1;
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       const long long gn = n0 + tx * 4 + j;
-      if (gn >= n_end) continue;
-      const unsigned long long key = make_key(acc[i][j], (unsigned int)(gn + row_offset));
-      if (key > t) {
-        const int pos = atomicAdd(count + gq, 1);
-        if (pos < cap) cand[(size_t)gq * cap + pos] = key;
+      if (gn < n_end && acc[i][j] > tau_score) {
+        if (pos < cap) cand[(size_t)gq * cap + pos] = make_key(acc[i][j], (unsigned int)(gn + row_offset));
+        ++pos;
       }
     }
   }
@@ -134,15 +131,21 @@ __device__ void bitonic_sort_desc(unsigned long long *keys, int n_pow2) {
   __syncthreads();
 }
 
-// Re-selects the best k candidates of every query whose list is more than half full (or of every
-// query when `final`), raises tau, and on `final` writes the sorted (row id, score) outputs.
+// Re-selects the best k candidates of a query and raises tau.  mode 0: only lists more than half full;
+// mode 2: every list; mode 1 ("final"): every list, and the sorted (row id, score) outputs are written.
+// Launched twice per prune: once with `smem_cap` = kPruneSmall slots of shared memory (lists of up to that
+// many candidates: high occupancy, the common case once tau has warmed up) and once with the full capacity
+// for longer lists; each launch skips the lists that belong to the other.
+constexpr int kPruneSmall = 2048;
 __global__ void __launch_bounds__(256) prune_kernel(unsigned long long *__restrict__ cand, int *__restrict__ count,
                                                     unsigned long long *__restrict__ tau, int cap, int k, int final,
-                                                    int32_t *__restrict__ out_idx, float *__restrict__ out_score) {
+                                                    int32_t *__restrict__ out_idx, float *__restrict__ out_score,
+                                                    int smem_cap) {
   extern __shared__ unsigned long long keys[];
   const int q = blockIdx.x;
   const int n = min(count[q], cap);
-  if (!final && n <= cap / 2) return;
+  if (final == 0 && n <= cap / 2) return;
+  if (smem_cap < cap ? (n > smem_cap) : (n <= kPruneSmall && cap > kPruneSmall)) return;
   int n_pow2 = 1;
   while (n_pow2 < n) n_pow2 <<= 1;
   if (n_pow2 < 2) n_pow2 = 2;
@@ -155,7 +158,7 @@ __global__ void __launch_bounds__(256) prune_kernel(unsigned long long *__restri
     count[q] = keep;
     if (keep == k) tau[q] = keys[k - 1];
   }
-  if (final) {
+  if (final == 1) {
     for (int i = threadIdx.x; i < k; i += blockDim.x) {
       if (i < keep) {
         out_idx[(size_t)q * k + i] = (int32_t)(0xffffffffu - (unsigned int)(keys[i] & 0xffffffffull));
@@ -173,30 +176,107 @@ __global__ void reset_topk_state_kernel(unsigned long long *tau, int *count, int
   if (q < Q) { tau[q] = 0ull; count[q] = 0; }
 }
 
+// Exact float32 re-scoring of the surviving candidates (tensor-core mode): the bf16x3 scores picked the
+// candidates, the returned scores and the final order come from fp32 dot products of the fp32 vectors.
+__global__ void __launch_bounds__(256) rescore_kernel(const float *__restrict__ Qm, const float *__restrict__ En,
+                                                      int d, long long row_begin, unsigned long long *__restrict__ cand,
+                                                      const int *__restrict__ count, int cap) {
+  extern __shared__ float qs[];
+  const int q = blockIdx.x;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+  const int n = min(count[q], cap);
+  for (int c = threadIdx.x; c < d; c += blockDim.x) qs[c] = Qm[(size_t)q * d + c];
+  __syncthreads();
+  unsigned long long *list = cand + (size_t)q * cap;
+  for (int j = warp; j < n; j += 2 * nwarps) {
+    const int j2 = j + nwarps;
+    const unsigned int r0 = key_row(list[j]);
+    const unsigned int r1 = j2 < n ? key_row(list[j2]) : r0;
+    const float *e0 = En + (size_t)((long long)r0 - row_begin) * d;
+    const float *e1 = En + (size_t)((long long)r1 - row_begin) * d;
+    float s0 = 0.f, s1 = 0.f;
+    for (int c = lane; c < d; c += 32) {
+      s0 = fmaf(e0[c], qs[c], s0);
+      s1 = fmaf(e1[c], qs[c], s1);
+    }
+    s0 = warp_sum(s0);
+    s1 = warp_sum(s1);
+    if (lane == 0) {
+      list[j] = make_key(s0, r0);
+      if (j2 < n) list[j2] = make_key(s1, r1);
+    }
+  }
+}
+
+static int launch_prune(const TopkState &s, int Q, int k, int mode, int32_t *out_idx, float *out_score,
+                        cudaStream_t st) {
+  const int small = std::min(kPruneSmall, s.cap);
+  prune_kernel<<<Q, 256, (size_t)small * sizeof(unsigned long long), st>>>(s.cand, s.count, s.tau, s.cap, k, mode,
+                                                                           out_idx, out_score, small);
+  SERT_LAUNCH_CHECK();
+  if (s.cap > kPruneSmall) {
+    prune_kernel<<<Q, 256, (size_t)s.cap * sizeof(unsigned long long), st>>>(s.cand, s.count, s.tau, s.cap, k, mode,
+                                                                             out_idx, out_score, s.cap);
+    SERT_LAUNCH_CHECK();
+  }
+  return 0;
+}
+
+// One pass over the shard.  `optimistic`: geometrically growing chunks (1024, 4096, ... rows) with a forced
+// prune after each, so tau tightens early and later chunks append only ~k*chunk/seen rows per query; a list
+// that would overflow sets *overflow and the caller falls back to the conservative pass (chunk = cap/2 rows,
+// which cannot overflow even if every score of a chunk survives).
+static int topk_pass(const TopkState &s, const float *queries_dev, int Q, int k_sel, bool optimistic,
+                     cudaStream_t st) {
+  const bool tensor = s.mode == SCORE_TENSOR;
+  reset_topk_state_kernel<<<cdiv(Q, 256), 256, 0, st>>>(s.tau, s.count, Q);
+  SERT_LAUNCH_CHECK();
+  SERT_CUDA(cudaMemsetAsync(s.overflow, 0, sizeof(int), st));
+  long long chunk = optimistic ? std::min<long long>(1024, s.cap / 2) : s.cap / 2;
+  for (long long n0 = 0; n0 < s.rows;) {
+    const long long n1 = std::min<long long>(s.rows, n0 + chunk);
+    if (tensor) {
+      TcEpilogue ep;
+      ep.mode = TC_EPI_TOPK;
+      ep.tau = s.tau; ep.count = s.count; ep.cand = s.cand; ep.cap = s.cap; ep.row_offset = s.row_begin;
+      ep.overflow = s.overflow;
+      if (launch_gemm_tc(s.q_split, Q, s.ent_split, s.rows, n0, n1, s.kt, ep, st)) return -1;
+    } else {
+      dim3 grid(cdiv(n1 - n0, TN), cdiv(Q, TQ));
+      score_filter_kernel<<<grid, 256, 0, st>>>(queries_dev, s.entities, Q, n0, n1, s.d, s.row_begin, s.tau, s.count,
+                                                s.cand, s.cap, s.overflow);
+      SERT_LAUNCH_CHECK();
+    }
+    // forced prune (mode 2) while tau is still loose or at the end; otherwise only lists more than half full
+    const bool force = optimistic || n1 == s.rows;
+    if (launch_prune(s, Q, k_sel, force ? 2 : 0, nullptr, nullptr, st)) return -1;
+    n0 = n1;
+    if (optimistic) chunk = std::min<long long>(chunk * 4, 1 << 16);
+  }
+  return 0;
+}
+
 int topk_sweep(const TopkState &s, const float *queries_dev, int Q, int k, int32_t *out_idx, float *out_score,
                cudaStream_t st) {
   SERT_REQUIRE(k >= 1 && k <= s.cap / 2, "k exceeds the scorer's max_k");
   SERT_REQUIRE(Q >= 0 && Q <= s.max_queries, "more queries than the scorer's max_queries");
   if (Q == 0) return 0;
-  reset_topk_state_kernel<<<cdiv(Q, 256), 256, 0, st>>>(s.tau, s.count, Q);
-  SERT_LAUNCH_CHECK();
-  const long long chunk = s.cap / 2;
-  const size_t smem = (size_t)s.cap * sizeof(unsigned long long);
-  for (long long n0 = 0; n0 < s.rows; n0 += chunk) {
-    const long long n1 = std::min<long long>(s.rows, n0 + chunk);
-    dim3 grid(cdiv(n1 - n0, TN), cdiv(Q, TQ));
-    score_filter_kernel<<<grid, 256, 0, st>>>(queries_dev, s.entities, Q, n0, n1, s.d, s.row_begin, s.tau, s.count,
-                                              s.cand, s.cap);
-    SERT_LAUNCH_CHECK();
-    const bool last = (n1 == s.rows);
-    prune_kernel<<<Q, 256, smem, st>>>(s.cand, s.count, s.tau, s.cap, k, last ? 1 : 0, out_idx, out_score);
-    SERT_LAUNCH_CHECK();
-  }
-  if (s.rows == 0) {
-    prune_kernel<<<Q, 256, smem, st>>>(s.cand, s.count, s.tau, s.cap, k, 1, out_idx, out_score);
+  const bool tensor = s.mode == SCORE_TENSOR;
+  // tensor-core mode keeps a margin of candidates beyond k so that bf16x3 rounding at the k-th place
+  // cannot drop a true top-k row before the exact re-scoring
+  const int k_sel = tensor ? std::min(s.cap / 2, k + 16) : k;
+  if (tensor && launch_split_bf16(queries_dev, Q, s.d, s.d, s.terms, SPLIT_A, s.q_split, st)) return -1;
+  if (topk_pass(s, queries_dev, Q, k_sel, true, st)) return -1;
+  int overflow = 0;
+  SERT_CUDA(cudaMemcpyAsync(&overflow, s.overflow, sizeof(int), cudaMemcpyDeviceToHost, st));
+  SERT_CUDA(cudaStreamSynchronize(st));
+  if (overflow && topk_pass(s, queries_dev, Q, k_sel, false, st)) return -1;
+  if (tensor && s.rows > 0) {
+    rescore_kernel<<<Q, 256, (size_t)s.d * sizeof(float), st>>>(queries_dev, s.entities, s.d, s.row_begin, s.cand,
+                                                                s.count, s.cap);
     SERT_LAUNCH_CHECK();
   }
-  return 0;
+  return launch_prune(s, Q, k, 1, out_idx, out_score, st);
 }
 
 int topk_prepare(int cap) {
@@ -281,8 +361,8 @@ static size_t carve_scorer(sert_scorer &sc, void *base, int64_t rows, int d, int
     off += bytes;
     return p;
   };
-  int cap = 4096;
-  while (cap / 2 < max_k) cap <<= 1;
+  int cap = 8192;                       // chunk = cap/2 entity rows per score-tile launch
+  while (cap / 2 < max_k + 16) cap <<= 1;
   sc.s.cap = cap;
   sc.s.rows = rows;
   sc.s.d = d;
@@ -292,7 +372,12 @@ static size_t carve_scorer(sert_scorer &sc, void *base, int64_t rows, int d, int
   sc.s.cand = reinterpret_cast<unsigned long long *>(take((size_t)max_queries * cap * sizeof(unsigned long long)));
   sc.s.tau = reinterpret_cast<unsigned long long *>(take((size_t)max_queries * sizeof(unsigned long long)));
   sc.s.count = reinterpret_cast<int *>(take((size_t)max_queries * sizeof(int)));
+  sc.s.overflow = reinterpret_cast<int *>(take(sizeof(int)));
   sc.queries = reinterpret_cast<float *>(take((size_t)max_queries * d * sizeof(float)));
+  sc.s.terms = 3;
+  sc.s.kt = sc.s.terms * tc_padded_k(d);
+  sc.s.ent_split = reinterpret_cast<__nv_bfloat16 *>(take((size_t)rows * sc.s.kt * sizeof(__nv_bfloat16)));
+  sc.s.q_split = reinterpret_cast<__nv_bfloat16 *>(take((size_t)max_queries * sc.s.kt * sizeof(__nv_bfloat16)));
   sc.out_idx = reinterpret_cast<int32_t *>(take((size_t)max_queries * max_k * sizeof(int32_t)));
   sc.out_score = reinterpret_cast<float *>(take((size_t)max_queries * max_k * sizeof(float)));
   return align_up(off, 256);
@@ -334,10 +419,23 @@ int sert_scorer_create(const float *entities_host, int64_t rows, int32_t d, int6
                                     cudaMemcpyHostToDevice, sc->st);
     if (e != cudaSuccess) { delete sc; set_error(cudaGetErrorString(e)); return -1; }
     if (normalise && launch_normalise_rows(sc->s.entities, sc->s.entities, rows, d, sc->st)) { delete sc; return -1; }
+    // bf16x3 split of the (normalised) entity rows: the B operand of the tcgen05 scoring GEMM
+    if (launch_split_bf16(sc->s.entities, rows, d, d, sc->s.terms, SPLIT_B, sc->s.ent_split, sc->st)) {
+      delete sc;
+      return -1;
+    }
   }
+  sc->s.mode = SCORE_TENSOR;
   cudaError_t e = cudaStreamSynchronize(sc->st);
   if (e != cudaSuccess) { delete sc; set_error(cudaGetErrorString(e)); return -1; }
   *out = sc;
+  return 0;
+}
+
+int sert_scorer_set_mode(sert_scorer *s, int32_t mode) {
+  SERT_REQUIRE(s, "null scorer");
+  SERT_REQUIRE(mode == SCORE_FMA || mode == SCORE_TENSOR, "unknown scoring mode");
+  s->s.mode = mode;
   return 0;
 }
 

@@ -4,9 +4,13 @@
 
 #include <algorithm>
 
+#include <cuda_bf16.h>
+
 #include "common.cuh"
 
 namespace sert {
+
+enum ScoreMode { SCORE_FMA = 0, SCORE_TENSOR = 1 };
 
 struct TopkState {
   float *entities = nullptr;            // (rows,d) float32, row-major (L2-normalised when asked)
@@ -17,7 +21,14 @@ struct TopkState {
   int cap = 0;                          // candidate slots per query (power of two, >= 2*max_k)
   unsigned long long *cand = nullptr;   // (max_queries, cap) keys
   unsigned long long *tau = nullptr;    // (max_queries,) key of the current k-th best (0 = none yet)
-  int *count = nullptr;                 // (max_queries,) used slots
+  int *count = nullptr;                 // (max_queries,) used slots (may exceed cap after an overflow)
+  int *overflow = nullptr;              // set when an append found its list full
+  // tensor-core mode (tcgen05 bf16x3 GEMM): split operands, K-major, Kt = terms * padded d
+  int mode = SCORE_TENSOR;
+  int terms = 3;
+  int kt = 0;
+  __nv_bfloat16 *ent_split = nullptr;   // (rows, kt)
+  __nv_bfloat16 *q_split = nullptr;     // (max_queries, kt)
 };
 
 int launch_normalise_rows(const float *in, float *out, int64_t rows, int d, cudaStream_t st);

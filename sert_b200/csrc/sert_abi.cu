@@ -77,6 +77,7 @@ struct sert_model {
   float *stage_w = nullptr, *stage_data = nullptr, *stage_f = nullptr;
   size_t stage_nnz_cap = 0;
   // optional per-kernel timing of the dense update (bench.py's roofline leg)
+  bool use_fused = true;              // fused tile kernel for the vector-space step when the shape fits
   bool profile = false;
   std::vector<std::pair<cudaEvent_t, cudaEvent_t>> prof_events;
 };
@@ -250,23 +251,35 @@ static int vs_train_step(sert_model &m, const int32_t *x, const int32_t *y, cons
       return -1;
     neg = m.neg;
   }
-  if (vs_forward(m, x, st)) return -1;
-  VsNceArgs a;
-  a.t = m.t; a.Eemb = m.theta + m.off[SERT_PARAM_ENTITY_REPR]; a.y = y; a.neg = neg; a.w = w;
-  a.gE = m.grad + m.off[SERT_PARAM_ENTITY_REPR]; a.flagE = m.flagE; a.stamp = m.stamp; a.da = m.da;
-  a.loss_acc = m.acc; a.dbg_scores = nullptr; a.dbg_u = nullptr; a.dbg_ell = nullptr;
-  a.B = B; a.k = c.num_negatives; a.de = de; a.inv_B = 1.0f / (float)B; a.train = true;
-  if (launch_vs_nce(a, st)) return -1;
-  // dh = da . Wp^T
-  if (launch_gemm_f32(m.da, Wp, m.dh, B, dw, de, false, true, de, de, dw, EPI_STORE, nullptr, 1, st)) return -1;
+  VsFusedArgs f;
+  f.x = x; f.R = m.theta + m.off[SERT_PARAM_WORD_REPR]; f.Wp = Wp; f.bp = m.theta + m.off[SERT_PARAM_DENSE_B];
+  f.Eemb = m.theta + m.off[SERT_PARAM_ENTITY_REPR]; f.y = y; f.neg = neg; f.w = w;
+  f.gE = m.grad + m.off[SERT_PARAM_ENTITY_REPR]; f.flagE = m.flagE;
+  f.gR = m.grad + m.off[SERT_PARAM_WORD_REPR]; f.flagR = m.flagR; f.stamp = m.stamp;
+  f.h = m.h; f.da = m.da; f.loss_acc = m.acc;
+  f.B = B; f.W = c.window; f.k = c.num_negatives; f.dw = dw; f.de = de; f.inv_B = 1.0f / (float)B;
+  const int fused = m.use_fused ? launch_vs_fused(f, st) : 1;
+  if (fused < 0) return -1;
+  if (fused == 1) {
+    // general-shape path: one kernel per stage
+    if (vs_forward(m, x, st)) return -1;
+    VsNceArgs a;
+    a.t = m.t; a.Eemb = m.theta + m.off[SERT_PARAM_ENTITY_REPR]; a.y = y; a.neg = neg; a.w = w;
+    a.gE = m.grad + m.off[SERT_PARAM_ENTITY_REPR]; a.flagE = m.flagE; a.stamp = m.stamp; a.da = m.da;
+    a.loss_acc = m.acc; a.dbg_scores = nullptr; a.dbg_u = nullptr; a.dbg_ell = nullptr;
+    a.B = B; a.k = c.num_negatives; a.de = de; a.inv_B = 1.0f / (float)B; a.train = true;
+    if (launch_vs_nce(a, st)) return -1;
+    // dh = da . Wp^T
+    if (launch_gemm_f32(m.da, Wp, m.dh, B, dw, de, false, true, de, de, dw, EPI_STORE, nullptr, 1, st)) return -1;
+    if (launch_scatter_rows(x, m.dh, m.grad + m.off[SERT_PARAM_WORD_REPR], m.flagR, m.stamp, B, c.window, dw,
+                            (float)c.window, st))
+      return -1;
+  }
   // gWp += h^T . da   (split-K over the batch)
   if (launch_gemm_f32(m.h, m.da, m.grad + m.off[SERT_PARAM_DENSE_W], dw, de, B, true, false, dw, de, de,
                       EPI_ATOMIC_ADD, nullptr, pick_split_k(dw, de, B), st))
     return -1;
   if (launch_colsum_atomic(m.da, m.grad + m.off[SERT_PARAM_DENSE_B], B, de, st)) return -1;
-  if (launch_scatter_rows(x, m.dh, m.grad + m.off[SERT_PARAM_WORD_REPR], m.flagR, m.stamp, B, c.window, dw,
-                          (float)c.window, st))
-    return -1;
   m.step += 1;
   OptimArgs o = optim_args(m, loss_out);
   o.c0 = adam_alpha_f32(m.step); o.c1 = 0.9f; o.c2 = 0.999f; o.c3 = 1e-8f;
@@ -457,6 +470,12 @@ int sert_model_set_step(sert_model *m, int64_t t) {
 int sert_model_get_step(sert_model *m, int64_t *t) {
   SERT_REQUIRE(m && t, "null argument");
   *t = m->step;
+  return 0;
+}
+
+int sert_model_set_fused(sert_model *m, int enable) {
+  SERT_REQUIRE(m, "null model");
+  m->use_fused = enable != 0;
   return 0;
 }
 

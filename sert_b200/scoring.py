@@ -39,6 +39,10 @@ class EntityScorer(object):
                                                 N.c_void_p(self.stream.cuda_stream), N.ctypes.byref(handle)))
         self.handle = handle
 
+    def set_mode(self, mode):
+        """'tensor' (default: tcgen05 bf16x3 GEMM + exact fp32 re-scoring) or 'fma' (fp32 CUDA-core tiles)."""
+        N.check(self.lib.sert_scorer_set_mode(self.handle, {'fma': 0, 'tensor': 1}[mode]))
+
     def close(self):
         if getattr(self, 'handle', None):
             self.lib.sert_scorer_destroy(self.handle)
@@ -87,6 +91,32 @@ class EntityScorer(object):
         return idx, score
 
 
+def pack_lists(idx, score):
+    """(Q,k) int32 row ids + (Q,k) float32 scores -> one int32 tensor (Q,k,2) so ONE collective moves both."""
+    import torch
+    return torch.stack([idx, score.view(torch.int32)], dim=-1).contiguous()
+
+
+def unpack_lists(gathered):
+    """(world,Q,k,2) int32 -> ((world,Q,k) int32 ids, (world,Q,k) float32 scores)."""
+    import torch
+    return gathered[..., 0].contiguous(), gathered[..., 1].contiguous().view(torch.float32)
+
+
+def all_gather_lists(idx, score, group=None):
+    """The single exchange step of sharded scoring: every rank receives every rank's (ids, scores)[Q,k]."""
+    import torch
+    import torch.distributed as dist
+    packed = pack_lists(idx, score)
+    world = dist.get_world_size(group)
+    gathered = torch.empty((world,) + tuple(packed.shape), dtype=torch.int32, device=packed.device)
+    if packed.is_cuda:
+        dist.all_gather_into_tensor(gathered, packed, group=group)         # NCCL: one fused all-gather
+    else:
+        dist.all_gather(list(gathered.unbind(0)), packed, group=group)     # gloo (CPU tests)
+    return unpack_lists(gathered)
+
+
 def shard_bounds(num_rows, world_size, rank):
     """Contiguous row shards of (almost) equal size: SURVEY.md 8(e)."""
     base, rem = divmod(num_rows, world_size)
@@ -116,12 +146,7 @@ class ShardedScorer(object):
         if self.world == 1:
             return idx, score
         Q = idx.shape[0]
-        # one collective: pack (idx, score bits) into a single int32 tensor [Q, k, 2]
-        packed = torch.stack([idx, score.view(torch.int32)], dim=-1).contiguous()
-        gathered = torch.empty((self.world,) + tuple(packed.shape), dtype=torch.int32, device=packed.device)
-        self.dist.all_gather_into_tensor(gathered, packed, group=self.group)
-        g_idx = gathered[..., 0].contiguous()
-        g_score = gathered[..., 1].contiguous().view(torch.float32)
+        g_idx, g_score = all_gather_lists(idx, score, self.group)
         out_idx = torch.empty_like(idx)
         out_score = torch.empty_like(score)
         N.check(self.local.lib.sert_topk_merge_dev(N.dev_ptr(g_idx), N.dev_ptr(g_score), self.world, Q, k,

@@ -11,15 +11,17 @@ def exact_topk(E, q, k):
     return order, np.take_along_axis(s, order, axis=1)
 
 
+@pytest.mark.parametrize('mode', ['tensor', 'fma'])
 @pytest.mark.parametrize('rows,d,Q,k', [(5000, 128, 37, 100), (12345, 256, 130, 10), (300, 64, 5, 100),
-                                        (64, 32, 3, 64), (9000, 20, 65, 128)])
-def test_topk_matches_exact(rows, d, Q, k):
+                                        (64, 32, 3, 64), (9000, 20, 65, 128), (20000, 300, 257, 100)])
+def test_topk_matches_exact(rows, d, Q, k, mode):
     from oracle import sert_oracle as O
     from sert_b200.scoring import EntityScorer
     rng = np.random.default_rng(rows + d)
     E = O.normalise_rows(rng.standard_normal((rows, d)))
     q = O.normalise_rows(rng.standard_normal((Q, d)))
     sc = EntityScorer(E, normalise=False, max_queries=64, max_k=128)
+    sc.set_mode(mode)
     idx, score = sc.topk(q, k)
     ref_idx, ref_score = exact_topk(E, q, k)
     np.testing.assert_allclose(score, ref_score, rtol=0, atol=2e-6)
@@ -80,3 +82,22 @@ def test_merge_of_shards_equals_single_device():
     torch.cuda.synchronize()
     assert (oi.cpu().numpy() == full_idx).all()
     np.testing.assert_array_equal(os_.cpu().numpy(), full_score)
+
+
+@pytest.mark.parametrize('mode', ['tensor', 'fma'])
+def test_adversarial_ascending_scores_take_the_exact_fallback(mode):
+    """Scores that grow with the row id defeat the optimistic threshold (every later row survives): the
+    candidate lists overflow and the sweep must fall back to the conservative, overflow-free pass."""
+    from sert_b200.scoring import EntityScorer
+    rows, d, k = 30000, 16, 10
+    rng = np.random.default_rng(3)
+    v = rng.standard_normal(d).astype(np.float32)
+    v /= np.linalg.norm(v)
+    E = (np.linspace(0.1, 1.0, rows, dtype=np.float32)[:, None] * v[None, :]).astype(np.float32)
+    q = np.stack([v, -v, 2 * v]).astype(np.float32)
+    sc = EntityScorer(E, max_queries=8, max_k=16)
+    sc.set_mode(mode)
+    idx, score = sc.topk(q, k)
+    ref_idx, ref_score = exact_topk(E, q, k)
+    np.testing.assert_array_equal(idx, ref_idx)
+    np.testing.assert_allclose(score, ref_score, rtol=1e-6, atol=1e-6)

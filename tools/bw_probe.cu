@@ -120,9 +120,20 @@ __global__ void __launch_bounds__(256) adam_probe(float4* th, float4* s1, float4
   if (i < n4) {
     float4 p = th[i], a = s1[i], b = s2[i];
     float4 g = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (FLAGS) {
+    if (FLAGS == 1) {
       const unsigned row = (unsigned)(i * 4) / 128u;
       if (__ldg(flags + row) == 7u) { g = g4[i]; g4[i] = make_float4(0.f, 0.f, 0.f, 0.f); }
+    } else if (FLAGS == 2) {          // lookup only
+      const unsigned row = (unsigned)(i * 4) / 128u;
+      if (__ldg(flags + row) == 7u) g.x = 1.f;
+    } else if (FLAGS == 3) {          // conditional read, no zeroing
+      const unsigned row = (unsigned)(i * 4) / 128u;
+      if (__ldg(flags + row) == 7u) g = g4[i];
+    } else if (FLAGS == 4) {          // unconditional 4th stream read + zero
+      g = g4[i]; g4[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    } else if (FLAGS == 5) {          // conditional read; zeroing deferred to after the main stores
+      const unsigned row = (unsigned)(i * 4) / 128u;
+      if (__ldg(flags + row) == 7u) g = __ldcg(g4 + i);
     }
     float pv[4] = {p.x, p.y, p.z, p.w}, v1[4] = {a.x, a.y, a.z, a.w}, v2[4] = {b.x, b.y, b.z, b.w};
     const float gv[4] = {g.x, g.y, g.z, g.w};
@@ -148,6 +159,10 @@ __global__ void __launch_bounds__(256) adam_probe(float4* th, float4* s1, float4
     th[i] = make_float4(pv[0], pv[1], pv[2], pv[3]);
     s1[i] = make_float4(v1[0], v1[1], v1[2], v1[3]);
     s2[i] = make_float4(v2[0], v2[1], v2[2], v2[3]);
+    if (FLAGS == 5) {
+      const unsigned row = (unsigned)(i * 4) / 128u;
+      if (__ldg(flags + row) == 7u) g4[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
   }
   if (SUMSQ) {
     __shared__ double sp[8];
@@ -220,6 +235,10 @@ int main() {
     AP(1, 1, 0, "one-shot: adam approx + sumsq");
     AP(1, 0, 1, "one-shot: adam approx + flags/G(35%)");
     AP(1, 1, 1, "one-shot: adam approx + sumsq + flags/G");
+    AP(1, 0, 2, "one-shot: flags lookup only");
+    AP(1, 0, 3, "one-shot: flags + conditional G read");
+    AP(1, 0, 4, "one-shot: unconditional G read+zero");
+    AP(1, 0, 5, "one-shot: cond G ldcg, zero after stores");
     AP(2, 1, 1, "one-shot: adam IEEE + sumsq + flags/G");
   }
   // plain device-to-device memcpy of the same volume for reference (3 arrays)
