@@ -267,26 +267,25 @@ gemm_tc_kernel(const __grid_constant__ TcMap map_a, const __grid_constant__ TcMa
           }
         }
       } else {
-        // ---- running top-k filter.  Pass 1: survivor bitmask per 32-column chunk (one compare per score).
-        uint32_t masks[BN / 32];
+        // ---- running top-k filter.  The chunk loops stay rolled: the epilogue's code must stay resident in
+        // the instruction caches (a fully unrolled two-pass version measured 6x slower: the warps sat in
+        // "no instruction" stalls).  Pass 1 counts this row's survivors, one compare per score.
         int total = 0;
-#pragma unroll
+#pragma unroll 1
         for (int ci = 0; ci < BN / 32; ++ci) {
           uint32_t v[32];
           tc_ld_32x32(t_row + (uint32_t)(ci * 32), v);
           tc_wait_ld();
           const long long left = args.n_end - (n0 + ci * 32);          // valid columns in this chunk
-          const uint32_t valid = left >= 32 ? 0xffffffffu : (left <= 0 ? 0u : ((1u << (int)left) - 1u));
-          uint32_t m = 0;
+          const int nv = left >= 32 ? 32 : (left <= 0 ? 0 : (int)left);
+          int cnt = 0;
 #pragma unroll
-          for (int j = 0; j < 32; ++j) m |= (__uint_as_float(v[j]) > tau_score ? 1u : 0u) << j;
-          m &= valid;
-          masks[ci] = m;
-          total += __popc(m);
+          for (int j = 0; j < 32; ++j) cnt += (j < nv && __uint_as_float(v[j]) > tau_score) ? 1 : 0;
+          total += cnt;
         }
         // Pass 2 (rare once tau has warmed up): ONE atomic per thread reserves its slots, then TMEM is read
-        // again.  tcgen05.ld is warp-collective (.sync.aligned), so the chunk loop and its skip test are
-        // warp-uniform (__any_sync); only the per-lane key stores diverge.
+        // again.  tcgen05.ld is warp-collective (.sync.aligned), so the chunk loop is warp-uniform; only the
+        // per-lane key stores diverge.
         if (__any_sync(0xffffffffu, total > 0)) {
           int pos = 0;
           unsigned long long *list = ep.cand + (size_t)(row_ok ? gm : 0) * ep.cap;
@@ -294,16 +293,17 @@ gemm_tc_kernel(const __grid_constant__ TcMap map_a, const __grid_constant__ TcMa
             pos = atomicAdd(ep.count + gm, total);
             if (pos + total > ep.cap) *ep.overflow = 1;
           }
-#pragma unroll
+#pragma unroll 1
           for (int ci = 0; ci < BN / 32; ++ci) {
-            const uint32_t m = masks[ci];
-            if (!__any_sync(0xffffffffu, m != 0u)) continue;
             uint32_t v[32];
             tc_ld_32x32(t_row + (uint32_t)(ci * 32), v);
             tc_wait_ld();
+            if (total == 0) continue;                                   // this lane has nothing to write
+            const long long left = args.n_end - (n0 + ci * 32);
+            const int nv = left >= 32 ? 32 : (left <= 0 ? 0 : (int)left);
 #pragma unroll
             for (int j = 0; j < 32; ++j) {
-              if ((m >> j) & 1u) {
+              if (j < nv && __uint_as_float(v[j]) > tau_score) {
                 if (pos < ep.cap)
                   list[pos] = make_key(__uint_as_float(v[j]), (unsigned int)(n0 + ci * 32 + j + ep.row_offset));
                 ++pos;

@@ -28,7 +28,7 @@ __host__ __device__ inline size_t fused_smem_floats(int TB, int dw, int de) {
 }
 
 template <int TB, int CW, int CE>
-__global__ void __launch_bounds__(kThreads, 1) vs_fused_kernel(VsFusedArgs a) {
+__global__ void __launch_bounds__(kThreads, TB <= 16 ? 2 : 1) vs_fused_kernel(VsFusedArgs a) {
   extern __shared__ __align__(16) float smem[];
   const int dw = a.dw, de = a.de, W = a.W;
   const int ldw = de + 1;
@@ -44,9 +44,11 @@ __global__ void __launch_bounds__(kThreads, 1) vs_fused_kernel(VsFusedArgs a) {
   __shared__ double s_loss[kWarps];
 
   // ---- phase 0: projection matrix and bias into shared memory --------------------------------------
-  for (int e = tid; e < dw * de; e += kThreads) {
-    const int r = e / de, c = e - r * de;
-    s.wp[r * ldw + c] = __ldg(a.Wp + e);
+  for (int e4 = tid; e4 < dw * de4; e4 += kThreads) {
+    const int r = e4 / de4, c = (e4 - r * de4) * 4;
+    const float4 v = __ldg(reinterpret_cast<const float4 *>(a.Wp) + e4);
+    float *dst = s.wp + r * ldw + c;
+    dst[0] = v.x; dst[1] = v.y; dst[2] = v.z; dst[3] = v.w;
   }
   for (int c = tid; c < de; c += kThreads) s.bp[c] = __ldg(a.bp + c);
 
@@ -294,14 +296,22 @@ int launch_vs_fused(const VsFusedArgs &a, cudaStream_t st) {
   if (a.B == 0) return 0;
   if (a.dw % 4 != 0 || a.de % 4 != 0) return 1;
   const int cw = (a.dw + 31) / 32, ce = (a.de + 31) / 32;
+  // 16-instance tiles, two CTAs per SM (16 warps in flight hide the gather / LDS latencies) when the tile
+  // fits twice in shared memory, else 32-instance tiles with one CTA per SM
+  const size_t bytes16 = fused_smem_floats(16, a.dw, a.de) * sizeof(float);
   const size_t bytes32 = fused_smem_floats(32, a.dw, a.de) * sizeof(float);
-  if (bytes32 > 200 * 1024) return 1;
-  if (ce == 4 && cw == 4) return launch_t<32, 4, 4>(a, bytes32, st);       // d = 128 (BASELINE configs[1])
-  if (ce == 2 && cw == 2) return launch_t<32, 2, 2>(a, bytes32, st);       // d = 64
-  if (ce == 1 && cw == 1) return launch_t<32, 1, 1>(a, bytes32, st);       // d = 32
-  if (ce == 2 && cw == 4) return launch_t<32, 4, 2>(a, bytes32, st);
-  if (ce == 4 && cw == 2) return launch_t<32, 2, 4>(a, bytes32, st);
-  if (ce == 4 && cw == 8) return launch_t<32, 8, 4>(a, bytes32, st);       // dw = 256, de = 128
+  const bool two = bytes16 <= 110 * 1024;
+  if (!two && bytes32 > 200 * 1024) return 1;
+#define SERT_FUSED_CASE(CWv, CEv)                                              \
+  if (cw == CWv && ce == CEv)                                                  \
+    return two ? launch_t<16, CWv, CEv>(a, bytes16, st) : launch_t<32, CWv, CEv>(a, bytes32, st);
+  SERT_FUSED_CASE(4, 4)     // d = 128 (BASELINE configs[1])
+  SERT_FUSED_CASE(2, 2)     // d = 64
+  SERT_FUSED_CASE(1, 1)     // d = 32
+  SERT_FUSED_CASE(4, 2)
+  SERT_FUSED_CASE(2, 4)
+  SERT_FUSED_CASE(8, 4)     // dw = 256, de = 128
+#undef SERT_FUSED_CASE
   return 1;
 }
 
