@@ -28,6 +28,7 @@ if ROOT not in sys.path:
 
 CFG2 = dict(V=100000, E=50000, dw=128, de=128, W=10, B=4096, k=10, lam=0.01)
 CFG3 = dict(Q=10000, E=50000, d=128, k=100)
+CFG4 = dict(Q=10000, E=1000000, d=256, k=100)
 METRIC = '(word,entity) pairs/sec train'
 UNIT = 'pairs/s'
 
@@ -54,7 +55,30 @@ class ClockSampler(object):
         self.stop_flag = threading.Event()
         self.thread = threading.Thread(target=self._run, daemon=True)
 
+    def _run_nvml(self):
+        """NVML polling (about 1 kHz possible; 2 ms period here) -- the nvidia-smi CLI needs ~100 ms per query,
+        longer than a short timed region."""
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(self.gpu_index)
+        mx = pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM)
+        bits = {'hw_slowdown': 0x8, 'sw_power_cap': 0x4, 'sw_thermal_slowdown': 0x20, 'hw_thermal_slowdown': 0x40}
+        get_reasons = getattr(pynvml, 'nvmlDeviceGetCurrentClocksEventReasons',
+                              getattr(pynvml, 'nvmlDeviceGetCurrentClocksThrottleReasons', None))
+        while not self.stop_flag.is_set():
+            sm = pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM)
+            mask = get_reasons(h) if get_reasons else 0
+            row = ['', str(sm), str(mx), '', '']
+            row += ['Active' if mask & bits[n] else 'Not Active'
+                    for n in ('hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap')]
+            self.samples.append(row)
+            self.stop_flag.wait(0.002)
+
     def _run(self):
+        try:
+            return self._run_nvml()
+        except Exception:
+            pass
         while not self.stop_flag.is_set():
             try:
                 out = subprocess.run(['nvidia-smi', '-i', str(self.gpu_index), '--query-gpu=' + self.Q,
@@ -256,32 +280,8 @@ def run_ours(args, rank, world, local_rank):
     del model
 
     # ---- entity scoring (row-sharded; one all-gather of per-shard top-k) ----
-    sc = CFG3
-    rng = np.random.default_rng(20160816 + 3)
-    ent = rng.standard_normal((sc['E'], sc['d'])).astype(np.float32)
-    ent /= np.linalg.norm(ent, axis=1)[:, None]
-    qs = rng.standard_normal((sc['Q'], sc['d'])).astype(np.float32)
-    qs /= np.linalg.norm(qs, axis=1)[:, None]
-    scorer = ShardedScorer(ent, sc['E'], max_queries=sc['Q'], max_k=128)
-    q_dev = torch.from_numpy(qs).cuda()
-    for _ in range(3):
-        scorer.topk_dev(q_dev, sc['k'])
-    barrier()
-    s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    reps = 5
-    s0.record()
-    for _ in range(reps):
-        idx, score = scorer.topk_dev(q_dev, sc['k'])
-    s1.record()
-    barrier()
-    sms = torch.tensor([s0.elapsed_time(s1) / reps], dtype=torch.float64, device='cuda')
-    if world > 1:
-        dist.all_reduce(sms, op=dist.ReduceOp.MAX)
-    score_value = sc['Q'] * sc['E'] / (float(sms.item()) * 1e-3)
-    # e2e scoring: host queries in, host lists out
-    t0 = time.perf_counter()
-    scorer.topk(qs, sc['k'])
-    score_e2e = sc['Q'] * sc['E'] / (time.perf_counter() - t0)
+    scoring = run_scoring(CFG4, 'BASELINE.json configs[3]', rank, world, barrier, cpu=False)
+    scoring_small = run_scoring(CFG3, 'BASELINE.json configs[2]', rank, world, barrier, cpu=(rank == 0))
 
     loglinear = run_loglinear_cfg1(rank) if rank == 0 else None
 
@@ -310,15 +310,87 @@ def run_ours(args, rank, world, local_rank):
                          'step_frac_of_hbm_peak': step_bytes / (ms_max / steps * 1e-3) / 1e9 / peak},
             'cpu_baseline': cpu,
             'loglinear': loglinear,
-            'scoring': {'metric': 'scored entities/sec', 'value': score_value, 'unit': 'entities/s',
-                        'workload': 'BASELINE.json configs[2]: Q=10000 x E=50000 d=128 top-100, rows sharded '
-                                    'over %d GPU(s), one all-gather' % world,
-                        'ms': float(sms.item()), 'e2e_value': score_e2e,
-                        'tflops': 2.0 * sc['Q'] * sc['E'] * sc['d'] / (float(sms.item()) * 1e-3) / 1e12},
+            'scoring': scoring,
+            'scoring_small': scoring_small,
         }
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
+
+
+def run_scoring(sc, label, rank, world, barrier, cpu):
+    """Scored entities/s for Q queries x E entities, top-k: rows sharded over the ranks (each rank builds only
+    its shard), ONE all-gather of the per-shard lists, merge on every rank."""
+    import torch
+    import torch.distributed as dist
+    from sert_b200.scoring import ShardedScorer, shard_bounds
+    begin, end = shard_bounds(sc['E'], world, rank)
+    rng = np.random.default_rng(20160816 + 3 + 7919 * rank)
+    ent = rng.standard_normal((end - begin, sc['d']), dtype=np.float32)
+    ent /= np.linalg.norm(ent, axis=1)[:, None]
+    qs = np.random.default_rng(20160816 + 4).standard_normal((sc['Q'], sc['d']), dtype=np.float32)
+    qs /= np.linalg.norm(qs, axis=1)[:, None]
+    scorer = ShardedScorer(ent, sc['E'], is_shard=True, max_queries=sc['Q'], max_k=128)
+    q_dev = torch.from_numpy(qs).cuda()
+    for _ in range(2):
+        scorer.topk_dev(q_dev, sc['k'])
+    barrier()
+    s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    reps = 3
+    s0.record()
+    for _ in range(reps):
+        scorer.topk_dev(q_dev, sc['k'])
+    s1.record()
+    barrier()
+    sms = torch.tensor([s0.elapsed_time(s1) / reps], dtype=torch.float64, device='cuda')
+    if world > 1:
+        dist.all_reduce(sms, op=dist.ReduceOp.MAX)
+    ms = float(sms.item())
+    # e2e: host queries in, host lists out (H2D of the queries, D2H of the lists inside the timed region)
+    barrier()
+    t0 = time.perf_counter()
+    scorer.topk(qs, sc['k'])
+    e2e_s = time.perf_counter() - t0
+    out = {'metric': 'scored entities/sec', 'value': sc['Q'] * sc['E'] / (ms * 1e-3), 'unit': 'entities/s',
+           'workload': '%s: Q=%d x E=%d d=%d top-%d, float32 vectors, rows sharded over %d GPU(s), one all-gather'
+                       % (label, sc['Q'], sc['E'], sc['d'], sc['k'], world),
+           'ms': ms, 'e2e_value': sc['Q'] * sc['E'] / e2e_s,
+           'algorithmic_tflops': 2.0 * sc['Q'] * sc['E'] * sc['d'] / (ms * 1e-3) / 1e12,
+           'tensor_tflops_bf16x3': 6.0 * sc['Q'] * sc['E'] * sc['d'] / (ms * 1e-3) / 1e12}
+    if cpu and world == 1:
+        out['cpu_baseline'] = scoring_cpu_baseline(ent, qs, sc['k'])
+    scorer.local.close()
+    del scorer
+    torch.cuda.empty_cache()
+    return out
+
+
+def scoring_cpu_baseline(ent, qs, k):
+    """(i) the reference's literal path (bin/query.py:304-359): per-query kd-tree k-NN + per-candidate scoring,
+    on a bounded sample of queries; (ii) a strong CPU baseline: batched sgemm + argpartition."""
+    import sklearn.neighbors
+    n_lit = 8
+    nn = sklearn.neighbors.NearestNeighbors(n_neighbors=k, algorithm='kd_tree', metric='euclidean')
+    nn.fit(ent)                                    # index build is not timed (done once in the callback's __init__)
+    t0 = time.perf_counter()
+    for i in range(n_lit):
+        _, indices = nn.kneighbors(qs[i:i + 1])
+        cands = {}
+        for candidate in indices[0, :]:            # the per-candidate Python loop of bin/query.py:348-359
+            cands[candidate] = (np.sum(ent[candidate, :] * qs[i, :]) + 1.0) / 2.0
+        sorted(cands.items(), reverse=True, key=lambda kv: kv[1])
+    lit = (time.perf_counter() - t0) / n_lit
+    n_b = 512
+    t0 = time.perf_counter()
+    s = qs[:n_b] @ ent.T
+    part = np.argpartition(-s, k, axis=1)[:, :k]
+    np.take_along_axis(s, part, axis=1).argsort(axis=1)
+    bat = (time.perf_counter() - t0) / n_b
+    E = ent.shape[0]
+    return {'literal_reference_path': {'value': E / lit, 'unit': 'entities/s', 'sample': '%d queries, sklearn kd_tree '
+                                       'k-NN (index build untimed) + per-candidate scoring loop' % n_lit},
+            'batched_sgemm_argpartition': {'value': E / bat, 'unit': 'entities/s', 'sample': '%d queries' % n_b},
+            'cores': len(os.sched_getaffinity(0)), 'kind': 'port'}
 
 
 def run_loglinear_cfg1(rank):

@@ -271,6 +271,7 @@ gemm_tc_kernel(const __grid_constant__ TcMap map_a, const __grid_constant__ TcMa
         // the instruction caches (a fully unrolled two-pass version measured 6x slower: the warps sat in
         // "no instruction" stalls).  Pass 1 counts this row's survivors, one compare per score.
         int total = 0;
+        uint32_t chunk_any = 0;                                          // warp-uniform: chunks with a survivor
 #pragma unroll 1
         for (int ci = 0; ci < BN / 32; ++ci) {
           uint32_t v[32];
@@ -282,11 +283,12 @@ gemm_tc_kernel(const __grid_constant__ TcMap map_a, const __grid_constant__ TcMa
 #pragma unroll
           for (int j = 0; j < 32; ++j) cnt += (j < nv && __uint_as_float(v[j]) > tau_score) ? 1 : 0;
           total += cnt;
+          chunk_any |= (__any_sync(0xffffffffu, cnt > 0) ? 1u : 0u) << ci;
         }
         // Pass 2 (rare once tau has warmed up): ONE atomic per thread reserves its slots, then TMEM is read
         // again.  tcgen05.ld is warp-collective (.sync.aligned), so the chunk loop is warp-uniform; only the
         // per-lane key stores diverge.
-        if (__any_sync(0xffffffffu, total > 0)) {
+        if (chunk_any != 0u) {
           int pos = 0;
           unsigned long long *list = ep.cand + (size_t)(row_ok ? gm : 0) * ep.cap;
           if (total > 0) {
@@ -295,6 +297,7 @@ gemm_tc_kernel(const __grid_constant__ TcMap map_a, const __grid_constant__ TcMa
           }
 #pragma unroll 1
           for (int ci = 0; ci < BN / 32; ++ci) {
+            if (!((chunk_any >> ci) & 1u)) continue;                    // warp-uniform skip
             uint32_t v[32];
             tc_ld_32x32(t_row + (uint32_t)(ci * 32), v);
             tc_wait_ld();
@@ -471,5 +474,49 @@ extern "C" SERT_API int sert_debug_gemm_tc(const float *a_host, const float *b_h
   }
   if (!rc) SERT_CUDA(cudaMemcpy(c_host, dC, (size_t)m * n * 4, cudaMemcpyDeviceToHost));
   cudaFree(dA); cudaFree(dB); cudaFree(dC); cudaFree(sA); cudaFree(sB); cudaFree(dbias);
+  return rc;
+}
+
+// ---- measurement hook: raw throughput of the tcgen05 kernel on zero operands ---------------------------
+// mode 0: fp32 store epilogue into ONE aliased row (ldc = 0: the C traffic stays in L2), mode 1: top-k filter
+// with thresholds that reject everything (pass 1 only).  Returns the mean launch time in milliseconds.
+extern "C" SERT_API int sert_debug_gemm_tc_bench(int m, int n, int kt, int reps, int mode, float *ms_out) {
+  using namespace sert;
+  SERT_REQUIRE(m > 0 && n > 0 && kt > 0 && kt % 64 == 0 && reps > 0 && ms_out, "bad argument");
+  __nv_bfloat16 *A = nullptr, *B = nullptr;
+  float *C = nullptr;
+  unsigned long long *tau = nullptr, *cand = nullptr;
+  int *count = nullptr, *overflow = nullptr;
+  SERT_CUDA(cudaMalloc(&A, (size_t)m * kt * 2));
+  SERT_CUDA(cudaMalloc(&B, (size_t)n * kt * 2));
+  SERT_CUDA(cudaMalloc(&C, (size_t)n * 4 + 1024));
+  SERT_CUDA(cudaMalloc(&tau, (size_t)m * 8));
+  SERT_CUDA(cudaMalloc(&cand, (size_t)m * 64 * 8));
+  SERT_CUDA(cudaMalloc(&count, (size_t)m * 4));
+  SERT_CUDA(cudaMalloc(&overflow, 4));
+  SERT_CUDA(cudaMemset(A, 0, (size_t)m * kt * 2));
+  SERT_CUDA(cudaMemset(B, 0, (size_t)n * kt * 2));
+  SERT_CUDA(cudaMemset(tau, 0xff, (size_t)m * 8));      // threshold decodes to NaN: no score compares greater
+  SERT_CUDA(cudaMemset(count, 0, (size_t)m * 4));
+  TcEpilogue ep;
+  if (mode == 0) {
+    ep.mode = TC_EPI_STORE; ep.C = C; ep.ldc = 0;
+  } else {
+    ep.mode = TC_EPI_TOPK; ep.tau = tau; ep.count = count; ep.cand = cand; ep.cap = 64; ep.overflow = overflow;
+  }
+  cudaEvent_t e0, e1;
+  SERT_CUDA(cudaEventCreate(&e0));
+  SERT_CUDA(cudaEventCreate(&e1));
+  int rc = 0;
+  for (int i = 0; i < 2 && !rc; ++i) rc = launch_gemm_tc(A, m, B, n, 0, n, kt, ep, nullptr);
+  SERT_CUDA(cudaEventRecord(e0));
+  for (int i = 0; i < reps && !rc; ++i) rc = launch_gemm_tc(A, m, B, n, 0, n, kt, ep, nullptr);
+  SERT_CUDA(cudaEventRecord(e1));
+  cudaError_t e = cudaEventSynchronize(e1);
+  if (!rc && e != cudaSuccess) { set_error(cudaGetErrorString(e)); rc = -1; }
+  float ms = 0.f;
+  if (!rc) { SERT_CUDA(cudaEventElapsedTime(&ms, e0, e1)); *ms_out = ms / reps; }
+  cudaFree(A); cudaFree(B); cudaFree(C); cudaFree(tau); cudaFree(cand); cudaFree(count); cudaFree(overflow);
+  cudaEventDestroy(e0); cudaEventDestroy(e1);
   return rc;
 }
