@@ -112,6 +112,9 @@ SERT_API int sert_model_profile(sert_model *m, int enable);
 /* Vector-space training step: 1 (default) = fused per-tile kernel when the shape fits in shared memory,
  * 0 = one kernel per stage (general shapes; also what the fused kernel is tested against). */
 SERT_API int sert_model_set_fused(sert_model *m, int enable);
+/* Log-linear word x entity GEMMs (sert/models.py:846-849 and its two gradients): 1 (default) = tcgen05 tensor
+ * cores on bf16x3-split operands whenever the output has >= 32 tiles of 128x256, 0 = fp32 FMA tiles always. */
+SERT_API int sert_model_set_tensor_cores(sert_model *m, int enable);
 SERT_API int sert_model_profile_read(sert_model *m, double *update_ms_total, int64_t *update_launches,
                                      double *update_bytes_per_launch);
 
@@ -191,6 +194,9 @@ SERT_API int sert_topk_merge_dev(const int32_t *idx_dev, const float *score_dev,
  * split terms per operand; host in / host out.  Used by tests/test_gpu_gemm_tc.py only. */
 SERT_API int sert_debug_gemm_tc(const float *a_host, const float *b_host, int m, int n, int k, int terms,
                                 const float *bias_host, float *c_host);
+/* Raw throughput of the tcgen05 kernel on zero operands (mode 0: store epilogue into one aliased row, mode 1:
+ * top-k filter that rejects everything); mean launch time in ms.  Used by tools/gemm_bench.py only. */
+SERT_API int sert_debug_gemm_tc_bench(int m, int n, int kt, int reps, int mode, float *ms_out);
 
 #ifdef __cplusplus
 }

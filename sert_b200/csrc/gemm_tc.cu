@@ -520,3 +520,53 @@ extern "C" SERT_API int sert_debug_gemm_tc_bench(int m, int n, int kt, int reps,
   cudaEventDestroy(e0); cudaEventDestroy(e1);
   return rc;
 }
+
+// ---- transposing fp32 -> bf16 split: dst (C, terms * R64) <- src (R, C) ----------------------------------
+namespace sert {
+
+__global__ void __launch_bounds__(256) split_bf16_t_kernel(const float *__restrict__ src, long long R, long long C,
+                                                           long long ld_src, long long Rp, int terms, int role,
+                                                           __nv_bfloat16 *__restrict__ dst) {
+  __shared__ float tile[32][33];
+  const long long c_tiles = (C + 31) / 32;
+  const long long r_tiles = Rp / 32;
+  for (long long t = blockIdx.x; t < c_tiles * r_tiles; t += gridDim.x) {
+    const long long r0 = (t / c_tiles) * 32, c0 = (t % c_tiles) * 32;
+    for (int j = threadIdx.y; j < 32; j += 8) {
+      const long long r = r0 + j, c = c0 + threadIdx.x;
+      tile[j][threadIdx.x] = (r < R && c < C) ? src[r * ld_src + c] : 0.f;
+    }
+    __syncthreads();
+    for (int j = threadIdx.y; j < 32; j += 8) {
+      const long long c = c0 + j, r = r0 + threadIdx.x;
+      if (c < C) {
+        const float x = tile[threadIdx.x][j];
+        const __nv_bfloat16 hi = __float2bfloat16_rn(x);
+        __nv_bfloat16 *d = dst + c * (terms * Rp) + r;
+        if (terms == 1) {
+          d[0] = hi;
+        } else {
+          const __nv_bfloat16 mid = __float2bfloat16_rn(x - __bfloat162float(hi));
+          d[0] = hi;
+          d[Rp] = role == SPLIT_A ? hi : mid;
+          d[2 * Rp] = role == SPLIT_A ? mid : hi;
+        }
+      }
+    }
+    __syncthreads();
+  }
+}
+
+int launch_split_bf16_t(const float *src, long long R, long long C, long long ld_src, int terms, SplitRole role,
+                        __nv_bfloat16 *dst, cudaStream_t st) {
+  SERT_REQUIRE(terms == 1 || terms == 3, "split terms must be 1 or 3");
+  if (R == 0 || C == 0) return 0;
+  const long long Rp = tc_padded_k((int)R);
+  const long long tiles = ((C + 31) / 32) * (Rp / 32);
+  const int blocks = (int)std::min<long long>(tiles, (long long)kNumSMs * 32);
+  split_bf16_t_kernel<<<blocks, dim3(32, 8), 0, st>>>(src, R, C, ld_src, Rp, terms, (int)role, dst);
+  SERT_LAUNCH_CHECK();
+  return 0;
+}
+
+}  // namespace sert

@@ -39,6 +39,10 @@ static inline int tc_padded_k(int K) { return (int)align_up((size_t)K, 64); }
 int launch_split_bf16(const float *src, long long rows, int K, long long ld_src, int terms, SplitRole role,
                       __nv_bfloat16 *dst, cudaStream_t st);
 
+// Transposing variant: dst (C, terms * R64) bf16 <- src (R, C) f32, i.e. the K-major split of src^T.
+int launch_split_bf16_t(const float *src, long long R, long long C, long long ld_src, int terms, SplitRole role,
+                        __nv_bfloat16 *dst, cudaStream_t st);
+
 // Runs the GEMM over B rows [n_begin, n_end) (columns of C).  A: (M, Kt) bf16, B: (N_total, Kt) bf16,
 // Kt = terms * Kp a multiple of 64.  For TC_EPI_STORE column n of C is B row n.
 int launch_gemm_tc(const __nv_bfloat16 *A, int M, const __nv_bfloat16 *B, long long N_total, long long n_begin,

@@ -8,6 +8,7 @@
 #include <vector>
 
 #include "kernels.cuh"
+#include "gemm_tc.cuh"
 #include "ll_kernels.cuh"
 
 namespace sert {
@@ -71,6 +72,14 @@ struct sert_model {
   float *dbg_scores = nullptr, *dbg_u = nullptr, *dbg_ell = nullptr;
   // log-linear workspaces
   float *X = nullptr, *Z = nullptr, *S = nullptr, *DS = nullptr, *dX = nullptr, *rmax = nullptr, *rsum = nullptr;
+  // bf16x3 split operands of the three word x entity GEMMs (tcgen05 path, csrc/gemm_tc.cu), all K-major:
+  __nv_bfloat16 *Xs = nullptr;     // (B*W, 3*dw64)   A of  Z  = X . Wd
+  __nv_bfloat16 *WdT_s = nullptr;  // (E,   3*dw64)   B of  Z  (transposed split of Wd (dw,E))
+  __nv_bfloat16 *dZs = nullptr;    // (B*W, 3*E64)    A of  dX = dZ . Wd^T
+  __nv_bfloat16 *Wd_s = nullptr;   // (dw,  3*E64)    B of  dX
+  __nv_bfloat16 *XT_s = nullptr;   // (dw,  3*BW64)   A of  dWd = X^T . dZ
+  __nv_bfloat16 *dZT_s = nullptr;  // (E,   3*BW64)   B of  dWd
+  bool use_tensor = true;
   // host-batch staging
   int32_t *stage_x = nullptr, *stage_y = nullptr, *stage_neg = nullptr, *stage_indices = nullptr;
   int64_t *stage_indptr = nullptr;
@@ -167,6 +176,13 @@ static size_t carve(sert_model &m, void *base) {
     m.dX = b.take<float>(B * W * dw);
     m.rmax = b.take<float>(B * W);
     m.rsum = b.take<float>(B * W);
+    const long long dw64 = tc_padded_k((int)dw), E64 = tc_padded_k((int)E), BW64 = tc_padded_k((int)(B * W));
+    m.Xs = b.take<__nv_bfloat16>(B * W * 3 * dw64);
+    m.WdT_s = b.take<__nv_bfloat16>(E * 3 * dw64);
+    m.dZs = b.take<__nv_bfloat16>(B * W * 3 * E64);
+    m.Wd_s = b.take<__nv_bfloat16>(dw * 3 * E64);
+    m.XT_s = b.take<__nv_bfloat16>(dw * 3 * BW64);
+    m.dZT_s = b.take<__nv_bfloat16>(E * 3 * BW64);
     m.dbg_ell = b.take<float>(B);
     m.stage_indptr = b.take<int64_t>(B + 1);
     m.stage_nnz_cap = (size_t)B * 64;            // host-streamed batches: up to 64 labels per row on average
@@ -309,6 +325,12 @@ static int vs_eval_step(sert_model &m, const int32_t *x, const int32_t *y, const
 }
 
 // ---- log-linear ---------------------------------------------------------------------------------
+// The tcgen05 kernel works on 128 x 256 output tiles with one persistent CTA per SM: it is used when the
+// output has enough tiles to occupy the chip, the fp32 FMA tiles (with split-K) otherwise.
+static bool ll_tensor(const sert_model &m, long long M, long long N) {
+  return m.use_tensor && ((M + 127) / 128) * ((N + 255) / 256) >= 32;
+}
+
 static int ll_forward(sert_model &m, const int32_t *x, int rows /* instances */, cudaStream_t st) {
   const sert_config &c = m.cfg;
   const int E = (int)c.entities, dw = c.word_dim;
@@ -317,7 +339,17 @@ static int ll_forward(sert_model &m, const int32_t *x, int rows /* instances */,
   float *Wd = m.theta + m.off[SERT_PARAM_DENSE_W];
   float *bd = m.theta + m.off[SERT_PARAM_DENSE_B];
   if (launch_gather_rows(x, R, m.X, BW, dw, st)) return -1;
-  if (launch_gemm_f32(m.X, Wd, m.Z, (int)BW, E, dw, false, false, dw, E, E, EPI_BIAS, bd, 1, st)) return -1;
+  if (ll_tensor(m, BW, E)) {
+    // Z = X . Wd + bd on the tensor cores: bf16x3 split of X (A) and of Wd^T (B), fp32 accumulation
+    const int kt = 3 * tc_padded_k(dw);
+    if (launch_split_bf16(m.X, BW, dw, dw, 3, SPLIT_A, m.Xs, st)) return -1;
+    if (launch_split_bf16_t(Wd, dw, E, E, 3, SPLIT_B, m.WdT_s, st)) return -1;
+    TcEpilogue ep;
+    ep.mode = TC_EPI_STORE; ep.C = m.Z; ep.ldc = E; ep.bias = bd;
+    if (launch_gemm_tc(m.Xs, (int)BW, m.WdT_s, E, 0, E, kt, ep, st)) return -1;
+  } else {
+    if (launch_gemm_f32(m.X, Wd, m.Z, (int)BW, E, dw, false, false, dw, E, E, EPI_BIAS, bd, 1, st)) return -1;
+  }
   return launch_ll_row_stats(m.Z, BW, E, E, m.rmax, m.rsum, st);
 }
 
@@ -345,11 +377,31 @@ static int ll_train_step(sert_model &m, const int32_t *x, const int64_t *indptr,
   if (launch_ll_instance(ll_instance_args(m, indptr, nnz_base, indices, data, w, true, nullptr), st)) return -1;
   if (launch_ll_dz(m.Z, m.rmax, m.rsum, m.DS, B, W, E, E, E, st)) return -1;
   // gWd += X^T . dZ ; gbd += colsum(dZ) ; dX = dZ . Wd^T
-  if (launch_gemm_f32(m.X, m.Z, m.grad + m.off[SERT_PARAM_DENSE_W], dw, E, BW, true, false, dw, E, E,
-                      EPI_ATOMIC_ADD, nullptr, pick_split_k(dw, E, BW), st))
-    return -1;
+  if (ll_tensor(m, dw, E)) {
+    // gWd = X^T . dZ : A = X^T (dw, B*W), B = dZ^T (E, B*W), both as transposed bf16x3 splits
+    const int kt = 3 * tc_padded_k(BW);
+    if (launch_split_bf16_t(m.X, BW, dw, dw, 3, SPLIT_A, m.XT_s, st)) return -1;
+    if (launch_split_bf16_t(m.Z, BW, E, E, 3, SPLIT_B, m.dZT_s, st)) return -1;
+    TcEpilogue ep;
+    ep.mode = TC_EPI_STORE; ep.C = m.grad + m.off[SERT_PARAM_DENSE_W]; ep.ldc = E;   // overwrites the (zeroed) grad
+    if (launch_gemm_tc(m.XT_s, dw, m.dZT_s, E, 0, E, kt, ep, st)) return -1;
+  } else {
+    if (launch_gemm_f32(m.X, m.Z, m.grad + m.off[SERT_PARAM_DENSE_W], dw, E, BW, true, false, dw, E, E,
+                        EPI_ATOMIC_ADD, nullptr, pick_split_k(dw, E, BW), st))
+      return -1;
+  }
   if (launch_colsum_atomic(m.Z, m.grad + m.off[SERT_PARAM_DENSE_B], BW, E, st)) return -1;
-  if (launch_gemm_f32(m.Z, Wd, m.dX, BW, dw, E, false, true, E, E, dw, EPI_STORE, nullptr, 1, st)) return -1;
+  if (ll_tensor(m, BW, dw)) {
+    // dX = dZ . Wd^T : A = dZ (B*W, E), B = Wd (dw, E)
+    const int kt = 3 * tc_padded_k(E);
+    if (launch_split_bf16(m.Z, BW, E, E, 3, SPLIT_A, m.dZs, st)) return -1;
+    if (launch_split_bf16(Wd, dw, E, E, 3, SPLIT_B, m.Wd_s, st)) return -1;
+    TcEpilogue ep;
+    ep.mode = TC_EPI_STORE; ep.C = m.dX; ep.ldc = dw;
+    if (launch_gemm_tc(m.dZs, BW, m.Wd_s, dw, 0, dw, kt, ep, st)) return -1;
+  } else {
+    if (launch_gemm_f32(m.Z, Wd, m.dX, BW, dw, E, false, true, E, E, dw, EPI_STORE, nullptr, 1, st)) return -1;
+  }
   if (launch_scatter_rows(x, m.dX, m.grad + m.off[SERT_PARAM_WORD_REPR], m.flagR, m.stamp, BW, 1, dw, 1.0f, st))
     return -1;
   m.step += 1;
@@ -476,6 +528,12 @@ int sert_model_get_step(sert_model *m, int64_t *t) {
 int sert_model_set_fused(sert_model *m, int enable) {
   SERT_REQUIRE(m, "null model");
   m->use_fused = enable != 0;
+  return 0;
+}
+
+int sert_model_set_tensor_cores(sert_model *m, int enable) {
+  SERT_REQUIRE(m, "null model");
+  m->use_tensor = enable != 0;
   return 0;
 }
 

@@ -119,3 +119,30 @@ def test_predict_fn_matches_oracle_and_pickles():
     np.testing.assert_allclose(got.sum(axis=2), 1.0, atol=1e-5)
     # fewer rows than the batch size (the batcher always sends full batches, but the ABI allows less)
     H.close(fn(batch[:3], mask[:3]), ref[:3], what='partial batch')
+
+
+@pytest.mark.parametrize('dims,tensor', [
+    (dict(V=3000, E=300, dw=64, W=10, B=512), 1),      # Z and dX on tcgen05 (40 tiles each), dWd on FMA tiles
+    (dict(V=2000, E=4096, dw=256, W=4, B=64), 1),      # Z and dWd on tcgen05 (32 tiles each), dX on FMA tiles
+    (dict(V=3000, E=300, dw=64, W=10, B=512), 0),      # same shapes, tensor cores off
+])
+def test_tensor_core_projection_matches_oracle(dims, tensor):
+    """The word x entity GEMMs through the tcgen05 bf16x3 path: logits within 1e-4 relative, 3 Adadelta steps."""
+    from oracle import sert_oracle as O
+    from sert_b200 import _native as N
+    p = H.ll_problem(41, n_batches=3, gain=2.0, **dims)
+    lam = 0.01
+    model = make_model(p, lam)
+    N.check(model._native.lib.sert_model_set_tensor_cores(model._native.handle, tensor))
+    oracle = H.ll_oracle(p, lam)
+    z, s, ell = forward_host(model, 0, 1)
+    B = p['B']
+    f = O.loglinear_forward(p['R'], p['Wd'], p['bd'], p['train'][0][B:2 * B])
+    H.close(z, f['z'].reshape(z.shape), what='per-word logits z')
+    H.close(s, f['s'], what='joint logits s')
+    for j, b in enumerate([2, 0, 1]):
+        H.close(model.train_fn(b), oracle.train_batch(b), what='train loss step %d' % j)
+    Wd, bd = model.get_dense()
+    H.close(model.get_representations(), oracle.R, rtol=2e-4, what='R')
+    H.close(Wd, oracle.Wd, rtol=2e-4, what='Wd')
+    H.close(bd, oracle.bd, rtol=2e-4, atol_scale=1e-4, what='bd')
