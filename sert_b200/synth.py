@@ -102,3 +102,46 @@ def vectorspace_corpus(seed, V, E, W, n_train, n_val):
 def glorot(rng, shape):
     a = np.sqrt(6.0 / (shape[0] + shape[1]))
     return rng.uniform(-a, a, size=shape).astype(np.float32)
+
+
+def write_corpus_files(directory, kind, seed, V, E, W, n_train, n_val, num_topics=12):
+    """Writes `data.npz`, `meta` and `topics` in the reference's on-disk formats (bin/prepare.py:373-416):
+    meta = 5 sequential pickles (args, words{str->Word(id,count)}, tokens[str], entity_indices_inv{int->str},
+    documents_per_entity); data.npz = x_train, y_train (CSR pickled as a 0-d object array), w_train,
+    x_validate, y_validate; topics = `topic_id;terms` lines.  Returns the paths."""
+    import argparse
+    import os
+    import pickle
+    from cvangysel.io_utils import Word
+    rng = np.random.default_rng(seed)
+    train, val = loglinear_corpus(seed, V, E, W, n_train, n_val)
+    def alpha(i):                       # letters only: parse_query drops digits (io_utils.py:70-88)
+        out = ''
+        while True:
+            out = chr(ord('a') + i % 26) + out
+            i //= 26
+            if i == 0:
+                return 'tok' + out
+    tokens = [alpha(i) for i in range(V)]
+    words = {tok: Word(id=i, count=int(V - i)) for i, tok in enumerate(tokens)}
+    entity_indices_inv = {i: 'entity-%05d' % i for i in range(E)}
+    documents_per_entity = {name: ['doc-%d' % i] for i, name in entity_indices_inv.items()}
+    data_args = argparse.Namespace(window_size=W, kind=kind)
+    os.makedirs(directory, exist_ok=True)
+    meta_path = os.path.join(directory, 'meta')
+    with open(meta_path, 'wb') as f:
+        for obj in (data_args, words, tokens, entity_indices_inv, documents_per_entity):
+            pickle.dump(obj, f, protocol=pickle.HIGHEST_PROTOCOL)
+    data_path = os.path.join(directory, 'data.npz')
+    with open(data_path, 'wb') as f:
+        np.savez(f, x_train=train[0], y_train=train[1], w_train=train[2], x_validate=val[0], y_validate=val[1])
+    topics_path = os.path.join(directory, 'topics')
+    with open(topics_path, 'w') as f:
+        for t in range(num_topics):
+            n_terms = int(rng.integers(1, 2 * W + 3))
+            terms = [tokens[int(i)] for i in sample_zipf(rng, V, n_terms)]
+            if t % 5 == 0:
+                terms.append('zzzunknownzzz')                     # an out-of-vocabulary term
+            f.write('T%03d;%s\n' % (t, ' '.join(terms)))
+        f.write('T999;onlyunknownterms here\n')                   # skipped with a warning (bin/query.py:139-142)
+    return data_path, meta_path, topics_path
