@@ -98,7 +98,12 @@ struct OptimArgs {
   unsigned int *ticket;            // unused (kept for layout stability)
   float *loss_out;
   float inv_B, reg_coeff;
+  int phase = 0;                   // 0 = all rows, 1 = rows not stamped this step, 2 = stamped rows + dense tensors
 };
+
+// stamps the table rows a vector-space batch will touch (word rows of x, entity rows of y and of the negatives)
+int launch_mark_rows(const int32_t *x, long long nx, const int32_t *y, long long ny, const int32_t *neg,
+                     long long nneg, uint32_t *flagR, uint32_t *flagE, uint32_t stamp, cudaStream_t st);
 int launch_adam(const OptimArgs &a, cudaStream_t st);
 int launch_adadelta(const OptimArgs &a, cudaStream_t st);
 // eval loss finalisation: loss_out = acc[0]*inv_B ; acc[0] = 0

@@ -28,7 +28,10 @@ __device__ __forceinline__ float fast_sqrt(float x) {
 // (tools/bw_probe.cu) the in-place 3-stream read-modify-write reaches 6.50 TB/s this way vs 5.3-6.2 TB/s
 // for persistent grid-stride variants -- the block scheduler interleaves the load and store phases of
 // many short CTAs better than a resident wave does.
-template <bool ADAM>
+// PHASE 0: every row.  PHASE 1: only table rows NOT stamped this step (their gradient is the L2 term alone, so
+// they can be updated while the forward/backward kernels of the same step are still running on another
+// stream).  PHASE 2: the stamped rows plus the dense tensors (projection matrix, bias).
+template <bool ADAM, int PHASE>
 __global__ void __launch_bounds__(256) dense_update_kernel(OptimArgs a) {
   const long long total4 = a.total >> 2;
   float4 *__restrict__ th4 = reinterpret_cast<float4 *>(a.theta);
@@ -47,15 +50,16 @@ __global__ void __launch_bounds__(256) dense_update_kernel(OptimArgs a) {
     for (int q = 1; q < kMaxSegments; ++q) s += (q < a.num_segments && e >= a.seg[q].offset) ? 1 : 0;
     const ParamSegment &sg = a.seg[s];
     const bool live = (e - sg.offset) < sg.count;   // false only inside inter-segment padding
-    if (live) {
+    bool touched = true;
+    if (live && sg.flags != nullptr) {
+      const unsigned int row = (unsigned int)(e - sg.offset) / (unsigned int)sg.row_len;
+      touched = (__ldg(sg.flags + row) == a.stamp);
+    }
+    const bool mine = PHASE == 0 ? true : (PHASE == 1 ? (sg.flags != nullptr && !touched) : touched);
+    if (live && mine) {
       const float4 p = th4[i4];
       const float4 x1 = s14[i4];
       const float4 x2 = s24[i4];
-      bool touched = true;
-      if (sg.flags != nullptr) {
-        const unsigned int row = (unsigned int)(e - sg.offset) / (unsigned int)sg.row_len;
-        touched = (__ldg(sg.flags + row) == a.stamp);
-      }
       float4 g = make_float4(0.f, 0.f, 0.f, 0.f);
       if (touched) g = __ldcg(g4 + i4);
       const float l2 = sg.regularised ? a.l2_scale : 0.0f;
@@ -125,13 +129,21 @@ static int launch_update(const OptimArgs &a, bool adam, cudaStream_t st) {
   const long long total4 = a.total / 4;
   const long long blocks = std::max<long long>(1, (total4 + 255) / 256);
   SERT_REQUIRE(blocks < (1ll << 31), "parameter arena too large for one launch");
-  if (adam)
-    dense_update_kernel<true><<<(int)blocks, 256, 0, st>>>(a);
-  else
-    dense_update_kernel<false><<<(int)blocks, 256, 0, st>>>(a);
+  const int g = (int)blocks;
+  if (adam) {
+    if (a.phase == 1) dense_update_kernel<true, 1><<<g, 256, 0, st>>>(a);
+    else if (a.phase == 2) dense_update_kernel<true, 2><<<g, 256, 0, st>>>(a);
+    else dense_update_kernel<true, 0><<<g, 256, 0, st>>>(a);
+  } else {
+    if (a.phase == 1) dense_update_kernel<false, 1><<<g, 256, 0, st>>>(a);
+    else if (a.phase == 2) dense_update_kernel<false, 2><<<g, 256, 0, st>>>(a);
+    else dense_update_kernel<false, 0><<<g, 256, 0, st>>>(a);
+  }
   SERT_LAUNCH_CHECK();
-  finalize_train_kernel<<<1, kSumsqSlots, 0, st>>>(a.acc, a.loss_out, a.inv_B, a.reg_coeff);
-  SERT_LAUNCH_CHECK();
+  if (a.phase != 1) {          // the loss is complete once the stamped rows have been processed
+    finalize_train_kernel<<<1, kSumsqSlots, 0, st>>>(a.acc, a.loss_out, a.inv_B, a.reg_coeff);
+    SERT_LAUNCH_CHECK();
+  }
   return 0;
 }
 

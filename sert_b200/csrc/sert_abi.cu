@@ -87,6 +87,12 @@ struct sert_model {
   size_t stage_nnz_cap = 0;
   // optional per-kernel timing of the dense update (bench.py's roofline leg)
   bool use_fused = true;              // fused tile kernel for the vector-space step when the shape fits
+  // second stream + fork/join events: the untouched-row part of the dense update can overlap the fwd/bwd kernels.
+  // Off by default: measured on B200 (cfg2) it does not pay -- the latency-bound fwd/bwd kernel slows down by
+  // about as much as the overlap saves once the streaming update saturates HBM (0.153 vs 0.150 ms/step).
+  bool overlap = false;
+  cudaStream_t st2 = nullptr;
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
   bool profile = false;
   std::vector<std::pair<cudaEvent_t, cudaEvent_t>> prof_events;
 };
@@ -267,6 +273,22 @@ static int vs_train_step(sert_model &m, const int32_t *x, const int32_t *y, cons
       return -1;
     neg = m.neg;
   }
+  // Rows this batch does not touch only receive the L2 gradient, which does not depend on the batch: their
+  // Adam update (about two thirds of the 24 B/param stream at cfg2) overlaps the forward/backward kernels,
+  // which read touched rows only.  The forward/backward kernels go to a library-owned HIGH-priority stream
+  // (enqueued first, so the block scheduler hands them SM slots ahead of the streaming kernel's thousands of
+  // short CTAs); the caller's stream runs the untouched-row update, joins, then updates the stamped rows.
+  const bool overlap = m.overlap && !m.profile && m.st2 != nullptr;
+  const int64_t t_next = m.step + 1;
+  cudaStream_t main_st = m.st;
+  if (overlap) {
+    if (launch_mark_rows(x, (long long)B * c.window, y, B, neg, (long long)B * c.num_negatives, m.flagR, m.flagE,
+                         m.stamp, main_st))
+      return -1;
+    SERT_CUDA(cudaEventRecord(m.ev_fork, main_st));
+    SERT_CUDA(cudaStreamWaitEvent(m.st2, m.ev_fork, 0));
+    st = m.st2;
+  }
   VsFusedArgs f;
   f.x = x; f.R = m.theta + m.off[SERT_PARAM_WORD_REPR]; f.Wp = Wp; f.bp = m.theta + m.off[SERT_PARAM_DENSE_B];
   f.Eemb = m.theta + m.off[SERT_PARAM_ENTITY_REPR]; f.y = y; f.neg = neg; f.w = w;
@@ -296,9 +318,19 @@ static int vs_train_step(sert_model &m, const int32_t *x, const int32_t *y, cons
                       EPI_ATOMIC_ADD, nullptr, pick_split_k(dw, de, B), st))
     return -1;
   if (launch_colsum_atomic(m.da, m.grad + m.off[SERT_PARAM_DENSE_B], B, de, st)) return -1;
-  m.step += 1;
+  m.step = t_next;
   OptimArgs o = optim_args(m, loss_out);
   o.c0 = adam_alpha_f32(m.step); o.c1 = 0.9f; o.c2 = 0.999f; o.c3 = 1e-8f;
+  if (overlap) {
+    SERT_CUDA(cudaEventRecord(m.ev_join, m.st2));
+    OptimArgs o1 = o;
+    o1.loss_out = nullptr;
+    o1.phase = 1;
+    if (launch_adam(o1, main_st)) return -1;
+    SERT_CUDA(cudaStreamWaitEvent(main_st, m.ev_join, 0));
+    o.phase = 2;
+    return launch_adam(o, main_st);
+  }
   return timed_update(m, o, true);
 }
 
@@ -477,6 +509,16 @@ int sert_model_create(const sert_config *cfg, void *arena_dev, size_t arena_byte
     set_error(std::string("cudaMemsetAsync: ") + cudaGetErrorString(e));
     return -1;
   }
+  if (is_vs(*cfg)) {
+    int least = 0, greatest = 0;
+    cudaDeviceGetStreamPriorityRange(&least, &greatest);
+    if (cudaStreamCreateWithPriority(&m->st2, cudaStreamNonBlocking, greatest) != cudaSuccess ||
+        cudaEventCreateWithFlags(&m->ev_fork, cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&m->ev_join, cudaEventDisableTiming) != cudaSuccess) {
+      m->st2 = nullptr;                  // no overlap stream: the step runs on one stream
+      cudaGetLastError();
+    }
+  }
   *out = m;
   return 0;
 }
@@ -484,6 +526,12 @@ int sert_model_create(const sert_config *cfg, void *arena_dev, size_t arena_byte
 int sert_model_destroy(sert_model *m) {
   if (m) {
     cudaStreamSynchronize(m->st);
+    if (m->st2) {
+      cudaStreamSynchronize(m->st2);
+      cudaStreamDestroy(m->st2);
+    }
+    if (m->ev_fork) cudaEventDestroy(m->ev_fork);
+    if (m->ev_join) cudaEventDestroy(m->ev_join);
     delete m;
   }
   return 0;
@@ -528,6 +576,12 @@ int sert_model_get_step(sert_model *m, int64_t *t) {
 int sert_model_set_fused(sert_model *m, int enable) {
   SERT_REQUIRE(m, "null model");
   m->use_fused = enable != 0;
+  return 0;
+}
+
+int sert_model_set_overlap(sert_model *m, int enable) {
+  SERT_REQUIRE(m, "null model");
+  m->overlap = enable != 0;
   return 0;
 }
 

@@ -50,7 +50,7 @@ def test_forward_logits_match_oracle(dims):
         H.close(ell, f['ell'], what='instance loss')
 
 
-@pytest.mark.parametrize('fused', [1, 0])
+@pytest.mark.parametrize('fused,overlap', [(1, 1), (1, 0), (0, 1), (0, 0)])
 @pytest.mark.parametrize('gain,weights,dims', [
     (1.0, False, dict(dw=64, de=48, W=5, B=128, k=6)),
     (1.0, True, dict(dw=128, de=128, W=10, B=160, k=10)),        # BASELINE configs[1] dims, ragged last tile
@@ -58,7 +58,7 @@ def test_forward_logits_match_oracle(dims):
     (1.0, True, dict(dw=300, de=128, W=4, B=64, k=10)),          # product-search dims (unfused path)
     (3.0, True, dict(dw=32, de=32, W=40, B=96, k=3)),            # window > 32
 ])
-def test_training_steps_match_oracle(gain, weights, dims, fused):
+def test_training_steps_match_oracle(gain, weights, dims, fused, overlap):
     """5 Adam steps + eval losses through the fused tile kernel and the per-stage kernels; gain=40 drives
     tanh / sigmoid into the 1e-7 clips."""
     from sert_b200 import _native as N
@@ -66,6 +66,7 @@ def test_training_steps_match_oracle(gain, weights, dims, fused):
     lam = 0.01
     model = make_model(p, lam)
     N.check(model._native.lib.sert_model_set_fused(model._native.handle, fused))
+    N.check(model._native.lib.sert_model_set_overlap(model._native.handle, overlap))
     oracle = H.vs_oracle(p, lam)
     order = [3, 0, 4, 1, 2]
     e0 = model.test_fn(1, p['neg'][1])
