@@ -112,8 +112,8 @@ SERT_API int sert_model_profile(sert_model *m, int enable);
 /* Vector-space training step: 1 (default) = fused per-tile kernel when the shape fits in shared memory,
  * 0 = one kernel per stage (general shapes; also what the fused kernel is tested against). */
 SERT_API int sert_model_set_fused(sert_model *m, int enable);
-/* Vector-space training step: 1 = the dense update of the table rows a batch does not touch runs concurrently
- * with the batch's forward/backward kernels (which go to a high-priority stream); 0 (default) = one stream. */
+/* Vector-space training step: 1 (default) = the two small dense-gradient kernels (gW = h^T.da, gb = colsum(da))
+ * run on a second stream concurrently with the Adam stream over the tables; 0 = everything on one stream. */
 SERT_API int sert_model_set_overlap(sert_model *m, int enable);
 /* Log-linear word x entity GEMMs (sert/models.py:846-849 and its two gradients): 1 (default) = tcgen05 tensor
  * cores on bf16x3-split operands whenever the output has >= 32 tiles of 128x256, 0 = fp32 FMA tiles always. */

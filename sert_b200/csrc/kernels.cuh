@@ -98,7 +98,8 @@ struct OptimArgs {
   unsigned int *ticket;            // unused (kept for layout stability)
   float *loss_out;
   float inv_B, reg_coeff;
-  int phase = 0;                   // 0 = all rows, 1 = rows not stamped this step, 2 = stamped rows + dense tensors
+  int phase = 0;                   // 0 = everything, 3 = row-stamped tables only, 4 = dense tensors only (1 / 2: see opt_kernels.cu)
+  long long first4 = 0;            // first 16-byte chunk to process (phase 4 starts at the first dense tensor)
 };
 
 // stamps the table rows a vector-space batch will touch (word rows of x, entity rows of y and of the negatives)

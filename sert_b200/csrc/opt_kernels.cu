@@ -28,9 +28,10 @@ __device__ __forceinline__ float fast_sqrt(float x) {
 // (tools/bw_probe.cu) the in-place 3-stream read-modify-write reaches 6.50 TB/s this way vs 5.3-6.2 TB/s
 // for persistent grid-stride variants -- the block scheduler interleaves the load and store phases of
 // many short CTAs better than a resident wave does.
-// PHASE 0: every row.  PHASE 1: only table rows NOT stamped this step (their gradient is the L2 term alone, so
-// they can be updated while the forward/backward kernels of the same step are still running on another
-// stream).  PHASE 2: the stamped rows plus the dense tensors (projection matrix, bias).
+// PHASE 0: everything.  PHASE 3: only the row-stamped tables (word / entity representations).  PHASE 4: only the
+// dense tensors (projection matrix, bias), whose gradients are produced by two small kernels that the caller
+// overlaps with phase 3 on a second stream.  (PHASE 1 / 2 split the tables into rows not stamped / stamped this
+// step; kept for experiments -- overlapping phase 1 with the forward/backward kernels measured no gain.)
 template <bool ADAM, int PHASE>
 __global__ void __launch_bounds__(256) dense_update_kernel(OptimArgs a) {
   const long long total4 = a.total >> 2;
@@ -42,7 +43,7 @@ __global__ void __launch_bounds__(256) dense_update_kernel(OptimArgs a) {
   const float one_m_c2 = 1.0f - a.c2;
   float sumsq = 0.f;
 
-  const long long i4 = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long i4 = a.first4 + (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i4 < total4) {
     const long long e = i4 << 2;
     int s = 0;
@@ -55,7 +56,11 @@ __global__ void __launch_bounds__(256) dense_update_kernel(OptimArgs a) {
       const unsigned int row = (unsigned int)(e - sg.offset) / (unsigned int)sg.row_len;
       touched = (__ldg(sg.flags + row) == a.stamp);
     }
-    const bool mine = PHASE == 0 ? true : (PHASE == 1 ? (sg.flags != nullptr && !touched) : touched);
+    const bool mine = PHASE == 0 ? true
+                      : PHASE == 1 ? (sg.flags != nullptr && !touched)
+                      : PHASE == 2 ? touched
+                      : PHASE == 3 ? (sg.flags != nullptr)
+                                   : (sg.flags == nullptr);
     if (live && mine) {
       const float4 p = th4[i4];
       const float4 x1 = s14[i4];
@@ -127,20 +132,24 @@ static int launch_update(const OptimArgs &a, bool adam, cudaStream_t st) {
   SERT_REQUIRE(a.total % 4 == 0, "parameter arena must be padded to 4 floats");
   SERT_REQUIRE(a.num_segments >= 1 && a.num_segments <= kMaxSegments, "bad segment table");
   const long long total4 = a.total / 4;
-  const long long blocks = std::max<long long>(1, (total4 + 255) / 256);
+  const long long blocks = std::max<long long>(1, (total4 - a.first4 + 255) / 256);
   SERT_REQUIRE(blocks < (1ll << 31), "parameter arena too large for one launch");
   const int g = (int)blocks;
   if (adam) {
     if (a.phase == 1) dense_update_kernel<true, 1><<<g, 256, 0, st>>>(a);
     else if (a.phase == 2) dense_update_kernel<true, 2><<<g, 256, 0, st>>>(a);
+    else if (a.phase == 3) dense_update_kernel<true, 3><<<g, 256, 0, st>>>(a);
+    else if (a.phase == 4) dense_update_kernel<true, 4><<<g, 256, 0, st>>>(a);
     else dense_update_kernel<true, 0><<<g, 256, 0, st>>>(a);
   } else {
     if (a.phase == 1) dense_update_kernel<false, 1><<<g, 256, 0, st>>>(a);
     else if (a.phase == 2) dense_update_kernel<false, 2><<<g, 256, 0, st>>>(a);
+    else if (a.phase == 3) dense_update_kernel<false, 3><<<g, 256, 0, st>>>(a);
+    else if (a.phase == 4) dense_update_kernel<false, 4><<<g, 256, 0, st>>>(a);
     else dense_update_kernel<false, 0><<<g, 256, 0, st>>>(a);
   }
   SERT_LAUNCH_CHECK();
-  if (a.phase != 1) {          // the loss is complete once the stamped rows have been processed
+  if (a.phase != 1 && a.phase != 3) {   // the loss is complete once the last phase of the step has run
     finalize_train_kernel<<<1, kSumsqSlots, 0, st>>>(a.acc, a.loss_out, a.inv_B, a.reg_coeff);
     SERT_LAUNCH_CHECK();
   }

@@ -87,10 +87,8 @@ struct sert_model {
   size_t stage_nnz_cap = 0;
   // optional per-kernel timing of the dense update (bench.py's roofline leg)
   bool use_fused = true;              // fused tile kernel for the vector-space step when the shape fits
-  // second stream + fork/join events: the untouched-row part of the dense update can overlap the fwd/bwd kernels.
-  // Off by default: measured on B200 (cfg2) it does not pay -- the latency-bound fwd/bwd kernel slows down by
-  // about as much as the overlap saves once the streaming update saturates HBM (0.153 vs 0.150 ms/step).
-  bool overlap = false;
+  // second stream + fork/join events: the two small dense-gradient kernels overlap the table update
+  bool overlap = true;
   cudaStream_t st2 = nullptr;
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
   bool profile = false;
@@ -273,22 +271,7 @@ static int vs_train_step(sert_model &m, const int32_t *x, const int32_t *y, cons
       return -1;
     neg = m.neg;
   }
-  // Rows this batch does not touch only receive the L2 gradient, which does not depend on the batch: their
-  // Adam update (about two thirds of the 24 B/param stream at cfg2) overlaps the forward/backward kernels,
-  // which read touched rows only.  The forward/backward kernels go to a library-owned HIGH-priority stream
-  // (enqueued first, so the block scheduler hands them SM slots ahead of the streaming kernel's thousands of
-  // short CTAs); the caller's stream runs the untouched-row update, joins, then updates the stamped rows.
-  const bool overlap = m.overlap && !m.profile && m.st2 != nullptr;
   const int64_t t_next = m.step + 1;
-  cudaStream_t main_st = m.st;
-  if (overlap) {
-    if (launch_mark_rows(x, (long long)B * c.window, y, B, neg, (long long)B * c.num_negatives, m.flagR, m.flagE,
-                         m.stamp, main_st))
-      return -1;
-    SERT_CUDA(cudaEventRecord(m.ev_fork, main_st));
-    SERT_CUDA(cudaStreamWaitEvent(m.st2, m.ev_fork, 0));
-    st = m.st2;
-  }
   VsFusedArgs f;
   f.x = x; f.R = m.theta + m.off[SERT_PARAM_WORD_REPR]; f.Wp = Wp; f.bp = m.theta + m.off[SERT_PARAM_DENSE_B];
   f.Eemb = m.theta + m.off[SERT_PARAM_ENTITY_REPR]; f.y = y; f.neg = neg; f.w = w;
@@ -313,23 +296,33 @@ static int vs_train_step(sert_model &m, const int32_t *x, const int32_t *y, cons
                             (float)c.window, st))
       return -1;
   }
-  // gWp += h^T . da   (split-K over the batch)
+  // The gradients of the dense tensors (gWp = h^T . da by split-K, gbp = colsum(da)) are only consumed by the
+  // last 16.5k parameters of the arena, so they run on a second stream concurrently with the Adam stream over
+  // the two tables (phase 3); the dense tensors are updated after the join (phase 4).  Saves the ~20 us the
+  // two small kernels would otherwise add to the critical path of the step.
+  const bool overlap = m.overlap && !m.profile && m.st2 != nullptr;
+  cudaStream_t side = overlap ? m.st2 : st;
+  if (overlap) {
+    SERT_CUDA(cudaEventRecord(m.ev_fork, st));
+    SERT_CUDA(cudaStreamWaitEvent(side, m.ev_fork, 0));
+  }
   if (launch_gemm_f32(m.h, m.da, m.grad + m.off[SERT_PARAM_DENSE_W], dw, de, B, true, false, dw, de, de,
-                      EPI_ATOMIC_ADD, nullptr, pick_split_k(dw, de, B), st))
+                      EPI_ATOMIC_ADD, nullptr, pick_split_k(dw, de, B), side))
     return -1;
-  if (launch_colsum_atomic(m.da, m.grad + m.off[SERT_PARAM_DENSE_B], B, de, st)) return -1;
+  if (launch_colsum_atomic(m.da, m.grad + m.off[SERT_PARAM_DENSE_B], B, de, side)) return -1;
   m.step = t_next;
   OptimArgs o = optim_args(m, loss_out);
   o.c0 = adam_alpha_f32(m.step); o.c1 = 0.9f; o.c2 = 0.999f; o.c3 = 1e-8f;
   if (overlap) {
-    SERT_CUDA(cudaEventRecord(m.ev_join, m.st2));
-    OptimArgs o1 = o;
-    o1.loss_out = nullptr;
-    o1.phase = 1;
-    if (launch_adam(o1, main_st)) return -1;
-    SERT_CUDA(cudaStreamWaitEvent(main_st, m.ev_join, 0));
-    o.phase = 2;
-    return launch_adam(o, main_st);
+    SERT_CUDA(cudaEventRecord(m.ev_join, side));
+    OptimArgs tables = o;
+    tables.loss_out = nullptr;
+    tables.phase = 3;
+    if (launch_adam(tables, st)) return -1;
+    SERT_CUDA(cudaStreamWaitEvent(st, m.ev_join, 0));
+    o.phase = 4;
+    o.first4 = m.off[SERT_PARAM_DENSE_W] / 4;       // W and b are the last two tensors of the arena
+    return launch_adam(o, st);
   }
   return timed_update(m, o, true);
 }

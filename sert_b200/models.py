@@ -337,6 +337,31 @@ class ModelBase(ModelInterface):
 
         return np.mean(errors), np.std(errors)
 
+    # -- checkpoint / resume (the reference saves no optimiser state and cannot resume) --
+    def _tensor_shapes(self):
+        raise NotImplementedError()
+
+    def get_checkpoint(self):
+        """Every parameter tensor with both optimiser-state arrays plus the optimiser step, as host arrays."""
+        ckpt = {'step': np.int64(self._native_step())}
+        for name, (which, shape) in self._tensor_shapes().items():
+            for slot, suffix in ((N.STATE_PARAM, ''), (N.STATE_S1, '/state1'), (N.STATE_S2, '/state2')):
+                ckpt[name + suffix] = self._native.get_tensor(which, shape, slot)
+        return ckpt
+
+    def set_checkpoint(self, ckpt):
+        for name, (which, shape) in self._tensor_shapes().items():
+            for slot, suffix in ((N.STATE_PARAM, ''), (N.STATE_S1, '/state1'), (N.STATE_S2, '/state2')):
+                array = np.asarray(ckpt[name + suffix], dtype=np.float32)
+                assert array.shape == tuple(shape), (name + suffix, array.shape, shape)
+                self._native.set_tensor(which, array, slot)
+        N.check(self._native.lib.sert_model_set_step(self._native.handle, int(ckpt['step'])))
+
+    def _native_step(self):
+        t = N.c_int64(0)
+        N.check(self._native.lib.sert_model_get_step(self._native.handle, N.ctypes.byref(t)))
+        return t.value
+
     def get_state(self):
         state = [self.predict_fn]
 
@@ -496,6 +521,11 @@ class LanguageModel(LanguageModelBase):
         return (self._native.get_tensor(N.PARAM_DENSE_W, (self.representation_size, self.output_layer_size)),
                 self._native.get_tensor(N.PARAM_DENSE_B, (self.output_layer_size,)))
 
+    def _tensor_shapes(self):
+        return {'representations': (N.PARAM_WORD_REPR, (self.vocabulary_size, self.representation_size)),
+                'dense_w': (N.PARAM_DENSE_W, (self.representation_size, self.output_layer_size)),
+                'dense_b': (N.PARAM_DENSE_B, (self.output_layer_size,))}
+
     @property
     def predict_fn(self):
         w, b = self.get_dense()
@@ -596,6 +626,12 @@ class VectorSpaceLanguageModel(VectorSpaceLanguageModelBase):
     def get_dense(self):
         return (self._native.get_tensor(N.PARAM_DENSE_W, (self.representation_size, self.entity_representation_size)),
                 self._native.get_tensor(N.PARAM_DENSE_B, (self.entity_representation_size,)))
+
+    def _tensor_shapes(self):
+        return {'entity_representations': (N.PARAM_ENTITY_REPR, (self.num_entities, self.entity_representation_size)),
+                'representations': (N.PARAM_WORD_REPR, (self.vocabulary_size, self.representation_size)),
+                'dense_w': (N.PARAM_DENSE_W, (self.representation_size, self.entity_representation_size)),
+                'dense_b': (N.PARAM_DENSE_B, (self.entity_representation_size,))}
 
     @property
     def predict_fn(self):

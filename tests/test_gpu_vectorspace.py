@@ -148,3 +148,23 @@ def test_predict_fn_matches_oracle_and_pickles():
         out = fn(avg)
         assert out.shape == (1, 128)
         H.close(out[0], O.vectorspace_predict(p['Wp'], p['bp'], avg), what='predict_fn')
+
+
+def test_checkpoint_resume_is_exact():
+    """Train 2 steps, checkpoint (parameters + Adam state + step), train 2 more; a fresh model restored from the
+    checkpoint must reproduce the last 2 steps (the reference cannot resume: no optimiser state)."""
+    p = H.vs_problem(31, V=500, E=120, dw=32, de=32, W=4, B=64, k=4, n_batches=4)
+    a = make_model(p, 0.01)
+    for j in range(2):
+        a.train_fn(j, p['neg'][j])
+    ckpt = a.get_checkpoint()
+    assert int(ckpt['step']) == 2
+    tail_a = [a.train_fn(j, p['neg'][j]) for j in (2, 3)]
+    b = make_model(p, 0.01)
+    b.set_checkpoint(ckpt)
+    tail_b = [b.train_fn(j, p['neg'][j]) for j in (2, 3)]
+    np.testing.assert_allclose(tail_a, tail_b, rtol=1e-6)     # float atomics: summation order may differ
+    Ra, Ea = a.get_representations()
+    Rb, Eb = b.get_representations()
+    np.testing.assert_allclose(Ra, Rb, rtol=1e-6, atol=1e-9)     # atomics order may differ in the last bit
+    np.testing.assert_allclose(Ea, Eb, rtol=1e-6, atol=1e-9)
