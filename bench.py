@@ -122,6 +122,10 @@ def make_problem(rank, n_batches, cfg=CFG2):
     rng = np.random.default_rng(seed)
     B = cfg['B']
     train, val = synth.vectorspace_corpus(seed, cfg['V'], cfg['E'], cfg['W'], B * n_batches, B)
+    if os.environ.get('SERT_BENCH_UNIFORM'):      # diagnostic only: uniform instead of Zipf word / label ids
+        u = np.random.default_rng(seed + 1)
+        train = (u.integers(0, cfg['V'], train[0].shape).astype(train[0].dtype),
+                 u.integers(0, cfg['E'], train[1].shape).astype(np.int32), train[2])
     R = synth.glorot(rng, (cfg['V'], cfg['dw']))
     Eemb = synth.glorot(rng, (cfg['E'], cfg['de']))
     Wp = synth.glorot(rng, (cfg['dw'], cfg['de']))

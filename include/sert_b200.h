@@ -109,8 +109,8 @@ SERT_API int sert_model_get_step(sert_model *m, int64_t *t);
  * summed kernel time, the launch count and the ALGORITHMIC bytes of one launch (24 B per parameter:
  * read+write of theta and the two optimiser-state arrays; DESIGN.md "roofline"). */
 SERT_API int sert_model_profile(sert_model *m, int enable);
-/* Vector-space training step: 1 (default) = fused per-tile kernel when the shape fits in shared memory,
- * 0 = one kernel per stage (general shapes; also what the fused kernel is tested against). */
+/* Vector-space training step: 1 (default) = fused forward+backward kernel (one warp per pair of instances) for
+ * representation sizes up to 384, 0 = one kernel per stage (any shape; also what the fused kernel is tested against). */
 SERT_API int sert_model_set_fused(sert_model *m, int enable);
 /* Vector-space training step: 1 (default) = the two small dense-gradient kernels (gW = h^T.da, gb = colsum(da))
  * run on a second stream concurrently with the Adam stream over the tables; 0 = everything on one stream. */

@@ -44,8 +44,8 @@ struct VsNceArgs {
 };
 int launch_vs_nce(const VsNceArgs &a, cudaStream_t st);
 
-// fused gather -> tanh projection -> loss fwd/bwd -> back-projection -> scatter for one instance tile per CTA
-// (csrc/vs_fused.cu).  Returns 0 = launched, 1 = shape not supported (use the unfused kernels), -1 = error.
+// fused gather -> tanh projection -> loss fwd/bwd -> back-projection -> scatter, one warp per pair of instances
+// (csrc/vs_warp.cu).  Returns 0 = launched, 1 = shape not supported (use the per-stage kernels), -1 = error.
 struct VsFusedArgs {
   const int32_t *x;       // (B,W)
   const float *R;         // (V,dw)
@@ -64,7 +64,8 @@ struct VsFusedArgs {
   int B, W, k, dw, de;
   float inv_B;
 };
-int launch_vs_fused(const VsFusedArgs &a, cudaStream_t st);
+// WpT_scratch: (de, dw) floats, receives the transpose of Wp (refreshed by every call).
+int launch_vs_fused(const VsFusedArgs &a, float *WpT_scratch, cudaStream_t st);
 
 // scatter-add of dh/denom into the word-gradient rows (autodiff of the gather, AdvancedIncSubtensor)
 int launch_scatter_rows(const int32_t *x, const float *dh, float *gR, uint32_t *flagR, uint32_t stamp,

@@ -67,7 +67,7 @@ struct sert_model {
   float *losses = nullptr;
   Dataset ds[2];
   // vector-space workspaces
-  float *h = nullptr, *t = nullptr, *da = nullptr, *dh = nullptr;
+  float *h = nullptr, *t = nullptr, *da = nullptr, *dh = nullptr, *WpT = nullptr;
   int32_t *neg = nullptr;
   float *dbg_scores = nullptr, *dbg_u = nullptr, *dbg_ell = nullptr;
   // log-linear workspaces
@@ -86,7 +86,7 @@ struct sert_model {
   float *stage_w = nullptr, *stage_data = nullptr, *stage_f = nullptr;
   size_t stage_nnz_cap = 0;
   // optional per-kernel timing of the dense update (bench.py's roofline leg)
-  bool use_fused = true;              // fused tile kernel for the vector-space step when the shape fits
+  bool use_fused = true;              // fused warp-per-instance-pair kernel for the vector-space step when the shape fits
   // second stream + fork/join events: the two small dense-gradient kernels overlap the table update
   bool overlap = true;
   cudaStream_t st2 = nullptr;
@@ -165,6 +165,7 @@ static size_t carve(sert_model &m, void *base) {
     m.t = b.take<float>(B * de);
     m.da = b.take<float>(B * de);
     m.dh = b.take<float>(B * dw);
+    m.WpT = b.take<float>(dw * de);
     m.neg = b.take<int32_t>(B * k);
     m.dbg_scores = b.take<float>(B * (k + 1));
     m.dbg_u = b.take<float>(B * de);
@@ -279,7 +280,7 @@ static int vs_train_step(sert_model &m, const int32_t *x, const int32_t *y, cons
   f.gR = m.grad + m.off[SERT_PARAM_WORD_REPR]; f.flagR = m.flagR; f.stamp = m.stamp;
   f.h = m.h; f.da = m.da; f.loss_acc = m.acc;
   f.B = B; f.W = c.window; f.k = c.num_negatives; f.dw = dw; f.de = de; f.inv_B = 1.0f / (float)B;
-  const int fused = m.use_fused ? launch_vs_fused(f, st) : 1;
+  const int fused = m.use_fused ? launch_vs_fused(f, m.WpT, st) : 1;
   if (fused < 0) return -1;
   if (fused == 1) {
     // general-shape path: one kernel per stage
