@@ -12,6 +12,8 @@
 // broken by lower row id, so selection and the final order are deterministic.
 #include "score.cuh"
 
+#include <stdlib.h>
+
 #include "gemm_tc.cuh"
 #include "kernels.cuh"
 #include "topk_keys.cuh"
@@ -208,8 +210,164 @@ __global__ void __launch_bounds__(256) rescore_kernel(const float *__restrict__ 
   }
 }
 
+// ---- prune by radix selection ---------------------------------------------------------------------------
+// Same contract as prune_kernel, but the k-th largest key is FOUND (11-bit MSB radix passes over the 64-bit keys
+// read from L2, then a direct ranking once <= 256 keys share the prefix) instead of sorting the whole list:
+// ~1 us per list of 1-2 k candidates instead of ~6 us, one launch with 8 KB + k keys of shared memory for any
+// list length.  Keys are unique (score bits | ~row id), so exactly k keys are >= the selected threshold.  Only
+// the final call sorts, and only the k survivors.
+constexpr int kSelBins = 2048;
+
+__global__ void __launch_bounds__(256) prune_select_kernel(unsigned long long *__restrict__ cand, int *__restrict__ count,
+                                                           unsigned long long *__restrict__ tau, int cap, int k,
+                                                           int mode, int32_t *__restrict__ out_idx,
+                                                           float *__restrict__ out_score, int k_pow2) {
+  extern __shared__ unsigned long long sel_out[];            // k_pow2 keys
+  __shared__ unsigned int hist[kSelBins];
+  __shared__ unsigned int warp_tot[8];
+  __shared__ unsigned long long s_prefix;
+  __shared__ int s_krem, s_bucket, s_fill;
+  __shared__ unsigned long long small[256];
+  const int q = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int n = min(count[q], cap);
+  if (mode == 0 && n <= cap / 4) return;
+  unsigned long long *mine = cand + (size_t)q * cap;
+  int keep = min(n, k);
+  unsigned long long T = 0ull;                               // threshold key: keep keys >= T
+
+  if (n > k) {
+    if (tid == 0) { s_prefix = 0ull; s_krem = k; }
+    int shift = 64;
+    unsigned long long mask = 0ull;                          // bits already decided
+    __syncthreads();
+    while (true) {
+      const int bits = shift >= 11 ? 11 : shift;
+      shift -= bits;
+      for (int b = tid; b < kSelBins; b += blockDim.x) hist[b] = 0u;
+      __syncthreads();
+      const unsigned long long prefix = s_prefix;
+      for (int i = tid; i < n; i += blockDim.x) {
+        const unsigned long long key = mine[i];
+        if ((key & mask) == prefix) atomicAdd(&hist[(unsigned int)(key >> shift) & ((1u << bits) - 1u)], 1u);
+      }
+      __syncthreads();
+      // suffix scan over the bins: each thread owns 8 consecutive bins (descending digit order)
+      const int nb = 1 << bits, per = kSelBins / 256;
+      unsigned int local[8], tsum = 0u;
+#pragma unroll
+      for (int j = 0; j < per; ++j) {
+        const int bin = nb - 1 - (tid * per + j);           // thread 0 holds the highest digits
+        local[j] = bin >= 0 ? hist[bin] : 0u;
+        tsum += local[j];
+      }
+      unsigned int incl = tsum;                              // inclusive scan over threads (descending digits)
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const unsigned int v = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += v;
+      }
+      if (lane == 31) warp_tot[warp] = incl;
+      __syncthreads();
+      unsigned int base = 0u;
+      for (int w = 0; w < warp; ++w) base += warp_tot[w];
+      const unsigned int before = base + incl - tsum;        // keys with a larger digit than this thread's bins
+      const int krem = s_krem;
+      __syncthreads();
+      if ((unsigned int)krem > before && (unsigned int)krem <= before + tsum) {
+        unsigned int acc = before;
+#pragma unroll
+        for (int j = 0; j < per; ++j) {
+          if ((unsigned int)krem <= acc + local[j]) {
+            const int bin = nb - 1 - (tid * per + j);
+            s_prefix = prefix | ((unsigned long long)bin << shift);
+            s_krem = krem - (int)acc;
+            s_bucket = (int)local[j];
+            break;
+          }
+          acc += local[j];
+        }
+      }
+      __syncthreads();
+      mask |= (((1ull << bits) - 1ull) << shift);
+      if (shift == 0 || s_bucket <= 256) break;
+    }
+    // direct ranking inside the bucket (<= 256 keys share the decided prefix, or every bit is decided)
+    const unsigned long long prefix = s_prefix;
+    if (tid == 0) s_fill = 0;
+    __syncthreads();
+    for (int i = tid; i < n; i += blockDim.x) {
+      const unsigned long long key = mine[i];
+      if ((key & mask) == prefix) small[atomicAdd(&s_fill, 1)] = key;
+    }
+    __syncthreads();
+    const int nsmall = s_fill, krem = s_krem;
+    if (tid < nsmall) {
+      const unsigned long long mykey = small[tid];
+      int larger = 0;
+      for (int j = 0; j < nsmall; ++j) larger += small[j] > mykey ? 1 : 0;
+      if (larger == krem - 1) s_prefix = mykey;              // the k-th largest key overall
+    }
+    __syncthreads();
+    T = s_prefix;
+  }
+
+  // ---- compaction: the survivors, in arbitrary order, go to shared memory and then to the list head ----
+  if (tid == 0) s_fill = 0;
+  __syncthreads();
+  for (int i = tid; i < n; i += blockDim.x) {
+    const unsigned long long key = mine[i];
+    if (key >= T) sel_out[atomicAdd(&s_fill, 1)] = key;
+  }
+  __syncthreads();
+  unsigned long long kth = ~0ull;
+  if (mode == 1) {
+    for (int i = keep + tid; i < k_pow2; i += blockDim.x) sel_out[i] = 0ull;
+    bitonic_sort_desc(sel_out, k_pow2);
+    if (keep > 0) kth = sel_out[keep - 1];
+  } else {
+    kth = T;
+  }
+  for (int i = tid; i < keep; i += blockDim.x) mine[i] = sel_out[i];
+  if (tid == 0) {
+    count[q] = keep;
+    if (keep == k) {
+      if (n > k) tau[q] = T;
+      else if (mode == 1) tau[q] = kth;
+      else {                                                  // exactly k candidates, unsorted: tau = their minimum
+        unsigned long long mn = ~0ull;
+        for (int i = 0; i < keep; ++i) mn = sel_out[i] < mn ? sel_out[i] : mn;
+        tau[q] = mn;
+      }
+    }
+  }
+  if (mode == 1) {
+    for (int i = tid; i < k; i += blockDim.x) {
+      if (i < keep) {
+        out_idx[(size_t)q * k + i] = (int32_t)key_row(sel_out[i]);
+        out_score[(size_t)q * k + i] = key_score(sel_out[i]);
+      } else {                                               // fewer than k rows in the shard
+        out_idx[(size_t)q * k + i] = -1;
+        out_score[(size_t)q * k + i] = -INFINITY;
+      }
+    }
+  }
+}
+
 static int launch_prune(const TopkState &s, int Q, int k, int mode, int32_t *out_idx, float *out_score,
                         cudaStream_t st) {
+  static int use_bitonic = -1;
+  if (use_bitonic < 0) {
+    const char *e = getenv("SERT_PRUNE");
+    use_bitonic = (e && e[0] == 'b') ? 1 : 0;               // SERT_PRUNE=bitonic: the full-sort prune, for A/B runs
+  }
+  if (!use_bitonic) {
+    int k_pow2 = 2;
+    while (k_pow2 < k) k_pow2 <<= 1;
+    prune_select_kernel<<<Q, 256, (size_t)k_pow2 * sizeof(unsigned long long), st>>>(s.cand, s.count, s.tau, s.cap, k,
+                                                                                   mode, out_idx, out_score, k_pow2);
+    SERT_LAUNCH_CHECK();
+    return 0;
+  }
   const int small = std::min(kPruneSmall, s.cap);
   prune_kernel<<<Q, 256, (size_t)small * sizeof(unsigned long long), st>>>(s.cand, s.count, s.tau, s.cap, k, mode,
                                                                            out_idx, out_score, small);

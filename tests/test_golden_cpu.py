@@ -204,3 +204,33 @@ def _run_callbacks(scorer_factory):
 
 def test_ranking_callbacks_match_reference_on_host():
     _run_callbacks(NumpyScorer)
+
+
+def test_embedding_utils_round_trip(tmp_path):
+    """word2vec-binary reader used by bin/train.py --representation_initializer (sub:embedding_utils.py:23-88)."""
+    from cvangysel import embedding_utils
+    rng = np.random.default_rng(0)
+    items = [('Alpha', rng.standard_normal(5).astype(np.float32)), ('beta', rng.standard_normal(5).astype(np.float32)),
+             ('gamma', rng.standard_normal(5).astype(np.float32))]
+    path = str(tmp_path / 'vectors.bin')
+    embedding_utils.write_binary_representations(path, items)
+    assert embedding_utils.get_binary_representations_info(path) == (3, 5)
+    loaded = dict(embedding_utils.load_binary_representations(path))
+    assert sorted(loaded) == ['alpha', 'beta', 'gamma']            # words are lower-cased on load
+    np.testing.assert_allclose(loaded['alpha'], items[0][1], rtol=0, atol=0)
+    only = dict(embedding_utils.load_binary_representations(path, ['beta']))
+    assert list(only) == ['beta']
+
+
+def test_argparse_validators_match_reference_semantics():
+    import argparse
+    from cvangysel import argparse_utils as A
+    assert A.positive_int('0') == 0 and A.positive_int('7') == 7         # the reference's "positive" accepts zero
+    assert A.ratio('0.01') == 0.01 and A.positive_float('2.5') == 2.5
+    for fn, bad in ((A.positive_int, '-1'), (A.positive_int, 'x'), (A.ratio, '1.5'), (A.positive_float, '0')):
+        with pytest.raises(argparse.ArgumentTypeError):
+            fn(bad)
+    with pytest.raises(argparse.ArgumentTypeError):
+        A.existing_file_path('/no/such/file')
+    with pytest.raises(argparse.ArgumentTypeError):
+        A.nonexisting_file_path(__file__)

@@ -146,3 +146,23 @@ def test_tensor_core_projection_matches_oracle(dims, tensor):
     H.close(model.get_representations(), oracle.R, rtol=2e-4, what='R')
     H.close(Wd, oracle.Wd, rtol=2e-4, what='Wd')
     H.close(bd, oracle.bd, rtol=2e-4, atol_scale=1e-4, what='bd')
+
+
+def test_empty_validation_set_and_tail_drop():
+    """0 validation instances: constructor reshapes x to (0, W) (sert/models.py:448-454); validation_error is
+    (nan, nan) as in the reference (np.mean of no batches); an incomplete last training batch is ignored."""
+    import warnings
+    import scipy.sparse as sp
+    p = H.ll_problem(51, V=200, E=30, dw=16, W=3, B=16, n_batches=2)
+    x, y, w = p['train']
+    empty = (np.zeros((0,), dtype=x.dtype), sp.csr_matrix((0, 30), dtype=np.float32))
+    p2 = dict(p, val=empty)
+    model = make_model(p2, 0.01)
+    with warnings.catch_warnings():
+        warnings.simplefilter('ignore')
+        mean, std = model.validation_error()
+    assert np.isnan(mean) and np.isnan(std)
+    n, loss = model.train(order=[0, 1])
+    assert n == 2 and np.isfinite(loss)          # 2*16+5 instances -> 2 batches, 5 dropped
+    with pytest.raises(RuntimeError, match='out of range'):
+        model.train_fn(2)
