@@ -6,7 +6,7 @@
 //   warp 1   allocates all 512 TMEM columns (two 128 x 256 fp32 accumulators), then one elected lane
 //            issues tcgen05.mma.cta_group::1.kind::f16 (M=128, N=256, K=16) x 4 per stage and
 //            tcgen05.commit's the stage's "empty" barrier / the accumulator's "full" barrier
-//   warps 2-5 epilogue: tcgen05.ld 32x32b.x32 of their 32-lane quarter, then either fp32 stores (+bias)
+//   warps 2-9 epilogue (two per 32-lane TMEM quarter, 128 columns each): tcgen05.ld 32x32b.x32, then fp32 stores (+bias)
 //            or the running top-k filter; double-buffered against the next tile's MMAs
 #include <cuda.h>
 
@@ -21,7 +21,8 @@ constexpr int BM = 128, BN = 256, BK = 64, STAGES = 4, UMMA_K = 16;
 constexpr uint32_t A_STAGE_BYTES = BM * BK * 2;   // 16 KB
 constexpr uint32_t B_STAGE_BYTES = BN * BK * 2;   // 32 KB
 constexpr uint32_t STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
-constexpr int NUM_THREADS = 192;
+constexpr int EPI_WARPS = 8;              // two warps per TMEM lane quarter, each owns half of the tile's columns
+constexpr int NUM_THREADS = 64 + 32 * EPI_WARPS;
 constexpr uint32_t TMEM_COLS = 512;
 constexpr size_t SMEM_BYTES = 1024 /*align slack*/ + (size_t)STAGES * STAGE_BYTES + 256 /*barriers*/;
 
@@ -157,7 +158,7 @@ gemm_tc_kernel(const __grid_constant__ TcMap map_a, const __grid_constant__ TcMa
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(tfull_bar(a), 1);
-      mbar_init(tempty_bar(a), 4);     // one arrive per epilogue warp
+      mbar_init(tempty_bar(a), EPI_WARPS);   // one arrive per epilogue warp
     }
     fence_barrier_init();
   }
@@ -216,8 +217,10 @@ gemm_tc_kernel(const __grid_constant__ TcMap map_a, const __grid_constant__ TcMa
       }
     }
   } else {
-    // ================= epilogue (warps 2..5) =================
+    // ================= epilogue (warps 2..9) =================
     const int quarter = warp & 3;                        // a warp may only touch TMEM lanes [32*(warp%4), +32)
+    const int col_lo = ((warp - 2) >> 2) * (BN / 2);     // ... and this warp handles columns [col_lo, col_lo + BN/2)
+    constexpr int CHUNKS = BN / 2 / 32;
     const int row = quarter * 32 + lane;
     int acc = 0;
     uint32_t acc_phase = 0;
@@ -239,7 +242,7 @@ gemm_tc_kernel(const __grid_constant__ TcMap map_a, const __grid_constant__ TcMa
       const uint32_t t_row = tmem_base + (uint32_t)acc * BN + ((uint32_t)(quarter * 32) << 16);
       if (ep.mode == TC_EPI_STORE) {
 #pragma unroll 1
-        for (int c0 = 0; c0 < BN; c0 += 32) {
+        for (int c0 = col_lo; c0 < col_lo + BN / 2; c0 += 32) {
           uint32_t v[32];
           tc_ld_32x32(t_row + (uint32_t)c0, v);
           tc_wait_ld();
@@ -273,11 +276,11 @@ gemm_tc_kernel(const __grid_constant__ TcMap map_a, const __grid_constant__ TcMa
         int total = 0;
         uint32_t chunk_any = 0;                                          // warp-uniform: chunks with a survivor
 #pragma unroll 1
-        for (int ci = 0; ci < BN / 32; ++ci) {
+        for (int ci = 0; ci < CHUNKS; ++ci) {
           uint32_t v[32];
-          tc_ld_32x32(t_row + (uint32_t)(ci * 32), v);
+          tc_ld_32x32(t_row + (uint32_t)(col_lo + ci * 32), v);
           tc_wait_ld();
-          const long long left = args.n_end - (n0 + ci * 32);          // valid columns in this chunk
+          const long long left = args.n_end - (n0 + col_lo + ci * 32);          // valid columns in this chunk
           const int nv = left >= 32 ? 32 : (left <= 0 ? 0 : (int)left);
           int cnt = 0;
 #pragma unroll
@@ -296,19 +299,20 @@ gemm_tc_kernel(const __grid_constant__ TcMap map_a, const __grid_constant__ TcMa
             if (pos + total > ep.cap) *ep.overflow = 1;
           }
 #pragma unroll 1
-          for (int ci = 0; ci < BN / 32; ++ci) {
+          for (int ci = 0; ci < CHUNKS; ++ci) {
             if (!((chunk_any >> ci) & 1u)) continue;                    // warp-uniform skip
             uint32_t v[32];
-            tc_ld_32x32(t_row + (uint32_t)(ci * 32), v);
+            tc_ld_32x32(t_row + (uint32_t)(col_lo + ci * 32), v);
             tc_wait_ld();
             if (total == 0) continue;                                   // this lane has nothing to write
-            const long long left = args.n_end - (n0 + ci * 32);
+            const long long left = args.n_end - (n0 + col_lo + ci * 32);
             const int nv = left >= 32 ? 32 : (left <= 0 ? 0 : (int)left);
 #pragma unroll
             for (int j = 0; j < 32; ++j) {
               if (j < nv && __uint_as_float(v[j]) > tau_score) {
                 if (pos < ep.cap)
-                  list[pos] = make_key(__uint_as_float(v[j]), (unsigned int)(n0 + ci * 32 + j + ep.row_offset));
+                  list[pos] = make_key(__uint_as_float(v[j]),
+                                       (unsigned int)(n0 + col_lo + ci * 32 + j + ep.row_offset));
                 ++pos;
               }
             }

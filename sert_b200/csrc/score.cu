@@ -240,7 +240,7 @@ __global__ void __launch_bounds__(256) prune_select_kernel(unsigned long long *_
     int shift = 64;
     unsigned long long mask = 0ull;                          // bits already decided
     __syncthreads();
-    while (true) {
+    while (n > 256) {                                        // short lists go straight to the direct ranking
       const int bits = shift >= 11 ? 11 : shift;
       shift -= bits;
       for (int b = tid; b < kSelBins; b += blockDim.x) hist[b] = 0u;
