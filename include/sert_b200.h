@@ -74,8 +74,9 @@ typedef struct sert_config {
   float   lambda;          /* --regularization_lambda, bin/train.py:58-59 */
   int32_t loss_slots;      /* capacity of the device-side per-batch loss buffer */
   uint64_t seed;           /* negative-sampler seed (reference: unseeded RandomStreams, sert/models.py:958-959) */
-  int64_t entity_begin;    /* first entity column/row owned by this rank (0 when not sharded) */
-  int64_t entity_count;    /* entities owned by this rank (== entities when not sharded) */
+  int32_t inference_only;  /* 1: parameters + forward workspaces only (predict_fn models); training calls are refused */
+  int32_t reserved0;       /* must be 0 */
+  int64_t reserved1;       /* must be 0 */
 } sert_config;
 
 typedef struct sert_model sert_model;     /* opaque */

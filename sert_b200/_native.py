@@ -28,7 +28,7 @@ class SertConfig(ctypes.Structure):
         ('word_dim', c_int32), ('entity_dim', c_int32),
         ('lambda_', c_float), ('loss_slots', c_int32),
         ('seed', ctypes.c_uint64),
-        ('entity_begin', c_int64), ('entity_count', c_int64),
+        ('inference_only', c_int32), ('reserved0', c_int32), ('reserved1', c_int64),
     ]
 
 

@@ -108,6 +108,7 @@ static int validate(const sert_config &c) {
   SERT_REQUIRE(c.word_dim > 0 && c.word_dim % 4 == 0, "word representation size must be a positive multiple of 4");
   SERT_REQUIRE(c.loss_slots > 0, "loss_slots must be positive");
   SERT_REQUIRE(c.lambda >= 0.f, "regularization lambda must be >= 0");
+  SERT_REQUIRE(c.reserved0 == 0 && c.reserved1 == 0, "reserved config fields must be zero");
   if (is_vs(c)) {
     SERT_REQUIRE(c.entity_dim > 0 && c.entity_dim % 4 == 0,
                  "entity representation size must be a positive multiple of 4");
@@ -150,12 +151,13 @@ static size_t carve(sert_model &m, void *base) {
     add(SERT_PARAM_DENSE_B, E, (int)E, 0);
   }
   m.total = o;
+  const bool train = c.inference_only == 0;
   m.theta = b.take<float>(o);
-  m.s1 = b.take<float>(o);
-  m.s2 = b.take<float>(o);
-  m.grad = b.take<float>(o);
-  m.flagR = b.take<uint32_t>(V);
-  m.flagE = is_vs(c) ? b.take<uint32_t>(E) : nullptr;
+  m.s1 = train ? b.take<float>(o) : nullptr;
+  m.s2 = train ? b.take<float>(o) : nullptr;
+  m.grad = train ? b.take<float>(o) : nullptr;
+  m.flagR = train ? b.take<uint32_t>(V) : nullptr;
+  m.flagE = (train && is_vs(c)) ? b.take<uint32_t>(E) : nullptr;
   m.acc = b.take<double>(1 + kSumsqSlots + 7);
   m.ticket = b.take<unsigned int>(4);
   m.losses = b.take<float>(c.loss_slots + 1);   // last slot: scratch for parity hooks
@@ -163,9 +165,9 @@ static size_t carve(sert_model &m, void *base) {
     const long long k = c.num_negatives;
     m.h = b.take<float>(B * dw);
     m.t = b.take<float>(B * de);
-    m.da = b.take<float>(B * de);
-    m.dh = b.take<float>(B * dw);
-    m.WpT = b.take<float>(dw * de);
+    m.da = train ? b.take<float>(B * de) : nullptr;
+    m.dh = train ? b.take<float>(B * dw) : nullptr;
+    m.WpT = train ? b.take<float>(dw * de) : nullptr;
     m.neg = b.take<int32_t>(B * k);
     m.dbg_scores = b.take<float>(B * (k + 1));
     m.dbg_u = b.take<float>(B * de);
@@ -177,17 +179,19 @@ static size_t carve(sert_model &m, void *base) {
     m.X = b.take<float>(B * W * dw);
     m.Z = b.take<float>(B * W * E);
     m.S = b.take<float>(B * E);
-    m.DS = b.take<float>(B * E);
-    m.dX = b.take<float>(B * W * dw);
+    m.DS = train ? b.take<float>(B * E) : nullptr;
+    m.dX = train ? b.take<float>(B * W * dw) : nullptr;
     m.rmax = b.take<float>(B * W);
     m.rsum = b.take<float>(B * W);
     const long long dw64 = tc_padded_k((int)dw), E64 = tc_padded_k((int)E), BW64 = tc_padded_k((int)(B * W));
     m.Xs = b.take<__nv_bfloat16>(B * W * 3 * dw64);
     m.WdT_s = b.take<__nv_bfloat16>(E * 3 * dw64);
-    m.dZs = b.take<__nv_bfloat16>(B * W * 3 * E64);
-    m.Wd_s = b.take<__nv_bfloat16>(dw * 3 * E64);
-    m.XT_s = b.take<__nv_bfloat16>(dw * 3 * BW64);
-    m.dZT_s = b.take<__nv_bfloat16>(E * 3 * BW64);
+    if (train) {
+      m.dZs = b.take<__nv_bfloat16>(B * W * 3 * E64);
+      m.Wd_s = b.take<__nv_bfloat16>(dw * 3 * E64);
+      m.XT_s = b.take<__nv_bfloat16>(dw * 3 * BW64);
+      m.dZT_s = b.take<__nv_bfloat16>(E * 3 * BW64);
+    }
     m.dbg_ell = b.take<float>(B);
     m.stage_indptr = b.take<int64_t>(B + 1);
     m.stage_nnz_cap = (size_t)B * 64;            // host-streamed batches: up to 64 labels per row on average
@@ -540,6 +544,7 @@ int sert_model_set_tensor(sert_model *m, int which, int slot, const float *host,
   SERT_REQUIRE(m && host, "null argument");
   SERT_REQUIRE(which >= 0 && which < 4 && m->cnt[which] > 0, "model has no such tensor");
   SERT_REQUIRE(slot >= 0 && slot <= 2, "bad state slot");
+  SERT_REQUIRE(slot == SERT_STATE_PARAM || m->cfg.inference_only == 0, "inference_only models keep no optimiser state");
   SERT_REQUIRE((long long)count == m->cnt[which], "tensor size mismatch");
   SERT_CUDA(cudaMemcpyAsync(tensor_ptr(m, which, slot), host, count * sizeof(float), cudaMemcpyHostToDevice, m->st));
   SERT_CUDA(cudaStreamSynchronize(m->st));
@@ -550,6 +555,7 @@ int sert_model_get_tensor(sert_model *m, int which, int slot, float *host, size_
   SERT_REQUIRE(m && host, "null argument");
   SERT_REQUIRE(which >= 0 && which < 4 && m->cnt[which] > 0, "model has no such tensor");
   SERT_REQUIRE(slot >= 0 && slot <= 2, "bad state slot");
+  SERT_REQUIRE(slot == SERT_STATE_PARAM || m->cfg.inference_only == 0, "inference_only models keep no optimiser state");
   SERT_REQUIRE((long long)count == m->cnt[which], "tensor size mismatch");
   SERT_CUDA(cudaMemcpyAsync(host, tensor_ptr(m, which, slot), count * sizeof(float), cudaMemcpyDeviceToHost, m->st));
   SERT_CUDA(cudaStreamSynchronize(m->st));
@@ -633,6 +639,7 @@ int sert_model_attach_dataset(sert_model *m, int split, int64_t n, const int32_t
 int sert_train_batches(sert_model *m, const int64_t *order_host, int64_t n, const int32_t *neg_dev,
                        int32_t first_slot) {
   SERT_REQUIRE(m && (order_host || n == 0), "null argument");
+  SERT_REQUIRE(m->cfg.inference_only == 0, "model was created inference_only: it cannot be trained");
   SERT_REQUIRE(first_slot >= 0 && first_slot + n <= m->cfg.loss_slots, "loss slots exhausted");
   const sert_config &c = m->cfg;
   const Dataset &d = m->ds[SERT_SPLIT_TRAIN];
@@ -701,6 +708,7 @@ int sert_train_batch_host(sert_model *m, const int32_t *x_host, const int32_t *y
                           const int32_t *indices_host, const float *data_host, const float *w_host,
                           const int32_t *neg_host, float *loss_host) {
   SERT_REQUIRE(m && x_host && loss_host, "null argument");
+  SERT_REQUIRE(m->cfg.inference_only == 0, "model was created inference_only: it cannot be trained");
   const sert_config &c = m->cfg;
   cudaStream_t st = m->st;
   const size_t B = c.batch;

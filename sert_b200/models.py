@@ -48,7 +48,7 @@ class _NativeModel(object):
     """Owns the HBM arena + the sert_model handle."""
 
     def __init__(self, kind, batch, window, vocab, entities, word_dim, entity_dim=0, num_negatives=0,
-                 lam=0.0, loss_slots=1 << 16, seed=None, device=None):
+                 lam=0.0, loss_slots=1 << 16, seed=None, device=None, inference_only=False):
         torch = _torch()
         self.lib = N.load()
         self.device = torch.device('cuda', torch.cuda.current_device() if device is None else device)
@@ -56,8 +56,8 @@ class _NativeModel(object):
             seed = int(np.random.randint(low=0, high=(1 << 30)))      # sert/models.py:958-959
         self.cfg = N.SertConfig(kind=kind, batch=batch, window=window, num_negatives=num_negatives or 0,
                                 vocab=vocab, entities=entities, word_dim=word_dim, entity_dim=entity_dim or 0,
-                                lambda_=lam, loss_slots=loss_slots, seed=seed, entity_begin=0,
-                                entity_count=entities)
+                                lambda_=lam, loss_slots=loss_slots, seed=seed,
+                                inference_only=int(bool(inference_only)), reserved0=0, reserved1=0)
         nbytes = N.c_size_t(0)
         N.check(self.lib.sert_model_arena_bytes(N.ctypes.byref(self.cfg), N.ctypes.byref(nbytes)))
         with torch.cuda.device(self.device):
@@ -422,7 +422,8 @@ class LogLinearPredictFn(object):
         if self._native is None:
             V, dw = self.representations.shape
             E = self.dense_w.shape[1]
-            nat = _NativeModel(N.KIND_LOGLINEAR, self.batch_size, self.window_size, V, E, dw, loss_slots=4)
+            nat = _NativeModel(N.KIND_LOGLINEAR, self.batch_size, self.window_size, V, E, dw, loss_slots=4,
+                               inference_only=True)
             nat.set_tensor(N.PARAM_WORD_REPR, self.representations)
             nat.set_tensor(N.PARAM_DENSE_W, self.dense_w)
             nat.set_tensor(N.PARAM_DENSE_B, self.dense_b)
@@ -461,7 +462,8 @@ class VectorSpacePredictFn(object):
     def _ensure(self):
         if self._native is None:
             dw, de = self.dense_w.shape
-            nat = _NativeModel(N.KIND_VECTORSPACE, 1024, 1, 4, 4, dw, entity_dim=de, num_negatives=1, loss_slots=4)
+            nat = _NativeModel(N.KIND_VECTORSPACE, 1024, 1, 4, 4, dw, entity_dim=de, num_negatives=1, loss_slots=4,
+                               inference_only=True)
             nat.set_tensor(N.PARAM_DENSE_W, self.dense_w)
             nat.set_tensor(N.PARAM_DENSE_B, self.dense_b)
             self._native = nat
