@@ -96,16 +96,12 @@ struct OptimArgs {
   float c0, c1, c2, c3;
   // loss finalisation by the last block: loss[slot] = data_acc*inv_B + reg_coeff * sum(theta^2)
   double *acc;                     // 1 + kSumsqSlots doubles, see above
-  unsigned int *ticket;            // unused (kept for layout stability)
   float *loss_out;
   float inv_B, reg_coeff;
-  int phase = 0;                   // 0 = everything, 3 = row-stamped tables only, 4 = dense tensors only (1 / 2: see opt_kernels.cu)
+  int phase = 0;                   // 0 = everything, 3 = row-stamped tables only, 4 = dense tensors only
   long long first4 = 0;            // first 16-byte chunk to process (phase 4 starts at the first dense tensor)
 };
 
-// stamps the table rows a vector-space batch will touch (word rows of x, entity rows of y and of the negatives)
-int launch_mark_rows(const int32_t *x, long long nx, const int32_t *y, long long ny, const int32_t *neg,
-                     long long nneg, uint32_t *flagR, uint32_t *flagE, uint32_t stamp, cudaStream_t st);
 int launch_adam(const OptimArgs &a, cudaStream_t st);
 int launch_adadelta(const OptimArgs &a, cudaStream_t st);
 // eval loss finalisation: loss_out = acc[0]*inv_B ; acc[0] = 0

@@ -30,8 +30,7 @@ __device__ __forceinline__ float fast_sqrt(float x) {
 // many short CTAs better than a resident wave does.
 // PHASE 0: everything.  PHASE 3: only the row-stamped tables (word / entity representations).  PHASE 4: only the
 // dense tensors (projection matrix, bias), whose gradients are produced by two small kernels that the caller
-// overlaps with phase 3 on a second stream.  (PHASE 1 / 2 split the tables into rows not stamped / stamped this
-// step; kept for experiments -- overlapping phase 1 with the forward/backward kernels measured no gain.)
+// overlaps with phase 3 on a second stream.
 template <bool ADAM, int PHASE>
 __global__ void __launch_bounds__(256) dense_update_kernel(OptimArgs a) {
   const long long total4 = a.total >> 2;
@@ -56,11 +55,7 @@ __global__ void __launch_bounds__(256) dense_update_kernel(OptimArgs a) {
       const unsigned int row = (unsigned int)(e - sg.offset) / (unsigned int)sg.row_len;
       touched = (__ldg(sg.flags + row) == a.stamp);
     }
-    const bool mine = PHASE == 0 ? true
-                      : PHASE == 1 ? (sg.flags != nullptr && !touched)
-                      : PHASE == 2 ? touched
-                      : PHASE == 3 ? (sg.flags != nullptr)
-                                   : (sg.flags == nullptr);
+    const bool mine = PHASE == 0 ? true : PHASE == 3 ? (sg.flags != nullptr) : (sg.flags == nullptr);
     if (live && mine) {
       const float4 p = th4[i4];
       const float4 x1 = s14[i4];
@@ -131,25 +126,22 @@ __global__ void finalize_train_kernel(double *acc, float *loss_out, float inv_B,
 static int launch_update(const OptimArgs &a, bool adam, cudaStream_t st) {
   SERT_REQUIRE(a.total % 4 == 0, "parameter arena must be padded to 4 floats");
   SERT_REQUIRE(a.num_segments >= 1 && a.num_segments <= kMaxSegments, "bad segment table");
+  SERT_REQUIRE(a.phase == 0 || a.phase == 3 || a.phase == 4, "bad update phase");
   const long long total4 = a.total / 4;
   const long long blocks = std::max<long long>(1, (total4 - a.first4 + 255) / 256);
   SERT_REQUIRE(blocks < (1ll << 31), "parameter arena too large for one launch");
   const int g = (int)blocks;
   if (adam) {
-    if (a.phase == 1) dense_update_kernel<true, 1><<<g, 256, 0, st>>>(a);
-    else if (a.phase == 2) dense_update_kernel<true, 2><<<g, 256, 0, st>>>(a);
-    else if (a.phase == 3) dense_update_kernel<true, 3><<<g, 256, 0, st>>>(a);
+    if (a.phase == 3) dense_update_kernel<true, 3><<<g, 256, 0, st>>>(a);
     else if (a.phase == 4) dense_update_kernel<true, 4><<<g, 256, 0, st>>>(a);
     else dense_update_kernel<true, 0><<<g, 256, 0, st>>>(a);
   } else {
-    if (a.phase == 1) dense_update_kernel<false, 1><<<g, 256, 0, st>>>(a);
-    else if (a.phase == 2) dense_update_kernel<false, 2><<<g, 256, 0, st>>>(a);
-    else if (a.phase == 3) dense_update_kernel<false, 3><<<g, 256, 0, st>>>(a);
+    if (a.phase == 3) dense_update_kernel<false, 3><<<g, 256, 0, st>>>(a);
     else if (a.phase == 4) dense_update_kernel<false, 4><<<g, 256, 0, st>>>(a);
     else dense_update_kernel<false, 0><<<g, 256, 0, st>>>(a);
   }
   SERT_LAUNCH_CHECK();
-  if (a.phase != 1 && a.phase != 3) {   // the loss is complete once the last phase of the step has run
+  if (a.phase != 3) {          // the loss is complete once the last phase of the step has run
     finalize_train_kernel<<<1, kSumsqSlots, 0, st>>>(a.acc, a.loss_out, a.inv_B, a.reg_coeff);
     SERT_LAUNCH_CHECK();
   }

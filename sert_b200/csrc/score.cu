@@ -133,46 +133,6 @@ __device__ void bitonic_sort_desc(unsigned long long *keys, int n_pow2) {
   __syncthreads();
 }
 
-// Re-selects the best k candidates of a query and raises tau.  mode 0: only lists more than half full;
-// mode 2: every list; mode 1 ("final"): every list, and the sorted (row id, score) outputs are written.
-// Launched twice per prune: once with `smem_cap` = kPruneSmall slots of shared memory (lists of up to that
-// many candidates: high occupancy, the common case once tau has warmed up) and once with the full capacity
-// for longer lists; each launch skips the lists that belong to the other.
-constexpr int kPruneSmall = 2048;
-__global__ void __launch_bounds__(256) prune_kernel(unsigned long long *__restrict__ cand, int *__restrict__ count,
-                                                    unsigned long long *__restrict__ tau, int cap, int k, int final,
-                                                    int32_t *__restrict__ out_idx, float *__restrict__ out_score,
-                                                    int smem_cap) {
-  extern __shared__ unsigned long long keys[];
-  const int q = blockIdx.x;
-  const int n = min(count[q], cap);
-  if (final == 0 && n <= cap / 2) return;
-  if (smem_cap < cap ? (n > smem_cap) : (n <= kPruneSmall && cap > kPruneSmall)) return;
-  int n_pow2 = 1;
-  while (n_pow2 < n) n_pow2 <<= 1;
-  if (n_pow2 < 2) n_pow2 = 2;
-  unsigned long long *mine = cand + (size_t)q * cap;
-  for (int i = threadIdx.x; i < n_pow2; i += blockDim.x) keys[i] = (i < n) ? mine[i] : 0ull;
-  bitonic_sort_desc(keys, n_pow2);
-  const int keep = min(n, k);
-  for (int i = threadIdx.x; i < keep; i += blockDim.x) mine[i] = keys[i];
-  if (threadIdx.x == 0) {
-    count[q] = keep;
-    if (keep == k) tau[q] = keys[k - 1];
-  }
-  if (final == 1) {
-    for (int i = threadIdx.x; i < k; i += blockDim.x) {
-      if (i < keep) {
-        out_idx[(size_t)q * k + i] = (int32_t)(0xffffffffu - (unsigned int)(keys[i] & 0xffffffffull));
-        out_score[(size_t)q * k + i] = unorderable((unsigned int)(keys[i] >> 32));
-      } else {                               // fewer than k rows in the shard
-        out_idx[(size_t)q * k + i] = -1;
-        out_score[(size_t)q * k + i] = -INFINITY;
-      }
-    }
-  }
-}
-
 __global__ void reset_topk_state_kernel(unsigned long long *tau, int *count, int Q) {
   const int q = blockIdx.x * blockDim.x + threadIdx.x;
   if (q < Q) { tau[q] = 0ull; count[q] = 0; }
@@ -211,10 +171,11 @@ __global__ void __launch_bounds__(256) rescore_kernel(const float *__restrict__ 
 }
 
 // ---- prune by radix selection ---------------------------------------------------------------------------
-// Same contract as prune_kernel, but the k-th largest key is FOUND (11-bit MSB radix passes over the 64-bit keys
-// read from L2, then a direct ranking once <= 256 keys share the prefix) instead of sorting the whole list:
-// ~1 us per list of 1-2 k candidates instead of ~6 us, one launch with 8 KB + k keys of shared memory for any
-// list length.  Keys are unique (score bits | ~row id), so exactly k keys are >= the selected threshold.  Only
+// Re-selects the best k candidates of a query and raises tau.  mode 0: only lists longer than cap/4; mode 2: every
+// list; mode 1 ("final"): every list, and the sorted (row id, score) outputs are written.  The k-th largest key is FOUND (11-bit MSB radix passes over the 64-bit keys
+// read from L2, then a direct ranking once <= 256 keys share the prefix) instead of sorting the whole list
+// (a full bitonic sort measured ~6 us per list of 1-2 k candidates and needed 64 KB of shared memory for the
+// longest lists; this is ~1 us with 8 KB + k keys for any list length).  Keys are unique (score bits | ~row id), so exactly k keys are >= the selected threshold.  Only
 // the final call sorts, and only the k survivors.
 constexpr int kSelBins = 2048;
 
@@ -355,28 +316,11 @@ __global__ void __launch_bounds__(256) prune_select_kernel(unsigned long long *_
 
 static int launch_prune(const TopkState &s, int Q, int k, int mode, int32_t *out_idx, float *out_score,
                         cudaStream_t st) {
-  static int use_bitonic = -1;
-  if (use_bitonic < 0) {
-    const char *e = getenv("SERT_PRUNE");
-    use_bitonic = (e && e[0] == 'b') ? 1 : 0;               // SERT_PRUNE=bitonic: the full-sort prune, for A/B runs
-  }
-  if (!use_bitonic) {
-    int k_pow2 = 2;
-    while (k_pow2 < k) k_pow2 <<= 1;
-    prune_select_kernel<<<Q, 256, (size_t)k_pow2 * sizeof(unsigned long long), st>>>(s.cand, s.count, s.tau, s.cap, k,
-                                                                                   mode, out_idx, out_score, k_pow2);
-    SERT_LAUNCH_CHECK();
-    return 0;
-  }
-  const int small = std::min(kPruneSmall, s.cap);
-  prune_kernel<<<Q, 256, (size_t)small * sizeof(unsigned long long), st>>>(s.cand, s.count, s.tau, s.cap, k, mode,
-                                                                           out_idx, out_score, small);
+  int k_pow2 = 2;
+  while (k_pow2 < k) k_pow2 <<= 1;
+  prune_select_kernel<<<Q, 256, (size_t)k_pow2 * sizeof(unsigned long long), st>>>(s.cand, s.count, s.tau, s.cap, k,
+                                                                                 mode, out_idx, out_score, k_pow2);
   SERT_LAUNCH_CHECK();
-  if (s.cap > kPruneSmall) {
-    prune_kernel<<<Q, 256, (size_t)s.cap * sizeof(unsigned long long), st>>>(s.cand, s.count, s.tau, s.cap, k, mode,
-                                                                             out_idx, out_score, s.cap);
-    SERT_LAUNCH_CHECK();
-  }
   return 0;
 }
 
@@ -438,10 +382,11 @@ int topk_sweep(const TopkState &s, const float *queries_dev, int Q, int k, int32
 }
 
 int topk_prepare(int cap) {
+  // the prune keeps k <= cap/2 survivors (rounded up to a power of two) in dynamic shared memory
   static int configured = 0;
-  const int smem = cap * (int)sizeof(unsigned long long);
-  if (smem > configured) {
-    SERT_CUDA(cudaFuncSetAttribute(prune_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  const int smem = (cap / 2) * (int)sizeof(unsigned long long);
+  if (smem > configured && smem > 40 * 1024) {
+    SERT_CUDA(cudaFuncSetAttribute(prune_select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     configured = smem;
   }
   return 0;

@@ -63,7 +63,6 @@ struct sert_model {
   int64_t step = 0;                   // Adam's t
   uint64_t sample_calls = 0;
   double *acc = nullptr;
-  unsigned int *ticket = nullptr;
   float *losses = nullptr;
   Dataset ds[2];
   // vector-space workspaces
@@ -83,7 +82,7 @@ struct sert_model {
   // host-batch staging
   int32_t *stage_x = nullptr, *stage_y = nullptr, *stage_neg = nullptr, *stage_indices = nullptr;
   int64_t *stage_indptr = nullptr;
-  float *stage_w = nullptr, *stage_data = nullptr, *stage_f = nullptr;
+  float *stage_w = nullptr, *stage_data = nullptr;
   size_t stage_nnz_cap = 0;
   // optional per-kernel timing of the dense update (bench.py's roofline leg)
   bool use_fused = true;              // fused warp-per-instance-pair kernel for the vector-space step when the shape fits
@@ -159,7 +158,6 @@ static size_t carve(sert_model &m, void *base) {
   m.flagR = train ? b.take<uint32_t>(V) : nullptr;
   m.flagE = (train && is_vs(c)) ? b.take<uint32_t>(E) : nullptr;
   m.acc = b.take<double>(1 + kSumsqSlots + 7);
-  m.ticket = b.take<unsigned int>(4);
   m.losses = b.take<float>(c.loss_slots + 1);   // last slot: scratch for parity hooks
   if (is_vs(c)) {
     const long long k = c.num_negatives;
@@ -174,7 +172,6 @@ static size_t carve(sert_model &m, void *base) {
     m.dbg_ell = b.take<float>(B);
     m.stage_neg = b.take<int32_t>(B * k);
     m.stage_y = b.take<int32_t>(B);
-    m.stage_f = b.take<float>(B * std::max(dw, de));
   } else {
     m.X = b.take<float>(B * W * dw);
     m.Z = b.take<float>(B * W * E);
@@ -225,7 +222,7 @@ static OptimArgs optim_args(sert_model &m, float *loss_out) {
   a.stamp = m.stamp;
   const float B = (float)m.cfg.batch;
   a.l2_scale = m.cfg.lambda > 0.f ? m.cfg.lambda / B : 0.f;
-  a.acc = m.acc; a.ticket = m.ticket; a.loss_out = loss_out;
+  a.acc = m.acc; a.loss_out = loss_out;
   a.inv_B = 1.0f / B;
   a.reg_coeff = m.cfg.lambda > 0.f ? m.cfg.lambda / (2.0f * B) : 0.f;
   return a;

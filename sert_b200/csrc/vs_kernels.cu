@@ -260,25 +260,6 @@ int launch_vs_nce(const VsNceArgs &a, cudaStream_t st) {
   return launch_vs_nce_t<8, 1>(a, st);
 }
 
-// stamps the rows a batch touches, before any of its kernels runs (see the phased dense update)
-__global__ void mark_rows_kernel(const int32_t *__restrict__ x, long long nx, const int32_t *__restrict__ y,
-                                 long long ny, const int32_t *__restrict__ neg, long long nneg,
-                                 uint32_t *__restrict__ flagR, uint32_t *__restrict__ flagE, uint32_t stamp) {
-  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < nx) flagR[x[i]] = stamp;
-  else if (i < nx + ny) flagE[y[i - nx]] = stamp;
-  else if (i < nx + ny + nneg) flagE[neg[i - nx - ny]] = stamp;
-}
-
-int launch_mark_rows(const int32_t *x, long long nx, const int32_t *y, long long ny, const int32_t *neg,
-                     long long nneg, uint32_t *flagR, uint32_t *flagE, uint32_t stamp, cudaStream_t st) {
-  const long long n = nx + ny + nneg;
-  if (n == 0) return 0;
-  mark_rows_kernel<<<cdiv(n, 256), 256, 0, st>>>(x, nx, y, ny, neg, nneg, flagR, flagE, stamp);
-  SERT_LAUNCH_CHECK();
-  return 0;
-}
-
 // ------------------------------------------------------------------------------------------------
 // Philox4x32-10 negatives: uniform over [0,E) with replacement, not excluding the positive
 // (sert/models.py:927-931,956-973).

@@ -101,3 +101,28 @@ def test_adversarial_ascending_scores_take_the_exact_fallback(mode):
     ref_idx, ref_score = exact_topk(E, q, k)
     np.testing.assert_array_equal(idx, ref_idx)
     np.testing.assert_allclose(score, ref_score, rtol=1e-6, atol=1e-6)
+
+
+def test_randomised_shapes_match_exact():
+    """Random (rows, d, Q, k) including rows < k, d that is no multiple of 4 / 64, Q above max_queries (chunked
+    calls) and k at the scorer's max_k; both arithmetic modes."""
+    from oracle import sert_oracle as O
+    from sert_b200.scoring import EntityScorer
+    rng = np.random.default_rng(2026)
+    for trial in range(10):
+        rows = int(rng.choice([1, 7, 63, 200, 1500, 9000, 40000]))
+        d = int(rng.choice([3, 10, 50, 64, 100, 128, 257]))
+        Q = int(rng.integers(1, 90))
+        k = int(rng.choice([1, 5, 32, 100]))
+        E = O.normalise_rows(rng.standard_normal((rows, d)))
+        q = O.normalise_rows(rng.standard_normal((Q, d)))
+        sc = EntityScorer(E, max_queries=32, max_k=100)
+        sc.set_mode('tensor' if trial % 2 == 0 else 'fma')
+        idx, score = sc.topk(q, k)
+        kk = min(k, rows)
+        ref_idx, ref_score = exact_topk(E, q, kk)
+        np.testing.assert_allclose(score[:, :kk], ref_score, rtol=0, atol=3e-6, err_msg=str((rows, d, Q, k)))
+        assert (idx[:, kk:] == -1).all()
+        gaps = np.abs(np.diff(ref_score, axis=1)).min(axis=1) > 2e-6 if kk > 1 else np.ones(Q, bool)
+        assert (idx[gaps][:, :kk] == ref_idx[gaps]).all(), (rows, d, Q, k)
+        sc.close()
