@@ -288,6 +288,7 @@ def run_ours(args, rank, world, local_rank):
     scoring_small = run_scoring(CFG3, 'BASELINE.json configs[2]', rank, world, barrier, cpu=(rank == 0))
 
     loglinear = run_loglinear_cfg1(rank) if rank == 0 else None
+    loglinear_stress = None if os.environ.get('SERT_BENCH_SKIP_CFG5') else run_loglinear_cfg5(rank, world, barrier)
 
     if rank == 0:
         cpu = cpu_baseline_sample()
@@ -314,6 +315,7 @@ def run_ours(args, rank, world, local_rank):
                          'step_frac_of_hbm_peak': step_bytes / (ms_max / steps * 1e-3) / 1e9 / peak},
             'cpu_baseline': cpu,
             'loglinear': loglinear,
+            'loglinear_stress': loglinear_stress,
             'scoring': scoring,
             'scoring_small': scoring_small,
         }
@@ -430,6 +432,49 @@ def run_loglinear_cfg1(rank):
                         'Adadelta + dense L2, exact per-word clipped path',
             'value': B / (ms * 1e-3), 'unit': UNIT, 'ms_per_step': ms,
             'cpu_port_value': B / (cpu_ms * 1e-3), 'cpu_port_ms_per_step': cpu_ms}
+
+
+def run_loglinear_cfg5(rank, world, barrier, steps=4):
+    """BASELINE.json configs[4]: log-linear V=500k E=200k d=300 window=10 B=1024 full-softmax stress.  N>1: the E
+    axis (dense layer columns, logits, softmax) is sharded over the ranks, the word table is replicated; five small
+    NCCL exchanges per step (sert_b200/sharding.py) -- strong scaling of ONE model, unlike the replica headline."""
+    import torch
+    import torch.distributed as dist
+    from sert_b200 import _native as N, models, sharding, synth
+    V, E, dw, W, B = 500000, 200000, 300, 10, 1024
+    nb = steps + 2
+    rng = np.random.default_rng(20160816 + 5)                  # same seed on every rank: identical initial values
+    train, val = synth.loglinear_corpus(20160821, V, E, W, B * nb, B)
+    R, Wd, bd = synth.glorot(rng, (V, dw)), synth.glorot(rng, (dw, E)), np.zeros(E, np.float32)
+    exchange = sharding.DistExchange() if world > 1 else None
+    model = models.LanguageModel(batch_size=B, window_size=W, representations_init=R, output_layer_size=E,
+                                 regularization_lambda=0.01, training_set=train, validation_set=val,
+                                 dense_init=(Wd, bd), loss_slots=64, entity_shard=exchange)
+    nat = model._native
+    order = np.arange(nb, dtype=np.int64)
+    nat._check(nat.lib.sert_train_batches(nat.handle, N.host_ptr(order[:2]), 2, None, 0))
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    nat._check(nat.lib.sert_train_batches(nat.handle, N.host_ptr(order[2:]), steps, None, 2))
+    e1.record()
+    barrier()
+    t = torch.tensor([e0.elapsed_time(e1) / steps], dtype=torch.float64, device='cuda')
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item())
+    losses = np.empty(nb, np.float32)
+    N.check(nat.lib.sert_losses_fetch(nat.handle, 0, nb, N.host_ptr(losses)))
+    arena_gb = nat.arena.numel() / 1e9
+    nat.close()
+    del model
+    torch.cuda.empty_cache()
+    return {'workload': 'BASELINE.json configs[4]: LanguageModel (log-linear) V=500k E=200k d=300 window=10 B=1024, '
+                        'Adadelta + dense L2, exact per-word clipped path, E sharded over %d GPU(s)' % world,
+            'value': B / (ms * 1e-3), 'unit': UNIT, 'ms_per_step': ms, 'scaling': 'strong',
+            'algorithmic_tflops': 6.0 * B * W * dw * E / (ms * 1e-3) / 1e12,
+            'exchanges_per_step': 0 if world == 1 else 5, 'arena_gb_per_gpu': arena_gb,
+            'losses': [float(v) for v in losses[:3]]}
 
 
 def cpu_baseline_sample():

@@ -122,6 +122,24 @@ SERT_API int sert_model_set_tensor_cores(sert_model *m, int enable);
 SERT_API int sert_model_profile_read(sert_model *m, double *update_ms_total, int64_t *update_launches,
                                      double *update_bytes_per_launch);
 
+/* ---- entity-sharded log-linear training (no reference counterpart: the reference is single-device; SURVEY.md
+ * 8(e) "column-parallel softmax") ----------------------------------------------------------------------
+ * A model created with cfg.entities = E_loc owns the columns [entity_begin, entity_begin+E_loc) of the dense
+ * layer W (dw,E) / b (E,) (sert/models.py:846-849) and of the logits; the word table R is replicated and gets
+ * the identical update on every rank.  CSR label indices stay GLOBAL entity ids.  The five exchange points of a
+ * step (row statistics of the two softmaxes, two per-row sums of the backward, the partial dX) call `fn` with a
+ * device buffer; the host performs the collective in place, ordered on the model's stream (torch.distributed /
+ * NCCL in sert_b200/sharding.py).  Per-batch losses are completed by one more all-reduce over the loss slots.
+ *   SERT_XCHG_ALLREDUCE_SUM: buf[0..count) <- sum over ranks.
+ *   SERT_XCHG_ALLGATHER:     buf holds world blocks of `count` floats; rank r filled block r; all blocks are
+ *                            gathered on every rank.
+ * `fn` returns 0 on success. */
+#define SERT_XCHG_ALLREDUCE_SUM 0
+#define SERT_XCHG_ALLGATHER     1
+typedef int (*sert_exchange_fn)(void *ctx, int32_t op, float *buf_dev, size_t count);
+SERT_API int sert_model_set_entity_shard(sert_model *m, int32_t rank, int32_t world, int64_t entity_begin,
+                                         int64_t entities_total, sert_exchange_fn fn, void *ctx);
+
 /* ---- device-resident data set: replaces the theano.shared X/Y/W variables, sert/models.py:470-480 -- */
 /* x_dev (N,W) int32; labels either one-hot y_dev (N,) int32 (vector space, bin/train.py:186-245) or CSR
  * (indptr_dev int64 (N+1), indices_dev int32, data_dev f32; bin/prepare.py:593-597); w_dev (N,) f32 or NULL

@@ -32,6 +32,9 @@ class SertConfig(ctypes.Structure):
     ]
 
 
+# include/sert_b200.h sert_exchange_fn: int (*)(void *ctx, int32_t op, float *buf_dev, size_t count)
+EXCHANGE_FN = ctypes.CFUNCTYPE(c_int, c_void_p, c_int32, c_void_p, c_size_t)
+
 # name -> (restype, argtypes); must list every symbol declared in include/sert_b200.h
 SIGNATURES = {
     'sert_abi_version': (c_int, []),
@@ -45,6 +48,7 @@ SIGNATURES = {
     'sert_model_get_tensor': (c_int, [c_void_p, c_int, c_int, c_void_p, c_size_t]),
     'sert_model_set_step': (c_int, [c_void_p, c_int64]),
     'sert_model_get_step': (c_int, [c_void_p, ctypes.POINTER(c_int64)]),
+    'sert_model_set_entity_shard': (c_int, [c_void_p, c_int32, c_int32, c_int64, c_int64, c_void_p, c_void_p]),
     'sert_model_profile': (c_int, [c_void_p, c_int]),
     'sert_model_set_fused': (c_int, [c_void_p, c_int]),
     'sert_model_set_overlap': (c_int, [c_void_p, c_int]),

@@ -80,7 +80,8 @@ struct ParamSegment {
   long long offset;      // float offset inside the arena arrays
   long long count;       // number of floats (multiple of 4, zero padded)
   int row_len;           // floats per row for flag lookup
-  int regularised;       // contributes to the L2 term (bias does not)
+  int regularised;       // 0: no L2 (bias); 1: L2 gradient + counted in the reported loss; 2: L2 gradient only
+                         // (replicated tensor of an entity-sharded model: rank 0 alone reports its norm)
   const uint32_t *flags; // per-row touched stamps or nullptr (= always read the gradient)
 };
 constexpr int kMaxSegments = 4;

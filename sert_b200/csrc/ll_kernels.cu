@@ -158,21 +158,32 @@ int launch_ll_instance(const LlInstanceArgs &a, cudaStream_t st) {
 }
 
 // ---- dZ in place: one block per (i,w) row ---------------------------------------------------------
+// MODE 0: both halves (single device).  Entity-sharded step: MODE 1 writes the shard's partial row sum
+// acc[r] = sum_{e local, p unclipped} ds[e] (all-reduced by the caller), MODE 2 applies dz = dp*p - p*acc[r].
+template <int MODE>
 __global__ void __launch_bounds__(256) ll_dz_kernel(float *__restrict__ Z, const float *__restrict__ rmax,
                                                     const float *__restrict__ rsum,
                                                     const float *__restrict__ DS, long long rows, int W, int E,
-                                                    long long ldz, long long lds) {
+                                                    long long ldz, long long lds, float *__restrict__ racc) {
   __shared__ float sm[32];
   for (long long r = blockIdx.x; r < rows; r += gridDim.x) {
     float *z = Z + r * ldz;
     const float *ds = DS + (r / W) * lds;
     const float m = rmax[r], s = rsum[r];
     float acc = 0.f;
-    for (int e = threadIdx.x; e < E; e += blockDim.x) {
-      const float p = expf(z[e] - m) / s;
-      if (p >= SERT_CLIP_LO && p <= SERT_CLIP_HI) acc += ds[e];   // dp*p = ds/clip(p)*p = ds when unclipped
+    if (MODE != 2) {
+      for (int e = threadIdx.x; e < E; e += blockDim.x) {
+        const float p = expf(z[e] - m) / s;
+        if (p >= SERT_CLIP_LO && p <= SERT_CLIP_HI) acc += ds[e];   // dp*p = ds/clip(p)*p = ds when unclipped
+      }
+      acc = block_bcast(block_sum(acc, sm), sm);
+      if (MODE == 1) {
+        if (threadIdx.x == 0) racc[r] = acc;
+        continue;
+      }
+    } else {
+      acc = racc[r];
     }
-    acc = block_bcast(block_sum(acc, sm), sm);
     for (int e = threadIdx.x; e < E; e += blockDim.x) {
       const float p = expf(z[e] - m) / s;
       const float dpp = (p >= SERT_CLIP_LO && p <= SERT_CLIP_HI) ? ds[e] : 0.f;
@@ -183,11 +194,114 @@ __global__ void __launch_bounds__(256) ll_dz_kernel(float *__restrict__ Z, const
 }
 
 int launch_ll_dz(float *Z, const float *rmax, const float *rsum, const float *DS, int B, int W, int E,
-                 int64_t ldz, int64_t lds, cudaStream_t st) {
+                 int64_t ldz, int64_t lds, cudaStream_t st, int mode, float *racc) {
   const long long rows = (long long)B * W;
   if (rows == 0) return 0;
-  ll_dz_kernel<<<(int)std::min<long long>(rows, 148 * 64), E >= 1024 ? 256 : 128, 0, st>>>(
-      Z, rmax, rsum, DS, rows, W, E, ldz, lds);
+  SERT_REQUIRE(mode == 0 || racc != nullptr, "sharded dZ needs the row-sum buffer");
+  const int grid = (int)std::min<long long>(rows, 148 * 64), threads = E >= 1024 ? 256 : 128;
+  if (mode == 0) ll_dz_kernel<0><<<grid, threads, 0, st>>>(Z, rmax, rsum, DS, rows, W, E, ldz, lds, racc);
+  else if (mode == 1) ll_dz_kernel<1><<<grid, threads, 0, st>>>(Z, rmax, rsum, DS, rows, W, E, ldz, lds, racc);
+  else ll_dz_kernel<2><<<grid, threads, 0, st>>>(Z, rmax, rsum, DS, rows, W, E, ldz, lds, racc);
+  SERT_LAUNCH_CHECK();
+  return 0;
+}
+
+// =================================================================================================
+// Entity-sharded (column-parallel) softmax pieces, SURVEY.md 8(e): every rank holds the columns
+// [e_begin, e_begin+E) of Wd / bd and therefore of Z and S.  Row statistics are computed per shard,
+// gathered, and combined here; label terms are computed by the rank that owns the label's column.
+// =================================================================================================
+
+// parts: [shard][2][rows] = per-shard (row max, row sum of exp(z - shard max)) -> global max / sum
+__global__ void ll_combine_stats_kernel(const float *__restrict__ parts, int shards, long long rows,
+                                        float *__restrict__ rmax, float *__restrict__ rsum) {
+  const long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= rows) return;
+  float m = -INFINITY;
+  for (int s = 0; s < shards; ++s) m = fmaxf(m, parts[(2ll * s) * rows + r]);
+  float sum = 0.f;
+  for (int s = 0; s < shards; ++s)
+    sum += parts[(2ll * s + 1) * rows + r] * expf(parts[(2ll * s) * rows + r] - m);
+  rmax[r] = m;
+  rsum[r] = sum;
+}
+
+int launch_ll_combine_stats(const float *parts, int shards, int64_t rows, float *rmax, float *rsum,
+                            cudaStream_t st) {
+  if (rows == 0) return 0;
+  ll_combine_stats_kernel<<<cdiv(rows, 256), 256, 0, st>>>(parts, shards, rows, rmax, rsum);
+  SERT_LAUNCH_CHECK();
+  return 0;
+}
+
+// One warp per instance: the label terms of the rows' cross-entropy that fall into this shard.
+// adot_out[i] = sum_{labels e in shard, o unclipped} (-cw*y/clip(o)) * o  (partial of sum_e do*o)
+__global__ void __launch_bounds__(256) ll_shard_labels_kernel(LlInstanceArgs a, const float *__restrict__ smax,
+                                                              const float *__restrict__ ssum, int e_begin,
+                                                              float *__restrict__ adot_out) {
+  const int i = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (i >= a.B) return;
+  const float *s = a.S + (long long)i * a.lds;
+  const float m = smax[i], sum = ssum[i];
+  const long long p0 = a.indptr[i] - a.nnz_base, p1 = a.indptr[i + 1] - a.nnz_base;
+  const float wi = a.w ? a.w[i] : 1.0f;
+  const float cw = a.train ? wi * a.inv_B : 0.f;
+  float ell = 0.f, adot = 0.f;
+  for (long long p = p0 + lane; p < p1; p += 32) {
+    const int e = a.indices[p] - e_begin;
+    if (e < 0 || e >= a.E) continue;
+    const float y = a.data[p];
+    const float o = expf(s[e] - m) / sum;
+    const float c = clipf_(o, SERT_CLIP_LO, SERT_CLIP_HI);
+    ell -= y * logf(c);
+    if (o >= SERT_CLIP_LO && o <= SERT_CLIP_HI) adot += (-cw * y / c) * o;
+  }
+  ell = warp_sum(ell);
+  adot = warp_sum(adot);
+  if (lane == 0) {
+    if (a.ell_out) a.ell_out[i] = ell;
+    if (adot_out) adot_out[i] = adot;
+    if (ell != 0.f) atomicAdd(a.loss_acc, (double)(a.train ? wi * ell : ell));
+  }
+}
+
+int launch_ll_shard_labels(const LlInstanceArgs &a, const float *smax, const float *ssum, int e_begin,
+                           float *adot_out, cudaStream_t st) {
+  if (a.B == 0) return 0;
+  ll_shard_labels_kernel<<<cdiv(a.B, 8), 256, 0, st>>>(a, smax, ssum, e_begin, adot_out);
+  SERT_LAUNCH_CHECK();
+  return 0;
+}
+
+// ds[i,e] = o*(do - adot[i]) over the shard's columns, adot all-reduced over the shards.
+__global__ void __launch_bounds__(256) ll_shard_ds_kernel(LlInstanceArgs a, const float *__restrict__ smax,
+                                                          const float *__restrict__ ssum, int e_begin,
+                                                          const float *__restrict__ adot_all) {
+  const int i = blockIdx.x;
+  const float *s = a.S + (long long)i * a.lds;
+  float *ds = a.DS + (long long)i * a.lds;
+  const float m = smax[i], sum = ssum[i], adot = adot_all[i];
+  for (int e = threadIdx.x; e < a.E; e += blockDim.x) ds[e] = -(expf(s[e] - m) / sum) * adot;
+  __syncthreads();
+  const long long p0 = a.indptr[i] - a.nnz_base, p1 = a.indptr[i + 1] - a.nnz_base;
+  const float wi = a.w ? a.w[i] : 1.0f;
+  const float cw = wi * a.inv_B;
+  for (long long p = p0 + threadIdx.x; p < p1; p += blockDim.x) {
+    const int e = a.indices[p] - e_begin;
+    if (e < 0 || e >= a.E) continue;
+    const float y = a.data[p];
+    const float o = expf(s[e] - m) / sum;
+    const float c = clipf_(o, SERT_CLIP_LO, SERT_CLIP_HI);
+    if (o >= SERT_CLIP_LO && o <= SERT_CLIP_HI) atomicAdd(ds + e, o * (-cw * y / c));
+  }
+}
+
+int launch_ll_shard_ds(const LlInstanceArgs &a, const float *smax, const float *ssum, int e_begin,
+                       const float *adot_all, cudaStream_t st) {
+  if (a.B == 0) return 0;
+  SERT_REQUIRE(a.DS != nullptr, "training needs a dS buffer");
+  ll_shard_ds_kernel<<<a.B, a.E >= 1024 ? 256 : 128, 0, st>>>(a, smax, ssum, e_begin, adot_all);
   SERT_LAUNCH_CHECK();
   return 0;
 }

@@ -32,7 +32,19 @@ struct LlInstanceArgs {
 int launch_ll_instance(const LlInstanceArgs &a, cudaStream_t st);
 
 // dZ[i,w,:] = p * (dp - sum_e dp*p), dp = ds/clip(p) on the unclipped entries; in place over Z.
+// mode 0: both halves; 1: racc[r] = partial row sum only; 2: apply with racc[r] given (entity-sharded step).
 int launch_ll_dz(float *Z, const float *rmax, const float *rsum, const float *DS, int B, int W, int E,
-                 int64_t ldz, int64_t lds, cudaStream_t st);
+                 int64_t ldz, int64_t lds, cudaStream_t st, int mode = 0, float *racc = nullptr);
+
+// ---- entity-sharded softmax pieces (columns [e_begin, e_begin+E) of the entity axis live on this rank) ----
+// parts [shard][2][rows] of gathered (row max, row sum) -> global statistics
+int launch_ll_combine_stats(const float *parts, int shards, int64_t rows, float *rmax, float *rsum,
+                            cudaStream_t st);
+// label terms owned by this shard: partial ell (into loss_acc / ell_out) and partial sum_e do*o (adot_out, train)
+int launch_ll_shard_labels(const LlInstanceArgs &a, const float *smax, const float *ssum, int e_begin,
+                           float *adot_out, cudaStream_t st);
+// ds over the shard's columns given the all-reduced adot
+int launch_ll_shard_ds(const LlInstanceArgs &a, const float *smax, const float *ssum, int e_begin,
+                       const float *adot_all, cudaStream_t st);
 
 }  // namespace sert

@@ -63,7 +63,7 @@ __global__ void __launch_bounds__(256) dense_update_kernel(OptimArgs a) {
       float4 g = make_float4(0.f, 0.f, 0.f, 0.f);
       if (touched) g = __ldcg(g4 + i4);
       const float l2 = sg.regularised ? a.l2_scale : 0.0f;
-      if (sg.regularised) sumsq = p.x * p.x + p.y * p.y + p.z * p.z + p.w * p.w;
+      if (sg.regularised == 1) sumsq = p.x * p.x + p.y * p.y + p.z * p.z + p.w * p.w;
       float pv[4] = {p.x, p.y, p.z, p.w};
       float v1[4] = {x1.x, x1.y, x1.z, x1.w};
       float v2[4] = {x2.x, x2.y, x2.z, x2.w};

@@ -79,6 +79,14 @@ struct sert_model {
   __nv_bfloat16 *XT_s = nullptr;   // (dw,  3*BW64)   A of  dWd = X^T . dZ
   __nv_bfloat16 *dZT_s = nullptr;  // (E,   3*BW64)   B of  dWd
   bool use_tensor = true;
+  // entity-sharded (column-parallel) log-linear step: this rank owns the columns [e_begin, e_begin + cfg.entities)
+  // of Wd / bd; R is replicated.  `exchange` performs the collectives on device buffers (include/sert_b200.h).
+  int shard_rank = 0, shard_world = 1;
+  int64_t e_begin = 0, e_total = 0;
+  sert_exchange_fn exchange = nullptr;
+  void *exchange_ctx = nullptr;
+  float *xstats = nullptr;         // [kMaxShards][2][B*W] gathered (row max, row sum)
+  float *smax = nullptr, *ssum = nullptr, *adot = nullptr, *racc = nullptr;
   // host-batch staging
   int32_t *stage_x = nullptr, *stage_y = nullptr, *stage_neg = nullptr, *stage_indices = nullptr;
   int64_t *stage_indptr = nullptr;
@@ -97,6 +105,7 @@ struct sert_model {
 namespace sert {
 
 static bool is_vs(const sert_config &c) { return c.kind == SERT_KIND_VECTORSPACE; }
+constexpr int kMaxShards = 16;
 
 static int validate(const sert_config &c) {
   SERT_REQUIRE(c.kind == SERT_KIND_LOGLINEAR || c.kind == SERT_KIND_VECTORSPACE, "unknown model kind");
@@ -180,6 +189,11 @@ static size_t carve(sert_model &m, void *base) {
     m.dX = train ? b.take<float>(B * W * dw) : nullptr;
     m.rmax = b.take<float>(B * W);
     m.rsum = b.take<float>(B * W);
+    m.xstats = b.take<float>(kMaxShards * 2 * B * W);
+    m.smax = b.take<float>(B);
+    m.ssum = b.take<float>(B);
+    m.adot = b.take<float>(B);
+    m.racc = b.take<float>(B * W);
     const long long dw64 = tc_padded_k((int)dw), E64 = tc_padded_k((int)E), BW64 = tc_padded_k((int)(B * W));
     m.Xs = b.take<__nv_bfloat16>(B * W * 3 * dw64);
     m.WdT_s = b.take<__nv_bfloat16>(E * 3 * dw64);
@@ -358,7 +372,8 @@ static bool ll_tensor(const sert_model &m, long long M, long long N) {
   return m.use_tensor && ((M + 127) / 128) * ((N + 255) / 256) >= 32;
 }
 
-static int ll_forward(sert_model &m, const int32_t *x, int rows /* instances */, cudaStream_t st) {
+static int ll_forward(sert_model &m, const int32_t *x, int rows /* instances */, cudaStream_t st,
+                      float *rmax_out = nullptr, float *rsum_out = nullptr) {
   const sert_config &c = m.cfg;
   const int E = (int)c.entities, dw = c.word_dim;
   const long long BW = (long long)rows * c.window;
@@ -377,7 +392,7 @@ static int ll_forward(sert_model &m, const int32_t *x, int rows /* instances */,
   } else {
     if (launch_gemm_f32(m.X, Wd, m.Z, (int)BW, E, dw, false, false, dw, E, E, EPI_BIAS, bd, 1, st)) return -1;
   }
-  return launch_ll_row_stats(m.Z, BW, E, E, m.rmax, m.rsum, st);
+  return launch_ll_row_stats(m.Z, BW, E, E, rmax_out ? rmax_out : m.rmax, rsum_out ? rsum_out : m.rsum, st);
 }
 
 static LlInstanceArgs ll_instance_args(sert_model &m, const int64_t *indptr, long long nnz_base,
@@ -391,19 +406,8 @@ static LlInstanceArgs ll_instance_args(sert_model &m, const int64_t *indptr, lon
   return a;
 }
 
-static int ll_train_step(sert_model &m, const int32_t *x, const int64_t *indptr, long long nnz_base,
-                         const int32_t *indices, const float *data, const float *w, float *loss_out) {
-  const sert_config &c = m.cfg;
-  cudaStream_t st = m.st;
-  const int B = c.batch, W = c.window, E = (int)c.entities, dw = c.word_dim;
-  const int BW = B * W;
-  float *Wd = m.theta + m.off[SERT_PARAM_DENSE_W];
-  m.stamp += 1;
-  if (ll_forward(m, x, B, st)) return -1;
-  if (launch_ll_joint(m.Z, m.rmax, m.rsum, m.S, B, W, E, E, E, st)) return -1;
-  if (launch_ll_instance(ll_instance_args(m, indptr, nnz_base, indices, data, w, true, nullptr), st)) return -1;
-  if (launch_ll_dz(m.Z, m.rmax, m.rsum, m.DS, B, W, E, E, E, st)) return -1;
-  // gWd += X^T . dZ ; gbd += colsum(dZ) ; dX = dZ . Wd^T
+// gWd += X^T . dZ ; gbd += colsum(dZ) ; dX = dZ . Wd^T   (dZ lives in m.Z)
+static int ll_backward_gemms(sert_model &m, int BW, int E, int dw, float *Wd, cudaStream_t st) {
   if (ll_tensor(m, dw, E)) {
     // gWd = X^T . dZ : A = X^T (dw, B*W), B = dZ^T (E, B*W), both as transposed bf16x3 splits
     const int kt = 3 * tc_padded_k(BW);
@@ -429,6 +433,22 @@ static int ll_train_step(sert_model &m, const int32_t *x, const int64_t *indptr,
   } else {
     if (launch_gemm_f32(m.Z, Wd, m.dX, BW, dw, E, false, true, E, E, dw, EPI_STORE, nullptr, 1, st)) return -1;
   }
+  return 0;
+}
+
+static int ll_train_step(sert_model &m, const int32_t *x, const int64_t *indptr, long long nnz_base,
+                         const int32_t *indices, const float *data, const float *w, float *loss_out) {
+  const sert_config &c = m.cfg;
+  cudaStream_t st = m.st;
+  const int B = c.batch, W = c.window, E = (int)c.entities, dw = c.word_dim;
+  const int BW = B * W;
+  float *Wd = m.theta + m.off[SERT_PARAM_DENSE_W];
+  m.stamp += 1;
+  if (ll_forward(m, x, B, st)) return -1;
+  if (launch_ll_joint(m.Z, m.rmax, m.rsum, m.S, B, W, E, E, E, st)) return -1;
+  if (launch_ll_instance(ll_instance_args(m, indptr, nnz_base, indices, data, w, true, nullptr), st)) return -1;
+  if (launch_ll_dz(m.Z, m.rmax, m.rsum, m.DS, B, W, E, E, E, st)) return -1;
+  if (ll_backward_gemms(m, BW, E, dw, Wd, st)) return -1;
   if (launch_scatter_rows(x, m.dX, m.grad + m.off[SERT_PARAM_WORD_REPR], m.flagR, m.stamp, BW, 1, dw, 1.0f, st))
     return -1;
   m.step += 1;
@@ -448,6 +468,86 @@ static int ll_eval_step(sert_model &m, const int32_t *x, const int64_t *indptr, 
                                           debug ? m.dbg_ell : nullptr), st))
     return -1;
   return launch_finalize_eval(m.acc, loss_out, 1.0f / (float)B, st);
+}
+
+// ---- log-linear, entity-sharded (SURVEY.md 8(e) "column-parallel softmax") -----------------------
+// cfg.entities is the shard width; CSR label indices are global entity ids.  Exchange points of one
+// training step (all through m.exchange, ordered on the model's stream):
+//   (1) all-gather of the per-word (row max, row sum)           2*B*W floats per rank
+//   (2) all-gather of the joint (row max, row sum)              2*B   floats per rank
+//   (3) all-reduce of sum_e do*o per instance                   B     floats
+//   (4) all-reduce of sum_e dp*p per word                       B*W   floats
+//   (5) all-reduce of the partial dX = dZ_loc . Wd_loc^T        B*W*dw floats
+// The word table R and its Adadelta state are replicated and receive the identical update on every rank.
+static int xchg(sert_model &m, int op, float *buf, size_t count) {
+  SERT_CUDA(cudaGetLastError());
+  const int rc = m.exchange(m.exchange_ctx, op, buf, count);
+  SERT_REQUIRE(rc == 0, "exchange callback failed");
+  return 0;
+}
+
+// this rank's slot of the gathered statistics: [shard][2][rows]
+static float *ll_my_stats(sert_model &m, long long rows) { return m.xstats + (size_t)m.shard_rank * 2 * rows; }
+// all-gathers the per-shard (row max, row sum) written to ll_my_stats() and combines them into (gmax, gsum)
+static int ll_shard_combine(sert_model &m, long long rows, float *gmax, float *gsum) {
+  if (xchg(m, SERT_XCHG_ALLGATHER, m.xstats, (size_t)2 * rows)) return -1;
+  return launch_ll_combine_stats(m.xstats, m.shard_world, rows, gmax, gsum, m.st);
+}
+
+static int ll_shard_forward(sert_model &m, const int32_t *x, const int64_t *indptr, long long nnz_base,
+                            const int32_t *indices, const float *data, const float *w, bool train,
+                            float *ell_out) {
+  const sert_config &c = m.cfg;
+  const int B = c.batch, W = c.window, E = (int)c.entities;
+  const long long BW = (long long)B * W;
+  float *mine = ll_my_stats(m, BW);
+  if (ll_forward(m, x, B, m.st, mine, mine + BW)) return -1;      // local columns of Z and their statistics
+  if (ll_shard_combine(m, BW, m.rmax, m.rsum)) return -1;
+  if (launch_ll_joint(m.Z, m.rmax, m.rsum, m.S, B, W, E, E, E, m.st)) return -1;
+  mine = ll_my_stats(m, B);
+  if (launch_ll_row_stats(m.S, B, E, E, mine, mine + B, m.st)) return -1;
+  if (ll_shard_combine(m, B, m.smax, m.ssum)) return -1;
+  LlInstanceArgs a = ll_instance_args(m, indptr, nnz_base, indices, data, w, train, ell_out);
+  return launch_ll_shard_labels(a, m.smax, m.ssum, (int)m.e_begin, train ? m.adot : nullptr, m.st);
+}
+
+static int ll_train_step_sharded(sert_model &m, const int32_t *x, const int64_t *indptr, long long nnz_base,
+                                 const int32_t *indices, const float *data, const float *w, float *loss_out) {
+  const sert_config &c = m.cfg;
+  cudaStream_t st = m.st;
+  const int B = c.batch, W = c.window, E = (int)c.entities, dw = c.word_dim;
+  const int BW = B * W;
+  float *Wd = m.theta + m.off[SERT_PARAM_DENSE_W];
+  m.stamp += 1;
+  if (ll_shard_forward(m, x, indptr, nnz_base, indices, data, w, true, nullptr)) return -1;
+  if (xchg(m, SERT_XCHG_ALLREDUCE_SUM, m.adot, (size_t)B)) return -1;
+  LlInstanceArgs a = ll_instance_args(m, indptr, nnz_base, indices, data, w, true, nullptr);
+  if (launch_ll_shard_ds(a, m.smax, m.ssum, (int)m.e_begin, m.adot, st)) return -1;
+  if (launch_ll_dz(m.Z, m.rmax, m.rsum, m.DS, B, W, E, E, E, st, 1, m.racc)) return -1;
+  if (xchg(m, SERT_XCHG_ALLREDUCE_SUM, m.racc, (size_t)BW)) return -1;
+  if (launch_ll_dz(m.Z, m.rmax, m.rsum, m.DS, B, W, E, E, E, st, 2, m.racc)) return -1;
+  if (ll_backward_gemms(m, BW, E, dw, Wd, st)) return -1;
+  if (xchg(m, SERT_XCHG_ALLREDUCE_SUM, m.dX, (size_t)BW * dw)) return -1;
+  if (launch_scatter_rows(x, m.dX, m.grad + m.off[SERT_PARAM_WORD_REPR], m.flagR, m.stamp, BW, 1, dw, 1.0f, st))
+    return -1;
+  m.step += 1;
+  OptimArgs o = optim_args(m, loss_out);
+  o.c0 = 1.0f; o.c1 = 0.95f; o.c2 = 0.f; o.c3 = 1e-6f;
+  return timed_update(m, o, false);
+}
+
+static int ll_eval_step_sharded(sert_model &m, const int32_t *x, const int64_t *indptr, long long nnz_base,
+                                const int32_t *indices, const float *data, float *loss_out, bool debug) {
+  if (ll_shard_forward(m, x, indptr, nnz_base, indices, data, nullptr, false, debug ? m.dbg_ell : nullptr))
+    return -1;
+  return launch_finalize_eval(m.acc, loss_out, 1.0f / (float)m.cfg.batch, m.st);
+}
+
+// Per-batch losses of a sharded model are partial sums (labels owned by the shard, norm of the shard's columns;
+// rank 0 adds the replicated word table): one all-reduce over the slots completes them.
+static int ll_reduce_losses(sert_model &m, int32_t first_slot, int64_t n) {
+  if (m.shard_world <= 1 || n == 0) return 0;
+  return xchg(m, SERT_XCHG_ALLREDUCE_SUM, m.losses + first_slot, (size_t)n);
 }
 
 static int check_batch(sert_model *m, int split, int64_t b) {
@@ -588,6 +688,21 @@ int sert_model_set_tensor_cores(sert_model *m, int enable) {
   return 0;
 }
 
+int sert_model_set_entity_shard(sert_model *m, int32_t rank, int32_t world, int64_t entity_begin,
+                                int64_t entities_total, sert_exchange_fn fn, void *ctx) {
+  SERT_REQUIRE(m && fn, "null argument");
+  SERT_REQUIRE(!is_vs(m->cfg), "entity sharding of the training step is defined for the log-linear model");
+  SERT_REQUIRE(world >= 1 && world <= kMaxShards && rank >= 0 && rank < world, "bad shard rank / world size");
+  SERT_REQUIRE(entity_begin >= 0 && entity_begin + m->cfg.entities <= entities_total && entities_total < (1ll << 31),
+               "shard columns out of range");
+  m->shard_rank = rank; m->shard_world = world; m->e_begin = entity_begin; m->e_total = entities_total;
+  m->exchange = fn; m->exchange_ctx = ctx;
+  // the replicated word table is L2-regularised on every rank but its norm enters the reported loss once
+  for (int s = 0; s < m->nseg; ++s)
+    if (m->seg[s].offset == m->off[SERT_PARAM_WORD_REPR]) m->seg[s].regularised = rank == 0 ? 1 : 2;
+  return 0;
+}
+
 int sert_model_profile(sert_model *m, int enable) {
   SERT_REQUIRE(m, "null model");
   m->profile = enable != 0;
@@ -651,11 +766,12 @@ int sert_train_batches(sert_model *m, const int64_t *order_host, int64_t n, cons
       const int32_t *neg = neg_dev ? neg_dev + j * (int64_t)c.batch * c.num_negatives : nullptr;
       rc = vs_train_step(*m, d.x + r0 * c.window, d.y + r0, w, neg, loss);
     } else {
-      rc = ll_train_step(*m, d.x + r0 * c.window, d.indptr + r0, 0, d.indices, d.data, w, loss);
+      rc = (m->exchange ? ll_train_step_sharded : ll_train_step)(*m, d.x + r0 * c.window, d.indptr + r0, 0,
+                                                                d.indices, d.data, w, loss);
     }
     if (rc) return -1;
   }
-  return 0;
+  return m->exchange ? ll_reduce_losses(*m, first_slot, n) : 0;
 }
 
 int sert_eval_batches(sert_model *m, int split, const int64_t *order_host, int64_t n, const int32_t *neg_dev,
@@ -674,11 +790,12 @@ int sert_eval_batches(sert_model *m, int split, const int64_t *order_host, int64
       const int32_t *neg = neg_dev ? neg_dev + j * (int64_t)c.batch * c.num_negatives : nullptr;
       rc = vs_eval_step(*m, d.x + r0 * c.window, d.y + r0, neg, loss, false);
     } else {
-      rc = ll_eval_step(*m, d.x + r0 * c.window, d.indptr + r0, 0, d.indices, d.data, loss, false);
+      rc = (m->exchange ? ll_eval_step_sharded : ll_eval_step)(*m, d.x + r0 * c.window, d.indptr + r0, 0,
+                                                              d.indices, d.data, loss, false);
     }
     if (rc) return -1;
   }
-  return 0;
+  return m->exchange ? ll_reduce_losses(*m, first_slot, n) : 0;
 }
 
 int sert_losses_fetch(sert_model *m, int32_t first_slot, int64_t n, float *out_host) {
@@ -734,7 +851,10 @@ int sert_train_batch_host(sert_model *m, const int32_t *x_host, const int32_t *y
     SERT_CUDA(cudaMemcpyAsync(m->stage_indptr, indptr_host, (B + 1) * sizeof(int64_t), cudaMemcpyHostToDevice, st));
     SERT_CUDA(cudaMemcpyAsync(m->stage_indices, indices_host + base, nnz * sizeof(int32_t), cudaMemcpyHostToDevice, st));
     SERT_CUDA(cudaMemcpyAsync(m->stage_data, data_host + base, nnz * sizeof(float), cudaMemcpyHostToDevice, st));
-    if (ll_train_step(*m, m->stage_x, m->stage_indptr, base, m->stage_indices, m->stage_data, w, loss)) return -1;
+    if ((m->exchange ? ll_train_step_sharded : ll_train_step)(*m, m->stage_x, m->stage_indptr, base,
+                                                              m->stage_indices, m->stage_data, w, loss))
+      return -1;
+    if (m->exchange && ll_reduce_losses(*m, c.loss_slots, 1)) return -1;
   }
   SERT_CUDA(cudaMemcpyAsync(loss_host, loss, sizeof(float), cudaMemcpyDeviceToHost, st));
   SERT_CUDA(cudaStreamSynchronize(st));
@@ -775,9 +895,12 @@ int sert_ll_forward_host(sert_model *m, int split, int64_t batch_index, float *o
   const sert_config &c = m->cfg;
   const Dataset &d = m->ds[split];
   const int64_t r0 = batch_index * c.batch;
-  if (ll_eval_step(*m, d.x + r0 * c.window, d.indptr + r0, 0, d.indices, d.data, m->losses + c.loss_slots, true))
+  if ((m->exchange ? ll_eval_step_sharded : ll_eval_step)(*m, d.x + r0 * c.window, d.indptr + r0, 0, d.indices,
+                                                          d.data, m->losses + c.loss_slots, true))
     return -1;
   const size_t B = c.batch, E = c.entities;
+  // sharded: z and s are this rank's columns; the instance losses are completed over the shards
+  if (m->exchange && out_ell_host && xchg(*m, SERT_XCHG_ALLREDUCE_SUM, m->dbg_ell, B)) return -1;
   if (out_z_host)
     SERT_CUDA(cudaMemcpyAsync(out_z_host, m->Z, B * c.window * E * sizeof(float), cudaMemcpyDeviceToHost, m->st));
   if (out_s_host) SERT_CUDA(cudaMemcpyAsync(out_s_host, m->S, B * E * sizeof(float), cudaMemcpyDeviceToHost, m->st));
@@ -792,6 +915,7 @@ int sert_predict_loglinear(sert_model *m, const int32_t *batch_host, int32_t row
   SERT_REQUIRE(!is_vs(m->cfg), "log-linear model required");
   const sert_config &c = m->cfg;
   SERT_REQUIRE(rows >= 0 && rows <= c.batch, "more rows than the model's batch size");
+  SERT_REQUIRE(m->exchange == nullptr, "predict_fn needs the full entity axis: gather the shards first");
   if (rows == 0) return 0;
   const size_t BW = (size_t)rows * c.window, E = c.entities;
   SERT_CUDA(cudaMemcpyAsync(m->stage_x, batch_host, BW * sizeof(int32_t), cudaMemcpyHostToDevice, m->st));

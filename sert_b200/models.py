@@ -69,6 +69,13 @@ class _NativeModel(object):
         self.handle = handle
         self.loss_slots = loss_slots
         self._keep = []          # torch tensors borrowed by the library
+        self.exchange = None     # sharding.Exchange of an entity-sharded log-linear model
+
+    def _check(self, rc):
+        """N.check, but an exception raised inside the exchange callback wins over the library's message."""
+        if rc != 0 and self.exchange is not None:
+            self.exchange.raise_pending()
+        N.check(rc)
 
     def close(self):
         if getattr(self, 'handle', None):
@@ -128,10 +135,10 @@ class _NativeModel(object):
             chunk = order[done:done + n]
             keep, negp = self._neg_dev(None if negatives is None else np.asarray(negatives)[done:done + n], n)
             if mode == 'train':
-                N.check(self.lib.sert_train_batches(self.handle, N.host_ptr(chunk), n, negp, 0))
+                self._check(self.lib.sert_train_batches(self.handle, N.host_ptr(chunk), n, negp, 0))
             else:
                 split = N.SPLIT_TRAIN if mode == 'test' else N.SPLIT_VALIDATE
-                N.check(self.lib.sert_eval_batches(self.handle, split, N.host_ptr(chunk), n, negp, 0))
+                self._check(self.lib.sert_eval_batches(self.handle, split, N.host_ptr(chunk), n, negp, 0))
             N.check(self.lib.sert_losses_fetch(self.handle, 0, n, N.host_ptr(out[done:done + n])))
             del keep
             done += n
@@ -346,16 +353,31 @@ class ModelBase(ModelInterface):
         ckpt = {'step': np.int64(self._native_step())}
         for name, (which, shape) in self._tensor_shapes().items():
             for slot, suffix in ((N.STATE_PARAM, ''), (N.STATE_S1, '/state1'), (N.STATE_S2, '/state2')):
-                ckpt[name + suffix] = self._native.get_tensor(which, shape, slot)
+                ckpt[name + suffix] = self._gather_columns(name, self._native.get_tensor(which, shape, slot))
         return ckpt
 
     def set_checkpoint(self, ckpt):
         for name, (which, shape) in self._tensor_shapes().items():
             for slot, suffix in ((N.STATE_PARAM, ''), (N.STATE_S1, '/state1'), (N.STATE_S2, '/state2')):
-                array = np.asarray(ckpt[name + suffix], dtype=np.float32)
+                array = self._slice_columns(name, np.asarray(ckpt[name + suffix], dtype=np.float32))
                 assert array.shape == tuple(shape), (name + suffix, array.shape, shape)
                 self._native.set_tensor(which, array, slot)
         N.check(self._native.lib.sert_model_set_step(self._native.handle, int(ckpt['step'])))
+
+    # entity-sharded models (LanguageModel(entity_shard=...)) hold column slices of some tensors; checkpoints and
+    # get_state() always carry the full tensors
+    _column_sharded = ()
+    _shard_span = None
+
+    def _gather_columns(self, name, array):
+        if self._shard_span is None or name not in self._column_sharded:
+            return array
+        return self._native.exchange.gather_columns(array, self._shard_span[2])
+
+    def _slice_columns(self, name, array):
+        if self._shard_span is None or name not in self._column_sharded:
+            return array
+        return np.ascontiguousarray(array[..., self._shard_span[0]:self._shard_span[1]])
 
     def _native_step(self):
         t = N.c_int64(0)
@@ -492,7 +514,11 @@ class LanguageModel(LanguageModelBase):
                  regularization_lambda,
                  training_set,
                  validation_set,
-                 dense_init=None, device=None, loss_slots=1 << 16):
+                 dense_init=None, device=None, loss_slots=1 << 16, entity_shard=None):
+        """``entity_shard``: a ``sert_b200.sharding.Exchange`` (one process per GPU, e.g. ``DistExchange()``);
+        this rank then owns a contiguous block of the E output columns, the word table is
+        replicated, and train()/train_error()/validation_error()/get_state() return the same values on every
+        rank.  All ranks must pass identical initial values and the same batch order."""
         super(LanguageModel, self).__init__(
             batch_size=batch_size,
             window_size=window_size,
@@ -509,24 +535,37 @@ class LanguageModel(LanguageModelBase):
             dense_init = (glorot_uniform((self.representation_size, self.output_layer_size)),
                           np.zeros(self.output_layer_size, dtype=np.float32))
 
+        self._local_entities = self.output_layer_size
+        if entity_shard is not None:
+            from sert_b200 import sharding
+            begin, end = sharding.shard_bounds(self.output_layer_size, entity_shard.world, entity_shard.rank)
+            assert end - begin >= 2, 'every shard needs at least two entity columns'
+            self._shard_span = (begin, end, self.output_layer_size)
+            self._column_sharded = ('dense_w', 'dense_b')
+            self._local_entities = end - begin
+
         self._native = _NativeModel(
             N.KIND_LOGLINEAR, self.batch_size, self.window_size, self.vocabulary_size,
-            self.output_layer_size, self.representation_size, lam=float(regularization_lambda),
+            self._local_entities, self.representation_size, lam=float(regularization_lambda),
             loss_slots=loss_slots, device=device)
+        if entity_shard is not None:
+            sharding.attach(self._native, entity_shard, self._shard_span[0], self.output_layer_size)
         self._native.set_tensor(N.PARAM_WORD_REPR, representations_init)
-        self._native.set_tensor(N.PARAM_DENSE_W, dense_init[0])
-        self._native.set_tensor(N.PARAM_DENSE_B, dense_init[1])
+        self._native.set_tensor(N.PARAM_DENSE_W, self._slice_columns('dense_w', np.asarray(dense_init[0])))
+        self._native.set_tensor(N.PARAM_DENSE_B, self._slice_columns('dense_b', np.asarray(dense_init[1])))
         self._attach_datasets()
         self._create_functions()
 
     def get_dense(self):
-        return (self._native.get_tensor(N.PARAM_DENSE_W, (self.representation_size, self.output_layer_size)),
-                self._native.get_tensor(N.PARAM_DENSE_B, (self.output_layer_size,)))
+        """Full (dw,E) W and (E,) b; a collective over the shards when the model is entity-sharded."""
+        shapes = self._tensor_shapes()
+        return tuple(self._gather_columns(name, self._native.get_tensor(*shapes[name]))
+                     for name in ('dense_w', 'dense_b'))
 
     def _tensor_shapes(self):
         return {'representations': (N.PARAM_WORD_REPR, (self.vocabulary_size, self.representation_size)),
-                'dense_w': (N.PARAM_DENSE_W, (self.representation_size, self.output_layer_size)),
-                'dense_b': (N.PARAM_DENSE_B, (self.output_layer_size,))}
+                'dense_w': (N.PARAM_DENSE_W, (self.representation_size, self._local_entities)),
+                'dense_b': (N.PARAM_DENSE_B, (self._local_entities,))}
 
     @property
     def predict_fn(self):

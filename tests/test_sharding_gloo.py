@@ -72,3 +72,63 @@ def test_all_gather_and_merge_world2(tmp_path):
     mp.spawn(worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
     a, b = np.load(tmp_path / 'ok_0.npy'), np.load(tmp_path / 'ok_1.npy')
     np.testing.assert_array_equal(a, b)             # every rank ends with the same merged list
+
+
+# ---- entity-sharded log-linear step: host-side exchange logic (sert_b200/sharding.py) over gloo ----------------
+def ll_worker(rank, world, port, out_dir):
+    """Each rank plays one column shard: the device kernels are replaced by numpy stand-ins on the shard's columns,
+    the exchanges go through the REAL callback (pointer -> arena view -> collective) that libsert_b200 would call."""
+    os.environ['MASTER_ADDR'] = '127.0.0.1'
+    os.environ['MASTER_PORT'] = str(port)
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    from oracle import sert_oracle as O
+    from sert_b200 import sharding
+    from tests import helpers as H
+    p = H.ll_problem(3, V=300, E=45, dw=8, W=3, B=16, n_batches=1)
+    B, W, E = p['B'], p['W'], p['E']
+    x = p['train'][0][:B]
+    f = O.loglinear_forward(p['R'], p['Wd'], p['bd'], x)
+    ref_ell = O.loglinear_instance_losses(f['o'], O.dense_rows(p['train'][1], 0, B))
+
+    ex = sharding.DistExchange()
+    b, e = sharding.shard_bounds(E, world, rank)
+    arena = torch.zeros(1 << 16, dtype=torch.uint8)
+    cb = ex.bind(arena)
+    fl = arena.view(torch.float32).numpy()            # float view of the fake arena
+    base = arena.data_ptr()
+
+    def exchange(op, off, count):
+        assert cb(None, op, base + 4 * off, count) == 0, ex._error
+
+    def gathered_stats(local, rows):
+        """local (rows, E_loc) -> global (max, sum) through the [shard][2][rows] all-gather layout."""
+        m = local.max(axis=1)
+        fl[rank * 2 * rows: rank * 2 * rows + rows] = m
+        fl[rank * 2 * rows + rows: (rank + 1) * 2 * rows] = np.exp(local - m[:, None]).sum(axis=1)
+        exchange(sharding.XCHG_ALLGATHER, 0, 2 * rows)
+        parts = fl[:world * 2 * rows].reshape(world, 2, rows).copy()
+        gm = parts[:, 0].max(axis=0)
+        return gm, (parts[:, 1] * np.exp(parts[:, 0] - gm)).sum(axis=0)
+
+    z = f['z'].reshape(B * W, E)[:, b:e]
+    gm, gs = gathered_stats(z, B * W)
+    pw = np.exp(z - gm[:, None]) / gs[:, None]
+    s = np.log(np.clip(pw, 1e-7, np.float32(1 - 1e-7))).reshape(B, W, e - b).sum(axis=1)
+    sm, ss = gathered_stats(s, B)
+    o = np.exp(s - sm[:, None]) / ss[:, None]
+    y = O.dense_rows(p['train'][1], 0, B)[:, b:e]
+    fl[4096:4096 + B] = -(y * np.log(np.clip(o, 1e-7, np.float32(1 - 1e-7)))).sum(axis=1)
+    exchange(sharding.XCHG_ALLREDUCE_SUM, 4096, B)
+    H.close(fl[4096:4096 + B], ref_ell, what='instance losses over %d shards' % world)
+    full = ex.gather_columns(p['Wd'][:, b:e], E)
+    np.testing.assert_array_equal(full, p['Wd'])
+    assert ex.calls == 3
+    np.save(os.path.join(out_dir, 'll_ok_%d.npy' % rank), fl[4096:4096 + B])
+    dist.destroy_process_group()
+
+
+def test_loglinear_exchange_world2(tmp_path):
+    port = 31500 + (os.getpid() % 2000)
+    mp.spawn(ll_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    a, b = np.load(tmp_path / 'll_ok_0.npy'), np.load(tmp_path / 'll_ok_1.npy')
+    np.testing.assert_array_equal(a, b)
