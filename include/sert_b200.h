@@ -110,9 +110,17 @@ SERT_API int sert_model_get_step(sert_model *m, int64_t *t);
  * summed kernel time, the launch count and the ALGORITHMIC bytes of one launch (24 B per parameter:
  * read+write of theta and the two optimiser-state arrays; DESIGN.md "roofline"). */
 SERT_API int sert_model_profile(sert_model *m, int enable);
-/* Vector-space training step: 1 (default) = fused forward+backward kernel (one warp per pair of instances) for
- * representation sizes up to 384, 0 = one kernel per stage (any shape; also what the fused kernel is tested against). */
+/* Vector-space training step: 1 (default) = fused forward+backward kernel -- one CTA per tile of 8 instances when both
+ * representation sizes are 128 (csrc/vs_tile.cu), else one warp per pair of instances for sizes up to 384
+ * (csrc/vs_warp.cu); 2 = always the warp kernel; 0 = one kernel per stage (any shape; what the fused kernels are
+ * tested against). */
 SERT_API int sert_model_set_fused(sert_model *m, int enable);
+/* Vector-space training step, fused tile kernel: word ids that occur very often in every batch ("the", "of", ...).
+ * Thousands of gradient-row additions per step on one row serialise in the L2 slices that own its four lines
+ * (tools/red_probe.cu), so additions to these rows are spread over 16 private copies and folded into the gradient
+ * row by a small kernel behind the step.  Result-neutral up to float summation order.  n <= 32; n = 0 turns it
+ * off.  The Python model picks the ids from the training set's word counts (sert_b200/models.py). */
+SERT_API int sert_model_set_hot_words(sert_model *m, const int32_t *ids_host, int32_t n);
 /* Vector-space training step: 1 (default) = the two small dense-gradient kernels (gW = h^T.da, gb = colsum(da))
  * run on a second stream concurrently with the Adam stream over the tables; 0 = everything on one stream. */
 SERT_API int sert_model_set_overlap(sert_model *m, int enable);

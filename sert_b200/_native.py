@@ -52,6 +52,7 @@ SIGNATURES = {
     'sert_model_profile': (c_int, [c_void_p, c_int]),
     'sert_model_set_fused': (c_int, [c_void_p, c_int]),
     'sert_model_set_overlap': (c_int, [c_void_p, c_int]),
+    'sert_model_set_hot_words': (c_int, [c_void_p, c_void_p, c_int32]),
     'sert_model_set_tensor_cores': (c_int, [c_void_p, c_int]),
     'sert_debug_gemm_tc_bench': (c_int, [c_int, c_int, c_int, c_int, c_int, ctypes.POINTER(c_float)]),
     'sert_model_profile_read': (c_int, [c_void_p, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(c_int64),

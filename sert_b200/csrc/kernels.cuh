@@ -63,9 +63,28 @@ struct VsFusedArgs {
   double *loss_acc;
   int B, W, k, dw, de;
   float inv_B;
+  // Hot word rows (tile kernel only; nullptr / 0 = none).  A word id that occurs thousands of times per batch makes
+  // thousands of row additions land on the same four L2 lines, which the L2 slices serialise (tools/red_probe.cu:
+  // 44 MB of row additions take 14-20 us on uniform rows and 39-44 us on Zipf rows; plain stores behave the same).
+  // Additions to a hot row go to one of `hot_replicas` private copies instead (chosen by CTA), and
+  // launch_hot_flush folds the copies into the gradient row afterwards.
+  const int8_t *hot_slot = nullptr;   // (V,) slot of a hot word id, -1 otherwise
+  float *hot_acc = nullptr;           // (hot_replicas, kMaxHotRows, dw) zero between steps
+  int hot_replicas = 0;               // power of two
+  const int32_t *hot_ids = nullptr;   // (n_hot,) word id of each slot
+  int n_hot = 0;
 };
-// WpT_scratch: (de, dw) floats, receives the transpose of Wp (refreshed by every call).
-int launch_vs_fused(const VsFusedArgs &a, float *WpT_scratch, cudaStream_t st);
+constexpr int kMaxHotRows = 32;
+constexpr int kHotReplicas = 16;
+// gR[hot_ids[s]] += sum_r hot_acc[r][s]; hot_acc <- 0; flagR[hot_ids[s]] = stamp       (n_hot CTAs)
+int launch_hot_flush(float *hot_acc, int replicas, const int32_t *hot_ids, int n_hot, int d, float *gR,
+                     uint32_t *flagR, uint32_t stamp, cudaStream_t st);
+// WpT_scratch: (de, dw) floats, the transpose of Wp; refresh_WpT = recompute it first (it is stale).
+// variant: 1 = CTA-per-8-instances tile kernel (csrc/vs_tile.cu) when d_w = d_e = 128, window <= 32, k <= 15, else the
+// warp kernel; 2 = warp kernel only.
+int launch_vs_fused(const VsFusedArgs &a, float *WpT_scratch, bool refresh_WpT, int variant, cudaStream_t st);
+// the tile kernel alone: 0 = launched, 1 = shape not served, -1 = error.  WpT: (de, dw) transpose of Wp.
+int launch_vs_tile(const VsFusedArgs &a, const float *WpT, cudaStream_t st);
 
 // scatter-add of dh/denom into the word-gradient rows (autodiff of the gather, AdvancedIncSubtensor)
 int launch_scatter_rows(const int32_t *x, const float *dh, float *gR, uint32_t *flagR, uint32_t stamp,
@@ -101,6 +120,10 @@ struct OptimArgs {
   float inv_B, reg_coeff;
   int phase = 0;                   // 0 = everything, 3 = row-stamped tables only, 4 = dense tensors only
   long long first4 = 0;            // first 16-byte chunk to process (phase 4 starts at the first dense tensor)
+  unsigned int *ticket = nullptr;  // phase 4: block counter (zero between launches); the last block finalises the loss
+  // phase 4, optional: segment `transposed_segment` ((rows, row_len) row-major) is also written transposed here
+  float *transposed = nullptr;
+  int transposed_segment = 0, transposed_rows = 0;
 };
 
 int launch_adam(const OptimArgs &a, cudaStream_t st);

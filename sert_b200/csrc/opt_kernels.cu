@@ -87,6 +87,13 @@ __global__ void __launch_bounds__(256) dense_update_kernel(OptimArgs a) {
         }
       }
       th4[i4] = make_float4(pv[0], pv[1], pv[2], pv[3]);
+      if (PHASE == 4 && a.transposed != nullptr && s == a.transposed_segment) {
+        // keep the (cols, rows) copy of the projection matrix current for the next step's back-projection
+        const unsigned int el = (unsigned int)(e - sg.offset);
+        const unsigned int r = el / (unsigned int)sg.row_len, c = el % (unsigned int)sg.row_len;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) a.transposed[(size_t)(c + j) * a.transposed_rows + r] = pv[j];
+      }
       s14[i4] = make_float4(v1[0], v1[1], v1[2], v1[3]);
       s24[i4] = make_float4(v2[0], v2[1], v2[2], v2[3]);
       // The gradient row is zeroed only now, behind the stores that depend on its value: a store issued
@@ -106,6 +113,34 @@ __global__ void __launch_bounds__(256) dense_update_kernel(OptimArgs a) {
     double tot = 0.0;
     for (int w = 0; w < (int)(blockDim.x >> 5); ++w) tot += s_part[w];
     if (tot != 0.0) atomicAdd(a.acc + 1 + (blockIdx.x & (kSumsqSlots - 1)), tot);
+  }
+  if (PHASE == 4) {
+    // The dense tensors are a handful of blocks: the last one to finish writes the step's loss (what
+    // finalize_train_kernel does behind the other phases) -- one launch less on the step's critical path.
+    __shared__ bool s_last;
+    if (threadIdx.x == 0) {
+      __threadfence();
+      s_last = atomicAdd(a.ticket, 1u) == gridDim.x - 1;
+    }
+    __syncthreads();
+    if (s_last) {                       // block-uniform
+      __threadfence();
+      double v = 0.0;
+      if (threadIdx.x < kSumsqSlots) {  // the slots are read in parallel: 64 dependent L2 round trips cost ~15 us
+        v = __ldcg(a.acc + 1 + threadIdx.x);
+        a.acc[1 + threadIdx.x] = 0.0;
+      }
+      v = warp_sum_d(v);
+      if (threadIdx.x < kSumsqSlots && (threadIdx.x & 31) == 0) s_part[threadIdx.x >> 5] = v;
+      __syncthreads();
+      if (threadIdx.x == 0) {
+        const double ss = s_part[0] + s_part[1];
+        if (a.loss_out != nullptr)
+          *a.loss_out = (float)((float)(__ldcg(a.acc) * (double)a.inv_B) + (float)((double)a.reg_coeff * ss));
+        a.acc[0] = 0.0;
+        *a.ticket = 0u;
+      }
+    }
   }
 }
 
@@ -127,6 +162,9 @@ static int launch_update(const OptimArgs &a, bool adam, cudaStream_t st) {
   SERT_REQUIRE(a.total % 4 == 0, "parameter arena must be padded to 4 floats");
   SERT_REQUIRE(a.num_segments >= 1 && a.num_segments <= kMaxSegments, "bad segment table");
   SERT_REQUIRE(a.phase == 0 || a.phase == 3 || a.phase == 4, "bad update phase");
+  SERT_REQUIRE(a.phase != 4 || a.ticket != nullptr, "phase 4 needs a ticket counter");
+  SERT_REQUIRE(a.transposed == nullptr || a.seg[a.transposed_segment].row_len % 4 == 0,
+               "transposed copy needs rows of 4n floats");
   const long long total4 = a.total / 4;
   const long long blocks = std::max<long long>(1, (total4 - a.first4 + 255) / 256);
   SERT_REQUIRE(blocks < (1ll << 31), "parameter arena too large for one launch");
@@ -141,7 +179,7 @@ static int launch_update(const OptimArgs &a, bool adam, cudaStream_t st) {
     else dense_update_kernel<false, 0><<<g, 256, 0, st>>>(a);
   }
   SERT_LAUNCH_CHECK();
-  if (a.phase != 3) {          // the loss is complete once the last phase of the step has run
+  if (a.phase == 0) {          // the loss is complete once the last phase of the step has run (phase 4 finalises itself)
     finalize_train_kernel<<<1, kSumsqSlots, 0, st>>>(a.acc, a.loss_out, a.inv_B, a.reg_coeff);
     SERT_LAUNCH_CHECK();
   }

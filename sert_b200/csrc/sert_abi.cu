@@ -67,6 +67,11 @@ struct sert_model {
   Dataset ds[2];
   // vector-space workspaces
   float *h = nullptr, *t = nullptr, *da = nullptr, *dh = nullptr, *WpT = nullptr;
+  // hot word rows of the fused tile kernel (kernels.cuh: VsFusedArgs::hot_slot)
+  int8_t *hot_slot = nullptr;
+  int32_t *hot_ids = nullptr;
+  float *hot_acc = nullptr;
+  int n_hot = 0;
   int32_t *neg = nullptr;
   float *dbg_scores = nullptr, *dbg_u = nullptr, *dbg_ell = nullptr;
   // log-linear workspaces
@@ -93,9 +98,10 @@ struct sert_model {
   float *stage_w = nullptr, *stage_data = nullptr;
   size_t stage_nnz_cap = 0;
   // optional per-kernel timing of the dense update (bench.py's roofline leg)
-  bool use_fused = true;              // fused warp-per-instance-pair kernel for the vector-space step when the shape fits
+  int use_fused = 1;                  // vector-space step: 0 = per-stage kernels, 1 = fused (tile kernel, else warp kernel), 2 = fused warp kernel
   // second stream + fork/join events: the two small dense-gradient kernels overlap the table update
   bool overlap = true;
+  bool wpt_valid = false;             // WpT holds the transpose of the current projection matrix
   cudaStream_t st2 = nullptr;
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
   bool profile = false;
@@ -175,6 +181,9 @@ static size_t carve(sert_model &m, void *base) {
     m.da = train ? b.take<float>(B * de) : nullptr;
     m.dh = train ? b.take<float>(B * dw) : nullptr;
     m.WpT = train ? b.take<float>(dw * de) : nullptr;
+    m.hot_slot = train ? b.take<int8_t>(V) : nullptr;
+    m.hot_ids = train ? b.take<int32_t>(kMaxHotRows) : nullptr;
+    m.hot_acc = train ? b.take<float>((long long)kHotReplicas * kMaxHotRows * dw) : nullptr;
     m.neg = b.take<int32_t>(B * k);
     m.dbg_scores = b.take<float>(B * (k + 1));
     m.dbg_u = b.take<float>(B * de);
@@ -295,7 +304,12 @@ static int vs_train_step(sert_model &m, const int32_t *x, const int32_t *y, cons
   f.gR = m.grad + m.off[SERT_PARAM_WORD_REPR]; f.flagR = m.flagR; f.stamp = m.stamp;
   f.h = m.h; f.da = m.da; f.loss_acc = m.acc;
   f.B = B; f.W = c.window; f.k = c.num_negatives; f.dw = dw; f.de = de; f.inv_B = 1.0f / (float)B;
-  const int fused = m.use_fused ? launch_vs_fused(f, m.WpT, st) : 1;
+  if (m.n_hot > 0) {
+    f.hot_slot = m.hot_slot; f.hot_acc = m.hot_acc; f.hot_replicas = kHotReplicas;
+    f.hot_ids = m.hot_ids; f.n_hot = m.n_hot;
+  }
+  const int fused = m.use_fused ? launch_vs_fused(f, m.WpT, !m.wpt_valid, m.use_fused, st) : 1;
+  if (fused == 0) m.wpt_valid = true;
   if (fused < 0) return -1;
   if (fused == 1) {
     // general-shape path: one kernel per stage
@@ -338,8 +352,18 @@ static int vs_train_step(sert_model &m, const int32_t *x, const int32_t *y, cons
     SERT_CUDA(cudaStreamWaitEvent(st, m.ev_join, 0));
     o.phase = 4;
     o.first4 = m.off[SERT_PARAM_DENSE_W] / 4;       // W and b are the last two tensors of the arena
+    o.ticket = reinterpret_cast<unsigned int *>(m.acc + 1 + kSumsqSlots);
+    if (m.wpt_valid && de % 4 == 0) {               // the update keeps the transposed copy current: no transpose launch
+      o.transposed = m.WpT;
+      o.transposed_rows = dw;
+      for (int s = 0; s < m.nseg; ++s)
+        if (m.seg[s].offset == m.off[SERT_PARAM_DENSE_W]) o.transposed_segment = s;
+    } else {
+      m.wpt_valid = false;
+    }
     return launch_adam(o, st);
   }
+  m.wpt_valid = false;
   return timed_update(m, o, true);
 }
 
@@ -645,6 +669,7 @@ int sert_model_set_tensor(sert_model *m, int which, int slot, const float *host,
   SERT_REQUIRE((long long)count == m->cnt[which], "tensor size mismatch");
   SERT_CUDA(cudaMemcpyAsync(tensor_ptr(m, which, slot), host, count * sizeof(float), cudaMemcpyHostToDevice, m->st));
   SERT_CUDA(cudaStreamSynchronize(m->st));
+  if (which == SERT_PARAM_DENSE_W && slot == SERT_STATE_PARAM) m->wpt_valid = false;
   return 0;
 }
 
@@ -672,7 +697,26 @@ int sert_model_get_step(sert_model *m, int64_t *t) {
 
 int sert_model_set_fused(sert_model *m, int enable) {
   SERT_REQUIRE(m, "null model");
-  m->use_fused = enable != 0;
+  SERT_REQUIRE(enable >= 0 && enable <= 2, "fused mode must be 0 (per-stage), 1 (auto) or 2 (warp kernel)");
+  m->use_fused = enable;
+  return 0;
+}
+
+int sert_model_set_hot_words(sert_model *m, const int32_t *ids_host, int32_t n) {
+  SERT_REQUIRE(m && (ids_host || n == 0), "null argument");
+  SERT_REQUIRE(is_vs(m->cfg) && m->cfg.inference_only == 0, "hot word rows apply to a trainable vector-space model");
+  SERT_REQUIRE(n >= 0 && n <= kMaxHotRows, "at most 32 hot word rows");
+  std::vector<int8_t> slot((size_t)m->cfg.vocab, (int8_t)-1);
+  for (int32_t s = 0; s < n; ++s) {
+    SERT_REQUIRE(ids_host[s] >= 0 && ids_host[s] < m->cfg.vocab, "hot word id out of range");
+    SERT_REQUIRE(slot[ids_host[s]] < 0, "duplicate hot word id");
+    slot[ids_host[s]] = (int8_t)s;
+  }
+  SERT_CUDA(cudaStreamSynchronize(m->st));
+  SERT_CUDA(cudaMemcpyAsync(m->hot_slot, slot.data(), slot.size(), cudaMemcpyHostToDevice, m->st));
+  if (n > 0) SERT_CUDA(cudaMemcpyAsync(m->hot_ids, ids_host, (size_t)n * sizeof(int32_t), cudaMemcpyHostToDevice, m->st));
+  SERT_CUDA(cudaStreamSynchronize(m->st));
+  m->n_hot = n;
   return 0;
 }
 

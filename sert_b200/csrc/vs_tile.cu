@@ -1,0 +1,290 @@
+// Vector-space training step, forward + backward, ONE CTA PER TILE OF 8 INSTANCES, d_w = d_e = 128
+// (BASELINE configs[1]; sert/models.py:1044-1098).  Same stages and arithmetic as csrc/vs_warp.cu, re-cut around
+// what the profiles of that kernel and of the earlier versions of this one showed (profiles/ncu_vs_tile_r1*.txt,
+// tools/red_probe.cu):
+//   * warp g owns instance g for the gather, the loss and the two scatters (one 512-byte row per request);
+//   * the two 128 x 128 matrix-vector products are computed for the 8 instances together, split along K: warp w
+//     reads rows 16w..16w+15 of the matrix straight from global memory (coalesced 512-byte requests, each row
+//     fetched once per CTA), multiplies them into 8 x 128 partial products held in registers, and the 8 partials
+//     are summed through shared memory so that warp g ends up with the full row of instance g.  Earlier cuts read
+//     64-byte slices of the matrix per warp, first through L1/L2 (bound by bytes in flight), then from a shared-memory
+//     copy (bound by the 4 shared-memory wavefronts every LDS.128 costs whatever it broadcasts);
+//   * the 1+k entity rows of an instance are prefetched into L2 when its indices arrive and copied to shared
+//     memory with cp.async (LDGSTS) behind the projection, into the space the partial products occupied;
+//   * the 1+k score partials of an instance are reduced with a 16-value transposing butterfly (16 shuffles
+//     instead of 5 per score), after which lane 2j holds score j and the sigmoid / log / clip arithmetic of all
+//     rows runs once, in parallel over the lanes, instead of once per row;
+//   * additions to the gradient rows of very frequent words go to per-CTA-group copies (kernels.cuh: hot_slot).
+// 32 resident warps per SM (vs_warp: 14), all 512 CTAs of a 4096-instance batch resident at once.
+#include <stdlib.h>
+
+#include <algorithm>
+
+#include "kernels.cuh"
+
+namespace sert {
+
+namespace {
+
+constexpr int kT = 8;                 // instances per CTA == warps per CTA
+constexpr int kThreads = kT * 32;
+constexpr int kD = 128;               // word and entity representation size served by this kernel
+constexpr int kD4 = kD / 4;
+constexpr int kLd = kD + 4;           // padded staging rows
+constexpr int kMaxRows = 16;          // 1 + k scores per instance handled by the butterfly
+constexpr int kMaxWindow = 32;
+constexpr int kRowsPerWarp = kD / kT; // matrix rows per warp in the K-split products
+constexpr int kPartFloats = kT * kT * kD;   // 8 warps x 8 instances x 128 partial products (32 KB)
+
+__device__ __forceinline__ float4 f4_zero() { return make_float4(0.f, 0.f, 0.f, 0.f); }
+__device__ __forceinline__ void f4_fma(float4 &acc, float s, const float4 &v) {
+  acc.x = fmaf(s, v.x, acc.x); acc.y = fmaf(s, v.y, acc.y); acc.z = fmaf(s, v.z, acc.z); acc.w = fmaf(s, v.w, acc.w);
+}
+__device__ __forceinline__ void f4_add(float4 &acc, const float4 &v) {
+  acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+}
+__device__ __forceinline__ void cp_async_16(void *smem_dst, const void *gmem_src) {
+  const unsigned int d = (unsigned int)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gmem_src) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+__device__ __forceinline__ void prefetch_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+
+// Row `warp` of  vec (8 x 128, shared, row stride kLd) . M (128 x 128, global, row-major), columns 4*lane..4*lane+3.
+// Every thread of the CTA must call.  `part` (kPartFloats floats of shared memory) is scratch; the barrier at the
+// start also publishes `vec`, the one at the end releases `part` for other uses.
+__device__ __forceinline__ float4 tile_matvec(const float *__restrict__ vec, float *part,
+                                              const float *__restrict__ M, int warp, int lane) {
+  float4 acc[kT];
+#pragma unroll
+  for (int g = 0; g < kT; ++g) acc[g] = f4_zero();
+  const float4 *m = reinterpret_cast<const float4 *>(M) + (size_t)warp * kRowsPerWarp * kD4 + lane;
+  __syncthreads();
+#pragma unroll
+  for (int q = 0; q < kRowsPerWarp; q += 4) {
+    const float4 r0 = __ldg(m + (q + 0) * kD4);
+    const float4 r1 = __ldg(m + (q + 1) * kD4);
+    const float4 r2 = __ldg(m + (q + 2) * kD4);
+    const float4 r3 = __ldg(m + (q + 3) * kD4);
+#pragma unroll
+    for (int g = 0; g < kT; ++g) {
+      const float4 s = *reinterpret_cast<const float4 *>(vec + g * kLd + warp * kRowsPerWarp + q);   // broadcast
+      f4_fma(acc[g], s.x, r0);
+      f4_fma(acc[g], s.y, r1);
+      f4_fma(acc[g], s.z, r2);
+      f4_fma(acc[g], s.w, r3);
+    }
+  }
+#pragma unroll
+  for (int g = 0; g < kT; ++g) reinterpret_cast<float4 *>(part + (size_t)(warp * kT + g) * kD)[lane] = acc[g];
+  __syncthreads();
+  float4 out = f4_zero();
+#pragma unroll
+  for (int w = 0; w < kT; ++w) f4_add(out, reinterpret_cast<const float4 *>(part + (size_t)(w * kT + warp) * kD)[lane]);
+  __syncthreads();
+  return out;
+}
+
+// One step of the transposing butterfly: 2n values per lane -> n values per lane; lanes whose bit `o` is set keep
+// the upper half.  After the steps o = 16, 8, 4, 2 and a plain exchange with o = 1, lanes 2j and 2j+1 hold the
+// warp-wide sum of value j.
+template <int n>
+__device__ __forceinline__ void fold(float (&v)[kMaxRows], int lane, int o) {
+  const bool upper = (lane & o) != 0;
+#pragma unroll
+  for (int i = 0; i < n; ++i) {
+    const float keep = upper ? v[i + n] : v[i];
+    const float send = upper ? v[i] : v[i + n];
+    v[i] = keep + __shfl_xor_sync(0xffffffffu, send, o);
+  }
+}
+
+__global__ void __launch_bounds__(kThreads, 4) vs_tile_kernel(VsFusedArgs a, const float *__restrict__ WpT) {
+  extern __shared__ __align__(16) float scratch[];      // partial products, then [kT][K1][kD] entity rows of the tile
+  __shared__ __align__(16) float hbuf[kT * kLd];        // h, later da
+  __shared__ int xs[kT * kMaxWindow];
+  __shared__ double s_loss[kT];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int W = a.W, K1 = a.k + 1;
+  const int i = blockIdx.x * kT + warp;  // warp == instance, everywhere but inside tile_matvec
+  const bool ok = i < a.B;
+  const float4 *R4 = reinterpret_cast<const float4 *>(a.R);
+  const float4 *E4 = reinterpret_cast<const float4 *>(a.Eemb);
+  float *my_ent = scratch + (size_t)warp * K1 * kD;
+
+  // ---- A: the instance's indices, touched stamps, entity rows on their way into L2 -------------------------
+  int xi = 0, ri = 0, xdst = 0;          // xdst: row id, or -1 - slot for a hot row (kernels.cuh: hot_slot)
+  if (ok && lane < W) {
+    xi = __ldg(a.x + (size_t)i * W + lane);
+    const int slot = a.hot_slot != nullptr ? (int)__ldg(a.hot_slot + xi) : -1;
+    xdst = slot < 0 ? xi : -1 - slot;
+    if (slot < 0) a.flagR[xi] = a.stamp;   // hot rows are stamped once, by launch_hot_flush
+  }
+  if (ok && lane < K1) {
+    ri = lane == 0 ? __ldg(a.y + i) : __ldg(a.neg + (size_t)i * a.k + lane - 1);
+    a.flagE[ri] = a.stamp;
+  }
+  xs[warp * kMaxWindow + lane] = xdst;   // read back by this warp only
+  for (int j = 0; j < K1; ++j) {
+    const int r = __shfl_sync(0xffffffffu, ri, j);
+    if (lane < 4) prefetch_l2(E4 + (size_t)r * kD4 + lane * 8);      // 4 lines of 128 B per row
+  }
+
+  // ---- B: gather + window mean (sert/models.py:180,226,1051) ------------------------------------------------
+  float4 h = f4_zero();
+#pragma unroll 5
+  for (int w = 0; w < W; ++w) {
+    const int r = __shfl_sync(0xffffffffu, xi, w);
+    f4_add(h, __ldg(R4 + (size_t)r * kD4 + lane));
+  }
+  const float den = (float)W;
+  h.x = __fdiv_rn(h.x, den); h.y = __fdiv_rn(h.y, den); h.z = __fdiv_rn(h.z, den); h.w = __fdiv_rn(h.w, den);
+  reinterpret_cast<float4 *>(hbuf + warp * kLd)[lane] = h;
+  if (ok) reinterpret_cast<float4 *>(a.h)[(size_t)i * kD4 + lane] = h;
+
+  // ---- C: t = tanh(h . Wp + bp) (sert/models.py:1055-1061) --------------------------------------------------
+  float4 t = tile_matvec(hbuf, scratch, a.Wp, warp, lane);
+  {
+    const float4 b = __ldg(reinterpret_cast<const float4 *>(a.bp) + lane);
+    t.x = tanhf(t.x + b.x); t.y = tanhf(t.y + b.y); t.z = tanhf(t.z + b.z); t.w = tanhf(t.w + b.w);
+  }
+  // the partial products are dead (barrier at the end of tile_matvec): this warp's entity rows take their place
+  for (int j = 0; j < K1; ++j) {
+    const int r = __shfl_sync(0xffffffffu, ri, j);
+    cp_async_16(my_ent + j * kD + lane * 4, E4 + (size_t)r * kD4 + lane);
+  }
+  cp_async_wait_all();
+  __syncwarp();
+
+  // ---- D: negative-sampling loss of the instance, forward and backward (sert/models.py:893-902,1072-1098) ----
+  float ell_lane = 0.f;
+  float wi = 1.0f;
+  {
+    float4 u;
+    u.x = clipf_(t.x, SERT_TANH_LO, SERT_TANH_HI); u.y = clipf_(t.y, SERT_TANH_LO, SERT_TANH_HI);
+    u.z = clipf_(t.z, SERT_TANH_LO, SERT_TANH_HI); u.w = clipf_(t.w, SERT_TANH_LO, SERT_TANH_HI);
+    float part[kMaxRows];
+#pragma unroll
+    for (int j = 0; j < kMaxRows; ++j) {
+      part[j] = 0.f;
+      if (j < K1) {
+        const float4 e = reinterpret_cast<const float4 *>(my_ent + j * kD)[lane];
+        part[j] = e.x * u.x + e.y * u.y + e.z * u.z + e.w * u.w;
+      }
+    }
+    fold<8>(part, lane, 16);
+    fold<4>(part, lane, 8);
+    fold<2>(part, lane, 4);
+    fold<1>(part, lane, 2);
+    const float score = part[0] + __shfl_xor_sync(0xffffffffu, part[0], 1);
+    const int j = lane >> 1;            // lanes 2j, 2j+1 hold score j
+    if (ok && a.w != nullptr) wi = __ldg(a.w + i);
+    const float coef_scale = ok ? wi * a.inv_B : 0.f;
+    float coef = 0.f;
+    if (j < K1) {
+      const float sg = sigmoidf_(score);
+      const float cl = clipf_(sg, SERT_CLIP_LO, SERT_CLIP_HI);
+      const bool inside = (sg >= SERT_CLIP_LO) && (sg <= SERT_CLIP_HI);
+      const float q = j == 0 ? cl : 1.0f - cl;          // probability the loss takes the log of
+      const float ellj = -logf(q);
+      const float mag = (coef_scale / q) * sg * (1.0f - sg);
+      coef = inside ? (j == 0 ? -mag : mag) : 0.0f;
+      if ((lane & 1) == 0) ell_lane = ellj;
+    }
+    float4 du = f4_zero();
+    for (int jj = 0; jj < K1; ++jj) {
+      const float c = __shfl_sync(0xffffffffu, coef, 2 * jj);
+      const int r = __shfl_sync(0xffffffffu, ri, jj);
+      const float4 e = reinterpret_cast<const float4 *>(my_ent + jj * kD)[lane];
+      f4_fma(du, c, e);
+      if (ok) red_add_f4(a.gE + ((size_t)r * kD4 + lane) * 4, make_float4(c * u.x, c * u.y, c * u.z, c * u.w));
+    }
+    float4 da;
+    da.x = (t.x >= SERT_TANH_LO && t.x <= SERT_TANH_HI) ? du.x * (1.0f - t.x * t.x) : 0.f;
+    da.y = (t.y >= SERT_TANH_LO && t.y <= SERT_TANH_HI) ? du.y * (1.0f - t.y * t.y) : 0.f;
+    da.z = (t.z >= SERT_TANH_LO && t.z <= SERT_TANH_HI) ? du.z * (1.0f - t.z * t.z) : 0.f;
+    da.w = (t.w >= SERT_TANH_LO && t.w <= SERT_TANH_HI) ? du.w * (1.0f - t.w * t.w) : 0.f;
+    reinterpret_cast<float4 *>(hbuf + warp * kLd)[lane] = da;     // h is dead since the barriers of C
+    if (ok) reinterpret_cast<float4 *>(a.da)[(size_t)i * kD4 + lane] = da;
+  }
+
+  // ---- E: dh = da . Wp^T, scatter-add of dh / W into the word-gradient rows (the entity rows are dead behind the
+  //         first barrier of tile_matvec) ------------------------------------------------------------------------
+  {
+    float4 dh = tile_matvec(hbuf, scratch, WpT, warp, lane);
+    dh.x = __fdiv_rn(dh.x, den); dh.y = __fdiv_rn(dh.y, den); dh.z = __fdiv_rn(dh.z, den); dh.w = __fdiv_rn(dh.w, den);
+    if (ok) {
+      float *dst = a.gR + lane * 4;
+      float *hot = a.hot_slot == nullptr
+                       ? nullptr
+                       : a.hot_acc + (size_t)(blockIdx.x & (a.hot_replicas - 1)) * kMaxHotRows * kD + lane * 4;
+      for (int w = 0; w < W; ++w) {
+        const int r = xs[warp * kMaxWindow + w];
+        red_add_f4(r >= 0 ? dst + (size_t)r * kD : hot + (size_t)(-1 - r) * kD, dh);
+      }
+    }
+  }
+
+  // ---- tile loss: sum_i w_i * ell_i ------------------------------------------------------------------------
+  const float ell = warp_sum(ell_lane);
+  if (lane == 0) s_loss[warp] = ok ? (double)(wi * ell) : 0.0;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double tot = 0.0;
+#pragma unroll
+    for (int wv = 0; wv < kT; ++wv) tot += s_loss[wv];
+    if (tot != 0.0) atomicAdd(a.loss_acc, tot);
+  }
+}
+
+// gR[hot_ids[s]] += sum over the replicas of hot_acc[.][s]; the replicas are zeroed for the next step.
+// One CTA per hot row, one float4 column per thread; all replica loads are issued before the first store.
+__global__ void __launch_bounds__(kD4) hot_flush_kernel(float *__restrict__ hot_acc, const int32_t *__restrict__ hot_ids,
+                                                        float *__restrict__ gR, uint32_t *__restrict__ flagR,
+                                                        uint32_t stamp) {
+  const int s = blockIdx.x, c = threadIdx.x;
+  const int row = __ldg(hot_ids + s);
+  float4 v[kHotReplicas];
+#pragma unroll
+  for (int r = 0; r < kHotReplicas; ++r)
+    v[r] = __ldcg(reinterpret_cast<const float4 *>(hot_acc + ((size_t)r * kMaxHotRows + s) * kD) + c);
+  float4 *g = reinterpret_cast<float4 *>(gR + (size_t)row * kD) + c;
+  float4 o = __ldcg(g);
+#pragma unroll
+  for (int r = 0; r < kHotReplicas; ++r) f4_add(o, v[r]);
+  *g = o;
+#pragma unroll
+  for (int r = 0; r < kHotReplicas; ++r)
+    reinterpret_cast<float4 *>(hot_acc + ((size_t)r * kMaxHotRows + s) * kD)[c] = f4_zero();
+  if (c == 0) flagR[row] = stamp;
+}
+
+}  // namespace
+
+int launch_hot_flush(float *hot_acc, int replicas, const int32_t *hot_ids, int n_hot, int d, float *gR,
+                     uint32_t *flagR, uint32_t stamp, cudaStream_t st) {
+  if (n_hot <= 0) return 0;
+  SERT_REQUIRE(replicas == kHotReplicas && d == kD, "hot-row flush is built for 16 copies of 128-float rows");
+  hot_flush_kernel<<<n_hot, kD4, 0, st>>>(hot_acc, hot_ids, gR, flagR, stamp);
+  SERT_LAUNCH_CHECK();
+  return 0;
+}
+
+// returns 0 = launched, 1 = shape not served by this kernel
+int launch_vs_tile(const VsFusedArgs &a, const float *WpT, cudaStream_t st) {
+  if (a.dw != kD || a.de != kD || a.W > kMaxWindow || a.k + 1 > kMaxRows) return 1;
+  const size_t smem = std::max((size_t)kT * (a.k + 1) * kD, (size_t)kPartFloats) * sizeof(float);
+  static bool attr_set = false;
+  if (!attr_set) {
+    SERT_CUDA(cudaFuncSetAttribute(vs_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                   (int)(kT * kMaxRows * kD * sizeof(float))));
+    attr_set = true;
+  }
+  vs_tile_kernel<<<cdiv(a.B, kT), kThreads, smem, st>>>(a, WpT);
+  SERT_LAUNCH_CHECK();
+  if (a.hot_slot != nullptr)
+    return launch_hot_flush(a.hot_acc, a.hot_replicas, a.hot_ids, a.n_hot, kD, a.gR, a.flagR, a.stamp, st);
+  return 0;
+}
+
+}  // namespace sert

@@ -259,7 +259,8 @@ __global__ void __launch_bounds__(kThreads, kInst == 1 ? 4 : 3) vs_warp_kernel(V
   }
 }
 
-// WpT (de, dw) <- Wp (dw, de): 64 KB at d = 128, refreshed every step (Wp changes with every update)
+// WpT (de, dw) <- Wp (dw, de): 64 KB at d = 128.  Only launched when the copy is stale (first step, parameters set
+// from the host): in steady state the dense update of the previous step writes it (opt_kernels.cu, phase 4).
 __global__ void transpose_small_kernel(const float *__restrict__ src, float *__restrict__ dst, int rows, int cols) {
   __shared__ float tile[32][33];
   const int r0 = blockIdx.y * 32, c0 = blockIdx.x * 32;
@@ -298,11 +299,18 @@ int launch_t(const VsFusedArgs &a, const float *WpT, cudaStream_t st) {
 }  // namespace
 
 // returns 0 = launched, 1 = shape not supported (caller uses the per-stage kernels), -1 = error
-int launch_vs_fused(const VsFusedArgs &a, float *WpT_scratch, cudaStream_t st) {
+// variant: 1 = tile kernel (csrc/vs_tile.cu) where the shape fits, else the warp kernel; 2 = warp kernel only
+int launch_vs_fused(const VsFusedArgs &a, float *WpT_scratch, bool refresh_WpT, int variant, cudaStream_t st) {
   if (a.B == 0) return 0;
   if (a.dw % 4 != 0 || a.de % 4 != 0 || a.dw > 384 || a.de > 384 || WpT_scratch == nullptr) return 1;
-  transpose_small_kernel<<<dim3(cdiv(a.de, 32), cdiv(a.dw, 32)), dim3(32, 8), 0, st>>>(a.Wp, WpT_scratch, a.dw, a.de);
-  SERT_LAUNCH_CHECK();
+  if (refresh_WpT) {
+    transpose_small_kernel<<<dim3(cdiv(a.de, 32), cdiv(a.dw, 32)), dim3(32, 8), 0, st>>>(a.Wp, WpT_scratch, a.dw, a.de);
+    SERT_LAUNCH_CHECK();
+  }
+  if (variant != 2) {
+    const int rc = launch_vs_tile(a, WpT_scratch, st);
+    if (rc <= 0) return rc;
+  }
   const int cw = (a.dw / 4 + 31) / 32, ce = (a.de / 4 + 31) / 32;
 #define SERT_WARP_CASE(CWv, CEv) \
   if (cw == CWv && ce == CEv) return launch_t<CWv, CEv>(a, WpT_scratch, st);

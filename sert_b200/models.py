@@ -662,7 +662,27 @@ class VectorSpaceLanguageModel(VectorSpaceLanguageModelBase):
         self._native.set_tensor(N.PARAM_DENSE_W, dense_init[0])
         self._native.set_tensor(N.PARAM_DENSE_B, dense_init[1])
         self._attach_datasets()
+        self.set_hot_words(self.pick_hot_words())
         self._create_functions()
+
+    HOT_WORD_MIN_PER_BATCH = 64     # expected occurrences per batch from which a word row counts as hot
+    MAX_HOT_WORDS = 32              # kMaxHotRows (csrc/kernels.cuh)
+
+    def pick_hot_words(self):
+        """Word ids whose gradient row receives so many additions per batch that they serialise in L2
+        (include/sert_b200.h: sert_model_set_hot_words), from the training set's word counts."""
+        x = self.training_set[0]
+        if x.size == 0:
+            return np.zeros(0, np.int32)
+        counts = np.bincount(np.asarray(x).ravel(), minlength=self.vocabulary_size)
+        per_batch = counts * (float(self.batch_size) / x.shape[0])
+        order = np.argsort(-per_batch, kind='stable')[:self.MAX_HOT_WORDS]
+        return order[per_batch[order] >= self.HOT_WORD_MIN_PER_BATCH].astype(np.int32)
+
+    def set_hot_words(self, ids):
+        ids = np.ascontiguousarray(ids, dtype=np.int32)
+        N.check(self._native.lib.sert_model_set_hot_words(self._native.handle, N.host_ptr(ids), int(ids.size)))
+        self.hot_words = ids
 
     def get_dense(self):
         return (self._native.get_tensor(N.PARAM_DENSE_W, (self.representation_size, self.entity_representation_size)),

@@ -50,17 +50,21 @@ def test_forward_logits_match_oracle(dims):
         H.close(ell, f['ell'], what='instance loss')
 
 
-@pytest.mark.parametrize('fused,overlap', [(1, 1), (1, 0), (0, 1), (0, 0)])
+@pytest.mark.parametrize('fused,overlap', [(1, 1), (1, 0), (2, 1), (0, 1), (0, 0)])
 @pytest.mark.parametrize('gain,weights,dims', [
     (1.0, False, dict(dw=64, de=48, W=5, B=128, k=6)),
-    (1.0, True, dict(dw=128, de=128, W=10, B=160, k=10)),        # BASELINE configs[1] dims, ragged last tile
+    (1.0, True, dict(dw=128, de=128, W=10, B=163, k=10)),        # BASELINE configs[1] dims, ragged last tile
+    (30.0, True, dict(dw=128, de=128, W=7, B=72, k=15)),         # tile kernel into the clips, 16 scores per instance
+    (1.0, False, dict(dw=128, de=128, W=32, B=40, k=1)),         # tile kernel, widest window / fewest negatives
+    (1.0, True, dict(dw=128, de=128, W=3, B=64, k=16)),          # 17 scores: falls back to the warp kernel
     (40.0, True, dict(dw=64, de=48, W=5, B=128, k=6)),
     (1.0, True, dict(dw=300, de=128, W=4, B=64, k=10)),          # product-search dims (unfused path)
     (3.0, True, dict(dw=32, de=32, W=40, B=96, k=3)),            # window > 32
 ])
 def test_training_steps_match_oracle(gain, weights, dims, fused, overlap):
-    """5 Adam steps + eval losses through the fused tile kernel and the per-stage kernels; gain=40 drives
-    tanh / sigmoid into the 1e-7 clips."""
+    """5 Adam steps + eval losses through the fused kernels (fused=1: tile kernel where d_w = d_e = 128, else the warp
+    kernel; fused=2: warp kernel) and the per-stage kernels (fused=0); gain >= 30 drives tanh / sigmoid into the
+    1e-7 clips."""
     from sert_b200 import _native as N
     p = H.vs_problem(5, V=800, E=300, n_batches=5, gain=gain, weights=weights, **dims)
     lam = 0.01
@@ -90,6 +94,30 @@ def test_training_steps_match_oracle(gain, weights, dims, fused, overlap):
     H.close(v, oracle.state['R'][1], rtol=2e-4, atol_scale=1e-4, what='Adam v (R)')
     H.close(model.test_fn(2, p['neg'][2]), oracle.eval_batch('train', 2, p['neg'][2]), rtol=2e-4,
             what='eval loss after training')
+
+
+@pytest.mark.parametrize('hot', ['auto', 'none', 'forced'])
+def test_hot_word_rows_are_result_neutral(hot):
+    """The tile kernel spreads the gradient additions of very frequent word ids over private copies
+    (sert_model_set_hot_words); whatever the hot set, the step must match the oracle."""
+    p = H.vs_problem(17, V=300, E=200, dw=128, de=128, W=10, B=200, k=10, n_batches=4, weights=True)
+    model = make_model(p, 0.01)
+    if hot == 'auto':
+        assert 1 <= model.hot_words.size <= 32          # V=300 Zipf: the top words exceed 64 occurrences per batch
+    elif hot == 'none':
+        model.set_hot_words([])
+    else:
+        model.set_hot_words(np.r_[np.arange(0, 300, 10), 7][:32])   # 31 ids, frequent and rare ones
+    oracle = H.vs_oracle(p, 0.01)
+    for j, b in enumerate([2, 0, 3, 1]):
+        H.close(model.train_fn(b, p['neg'][j]), oracle.train_batch(b, p['neg'][j]), what='train loss step %d' % j)
+    R, Eemb = model.get_representations()
+    H.close(R, oracle.R, rtol=2e-4, what='R')
+    H.close(Eemb, oracle.Eemb, rtol=2e-4, what='Eemb')
+    with pytest.raises(RuntimeError, match='duplicate hot word'):
+        model.set_hot_words([3, 3])
+    with pytest.raises(RuntimeError, match='out of range'):
+        model.set_hot_words([300])
 
 
 def test_epoch_api_and_host_batches():
