@@ -67,18 +67,21 @@ struct VsFusedArgs {
   // thousands of row additions land on the same four L2 lines, which the L2 slices serialise (tools/red_probe.cu:
   // 44 MB of row additions take 14-20 us on uniform rows and 39-44 us on Zipf rows; plain stores behave the same).
   // Additions to a hot row go to one of `hot_replicas` private copies instead (chosen by CTA), and
-  // launch_hot_flush folds the copies into the gradient row afterwards.
+  // launch_hot_update applies their sum (the dense update skips rows flagged kHotRowMark).
   const int8_t *hot_slot = nullptr;   // (V,) slot of a hot word id, -1 otherwise
   float *hot_acc = nullptr;           // (hot_replicas, kMaxHotRows, dw) zero between steps
   int hot_replicas = 0;               // power of two
-  const int32_t *hot_ids = nullptr;   // (n_hot,) word id of each slot
-  int n_hot = 0;
+  // Loss of the PREVIOUS step, finalised by one extra CTA of the tile kernel (its accumulators are complete by
+  // then and nothing else on the step's critical path needs them): nullptr = nothing pending.
+  double *fin_acc = nullptr;
+  float *fin_loss = nullptr;
+  float fin_inv_B = 0.f, fin_reg_coeff = 0.f;
 };
 constexpr int kMaxHotRows = 32;
 constexpr int kHotReplicas = 16;
-// gR[hot_ids[s]] += sum_r hot_acc[r][s]; hot_acc <- 0; flagR[hot_ids[s]] = stamp       (n_hot CTAs)
-int launch_hot_flush(float *hot_acc, int replicas, const int32_t *hot_ids, int n_hot, int d, float *gR,
-                     uint32_t *flagR, uint32_t stamp, cudaStream_t st);
+constexpr uint32_t kHotRowMark = 0xffffffffu;   // flag value of a hot row: the dense update leaves the row alone
+// true when launch_vs_tile serves this shape
+bool vs_tile_supported(int dw, int de, int W, int k);
 // WpT_scratch: (de, dw) floats, the transpose of Wp; refresh_WpT = recompute it first (it is stale).
 // variant: 1 = CTA-per-8-instances tile kernel (csrc/vs_tile.cu) when d_w = d_e = 128, window <= 32, k <= 15, else the
 // warp kernel; 2 = warp kernel only.
@@ -120,12 +123,31 @@ struct OptimArgs {
   float inv_B, reg_coeff;
   int phase = 0;                   // 0 = everything, 3 = row-stamped tables only, 4 = dense tensors only
   long long first4 = 0;            // first 16-byte chunk to process (phase 4 starts at the first dense tensor)
-  unsigned int *ticket = nullptr;  // phase 4: block counter (zero between launches); the last block finalises the loss
+  unsigned int *ticket = nullptr;  // phase 4: block counter (zero between launches); the last block finalises the
+                                   // loss.  nullptr: the caller finalises later (launch_finalize_train / the next
+                                   // step's tile kernel)
   // phase 4, optional: segment `transposed_segment` ((rows, row_len) row-major) is also written transposed here
   float *transposed = nullptr;
   int transposed_segment = 0, transposed_rows = 0;
 };
 
+// Adam + L2 of the hot word rows (gradient = sum of the private copies), see opt_kernels.cu
+struct HotUpdateArgs {
+  float *theta, *s1, *s2, *grad;   // arena arrays
+  long long table_offset;          // float offset of the word table inside them
+  int d;                           // floats per row
+  float *hot_acc;                  // (kHotReplicas, kMaxHotRows, d)
+  const int32_t *hot_ids;
+  int n_hot;
+  float l2_scale, c0, c1, c2, c3;
+  double *acc;                     // sum(theta^2) goes to acc[1 + slot]
+  int counted;                     // 1: this rank reports the table's norm in the loss
+};
+int launch_hot_update(const HotUpdateArgs &h, cudaStream_t st);
+// flags[hot_ids[s]] = value  (kHotRowMark to hand the rows to launch_hot_update, 0 to hand them back)
+int launch_hot_mark(uint32_t *flags, const int32_t *hot_ids, int n_hot, uint32_t value, cudaStream_t st);
+// train loss finalisation as a kernel of its own: loss_out = acc[0]*inv_B + reg_coeff*sum(acc[1..64]); acc <- 0
+int launch_finalize_train(double *acc, float *loss_out, float inv_B, float reg_coeff, cudaStream_t st);
 int launch_adam(const OptimArgs &a, cudaStream_t st);
 int launch_adadelta(const OptimArgs &a, cudaStream_t st);
 // eval loss finalisation: loss_out = acc[0]*inv_B ; acc[0] = 0

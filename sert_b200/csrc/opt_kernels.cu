@@ -24,6 +24,26 @@ __device__ __forceinline__ float fast_sqrt(float x) {
   return r;
 }
 
+// One element of lasagne.updates.adam / adadelta (Lasagne 0.1 forms); gj already holds the L2 term.
+template <bool ADAM>
+__device__ __forceinline__ void update_element(float &p, float &s1, float &s2, float gj, float c0, float c1, float c2,
+                                               float c3) {
+  if (ADAM) {
+    // m <- b1 m + (1-b1) g ; v <- b2 v + (1-b2) g^2 ; theta <- theta - a_t m / (sqrt(v) + eps)
+    const float m = c1 * s1 + (1.0f - c1) * gj;
+    const float v = c2 * s2 + (1.0f - c2) * gj * gj;
+    p = p - __fdividef(c0 * m, fast_sqrt(v) + c3);
+    s1 = m; s2 = v;
+  } else {
+    // accu <- rho accu + (1-rho) g^2 ; upd = g sqrt(delta+eps)/sqrt(accu+eps) ;
+    // theta <- theta - lr upd ; delta <- rho delta + (1-rho) upd^2
+    const float accu = c1 * s1 + (1.0f - c1) * gj * gj;
+    const float upd = __fdividef(gj * fast_sqrt(s2 + c3), fast_sqrt(accu + c3));
+    p = p - c0 * upd;
+    s1 = accu; s2 = c1 * s2 + (1.0f - c1) * upd * upd;
+  }
+}
+
 // One 16-byte chunk of each stream per thread, one-shot grid (no grid-stride loop): measured on B200
 // (tools/bw_probe.cu) the in-place 3-stream read-modify-write reaches 6.50 TB/s this way vs 5.3-6.2 TB/s
 // for persistent grid-stride variants -- the block scheduler interleaves the load and store phases of
@@ -38,8 +58,6 @@ __global__ void __launch_bounds__(256) dense_update_kernel(OptimArgs a) {
   float4 *__restrict__ s14 = reinterpret_cast<float4 *>(a.s1);
   float4 *__restrict__ s24 = reinterpret_cast<float4 *>(a.s2);
   float4 *__restrict__ g4 = reinterpret_cast<float4 *>(a.grad);
-  const float one_m_c1 = 1.0f - a.c1;
-  const float one_m_c2 = 1.0f - a.c2;
   float sumsq = 0.f;
 
   const long long i4 = a.first4 + (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -50,13 +68,15 @@ __global__ void __launch_bounds__(256) dense_update_kernel(OptimArgs a) {
     for (int q = 1; q < kMaxSegments; ++q) s += (q < a.num_segments && e >= a.seg[q].offset) ? 1 : 0;
     const ParamSegment &sg = a.seg[s];
     const bool live = (e - sg.offset) < sg.count;   // false only inside inter-segment padding
-    bool touched = true;
+    bool touched = true, skip = false;
     if (live && sg.flags != nullptr) {
       const unsigned int row = (unsigned int)(e - sg.offset) / (unsigned int)sg.row_len;
-      touched = (__ldg(sg.flags + row) == a.stamp);
+      const uint32_t flag = __ldg(sg.flags + row);
+      touched = (flag == a.stamp);
+      skip = (flag == kHotRowMark);       // updated by hot_update_kernel on the side stream
     }
     const bool mine = PHASE == 0 ? true : PHASE == 3 ? (sg.flags != nullptr) : (sg.flags == nullptr);
-    if (live && mine) {
+    if (live && mine && !skip) {
       const float4 p = th4[i4];
       const float4 x1 = s14[i4];
       const float4 x2 = s24[i4];
@@ -70,21 +90,7 @@ __global__ void __launch_bounds__(256) dense_update_kernel(OptimArgs a) {
       const float gv[4] = {g.x, g.y, g.z, g.w};
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
-        const float gj = gv[j] + l2 * pv[j];
-        if (ADAM) {
-          // m <- b1 m + (1-b1) g ; v <- b2 v + (1-b2) g^2 ; theta <- theta - a_t m / (sqrt(v) + eps)
-          const float m = a.c1 * v1[j] + one_m_c1 * gj;
-          const float v = a.c2 * v2[j] + one_m_c2 * gj * gj;
-          pv[j] = pv[j] - __fdividef(a.c0 * m, fast_sqrt(v) + a.c3);
-          v1[j] = m; v2[j] = v;
-        } else {
-          // accu <- rho accu + (1-rho) g^2 ; upd = g sqrt(delta+eps)/sqrt(accu+eps) ;
-          // theta <- theta - lr upd ; delta <- rho delta + (1-rho) upd^2
-          const float accu = a.c1 * v1[j] + one_m_c1 * gj * gj;
-          const float upd = __fdividef(gj * fast_sqrt(v2[j] + a.c3), fast_sqrt(accu + a.c3));
-          pv[j] = pv[j] - a.c0 * upd;
-          v1[j] = accu; v2[j] = a.c1 * v2[j] + one_m_c1 * upd * upd;
-        }
+        update_element<ADAM>(pv[j], v1[j], v2[j], gv[j] + l2 * pv[j], a.c0, a.c1, a.c2, a.c3);
       }
       th4[i4] = make_float4(pv[0], pv[1], pv[2], pv[3]);
       if (PHASE == 4 && a.transposed != nullptr && s == a.transposed_segment) {
@@ -114,7 +120,7 @@ __global__ void __launch_bounds__(256) dense_update_kernel(OptimArgs a) {
     for (int w = 0; w < (int)(blockDim.x >> 5); ++w) tot += s_part[w];
     if (tot != 0.0) atomicAdd(a.acc + 1 + (blockIdx.x & (kSumsqSlots - 1)), tot);
   }
-  if (PHASE == 4) {
+  if (PHASE == 4 && a.ticket != nullptr) {
     // The dense tensors are a handful of blocks: the last one to finish writes the step's loss (what
     // finalize_train_kernel does behind the other phases) -- one launch less on the step's critical path.
     __shared__ bool s_last;
@@ -162,7 +168,6 @@ static int launch_update(const OptimArgs &a, bool adam, cudaStream_t st) {
   SERT_REQUIRE(a.total % 4 == 0, "parameter arena must be padded to 4 floats");
   SERT_REQUIRE(a.num_segments >= 1 && a.num_segments <= kMaxSegments, "bad segment table");
   SERT_REQUIRE(a.phase == 0 || a.phase == 3 || a.phase == 4, "bad update phase");
-  SERT_REQUIRE(a.phase != 4 || a.ticket != nullptr, "phase 4 needs a ticket counter");
   SERT_REQUIRE(a.transposed == nullptr || a.seg[a.transposed_segment].row_len % 4 == 0,
                "transposed copy needs rows of 4n floats");
   const long long total4 = a.total / 4;
@@ -183,6 +188,79 @@ static int launch_update(const OptimArgs &a, bool adam, cudaStream_t st) {
     finalize_train_kernel<<<1, kSumsqSlots, 0, st>>>(a.acc, a.loss_out, a.inv_B, a.reg_coeff);
     SERT_LAUNCH_CHECK();
   }
+  return 0;
+}
+
+// Adam + L2 for the hot word rows of the fused tile kernel (kernels.cuh: VsFusedArgs::hot_slot): the gradient of hot
+// row s is the sum of its kHotReplicas private copies (plus whatever sits in the gradient row itself); the copies
+// are zeroed for the next step.  One CTA per hot row, one 16-byte chunk per thread, off the step's critical path.
+__global__ void __launch_bounds__(128) hot_update_kernel(HotUpdateArgs h) {
+  const int s = blockIdx.x;
+  const int row = __ldg(h.hot_ids + s);
+  float sumsq = 0.f;
+  for (int c = threadIdx.x; c < h.d / 4; c += blockDim.x) {
+    float4 v[kHotReplicas];
+#pragma unroll
+    for (int r = 0; r < kHotReplicas; ++r)
+      v[r] = __ldcg(reinterpret_cast<const float4 *>(h.hot_acc + ((size_t)r * kMaxHotRows + s) * h.d) + c);
+    const size_t i4 = ((size_t)h.table_offset + (size_t)row * h.d) / 4 + c;
+    float4 g = __ldcg(reinterpret_cast<const float4 *>(h.grad) + i4);
+#pragma unroll
+    for (int r = 0; r < kHotReplicas; ++r) { g.x += v[r].x; g.y += v[r].y; g.z += v[r].z; g.w += v[r].w; }
+    const float4 p = reinterpret_cast<float4 *>(h.theta)[i4];
+    const float4 x1 = reinterpret_cast<float4 *>(h.s1)[i4];
+    const float4 x2 = reinterpret_cast<float4 *>(h.s2)[i4];
+    sumsq += p.x * p.x + p.y * p.y + p.z * p.z + p.w * p.w;
+    float pv[4] = {p.x, p.y, p.z, p.w};
+    float v1[4] = {x1.x, x1.y, x1.z, x1.w};
+    float v2[4] = {x2.x, x2.y, x2.z, x2.w};
+    const float gv[4] = {g.x, g.y, g.z, g.w};
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+      update_element<true>(pv[j], v1[j], v2[j], gv[j] + h.l2_scale * pv[j], h.c0, h.c1, h.c2, h.c3);
+    reinterpret_cast<float4 *>(h.theta)[i4] = make_float4(pv[0], pv[1], pv[2], pv[3]);
+    reinterpret_cast<float4 *>(h.s1)[i4] = make_float4(v1[0], v1[1], v1[2], v1[3]);
+    reinterpret_cast<float4 *>(h.s2)[i4] = make_float4(v2[0], v2[1], v2[2], v2[3]);
+    reinterpret_cast<float4 *>(h.grad)[i4] = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int r = 0; r < kHotReplicas; ++r)
+      reinterpret_cast<float4 *>(h.hot_acc + ((size_t)r * kMaxHotRows + s) * h.d)[c] = make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+  __shared__ double s_part[4];
+  double d = warp_sum_d(h.counted ? (double)sumsq : 0.0);
+  if ((threadIdx.x & 31) == 0) s_part[threadIdx.x >> 5] = d;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double tot = 0.0;
+    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) tot += s_part[w];
+    if (tot != 0.0) atomicAdd(h.acc + 1 + (s & (kSumsqSlots - 1)), tot);
+  }
+}
+
+int launch_hot_update(const HotUpdateArgs &h, cudaStream_t st) {
+  if (h.n_hot <= 0) return 0;
+  SERT_REQUIRE(h.d % 4 == 0 && h.table_offset % 4 == 0, "hot rows must be 16-byte aligned");
+  const int threads = std::min(128, std::max(32, (h.d / 4 + 31) / 32 * 32));
+  hot_update_kernel<<<h.n_hot, threads, 0, st>>>(h);
+  SERT_LAUNCH_CHECK();
+  return 0;
+}
+
+__global__ void hot_mark_kernel(uint32_t *flags, const int32_t *ids, int n, uint32_t value) {
+  const int s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s < n) flags[ids[s]] = value;
+}
+
+int launch_hot_mark(uint32_t *flags, const int32_t *hot_ids, int n_hot, uint32_t value, cudaStream_t st) {
+  if (n_hot <= 0) return 0;
+  hot_mark_kernel<<<1, 64, 0, st>>>(flags, hot_ids, n_hot, value);
+  SERT_LAUNCH_CHECK();
+  return 0;
+}
+
+int launch_finalize_train(double *acc, float *loss_out, float inv_B, float reg_coeff, cudaStream_t st) {
+  finalize_train_kernel<<<1, kSumsqSlots, 0, st>>>(acc, loss_out, inv_B, reg_coeff);
+  SERT_LAUNCH_CHECK();
   return 0;
 }
 

@@ -102,6 +102,10 @@ struct sert_model {
   // second stream + fork/join events: the two small dense-gradient kernels overlap the table update
   bool overlap = true;
   bool wpt_valid = false;             // WpT holds the transpose of the current projection matrix
+  // lazy vector-space steps (vs_train_step): accumulator bank and loss slot of the step whose loss is not written yet
+  int pending_bank = -1;
+  float *pending_loss = nullptr;
+  bool hot_marked = false;            // flagR of the hot word rows carries kHotRowMark
   cudaStream_t st2 = nullptr;
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
   bool profile = false;
@@ -111,6 +115,10 @@ struct sert_model {
 namespace sert {
 
 static bool is_vs(const sert_config &c) { return c.kind == SERT_KIND_VECTORSPACE; }
+// loss accumulators: two banks of (data-loss sum, kSumsqSlots partial sums of theta^2), 8 spare doubles (ticket)
+constexpr int kAccBank = 1 + kSumsqSlots + 7;
+constexpr int kAccDoubles = 2 * kAccBank + 8;
+static double *acc_bank(sert_model &m, int bank) { return m.acc + (size_t)bank * kAccBank; }
 constexpr int kMaxShards = 16;
 
 static int validate(const sert_config &c) {
@@ -172,7 +180,7 @@ static size_t carve(sert_model &m, void *base) {
   m.grad = train ? b.take<float>(o) : nullptr;
   m.flagR = train ? b.take<uint32_t>(V) : nullptr;
   m.flagE = (train && is_vs(c)) ? b.take<uint32_t>(E) : nullptr;
-  m.acc = b.take<double>(1 + kSumsqSlots + 7);
+  m.acc = b.take<double>(kAccDoubles);
   m.losses = b.take<float>(c.loss_slots + 1);   // last slot: scratch for parity hooks
   if (is_vs(c)) {
     const long long k = c.num_negatives;
@@ -284,40 +292,73 @@ static int vs_forward(sert_model &m, const int32_t *x, cudaStream_t st) {
                          c.entity_dim, c.entity_dim, EPI_BIAS_TANH, bp, 1, st);
 }
 
+// Loss of a "lazy" training step (below) that no later tile kernel has finalised: one small kernel on the stream.
+static int flush_pending(sert_model &m) {
+  if (m.pending_bank < 0) return 0;
+  const float B = (float)m.cfg.batch;
+  const float reg = m.cfg.lambda > 0.f ? m.cfg.lambda / (2.0f * B) : 0.f;
+  const int rc = launch_finalize_train(acc_bank(m, m.pending_bank), m.pending_loss, 1.0f / B, reg, m.st);
+  m.pending_bank = -1;
+  m.pending_loss = nullptr;
+  return rc;
+}
+
+// Hot word rows belong to launch_hot_update only while the lazy tile path runs (their flags carry kHotRowMark).
+static int set_hot_marks(sert_model &m, bool on) {
+  if (m.hot_marked == on || m.n_hot == 0) return 0;
+  m.hot_marked = on;
+  return launch_hot_mark(m.flagR, m.hot_ids, m.n_hot, on ? kHotRowMark : 0u, m.st);
+}
+
 static int vs_train_step(sert_model &m, const int32_t *x, const int32_t *y, const float *w,
                          const int32_t *neg, float *loss_out) {
   const sert_config &c = m.cfg;
   cudaStream_t st = m.st;
   const int B = c.batch, dw = c.word_dim, de = c.entity_dim;
   float *Wp = m.theta + m.off[SERT_PARAM_DENSE_W];
+  const bool overlap = m.overlap && !m.profile && m.st2 != nullptr;
+  // "Lazy" step = fused tile kernel + second stream.  Its critical path is two kernels, the tile kernel and the
+  // Adam stream over the two tables; everything else -- gradients and update of the projection matrix and bias,
+  // update of the hot word rows -- runs on the second stream under the table update, and the scalar loss is
+  // written by the NEXT step's tile kernel (or by flush_pending when no step follows).
+  const bool lazy = overlap && m.use_fused == 1 && m.WpT != nullptr && vs_tile_supported(dw, de, c.window, c.num_negatives);
+  if (!lazy && flush_pending(m)) return -1;
+  if (set_hot_marks(m, lazy)) return -1;
   m.stamp += 1;
+  if (m.stamp == kHotRowMark) m.stamp = 1;          // never collides in practice (2^32 steps); keeps the mark unique
   if (neg == nullptr) {
     if (launch_sample_negatives(m.neg, (int64_t)B * c.num_negatives, c.entities, c.seed, m.sample_calls++, st))
       return -1;
     neg = m.neg;
   }
   const int64_t t_next = m.step + 1;
+  const int bank = lazy ? (m.pending_bank == 0 ? 1 : 0) : 0;
+  double *acc = acc_bank(m, bank);
   VsFusedArgs f;
   f.x = x; f.R = m.theta + m.off[SERT_PARAM_WORD_REPR]; f.Wp = Wp; f.bp = m.theta + m.off[SERT_PARAM_DENSE_B];
   f.Eemb = m.theta + m.off[SERT_PARAM_ENTITY_REPR]; f.y = y; f.neg = neg; f.w = w;
   f.gE = m.grad + m.off[SERT_PARAM_ENTITY_REPR]; f.flagE = m.flagE;
   f.gR = m.grad + m.off[SERT_PARAM_WORD_REPR]; f.flagR = m.flagR; f.stamp = m.stamp;
-  f.h = m.h; f.da = m.da; f.loss_acc = m.acc;
+  f.h = m.h; f.da = m.da; f.loss_acc = acc;
   f.B = B; f.W = c.window; f.k = c.num_negatives; f.dw = dw; f.de = de; f.inv_B = 1.0f / (float)B;
-  if (m.n_hot > 0) {
+  if (lazy && m.n_hot > 0) {
     f.hot_slot = m.hot_slot; f.hot_acc = m.hot_acc; f.hot_replicas = kHotReplicas;
-    f.hot_ids = m.hot_ids; f.n_hot = m.n_hot;
+  }
+  if (lazy && m.pending_bank >= 0) {
+    f.fin_acc = acc_bank(m, m.pending_bank); f.fin_loss = m.pending_loss;
+    f.fin_inv_B = 1.0f / (float)B; f.fin_reg_coeff = c.lambda > 0.f ? c.lambda / (2.0f * (float)B) : 0.f;
   }
   const int fused = m.use_fused ? launch_vs_fused(f, m.WpT, !m.wpt_valid, m.use_fused, st) : 1;
   if (fused == 0) m.wpt_valid = true;
   if (fused < 0) return -1;
+  if (lazy) { m.pending_bank = -1; m.pending_loss = nullptr; }      // the tile kernel has taken care of it
   if (fused == 1) {
     // general-shape path: one kernel per stage
     if (vs_forward(m, x, st)) return -1;
     VsNceArgs a;
     a.t = m.t; a.Eemb = m.theta + m.off[SERT_PARAM_ENTITY_REPR]; a.y = y; a.neg = neg; a.w = w;
     a.gE = m.grad + m.off[SERT_PARAM_ENTITY_REPR]; a.flagE = m.flagE; a.stamp = m.stamp; a.da = m.da;
-    a.loss_acc = m.acc; a.dbg_scores = nullptr; a.dbg_u = nullptr; a.dbg_ell = nullptr;
+    a.loss_acc = acc; a.dbg_scores = nullptr; a.dbg_u = nullptr; a.dbg_ell = nullptr;
     a.B = B; a.k = c.num_negatives; a.de = de; a.inv_B = 1.0f / (float)B; a.train = true;
     if (launch_vs_nce(a, st)) return -1;
     // dh = da . Wp^T
@@ -328,9 +369,7 @@ static int vs_train_step(sert_model &m, const int32_t *x, const int32_t *y, cons
   }
   // The gradients of the dense tensors (gWp = h^T . da by split-K, gbp = colsum(da)) are only consumed by the
   // last 16.5k parameters of the arena, so they run on a second stream concurrently with the Adam stream over
-  // the two tables (phase 3); the dense tensors are updated after the join (phase 4).  Saves the ~20 us the
-  // two small kernels would otherwise add to the critical path of the step.
-  const bool overlap = m.overlap && !m.profile && m.st2 != nullptr;
+  // the two tables (phase 3); the dense tensors are updated behind them (phase 4).
   cudaStream_t side = overlap ? m.st2 : st;
   if (overlap) {
     SERT_CUDA(cudaEventRecord(m.ev_fork, st));
@@ -342,35 +381,58 @@ static int vs_train_step(sert_model &m, const int32_t *x, const int32_t *y, cons
   if (launch_colsum_atomic(m.da, m.grad + m.off[SERT_PARAM_DENSE_B], B, de, side)) return -1;
   m.step = t_next;
   OptimArgs o = optim_args(m, loss_out);
+  o.acc = acc;
   o.c0 = adam_alpha_f32(m.step); o.c1 = 0.9f; o.c2 = 0.999f; o.c3 = 1e-8f;
-  if (overlap) {
+  if (!overlap) {
+    m.wpt_valid = false;
+    return timed_update(m, o, true);
+  }
+  OptimArgs dense = o;
+  dense.phase = 4;
+  dense.first4 = m.off[SERT_PARAM_DENSE_W] / 4;       // W and b are the last two tensors of the arena
+  if (m.wpt_valid && de % 4 == 0) {                   // the update keeps the transposed copy current: no transpose launch
+    dense.transposed = m.WpT;
+    dense.transposed_rows = dw;
+    for (int s = 0; s < m.nseg; ++s)
+      if (m.seg[s].offset == m.off[SERT_PARAM_DENSE_W]) dense.transposed_segment = s;
+  } else {
+    m.wpt_valid = false;
+  }
+  OptimArgs tables = o;
+  tables.loss_out = nullptr;
+  tables.phase = 3;
+  if (lazy) {
+    // second stream: dense tensors and hot rows; first stream: the two tables; join; loss left pending
+    dense.loss_out = nullptr;
+    if (launch_adam(dense, side)) return -1;
+    if (m.n_hot > 0) {
+      HotUpdateArgs h;
+      h.theta = m.theta; h.s1 = m.s1; h.s2 = m.s2; h.grad = m.grad;
+      h.table_offset = m.off[SERT_PARAM_WORD_REPR]; h.d = dw;
+      h.hot_acc = m.hot_acc; h.hot_ids = m.hot_ids; h.n_hot = m.n_hot;
+      h.l2_scale = o.l2_scale; h.c0 = o.c0; h.c1 = o.c1; h.c2 = o.c2; h.c3 = o.c3;
+      h.acc = acc; h.counted = 1;
+      if (launch_hot_update(h, side)) return -1;
+    }
     SERT_CUDA(cudaEventRecord(m.ev_join, side));
-    OptimArgs tables = o;
-    tables.loss_out = nullptr;
-    tables.phase = 3;
     if (launch_adam(tables, st)) return -1;
     SERT_CUDA(cudaStreamWaitEvent(st, m.ev_join, 0));
-    o.phase = 4;
-    o.first4 = m.off[SERT_PARAM_DENSE_W] / 4;       // W and b are the last two tensors of the arena
-    o.ticket = reinterpret_cast<unsigned int *>(m.acc + 1 + kSumsqSlots);
-    if (m.wpt_valid && de % 4 == 0) {               // the update keeps the transposed copy current: no transpose launch
-      o.transposed = m.WpT;
-      o.transposed_rows = dw;
-      for (int s = 0; s < m.nseg; ++s)
-        if (m.seg[s].offset == m.off[SERT_PARAM_DENSE_W]) o.transposed_segment = s;
-    } else {
-      m.wpt_valid = false;
-    }
-    return launch_adam(o, st);
+    m.pending_bank = bank;
+    m.pending_loss = loss_out;
+    return 0;
   }
-  m.wpt_valid = false;
-  return timed_update(m, o, true);
+  SERT_CUDA(cudaEventRecord(m.ev_join, side));
+  if (launch_adam(tables, st)) return -1;
+  SERT_CUDA(cudaStreamWaitEvent(st, m.ev_join, 0));
+  dense.ticket = reinterpret_cast<unsigned int *>(m.acc + kAccDoubles - 4);
+  return launch_adam(dense, st);
 }
 
 static int vs_eval_step(sert_model &m, const int32_t *x, const int32_t *y, const int32_t *neg,
                         float *loss_out, bool debug) {
   const sert_config &c = m.cfg;
   cudaStream_t st = m.st;
+  if (flush_pending(m)) return -1;
   if (neg == nullptr) {
     // the eval loss draws its own negatives (loss_fn is instantiated twice, sert/models.py:745-752)
     if (launch_sample_negatives(m.neg, (int64_t)c.batch * c.num_negatives, c.entities, c.seed,
@@ -712,6 +774,7 @@ int sert_model_set_hot_words(sert_model *m, const int32_t *ids_host, int32_t n) 
     SERT_REQUIRE(slot[ids_host[s]] < 0, "duplicate hot word id");
     slot[ids_host[s]] = (int8_t)s;
   }
+  if (flush_pending(*m) || set_hot_marks(*m, false)) return -1;      // the old rows go back to the dense update
   SERT_CUDA(cudaStreamSynchronize(m->st));
   SERT_CUDA(cudaMemcpyAsync(m->hot_slot, slot.data(), slot.size(), cudaMemcpyHostToDevice, m->st));
   if (n > 0) SERT_CUDA(cudaMemcpyAsync(m->hot_ids, ids_host, (size_t)n * sizeof(int32_t), cudaMemcpyHostToDevice, m->st));
@@ -815,6 +878,7 @@ int sert_train_batches(sert_model *m, const int64_t *order_host, int64_t n, cons
     }
     if (rc) return -1;
   }
+  if (flush_pending(*m)) return -1;
   return m->exchange ? ll_reduce_losses(*m, first_slot, n) : 0;
 }
 
@@ -823,6 +887,7 @@ int sert_eval_batches(sert_model *m, int split, const int64_t *order_host, int64
   SERT_REQUIRE(m && (order_host || n == 0), "null argument");
   SERT_REQUIRE(first_slot >= 0 && first_slot + n <= m->cfg.loss_slots, "loss slots exhausted");
   const sert_config &c = m->cfg;
+  if (flush_pending(*m)) return -1;
   for (int64_t j = 0; j < n; ++j) {
     const int64_t b = order_host[j];
     if (check_batch(m, split, b)) return -1;
@@ -845,6 +910,7 @@ int sert_eval_batches(sert_model *m, int split, const int64_t *order_host, int64
 int sert_losses_fetch(sert_model *m, int32_t first_slot, int64_t n, float *out_host) {
   SERT_REQUIRE(m && (out_host || n == 0), "null argument");
   SERT_REQUIRE(first_slot >= 0 && first_slot + n <= m->cfg.loss_slots, "loss slot range out of bounds");
+  if (flush_pending(*m)) return -1;
   if (n > 0)
     SERT_CUDA(cudaMemcpyAsync(out_host, m->losses + first_slot, n * sizeof(float), cudaMemcpyDeviceToHost, m->st));
   SERT_CUDA(cudaStreamSynchronize(m->st));
@@ -887,6 +953,7 @@ int sert_train_batch_host(sert_model *m, const int32_t *x_host, const int32_t *y
       neg = m->stage_neg;
     }
     if (vs_train_step(*m, m->stage_x, m->stage_y, w, neg, loss)) return -1;
+    if (flush_pending(*m)) return -1;
   } else {
     SERT_REQUIRE(indptr_host && indices_host && data_host, "log-linear batches need CSR labels");
     const int64_t base = indptr_host[0];

@@ -14,7 +14,8 @@
 //   * the 1+k score partials of an instance are reduced with a 16-value transposing butterfly (16 shuffles
 //     instead of 5 per score), after which lane 2j holds score j and the sigmoid / log / clip arithmetic of all
 //     rows runs once, in parallel over the lanes, instead of once per row;
-//   * additions to the gradient rows of very frequent words go to per-CTA-group copies (kernels.cuh: hot_slot).
+//   * additions to the gradient rows of very frequent words go to per-CTA-group copies (kernels.cuh: hot_slot);
+//   * one extra CTA writes the PREVIOUS step's loss, so that no finalisation kernel sits between two steps.
 // 32 resident warps per SM (vs_warp: 14), all 512 CTAs of a 4096-instance batch resident at once.
 #include <stdlib.h>
 
@@ -105,6 +106,24 @@ __global__ void __launch_bounds__(kThreads, 4) vs_tile_kernel(VsFusedArgs a, con
   __shared__ int xs[kT * kMaxWindow];
   __shared__ double s_loss[kT];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (blockIdx.x == gridDim.x - 1) {
+    // The extra CTA: the previous step's loss (kernels.cuh: fin_acc).  loss = mean data loss + lambda/(2B) *
+    // sum(theta^2) (sert/models.py:745-755,773-793), accumulators reset for the step after this one.
+    if (a.fin_acc != nullptr && warp < 2) {
+      const int s = threadIdx.x;        // kSumsqSlots == 64 slots, two warps
+      double v = __ldcg(a.fin_acc + 1 + s);
+      a.fin_acc[1 + s] = 0.0;
+      v = warp_sum_d(v);
+      if (lane == 0) s_loss[warp] = v;
+      asm volatile("bar.sync 1, 64;" ::: "memory");
+      if (s == 0) {
+        const double ss = s_loss[0] + s_loss[1];
+        *a.fin_loss = (float)((float)(__ldcg(a.fin_acc) * (double)a.fin_inv_B) + (float)((double)a.fin_reg_coeff * ss));
+        a.fin_acc[0] = 0.0;
+      }
+    }
+    return;
+  }
   const int W = a.W, K1 = a.k + 1;
   const int i = blockIdx.x * kT + warp;  // warp == instance, everywhere but inside tile_matvec
   const bool ok = i < a.B;
@@ -118,7 +137,7 @@ __global__ void __launch_bounds__(kThreads, 4) vs_tile_kernel(VsFusedArgs a, con
     xi = __ldg(a.x + (size_t)i * W + lane);
     const int slot = a.hot_slot != nullptr ? (int)__ldg(a.hot_slot + xi) : -1;
     xdst = slot < 0 ? xi : -1 - slot;
-    if (slot < 0) a.flagR[xi] = a.stamp;   // hot rows are stamped once, by launch_hot_flush
+    if (slot < 0) a.flagR[xi] = a.stamp;   // hot rows keep their kHotRowMark
   }
   if (ok && lane < K1) {
     ri = lane == 0 ? __ldg(a.y + i) : __ldg(a.neg + (size_t)i * a.k + lane - 1);
@@ -237,42 +256,15 @@ __global__ void __launch_bounds__(kThreads, 4) vs_tile_kernel(VsFusedArgs a, con
   }
 }
 
-// gR[hot_ids[s]] += sum over the replicas of hot_acc[.][s]; the replicas are zeroed for the next step.
-// One CTA per hot row, one float4 column per thread; all replica loads are issued before the first store.
-__global__ void __launch_bounds__(kD4) hot_flush_kernel(float *__restrict__ hot_acc, const int32_t *__restrict__ hot_ids,
-                                                        float *__restrict__ gR, uint32_t *__restrict__ flagR,
-                                                        uint32_t stamp) {
-  const int s = blockIdx.x, c = threadIdx.x;
-  const int row = __ldg(hot_ids + s);
-  float4 v[kHotReplicas];
-#pragma unroll
-  for (int r = 0; r < kHotReplicas; ++r)
-    v[r] = __ldcg(reinterpret_cast<const float4 *>(hot_acc + ((size_t)r * kMaxHotRows + s) * kD) + c);
-  float4 *g = reinterpret_cast<float4 *>(gR + (size_t)row * kD) + c;
-  float4 o = __ldcg(g);
-#pragma unroll
-  for (int r = 0; r < kHotReplicas; ++r) f4_add(o, v[r]);
-  *g = o;
-#pragma unroll
-  for (int r = 0; r < kHotReplicas; ++r)
-    reinterpret_cast<float4 *>(hot_acc + ((size_t)r * kMaxHotRows + s) * kD)[c] = f4_zero();
-  if (c == 0) flagR[row] = stamp;
-}
-
 }  // namespace
 
-int launch_hot_flush(float *hot_acc, int replicas, const int32_t *hot_ids, int n_hot, int d, float *gR,
-                     uint32_t *flagR, uint32_t stamp, cudaStream_t st) {
-  if (n_hot <= 0) return 0;
-  SERT_REQUIRE(replicas == kHotReplicas && d == kD, "hot-row flush is built for 16 copies of 128-float rows");
-  hot_flush_kernel<<<n_hot, kD4, 0, st>>>(hot_acc, hot_ids, gR, flagR, stamp);
-  SERT_LAUNCH_CHECK();
-  return 0;
+bool vs_tile_supported(int dw, int de, int W, int k) {
+  return dw == kD && de == kD && W >= 1 && W <= kMaxWindow && k + 1 <= kMaxRows;
 }
 
 // returns 0 = launched, 1 = shape not served by this kernel
 int launch_vs_tile(const VsFusedArgs &a, const float *WpT, cudaStream_t st) {
-  if (a.dw != kD || a.de != kD || a.W > kMaxWindow || a.k + 1 > kMaxRows) return 1;
+  if (!vs_tile_supported(a.dw, a.de, a.W, a.k)) return 1;
   const size_t smem = std::max((size_t)kT * (a.k + 1) * kD, (size_t)kPartFloats) * sizeof(float);
   static bool attr_set = false;
   if (!attr_set) {
@@ -280,10 +272,9 @@ int launch_vs_tile(const VsFusedArgs &a, const float *WpT, cudaStream_t st) {
                                    (int)(kT * kMaxRows * kD * sizeof(float))));
     attr_set = true;
   }
-  vs_tile_kernel<<<cdiv(a.B, kT), kThreads, smem, st>>>(a, WpT);
+  static_assert(kSumsqSlots == 64, "the finalising CTA reads the slots with two warps");
+  vs_tile_kernel<<<cdiv(a.B, kT) + 1, kThreads, smem, st>>>(a, WpT);    // + 1: the CTA that finalises the previous loss
   SERT_LAUNCH_CHECK();
-  if (a.hot_slot != nullptr)
-    return launch_hot_flush(a.hot_acc, a.hot_replicas, a.hot_ids, a.n_hot, kD, a.gR, a.flagR, a.stamp, st);
   return 0;
 }
 
