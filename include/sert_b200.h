@@ -175,6 +175,16 @@ SERT_API int sert_train_batch_host(sert_model *m, const int32_t *x_host, const i
                           const int64_t *indptr_host, const int32_t *indices_host, const float *data_host,
                           const float *w_host, const int32_t *neg_host, float *loss_host);
 
+/* Pipelined form of the above for the vector-space model: enqueues host->device copies (own copy stream, two
+ * staging sets) and the step, and returns a ticket without waiting for the device, so the host prepares batch n+1
+ * while batch n runs.  x/y/w/neg must stay valid until the step has started (pinned memory for real overlap).
+ * sert_train_host_wait blocks until the loss of `ticket` (one of the last 8 issued) is in host memory, stores it in
+ * *loss_host and fails with the reference's NaN/Inf message (sert/models.py:372-379) like the synchronous call.
+ * Same results as sert_train_batch_host: only the host/device synchronisation moves. */
+SERT_API int sert_train_batch_host_async(sert_model *m, const int32_t *x_host, const int32_t *y_host,
+                                const float *w_host, const int32_t *neg_host, int64_t *ticket_out);
+SERT_API int sert_train_host_wait(sert_model *m, int64_t ticket, float *loss_host);
+
 /* ---- parity hooks (no reference counterpart; expose the graph's intermediate tensors) ---------- */
 /* vector space: forward of one attached batch; out_scores_host (B,1+k) = [u.E[y], u.E[n_j]] logits,
  * out_proj_host (B,de) = clipped tanh projection u, out_ell_host (B,) instance losses. Any may be NULL. */

@@ -52,6 +52,8 @@ SIGNATURES = {
     'sert_model_profile': (c_int, [c_void_p, c_int]),
     'sert_model_set_fused': (c_int, [c_void_p, c_int]),
     'sert_model_set_overlap': (c_int, [c_void_p, c_int]),
+    'sert_train_batch_host_async': (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
+    'sert_train_host_wait': (c_int, [c_void_p, c_int64, c_void_p]),
     'sert_model_set_hot_words': (c_int, [c_void_p, c_void_p, c_int32]),
     'sert_model_set_tensor_cores': (c_int, [c_void_p, c_int]),
     'sert_debug_gemm_tc_bench': (c_int, [c_int, c_int, c_int, c_int, c_int, ctypes.POINTER(c_float)]),

@@ -106,6 +106,21 @@ struct sert_model {
   int pending_bank = -1;
   float *pending_loss = nullptr;
   bool hot_marked = false;            // flagR of the hot word rows carries kHotRowMark
+  // pipelined host batches (sert_train_batch_host_async): copy streams, second staging set, loss ring
+  static constexpr int kPipe = 8;
+  bool pipe_ready = false;
+  cudaStream_t st_h2d = nullptr, st_d2h = nullptr;
+  cudaEvent_t ev_copied[2] = {nullptr, nullptr}, ev_free[2] = {nullptr, nullptr};
+  bool ev_free_set[2] = {false, false};
+  cudaEvent_t ev_fused = nullptr;     // recorded behind the forward/backward kernels of a step (want_fused_event)
+  bool want_fused_event = false;
+  cudaEvent_t ev_loss[kPipe] = {};
+  int32_t *stage2_x = nullptr, *stage2_y = nullptr, *stage2_neg = nullptr;
+  float *stage2_w = nullptr;
+  float *pipe_losses = nullptr;       // device, kPipe slots
+  float *pin_loss = nullptr;          // pinned host, kPipe slots
+  int64_t host_steps = 0;             // tickets issued so far
+  int64_t host_unfetched = -1;        // ticket whose loss is not yet on its way to the host
   cudaStream_t st2 = nullptr;
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
   bool profile = false;
@@ -198,6 +213,13 @@ static size_t carve(sert_model &m, void *base) {
     m.dbg_ell = b.take<float>(B);
     m.stage_neg = b.take<int32_t>(B * k);
     m.stage_y = b.take<int32_t>(B);
+    if (train) {
+      m.stage2_x = b.take<int32_t>(B * W);
+      m.stage2_y = b.take<int32_t>(B);
+      m.stage2_neg = b.take<int32_t>(B * k);
+      m.stage2_w = b.take<float>(B);
+      m.pipe_losses = b.take<float>(sert_model::kPipe);
+    }
   } else {
     m.X = b.take<float>(B * W * dw);
     m.Z = b.take<float>(B * W * E);
@@ -351,6 +373,7 @@ static int vs_train_step(sert_model &m, const int32_t *x, const int32_t *y, cons
   const int fused = m.use_fused ? launch_vs_fused(f, m.WpT, !m.wpt_valid, m.use_fused, st) : 1;
   if (fused == 0) m.wpt_valid = true;
   if (fused < 0) return -1;
+  if (m.want_fused_event) SERT_CUDA(cudaEventRecord(m.ev_fused, st));   // the previous step's loss is final here
   if (lazy) { m.pending_bank = -1; m.pending_loss = nullptr; }      // the tile kernel has taken care of it
   if (fused == 1) {
     // general-shape path: one kernel per stage
@@ -713,6 +736,16 @@ int sert_model_destroy(sert_model *m) {
     }
     if (m->ev_fork) cudaEventDestroy(m->ev_fork);
     if (m->ev_join) cudaEventDestroy(m->ev_join);
+    if (m->st_h2d) { cudaStreamSynchronize(m->st_h2d); cudaStreamDestroy(m->st_h2d); }
+    if (m->st_d2h) { cudaStreamSynchronize(m->st_d2h); cudaStreamDestroy(m->st_d2h); }
+    for (int q = 0; q < 2; ++q) {
+      if (m->ev_copied[q]) cudaEventDestroy(m->ev_copied[q]);
+      if (m->ev_free[q]) cudaEventDestroy(m->ev_free[q]);
+    }
+    if (m->ev_fused) cudaEventDestroy(m->ev_fused);
+    for (int q = 0; q < sert_model::kPipe; ++q)
+      if (m->ev_loss[q]) cudaEventDestroy(m->ev_loss[q]);
+    if (m->pin_loss) cudaFreeHost(m->pin_loss);
     delete m;
   }
   return 0;
@@ -969,6 +1002,96 @@ int sert_train_batch_host(sert_model *m, const int32_t *x_host, const int32_t *y
   }
   SERT_CUDA(cudaMemcpyAsync(loss_host, loss, sizeof(float), cudaMemcpyDeviceToHost, st));
   SERT_CUDA(cudaStreamSynchronize(st));
+  if (!isfinite(*loss_host)) {
+    char buf[160];
+    snprintf(buf, sizeof(buf), "Encountered NaN or infinity (%f) during batch iteration.", (double)*loss_host);
+    set_error(buf);
+    return -2;
+  }
+  return 0;
+}
+
+// ---- pipelined host batches ------------------------------------------------------------------------------------
+static int pipe_setup(sert_model &m) {
+  if (m.pipe_ready) return 0;
+  SERT_CUDA(cudaStreamCreateWithFlags(&m.st_h2d, cudaStreamNonBlocking));
+  SERT_CUDA(cudaStreamCreateWithFlags(&m.st_d2h, cudaStreamNonBlocking));
+  for (int q = 0; q < 2; ++q) {
+    SERT_CUDA(cudaEventCreateWithFlags(&m.ev_copied[q], cudaEventDisableTiming));
+    SERT_CUDA(cudaEventCreateWithFlags(&m.ev_free[q], cudaEventDisableTiming));
+  }
+  SERT_CUDA(cudaEventCreateWithFlags(&m.ev_fused, cudaEventDisableTiming));
+  for (int q = 0; q < sert_model::kPipe; ++q) SERT_CUDA(cudaEventCreateWithFlags(&m.ev_loss[q], cudaEventDisableTiming));
+  SERT_CUDA(cudaMallocHost(reinterpret_cast<void **>(&m.pin_loss), sert_model::kPipe * sizeof(float)));
+  m.pipe_ready = true;
+  return 0;
+}
+
+// loss of ticket t: device slot -> pinned host slot on the D2H stream, once `after` has happened
+static int pipe_dispatch_loss(sert_model &m, int64_t t, cudaEvent_t after) {
+  const int q = (int)(t % sert_model::kPipe);
+  SERT_CUDA(cudaStreamWaitEvent(m.st_d2h, after, 0));
+  SERT_CUDA(cudaMemcpyAsync(m.pin_loss + q, m.pipe_losses + q, sizeof(float), cudaMemcpyDeviceToHost, m.st_d2h));
+  SERT_CUDA(cudaEventRecord(m.ev_loss[q], m.st_d2h));
+  return 0;
+}
+
+int sert_train_batch_host_async(sert_model *m, const int32_t *x_host, const int32_t *y_host, const float *w_host,
+                                const int32_t *neg_host, int64_t *ticket_out) {
+  SERT_REQUIRE(m && x_host && y_host && ticket_out, "null argument");
+  SERT_REQUIRE(is_vs(m->cfg) && m->cfg.inference_only == 0, "pipelined host batches need a trainable vector-space model");
+  if (pipe_setup(*m)) return -1;
+  const sert_config &c = m->cfg;
+  const size_t B = c.batch;
+  const int64_t t = m->host_steps;
+  const int set = (int)(t & 1), q = (int)(t % sert_model::kPipe);
+  // the ring slot of ticket t - kPipe is reused: its loss must have reached the host
+  if (t >= sert_model::kPipe && m->host_unfetched != t - sert_model::kPipe) SERT_CUDA(cudaEventSynchronize(m->ev_loss[q]));
+  SERT_REQUIRE(m->host_unfetched < 0 || m->host_unfetched > t - sert_model::kPipe, "loss ring overrun");
+  int32_t *sx = set ? m->stage2_x : m->stage_x, *sy = set ? m->stage2_y : m->stage_y;
+  int32_t *sn = set ? m->stage2_neg : m->stage_neg;
+  float *sw = set ? m->stage2_w : m->stage_w;
+  // host -> device on the copy stream, into the staging set the step before last has released
+  if (m->ev_free_set[set]) SERT_CUDA(cudaStreamWaitEvent(m->st_h2d, m->ev_free[set], 0));
+  SERT_CUDA(cudaMemcpyAsync(sx, x_host, B * c.window * sizeof(int32_t), cudaMemcpyHostToDevice, m->st_h2d));
+  SERT_CUDA(cudaMemcpyAsync(sy, y_host, B * sizeof(int32_t), cudaMemcpyHostToDevice, m->st_h2d));
+  if (w_host) SERT_CUDA(cudaMemcpyAsync(sw, w_host, B * sizeof(float), cudaMemcpyHostToDevice, m->st_h2d));
+  if (neg_host)
+    SERT_CUDA(cudaMemcpyAsync(sn, neg_host, B * c.num_negatives * sizeof(int32_t), cudaMemcpyHostToDevice, m->st_h2d));
+  SERT_CUDA(cudaEventRecord(m->ev_copied[set], m->st_h2d));
+  SERT_CUDA(cudaStreamWaitEvent(m->st, m->ev_copied[set], 0));
+  m->want_fused_event = true;
+  const int rc = vs_train_step(*m, sx, sy, w_host ? sw : nullptr, neg_host ? sn : nullptr, m->pipe_losses + q);
+  m->want_fused_event = false;
+  if (rc) return -1;
+  SERT_CUDA(cudaEventRecord(m->ev_free[set], m->st));
+  m->ev_free_set[set] = true;
+  // the loss of the ticket before this one is final behind this step's forward/backward kernel
+  if (m->host_unfetched >= 0 && pipe_dispatch_loss(*m, m->host_unfetched, m->ev_fused)) return -1;
+  m->host_unfetched = -1;
+  if (m->pending_bank >= 0) {
+    m->host_unfetched = t;                      // written by the next step's tile kernel (or sert_train_host_wait)
+  } else {
+    if (pipe_dispatch_loss(*m, t, m->ev_free[set])) return -1;
+  }
+  *ticket_out = t;
+  m->host_steps = t + 1;
+  return 0;
+}
+
+int sert_train_host_wait(sert_model *m, int64_t ticket, float *loss_host) {
+  SERT_REQUIRE(m && loss_host, "null argument");
+  SERT_REQUIRE(ticket >= 0 && ticket < m->host_steps && ticket >= m->host_steps - sert_model::kPipe,
+               "ticket out of the window of the last 8 pipelined steps");
+  if (ticket == m->host_unfetched) {
+    if (flush_pending(*m)) return -1;
+    SERT_CUDA(cudaEventRecord(m->ev_fused, m->st));
+    if (pipe_dispatch_loss(*m, ticket, m->ev_fused)) return -1;
+    m->host_unfetched = -1;
+  }
+  const int q = (int)(ticket % sert_model::kPipe);
+  SERT_CUDA(cudaEventSynchronize(m->ev_loss[q]));
+  *loss_host = m->pin_loss[q];
   if (!isfinite(*loss_host)) {
     char buf[160];
     snprintf(buf, sizeof(buf), "Encountered NaN or infinity (%f) during batch iteration.", (double)*loss_host);

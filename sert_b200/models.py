@@ -684,6 +684,40 @@ class VectorSpaceLanguageModel(VectorSpaceLanguageModelBase):
         N.check(self._native.lib.sert_model_set_hot_words(self._native.handle, N.host_ptr(ids), int(ids.size)))
         self.hot_words = ids
 
+    def train_stream(self, batches, depth=2):
+        """Trains on host batches that are NOT part of the device-resident data set, pipelined: the host->device copy and
+        the enqueueing of batch n+1 overlap the device work of batch n (include/sert_b200.h:
+        sert_train_batch_host_async).  `batches` yields (x (B,W), y (B,), w (B,) or None, negatives (B,k) or None);
+        returns the float32 train losses, one per batch; NaN/Inf raises like train() (sert/models.py:372-379).
+        Arrays are used in place when they already are C-contiguous int32 / float32 (pin them for real overlap)."""
+        nat = self._native
+        B, W, k = self.batch_size, self.window_size, nat.cfg.num_negatives
+        losses, inflight = [], []
+        ticket, value = N.c_int64(0), N.ctypes.c_float(0)
+
+        def wait_oldest():
+            t, keep = inflight.pop(0)
+            N.check(nat.lib.sert_train_host_wait(nat.handle, t, N.ctypes.byref(value)))
+            losses.append(value.value)
+            del keep
+
+        for x, y, w, neg in batches:
+            x = np.ascontiguousarray(x, dtype=np.int32)
+            y = np.ascontiguousarray(y, dtype=np.int32)
+            w = None if w is None else np.ascontiguousarray(w, dtype=np.float32)
+            neg = None if neg is None else np.ascontiguousarray(neg, dtype=np.int32)
+            assert x.shape == (B, W) and y.shape == (B,), 'host batches are (batch_size, window_size) / (batch_size,)'
+            assert w is None or w.shape == (B,)
+            assert neg is None or neg.shape == (B, k)
+            N.check(nat.lib.sert_train_batch_host_async(nat.handle, N.host_ptr(x), N.host_ptr(y), N.host_ptr(w),
+                                                        N.host_ptr(neg), N.ctypes.byref(ticket)))
+            inflight.append((ticket.value, (x, y, w, neg)))
+            while len(inflight) > max(1, depth) - 1 and len(inflight) > 1:
+                wait_oldest()
+        while inflight:
+            wait_oldest()
+        return np.asarray(losses, dtype=np.float32)
+
     def get_dense(self):
         return (self._native.get_tensor(N.PARAM_DENSE_W, (self.representation_size, self.entity_representation_size)),
                 self._native.get_tensor(N.PARAM_DENSE_B, (self.entity_representation_size,)))

@@ -148,6 +148,51 @@ def test_epoch_api_and_host_batches():
     assert np.isfinite(mean_e) and std_e >= 0
 
 
+@pytest.mark.parametrize('dims', [dict(dw=128, de=128, W=10, B=96, k=10), dict(dw=32, de=48, W=4, B=64, k=5)])
+def test_pipelined_host_batches_match_resident_training(dims):
+    """sert_train_batch_host_async / sert_train_host_wait (train_stream): same losses and parameters as train_fn on the
+    resident data set, for the lazy tile-kernel step and for the per-stage step; tickets waited late and in bulk."""
+    from sert_b200 import _native as N
+    p = H.vs_problem(23, V=700, E=180, n_batches=11, weights=True, **dims)
+    B = p['B']
+    a, b = make_model(p, 0.01), make_model(p, 0.01)
+    order = [4, 0, 9, 2, 7, 1, 10, 3, 8, 5, 6]
+    ref = [a.train_fn(bi, p['neg'][j]) for j, bi in enumerate(order)]
+    x, y, w = p['train']
+
+    def batches(lo, hi):
+        for j in range(lo, hi):
+            sl = slice(order[j] * B, (order[j] + 1) * B)
+            yield x[sl], y[sl], w[sl], p['neg'][j]
+
+    got = list(b.train_stream(batches(0, 5)))
+    # resident-data steps in between share the accumulators and the pending loss with the pipelined ones
+    got.append(b.train_fn(order[5], p['neg'][5]))
+    got += list(b.train_stream(batches(6, 11), depth=4))
+    np.testing.assert_allclose(got, ref, rtol=1e-5)
+    Ra, Ea = a.get_representations()
+    Rb, Eb = b.get_representations()
+    # float atomics: the summation order of a gradient row differs from run to run, and Adam's m / sqrt(v) turns a
+    # last-bit difference of a nearly cancelling sum into a visible one -- same tolerance as against the oracle
+    H.close(Rb, Ra, rtol=2e-4, what='R, pipelined vs resident')
+    H.close(Eb, Ea, rtol=2e-4, what='Eemb, pipelined vs resident')
+    oracle = H.vs_oracle(p, 0.01)
+    for j, bi in enumerate(order):
+        oracle.train_batch(bi, p['neg'][j])
+    H.close(Rb, oracle.R, rtol=2e-4, what='R, pipelined vs oracle')
+    H.close(Eb, oracle.Eemb, rtol=2e-4, what='Eemb, pipelined vs oracle')
+    # tickets: only the last 8 can be waited for; a NaN surfaces at the wait
+    nat = b._native
+    out = N.ctypes.c_float(0)
+    assert nat.lib.sert_train_host_wait(nat.handle, 0, N.ctypes.byref(out)) != 0
+    assert 'window' in N.last_error()
+    bad = p['Wp'].copy()
+    bad[0, 0] = np.nan
+    nat.set_tensor(N.PARAM_DENSE_W, bad)
+    with pytest.raises(RuntimeError, match='NaN or infinity'):
+        b.train_stream(batches(0, 2))
+
+
 def test_device_sampled_negatives_and_nan_guard():
     p = H.vs_problem(3, V=400, E=100, dw=16, de=16, W=3, B=32, k=4, n_batches=3)
     model = make_model(p, 0.0, seed=1234)
