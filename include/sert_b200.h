@@ -210,8 +210,12 @@ SERT_API int sert_scorer_create(const float *entities_host, int64_t rows, int32_
                        int32_t normalise, int32_t max_queries, int32_t max_k, void *arena_dev,
                        size_t arena_bytes, void *stream, sert_scorer **out);
 SERT_API int sert_scorer_destroy(sert_scorer *s);
-/* Scoring arithmetic: 1 (default) = tcgen05 tensor cores on a 3-term bf16 split of both operands (fp32-class
- * accuracy) followed by an exact fp32 re-scoring of the surviving candidates; 0 = fp32 FMA tiles on CUDA cores. */
+/* Scoring arithmetic.  1 (default) = tcgen05 tensor cores, coarse-then-exact: one bf16 GEMM scores every row, each
+ * query keeps every row within a rigorous rounding-error margin of its k-th best (|q| max|e| 2^-7, see score.cu),
+ * and the survivors are re-scored in fp32, so the returned top k is the exact fp32 top k at a third of the tensor
+ * work; queries with too many near-ties for the margin fall back to mode 2 automatically.  2 = tensor cores on a
+ * 3-term bf16 split of both operands (fp32-class scores throughout) + fp32 re-scoring.  0 = fp32 FMA tiles on CUDA
+ * cores. */
 SERT_API int sert_scorer_set_mode(sert_scorer *s, int32_t mode);
 /* Top-k by inner product of q query vectors (host f32 (q,d); normalise_q!=0 L2-normalises them,
  * bin/query.py:333-336) against the shard.  Outputs (q,k) global row ids and float32 inner products,

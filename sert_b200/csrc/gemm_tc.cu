@@ -352,15 +352,17 @@ int get_encode_fn(EncodeTiledFn *out) {
   return 0;
 }
 
-// 2-D bf16 tensor (rows, Kt) row-major; box = (64 elements of K) x box_rows, 128-byte swizzle, zero OOB fill.
-int make_map(const __nv_bfloat16 *base, long long rows, int Kt, int box_rows, TcMap *out) {
+// 2-D bf16 tensor (rows, Kt) row-major with row stride ld elements; box = (64 elements of K) x box_rows, 128-byte
+// swizzle, zero OOB fill.
+int make_map(const __nv_bfloat16 *base, long long rows, int Kt, long long ld, int box_rows, TcMap *out) {
   static_assert(sizeof(CUtensorMap) <= sizeof(TcMap), "CUtensorMap does not fit");
   EncodeTiledFn encode;
   if (get_encode_fn(&encode)) return -1;
   SERT_REQUIRE((reinterpret_cast<uintptr_t>(base) & 15) == 0, "tensor-map base must be 16-byte aligned");
   SERT_REQUIRE(Kt % BK == 0, "K must be padded to a multiple of 64");
   const cuuint64_t gdim[2] = {(cuuint64_t)Kt, (cuuint64_t)std::max<long long>(rows, 1)};
-  const cuuint64_t gstride[1] = {(cuuint64_t)Kt * sizeof(__nv_bfloat16)};
+  SERT_REQUIRE(ld >= Kt && ld % 8 == 0, "row stride must cover K and be a multiple of 16 bytes");
+  const cuuint64_t gstride[1] = {(cuuint64_t)ld * sizeof(__nv_bfloat16)};
   const cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)box_rows};
   const cuuint32_t estride[2] = {1, 1};
   const CUresult r = encode(reinterpret_cast<CUtensorMap *>(out->bytes), CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2,
@@ -375,12 +377,18 @@ int make_map(const __nv_bfloat16 *base, long long rows, int Kt, int box_rows, Tc
 
 int launch_gemm_tc(const __nv_bfloat16 *A, int M, const __nv_bfloat16 *B, long long N_total, long long n_begin,
                    long long n_end, int Kt, const TcEpilogue &epi, cudaStream_t st) {
+  return launch_gemm_tc_ld(A, Kt, M, B, Kt, N_total, n_begin, n_end, Kt, epi, st);
+}
+
+int launch_gemm_tc_ld(const __nv_bfloat16 *A, long long lda, int M, const __nv_bfloat16 *B, long long ldb,
+                      long long N_total, long long n_begin, long long n_end, int Kt, const TcEpilogue &epi,
+                      cudaStream_t st) {
   if (M == 0 || n_end <= n_begin) return 0;
   SERT_REQUIRE(n_begin >= 0 && n_end <= N_total && N_total < (1ll << 31), "bad column range");
   SERT_REQUIRE(Kt > 0 && Kt % BK == 0, "K must be a positive multiple of 64");
   TcMap ma, mb;
-  if (make_map(A, M, Kt, BM, &ma)) return -1;
-  if (make_map(B, N_total, Kt, BN, &mb)) return -1;
+  if (make_map(A, M, Kt, lda, BM, &ma)) return -1;
+  if (make_map(B, N_total, Kt, ldb, BN, &mb)) return -1;
   static bool configured = false;
   static int sms = kNumSMs;
   if (!configured) {

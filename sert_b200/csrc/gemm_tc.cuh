@@ -47,5 +47,10 @@ int launch_split_bf16_t(const float *src, long long R, long long C, long long ld
 // Kt = terms * Kp a multiple of 64.  For TC_EPI_STORE column n of C is B row n.
 int launch_gemm_tc(const __nv_bfloat16 *A, int M, const __nv_bfloat16 *B, long long N_total, long long n_begin,
                    long long n_end, int Kt, const TcEpilogue &epi, cudaStream_t st);
+// Same with explicit row strides (elements): the first Kt columns of wider operands, e.g. the hi.hi term alone of
+// 3-term split operands (Kt = Kp, lda = ldb = 3 Kp).
+int launch_gemm_tc_ld(const __nv_bfloat16 *A, long long lda, int M, const __nv_bfloat16 *B, long long ldb,
+                      long long N_total, long long n_begin, long long n_end, int Kt, const TcEpilogue &epi,
+                      cudaStream_t st);
 
 }  // namespace sert

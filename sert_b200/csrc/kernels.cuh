@@ -121,6 +121,7 @@ struct OptimArgs {
   double *acc;                     // 1 + kSumsqSlots doubles, see above
   float *loss_out;
   float inv_B, reg_coeff;
+  bool no_finalize = false;        // phase 0: leave the loss to a later launch_finalize_train
   int phase = 0;                   // 0 = everything, 3 = row-stamped tables only, 4 = dense tensors only
   long long first4 = 0;            // first 16-byte chunk to process (phase 4 starts at the first dense tensor)
   unsigned int *ticket = nullptr;  // phase 4: block counter (zero between launches); the last block finalises the

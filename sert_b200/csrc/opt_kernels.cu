@@ -184,7 +184,7 @@ static int launch_update(const OptimArgs &a, bool adam, cudaStream_t st) {
     else dense_update_kernel<false, 0><<<g, 256, 0, st>>>(a);
   }
   SERT_LAUNCH_CHECK();
-  if (a.phase == 0) {          // the loss is complete once the last phase of the step has run (phase 4 finalises itself)
+  if (a.phase == 0 && !a.no_finalize) {          // the loss is complete once the last phase of the step has run (phase 4 finalises itself)
     finalize_train_kernel<<<1, kSumsqSlots, 0, st>>>(a.acc, a.loss_out, a.inv_B, a.reg_coeff);
     SERT_LAUNCH_CHECK();
   }

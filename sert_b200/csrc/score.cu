@@ -13,6 +13,7 @@
 #include "score.cuh"
 
 #include <stdlib.h>
+#include <string.h>
 
 #include "gemm_tc.cuh"
 #include "kernels.cuh"
@@ -170,6 +171,32 @@ __global__ void __launch_bounds__(256) rescore_kernel(const float *__restrict__ 
   }
 }
 
+// margin[q] = 2 eps_q (topk_sweep), one warp per query
+__global__ void __launch_bounds__(256) query_margin_kernel(const float *__restrict__ Qm, int Q, int d, float ent_norm_max,
+                                                           float *__restrict__ margin) {
+  const int q = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (q >= Q) return;
+  float ss = 0.f;
+  for (int c = lane; c < d; c += 32) { const float v = Qm[(size_t)q * d + c]; ss = fmaf(v, v, ss); }
+  ss = warp_sum(ss);
+  if (lane == 0) {
+    const float eps = sqrtf(ss) * ent_norm_max * (0.00390625f + 3.8147e-6f + (float)d * 1.1920929e-7f);
+    margin[q] = 2.0f * eps * 1.02f;
+  }
+}
+
+// largest row norm, as ordered uint bits (norms are >= 0)
+__global__ void __launch_bounds__(256) row_norm_max_kernel(const float *__restrict__ E, long long rows, int d,
+                                                           unsigned int *__restrict__ out) {
+  const long long r = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (r >= rows) return;
+  float ss = 0.f;
+  for (int c = lane; c < d; c += 32) { const float v = E[(size_t)r * d + c]; ss = fmaf(v, v, ss); }
+  ss = warp_sum(ss);
+  if (lane == 0) atomicMax(out, __float_as_uint(sqrtf(ss)));
+}
+
 // ---- prune by radix selection ---------------------------------------------------------------------------
 // Re-selects the best k candidates of a query and raises tau.  mode 0: only lists longer than cap/4; mode 2: every
 // list; mode 1 ("final"): every list, and the sorted (row id, score) outputs are written.  The k-th largest key is FOUND (11-bit MSB radix passes over the 64-bit keys
@@ -182,7 +209,8 @@ constexpr int kSelBins = 2048;
 __global__ void __launch_bounds__(256) prune_select_kernel(unsigned long long *__restrict__ cand, int *__restrict__ count,
                                                            unsigned long long *__restrict__ tau, int cap, int k,
                                                            int mode, int32_t *__restrict__ out_idx,
-                                                           float *__restrict__ out_score, int k_pow2) {
+                                                           float *__restrict__ out_score, int k_pow2,
+                                                           const float *__restrict__ margin, int *__restrict__ overflow) {
   extern __shared__ unsigned long long sel_out[];            // k_pow2 keys
   __shared__ unsigned int hist[kSelBins];
   __shared__ unsigned int warp_tot[8];
@@ -272,6 +300,43 @@ __global__ void __launch_bounds__(256) prune_select_kernel(unsigned long long *_
     T = s_prefix;
   }
 
+  if (margin != nullptr) {
+    // ---- margin mode (coarse scores): keep EVERY candidate whose score is within margin[q] of the k-th best, so that
+    // no row whose exact score belongs to the top k is dropped (topk_sweep).  k_pow2 = cap/2 slots of shared memory.
+    if (n < k) return;                                       // nothing to drop, no threshold yet
+    if (tid == 0) s_fill = 0;
+    __syncthreads();
+    if (n == k) {                                            // the k-th best is the minimum
+      unsigned long long mn = ~0ull;
+      for (int i = tid; i < n; i += blockDim.x) mn = min(mn, mine[i]);
+      for (int o = 16; o > 0; o >>= 1) mn = min(mn, __shfl_xor_sync(0xffffffffu, mn, o));
+      if (lane == 0) small[warp] = mn;
+      __syncthreads();
+      if (tid == 0) {
+        for (int w = 1; w < 8; ++w) mn = min(mn, small[w]);
+        tau[q] = make_key(key_score(mn) - margin[q], 0xffffffffu);
+      }
+      return;
+    }
+    const unsigned long long Tm = make_key(key_score(T) - margin[q], 0xffffffffu);   // smallest key of that score
+    for (int i = tid; i < n; i += blockDim.x) {
+      const unsigned long long key = mine[i];
+      if (key >= Tm) {
+        const int slot = atomicAdd(&s_fill, 1);
+        if (slot < k_pow2) sel_out[slot] = key;
+      }
+    }
+    __syncthreads();
+    const int c = s_fill;
+    if (c > k_pow2) {                                        // too many near-ties for the coarse scores: exact sweep instead
+      if (tid == 0) *overflow = 1;
+      return;
+    }
+    for (int i = tid; i < c; i += blockDim.x) mine[i] = sel_out[i];
+    if (tid == 0) { count[q] = c; tau[q] = Tm; }
+    return;
+  }
+
   // ---- compaction: the survivors, in arbitrary order, go to shared memory and then to the list head ----
   if (tid == 0) s_fill = 0;
   __syncthreads();
@@ -315,11 +380,12 @@ __global__ void __launch_bounds__(256) prune_select_kernel(unsigned long long *_
 }
 
 static int launch_prune(const TopkState &s, int Q, int k, int mode, int32_t *out_idx, float *out_score,
-                        cudaStream_t st) {
+                        cudaStream_t st, const float *margin = nullptr) {
   int k_pow2 = 2;
   while (k_pow2 < k) k_pow2 <<= 1;
-  prune_select_kernel<<<Q, 256, (size_t)k_pow2 * sizeof(unsigned long long), st>>>(s.cand, s.count, s.tau, s.cap, k,
-                                                                                 mode, out_idx, out_score, k_pow2);
+  if (margin != nullptr) k_pow2 = s.cap / 2;
+  prune_select_kernel<<<Q, 256, (size_t)k_pow2 * sizeof(unsigned long long), st>>>(
+      s.cand, s.count, s.tau, s.cap, k, mode, out_idx, out_score, k_pow2, margin, s.overflow);
   SERT_LAUNCH_CHECK();
   return 0;
 }
@@ -329,7 +395,7 @@ static int launch_prune(const TopkState &s, int Q, int k, int mode, int32_t *out
 // that would overflow sets *overflow and the caller falls back to the conservative pass (chunk = cap/2 rows,
 // which cannot overflow even if every score of a chunk survives).
 static int topk_pass(const TopkState &s, const float *queries_dev, int Q, int k_sel, bool optimistic,
-                     cudaStream_t st) {
+                     cudaStream_t st, bool coarse = false) {
   const bool tensor = s.mode == SCORE_TENSOR;
   reset_topk_state_kernel<<<cdiv(Q, 256), 256, 0, st>>>(s.tau, s.count, Q);
   SERT_LAUNCH_CHECK();
@@ -342,7 +408,9 @@ static int topk_pass(const TopkState &s, const float *queries_dev, int Q, int k_
       ep.mode = TC_EPI_TOPK;
       ep.tau = s.tau; ep.count = s.count; ep.cand = s.cand; ep.cap = s.cap; ep.row_offset = s.row_begin;
       ep.overflow = s.overflow;
-      if (launch_gemm_tc(s.q_split, Q, s.ent_split, s.rows, n0, n1, s.kt, ep, st)) return -1;
+      // coarse: the first block of both operands is the hi term ([hi|hi|mid] x [hi|mid|hi]); same buffers, depth kt/3
+      const int depth = coarse ? s.kt / s.terms : s.kt;
+      if (launch_gemm_tc_ld(s.q_split, s.kt, Q, s.ent_split, s.kt, s.rows, n0, n1, depth, ep, st)) return -1;
     } else {
       dim3 grid(cdiv(n1 - n0, TN), cdiv(Q, TQ));
       score_filter_kernel<<<grid, 256, 0, st>>>(queries_dev, s.entities, Q, n0, n1, s.d, s.row_begin, s.tau, s.count,
@@ -351,7 +419,7 @@ static int topk_pass(const TopkState &s, const float *queries_dev, int Q, int k_
     }
     // forced prune (mode 2) while tau is still loose or at the end; otherwise only lists more than half full
     const bool force = optimistic || n1 == s.rows;
-    if (launch_prune(s, Q, k_sel, force ? 2 : 0, nullptr, nullptr, st)) return -1;
+    if (launch_prune(s, Q, k_sel, force ? 2 : 0, nullptr, nullptr, st, coarse ? s.margin : nullptr)) return -1;
     n0 = n1;
     if (optimistic) chunk = std::min<long long>(chunk * 4, 1 << 16);
   }
@@ -368,11 +436,26 @@ int topk_sweep(const TopkState &s, const float *queries_dev, int Q, int k, int32
   // cannot drop a true top-k row before the exact re-scoring
   const int k_sel = tensor ? std::min(s.cap / 2, k + 16) : k;
   if (tensor && launch_split_bf16(queries_dev, Q, s.d, s.d, s.terms, SPLIT_A, s.q_split, st)) return -1;
-  if (topk_pass(s, queries_dev, Q, k_sel, true, st)) return -1;
-  int overflow = 0;
-  SERT_CUDA(cudaMemcpyAsync(&overflow, s.overflow, sizeof(int), cudaMemcpyDeviceToHost, st));
-  SERT_CUDA(cudaStreamSynchronize(st));
-  if (overflow && topk_pass(s, queries_dev, Q, k_sel, false, st)) return -1;
+  int overflow = 1;
+  if (tensor && s.coarse && s.terms == 3 && s.margin != nullptr) {
+    // Coarse-then-exact: ONE bf16 GEMM (the hi.hi term, a third of the tensor work) scores every row with an error
+    // of at most eps_q = |q| max|e| (2^-8 + 2^-18 + d 2^-23): bf16 round-to-nearest is 2^-9 relative per operand, the
+    // products sum to at most |q||e| (Cauchy-Schwarz), d 2^-23 covers the fp32 accumulation.  Every row of the exact
+    // top k then scores within 2 eps_q of the coarse k-th best, so the lists keep everything above (k-th - 2 eps_q);
+    // the survivors (k + a few dozen on these workloads) are re-scored in fp32 below.  Lists that would exceed cap/2
+    // (many near-ties) raise the overflow flag and the bf16x3 sweep runs instead.
+    query_margin_kernel<<<cdiv(Q, 8), 256, 0, st>>>(queries_dev, Q, s.d, s.ent_norm_max, s.margin);
+    SERT_LAUNCH_CHECK();
+    if (topk_pass(s, queries_dev, Q, k, true, st, true)) return -1;
+    SERT_CUDA(cudaMemcpyAsync(&overflow, s.overflow, sizeof(int), cudaMemcpyDeviceToHost, st));
+    SERT_CUDA(cudaStreamSynchronize(st));
+  }
+  if (overflow) {
+    if (topk_pass(s, queries_dev, Q, k_sel, true, st)) return -1;
+    SERT_CUDA(cudaMemcpyAsync(&overflow, s.overflow, sizeof(int), cudaMemcpyDeviceToHost, st));
+    SERT_CUDA(cudaStreamSynchronize(st));
+    if (overflow && topk_pass(s, queries_dev, Q, k_sel, false, st)) return -1;
+  }
   if (tensor && s.rows > 0) {
     rescore_kernel<<<Q, 256, (size_t)s.d * sizeof(float), st>>>(queries_dev, s.entities, s.d, s.row_begin, s.cand,
                                                                 s.count, s.cap);
@@ -475,7 +558,8 @@ static size_t carve_scorer(sert_scorer &sc, void *base, int64_t rows, int d, int
   sc.s.cand = reinterpret_cast<unsigned long long *>(take((size_t)max_queries * cap * sizeof(unsigned long long)));
   sc.s.tau = reinterpret_cast<unsigned long long *>(take((size_t)max_queries * sizeof(unsigned long long)));
   sc.s.count = reinterpret_cast<int *>(take((size_t)max_queries * sizeof(int)));
-  sc.s.overflow = reinterpret_cast<int *>(take(sizeof(int)));
+  sc.s.overflow = reinterpret_cast<int *>(take(2 * sizeof(int)));      // [1]: scratch of row_norm_max_kernel
+  sc.s.margin = reinterpret_cast<float *>(take((size_t)max_queries * sizeof(float)));
   sc.queries = reinterpret_cast<float *>(take((size_t)max_queries * d * sizeof(float)));
   sc.s.terms = 3;
   sc.s.kt = sc.s.terms * tc_padded_k(d);
@@ -529,16 +613,27 @@ int sert_scorer_create(const float *entities_host, int64_t rows, int32_t d, int6
     }
   }
   sc->s.mode = SCORE_TENSOR;
+  unsigned int norm_bits = 0u;
+  if (rows > 0) {
+    unsigned int *scratch = reinterpret_cast<unsigned int *>(sc->s.overflow + 1);
+    cudaMemsetAsync(scratch, 0, sizeof(unsigned int), sc->st);
+    row_norm_max_kernel<<<cdiv(rows, 8), 256, 0, sc->st>>>(sc->s.entities, rows, d, scratch);
+    count_launch();
+    cudaMemcpyAsync(&norm_bits, scratch, sizeof(unsigned int), cudaMemcpyDeviceToHost, sc->st);
+  }
   cudaError_t e = cudaStreamSynchronize(sc->st);
+  if (e == cudaSuccess) e = cudaGetLastError();
   if (e != cudaSuccess) { delete sc; set_error(cudaGetErrorString(e)); return -1; }
+  memcpy(&sc->s.ent_norm_max, &norm_bits, sizeof(float));
   *out = sc;
   return 0;
 }
 
 int sert_scorer_set_mode(sert_scorer *s, int32_t mode) {
   SERT_REQUIRE(s, "null scorer");
-  SERT_REQUIRE(mode == SCORE_FMA || mode == SCORE_TENSOR, "unknown scoring mode");
-  s->s.mode = mode;
+  SERT_REQUIRE(mode == SCORE_FMA || mode == SCORE_TENSOR || mode == 2, "unknown scoring mode");
+  s->s.coarse = mode == 2 ? 0 : 1;      // 2: tensor cores without the coarse first sweep (bf16x3 scores throughout)
+  s->s.mode = mode == 2 ? SCORE_TENSOR : mode;
   return 0;
 }
 

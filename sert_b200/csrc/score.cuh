@@ -29,6 +29,11 @@ struct TopkState {
   int kt = 0;
   __nv_bfloat16 *ent_split = nullptr;   // (rows, kt)
   __nv_bfloat16 *q_split = nullptr;     // (max_queries, kt)
+  // coarse-then-exact sweep (score.cu: topk_sweep): the hi.hi term alone selects candidates, with a per-query score
+  // margin that bounds its rounding error rigorously
+  int coarse = 1;
+  float *margin = nullptr;              // (max_queries,)
+  float ent_norm_max = 0.f;             // largest L2 norm of an entity row
 };
 
 int launch_normalise_rows(const float *in, float *out, int64_t rows, int d, cudaStream_t st);

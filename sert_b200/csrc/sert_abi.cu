@@ -293,14 +293,18 @@ static int pick_split_k(int M, int N, int K) {
 // dense update, optionally bracketed by CUDA events on the model's stream (profile mode)
 static int timed_update(sert_model &m, const OptimArgs &o, bool adam) {
   if (!m.profile) return adam ? launch_adam(o, m.st) : launch_adadelta(o, m.st);
+  // the events bracket the streaming kernel alone; the one-block loss finalisation follows outside them
   cudaEvent_t a, b;
   SERT_CUDA(cudaEventCreate(&a));
   SERT_CUDA(cudaEventCreate(&b));
+  OptimArgs k = o;
+  k.no_finalize = true;
   SERT_CUDA(cudaEventRecord(a, m.st));
-  const int rc = adam ? launch_adam(o, m.st) : launch_adadelta(o, m.st);
+  const int rc = adam ? launch_adam(k, m.st) : launch_adadelta(k, m.st);
   SERT_CUDA(cudaEventRecord(b, m.st));
   m.prof_events.emplace_back(a, b);
-  return rc;
+  if (rc) return rc;
+  return launch_finalize_train(o.acc, o.loss_out, o.inv_B, o.reg_coeff, m.st);
 }
 
 // ---- vector space: one training step on device-resident batch pointers --------------------------

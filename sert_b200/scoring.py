@@ -40,8 +40,10 @@ class EntityScorer(object):
         self.handle = handle
 
     def set_mode(self, mode):
-        """'tensor' (default: tcgen05 bf16x3 GEMM + exact fp32 re-scoring) or 'fma' (fp32 CUDA-core tiles)."""
-        N.check(self.lib.sert_scorer_set_mode(self.handle, {'fma': 0, 'tensor': 1}[mode]))
+        """'tensor' (default: one coarse bf16 tcgen05 GEMM with a rigorous score margin, exact fp32 re-scoring of the
+        survivors, automatic fall-back to 'tensor3' on too many near-ties), 'tensor3' (bf16x3 GEMM + fp32 re-scoring)
+        or 'fma' (fp32 CUDA-core tiles)."""
+        N.check(self.lib.sert_scorer_set_mode(self.handle, {'fma': 0, 'tensor': 1, 'tensor3': 2}[mode]))
 
     def close(self):
         if getattr(self, 'handle', None):

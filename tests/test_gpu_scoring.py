@@ -11,7 +11,7 @@ def exact_topk(E, q, k):
     return order, np.take_along_axis(s, order, axis=1)
 
 
-@pytest.mark.parametrize('mode', ['tensor', 'fma'])
+@pytest.mark.parametrize('mode', ['tensor', 'tensor3', 'fma'])
 @pytest.mark.parametrize('rows,d,Q,k', [(5000, 128, 37, 100), (12345, 256, 130, 10), (300, 64, 5, 100),
                                         (64, 32, 3, 64), (9000, 20, 65, 128), (20000, 300, 257, 100)])
 def test_topk_matches_exact(rows, d, Q, k, mode):
@@ -84,7 +84,7 @@ def test_merge_of_shards_equals_single_device():
     np.testing.assert_array_equal(os_.cpu().numpy(), full_score)
 
 
-@pytest.mark.parametrize('mode', ['tensor', 'fma'])
+@pytest.mark.parametrize('mode', ['tensor', 'tensor3', 'fma'])
 def test_adversarial_ascending_scores_take_the_exact_fallback(mode):
     """Scores that grow with the row id defeat the optimistic threshold (every later row survives): the
     candidate lists overflow and the sweep must fall back to the conservative, overflow-free pass."""
@@ -103,6 +103,41 @@ def test_adversarial_ascending_scores_take_the_exact_fallback(mode):
     np.testing.assert_allclose(score, ref_score, rtol=1e-6, atol=1e-6)
 
 
+def test_coarse_sweep_keeps_the_exact_top_k_among_near_ties():
+    """Rows whose exact scores differ by far less than the bf16 rounding error of the coarse sweep (1e-5 apart around
+    the k-th place): the margin must keep all of them for the fp32 re-scoring.  A second matrix has 6000 rows 1e-6
+    apart, all inside the margin band and more than a list holds: the coarse sweep overflows and the bf16x3 sweep
+    answers."""
+    from sert_b200.scoring import EntityScorer
+    rng = np.random.default_rng(12)
+    d, k = 64, 20
+    for band, step in ((300, 1e-5), (6000, 1e-6)):
+        rows = 20000
+        q = rng.standard_normal((4, d)).astype(np.float32)
+        q /= np.linalg.norm(q, axis=1)[:, None]
+        E = rng.standard_normal((rows, d)).astype(np.float32)
+        E /= np.linalg.norm(E, axis=1)[:, None] * 2.0            # background: scores in (-0.5, 0.5)
+        # a band of rows almost parallel to q[0], scores 0.9 + j * 1e-5 in shuffled row positions
+        pos = rng.choice(rows, band, replace=False)
+        noise = rng.standard_normal((band, d)).astype(np.float32)
+        noise -= (noise @ q[0])[:, None] * q[0][None, :]
+        noise /= np.linalg.norm(noise, axis=1)[:, None]
+        s = (0.9 + step * np.arange(band)).astype(np.float32)
+        E[pos] = s[:, None] * q[0][None, :] + np.sqrt(np.maximum(0, 0.98 - s * s))[:, None] * noise
+        sc = EntityScorer(E, max_queries=8, max_k=32)
+        idx, score = sc.topk(q, k)
+        ref_idx, ref_score = exact_topk(E, q, k)
+        np.testing.assert_allclose(score, ref_score, rtol=0, atol=2e-6)
+        gaps = np.abs(np.diff(ref_score, axis=1)).min(axis=1) > 1e-6
+        assert (idx[gaps] == ref_idx[gaps]).all()
+        assert set(idx[0].tolist()) <= set(pos.tolist())
+        # whatever the order inside fp32 noise, the returned SET is the exact top k up to score ties below 2e-6
+        kth = ref_score[0, -1]
+        exact0 = (q[0].astype(np.float64) @ E.astype(np.float64).T)
+        assert (exact0[idx[0]] >= kth - 2e-6).all()
+        sc.close()
+
+
 def test_randomised_shapes_match_exact():
     """Random (rows, d, Q, k) including rows < k, d that is no multiple of 4 / 64, Q above max_queries (chunked
     calls) and k at the scorer's max_k; both arithmetic modes."""
@@ -117,7 +152,7 @@ def test_randomised_shapes_match_exact():
         E = O.normalise_rows(rng.standard_normal((rows, d)))
         q = O.normalise_rows(rng.standard_normal((Q, d)))
         sc = EntityScorer(E, max_queries=32, max_k=100)
-        sc.set_mode('tensor' if trial % 2 == 0 else 'fma')
+        sc.set_mode(['tensor', 'fma', 'tensor3'][trial % 3])
         idx, score = sc.topk(q, k)
         kk = min(k, rows)
         ref_idx, ref_score = exact_topk(E, q, kk)

@@ -185,7 +185,7 @@ def test_pipelined_host_batches_match_resident_training(dims):
     nat = b._native
     out = N.ctypes.c_float(0)
     assert nat.lib.sert_train_host_wait(nat.handle, 0, N.ctypes.byref(out)) != 0
-    assert 'window' in N.last_error()
+    assert b'window' in N.load().sert_last_error()
     bad = p['Wp'].copy()
     bad[0, 0] = np.nan
     nat.set_tensor(N.PARAM_DENSE_W, bad)
