@@ -394,6 +394,10 @@ static int launch_prune(const TopkState &s, int Q, int k, int mode, int32_t *out
 // prune after each, so tau tightens early and later chunks append only ~k*chunk/seen rows per query; a list
 // that would overflow sets *overflow and the caller falls back to the conservative pass (chunk = cap/2 rows,
 // which cannot overflow even if every score of a chunk survives).
+// rows per launch once tau has warmed up: two 256-row n-tiles per SM (the B-stationary schedule of gemm_tc.cu
+// hands whole n-tiles to CTAs)
+constexpr long long kBigChunk = 2ll * kNumSMs * 256;
+
 static int topk_pass(const TopkState &s, const float *queries_dev, int Q, int k_sel, bool optimistic,
                      cudaStream_t st, bool coarse = false) {
   const bool tensor = s.mode == SCORE_TENSOR;
@@ -417,11 +421,13 @@ static int topk_pass(const TopkState &s, const float *queries_dev, int Q, int k_
                                                 s.cand, s.cap, s.overflow);
       SERT_LAUNCH_CHECK();
     }
-    // forced prune (mode 2) while tau is still loose or at the end; otherwise only lists more than half full
-    const bool force = optimistic || n1 == s.rows;
+    // forced prune (mode 2) while tau is still loose (the geometric warm-up) or at the end; otherwise only the
+    // lists more than a quarter full (a warmed-up tau lets ~k * chunk / seen rows through per chunk)
+    const bool warm = optimistic && chunk >= kBigChunk;
+    const bool force = (optimistic && !warm) || n1 == s.rows;
     if (launch_prune(s, Q, k_sel, force ? 2 : 0, nullptr, nullptr, st, coarse ? s.margin : nullptr)) return -1;
     n0 = n1;
-    if (optimistic) chunk = std::min<long long>(chunk * 4, 1 << 16);
+    if (optimistic) chunk = std::min<long long>(chunk * 4, kBigChunk);
   }
   return 0;
 }
