@@ -25,7 +25,9 @@ constexpr uint32_t STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
 constexpr int EPI_WARPS = 8;              // two warps per TMEM lane quarter, each owns half of the tile's columns
 constexpr int NUM_THREADS = 64 + 32 * EPI_WARPS;
 constexpr uint32_t TMEM_COLS = 512;
-constexpr size_t SMEM_BYTES = 1024 /*align slack*/ + (size_t)STAGES * STAGE_BYTES + 256 /*barriers*/;
+constexpr int STASH = 8;                  // survivors a lane can park in shared memory per tile (top-k epilogue)
+constexpr uint32_t STASH_BYTES = EPI_WARPS * 32 * STASH * 8;
+constexpr size_t SMEM_BYTES = 1024 /*align slack*/ + (size_t)STAGES * STAGE_BYTES + 256 /*barriers*/ + STASH_BYTES;
 
 struct alignas(64) TcMap {
   unsigned char bytes[128];
@@ -43,13 +45,18 @@ struct KernelArgs {
 // is loaded ONCE and stays in shared memory: at K = 256 a 128 x 256 tile needs 192 KB of operands for 2048 cycles of
 // MMA, more than L2 can feed all SMs (measured 8.8 TB/s of L2 reads, 6200 cycles per tile); keeping B resident
 // leaves the 64 KB A tile.  Needs num_kb <= STAGES (B of one n-tile fits in the B slots of the ring).
+// The CTAs start their sweeps at different m-tiles (blockIdx.x apart): 148 SMs asking L2 for the same A tile at the
+// same moment queue up on the slices that hold its lines (measured: 10.3 k cycles per tile unstaggered).
+// seq = position inside the n-tile's sweep (0 = first, num_m_tiles - 1 = last).
 template <bool BSTAT>
-__device__ __forceinline__ bool cta_tile(int it, int num_m_tiles, int num_n_tiles, int &mt, int &nt) {
+__device__ __forceinline__ bool cta_tile(int it, int num_m_tiles, int num_n_tiles, int &mt, int &nt, int &seq) {
   if (BSTAT) {
     nt = blockIdx.x + (it / num_m_tiles) * gridDim.x;
-    mt = it % num_m_tiles;
+    seq = it % num_m_tiles;
+    mt = (seq + blockIdx.x) % num_m_tiles;
     return nt < num_n_tiles;
   }
+  seq = 0;
   const long long t = blockIdx.x + (long long)it * gridDim.x;
   mt = (int)(t % num_m_tiles);
   nt = (int)(t / num_m_tiles);
@@ -163,6 +170,7 @@ gemm_tc_kernel(const __grid_constant__ TcMap map_a, const __grid_constant__ TcMa
   const uint32_t tmem_ptr_smem = bars + 8u * (2 * STAGES + 4);
   const uint32_t bfull_bar = bars + 8u * (2 * STAGES + 5);    // BSTAT: the n-tile's B blocks have landed
   const uint32_t bempty_bar = bars + 8u * (2 * STAGES + 6);   // BSTAT: every MMA of the n-tile has retired
+  const uint32_t stash_base = bars + 256u;                    // top-k epilogue: STASH keys per epilogue thread
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -197,11 +205,11 @@ gemm_tc_kernel(const __grid_constant__ TcMap map_a, const __grid_constant__ TcMa
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0, bphase = 0;
-      int mt, nt;
-      for (int it = 0; cta_tile<BSTAT>(it, num_m_tiles, num_n_tiles, mt, nt); ++it) {
+      int mt, nt, seq;
+      for (int it = 0; cta_tile<BSTAT>(it, num_m_tiles, num_n_tiles, mt, nt, seq); ++it) {
         const int m0 = mt * BM;
         const int n0 = (int)(args.n_begin + (long long)nt * BN);
-        if (BSTAT && mt == 0) {
+        if (BSTAT && seq == 0) {
           mbar_wait(bempty_bar, bphase ^ 1u);            // the previous n-tile's MMAs no longer read the B slots
           mbar_expect_tx(bfull_bar, (uint32_t)args.num_kb * B_STAGE_BYTES);
           for (int kb = 0; kb < args.num_kb; ++kb)
@@ -225,9 +233,9 @@ gemm_tc_kernel(const __grid_constant__ TcMap map_a, const __grid_constant__ TcMa
       uint32_t phase = 0;
       int acc = 0;
       uint32_t acc_phase = 0, bphase = 0;
-      int mt, nt;
-      for (int it = 0; cta_tile<BSTAT>(it, num_m_tiles, num_n_tiles, mt, nt); ++it) {
-        if (BSTAT && mt == 0) {
+      int mt, nt, seq;
+      for (int it = 0; cta_tile<BSTAT>(it, num_m_tiles, num_n_tiles, mt, nt, seq); ++it) {
+        if (BSTAT && seq == 0) {
           mbar_wait(bfull_bar, bphase);                  // this n-tile's B blocks have landed
           bphase ^= 1u;
         }
@@ -249,7 +257,7 @@ gemm_tc_kernel(const __grid_constant__ TcMap map_a, const __grid_constant__ TcMa
           if (++stage == STAGES) { stage = 0; phase ^= 1u; }
         }
         tc_commit(tfull_bar(acc));                       // accumulator complete -> epilogue
-        if (BSTAT && mt == num_m_tiles - 1) tc_commit(bempty_bar);   // ... and the B slots are free once it is
+        if (BSTAT && seq == num_m_tiles - 1) tc_commit(bempty_bar);   // ... and the B slots are free once it is
         if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
       }
     }
@@ -262,8 +270,8 @@ gemm_tc_kernel(const __grid_constant__ TcMap map_a, const __grid_constant__ TcMa
     int acc = 0;
     uint32_t acc_phase = 0;
     const TcEpilogue &ep = args.epi;
-    int mt, nt;
-    for (int it = 0; cta_tile<BSTAT>(it, num_m_tiles, num_n_tiles, mt, nt); ++it) {
+    int mt, nt, seq;
+    for (int it = 0; cta_tile<BSTAT>(it, num_m_tiles, num_n_tiles, mt, nt, seq); ++it) {
       const int m0 = mt * BM;
       const long long n0 = args.n_begin + (long long)nt * BN;
       const int gm = m0 + row;
@@ -310,9 +318,12 @@ gemm_tc_kernel(const __grid_constant__ TcMap map_a, const __grid_constant__ TcMa
       } else {
         // ---- running top-k filter.  The chunk loops stay rolled: the epilogue's code must stay resident in
         // the instruction caches (a fully unrolled two-pass version measured 6x slower: the warps sat in
-        // "no instruction" stalls).  Pass 1 counts this row's survivors, one compare per score.
+        // "no instruction" stalls).  Pass 1 counts this row's survivors, one compare per score, and parks the
+        // first STASH of them as keys in shared memory: reading the accumulator once is all the TMEM bandwidth
+        // a K = 256 tile leaves (a tile's 128 KB at 64 B/cycle = its 2048 cycles of MMA).
         int total = 0;
         uint32_t chunk_any = 0;                                          // warp-uniform: chunks with a survivor
+        const uint32_t my_stash = stash_base + (uint32_t)(((warp - 2) * 32 + lane) * STASH) * 8u;
 #pragma unroll 1
         for (int ci = 0; ci < CHUNKS; ++ci) {
           uint32_t v[32];
@@ -323,11 +334,44 @@ gemm_tc_kernel(const __grid_constant__ TcMap map_a, const __grid_constant__ TcMa
           int cnt = 0;
 #pragma unroll
           for (int j = 0; j < 32; ++j) cnt += (j < nv && __uint_as_float(v[j]) > tau_score) ? 1 : 0;
+          if (cnt > 0) {                                                 // rare once tau has warmed up
+            int at = total;
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              if (j < nv && __uint_as_float(v[j]) > tau_score) {
+                if (at < STASH) {
+                  const unsigned long long key = make_key(
+                      __uint_as_float(v[j]), (unsigned int)(n0 + col_lo + ci * 32 + j + ep.row_offset));
+                  asm volatile("st.shared.b64 [%0], %1;" ::"r"(my_stash + (uint32_t)at * 8u), "l"(key) : "memory");
+                }
+                ++at;
+              }
+            }
+          }
           total += cnt;
           chunk_any |= (__any_sync(0xffffffffu, cnt > 0) ? 1u : 0u) << ci;
         }
-        // Pass 2 (rare once tau has warmed up): ONE atomic per thread reserves its slots, then TMEM is read
-        // again.  tcgen05.ld is warp-collective (.sync.aligned), so the chunk loop is warp-uniform; only the
+        if (!__any_sync(0xffffffffu, total > STASH)) {
+          // Everything this warp keeps sits in shared memory: hand the accumulator back to the MMA warp FIRST,
+          // then reserve list slots (one returning atomic per lane, ~1 us) and copy the keys out.
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(tempty_bar(acc));
+          if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+          if (total > 0) {
+            unsigned long long *list = ep.cand + (size_t)gm * ep.cap;
+            const int pos = atomicAdd(ep.count + gm, total);
+            if (pos + total > ep.cap) *ep.overflow = 1;
+            for (int i = 0; i < total; ++i) {
+              unsigned long long key;
+              asm volatile("ld.shared.b64 %0, [%1];" : "=l"(key) : "r"(my_stash + (uint32_t)i * 8u) : "memory");
+              if (pos + i < ep.cap) list[pos + i] = key;
+            }
+          }
+          continue;
+        }
+        // Pass 2 (cold tau: the first chunks of a sweep): ONE atomic per thread reserves its slots, then TMEM is
+        // read again.  tcgen05.ld is warp-collective (.sync.aligned), so the chunk loop is warp-uniform; only the
         // per-lane key stores diverge.
         if (chunk_any != 0u) {
           int pos = 0;
