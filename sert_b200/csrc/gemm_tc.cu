@@ -26,7 +26,7 @@ constexpr int EPI_WARPS = 8;              // two warps per TMEM lane quarter, ea
 constexpr int NUM_THREADS = 64 + 32 * EPI_WARPS;
 constexpr uint32_t TMEM_COLS = 512;
 constexpr int STASH = 8;                  // survivors a lane can park in shared memory per tile (top-k epilogue)
-constexpr uint32_t STASH_BYTES = EPI_WARPS * 32 * STASH * 8;
+constexpr uint32_t STASH_BYTES = 2 * EPI_WARPS * 32 * STASH * 8;   // two buffers: this tile's and the previous one's
 constexpr size_t SMEM_BYTES = 1024 /*align slack*/ + (size_t)STAGES * STAGE_BYTES + 256 /*barriers*/ + STASH_BYTES;
 
 struct alignas(64) TcMap {
@@ -270,6 +270,22 @@ gemm_tc_kernel(const __grid_constant__ TcMap map_a, const __grid_constant__ TcMa
     int acc = 0;
     uint32_t acc_phase = 0;
     const TcEpilogue &ep = args.epi;
+    // top-k epilogue: the keys parked by the PREVIOUS tile wait for their list slots (pend_pos is the result of an
+    // atomicAdd issued one tile ago: its ~1 us round trip runs under this tile's accumulator read)
+    int pend_total = 0, pend_pos = 0, pend_gm = 0, stash_buf = 0;
+    auto flush_pending = [&]() {
+      if (pend_total > 0) {
+        if (pend_pos + pend_total > ep.cap) *ep.overflow = 1;
+        unsigned long long *list = ep.cand + (size_t)pend_gm * ep.cap;
+        const uint32_t src = stash_base + (uint32_t)((((stash_buf ^ 1) * EPI_WARPS + (warp - 2)) * 32 + lane) * STASH) * 8u;
+        for (int i = 0; i < pend_total; ++i) {
+          unsigned long long key;
+          asm volatile("ld.shared.b64 %0, [%1];" : "=l"(key) : "r"(src + (uint32_t)i * 8u) : "memory");
+          if (pend_pos + i < ep.cap) list[pend_pos + i] = key;
+        }
+      }
+      pend_total = 0;
+    };
     int mt, nt, seq;
     for (int it = 0; cta_tile<BSTAT>(it, num_m_tiles, num_n_tiles, mt, nt, seq); ++it) {
       const int m0 = mt * BM;
@@ -323,7 +339,7 @@ gemm_tc_kernel(const __grid_constant__ TcMap map_a, const __grid_constant__ TcMa
         // a K = 256 tile leaves (a tile's 128 KB at 64 B/cycle = its 2048 cycles of MMA).
         int total = 0;
         uint32_t chunk_any = 0;                                          // warp-uniform: chunks with a survivor
-        const uint32_t my_stash = stash_base + (uint32_t)(((warp - 2) * 32 + lane) * STASH) * 8u;
+        const uint32_t my_stash = stash_base + (uint32_t)(((stash_buf * EPI_WARPS + (warp - 2)) * 32 + lane) * STASH) * 8u;
 #pragma unroll 1
         for (int ci = 0; ci < CHUNKS; ++ci) {
           uint32_t v[32];
@@ -352,24 +368,23 @@ gemm_tc_kernel(const __grid_constant__ TcMap map_a, const __grid_constant__ TcMa
           chunk_any |= (__any_sync(0xffffffffu, cnt > 0) ? 1u : 0u) << ci;
         }
         if (!__any_sync(0xffffffffu, total > STASH)) {
-          // Everything this warp keeps sits in shared memory: hand the accumulator back to the MMA warp FIRST,
-          // then reserve list slots (one returning atomic per lane, ~1 us) and copy the keys out.
+          // Everything this warp keeps sits in shared memory: hand the accumulator back to the MMA warp, copy out
+          // the previous tile's keys (their slots were reserved a tile ago), reserve this tile's slots.
           tc_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive(tempty_bar(acc));
           if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+          flush_pending();                                // previous tile's keys: buffer stash_buf ^ 1
           if (total > 0) {
-            unsigned long long *list = ep.cand + (size_t)gm * ep.cap;
-            const int pos = atomicAdd(ep.count + gm, total);
-            if (pos + total > ep.cap) *ep.overflow = 1;
-            for (int i = 0; i < total; ++i) {
-              unsigned long long key;
-              asm volatile("ld.shared.b64 %0, [%1];" : "=l"(key) : "r"(my_stash + (uint32_t)i * 8u) : "memory");
-              if (pos + i < ep.cap) list[pos + i] = key;
-            }
+            pend_pos = atomicAdd(ep.count + gm, total);
+            pend_total = total;
+            pend_gm = gm;
           }
+          stash_buf ^= 1;                                 // this tile's keys now sit in the "previous" buffer
           continue;
         }
+        // cold tau: finish the previous tile's keys first, then the two-pass path below
+        flush_pending();
         // Pass 2 (cold tau: the first chunks of a sweep): ONE atomic per thread reserves its slots, then TMEM is
         // read again.  tcgen05.ld is warp-collective (.sync.aligned), so the chunk loop is warp-uniform; only the
         // per-lane key stores diverge.
@@ -406,6 +421,7 @@ gemm_tc_kernel(const __grid_constant__ TcMap map_a, const __grid_constant__ TcMa
       if (lane == 0) mbar_arrive(tempty_bar(acc));
       if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
     }
+    flush_pending();
   }
 
   tc_fence_before();
