@@ -347,25 +347,39 @@ gemm_tc_kernel(const __grid_constant__ TcMap map_a, const __grid_constant__ TcMa
           tc_wait_ld();
           const long long left = args.n_end - (n0 + col_lo + ci * 32);          // valid columns in this chunk
           const int nv = left >= 32 ? 32 : (left <= 0 ? 0 : (int)left);
-          int cnt = 0;
+          // One max-reduction per chunk instead of 32 compares feeding a dependent count: the two epilogue warps of
+          // a scheduler issue ~150 instead of ~1400 instructions per tile (ncu: the epilogue was issue-bound on
+          // dependent integer adds, 7 k cycles per tile against 2 k cycles of MMA at K = 256).
+          float mx = -INFINITY;
+          if (nv == 32) {
+            float m16[16];
 #pragma unroll
-          for (int j = 0; j < 32; ++j) cnt += (j < nv && __uint_as_float(v[j]) > tau_score) ? 1 : 0;
-          if (cnt > 0) {                                                 // rare once tau has warmed up
-            int at = total;
+            for (int j = 0; j < 16; ++j) m16[j] = fmaxf(__uint_as_float(v[2 * j]), __uint_as_float(v[2 * j + 1]));
+#pragma unroll
+            for (int j = 0; j < 8; ++j) m16[j] = fmaxf(m16[2 * j], m16[2 * j + 1]);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) m16[j] = fmaxf(m16[2 * j], m16[2 * j + 1]);
+            mx = fmaxf(fmaxf(m16[0], m16[1]), fmaxf(m16[2], m16[3]));
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (j < nv) mx = fmaxf(mx, __uint_as_float(v[j]));
+          }
+          const bool hit = mx > tau_score;
+          if (hit) {                                                     // rare once tau has warmed up
 #pragma unroll
             for (int j = 0; j < 32; ++j) {
               if (j < nv && __uint_as_float(v[j]) > tau_score) {
-                if (at < STASH) {
+                if (total < STASH) {
                   const unsigned long long key = make_key(
                       __uint_as_float(v[j]), (unsigned int)(n0 + col_lo + ci * 32 + j + ep.row_offset));
-                  asm volatile("st.shared.b64 [%0], %1;" ::"r"(my_stash + (uint32_t)at * 8u), "l"(key) : "memory");
+                  asm volatile("st.shared.b64 [%0], %1;" ::"r"(my_stash + (uint32_t)total * 8u), "l"(key) : "memory");
                 }
-                ++at;
+                ++total;
               }
             }
           }
-          total += cnt;
-          chunk_any |= (__any_sync(0xffffffffu, cnt > 0) ? 1u : 0u) << ci;
+          chunk_any |= (__any_sync(0xffffffffu, hit) ? 1u : 0u) << ci;
         }
         if (!__any_sync(0xffffffffu, total > STASH)) {
           // Everything this warp keeps sits in shared memory: hand the accumulator back to the MMA warp, copy out
