@@ -296,17 +296,6 @@ gemm_tc_kernel(const __grid_constant__ TcMap map_a, const __grid_constant__ TcMa
       pend_total = 0;
     };
     int mt, nt, seq;
-    // this row's threshold for tile `it2`, fetched one tile ahead (an L2 round trip per tile otherwise sits at the
-    // head of the epilogue's critical path)
-    auto load_tau = [&](int it2) -> unsigned long long {
-      int mt2, nt2, seq2;
-      if (ep.mode == TC_EPI_TOPK && cta_tile<BSTAT>(it2, num_m_tiles, num_n_tiles, mt2, nt2, seq2)) {
-        const int gm2 = mt2 * BM + row;
-        if (gm2 < args.M) return __ldg(ep.tau + gm2);
-      }
-      return 0ull;
-    };
-    unsigned long long tau_next = load_tau(0);
     for (int it = 0; cta_tile<BSTAT>(it, num_m_tiles, num_n_tiles, mt, nt, seq); ++it) {
       const int m0 = mt * BM;
       const long long n0 = args.n_begin + (long long)nt * BN;
@@ -315,8 +304,10 @@ gemm_tc_kernel(const __grid_constant__ TcMap map_a, const __grid_constant__ TcMa
       // Rows are swept in increasing id order and tau only moves between launches, so a later row that
       // ties tau's score has a larger id (= a smaller key): `score > tau_score` is the exact key test.
       float tau_score = INFINITY;
-      if (ep.mode == TC_EPI_TOPK && row_ok) tau_score = tau_next == 0ull ? -INFINITY : key_score(tau_next);
-      tau_next = load_tau(it + 1);
+      if (ep.mode == TC_EPI_TOPK && row_ok) {
+        const unsigned long long tau_key = ep.tau[gm];
+        tau_score = tau_key == 0ull ? -INFINITY : key_score(tau_key);
+      }
       mbar_wait(tfull_bar(acc), acc_phase);
       tc_fence_after();
       const uint32_t t_row = tmem_base + (uint32_t)acc * BN + ((uint32_t)(quarter * 32) << 16);
@@ -358,7 +349,11 @@ gemm_tc_kernel(const __grid_constant__ TcMap map_a, const __grid_constant__ TcMa
         int total = 0;
         uint32_t chunk_any = 0;                                          // warp-uniform: chunks with a survivor
         const uint32_t my_stash = stash_base + (uint32_t)(((stash_buf * EPI_WARPS + (warp - 2)) * 32 + lane) * STASH) * 8u;
-        auto process = [&](const uint32_t (&v)[32], int ci) {
+#pragma unroll 1
+        for (int ci = 0; ci < CHUNKS; ++ci) {
+          uint32_t v[32];
+          tc_ld_32x32(t_row + (uint32_t)(col_lo + ci * 32), v);
+          tc_wait_ld();
           const long long left = args.n_end - (n0 + col_lo + ci * 32);          // valid columns in this chunk
           const int nv = left >= 32 ? 32 : (left <= 0 ? 0 : (int)left);
           // One max-reduction per chunk instead of 32 compares feeding a dependent count: the two epilogue warps of
@@ -390,19 +385,6 @@ gemm_tc_kernel(const __grid_constant__ TcMap map_a, const __grid_constant__ TcMa
             }
           }
           chunk_any |= (__any_sync(0xffffffffu, hit) ? 1u : 0u) << ci;
-        };
-        // the accumulator read of chunk ci+1 is in flight while chunk ci is examined
-        static_assert(CHUNKS % 2 == 0, "chunks are processed in pairs");
-        uint32_t va[32], vb[32];
-        tc_ld_32x32(t_row + (uint32_t)col_lo, va);
-#pragma unroll 1
-        for (int ci = 0; ci < CHUNKS; ci += 2) {
-          tc_wait_ld();
-          tc_ld_32x32(t_row + (uint32_t)(col_lo + (ci + 1) * 32), vb);
-          process(va, ci);
-          tc_wait_ld();
-          if (ci + 2 < CHUNKS) tc_ld_32x32(t_row + (uint32_t)(col_lo + (ci + 2) * 32), va);
-          process(vb, ci + 1);
         }
         if (!__any_sync(0xffffffffu, total > STASH)) {
           // Everything this warp keeps sits in shared memory: hand the accumulator back to the MMA warp, copy out
