@@ -153,15 +153,6 @@ constexpr uint32_t make_idesc(int m, int n) {
   return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
 }
 
-// parks one surviving (score, row) key in the lane's shared-memory stash; returns the new survivor count
-__device__ __noinline__ int stash_key(uint32_t stash, int total, float score, unsigned int row) {
-  if (total < STASH) {
-    const unsigned long long key = make_key(score, row);
-    asm volatile("st.shared.b64 [%0], %1;" ::"r"(stash + (uint32_t)total * 8u), "l"(key) : "memory");
-  }
-  return total + 1;
-}
-
 // ---- the kernel -----------------------------------------------------------------------------------
 template <bool BSTAT>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
@@ -378,10 +369,14 @@ gemm_tc_kernel(const __grid_constant__ TcMap map_a, const __grid_constant__ TcMa
           if (hit) {                                                     // rare once tau has warmed up
 #pragma unroll
             for (int j = 0; j < 32; ++j) {
-              // a real call: predicated-off inline bodies would still cost their ~10 issue slots per column
-              if (j < nv && __uint_as_float(v[j]) > tau_score)
-                total = stash_key(my_stash, total, __uint_as_float(v[j]),
-                                  (unsigned int)(n0 + col_lo + ci * 32 + j + ep.row_offset));
+              if (j < nv && __uint_as_float(v[j]) > tau_score) {
+                if (total < STASH) {
+                  const unsigned long long key = make_key(
+                      __uint_as_float(v[j]), (unsigned int)(n0 + col_lo + ci * 32 + j + ep.row_offset));
+                  asm volatile("st.shared.b64 [%0], %1;" ::"r"(my_stash + (uint32_t)total * 8u), "l"(key) : "memory");
+                }
+                ++total;
+              }
             }
           }
           chunk_any |= (__any_sync(0xffffffffu, hit) ? 1u : 0u) << ci;
