@@ -42,6 +42,17 @@ def measured_peaks():
     return 6650.0, 'fallback (B200_PROFILING.md)'
 
 
+def measured_tensor_peak():
+    """Sustained dense bf16 TFLOP/s of this pool's B200s (a scoring sweep is a long tensor-core job)."""
+    path = os.path.join(ROOT, 'MEASURED_PEAKS.json')
+    if os.path.exists(path):
+        with open(path) as f:
+            d = json.load(f)
+        if 'bf16_tflops_sustained' in d:
+            return float(d['bf16_tflops_sustained']), 'measured (MEASURED_PEAKS.json bf16_tflops_sustained)'
+    return 1374.0, 'fallback (B200_PROFILING.md)'
+
+
 class ClockSampler(object):
     """Samples nvidia-smi clocks / throttle reasons while the timed region runs."""
 
@@ -401,7 +412,12 @@ def run_scoring(sc, label, rank, world, barrier, cpu):
                        % (label, sc['Q'], sc['E'], sc['d'], sc['k'], world),
            'ms': ms, 'e2e_value': sc['Q'] * sc['E'] / e2e_s,
            'algorithmic_tflops': 2.0 * sc['Q'] * sc['E'] * sc['d'] / (ms * 1e-3) / 1e12,
-           'tensor_tflops_bf16x3': 6.0 * sc['Q'] * sc['E'] * sc['d'] / (ms * 1e-3) / 1e12}
+           'arithmetic': 'coarse-then-exact: one bf16 tcgen05 GEMM (2*Q*E*d flops) with a rigorous rounding-error '
+                         'margin, fp32 re-scoring of the survivors; returned lists are the exact fp32 top-k'}
+    tpeak, tsrc = measured_tensor_peak()
+    out['roofline'] = {'bound': 'tensor', 'kernel': 'gemm_tc_kernel + top-k epilogue (csrc/gemm_tc.cu), whole sweep',
+                       'achieved': out['algorithmic_tflops'], 'peak': tpeak, 'unit': 'TFLOP/s',
+                       'frac': out['algorithmic_tflops'] / tpeak, 'peak_source': tsrc, 'traffic': None}
     if cpu and world == 1:
         out['cpu_baseline'] = scoring_cpu_baseline(ent, qs, sc['k'])
     scorer.local.close()

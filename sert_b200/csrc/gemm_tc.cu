@@ -519,11 +519,13 @@ int launch_gemm_tc_ld(const __nv_bfloat16 *A, long long lda, int M, const __nv_b
   args.epi = epi;
   const long long m_tiles = (M + BM - 1) / BM, n_tiles = (n_end - n_begin + BN - 1) / BN;
   const long long tiles = m_tiles * n_tiles;
-  // B-stationary schedule: K fits the ring's B slots, every CTA gets an n-tile, enough m-tiles to amortise the load
-  // of B (one bubble per n-tile), and whole n-tiles balance at least as well as single tiles would
+  // B-stationary schedule (opt-in, SERT_GEMM_BSTAT=1): K fits the ring's B slots, every CTA gets an n-tile, enough
+  // m-tiles to amortise the load of B (one bubble per n-tile), and whole n-tiles balance at least as well as single
+  // tiles would.  Measured at BASELINE configs[3] it is 2-3 % SLOWER than the classic order (8.86 vs 8.62 ms): the
+  // top-k epilogue, not L2, paces the K = 256 tiles (ncu: tensor pipe 37 % active, L2 11 %), so it stays off.
   const long long per_cta = (n_tiles + sms - 1) / sms;
   const bool bstat = args.num_kb <= STAGES && m_tiles >= 8 && n_tiles >= sms &&
-                     per_cta * sms * 10 <= n_tiles * 12 && getenv("SERT_GEMM_CLASSIC") == nullptr;
+                     per_cta * sms * 10 <= n_tiles * 12 && getenv("SERT_GEMM_BSTAT") != nullptr;
   if (bstat) {
     gemm_tc_kernel<true><<<(int)std::min<long long>(n_tiles, sms), NUM_THREADS, SMEM_BYTES, st>>>(ma, mb, args);
     SERT_LAUNCH_CHECK();
