@@ -10,6 +10,7 @@ What runs unmodified from /root/reference:
   * sert/inference.py, sert/math_utils.py                       (pure numpy; run as they are)
   * bin/query.py  callbacks   (LogLinearCallback, VectorSpaceCallback, compute_normalised_entropy)
   * bin/train.py  sparse_to_one_hot_multiple
+  * bin/prepare.py instances_and_labels_to_arrays (and the w_train expression of main(), :395-399)
   * cvangysel-common trec_utils.parse_query / parse_topics / write_run
 Third-party modules the reference imports but this path never calls (bs4, nltk, gensim) are
 stubbed with empty modules; cvangysel.sklearn_utils.neighbors_algorithm, which crashes on modern sklearn
@@ -40,7 +41,7 @@ class _Stub(types.ModuleType):
         return type(item, (object,), {})
 
 
-for name in ('bs4', 'nltk', 'nltk.probability', 'nltk.corpus', 'gensim'):
+for name in ('bs4', 'nltk', 'nltk.probability', 'nltk.corpus', 'gensim', 'sklearn.cross_validation'):
     sys.modules.setdefault(name, _Stub(name))
 sys.modules['nltk'].probability = sys.modules['nltk.probability']
 sys.modules['nltk'].corpus = sys.modules['nltk.corpus']
@@ -70,6 +71,7 @@ def load_script(name):
 
 ref_query = load_script('query')
 ref_train = load_script('train')
+ref_prepare = load_script('prepare')
 
 from sert_b200 import synth  # noqa: E402
 
@@ -231,6 +233,38 @@ def gen_one_hot():
     np.savez_compressed(os.path.join(HERE, 'one_hot_ref.npz'), **out)
 
 
+def gen_prepare():
+    """bin/prepare.py:543-599 on a seeded list of (doc_id, window, label) instances, shuffled and not."""
+    rng = np.random.default_rng(20160816 + 31)
+    n, W, V, n_ent = 240, 5, 70000, 14           # V > 65536: uint32 instances like BASELINE configs[1]
+    entity_ids = ['ent-%02d' % i for i in range(n_ent)]
+    class_mapping = {e: i for i, e in enumerate(rng.permutation(entity_ids).tolist())}
+    docs = ['doc%03d' % i for i in range(40)]
+    instances = []
+    for i in range(n):
+        k = int(rng.choice([1, 2, 3, 5], p=[0.6, 0.2, 0.15, 0.05]))
+        ents = rng.choice(n_ent, k, replace=False)
+        label = {entity_ids[int(e)]: 1.0 / k for e in ents}
+        instances.append((docs[int(rng.integers(0, len(docs)))], tuple(int(v) for v in rng.integers(0, V, W)), label))
+    per_doc = {}
+    for doc_id, _, _ in instances:
+        per_doc[doc_id] = per_doc.get(doc_id, 0) + 1
+    max_len = max(per_doc.values())
+    out = {'window_size': W, 'num_words': V, 'class_mapping': class_mapping, 'max_document_length': max_len,
+           'instances': [[d, list(w), sorted(l.items())] for d, w, l in instances], 'cases': {}}
+    for shuffle in (False, True):
+        inst = list(instances)
+        np.random.seed(4711)
+        x, y = ref_prepare.instances_and_labels_to_arrays(inst, W, class_mapping, np.min_scalar_type(V - 1), shuffle)
+        w = np.fromiter((float(max_len) / per_doc[doc_id] for doc_id, _, _ in inst), np.float32, len(inst))
+        out['cases']['shuffle' if shuffle else 'ordered'] = {
+            'x': x.tolist(), 'x_dtype': str(x.dtype), 'indptr': y.indptr.tolist(), 'indices': y.indices.tolist(),
+            'data': [float(v) for v in y.data], 'y_dtype': str(y.dtype), 'indices_dtype': str(y.indices.dtype),
+            'shape': list(y.shape), 'w': [float(v) for v in w]}
+    with open(os.path.join(HERE, 'prepare_ref.json'), 'w') as f:
+        json.dump(out, f)
+
+
 def gen_query_callbacks():
     """The reference's ranking callbacks on synthetic predict_fn outputs."""
     rng = np.random.default_rng(505)
@@ -283,6 +317,7 @@ if __name__ == '__main__':
     gen_inference()
     gen_trec()
     gen_one_hot()
+    gen_prepare()
     gen_query_callbacks()
     print('golden fixtures written to', HERE)
     for f in sorted(os.listdir(HERE)):

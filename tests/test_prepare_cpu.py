@@ -1,0 +1,75 @@
+"""sert_b200/prepare.py (the packing step that feeds the hot path) against the fixture made
+by running the reference's own bin/prepare.py::instances_and_labels_to_arrays (tests/golden/make_golden.py)."""
+import json
+import os
+import pickle
+
+import numpy as np
+import pytest
+from scipy import sparse
+
+from sert_b200 import prepare
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+@pytest.fixture(scope='module')
+def ref():
+    with open(os.path.join(HERE, 'golden', 'prepare_ref.json')) as f:
+        d = json.load(f)
+    d['instances'] = [(doc, tuple(w), dict((e, m) for e, m in label)) for doc, w, label in d['instances']]
+    return d
+
+
+@pytest.mark.parametrize('case', ['ordered', 'shuffle'])
+def test_instances_and_labels_to_arrays_matches_reference(ref, case):
+    inst = list(ref['instances'])
+    np.random.seed(4711)                      # the reference shuffles with the global numpy RNG
+    dtype = np.min_scalar_type(ref['num_words'] - 1)
+    x, y = prepare.instances_and_labels_to_arrays(inst, ref['window_size'], ref['class_mapping'], dtype,
+                                                  case == 'shuffle')
+    c = ref['cases'][case]
+    assert str(x.dtype) == c['x_dtype'] == 'uint32'
+    np.testing.assert_array_equal(x, np.array(c['x'], dtype=dtype))
+    assert sparse.isspmatrix_csr(y) and list(y.shape) == c['shape']
+    assert str(y.dtype) == c['y_dtype'] and str(y.indices.dtype) == c['indices_dtype']
+    np.testing.assert_array_equal(y.indptr, c['indptr'])
+    np.testing.assert_array_equal(y.indices, c['indices'])
+    np.testing.assert_array_equal(y.data, np.array(c['data'], dtype=np.float32))
+    per_doc = {}
+    for doc_id, _, _ in inst:
+        per_doc[doc_id] = per_doc.get(doc_id, 0) + 1
+    w = prepare.instance_weights(inst, per_doc, ref['max_document_length'])
+    assert w.dtype == np.float32
+    np.testing.assert_array_equal(w, np.array(c['w'], dtype=np.float32))
+
+
+def test_edge_cases_and_file_round_trip(ref, tmp_path):
+    # empty instance list: (0, W) / (0, E) like the reference's fromiter / csr_matrix on empty inputs
+    x, y = prepare.instances_and_labels_to_arrays([], 3, {'a': 0, 'b': 1}, np.uint16, shuffle=False)
+    assert x.shape == (0, 3) and x.dtype == np.uint16 and y.shape == (0, 2) and y.nnz == 0
+    # uint32 above 65 536 words / uint16 up to there; entity indexing drops entities without instances, in order
+    packed = prepare.pack(list(ref['instances'][:50]), list(ref['instances'][50:60]), ref['window_size'],
+                          ref['num_words'], {'ent-%02d' % i: (i % 3) for i in range(14)}, shuffle=False)
+    assert packed['x_train'].dtype == np.uint32 and packed['x_train'].shape == (50, ref['window_size'])
+    small = prepare.pack([('d', (1, 2), {'ent-01': 1.0})], [('d', (3, 4), {'ent-02': 1.0})], 2, 65536,
+                         {'ent-01': 1, 'ent-02': 1}, instances_per_document={'d': 2}, max_document_length=4)
+    assert small['x_train'].dtype == np.uint16 and small['w_train'].tolist() == [2.0]
+    kept = [e for e in ('ent-%02d' % i for i in range(14)) if int(e[-2:]) % 3]
+    assert [packed['entity_indices_inv'][i] for i in range(len(kept))] == kept
+    # data.npz / meta round trip in the formats bin/train.py and bin/query.py read
+    c = ref['cases']['ordered']
+    y = sparse.csr_matrix((np.array(c['data'], np.float32), np.array(c['indices']), np.array(c['indptr'])),
+                          shape=c['shape'])
+    xs = np.array(c['x'], dtype=np.uint32)
+    w = np.array(c['w'], dtype=np.float32)
+    data_path, meta_path = str(tmp_path / 'data.npz'), str(tmp_path / 'meta')
+    prepare.write_data(data_path, xs, y, xs[:7], y[:7], w_train=w)
+    loaded = np.load(data_path, allow_pickle=True)
+    assert list(loaded.keys()) == ['x_train', 'y_train', 'w_train', 'x_validate', 'y_validate']
+    np.testing.assert_array_equal(loaded['x_train'], xs)
+    assert (loaded['y_train'].item() != y).nnz == 0 and loaded['y_validate'].item().shape == (7, c['shape'][1])
+    prepare.write_meta(meta_path, {'window_size': 5}, {'w': (0, 3)}, ['w'], {0: 'ent-00'}, {'ent-00': ['doc000']})
+    with open(meta_path, 'rb') as f:
+        objs = [pickle.load(f) for _ in range(5)]
+    assert objs[3] == {0: 'ent-00'} and prepare.read_meta(meta_path)[2] == ['w']
