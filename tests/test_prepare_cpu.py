@@ -49,14 +49,20 @@ def test_edge_cases_and_file_round_trip(ref, tmp_path):
     x, y = prepare.instances_and_labels_to_arrays([], 3, {'a': 0, 'b': 1}, np.uint16, shuffle=False)
     assert x.shape == (0, 3) and x.dtype == np.uint16 and y.shape == (0, 2) and y.nnz == 0
     # uint32 above 65 536 words / uint16 up to there; entity indexing drops entities without instances, in order
+    per_entity = {'ghost-a': 0}
+    for _, _, label in ref['instances'][:60]:
+        for e in label:
+            per_entity[e] = per_entity.get(e, 0) + 1
+    per_entity['ghost-b'] = 0
     packed = prepare.pack(list(ref['instances'][:50]), list(ref['instances'][50:60]), ref['window_size'],
-                          ref['num_words'], {'ent-%02d' % i: (i % 3) for i in range(14)}, shuffle=False)
+                          ref['num_words'], per_entity, shuffle=False)
     assert packed['x_train'].dtype == np.uint32 and packed['x_train'].shape == (50, ref['window_size'])
+    kept = [e for e in per_entity if per_entity[e]]
+    assert [packed['entity_indices_inv'][i] for i in range(len(kept))] == kept
+    assert packed['y_train'].shape == (50, len(kept)) and packed['y_validate'].shape == (10, len(kept))
     small = prepare.pack([('d', (1, 2), {'ent-01': 1.0})], [('d', (3, 4), {'ent-02': 1.0})], 2, 65536,
                          {'ent-01': 1, 'ent-02': 1}, instances_per_document={'d': 2}, max_document_length=4)
     assert small['x_train'].dtype == np.uint16 and small['w_train'].tolist() == [2.0]
-    kept = [e for e in ('ent-%02d' % i for i in range(14)) if int(e[-2:]) % 3]
-    assert [packed['entity_indices_inv'][i] for i in range(len(kept))] == kept
     # data.npz / meta round trip in the formats bin/train.py and bin/query.py read
     c = ref['cases']['ordered']
     y = sparse.csr_matrix((np.array(c['data'], np.float32), np.array(c['indices']), np.array(c['indptr'])),
