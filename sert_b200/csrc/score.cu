@@ -383,7 +383,9 @@ static int launch_prune(const TopkState &s, int Q, int k, int mode, int32_t *out
                         cudaStream_t st, const float *margin = nullptr) {
   int k_pow2 = 2;
   while (k_pow2 < k) k_pow2 <<= 1;
-  if (margin != nullptr) k_pow2 = s.cap / 2;
+  // margin mode keeps k + (rows inside the margin band) survivors: 1024 slots (8 KB, 8 CTAs per SM) hold them on
+  // every workload where the coarse sweep pays; more near-ties than that raise the overflow flag (bf16x3 sweep)
+  if (margin != nullptr) k_pow2 = std::min(s.cap / 2, std::max(1024, 2 * k_pow2));
   prune_select_kernel<<<Q, 256, (size_t)k_pow2 * sizeof(unsigned long long), st>>>(
       s.cand, s.count, s.tau, s.cap, k, mode, out_idx, out_score, k_pow2, margin, s.overflow);
   SERT_LAUNCH_CHECK();
@@ -452,7 +454,7 @@ int topk_sweep(const TopkState &s, const float *queries_dev, int Q, int k, int32
     // of at most eps_q = |q| max|e| (2^-8 + 2^-18 + d 2^-23): bf16 round-to-nearest is 2^-9 relative per operand, the
     // products sum to at most |q||e| (Cauchy-Schwarz), d 2^-23 covers the fp32 accumulation.  Every row of the exact
     // top k then scores within 2 eps_q of the coarse k-th best, so the lists keep everything above (k-th - 2 eps_q);
-    // the survivors (k + a few dozen on these workloads) are re-scored in fp32 below.  Lists that would exceed cap/2
+    // the survivors (k + a few dozen on these workloads) are re-scored in fp32 below.  Lists beyond max(1024, 4k) rows
     // (many near-ties) raise the overflow flag and the bf16x3 sweep runs instead.
     query_margin_kernel<<<cdiv(Q, 8), 256, 0, st>>>(queries_dev, Q, s.d, s.ent_norm_max, s.margin);
     SERT_LAUNCH_CHECK();
