@@ -22,10 +22,15 @@ constexpr int BM = 128, BN = 256, BK = 64, STAGES = 4, UMMA_K = 16;
 constexpr uint32_t A_STAGE_BYTES = BM * BK * 2;   // 16 KB
 constexpr uint32_t B_STAGE_BYTES = BN * BK * 2;   // 32 KB
 constexpr uint32_t STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
-constexpr int EPI_WARPS = 8;              // two warps per TMEM lane quarter, each owns half of the tile's columns
+#ifndef SERT_TC_EPI_WARPS
+#define SERT_TC_EPI_WARPS 16
+#endif
+constexpr int EPI_WARPS = SERT_TC_EPI_WARPS;   // EPI_WARPS/4 warps per TMEM lane quarter, each owns a slice of the tile's columns
+constexpr int COLS_PER_WARP = BN / (EPI_WARPS / 4);
+static_assert(EPI_WARPS % 4 == 0 && COLS_PER_WARP % 32 == 0, "epilogue warps split the columns in 32-column chunks");
 constexpr int NUM_THREADS = 64 + 32 * EPI_WARPS;
 constexpr uint32_t TMEM_COLS = 512;
-constexpr int STASH = 8;                  // survivors a lane can park in shared memory per tile (top-k epilogue)
+constexpr int STASH = 64 / EPI_WARPS;     // survivors a lane can park in shared memory per tile (top-k epilogue)
 constexpr uint32_t STASH_BYTES = 2 * EPI_WARPS * 32 * STASH * 8;   // two buffers: this tile's and the previous one's
 constexpr size_t SMEM_BYTES = 1024 /*align slack*/ + (size_t)STAGES * STAGE_BYTES + 256 /*barriers*/ + STASH_BYTES;
 
@@ -264,8 +269,8 @@ gemm_tc_kernel(const __grid_constant__ TcMap map_a, const __grid_constant__ TcMa
   } else {
     // ================= epilogue (warps 2..9) =================
     const int quarter = warp & 3;                        // a warp may only touch TMEM lanes [32*(warp%4), +32)
-    const int col_lo = ((warp - 2) >> 2) * (BN / 2);     // ... and this warp handles columns [col_lo, col_lo + BN/2)
-    constexpr int CHUNKS = BN / 2 / 32;
+    const int col_lo = ((warp - 2) >> 2) * COLS_PER_WARP;   // ... and this warp handles columns [col_lo, +COLS_PER_WARP)
+    constexpr int CHUNKS = COLS_PER_WARP / 32;
     const int row = quarter * 32 + lane;
     int acc = 0;
     uint32_t acc_phase = 0;
@@ -304,7 +309,7 @@ gemm_tc_kernel(const __grid_constant__ TcMap map_a, const __grid_constant__ TcMa
       const uint32_t t_row = tmem_base + (uint32_t)acc * BN + ((uint32_t)(quarter * 32) << 16);
       if (ep.mode == TC_EPI_STORE) {
 #pragma unroll 1
-        for (int c0 = col_lo; c0 < col_lo + BN / 2; c0 += 32) {
+        for (int c0 = col_lo; c0 < col_lo + COLS_PER_WARP; c0 += 32) {
           uint32_t v[32];
           tc_ld_32x32(t_row + (uint32_t)c0, v);
           tc_wait_ld();
