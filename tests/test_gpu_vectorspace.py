@@ -120,6 +120,30 @@ def test_hot_word_rows_are_result_neutral(hot):
         model.set_hot_words([300])
 
 
+def test_switching_step_variants_mid_training_keeps_parity():
+    """The lazy tile step leaves a loss pending and marks the hot word rows; switching to the warp kernel, the per-stage
+    kernels, the single-stream step and back must flush / unmark them: every loss and the final tables match the oracle."""
+    from sert_b200 import _native as N
+    p = H.vs_problem(41, V=400, E=150, dw=128, de=128, W=6, B=200, k=7, n_batches=10, weights=True)
+    model = make_model(p, 0.01)
+    assert model.hot_words.size >= 1
+    oracle = H.vs_oracle(p, 0.01)
+    lib, h = model._native.lib, model._native.handle
+    plan = [(1, 1), (1, 1), (2, 1), (0, 1), (1, 1), (1, 0), (1, 1), (2, 0), (1, 1), (1, 1)]     # (fused, overlap)
+    for j, (fused, overlap) in enumerate(plan):
+        N.check(lib.sert_model_set_fused(h, fused))
+        N.check(lib.sert_model_set_overlap(h, overlap))
+        H.close(model.train_fn(j, p['neg'][j]), oracle.train_batch(j, p['neg'][j]), what='train loss step %d' % j)
+        if j == 4:      # an eval between lazy steps shares the accumulators
+            H.close(model.test_fn(0, p['neg'][0]), oracle.eval_batch('train', 0, p['neg'][0]), rtol=2e-4, what='eval')
+    R, Eemb = model.get_representations()
+    Wp, bp = model.get_dense()
+    H.close(R, oracle.R, rtol=2e-4, what='R')
+    H.close(Eemb, oracle.Eemb, rtol=2e-4, what='Eemb')
+    H.close(Wp, oracle.Wp, rtol=2e-4, what='Wp')
+    H.close(bp, oracle.bp, rtol=2e-4, atol_scale=1e-4, what='bp')
+
+
 def test_epoch_api_and_host_batches():
     """train() over a whole epoch in one call == per-batch train_fn; streamed host batches == resident data."""
     from sert_b200 import _native as N
