@@ -356,7 +356,8 @@ def run_ours(args, rank, world, local_rank):
                            'step b is enqueued',
                     'synchronous_value': e2e_sync_value,
                     'synchronous_api': 'sert_train_batch_host (one host/device sync per step)'},
-            'roofline': {'bound': 'hbm', 'kernel': 'dense_update_kernel<Adam> (csrc/opt_kernels.cu)',
+            'roofline': {'bound': 'hbm', 'kernel': 'dense_update_kernel<Adam, tables> (csrc/opt_kernels.cu), CUDA events '
+                                                   'around every launch inside running steps',
                          'achieved': achieved, 'peak': peak, 'unit': 'GB/s', 'frac': achieved / peak,
                          'traffic': traffic, 'peak_source': peak_src,
                          'algorithmic_bytes_per_launch': bpl.value, 'kernel_ms': upd_ms,

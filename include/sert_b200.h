@@ -106,9 +106,11 @@ SERT_API int sert_model_set_step(sert_model *m, int64_t t);
 SERT_API int sert_model_get_step(sert_model *m, int64_t *t);
 
 /* Measurement hook (no reference counterpart): when enabled, every training step brackets its dense
- * optimiser kernel with CUDA events on the model's stream.  profile_read synchronises and returns the
- * summed kernel time, the launch count and the ALGORITHMIC bytes of one launch (24 B per parameter:
- * read+write of theta and the two optimiser-state arrays; DESIGN.md "roofline"). */
+ * optimiser kernel with CUDA events on the model's stream -- in the two-stream vector-space step that is the
+ * streaming kernel over the two tables, timed in situ (the small kernels of the second stream run beside it as
+ * they do in an unprofiled step).  profile_read synchronises and returns the summed kernel time, the launch count
+ * and the ALGORITHMIC bytes of one launch (24 B per parameter the launch covers: read+write of theta and the two
+ * optimiser-state arrays; DESIGN.md "roofline"). */
 SERT_API int sert_model_profile(sert_model *m, int enable);
 /* Vector-space training step: 1 (default) = fused forward+backward kernel -- one CTA per tile of 8 instances when both
  * representation sizes are 128 (csrc/vs_tile.cu), else one warp per pair of instances for sizes up to 384

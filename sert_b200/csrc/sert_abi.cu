@@ -124,6 +124,7 @@ struct sert_model {
   cudaStream_t st2 = nullptr;
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
   bool profile = false;
+  double prof_bytes = 0.0;            // algorithmic bytes of the launches timed in profile mode
   std::vector<std::pair<cudaEvent_t, cudaEvent_t>> prof_events;
 };
 
@@ -303,7 +304,12 @@ static int timed_update(sert_model &m, const OptimArgs &o, bool adam) {
   const int rc = adam ? launch_adam(k, m.st) : launch_adadelta(k, m.st);
   SERT_CUDA(cudaEventRecord(b, m.st));
   m.prof_events.emplace_back(a, b);
-  if (rc) return rc;
+  // algorithmic bytes of this launch: theta and two state arrays read and written, float32
+  long long params = 0;
+  for (int sg = 0; sg < o.num_segments; ++sg)
+    if (o.phase == 0 || (o.phase == 3) == (o.seg[sg].flags != nullptr)) params += o.seg[sg].count;
+  m.prof_bytes = 24.0 * (double)params;
+  if (rc || o.phase != 0) return rc;
   return launch_finalize_train(o.acc, o.loss_out, o.inv_B, o.reg_coeff, m.st);
 }
 
@@ -342,7 +348,7 @@ static int vs_train_step(sert_model &m, const int32_t *x, const int32_t *y, cons
   cudaStream_t st = m.st;
   const int B = c.batch, dw = c.word_dim, de = c.entity_dim;
   float *Wp = m.theta + m.off[SERT_PARAM_DENSE_W];
-  const bool overlap = m.overlap && !m.profile && m.st2 != nullptr;
+  const bool overlap = m.overlap && m.st2 != nullptr;
   // "Lazy" step = fused tile kernel + second stream.  Its critical path is two kernels, the tile kernel and the
   // Adam stream over the two tables; everything else -- gradients and update of the projection matrix and bias,
   // update of the hot word rows -- runs on the second stream under the table update, and the scalar loss is
@@ -442,14 +448,14 @@ static int vs_train_step(sert_model &m, const int32_t *x, const int32_t *y, cons
       if (launch_hot_update(h, side)) return -1;
     }
     SERT_CUDA(cudaEventRecord(m.ev_join, side));
-    if (launch_adam(tables, st)) return -1;
+    if (timed_update(m, tables, true)) return -1;     // profile mode: events around the table stream, in situ
     SERT_CUDA(cudaStreamWaitEvent(st, m.ev_join, 0));
     m.pending_bank = bank;
     m.pending_loss = loss_out;
     return 0;
   }
   SERT_CUDA(cudaEventRecord(m.ev_join, side));
-  if (launch_adam(tables, st)) return -1;
+  if (timed_update(m, tables, true)) return -1;
   SERT_CUDA(cudaStreamWaitEvent(st, m.ev_join, 0));
   dense.ticket = reinterpret_cast<unsigned int *>(m.acc + kAccDoubles - 4);
   return launch_adam(dense, st);
@@ -867,9 +873,7 @@ int sert_model_profile_read(sert_model *m, double *update_ms_total, int64_t *upd
   }
   *update_ms_total = tot;
   *update_launches = (int64_t)m->prof_events.size();
-  long long params = 0;
-  for (int w = 0; w < 4; ++w) params += m->cnt[w];
-  *update_bytes_per_launch = 24.0 * (double)params;   // read+write of theta and two state arrays, f32
+  *update_bytes_per_launch = m->prof_bytes;           // read+write of theta and two state arrays, f32
   m->prof_events.clear();
   return 0;
 }
