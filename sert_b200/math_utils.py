@@ -3,18 +3,13 @@ import numpy as np
 import scipy.stats
 
 
-def entropy(pk, *args, **kwargs):
-    """scipy.stats.entropy with an optional normalize=True dividing by the maximum entropy log(n)."""
-    normalize = kwargs.pop('normalize', False)
-
-    e = scipy.stats.entropy(pk, *args, **kwargs)
-
-    if normalize:
-        maximum_entropy = np.log(np.size(pk))
-        base = kwargs.get('base')
-        if base:
-            maximum_entropy /= np.log(base)
-
-        e /= maximum_entropy
-
-    return e
+def entropy(pk, *args, normalize=False, **kwargs):
+    """scipy.stats.entropy(pk, ...); normalize=True divides by the entropy of the uniform distribution over
+    np.size(pk) outcomes, log(n) in the requested base, so the result lies in [0, 1]."""
+    value = scipy.stats.entropy(pk, *args, **kwargs)
+    if not normalize:
+        return value
+    uniform = np.log(np.size(pk))          # numpy's log: the debug output is compared bit for bit with the reference's
+    if kwargs.get('base'):
+        uniform /= np.log(kwargs['base'])
+    return value / uniform

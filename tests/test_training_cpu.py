@@ -1,0 +1,99 @@
+"""Host logic of the training driver (sert_b200/training.py behind bin/train.py): command line, data.npz loading,
+one-hot expansion, pre-trained initialisation and the epoch protocol of bin/train.py:262-348, on a fake model."""
+import collections
+import os
+import pickle
+
+import numpy as np
+import pytest
+from scipy import sparse
+
+from sert_b200 import models, prepare, training
+
+
+class FakeModel(models.ModelInterface):
+    def __init__(self, train_errors):
+        super(FakeModel, self).__init__(batch_size=4)
+        self.train_errors = list(train_errors)
+        self.calls = []
+
+    def train(self):
+        self.calls.append('train')
+        return 3, 0.5
+
+    def train_error(self):
+        self.calls.append('train_error')
+        return self.train_errors.pop(0), 0.1
+
+    def validation_error(self):
+        self.calls.append('validation_error')
+        return 1.0, 0.2
+
+    def get_state(self):
+        return ['predict_fn', np.arange(3)]
+
+
+def test_command_line_matches_the_reference_flags(tmp_path):
+    data = tmp_path / 'data.npz'
+    data.write_bytes(b'x')
+    args = training.parse_args(['--data', str(data), '--meta', str(data), '--type', 'vectorspace',
+                                '--model_output', 'out', '--batch_size', '4096', '--num_negative_samples', '10',
+                                '--word_representation_size', '128', '--one_hot_classes'])
+    assert args.type is models.VectorSpaceLanguageModel and args.entity_representation_size == 128
+    assert args.regularization_lambda == 0.01 and args.iterations == 1 and args.one_hot_classes
+    with pytest.raises(SystemExit):
+        training.parse_args(['--data', str(data), '--meta', str(data), '--type', 'cnn', '--model_output', 'o'])
+    with pytest.raises(SystemExit):
+        training.parse_args(['--data', str(tmp_path / 'missing'), '--meta', str(data), '--type', 'loglinear',
+                             '--model_output', 'o'])
+
+
+def test_data_loading_weights_and_one_hot(tmp_path):
+    y = sparse.csr_matrix(np.array([[0.5, 0.5, 0], [0, 0, 1.0], [0, 1.0, 0]], dtype=np.float32))
+    x = np.arange(6, dtype=np.uint16).reshape(3, 2)
+    w = np.array([1.0, 2.0, 3.0], dtype=np.float32)
+    path = str(tmp_path / 'data.npz')
+    prepare.write_data(path, x, y, x[:1], y[:1], w_train=w)
+    (xt, yt, wt), (xv, yv) = training.load_data_sets(path)
+    np.testing.assert_array_equal(wt, w)
+    assert sparse.issparse(yt) and yv.shape == (1, 3)
+    (_, _, wt2), _ = training.load_data_sets(path, ignore_weights=True)
+    np.testing.assert_array_equal(wt2, np.ones(3, np.float32))
+    (x1, y1, w1), (xv1, yv1) = training.to_one_hot((xt, yt, wt), (xv, yv))
+    assert x1.shape == (4, 2) and sorted(y1.tolist()) == [0, 1, 1, 2] and w1.shape == (4,)
+    assert yv1.tolist() == [0, 1] and xv1.shape == (2, 2)
+    with pytest.raises(RuntimeError, match='expects sparse truth values'):
+        training.to_one_hot((xt, yt.toarray(), wt), (xv, yv))
+
+
+def test_pretrained_rows_overwrite_the_glorot_table(tmp_path):
+    Word = collections.namedtuple('Word', ['id', 'count'])
+    words = {'Alpha': Word(0, 5), 'beta': Word(1, 3), 'gamma': Word(2, 1)}
+    path = str(tmp_path / 'w2v.bin')
+    vectors = {'alpha': np.full(4, 0.25, np.float32), 'beta': np.full(4, -0.5, np.float32)}
+    with open(path, 'wb') as f:                          # word2vec binary: "<n> <d>\n" then "<word> " + d float32 + "\n"
+        f.write(b'2 4\n')
+        for word, vec in vectors.items():
+            f.write(word.encode() + b' ' + vec.tobytes() + b'\n')
+    np.random.seed(0)
+    table = training.word_representations(4, words, ['alpha', 'beta', 'gamma'], path)
+    assert table.shape == (3, 4) and table.dtype == np.float32
+    np.testing.assert_array_equal(table[0], vectors['alpha'])      # looked up lower-cased
+    np.testing.assert_array_equal(table[1], vectors['beta'])
+    limit = np.sqrt(6.0 / (3 + 4))
+    assert np.all(np.abs(table[2]) <= limit) and np.any(table[2] != 0)
+
+
+def test_epoch_protocol_dumps_every_epoch_and_stops_when_learning_stalls(tmp_path):
+    out = str(tmp_path / 'model')
+    model = FakeModel([2.0, 1.5, 1.2, 1.2 + 1e-7, 0.3])
+    training.train(model, 10, out, abort_threshold=1e-5, additional_args=[{'window_size': 5}])
+    # errors(0), dump(0), then train -> errors -> dump per epoch; the 3rd epoch moves the error by 1e-7: stop
+    assert model.calls == ['train_error', 'validation_error'] + ['train', 'train_error', 'validation_error'] * 3
+    assert sorted(os.listdir(str(tmp_path))) == ['model_0.bin', 'model_1.bin', 'model_2.bin', 'model_3.bin']
+    with open(out + '_2.bin', 'rb') as f:
+        objs = [pickle.load(f) for _ in range(3)]
+    assert objs[0] == {'window_size': 5} and objs[1] == 'predict_fn' and objs[2].tolist() == [0, 1, 2]
+    assert training.EpochLoop.delta([2.0, 1.0]) == (-1.0, -0.5) and training.EpochLoop.delta([2.0]) == (0.0, 0.0)
+    with pytest.raises(AssertionError):
+        training.train(FakeModel([float('nan'), float('nan')]), 1, str(tmp_path / 'bad'))
