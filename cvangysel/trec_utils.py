@@ -71,3 +71,44 @@ def write_run(model_name, data, out_f, max_objects_per_query=sys.maxsize, skip_s
                 object_id = object_id.decode('utf8')
             lines.append('{0} Q0 {1} {2} {3} {4}\n'.format(subject_id, object_id, rank, relevance, model_name))
         out_f.write(''.join(lines))
+
+
+def write_run_arrays(model_name, subject_ids, object_ids, relevances, out_f, counts=None,
+                     max_objects_per_query=sys.maxsize):
+    """write_run for rankings that already are arrays (the output of a batched top-k scorer): row q of `object_ids`
+    (Q, k) str and `relevances` (Q, k) float holds the `counts[q]` (default k) assessed objects of `subject_ids[q]`.
+    Produces byte for byte what write_run writes for {subject: [(relevance, object_id), ...]} -- the descending
+    (relevance, object id) order of trec_utils.py:560-561 and '{0}'.format of the relevance values -- with one lexsort
+    for all subjects instead of a tuple sort per subject, and no per-assessment tuples to build."""
+    import numpy as np
+    rel = np.asarray(relevances)
+    ids = np.asarray(object_ids, dtype=str)
+    assert rel.ndim == 2 and ids.shape == rel.shape and len(subject_ids) == rel.shape[0]
+    num_subjects, k = rel.shape
+    counts = np.full(num_subjects, k, dtype=np.int64) if counts is None else np.asarray(counts, dtype=np.int64)
+    valid = np.arange(k)[None, :] < counts[:, None]
+    for q in np.flatnonzero(counts == 0):
+        logging.warning('Received empty ranking for %s; ignoring.', subject_ids[q])
+    if num_subjects == 0 or k == 0:
+        return
+    # unused slots sort behind every real assessment
+    rel_key = np.where(valid, rel, -np.inf)
+    ids_key = np.where(valid, ids, '')
+    order = np.lexsort((ids_key, rel_key), axis=-1)[:, ::-1]          # descending (relevance, object id)
+    rel_sorted = np.take_along_axis(rel, order, axis=1)
+    ids_sorted = np.take_along_axis(ids, order, axis=1)
+    # Python floats / str from here: repr(float) is what '{0}'.format(numpy scalar) emits (float.__format__ of the
+    # value widened to double), and one f-string per line over plain lists beats numpy's fixed-width string arrays
+    rel_rows = rel_sorted.astype(np.float64).tolist()
+    ids_rows = ids_sorted.tolist()
+    limits = np.minimum(counts, max_objects_per_query).tolist()
+    tail = ' {0}\n'.format(model_name)
+    chunks = []
+    for q, subject in enumerate(subject_ids):
+        if isinstance(subject, bytes):
+            subject = subject.decode('utf8')
+        head = subject + ' Q0 '
+        n = limits[q]
+        chunks.append(''.join([f'{head}{o} {r} {v}{tail}'
+                               for r, (o, v) in enumerate(zip(ids_rows[q][:n], rel_rows[q][:n]), start=1)]))
+    out_f.write(''.join(chunks))

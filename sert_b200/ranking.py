@@ -17,9 +17,11 @@ order), the host then
 import collections
 import logging
 import operator
+import sys
 
 import numpy as np
 
+from cvangysel import trec_utils
 from sert_b200 import inference, math_utils
 
 CANDIDATE_MARGIN = 28       # extra device candidates re-ranked on the host (fp32 near-ties at the k-th place)
@@ -214,3 +216,17 @@ def compute_normalised_entropy(distribution, base=2):
 
     return [math_utils.entropy(distribution[i, :], base=base, normalize=True)
             for i in range(distribution.shape[0])]
+
+
+def write_topk_run(model_name, topic_ids, top_indices, relevances, entity_indices_inv, out_f,
+                   max_objects_per_query=sys.maxsize):
+    """Entity-finding run file (`<run_out>_ef`, bin/query.py:149-156) straight from a batched device ranking:
+    `top_indices` (Q, k) internal entity rows as returned by scoring.EntityScorer.topk (-1 = no row, shards shorter
+    than k) and `relevances` (Q, k).  Same bytes as feeding ranker_callback / trec_utils.write_run topic by topic."""
+    top_indices = np.asarray(top_indices)
+    lookup = np.array([entity_indices_inv[i] for i in range(len(entity_indices_inv))], dtype=str)
+    present = top_indices >= 0
+    assert (present[:, :-1] >= present[:, 1:]).all(), 'missing rows must trail the list'
+    object_ids = lookup[np.where(present, top_indices, 0)]
+    trec_utils.write_run_arrays(model_name, topic_ids, object_ids, relevances, out_f, counts=present.sum(axis=1),
+                                max_objects_per_query=max_objects_per_query)

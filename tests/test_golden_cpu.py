@@ -234,3 +234,50 @@ def test_argparse_validators_match_reference_semantics():
         A.existing_file_path('/no/such/file')
     with pytest.raises(argparse.ArgumentTypeError):
         A.nonexisting_file_path(__file__)
+
+
+def test_write_run_arrays_equals_write_run():
+    """the array form of write_run emits the same bytes as the (reference-pinned) dict form,
+    ties in relevance broken by descending object id, float32 and float64 relevance values, ragged rows."""
+    import collections
+    from cvangysel import trec_utils
+    rng = np.random.default_rng(7)
+    Q, k = 23, 17
+    pool = np.array(['ent-%d' % i for i in range(40)] + ['e%s' % ('x' * i) for i in range(1, 6)] + ['Z', 'a', 'B-1'])
+    for dtype in (np.float32, np.float64):
+        ids = np.stack([rng.choice(pool, k, replace=False) for _ in range(Q)])
+        rel = np.round(rng.random((Q, k)), 1).astype(dtype)                 # many ties
+        rel[0, :3] = [1e-5, 123456.789, 3.0000001e-12]
+        rel[1, :2] = [-0.0, 0.0]
+        counts = rng.integers(0, k + 1, Q)
+        counts[:3] = [k, k, 0]
+        subjects = ['T%02d' % q for q in range(Q)]
+        subjects[4] = b'bytes-topic'
+        for limit in (10 ** 9, 5):
+            data = collections.OrderedDict(
+                (subjects[q], [(rel[q, j], ids[q, j].item()) for j in range(counts[q])]) for q in range(Q))
+            a, b = io.StringIO(), io.StringIO()
+            trec_utils.write_run('model_3.bin', data, a, max_objects_per_query=limit)
+            trec_utils.write_run_arrays('model_3.bin', subjects, ids, rel, b, counts=counts,
+                                        max_objects_per_query=limit)
+            assert a.getvalue() == b.getvalue() and a.getvalue().count('\n') > 50
+
+
+def test_write_topk_run_from_device_style_arrays():
+    import collections
+    from cvangysel import trec_utils
+    from sert_b200 import ranking
+    rng = np.random.default_rng(11)
+    E, Q, k = 60, 9, 12
+    inv = {i: 'entity/%03d' % (E - i) for i in range(E)}
+    idx = np.stack([rng.choice(E, k, replace=False) for _ in range(Q)]).astype(np.int32)
+    rel = np.sort(rng.random((Q, k)).astype(np.float32), axis=1)[:, ::-1].copy()
+    idx[2, 7:] = -1                                       # a shard shorter than k
+    idx[5, :] = -1
+    topics = ['t%d' % q for q in range(Q)]
+    data = collections.OrderedDict(
+        (topics[q], [(rel[q, j], inv[int(idx[q, j])]) for j in range(k) if idx[q, j] >= 0]) for q in range(Q))
+    a, b = io.StringIO(), io.StringIO()
+    trec_utils.write_run('m.bin', data, a)
+    ranking.write_topk_run('m.bin', topics, idx, rel, inv, b)
+    assert a.getvalue() == b.getvalue() and a.getvalue().count('\n') == (idx >= 0).sum()
