@@ -4,6 +4,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <atomic>
 #include <string>
 
 #include "../../include/sert_b200.h"
@@ -39,6 +40,11 @@ void count_launch(uint64_t n = 1);
   } while (0)
 
 static inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+// True the first time it is called for the current device with a given `mask` (one static std::atomic<uint64_t> per
+// call site): per-device one-time set-up such as cudaFuncSetAttribute, safe when several host threads drive
+// different devices of one process.
+bool first_use_on_device(std::atomic<uint64_t> &mask);
 static inline int cdiv(long long a, long long b) { return (int)((a + b - 1) / b); }
 
 constexpr int kNumSMs = 148;  // B200: 2 dies x 74 SMs

@@ -506,16 +506,14 @@ int launch_gemm_tc_ld(const __nv_bfloat16 *A, long long lda, int M, const __nv_b
   TcMap ma, mb;
   if (make_map(A, M, Kt, lda, BM, &ma)) return -1;
   if (make_map(B, N_total, Kt, ldb, BN, &mb)) return -1;
-  static bool configured = false;
-  static int sms = kNumSMs;
-  if (!configured) {
+  static std::atomic<uint64_t> configured{0};
+  if (first_use_on_device(configured)) {
     SERT_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
     SERT_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
-    int dev = 0;
-    SERT_CUDA(cudaGetDevice(&dev));
-    SERT_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-    configured = true;
   }
+  int dev = 0, sms = kNumSMs;
+  SERT_CUDA(cudaGetDevice(&dev));
+  SERT_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
   KernelArgs args;
   args.M = M;
   args.n_begin = n_begin;

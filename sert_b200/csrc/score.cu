@@ -478,12 +478,11 @@ int topk_sweep(const TopkState &s, const float *queries_dev, int Q, int k, int32
 
 int topk_prepare(int cap) {
   // the prune keeps k <= cap/2 survivors (rounded up to a power of two) in dynamic shared memory
-  static int configured = 0;
-  const int smem = (cap / 2) * (int)sizeof(unsigned long long);
-  if (smem > configured && smem > 40 * 1024) {
-    SERT_CUDA(cudaFuncSetAttribute(prune_select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    configured = smem;
-  }
+  // once per device: room for the largest list the ABI admits (max_k <= 8192 -> cap <= 32768 -> 128 KB)
+  static std::atomic<uint64_t> configured{0};
+  (void)cap;
+  if (first_use_on_device(configured))
+    SERT_CUDA(cudaFuncSetAttribute(prune_select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 1024));
   return 0;
 }
 

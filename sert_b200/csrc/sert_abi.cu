@@ -17,6 +17,12 @@ static thread_local std::string g_error;
 static std::atomic<uint64_t> g_launches{0};
 void set_error(const std::string &msg) { g_error = msg; }
 void count_launch(uint64_t n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+bool first_use_on_device(std::atomic<uint64_t> &mask) {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return true;
+  const uint64_t bit = 1ull << (dev & 63);
+  return (mask.fetch_or(bit, std::memory_order_acq_rel) & bit) == 0;
+}
 
 // ---- bump allocator over the caller-provided HBM arena ------------------------------------------
 struct Bump {

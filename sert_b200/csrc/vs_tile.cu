@@ -266,12 +266,10 @@ bool vs_tile_supported(int dw, int de, int W, int k) {
 int launch_vs_tile(const VsFusedArgs &a, const float *WpT, cudaStream_t st) {
   if (!vs_tile_supported(a.dw, a.de, a.W, a.k)) return 1;
   const size_t smem = std::max((size_t)kT * (a.k + 1) * kD, (size_t)kPartFloats) * sizeof(float);
-  static bool attr_set = false;
-  if (!attr_set) {
+  static std::atomic<uint64_t> configured{0};
+  if (first_use_on_device(configured))
     SERT_CUDA(cudaFuncSetAttribute(vs_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                    (int)(kT * kMaxRows * kD * sizeof(float))));
-    attr_set = true;
-  }
   static_assert(kSumsqSlots == 64, "the finalising CTA reads the slots with two warps");
   vs_tile_kernel<<<cdiv(a.B, kT) + 1, kThreads, smem, st>>>(a, WpT);    // + 1: the CTA that finalises the previous loss
   SERT_LAUNCH_CHECK();

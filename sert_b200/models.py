@@ -145,6 +145,21 @@ class _NativeModel(object):
         return out
 
 
+HOT_WORD_MIN_PER_BATCH = 64     # expected occurrences per batch from which a word's gradient row counts as hot
+MAX_HOT_WORDS = 32              # kMaxHotRows (csrc/kernels.cuh)
+
+
+def hot_word_ids(x, vocabulary_size, batch_size, min_per_batch=HOT_WORD_MIN_PER_BATCH, max_words=MAX_HOT_WORDS):
+    """The (at most `max_words`) word ids expected at least `min_per_batch` times in a batch of `batch_size` windows
+    of x (N, W), most frequent first; ties keep the lower id."""
+    x = np.asarray(x)
+    if x.size == 0:
+        return np.zeros(0, np.int32)
+    per_batch = np.bincount(x.ravel(), minlength=vocabulary_size) * (float(batch_size) / x.shape[0])
+    order = np.argsort(-per_batch, kind='stable')[:max_words]
+    return order[per_batch[order] >= min_per_batch].astype(np.int32)
+
+
 class ModelInterface(object):
     """sert/models.py:295-411."""
 
@@ -665,19 +680,10 @@ class VectorSpaceLanguageModel(VectorSpaceLanguageModelBase):
         self.set_hot_words(self.pick_hot_words())
         self._create_functions()
 
-    HOT_WORD_MIN_PER_BATCH = 64     # expected occurrences per batch from which a word row counts as hot
-    MAX_HOT_WORDS = 32              # kMaxHotRows (csrc/kernels.cuh)
-
     def pick_hot_words(self):
         """Word ids whose gradient row receives so many additions per batch that they serialise in L2
         (include/sert_b200.h: sert_model_set_hot_words), from the training set's word counts."""
-        x = self.training_set[0]
-        if x.size == 0:
-            return np.zeros(0, np.int32)
-        counts = np.bincount(np.asarray(x).ravel(), minlength=self.vocabulary_size)
-        per_batch = counts * (float(self.batch_size) / x.shape[0])
-        order = np.argsort(-per_batch, kind='stable')[:self.MAX_HOT_WORDS]
-        return order[per_batch[order] >= self.HOT_WORD_MIN_PER_BATCH].astype(np.int32)
+        return hot_word_ids(self.training_set[0], self.vocabulary_size, self.batch_size)
 
     def set_hot_words(self, ids):
         ids = np.ascontiguousarray(ids, dtype=np.int32)

@@ -97,3 +97,17 @@ def test_epoch_protocol_dumps_every_epoch_and_stops_when_learning_stalls(tmp_pat
     assert training.EpochLoop.delta([2.0, 1.0]) == (-1.0, -0.5) and training.EpochLoop.delta([2.0]) == (0.0, 0.0)
     with pytest.raises(AssertionError):
         training.train(FakeModel([float('nan'), float('nan')]), 1, str(tmp_path / 'bad'))
+
+
+def test_hot_word_selection():
+    rng = np.random.default_rng(3)
+    x = rng.integers(10, 1000, (4000, 10))
+    x[:, 0] = 7                      # once in every window: 100 per batch of 100
+    x[::2, 1] = 3                    # every other window: 50 per batch -> below the threshold of 64
+    x[:, 2] = np.where(np.arange(4000) % 4 < 3, 5, x[:, 2])     # 75 per batch
+    ids = models.hot_word_ids(x, 1000, 100)
+    assert ids.dtype == np.int32 and ids.tolist() == [7, 5]
+    assert models.hot_word_ids(x, 1000, 200).tolist()[:3] == [7, 5, 3]          # 200 / 150 / 100 per batch
+    assert models.hot_word_ids(np.zeros((0, 10), np.int64), 1000, 100).size == 0
+    dense = np.tile(np.arange(40), (50, 1))                                     # 40 words, each once per window
+    assert models.hot_word_ids(dense, 40, 128).tolist() == list(range(32))      # capped at 32, lower ids first
