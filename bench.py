@@ -330,14 +330,23 @@ def run_ours(args, rank, world, local_rank):
     del model
 
     # ---- entity scoring (row-sharded; one all-gather of per-shard top-k) ----
-    scoring = run_scoring(CFG4, 'BASELINE.json configs[3]', rank, world, barrier, cpu=False)
-    scoring_small = run_scoring(CFG3, 'BASELINE.json configs[2]', rank, world, barrier, cpu=(rank == 0))
+    def leg(fn, *a, **kw):
+        """A secondary leg must not take the headline line down with it: its failure is reported in its place."""
+        try:
+            return fn(*a, **kw)
+        except Exception as exc:                     # noqa: BLE001
+            import traceback
+            traceback.print_exc(file=sys.stderr)
+            return {'error': '%s: %s' % (type(exc).__name__, exc)}
 
-    loglinear = run_loglinear_cfg1(rank) if rank == 0 else None
-    loglinear_stress = None if os.environ.get('SERT_BENCH_SKIP_CFG5') else run_loglinear_cfg5(rank, world, barrier)
+    scoring = leg(run_scoring, CFG4, 'BASELINE.json configs[3]', rank, world, barrier, cpu=False)
+    scoring_small = leg(run_scoring, CFG3, 'BASELINE.json configs[2]', rank, world, barrier, cpu=(rank == 0))
+
+    loglinear = leg(run_loglinear_cfg1, rank) if rank == 0 else None
+    loglinear_stress = None if os.environ.get('SERT_BENCH_SKIP_CFG5') else leg(run_loglinear_cfg5, rank, world, barrier)
 
     if rank == 0:
-        cpu = cpu_baseline_sample()
+        cpu = leg(cpu_baseline_sample)
         line = {
             'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': steps, 'warmup': warm,
             'ms_per_step': ms_max / steps, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
