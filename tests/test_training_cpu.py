@@ -111,3 +111,27 @@ def test_hot_word_selection():
     assert models.hot_word_ids(np.zeros((0, 10), np.int64), 1000, 100).size == 0
     dense = np.tile(np.arange(40), (50, 1))                                     # 40 words, each once per window
     assert models.hot_word_ids(dense, 40, 128).tolist() == list(range(32))      # capped at 32, lower ids first
+
+
+def test_synthetic_corpus_files_feed_the_training_driver(tmp_path):
+    """The files the CLI tests train from (synth.write_corpus_files) are in the reference's on-disk formats: the driver's
+    loader, the meta reader and the topic parser accept them (the GPU-side continuation is tests/test_gpu_cli.py)."""
+    from cvangysel import trec_utils
+    from scipy import sparse as sp
+    from sert_b200 import synth
+    data_path, meta_path, topics_path = synth.write_corpus_files(str(tmp_path), 'loglinear', 5, V=300, E=40, W=4,
+                                                                 n_train=96, n_val=32)
+    (x, y, w), (xv, yv) = training.load_data_sets(data_path)
+    assert x.shape == (96, 4) and x.dtype == np.uint16 and sp.issparse(y) and y.shape == (96, 40)
+    assert w.shape == (96,) and w.dtype == np.float32 and xv.shape == (32, 4) and yv.shape == (32, 40)
+    np.testing.assert_allclose(np.asarray(y.sum(axis=1)).ravel(), 1.0, rtol=1e-6)       # label masses sum to one
+    data_args, words, tokens, entity_indices_inv, documents_per_entity = prepare.read_meta(meta_path)
+    assert data_args.window_size == 4 and len(words) == len(tokens) == 300 and len(entity_indices_inv) == 40
+    assert int(x.max()) < len(words) and words[tokens[17]].id == 17
+    with open(topics_path) as f:
+        topics = trec_utils.parse_topics(f)
+    assert 'T999' in topics and len(topics) == 13
+    known = [t for t in trec_utils.parse_query(topics['T000']) if t in words]
+    assert known and 'zzzunknownzzz' not in words
+    (x1, y1, w1), _ = training.to_one_hot((x, y, w), (xv, yv))
+    assert x1.shape[0] == y.nnz and y1.dtype == np.int32 and int(y1.max()) < 40
