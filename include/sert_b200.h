@@ -187,6 +187,18 @@ SERT_API int sert_train_batch_host_async(sert_model *m, const int32_t *x_host, c
                                 const float *w_host, const int32_t *neg_host, int64_t *ticket_out);
 SERT_API int sert_train_host_wait(sert_model *m, int64_t ticket, float *loss_host);
 
+/* ---- run files: the step behind scoring (cvangysel-common trec_utils.write_run, trec_utils.py:531-580) ---- */
+/* Formats n_lines lines "<subject> Q0 <object> <rank> <relevance> <model_name>\n" into `out` (host memory, `capacity`
+ * bytes; 64 bytes + the three strings per line always suffice).  Subjects and objects are UTF-8 blobs with n+1 byte
+ * offsets; every line names its subject, object, rank and relevance.  The relevance is printed like Python's
+ * '{0}'.format(float) (repr: shortest round-trip digits, exponent notation outside 1e-4 <= |v| < 1e16), so the bytes
+ * equal write_run's.  Pure host code (no device needed).  Returns the bytes written, -1 on a null argument, -2 when
+ * `out` is too small. */
+SERT_API int64_t sert_format_run(const char *subject_blob, const int64_t *subject_off, const char *object_blob,
+                        const int64_t *object_off, const int32_t *line_subject, const int32_t *line_object,
+                        const int32_t *line_rank, const double *line_relevance, int64_t n_lines,
+                        const char *model_name, char *out, int64_t capacity);
+
 /* ---- parity hooks (no reference counterpart; expose the graph's intermediate tensors) ---------- */
 /* vector space: forward of one attached batch; out_scores_host (B,1+k) = [u.E[y], u.E[n_j]] logits,
  * out_proj_host (B,de) = clipped tanh projection u, out_ell_host (B,) instance losses. Any may be NULL. */

@@ -64,6 +64,8 @@ SIGNATURES = {
     'sert_train_batches': (c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_int32]),
     'sert_eval_batches': (c_int, [c_void_p, c_int, c_void_p, c_int64, c_void_p, c_int32]),
     'sert_losses_fetch': (c_int, [c_void_p, c_int32, c_int64, c_void_p]),
+    'sert_format_run': (c_int64, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                                  c_int64, ctypes.c_char_p, c_void_p, c_int64]),
     'sert_train_batch_host': (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                                       c_void_p, c_void_p]),
     'sert_vs_forward_host': (c_int, [c_void_p, c_int, c_int64, c_void_p, c_void_p, c_void_p, c_void_p]),

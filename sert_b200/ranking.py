@@ -218,15 +218,52 @@ def compute_normalised_entropy(distribution, base=2):
             for i in range(distribution.shape[0])]
 
 
+def _utf8_blob(strings):
+    """(concatenated UTF-8 bytes as uint8 array, int64 offsets of len(strings) + 1)."""
+    encoded = [s if isinstance(s, bytes) else str(s).encode('utf8') for s in strings]
+    offsets = np.zeros(len(encoded) + 1, dtype=np.int64)
+    np.cumsum([len(e) for e in encoded], out=offsets[1:])
+    blob = np.frombuffer(b''.join(encoded) or b'\0', dtype=np.uint8)
+    return blob, offsets
+
+
 def write_topk_run(model_name, topic_ids, top_indices, relevances, entity_indices_inv, out_f,
                    max_objects_per_query=sys.maxsize):
     """Entity-finding run file (`<run_out>_ef`, bin/query.py:149-156) straight from a batched device ranking:
     `top_indices` (Q, k) internal entity rows as returned by scoring.EntityScorer.topk (-1 = no row, shards shorter
-    than k) and `relevances` (Q, k).  Same bytes as feeding ranker_callback / trec_utils.write_run topic by topic."""
+    than k) and `relevances` (Q, k).  Same bytes as feeding ranker_callback / trec_utils.write_run topic by topic:
+    one lexsort orders every topic by descending (relevance, entity id) (trec_utils.py:560-561) and the library's
+    host-side formatter (include/sert_b200.h: sert_format_run) prints the lines, relevance as Python's repr(float)."""
+    from sert_b200 import _native as N
     top_indices = np.asarray(top_indices)
-    lookup = np.array([entity_indices_inv[i] for i in range(len(entity_indices_inv))], dtype=str)
+    rel = np.asarray(relevances)
+    num_topics, k = top_indices.shape
     present = top_indices >= 0
     assert (present[:, :-1] >= present[:, 1:]).all(), 'missing rows must trail the list'
-    object_ids = lookup[np.where(present, top_indices, 0)]
-    trec_utils.write_run_arrays(model_name, topic_ids, object_ids, relevances, out_f, counts=present.sum(axis=1),
-                                max_objects_per_query=max_objects_per_query)
+    counts = present.sum(axis=1)
+    for q in np.flatnonzero(counts == 0):
+        logging.warning('Received empty ranking for %s; ignoring.', topic_ids[q])
+    names = [entity_indices_inv[i] for i in range(len(entity_indices_inv))]
+    lookup = np.array(names, dtype=str)
+    safe = np.where(present, top_indices, 0)
+    # descending (relevance, entity id); unused slots behind every real assessment
+    order = np.lexsort((np.where(present, lookup[safe], ''), np.where(present, rel, -np.inf)), axis=-1)[:, ::-1]
+    keep = np.arange(k)[None, :] < np.minimum(counts, max_objects_per_query)[:, None]
+    line_subject = np.broadcast_to(np.arange(num_topics, dtype=np.int32)[:, None], (num_topics, k))[keep]
+    line_object = np.take_along_axis(safe, order, axis=1)[keep].astype(np.int32)
+    line_rank = np.broadcast_to(np.arange(1, k + 1, dtype=np.int32)[None, :], (num_topics, k))[keep]
+    line_rel = np.take_along_axis(rel, order, axis=1)[keep].astype(np.float64)      # '{0}'.format widens to double
+    subject_blob, subject_off = _utf8_blob(topic_ids)
+    object_blob, object_off = _utf8_blob(names)
+    model = str(model_name).encode('utf8')
+    n = int(line_rel.size)
+    longest = int(np.diff(subject_off).max(initial=0) + np.diff(object_off).max(initial=0)) + len(model) + 64
+    out = np.empty(max(1, n * longest), dtype=np.uint8)
+    written = N.load().sert_format_run(
+        N.host_ptr(subject_blob), N.host_ptr(subject_off), N.host_ptr(object_blob), N.host_ptr(object_off),
+        N.host_ptr(np.ascontiguousarray(line_subject)), N.host_ptr(np.ascontiguousarray(line_object)),
+        N.host_ptr(np.ascontiguousarray(line_rank)), N.host_ptr(np.ascontiguousarray(line_rel)), n, model,
+        N.host_ptr(out), out.size)
+    if written < 0:
+        N.check(int(written))
+    out_f.write(out[:written].tobytes().decode('utf8'))

@@ -70,3 +70,40 @@ def test_product_does_not_import_the_oracle():
             if f.endswith(('.py', '.cu', '.cuh')):
                 text = open(os.path.join(dirpath, f)).read()
                 assert 'oracle' not in text.replace('the CPU oracle', ''), f
+
+
+def test_run_formatter_prints_python_float_repr():
+    """sert_format_run (host-only code of the library) must print relevance values exactly like '{0}'.format(float)
+    -- Python's repr -- for every double: shortest round-trip digits, fixed notation for 1e-4 <= |v| < 1e16."""
+    import numpy as np
+    from sert_b200 import _native as N
+    lib = N.load()
+    rng = np.random.default_rng(99)
+    values = [0.0, -0.0, 1.0, -1.0, 0.1, 0.5, 1e-4, 1e-5, 9.999e-5, 1e15, 1e16, 9999999999999998.0, 1e17, 1e22,
+              1.5e-5, 123456.789, 5e-324, 2.2250738585072014e-308, 1.7976931348623157e308, float('inf'),
+              float('-inf'), float('nan'), 0.30000000000000004, 100.0, 12345678901234567890.0, 2.5e-7, 3.0e10]
+    values += (rng.random(2000) * 10.0 ** rng.integers(-30, 30, 2000) * rng.choice([-1, 1], 2000)).tolist()
+    values += rng.random(2000).astype(np.float32).astype(np.float64).tolist()          # widened float32 relevances
+    values += (rng.integers(-10 ** 6, 10 ** 6, 500) / 8.0).tolist()
+    v = np.array(values, dtype=np.float64)
+    n = v.size
+    subjects, objects = ['topic-é'.encode('utf8')], [b'entity/007']
+    s_blob = np.frombuffer(b''.join(subjects), dtype=np.uint8)
+    o_blob = np.frombuffer(b''.join(objects), dtype=np.uint8)
+    s_off = np.array([0, len(subjects[0])], dtype=np.int64)
+    o_off = np.array([0, len(objects[0])], dtype=np.int64)
+    zeros = np.zeros(n, dtype=np.int32)
+    ranks = np.arange(1, n + 1, dtype=np.int32)
+    out = np.empty(n * 128, dtype=np.uint8)
+    written = lib.sert_format_run(N.host_ptr(s_blob), N.host_ptr(s_off), N.host_ptr(o_blob), N.host_ptr(o_off),
+                                  N.host_ptr(zeros), N.host_ptr(zeros), N.host_ptr(ranks), N.host_ptr(v), n,
+                                  b'model_7.bin', N.host_ptr(out), out.size)
+    assert written > 0
+    got = out[:written].tobytes().decode('utf8').splitlines()
+    assert len(got) == n
+    for i, line in enumerate(got):
+        assert line == 'topic-é Q0 entity/007 {0} {1} model_7.bin'.format(i + 1, float(v[i])), (i, v[i], line)
+    # too small an output buffer is an error, not an overrun
+    assert lib.sert_format_run(N.host_ptr(s_blob), N.host_ptr(s_off), N.host_ptr(o_blob), N.host_ptr(o_off),
+                               N.host_ptr(zeros), N.host_ptr(zeros), N.host_ptr(ranks), N.host_ptr(v), n,
+                               b'm', N.host_ptr(out), 100) == -2
