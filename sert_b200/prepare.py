@@ -3,14 +3,57 @@ into the arrays of `data.npz`, and the `data.npz` / `meta` writers.
 
 Mirrors bin/prepare.py:373-416 (writers, instance weights) and :543-599 (`instances_and_labels_to_arrays`), same
 signatures and outputs; the per-non-zero Python loops of the reference (one `sorted(...)`, three `list.extend` per
-instance) are replaced by one pass that fills flat numpy arrays and a single lexsort.  Corpus reading, tokenising and
-windowing (bin/prepare.py:474-533, cvangysel io_utils) stay out of scope.
+instance) are replaced by one pass that fills flat numpy arrays and a single lexsort.  The windowing of a document's
+token stream (cvangysel io_utils.py:151-211, driven from bin/prepare.py:499-512) is here as strided array views;
+corpus reading and the character-level tokeniser stay out of scope.
 """
 import logging
 import pickle
 
 import numpy as np
 from scipy import sparse
+
+
+def windows_from_ids(ids, window_size, stride=1, padding_id=None):
+    """All windows the reference's generator yields for ONE eos-free run of in-vocabulary word ids
+    (cvangysel io_utils.py:151-211): full windows at offsets 0, stride, 2*stride, ...; when tokens remain behind the
+    last full window (or the run is shorter than a window) and `padding_id` is given, one more window padded to
+    `window_size`.  Returns an (n, window_size) array of ids' dtype; a strided view is copied once."""
+    ids = np.asarray(ids)
+    assert ids.ndim == 1 and 1 <= stride <= window_size
+    n = ids.shape[0]
+    if n >= window_size:
+        full = np.lib.stride_tricks.sliding_window_view(ids, window_size)[::stride]
+        consumed = (full.shape[0] - 1) * stride + window_size       # tokens read when the last full window was yielded
+    else:
+        full = np.empty((0, window_size), dtype=ids.dtype)
+        consumed = 0
+    new_tokens = n - consumed
+    if padding_id is None or new_tokens <= 0:
+        return np.ascontiguousarray(full)
+    # the generator keeps window_size - stride old tokens, reads the new ones, then pads
+    start = full.shape[0] * stride if full.shape[0] else 0
+    tail = np.full(window_size, padding_id, dtype=ids.dtype)
+    tail[:n - start] = ids[start:]
+    return np.concatenate([full, tail[None, :]], axis=0)
+
+
+def document_windows(tokens, words, window_size, stride=1, padding_token=None, eos_token='</s>', eos_chars=()):
+    """windowed_translated_token_stream (io_utils.py:151-211) as arrays: out-of-vocabulary tokens are dropped, an
+    end-of-sentence token clears the window (only full windows survive from the runs before it), the run that ends
+    the stream gets the padded tail.  `words`: {token: Word(id, count)}.  Returns (n, window_size) int64 ids."""
+    assert eos_token in words and (padding_token is None or padding_token in words)
+    runs, current = [], []
+    for token in tokens:
+        if token in eos_chars or token == eos_token:
+            runs.append(current)
+            current = []
+        elif token in words:
+            current.append(words[token].id)
+    padding_id = None if padding_token is None else words[padding_token].id
+    parts = [windows_from_ids(np.asarray(run, dtype=np.int64), window_size, stride) for run in runs]
+    parts.append(windows_from_ids(np.asarray(current, dtype=np.int64), window_size, stride, padding_id))
+    return np.concatenate(parts, axis=0) if parts else np.empty((0, window_size), dtype=np.int64)
 
 
 def instances_and_labels_to_arrays(instances, window_size, class_mapping, instance_dtype, shuffle):

@@ -11,6 +11,7 @@ What runs unmodified from /root/reference:
   * bin/query.py  callbacks   (LogLinearCallback, VectorSpaceCallback, compute_normalised_entropy)
   * bin/train.py  sparse_to_one_hot_multiple
   * bin/prepare.py instances_and_labels_to_arrays (and the w_train expression of main(), :395-399)
+  * cvangysel-common io_utils.windowed_translated_token_stream
   * cvangysel-common trec_utils.parse_query / parse_topics / write_run
 Third-party modules the reference imports but this path never calls (bs4, nltk, gensim) are
 stubbed with empty modules; cvangysel.sklearn_utils.neighbors_algorithm, which crashes on modern sklearn
@@ -261,6 +262,29 @@ def gen_prepare():
             'x': x.tolist(), 'x_dtype': str(x.dtype), 'indptr': y.indptr.tolist(), 'indices': y.indices.tolist(),
             'data': [float(v) for v in y.data], 'y_dtype': str(y.dtype), 'indices_dtype': str(y.indices.dtype),
             'shape': list(y.shape), 'w': [float(v) for v in w]}
+    # cvangysel io_utils.windowed_translated_token_stream (io_utils.py:151-211) on seeded token streams: out-of-vocabulary
+    # tokens, end-of-sentence tokens, every (window, stride) pair up to 6, with and without padding
+    import collections
+    import random
+    from cvangysel import io_utils as ref_io
+    Word = collections.namedtuple('Word', ['id', 'count'])
+    vocab = ['</s>', '<pad>'] + ['w%d' % i for i in range(25)]
+    words = {t: Word(i, 1) for i, t in enumerate(vocab)}
+    rnd = random.Random(20160816)
+    cases = []
+    for trial in range(120):
+        n = rnd.choice([0, 1, 2, 3, 5, 8, 13, 21, 34])
+        toks = ['</s>' if (trial % 3 == 0 and rnd.random() < 0.15) else rnd.choice(vocab[2:] + ['oov-a', 'oov-b'])
+                for _ in range(n)]
+        W = rnd.randint(1, 6)
+        stride = rnd.randint(1, W)
+        pad = rnd.choice([None, '<pad>'])
+        windows = list(ref_io.windowed_translated_token_stream(iter(toks), W, words, eos_chars=[], stride=stride,
+                                                                padding_token=pad))
+        cases.append({'tokens': toks, 'window_size': W, 'stride': stride, 'padding_token': pad,
+                      'windows': [list(w) for w in windows]})
+    out['window_vocab'] = vocab
+    out['window_cases'] = cases
     with open(os.path.join(HERE, 'prepare_ref.json'), 'w') as f:
         json.dump(out, f)
 

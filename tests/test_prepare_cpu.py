@@ -79,3 +79,26 @@ def test_edge_cases_and_file_round_trip(ref, tmp_path):
     with open(meta_path, 'rb') as f:
         objs = [pickle.load(f) for _ in range(5)]
     assert objs[3] == {0: 'ent-00'} and prepare.read_meta(meta_path)[2] == ['w']
+
+
+def test_document_windows_match_the_reference_generator(ref):
+    """cvangysel io_utils.windowed_translated_token_stream (io_utils.py:151-211) as strided arrays: 120 seeded token
+    streams with OOV tokens, end-of-sentence tokens, strides 1..window and optional padding (fixture made by running
+    the reference's generator)."""
+    import collections
+    Word = collections.namedtuple('Word', ['id', 'count'])
+    words = {t: Word(i, 1) for i, t in enumerate(ref['window_vocab'])}
+    seen_padded = seen_eos = 0
+    for case in ref['window_cases']:
+        got = prepare.document_windows(case['tokens'], words, case['window_size'], case['stride'],
+                                       case['padding_token'])
+        assert got.shape == (len(case['windows']), case['window_size']) and got.dtype == np.int64
+        assert got.tolist() == case['windows'], case
+        seen_padded += any(words['<pad>'].id in w for w in case['windows'])
+        seen_eos += '</s>' in case['tokens']
+    assert seen_padded > 10 and seen_eos > 10
+    # one run of ids, the building block: 7 tokens, window 3, stride 2 -> [0:3], [2:5], [4:7]; 8 tokens add a padded tail
+    assert prepare.windows_from_ids(np.arange(7), 3, 2, padding_id=99).tolist() == [[0, 1, 2], [2, 3, 4], [4, 5, 6]]
+    assert prepare.windows_from_ids(np.arange(8), 3, 2, padding_id=99).tolist()[-1] == [6, 7, 99]
+    assert prepare.windows_from_ids(np.arange(8), 3, 2).shape == (3, 3)
+    assert prepare.windows_from_ids(np.arange(2, dtype=np.uint16), 4, 1, padding_id=9).tolist() == [[0, 1, 9, 9]]
