@@ -92,6 +92,45 @@ def instances_and_labels_to_arrays(instances, window_size, class_mapping, instan
     return x, y
 
 
+def pack_document_windows(doc_windows, doc_entities, class_mapping, instance_dtype, shuffle,
+                          max_document_length=None):
+    """instances_and_labels_to_arrays (+ the w_train expression of bin/prepare.py:395-399) for instances that never
+    become Python tuples: `doc_windows[d]` is the (n_d, W) window array of document d (document_windows above),
+    `doc_entities[d]` the entity ids associated with it; every window of a document carries the candidate-centric
+    label of bin/prepare.py:436-439,516-523 (mass 1/len(entities) on each).  Documents are taken in the given order
+    and, with `shuffle`, permuted exactly like np.random.shuffle(instances) permutes the reference's list.
+    Returns x, y (CSR float32) and, when `max_document_length` is given, w = max_document_length / n_d per window."""
+    num_classes = len(class_mapping)
+    counts = np.array([w.shape[0] for w in doc_windows], dtype=np.int64)
+    num_instances = int(counts.sum())
+    window_size = doc_windows[0].shape[1] if len(doc_windows) else 0
+    x = (np.concatenate(doc_windows, axis=0) if num_instances else np.empty((0, window_size))).astype(instance_dtype)
+    label_cols = [np.sort(np.fromiter((class_mapping[e] for e in ents), dtype=np.int64, count=len(ents)))
+                  for ents in doc_entities]
+    label_sizes = np.array([c.shape[0] for c in label_cols], dtype=np.int64)
+    assert len(label_cols) == len(doc_windows) and (num_instances == 0 or label_sizes[counts > 0].min() > 0)
+    # row r of document d: the document's sorted columns, mass 1/|label|
+    row_sizes = np.repeat(label_sizes, counts)
+    indptr = np.zeros(num_instances + 1, dtype=np.int64)
+    np.cumsum(row_sizes, out=indptr[1:])
+    indices = (np.concatenate([np.tile(c, n) for c, n in zip(label_cols, counts)])
+               if num_instances else np.empty(0, dtype=np.int64))
+    data = np.repeat((1.0 / np.maximum(row_sizes, 1)).astype(np.float32), row_sizes)
+    y = sparse.csr_matrix((data, indices, indptr), shape=(num_instances, num_classes))
+    w = None
+    if max_document_length is not None:
+        w = np.repeat((float(max_document_length) / np.maximum(counts, 1)).astype(np.float32), counts)
+    if shuffle:
+        logging.info('Shuffling instance and label pairs.')
+        order = np.arange(num_instances)
+        np.random.shuffle(order)              # the permutation np.random.shuffle applies to a list of this length
+        x, y = x[order], y[order]
+        w = None if w is None else w[order]
+    y.indices = y.indices.astype(np.int32, copy=False)
+    y.indptr = y.indptr.astype(np.int32, copy=False)
+    return x, y, w
+
+
 def instance_weights(instances, instances_per_document, max_document_length):
     """bin/prepare.py:395-399: w = max_document_length / (#instances of the instance's document), float32."""
     return np.fromiter((float(max_document_length) / instances_per_document[doc_id] for doc_id, _, _ in instances),

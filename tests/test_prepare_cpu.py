@@ -102,3 +102,38 @@ def test_document_windows_match_the_reference_generator(ref):
     assert prepare.windows_from_ids(np.arange(8), 3, 2, padding_id=99).tolist()[-1] == [6, 7, 99]
     assert prepare.windows_from_ids(np.arange(8), 3, 2).shape == (3, 3)
     assert prepare.windows_from_ids(np.arange(2, dtype=np.uint16), 4, 1, padding_id=9).tolist() == [[0, 1, 9, 9]]
+
+
+@pytest.mark.parametrize('shuffle', [False, True])
+def test_pack_document_windows_equals_the_tuple_path(shuffle):
+    """Array-native packing == instances_and_labels_to_arrays (pinned to the reference above) on the instances the same
+    documents expand to, including the in-place shuffle driven by the global numpy RNG, and the w_train values."""
+    rng = np.random.default_rng(8)
+    W, V, n_ent = 4, 500, 9
+    entity_ids = ['e%d' % i for i in range(n_ent)]
+    class_mapping = {e: i for i, e in enumerate(rng.permutation(entity_ids).tolist())}
+    doc_windows, doc_entities, instances, per_doc = [], [], [], {}
+    for d in range(30):
+        n = int(rng.integers(0, 7))                      # documents without windows occur
+        win = rng.integers(0, V, (n, W))
+        ents = rng.choice(entity_ids, int(rng.integers(1, 4)), replace=False).tolist()
+        doc_windows.append(win)
+        doc_entities.append(ents)
+        label = {e: 1.0 / len(ents) for e in ents}
+        per_doc['d%d' % d] = n
+        instances += [('d%d' % d, tuple(row), label) for row in win.tolist()]
+    max_len = max(per_doc.values())
+    np.random.seed(99)
+    inst = list(instances)
+    x_ref, y_ref = prepare.instances_and_labels_to_arrays(inst, W, class_mapping, np.uint16, shuffle)
+    w_ref = prepare.instance_weights(inst, per_doc, max_len)
+    np.random.seed(99)
+    x, y, w = prepare.pack_document_windows(doc_windows, doc_entities, class_mapping, np.uint16, shuffle,
+                                            max_document_length=max_len)
+    assert x.dtype == np.uint16 and y.indices.dtype == np.int32
+    np.testing.assert_array_equal(x, x_ref)
+    assert y.shape == y_ref.shape and (y != y_ref).nnz == 0
+    np.testing.assert_array_equal(y.indptr, y_ref.indptr)
+    np.testing.assert_array_equal(y.indices, y_ref.indices)
+    np.testing.assert_array_equal(y.data, y_ref.data)
+    np.testing.assert_array_equal(w, w_ref)

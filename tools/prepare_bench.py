@@ -31,6 +31,15 @@ xa, ya = prepare.instances_and_labels_to_arrays(list(instances), W, class_mappin
 t_mine = time.perf_counter() - t0
 print('instances_and_labels_to_arrays: %d instances, %d labels: %.2f s (this repo)' % (n, ya.nnz, t_mine))
 
+# the same instances as per-document window arrays (50 consecutive instances share a document and its label)
+doc_windows = [x[i:i + 50] for i in range(0, n, 50)]
+doc_entities = [list(instances[i][2]) for i in range(0, n, 50)]
+t0 = time.perf_counter()
+xb, yb, wb = prepare.pack_document_windows(doc_windows, doc_entities, class_mapping, np.uint32, False, 50)
+t_arr = time.perf_counter() - t0
+print('pack_document_windows: %d documents -> %d instances: %.3f s (this repo, array-native)' % (
+    len(doc_windows), xb.shape[0], t_arr))
+
 Word = collections.namedtuple('Word', ['id', 'count'])
 vocab = ['</s>', '<pad>'] + ['w%d' % i for i in range(5000)]
 words = {t: Word(i, 1) for i, t in enumerate(vocab)}
