@@ -225,12 +225,18 @@ SERT_API int sert_scorer_create(const float *entities_host, int64_t rows, int32_
                        size_t arena_bytes, void *stream, sert_scorer **out);
 SERT_API int sert_scorer_destroy(sert_scorer *s);
 /* Scoring arithmetic.  1 (default) = tcgen05 tensor cores, coarse-then-exact: one bf16 GEMM scores every row, each
- * query keeps every row within a rigorous rounding-error margin of its k-th best (|q| max|e| 2^-7, see score.cu),
- * and the survivors are re-scored in fp32, so the returned top k is the exact fp32 top k at a third of the tensor
- * work; queries with too many near-ties for the margin fall back to mode 2 automatically.  2 = tensor cores on a
- * 3-term bf16 split of both operands (fp32-class scores throughout) + fp32 re-scoring.  0 = fp32 FMA tiles on CUDA
+ * query keeps every row within a rigorous rounding-error margin of its k-th best (|q - bf16(q)| max|e| +
+ * |bf16(q)| max|e - bf16(e)|, see score.cu), and the survivors are re-scored in fp32, so the returned top k is the
+ * exact fp32 top k at a third of the tensor work.  The sweep is ONE GEMM launch over the shard: a strided row sample
+ * seeds every query's threshold first, and one kernel selects, re-scores and sorts afterwards; a query whose list
+ * comes up short or holds too many near-ties sends the call to the chunked sweeps (3, then 2) automatically.
+ * 3 = the same coarse arithmetic in growing chunks with a prune after each (no threshold seed).  2 = tensor cores on
+ * a 3-term bf16 split of both operands (fp32-class scores throughout) + fp32 re-scoring.  0 = fp32 FMA tiles on CUDA
  * cores. */
 SERT_API int sert_scorer_set_mode(sert_scorer *s, int32_t mode);
+/* Host counters since creation: top-k calls answered by the seeded one-launch sweep / calls that fell back to the
+ * chunked sweeps (measurement and tests; no reference counterpart). */
+SERT_API int sert_scorer_stats(sert_scorer *s, int64_t *seeded_sweeps, int64_t *fallback_sweeps);
 /* Top-k by inner product of q query vectors (host f32 (q,d); normalise_q!=0 L2-normalises them,
  * bin/query.py:333-336) against the shard.  Outputs (q,k) global row ids and float32 inner products,
  * sorted by score descending (ties: lower row id first). */

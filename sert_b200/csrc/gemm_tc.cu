@@ -213,7 +213,7 @@ gemm_tc_kernel(const __grid_constant__ TcMap map_a, const __grid_constant__ TcMa
       int mt, nt, seq;
       for (int it = 0; cta_tile<BSTAT>(it, num_m_tiles, num_n_tiles, mt, nt, seq); ++it) {
         const int m0 = mt * BM;
-        const int n0 = (int)(args.n_begin + (long long)nt * BN);
+        const int n0 = (int)(args.n_begin + (long long)nt * BN * args.epi.tile_stride);
         if (BSTAT && seq == 0) {
           mbar_wait(bempty_bar, bphase ^ 1u);            // the previous n-tile's MMAs no longer read the B slots
           mbar_expect_tx(bfull_bar, (uint32_t)args.num_kb * B_STAGE_BYTES);
@@ -294,7 +294,7 @@ gemm_tc_kernel(const __grid_constant__ TcMap map_a, const __grid_constant__ TcMa
     int mt, nt, seq;
     for (int it = 0; cta_tile<BSTAT>(it, num_m_tiles, num_n_tiles, mt, nt, seq); ++it) {
       const int m0 = mt * BM;
-      const long long n0 = args.n_begin + (long long)nt * BN;
+      const long long n0 = args.n_begin + (long long)nt * BN * args.epi.tile_stride;
       const int gm = m0 + row;
       const bool row_ok = gm < args.M;
       // Rows are swept in increasing id order and tau only moves between launches, so a later row that
@@ -336,6 +336,33 @@ gemm_tc_kernel(const __grid_constant__ TcMap map_a, const __grid_constant__ TcMa
             }
           }
         }
+      } else if (ep.mode == TC_EPI_GROUPMAX) {
+        // ---- maxima over groups of 8 or 64 columns (full tiles only): the sample the scoring sweep seeds its
+        // thresholds from (score.cu: seed_tau_kernel)
+        float mx = -INFINITY;
+#pragma unroll 1
+        for (int ci = 0; ci < CHUNKS; ++ci) {
+          uint32_t v[32];
+          tc_ld_32x32(t_row + (uint32_t)(col_lo + ci * 32), v);
+          tc_wait_ld();
+          float m4[4];
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const float a = fmaxf(fmaxf(__uint_as_float(v[8 * j]), __uint_as_float(v[8 * j + 1])),
+                                  fmaxf(__uint_as_float(v[8 * j + 2]), __uint_as_float(v[8 * j + 3])));
+            const float b = fmaxf(fmaxf(__uint_as_float(v[8 * j + 4]), __uint_as_float(v[8 * j + 5])),
+                                  fmaxf(__uint_as_float(v[8 * j + 6]), __uint_as_float(v[8 * j + 7])));
+            m4[j] = fmaxf(a, b);
+          }
+          if (ep.group == 8) {
+            if (row_ok)
+              *reinterpret_cast<float4 *>(ep.gmax + (size_t)gm * ep.gmax_ld + (size_t)nt * (BN / 8) +
+                                          (col_lo + ci * 32) / 8) = make_float4(m4[0], m4[1], m4[2], m4[3]);
+          } else {
+            mx = fmaxf(mx, fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3])));
+          }
+        }
+        if (ep.group != 8 && row_ok) ep.gmax[(size_t)gm * ep.gmax_ld + (size_t)nt * (BN / COLS_PER_WARP) + col_lo / COLS_PER_WARP] = mx;
       } else {
         // ---- running top-k filter.  The chunk loops stay rolled: the epilogue's code must stay resident in
         // the instruction caches (a fully unrolled two-pass version measured 6x slower: the warps sat in

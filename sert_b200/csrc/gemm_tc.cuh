@@ -13,7 +13,7 @@
 
 namespace sert {
 
-enum TcEpilogueMode { TC_EPI_STORE = 0, TC_EPI_TOPK = 1 };
+enum TcEpilogueMode { TC_EPI_STORE = 0, TC_EPI_TOPK = 1, TC_EPI_GROUPMAX = 2 };
 
 struct TcEpilogue {
   int mode = TC_EPI_STORE;
@@ -28,6 +28,14 @@ struct TcEpilogue {
   int cap = 0;
   long long row_offset = 0;     // global id of B row 0
   int *overflow = nullptr;      // set to 1 when a candidate list is full
+  // TC_EPI_GROUPMAX (threshold seeding of the scoring sweep, score.cu): every n-tile must be full (256 valid rows).
+  // gmax[m * gmax_ld + tile * (256 / group) + c / group] = max over the `group` (8 or 64) columns around column c
+  // of n-tile `tile`; nothing else is written.
+  float *gmax = nullptr;
+  int gmax_ld = 0;
+  int group = 64;
+  // every mode: n-tile t covers B rows [n_begin + t * 256 * tile_stride, +256): a strided sample of the rows when > 1
+  int tile_stride = 1;
 };
 
 enum SplitRole { SPLIT_A = 0, SPLIT_B = 1 };

@@ -12,6 +12,7 @@
 // broken by lower row id, so selection and the final order are deterministic.
 #include "score.cuh"
 
+#include <math.h>
 #include <stdlib.h>
 #include <string.h>
 
@@ -139,62 +140,323 @@ __global__ void reset_topk_state_kernel(unsigned long long *tau, int *count, int
   if (q < Q) { tau[q] = 0ull; count[q] = 0; }
 }
 
-// Exact float32 re-scoring of the surviving candidates (tensor-core mode): the bf16x3 scores picked the
+// fp32 inner product of a query held in shared memory with one entity row, by a whole warp.  ONE summation order for
+// every caller (finalize_kernel, rescore_kernel), so a (query, row) pair scores bit-identically whichever path or
+// shard layout produced the candidate: lane l accumulates elements 4l..4l+3, 4(l+32).. with fmaf, then a butterfly.
+__device__ __forceinline__ float warp_dot(const float *__restrict__ qs, const float *__restrict__ e, int d, int lane) {
+  float s = 0.f;
+  if ((d & 3) == 0 && (reinterpret_cast<uintptr_t>(e) & 15) == 0) {
+    const float4 *e4 = reinterpret_cast<const float4 *>(e);
+    const float4 *q4 = reinterpret_cast<const float4 *>(qs);
+    for (int c = lane; c < (d >> 2); c += 32) {
+      const float4 ev = __ldg(e4 + c);
+      const float4 qv = q4[c];
+      s = fmaf(ev.x, qv.x, s); s = fmaf(ev.y, qv.y, s); s = fmaf(ev.z, qv.z, s); s = fmaf(ev.w, qv.w, s);
+    }
+  } else {
+    for (int c0 = lane * 4; c0 < d; c0 += 128) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        if (c0 + j < d) s = fmaf(__ldg(e + c0 + j), qs[c0 + j], s);
+    }
+  }
+  return warp_sum(s);
+}
+
+// Exact float32 re-scoring of the surviving candidates (tensor-core mode): the bf16 scores picked the
 // candidates, the returned scores and the final order come from fp32 dot products of the fp32 vectors.
 __global__ void __launch_bounds__(256) rescore_kernel(const float *__restrict__ Qm, const float *__restrict__ En,
                                                       int d, long long row_begin, unsigned long long *__restrict__ cand,
                                                       const int *__restrict__ count, int cap) {
-  extern __shared__ float qs[];
+  extern __shared__ __align__(16) float qs[];
   const int q = blockIdx.x;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
   const int n = min(count[q], cap);
   for (int c = threadIdx.x; c < d; c += blockDim.x) qs[c] = Qm[(size_t)q * d + c];
   __syncthreads();
   unsigned long long *list = cand + (size_t)q * cap;
-  for (int j = warp; j < n; j += 2 * nwarps) {
-    const int j2 = j + nwarps;
+  for (int j = warp; j < n; j += nwarps) {
     const unsigned int r0 = key_row(list[j]);
-    const unsigned int r1 = j2 < n ? key_row(list[j2]) : r0;
-    const float *e0 = En + (size_t)((long long)r0 - row_begin) * d;
-    const float *e1 = En + (size_t)((long long)r1 - row_begin) * d;
-    float s0 = 0.f, s1 = 0.f;
-    for (int c = lane; c < d; c += 32) {
-      s0 = fmaf(e0[c], qs[c], s0);
-      s1 = fmaf(e1[c], qs[c], s1);
-    }
-    s0 = warp_sum(s0);
-    s1 = warp_sum(s1);
-    if (lane == 0) {
-      list[j] = make_key(s0, r0);
-      if (j2 < n) list[j2] = make_key(s1, r1);
-    }
+    const float s0 = warp_dot(qs, En + (size_t)((long long)r0 - row_begin) * d, d, lane);
+    if (lane == 0) list[j] = make_key(s0, r0);
   }
 }
 
-// margin[q] = 2 eps_q (topk_sweep), one warp per query
-__global__ void __launch_bounds__(256) query_margin_kernel(const float *__restrict__ Qm, int Q, int d, float ent_norm_max,
-                                                           float *__restrict__ margin) {
+// Queries of a tensor-core sweep, one warp per query: the 3-term bf16 split row [hi | hi | mid] (the A operand of
+// gemm_tc.cuh), the reset of the query's list state, and the rigorous error margin of the COARSE scores (hi.hi term
+// alone):  q.e - qh.eh = (q - qh).e + qh.(e - eh)  =>  |coarse - exact| <= |q - qh| max|e| + |qh| max|e - eh|
+// (Cauchy-Schwarz, exact in real arithmetic; bf16 round-to-nearest has unit roundoff 2^-8, and measuring the two
+// residual norms instead of assuming the worst case 2^-8 |q| roughly halves the band), plus d 2^-22 |qh| max|eh| for
+// the fp32 accumulation of the exact bf16 products inside the tensor core (truncating adds: one ulp each).  Two rows
+// whose exact scores order one way can order the other way in the coarse scores only within 2 eps_q: margin = 2 eps_q.
+__global__ void __launch_bounds__(256) prep_queries_kernel(const float *__restrict__ Qm, int Q, int d, int Kp,
+                                                           __nv_bfloat16 *__restrict__ split, float ent_norm_max,
+                                                           float ent_err_max, float *__restrict__ margin,
+                                                           unsigned long long *__restrict__ tau, int *__restrict__ count) {
   const int q = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
   if (q >= Q) return;
-  float ss = 0.f;
-  for (int c = lane; c < d; c += 32) { const float v = Qm[(size_t)q * d + c]; ss = fmaf(v, v, ss); }
-  ss = warp_sum(ss);
+  __nv_bfloat16 *row = split + (size_t)q * 3 * Kp;
+  float e2 = 0.f, h2 = 0.f;
+  for (int c = lane; c < Kp; c += 32) {
+    const float x = c < d ? Qm[(size_t)q * d + c] : 0.f;
+    const __nv_bfloat16 hi = __float2bfloat16_rn(x);
+    const float fh = __bfloat162float(hi);
+    const float r = x - fh;                                  // exact (Sterbenz-like: fh is x rounded to 8 bits)
+    row[c] = hi;
+    row[Kp + c] = hi;
+    row[2 * Kp + c] = __float2bfloat16_rn(r);
+    e2 = fmaf(r, r, e2);
+    h2 = fmaf(fh, fh, h2);
+  }
+  e2 = warp_sum(e2);
+  h2 = warp_sum(h2);
   if (lane == 0) {
-    const float eps = sqrtf(ss) * ent_norm_max * (0.00390625f + 3.8147e-6f + (float)d * 1.1920929e-7f);
-    margin[q] = 2.0f * eps * 1.02f;
+    const float qh = sqrtf(h2);
+    const float eps = sqrtf(e2) * ent_norm_max + qh * ent_err_max + (float)d * 2.3841858e-7f * qh * ent_norm_max * 1.004f;
+    margin[q] = 2.0f * eps * 1.02f + 1e-30f;
+    tau[q] = 0ull;
+    count[q] = 0;
   }
 }
 
-// largest row norm, as ordered uint bits (norms are >= 0)
+// largest row norm and largest bf16-rounding residual norm, as ordered uint bits (norms are >= 0): out[0], out[1]
 __global__ void __launch_bounds__(256) row_norm_max_kernel(const float *__restrict__ E, long long rows, int d,
                                                            unsigned int *__restrict__ out) {
   const long long r = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (r >= rows) return;
-  float ss = 0.f;
-  for (int c = lane; c < d; c += 32) { const float v = E[(size_t)r * d + c]; ss = fmaf(v, v, ss); }
+  float ss = 0.f, rr = 0.f;
+  for (int c = lane; c < d; c += 32) {
+    const float v = E[(size_t)r * d + c];
+    const float res = v - __bfloat162float(__float2bfloat16_rn(v));
+    ss = fmaf(v, v, ss);
+    rr = fmaf(res, res, rr);
+  }
   ss = warp_sum(ss);
-  if (lane == 0) atomicMax(out, __float_as_uint(sqrtf(ss)));
+  rr = warp_sum(rr);
+  if (lane == 0) {
+    atomicMax(out, __float_as_uint(sqrtf(ss)));
+    atomicMax(out + 1, __float_as_uint(sqrtf(rr)));
+  }
+}
+
+// ---- seeded sweep: threshold seed from a strided row sample --------------------------------------------------
+// The sample GEMM (TC_EPI_GROUPMAX) left, per query, the maxima of G groups of g sampled rows.  The j-th largest
+// group maximum is a LOWER bound of the j-th largest sampled score, and with j/G ~ 1 - exp(-g T/rows) about T rows of
+// the shard score above it (topk_plan picks g, G, j for T ~ 5k).  tau = that value - margin; the one-launch sweep
+// then appends every row scoring above tau.  Nothing here has to be right for the result to be exact: finalize_kernel
+// verifies that the list holds >= k rows and that (k-th best - margin) clears tau, else the flag sends the call to
+// the multi-chunk sweep.  One warp per query; bitwise bisection on the order-preserving bits.
+__global__ void __launch_bounds__(256) seed_tau_kernel(const float *__restrict__ gmax, int ld, int G, int j,
+                                                       const float *__restrict__ margin,
+                                                       unsigned long long *__restrict__ tau, int Q) {
+  const int q = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (q >= Q) return;
+  unsigned int v[kSeedGroups / 32];
+#pragma unroll
+  for (int i = 0; i < kSeedGroups / 32; ++i) {
+    const int g = lane + 32 * i;
+    v[i] = g < G ? orderable(gmax[(size_t)q * ld + g]) : 0u;
+  }
+  unsigned int t = 0u;
+#pragma unroll 1
+  for (int bit = 31; bit >= 0; --bit) {
+    const unsigned int cand = t | (1u << bit);
+    unsigned int c = 0u;
+#pragma unroll
+    for (int i = 0; i < kSeedGroups / 32; ++i) c += v[i] >= cand ? 1u : 0u;
+    c = __reduce_add_sync(0xffffffffu, c);
+    if (c >= (unsigned int)j) t = cand;
+  }
+  if (lane == 0) tau[q] = make_key(unorderable(t) - margin[q], 0xffffffffu);
+}
+
+// ---- seeded sweep: selection + exact re-scoring + final order in ONE kernel, one warp per query ---------------
+// The list holds every row whose coarse score beat tau (a few hundred to a thousand keys, straight from the GEMM
+// epilogue, in L2).  (1) A 256-bin histogram between the list's smallest and largest score locates the bin of the
+// k-th best; Lf = the smallest score in that bin or above is a lower bound of the k-th best coarse score.  (2) Every
+// row with coarse score >= Lf - margin is kept: by the margin's construction this includes every row of the exact
+// top k (prep_queries_kernel).  (3) The survivors (k + the margin band) are re-scored with fp32 dot products, sorted
+// in shared memory, and the best k are written.  Sets *flag (=> multi-chunk sweep) when the list is short of k rows,
+// when Lf - margin does not clear the seeded tau (rows the guarantee needs may have been filtered), or when more
+// survivors than the shared-memory slots remain (masses of near-ties).
+struct FinalizeArgs {
+  const float *Qm;
+  const float *En;
+  int Q, d;
+  long long row_begin, rows;
+  const unsigned long long *cand;
+  const int *count;
+  int cap;
+  const unsigned long long *tau;
+  const float *margin;
+  int k, cmax;
+  int32_t *out_idx;
+  float *out_score;
+  int *flag;
+  int per_warp_bytes;
+};
+
+__global__ void __launch_bounds__(256) finalize_kernel(const FinalizeArgs a) {
+  extern __shared__ __align__(16) unsigned char fin_smem[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int q = blockIdx.x * (blockDim.x >> 5) + warp;
+  if (q >= a.Q) return;
+  unsigned char *mine = fin_smem + (size_t)warp * a.per_warp_bytes;
+  unsigned long long *keys = reinterpret_cast<unsigned long long *>(mine);
+  int *hist = reinterpret_cast<int *>(mine + (size_t)a.cmax * 8);
+  float *qs = reinterpret_cast<float *>(mine + (size_t)a.cmax * 8 + 1024);
+  const unsigned long long *list = a.cand + (size_t)q * a.cap;
+  const int n = min(a.count[q], a.cap);
+  const int need = (int)min((long long)a.k, a.rows);
+  const unsigned long long tk = a.tau[q];
+  const float tau_s = tk != 0ull ? key_score(tk) : -INFINITY;
+  int32_t *oi = a.out_idx + (size_t)q * a.k;
+  float *os = a.out_score + (size_t)q * a.k;
+  if (n < need || a.count[q] > a.cap) {
+    if (lane == 0) *a.flag = 1;
+    return;
+  }
+  if (need == 0) {
+    for (int i = lane; i < a.k; i += 32) { oi[i] = -1; os[i] = -INFINITY; }
+    return;
+  }
+  // (1) score range of the list, histogram, bin of the need-th best
+  float hi = -INFINITY, lo = INFINITY;
+  for (int i = lane; i < n; i += 32) {
+    const float s = key_score(list[i]);
+    hi = fmaxf(hi, s);
+    lo = fminf(lo, s);
+  }
+  hi = warp_max(hi);
+  lo = -warp_max(-lo);
+  const float scale = hi > lo ? 255.9f / (hi - lo) : 0.f;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) hist[lane * 8 + i] = 0;
+  __syncwarp();
+  for (int i = lane; i < n; i += 32) {
+    const int b = min(255, (int)((key_score(list[i]) - lo) * scale));
+    atomicAdd(&hist[b], 1);
+  }
+  __syncwarp();
+  int local[8], lsum = 0;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) { local[i] = hist[lane * 8 + i]; lsum += local[i]; }
+  int incl = lsum;                                           // suffix sums over lanes: lanes above hold higher bins
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const int v = __shfl_down_sync(0xffffffffu, incl, o);
+    if (lane + o < 32) incl += v;
+  }
+  const int above = incl - lsum;                             // keys in bins of higher lanes
+  int bstar = -1;
+  if (above < need && need <= above + lsum) {
+    int acc = above;
+#pragma unroll
+    for (int i = 7; i >= 0; --i) {
+      if (bstar < 0 && acc + local[i] >= need) bstar = lane * 8 + i;
+      acc += local[i];
+    }
+  }
+  bstar = __reduce_max_sync(0xffffffffu, bstar);
+  // (2) Lf = smallest score at or above that bin; survivors = everything within the margin below it
+  float lf = INFINITY;
+  for (int i = lane; i < n; i += 32) {
+    const float s = key_score(list[i]);
+    if (min(255, (int)((s - lo) * scale)) >= bstar) lf = fminf(lf, s);
+  }
+  lf = -warp_max(-lf);
+  const float thr = lf - a.margin[q];
+  if (tk != 0ull && !(thr > tau_s)) {
+    if (lane == 0) *a.flag = 1;
+    return;
+  }
+  int c = 0;
+  for (int i0 = 0; i0 < n; i0 += 32) {
+    const int i = i0 + lane;
+    unsigned long long key = 0ull;
+    bool keep = false;
+    if (i < n) {
+      key = list[i];
+      keep = key_score(key) >= thr;
+    }
+    const unsigned int m = __ballot_sync(0xffffffffu, keep);
+    const int pos = c + __popc(m & ((1u << lane) - 1u));
+    if (keep && pos < a.cmax) keys[pos] = key;
+    c += __popc(m);
+  }
+  if (c > a.cmax) {
+    if (lane == 0) *a.flag = 1;
+    return;
+  }
+  // (3) exact fp32 scores of the survivors
+  for (int cc = lane; cc < a.d; cc += 32) qs[cc] = a.Qm[(size_t)q * a.d + cc];
+  __syncwarp();
+  for (int j0 = 0; j0 < c; j0 += 4) {
+    unsigned int r[4];
+    float sc[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) r[i] = key_row(keys[min(j0 + i, c - 1)]);
+    if ((a.d & 3) == 0) {
+      // four rows in flight: the loads of a row are one or two 16-byte requests per lane, latency-bound on their own
+      const float4 *q4 = reinterpret_cast<const float4 *>(qs);
+      const float4 *e4[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+        e4[i] = reinterpret_cast<const float4 *>(a.En + (size_t)((long long)r[i] - a.row_begin) * a.d);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) sc[i] = 0.f;
+      for (int cc = lane; cc < (a.d >> 2); cc += 32) {
+        const float4 qv = q4[cc];
+        float4 ev[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) ev[i] = __ldg(e4[i] + cc);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          sc[i] = fmaf(ev[i].x, qv.x, sc[i]); sc[i] = fmaf(ev[i].y, qv.y, sc[i]);
+          sc[i] = fmaf(ev[i].z, qv.z, sc[i]); sc[i] = fmaf(ev[i].w, qv.w, sc[i]);
+        }
+      }
+#pragma unroll
+      for (int i = 0; i < 4; ++i) sc[i] = warp_sum(sc[i]);
+    } else {
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+        sc[i] = warp_dot(qs, a.En + (size_t)((long long)r[i] - a.row_begin) * a.d, a.d, lane);
+    }
+    __syncwarp();
+    if (lane < 4 && j0 + lane < c) {
+      const float mine_s = lane == 0 ? sc[0] : (lane == 1 ? sc[1] : (lane == 2 ? sc[2] : sc[3]));
+      const unsigned int mine_r = lane == 0 ? r[0] : (lane == 1 ? r[1] : (lane == 2 ? r[2] : r[3]));
+      keys[j0 + lane] = make_key(mine_s, mine_r);
+    }
+  }
+  // (4) order the survivors (bitonic, descending, in the warp's shared-memory slots) and write the best `need`
+  int n_pow2 = 32;
+  while (n_pow2 < c) n_pow2 <<= 1;
+  for (int i = c + lane; i < n_pow2; i += 32) keys[i] = 0ull;
+  for (int size = 2; size <= n_pow2; size <<= 1) {
+    for (int stride = size >> 1; stride > 0; stride >>= 1) {
+      __syncwarp();
+      for (int t = lane; t < (n_pow2 >> 1); t += 32) {
+        const int l = 2 * t - (t & (stride - 1));
+        const int h = l + stride;
+        const bool desc = ((l & size) == 0);
+        const unsigned long long x = keys[l], y = keys[h];
+        if ((x < y) == desc) { keys[l] = y; keys[h] = x; }
+      }
+    }
+  }
+  __syncwarp();
+  for (int i = lane; i < a.k; i += 32) {
+    if (i < need) {
+      oi[i] = (int32_t)key_row(keys[i]);
+      os[i] = key_score(keys[i]);
+    } else {
+      oi[i] = -1;
+      os[i] = -INFINITY;
+    }
+  }
 }
 
 // ---- prune by radix selection ---------------------------------------------------------------------------
@@ -438,6 +700,48 @@ static int topk_pass(const TopkState &s, const float *queries_dev, int Q, int k_
   return 0;
 }
 
+// ---- seeded sweep: plan ------------------------------------------------------------------------------------------
+// Picks the row sample (G groups of g rows = G*g/256 strided n-tiles) and the rank j of the group maximum that seeds
+// tau so that about T ~ 5k rows per query survive the one-launch sweep.  With x = g T / rows a group holds a row
+// above the T-th best score with probability 1 - exp(-x); j = that fraction of G.  j >= 16 keeps the survivor count
+// concentrated (relative spread ~ 1/sqrt(j)): P(fewer than k survive) ~ P(Gamma(j) < j k / T) < 1e-6 per query at
+// T = 5k; when the sample would have to exceed G = 256 groups T is raised instead.  Of the two group sizes the
+// epilogue offers, the smaller sample wins.  Shards of at most cap/2 rows need no seed (every row fits the list).
+struct SweepPlan {
+  bool seeded = false;
+  int g = 0, G = 0, j = 0;
+  long long stride = 1;       // n-tiles between sample tiles
+};
+
+static SweepPlan topk_plan(long long rows, int k, int cap) {
+  SweepPlan best;
+  const double T0 = std::max(5.0 * k, 320.0);
+  for (int g : {8, 64}) {
+    const int unit = 256 / g;                                 // groups per n-tile
+    double x = T0 * g / (double)rows;
+    if (x > 1.0) continue;
+    double frac = 1.0 - exp(-x);
+    long long G = (long long)ceil(32.0 / frac);
+    G = std::min<long long>((G + unit - 1) / unit * unit, kSeedGroups);
+    int j = (int)floor(frac * (double)G);
+    if (j < 16) {
+      j = 16;                                                 // raises the expected survivors to rows * -ln(1 - j/G) / g
+      const double T = (double)rows * -log(1.0 - (double)j / (double)G) / g;
+      if (T > cap / 4) continue;
+    }
+    const long long S = G * g;
+    if (S * 2 > rows) continue;
+    if (!best.seeded || S < (long long)best.G * best.g) {
+      best.seeded = true;
+      best.g = g; best.G = (int)G; best.j = j;
+      best.stride = ((rows + 255) / 256) / (S / 256);
+    }
+  }
+  return best;
+}
+
+static int finalize_per_warp_bytes(int cmax, int d) { return (int)align_up((size_t)cmax * 8 + 1024 + (size_t)d * 4, 16); }
+
 int topk_sweep(const TopkState &s, const float *queries_dev, int Q, int k, int32_t *out_idx, float *out_score,
                cudaStream_t st) {
   SERT_REQUIRE(k >= 1 && k <= s.cap / 2, "k exceeds the scorer's max_k");
@@ -447,17 +751,52 @@ int topk_sweep(const TopkState &s, const float *queries_dev, int Q, int k, int32
   // tensor-core mode keeps a margin of candidates beyond k so that bf16x3 rounding at the k-th place
   // cannot drop a true top-k row before the exact re-scoring
   const int k_sel = tensor ? std::min(s.cap / 2, k + 16) : k;
-  if (tensor && launch_split_bf16(queries_dev, Q, s.d, s.d, s.terms, SPLIT_A, s.q_split, st)) return -1;
+  if (tensor) {
+    // split rows [hi|hi|mid] of the queries, their coarse-score margins, list state reset
+    prep_queries_kernel<<<cdiv(Q, 8), 256, 0, st>>>(queries_dev, Q, s.d, s.kt / s.terms, s.q_split, s.ent_norm_max,
+                                                    s.ent_err_max, s.margin, s.tau, s.count);
+    SERT_LAUNCH_CHECK();
+  }
   int overflow = 1;
   if (tensor && s.coarse && s.terms == 3 && s.margin != nullptr) {
-    // Coarse-then-exact: ONE bf16 GEMM (the hi.hi term, a third of the tensor work) scores every row with an error
-    // of at most eps_q = |q| max|e| (2^-8 + 2^-18 + d 2^-23): bf16 round-to-nearest is 2^-9 relative per operand, the
-    // products sum to at most |q||e| (Cauchy-Schwarz), d 2^-23 covers the fp32 accumulation.  Every row of the exact
-    // top k then scores within 2 eps_q of the coarse k-th best, so the lists keep everything above (k-th - 2 eps_q);
-    // the survivors (k + a few dozen on these workloads) are re-scored in fp32 below.  Lists beyond max(1024, 4k) rows
-    // (many near-ties) raise the overflow flag and the bf16x3 sweep runs instead.
-    query_margin_kernel<<<cdiv(Q, 8), 256, 0, st>>>(queries_dev, Q, s.d, s.ent_norm_max, s.margin);
-    SERT_LAUNCH_CHECK();
+    // Coarse-then-exact: ONE bf16 GEMM (the hi.hi term, a third of the tensor work) scores every row with an error of
+    // at most eps_q (prep_queries_kernel).  Every row of the exact top k then scores within 2 eps_q of the coarse k-th
+    // best, so everything above (k-th - 2 eps_q) is kept and re-scored in fp32.
+    int cmax = 512;
+    while (cmax < 2 * k + 256) cmax <<= 1;
+    const int per_warp = finalize_per_warp_bytes(cmax, s.d);
+    const int warps = std::min(8, (200 * 1024) / per_warp);
+    const SweepPlan plan = topk_plan(s.rows, k, s.cap);
+    if (s.seeded && warps >= 1 && s.rows > 0 && (plan.seeded || s.rows <= s.cap / 2)) {
+      // Seeded one-launch sweep: sample GEMM -> tau -> ONE GEMM over the shard -> finalize (select, re-score, sort).
+      SERT_CUDA(cudaMemsetAsync(s.overflow, 0, sizeof(int), st));
+      TcEpilogue ep;
+      const int depth = s.kt / s.terms;     // first block of both split operands = the hi term
+      if (plan.seeded) {
+        ep.mode = TC_EPI_GROUPMAX;
+        ep.gmax = s.gmax; ep.gmax_ld = kSeedGroups; ep.group = plan.g; ep.tile_stride = (int)plan.stride;
+        const long long sample_rows = (long long)plan.G * plan.g;
+        if (launch_gemm_tc_ld(s.q_split, s.kt, Q, s.ent_split, s.kt, s.rows, 0, sample_rows, depth, ep, st)) return -1;
+        seed_tau_kernel<<<cdiv(Q, 8), 256, 0, st>>>(s.gmax, kSeedGroups, plan.G, plan.j, s.margin, s.tau, Q);
+        SERT_LAUNCH_CHECK();
+      }
+      ep = TcEpilogue();
+      ep.mode = TC_EPI_TOPK;
+      ep.tau = s.tau; ep.count = s.count; ep.cand = s.cand; ep.cap = s.cap; ep.row_offset = s.row_begin;
+      ep.overflow = s.overflow;
+      if (launch_gemm_tc_ld(s.q_split, s.kt, Q, s.ent_split, s.kt, s.rows, 0, s.rows, depth, ep, st)) return -1;
+      FinalizeArgs fa;
+      fa.Qm = queries_dev; fa.En = s.entities; fa.Q = Q; fa.d = s.d; fa.row_begin = s.row_begin; fa.rows = s.rows;
+      fa.cand = s.cand; fa.count = s.count; fa.cap = s.cap; fa.tau = s.tau; fa.margin = s.margin; fa.k = k;
+      fa.cmax = cmax; fa.out_idx = out_idx; fa.out_score = out_score; fa.flag = s.overflow; fa.per_warp_bytes = per_warp;
+      finalize_kernel<<<cdiv(Q, warps), warps * 32, (size_t)warps * per_warp, st>>>(fa);
+      SERT_LAUNCH_CHECK();
+      SERT_CUDA(cudaMemcpyAsync(&overflow, s.overflow, sizeof(int), cudaMemcpyDeviceToHost, st));
+      SERT_CUDA(cudaStreamSynchronize(st));
+      if (s.stats) ++s.stats[overflow ? 1 : 0];
+      if (!overflow) return 0;
+      // a list came up short, overflowed, or held too many near-ties: the multi-chunk sweeps below answer
+    }
     if (topk_pass(s, queries_dev, Q, k, true, st, true)) return -1;
     SERT_CUDA(cudaMemcpyAsync(&overflow, s.overflow, sizeof(int), cudaMemcpyDeviceToHost, st));
     SERT_CUDA(cudaStreamSynchronize(st));
@@ -474,16 +813,6 @@ int topk_sweep(const TopkState &s, const float *queries_dev, int Q, int k, int32
     SERT_LAUNCH_CHECK();
   }
   return launch_prune(s, Q, k, 1, out_idx, out_score, st);
-}
-
-int topk_prepare(int cap) {
-  // the prune keeps k <= cap/2 survivors (rounded up to a power of two) in dynamic shared memory
-  // once per device: room for the largest list the ABI admits (max_k <= 8192 -> cap <= 32768 -> 128 KB)
-  static std::atomic<uint64_t> configured{0};
-  (void)cap;
-  if (first_use_on_device(configured))
-    SERT_CUDA(cudaFuncSetAttribute(prune_select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 1024));
-  return 0;
 }
 
 // ---- merge of gathered per-shard lists: [parts][q][k] -> (q,k) ------------------------------------
@@ -516,6 +845,19 @@ __global__ void __launch_bounds__(256) merge_kernel(const int32_t *__restrict__ 
   }
 }
 
+int topk_prepare(int cap) {
+  // the prune keeps k <= cap/2 survivors (rounded up to a power of two) in dynamic shared memory
+  // once per device: room for the largest list the ABI admits (max_k <= 8192 -> cap <= 32768 -> 128 KB)
+  static std::atomic<uint64_t> configured{0};
+  (void)cap;
+  if (first_use_on_device(configured)) {
+    SERT_CUDA(cudaFuncSetAttribute(prune_select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 1024));
+    SERT_CUDA(cudaFuncSetAttribute(finalize_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    SERT_CUDA(cudaFuncSetAttribute(merge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+  }
+  return 0;
+}
+
 int launch_topk_merge(const int32_t *idx, const float *score, int parts, int Q, int k, int32_t *out_idx,
                       float *out_score, cudaStream_t st) {
   SERT_REQUIRE(parts >= 1 && k >= 1, "bad merge shape");
@@ -524,11 +866,7 @@ int launch_topk_merge(const int32_t *idx, const float *score, int parts, int Q, 
   while (n_pow2 < parts * k) n_pow2 <<= 1;
   const size_t smem = (size_t)n_pow2 * sizeof(unsigned long long);
   SERT_REQUIRE(smem <= 200 * 1024, "merge fan-in too large");
-  static size_t configured = 0;
-  if (smem > configured) {
-    SERT_CUDA(cudaFuncSetAttribute(merge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    configured = smem;
-  }
+  if (topk_prepare(0)) return -1;             // per-device shared-memory opt-in (was a process-wide static)
   merge_kernel<<<Q, 256, smem, st>>>(idx, score, parts, Q, k, out_idx, out_score, n_pow2);
   SERT_LAUNCH_CHECK();
   return 0;
@@ -546,6 +884,7 @@ struct sert_scorer {
   int32_t *out_idx = nullptr;   // (max_queries, max_k)
   float *out_score = nullptr;
   int max_k = 0;
+  long long stats[2] = {0, 0};
 };
 
 namespace sert {
@@ -569,8 +908,9 @@ static size_t carve_scorer(sert_scorer &sc, void *base, int64_t rows, int d, int
   sc.s.cand = reinterpret_cast<unsigned long long *>(take((size_t)max_queries * cap * sizeof(unsigned long long)));
   sc.s.tau = reinterpret_cast<unsigned long long *>(take((size_t)max_queries * sizeof(unsigned long long)));
   sc.s.count = reinterpret_cast<int *>(take((size_t)max_queries * sizeof(int)));
-  sc.s.overflow = reinterpret_cast<int *>(take(2 * sizeof(int)));      // [1]: scratch of row_norm_max_kernel
+  sc.s.overflow = reinterpret_cast<int *>(take(4 * sizeof(int)));      // [1], [2]: scratch of row_norm_max_kernel
   sc.s.margin = reinterpret_cast<float *>(take((size_t)max_queries * sizeof(float)));
+  sc.s.gmax = reinterpret_cast<float *>(take((size_t)max_queries * kSeedGroups * sizeof(float)));
   sc.queries = reinterpret_cast<float *>(take((size_t)max_queries * d * sizeof(float)));
   sc.s.terms = 3;
   sc.s.kt = sc.s.terms * tc_padded_k(d);
@@ -611,6 +951,7 @@ int sert_scorer_create(const float *entities_host, int64_t rows, int32_t d, int6
   }
   sc->st = static_cast<cudaStream_t>(stream);
   sc->s.row_begin = row_begin;
+  sc->s.stats = sc->stats;
   if (topk_prepare(sc->s.cap)) { delete sc; return -1; }
   if (rows > 0) {
     cudaError_t e = cudaMemcpyAsync(sc->s.entities, entities_host, (size_t)rows * d * sizeof(float),
@@ -624,27 +965,36 @@ int sert_scorer_create(const float *entities_host, int64_t rows, int32_t d, int6
     }
   }
   sc->s.mode = SCORE_TENSOR;
-  unsigned int norm_bits = 0u;
+  unsigned int norm_bits[2] = {0u, 0u};
   if (rows > 0) {
     unsigned int *scratch = reinterpret_cast<unsigned int *>(sc->s.overflow + 1);
-    cudaMemsetAsync(scratch, 0, sizeof(unsigned int), sc->st);
+    cudaMemsetAsync(scratch, 0, 2 * sizeof(unsigned int), sc->st);
     row_norm_max_kernel<<<cdiv(rows, 8), 256, 0, sc->st>>>(sc->s.entities, rows, d, scratch);
     count_launch();
-    cudaMemcpyAsync(&norm_bits, scratch, sizeof(unsigned int), cudaMemcpyDeviceToHost, sc->st);
+    cudaMemcpyAsync(norm_bits, scratch, 2 * sizeof(unsigned int), cudaMemcpyDeviceToHost, sc->st);
   }
   cudaError_t e = cudaStreamSynchronize(sc->st);
   if (e == cudaSuccess) e = cudaGetLastError();
   if (e != cudaSuccess) { delete sc; set_error(cudaGetErrorString(e)); return -1; }
-  memcpy(&sc->s.ent_norm_max, &norm_bits, sizeof(float));
+  memcpy(&sc->s.ent_norm_max, &norm_bits[0], sizeof(float));
+  memcpy(&sc->s.ent_err_max, &norm_bits[1], sizeof(float));
   *out = sc;
   return 0;
 }
 
 int sert_scorer_set_mode(sert_scorer *s, int32_t mode) {
   SERT_REQUIRE(s, "null scorer");
-  SERT_REQUIRE(mode == SCORE_FMA || mode == SCORE_TENSOR || mode == 2, "unknown scoring mode");
+  SERT_REQUIRE(mode >= 0 && mode <= 3, "unknown scoring mode");
   s->s.coarse = mode == 2 ? 0 : 1;      // 2: tensor cores without the coarse first sweep (bf16x3 scores throughout)
-  s->s.mode = mode == 2 ? SCORE_TENSOR : mode;
+  s->s.seeded = mode == 3 ? 0 : 1;      // 3: coarse sweep in growing chunks with a prune after each (no threshold seed)
+  s->s.mode = mode == SCORE_FMA ? SCORE_FMA : SCORE_TENSOR;
+  return 0;
+}
+
+int sert_scorer_stats(sert_scorer *s, int64_t *seeded_sweeps, int64_t *fallback_sweeps) {
+  SERT_REQUIRE(s && seeded_sweeps && fallback_sweeps, "null argument");
+  *seeded_sweeps = s->stats[0];
+  *fallback_sweeps = s->stats[1];
   return 0;
 }
 

@@ -34,7 +34,14 @@ struct TopkState {
   int coarse = 1;
   float *margin = nullptr;              // (max_queries,)
   float ent_norm_max = 0.f;             // largest L2 norm of an entity row
+  float ent_err_max = 0.f;              // largest L2 norm of (row - bf16(row)): the rows' share of the coarse error
+  // seeded single-launch sweep (score.cu: topk_sweep): group maxima of a strided row sample, (max_queries, kSeedGroups)
+  float *gmax = nullptr;
+  int seeded = 1;                       // 0: always the multi-chunk sweep (tests, diagnostics)
+  long long *stats = nullptr;           // host counters: [0] sweeps answered by the seeded path, [1] sweeps that fell back
 };
+
+constexpr int kSeedGroups = 256;        // most group maxima per query the threshold seed selects from
 
 int launch_normalise_rows(const float *in, float *out, int64_t rows, int d, cudaStream_t st);
 int topk_prepare(int cap);

@@ -40,10 +40,17 @@ class EntityScorer(object):
         self.handle = handle
 
     def set_mode(self, mode):
-        """'tensor' (default: one coarse bf16 tcgen05 GEMM with a rigorous score margin, exact fp32 re-scoring of the
-        survivors, automatic fall-back to 'tensor3' on too many near-ties), 'tensor3' (bf16x3 GEMM + fp32 re-scoring)
-        or 'fma' (fp32 CUDA-core tiles)."""
-        N.check(self.lib.sert_scorer_set_mode(self.handle, {'fma': 0, 'tensor': 1, 'tensor3': 2}[mode]))
+        """'tensor' (default: one coarse bf16 tcgen05 GEMM launch with seeded thresholds and a rigorous score margin,
+        exact fp32 re-scoring of the survivors, automatic fall-back on short lists / too many near-ties),
+        'tensor_chunked' (the same arithmetic in growing chunks, no threshold seed), 'tensor3' (bf16x3 GEMM + fp32
+        re-scoring) or 'fma' (fp32 CUDA-core tiles)."""
+        N.check(self.lib.sert_scorer_set_mode(self.handle, {'fma': 0, 'tensor': 1, 'tensor3': 2, 'tensor_chunked': 3}[mode]))
+
+    def stats(self):
+        """(calls answered by the seeded one-launch sweep, calls that fell back to the chunked sweeps)."""
+        a, b = N.c_int64(0), N.c_int64(0)
+        N.check(self.lib.sert_scorer_stats(self.handle, N.ctypes.byref(a), N.ctypes.byref(b)))
+        return int(a.value), int(b.value)
 
     def close(self):
         if getattr(self, 'handle', None):

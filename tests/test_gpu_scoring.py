@@ -11,7 +11,7 @@ def exact_topk(E, q, k):
     return order, np.take_along_axis(s, order, axis=1)
 
 
-@pytest.mark.parametrize('mode', ['tensor', 'tensor3', 'fma'])
+@pytest.mark.parametrize('mode', ['tensor', 'tensor_chunked', 'tensor3', 'fma'])
 @pytest.mark.parametrize('rows,d,Q,k', [(5000, 128, 37, 100), (12345, 256, 130, 10), (300, 64, 5, 100),
                                         (64, 32, 3, 64), (9000, 20, 65, 128), (20000, 300, 257, 100)])
 def test_topk_matches_exact(rows, d, Q, k, mode):
@@ -84,7 +84,7 @@ def test_merge_of_shards_equals_single_device():
     np.testing.assert_array_equal(os_.cpu().numpy(), full_score)
 
 
-@pytest.mark.parametrize('mode', ['tensor', 'tensor3', 'fma'])
+@pytest.mark.parametrize('mode', ['tensor', 'tensor_chunked', 'tensor3', 'fma'])
 def test_adversarial_ascending_scores_take_the_exact_fallback(mode):
     """Scores that grow with the row id defeat the optimistic threshold (every later row survives): the
     candidate lists overflow and the sweep must fall back to the conservative, overflow-free pass."""
@@ -144,7 +144,7 @@ def test_randomised_shapes_match_exact():
     from oracle import sert_oracle as O
     from sert_b200.scoring import EntityScorer
     rng = np.random.default_rng(2026)
-    for trial in range(10):
+    for trial in range(16):
         rows = int(rng.choice([1, 7, 63, 200, 1500, 9000, 40000]))
         d = int(rng.choice([3, 10, 50, 64, 100, 128, 257]))
         Q = int(rng.integers(1, 90))
@@ -152,7 +152,7 @@ def test_randomised_shapes_match_exact():
         E = O.normalise_rows(rng.standard_normal((rows, d)))
         q = O.normalise_rows(rng.standard_normal((Q, d)))
         sc = EntityScorer(E, max_queries=32, max_k=100)
-        sc.set_mode(['tensor', 'fma', 'tensor3'][trial % 3])
+        sc.set_mode(['tensor', 'fma', 'tensor3', 'tensor_chunked'][trial % 4])
         idx, score = sc.topk(q, k)
         kk = min(k, rows)
         ref_idx, ref_score = exact_topk(E, q, kk)
@@ -161,3 +161,78 @@ def test_randomised_shapes_match_exact():
         gaps = np.abs(np.diff(ref_score, axis=1)).min(axis=1) > 2e-6 if kk > 1 else np.ones(Q, bool)
         assert (idx[gaps][:, :kk] == ref_idx[gaps]).all(), (rows, d, Q, k)
         sc.close()
+
+
+def test_seeded_sweep_answers_ordinary_shards_and_agrees_with_the_chunked_sweep():
+    """The one-launch sweep (strided sample -> seeded thresholds -> one GEMM -> finalize) answers random shards
+    without falling back, and returns bit-identical lists and scores to the chunked coarse sweep."""
+    from oracle import sert_oracle as O
+    from sert_b200.scoring import EntityScorer
+    rng = np.random.default_rng(99)
+    for rows, d, Q, k in [(50000, 128, 300, 100), (6250, 128, 200, 100), (130000, 256, 64, 100), (20000, 64, 50, 10)]:
+        E = O.normalise_rows(rng.standard_normal((rows, d)))
+        q = O.normalise_rows(rng.standard_normal((Q, d)))
+        sc = EntityScorer(E, max_queries=512, max_k=128)
+        idx, score = sc.topk(q, k)
+        assert sc.stats() == (1, 0), (rows, d, sc.stats())
+        sc.set_mode('tensor_chunked')
+        idx2, score2 = sc.topk(q, k)
+        np.testing.assert_array_equal(idx, idx2)
+        np.testing.assert_array_equal(score, score2)
+        ref_idx, ref_score = exact_topk(E, q, k)
+        np.testing.assert_allclose(score, ref_score, rtol=0, atol=2e-6)
+        gaps = np.abs(np.diff(ref_score, axis=1)).min(axis=1) > 1e-6
+        assert (idx[gaps] == ref_idx[gaps]).all()
+        sc.close()
+
+
+def test_seeded_sweep_falls_back_when_the_sample_misleads():
+    """50 rows almost parallel to the query sit exactly in the sampled tiles, one per sample group: the seeded
+    threshold lands just below their score, fewer than k rows survive the sweep, and the call must fall back to the
+    chunked sweep and still return the exact top k."""
+    from oracle import sert_oracle as O
+    from sert_b200.scoring import EntityScorer
+    rng = np.random.default_rng(7)
+    rows, d, k = 20000, 64, 100
+    E = O.normalise_rows(rng.standard_normal((rows, d))) * np.float32(0.5)
+    q = O.normalise_rows(rng.standard_normal((3, d)))
+    # plan for (20000 rows, k=100): groups of 8 rows, 192 groups = 6 sample tiles, every 13th n-tile (score.cu: topk_plan)
+    n_tiles = (rows + 255) // 256
+    stride = n_tiles // 6
+    for i in range(50):
+        E[(i % 6) * stride * 256 + 8 * (i // 6)] = q[0] * np.float32(0.9)
+    sc = EntityScorer(E, max_queries=8, max_k=128)
+    idx, score = sc.topk(q, k)
+    assert sc.stats() == (0, 1), sc.stats()
+    ref_idx, ref_score = exact_topk(E, q, k)
+    np.testing.assert_allclose(score, ref_score, rtol=0, atol=2e-6)
+    gaps = np.abs(np.diff(ref_score, axis=1)).min(axis=1) > 1e-6
+    assert (idx[gaps] == ref_idx[gaps]).all()
+
+
+def test_coarse_margin_covers_bf16_rounding_midpoints():
+    """operands next to bf16 rounding midpoints make the coarse (hi.hi) score err by the full unit
+    roundoff 2^-8 per operand.  Family A rows (and the query) sit just below a midpoint and round DOWN: exact score
+    1.0073, coarse 1.0.  Family B rows alternate an element that rounds UP with an exactly representable one:
+    exact 1.0038, coarse 1.00195.  The coarse order is the reverse of the exact one, so without a margin of the full
+    error bound the coarse top k would be all B; the exact top k is all A."""
+    from sert_b200.scoring import EntityScorer
+    d, k, rows = 64, 20, 12000
+    rng = np.random.default_rng(4)
+    base = np.float32(1.0 / 8.0)
+    down = np.float32(1.0 + 2.0 ** -8 - 2.0 ** -12)
+    q = np.full((1, d), down * base, np.float32)
+    E = (rng.standard_normal((rows, d)) * 0.01).astype(np.float32)     # background, scores near 0
+    pos = rng.choice(rows, 60, replace=False)
+    E[pos[:30]] = down * base
+    fam_b = np.empty(d, np.float32)
+    fam_b[0::2] = np.float32(1.0 + 2.0 ** -8 + 2.0 ** -12) * base
+    fam_b[1::2] = np.float32(1.0 - 2.0 ** -8) * base
+    E[pos[30:]] = fam_b
+    sc = EntityScorer(E, max_queries=4, max_k=32)
+    for mode in ('tensor', 'tensor_chunked'):
+        sc.set_mode(mode)
+        idx, score = sc.topk(q, k)
+        ref_idx, ref_score = exact_topk(E, q, k)
+        np.testing.assert_allclose(score, ref_score, rtol=0, atol=2e-6)
+        assert set(idx[0].tolist()) <= set(pos[:30].tolist()), mode
