@@ -81,12 +81,27 @@ typedef struct sert_config {
 
 typedef struct sert_model sert_model;     /* opaque */
 typedef struct sert_scorer sert_scorer;   /* opaque */
+typedef struct sert_comm sert_comm;       /* opaque: one NCCL communicator (one rank = one process = one GPU) */
 
 /* ---- library --------------------------------------------------------------------------- */
 SERT_API int         sert_abi_version(void);
 SERT_API const char *sert_last_error(void);
 /* number of kernels this library has launched since load (bench.py's gpu_launches) */
 SERT_API uint64_t    sert_launch_count(void);
+
+/* ---- communicator (no reference counterpart: the reference is single-device) --------
+ * The collectives of the sharded paths -- the ONE all-gather of per-shard top-k lists of row-sharded scoring and the
+ * five small exchanges of an entity-sharded log-linear step -- are NCCL calls issued by the library on the stream of
+ * the scorer / model.  The host ships nothing but the 128-byte unique id: rank 0 calls sert_comm_unique_id, every
+ * rank receives the bytes over any channel (sert_b200/comm.py uses torch.distributed's store) and calls
+ * sert_comm_init on its own device (cudaSetDevice first; collective: returns when all ranks have joined).
+ * libnccl.so.2 is loaded on first use (the copy already in the process when torch is imported). */
+SERT_API int sert_comm_unique_id(void *id_out, size_t capacity /* >= 128 */);
+SERT_API int sert_comm_init(int32_t rank, int32_t world, const void *unique_id, sert_comm **out);
+SERT_API int sert_comm_destroy(sert_comm *c);
+/* rank, world, NCCL version code, collectives issued and payload bytes so far (any pointer may be NULL) */
+SERT_API int sert_comm_info(sert_comm *c, int32_t *rank, int32_t *world, int32_t *nccl_version, int64_t *collectives,
+                            int64_t *bytes);
 
 /* ---- model life cycle: replaces the model constructors, sert/models.py:806-878,1026-1105 -- */
 /* HBM bytes the model needs for parameters, optimiser state, gradients and workspaces. */
@@ -149,6 +164,11 @@ SERT_API int sert_model_profile_read(sert_model *m, double *update_ms_total, int
 typedef int (*sert_exchange_fn)(void *ctx, int32_t op, float *buf_dev, size_t count);
 SERT_API int sert_model_set_entity_shard(sert_model *m, int32_t rank, int32_t world, int64_t entity_begin,
                                          int64_t entities_total, sert_exchange_fn fn, void *ctx);
+
+/* The same sharding with the five exchanges issued by the library as NCCL collectives on the model's stream
+ * (rank / world come from the communicator); the callback form above remains for gloo / single-device tests. */
+SERT_API int sert_model_set_entity_shard_comm(sert_model *m, sert_comm *comm, int64_t entity_begin,
+                                              int64_t entities_total);
 
 /* ---- device-resident data set: replaces the theano.shared X/Y/W variables, sert/models.py:470-480 -- */
 /* x_dev (N,W) int32; labels either one-hot y_dev (N,) int32 (vector space, bin/train.py:186-245) or CSR
@@ -237,6 +257,12 @@ SERT_API int sert_scorer_set_mode(sert_scorer *s, int32_t mode);
 /* Host counters since creation: top-k calls answered by the seeded one-launch sweep / calls that fell back to the
  * chunked sweeps (measurement and tests; no reference counterpart). */
 SERT_API int sert_scorer_stats(sert_scorer *s, int64_t *seeded_sweeps, int64_t *fallback_sweeps);
+/* Row-sharded scoring: this scorer holds rows [row_begin, row_begin+rows) of the global matrix and
+ * `comm` joins the other shards.  Every top-k call then runs the local sweep, ONE ncclAllGather of the packed
+ * (row id, score)[q,k] lists (q*k*8 bytes per rank) and a k-way merge on the scorer's stream, and returns the top k of
+ * the GLOBAL matrix on every rank -- the same list a single device returns (keys carry global row ids; ties order by
+ * row id).  All ranks must issue the same calls.  comm = NULL detaches. */
+SERT_API int sert_scorer_set_comm(sert_scorer *s, sert_comm *comm);
 /* Top-k by inner product of q query vectors (host f32 (q,d); normalise_q!=0 L2-normalises them,
  * bin/query.py:333-336) against the shard.  Outputs (q,k) global row ids and float32 inner products,
  * sorted by score descending (ties: lower row id first). */

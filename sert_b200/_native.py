@@ -49,6 +49,13 @@ SIGNATURES = {
     'sert_model_set_step': (c_int, [c_void_p, c_int64]),
     'sert_model_get_step': (c_int, [c_void_p, ctypes.POINTER(c_int64)]),
     'sert_model_set_entity_shard': (c_int, [c_void_p, c_int32, c_int32, c_int64, c_int64, c_void_p, c_void_p]),
+    'sert_comm_unique_id': (c_int, [c_void_p, c_size_t]),
+    'sert_comm_init': (c_int, [c_int32, c_int32, c_void_p, ctypes.POINTER(c_void_p)]),
+    'sert_comm_destroy': (c_int, [c_void_p]),
+    'sert_comm_info': (c_int, [c_void_p, ctypes.POINTER(c_int32), ctypes.POINTER(c_int32), ctypes.POINTER(c_int32),
+                               ctypes.POINTER(c_int64), ctypes.POINTER(c_int64)]),
+    'sert_model_set_entity_shard_comm': (c_int, [c_void_p, c_void_p, c_int64, c_int64]),
+    'sert_scorer_set_comm': (c_int, [c_void_p, c_void_p]),
     'sert_model_profile': (c_int, [c_void_p, c_int]),
     'sert_model_set_fused': (c_int, [c_void_p, c_int]),
     'sert_model_set_overlap': (c_int, [c_void_p, c_int]),

@@ -16,6 +16,7 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include "comm.cuh"
 #include "gemm_tc.cuh"
 #include "kernels.cuh"
 #include "topk_keys.cuh"
@@ -817,8 +818,9 @@ int topk_sweep(const TopkState &s, const float *queries_dev, int Q, int k, int32
 
 // ---- merge of gathered per-shard lists: [parts][q][k] -> (q,k) ------------------------------------
 __global__ void __launch_bounds__(256) merge_kernel(const int32_t *__restrict__ idx, const float *__restrict__ score,
-                                                    int parts, int Q, int k, int32_t *__restrict__ out_idx,
-                                                    float *__restrict__ out_score, int n_pow2) {
+                                                    size_t part_stride, int parts, int Q, int k,
+                                                    int32_t *__restrict__ out_idx, float *__restrict__ out_score,
+                                                    int n_pow2) {
   extern __shared__ unsigned long long keys[];
   const int q = blockIdx.x;
   const int n = parts * k;
@@ -826,7 +828,7 @@ __global__ void __launch_bounds__(256) merge_kernel(const int32_t *__restrict__ 
     unsigned long long key = 0ull;
     if (i < n) {
       const int p = i / k, j = i % k;
-      const size_t src = ((size_t)p * Q + q) * k + j;
+      const size_t src = (size_t)p * part_stride + (size_t)q * k + j;
       const int32_t id = idx[src];
       if (id >= 0) key = make_key(score[src], (unsigned int)id);
     }
@@ -859,7 +861,8 @@ int topk_prepare(int cap) {
 }
 
 int launch_topk_merge(const int32_t *idx, const float *score, int parts, int Q, int k, int32_t *out_idx,
-                      float *out_score, cudaStream_t st) {
+                      float *out_score, cudaStream_t st, size_t part_stride) {
+  if (part_stride == 0) part_stride = (size_t)Q * k;
   SERT_REQUIRE(parts >= 1 && k >= 1, "bad merge shape");
   if (Q == 0) return 0;
   int n_pow2 = 2;
@@ -867,7 +870,7 @@ int launch_topk_merge(const int32_t *idx, const float *score, int parts, int Q, 
   const size_t smem = (size_t)n_pow2 * sizeof(unsigned long long);
   SERT_REQUIRE(smem <= 200 * 1024, "merge fan-in too large");
   if (topk_prepare(0)) return -1;             // per-device shared-memory opt-in (was a process-wide static)
-  merge_kernel<<<Q, 256, smem, st>>>(idx, score, parts, Q, k, out_idx, out_score, n_pow2);
+  merge_kernel<<<Q, 256, smem, st>>>(idx, score, part_stride, parts, Q, k, out_idx, out_score, n_pow2);
   SERT_LAUNCH_CHECK();
   return 0;
 }
@@ -885,7 +888,25 @@ struct sert_scorer {
   float *out_score = nullptr;
   int max_k = 0;
   long long stats[2] = {0, 0};
+  // row-sharded scoring (sert_scorer_set_comm): gathered per-shard lists, world blocks of [ids (Q,k) | scores (Q,k)]
+  sert_comm *comm = nullptr;
+  int32_t *gathered = nullptr;
 };
+
+// Top k of the GLOBAL entity matrix on every rank: local sweep into this rank's block of the gather buffer, ONE
+// all-gather of the packed (row id, score)[Q,k] lists (Q k 8 bytes per rank), k-way merge.  Keys carry global row
+// ids and ties order by row id, so the merged list equals the single-device list.
+static int scorer_topk(sert_scorer *s, const float *q_dev, int q, int k, int32_t *out_idx, float *out_score) {
+  if (s->comm == nullptr || s->comm->world == 1) return sert::topk_sweep(s->s, q_dev, q, k, out_idx, out_score, s->st);
+  const size_t block = (size_t)2 * q * k;                    // 32-bit words per rank
+  int32_t *mine = s->gathered + (size_t)s->comm->rank * block;
+  if (sert::topk_sweep(s->s, q_dev, q, k, mine, reinterpret_cast<float *>(mine + (size_t)q * k), s->st)) return -1;
+  if (sert::comm_all_gather(s->comm, mine, s->gathered, block * 4, s->st)) return -1;
+  return sert::launch_topk_merge(s->gathered, reinterpret_cast<const float *>(s->gathered + (size_t)q * k), s->comm->world,
+                                 q, k, out_idx, out_score, s->st, block);
+}
+
+
 
 namespace sert {
 static size_t carve_scorer(sert_scorer &sc, void *base, int64_t rows, int d, int max_queries, int max_k) {
@@ -998,9 +1019,19 @@ int sert_scorer_stats(sert_scorer *s, int64_t *seeded_sweeps, int64_t *fallback_
   return 0;
 }
 
+int sert_scorer_set_comm(sert_scorer *s, sert_comm *comm) {
+  SERT_REQUIRE(s, "null scorer");
+  if (s->gathered) { cudaStreamSynchronize(s->st); cudaFree(s->gathered); s->gathered = nullptr; }
+  s->comm = comm;
+  if (comm != nullptr && comm->world > 1)
+    SERT_CUDA(cudaMalloc(&s->gathered, (size_t)comm->world * 2 * s->s.max_queries * s->max_k * sizeof(int32_t)));
+  return 0;
+}
+
 int sert_scorer_destroy(sert_scorer *s) {
   if (s) {
     cudaStreamSynchronize(s->st);
+    if (s->gathered) cudaFree(s->gathered);
     delete s;
   }
   return 0;
@@ -1016,7 +1047,7 @@ int sert_scorer_topk_dev(sert_scorer *s, const float *queries_dev, int32_t q, in
     if (launch_normalise_rows(queries_dev, s->queries, q, s->s.d, s->st)) return -1;
     qq = s->queries;
   }
-  return topk_sweep(s->s, qq, q, k, out_idx_dev, out_score_dev, s->st);
+  return scorer_topk(s, qq, q, k, out_idx_dev, out_score_dev);
 }
 
 int sert_scorer_topk_host(sert_scorer *s, const float *queries_host, int32_t q, int32_t normalise_q, int32_t k,
@@ -1028,7 +1059,7 @@ int sert_scorer_topk_host(sert_scorer *s, const float *queries_host, int32_t q, 
   SERT_CUDA(cudaMemcpyAsync(s->queries, queries_host, (size_t)q * s->s.d * sizeof(float), cudaMemcpyHostToDevice,
                             s->st));
   if (normalise_q && launch_normalise_rows(s->queries, s->queries, q, s->s.d, s->st)) return -1;
-  if (topk_sweep(s->s, s->queries, q, k, s->out_idx, s->out_score, s->st)) return -1;
+  if (scorer_topk(s, s->queries, q, k, s->out_idx, s->out_score)) return -1;
   SERT_CUDA(cudaMemcpyAsync(out_idx_host, s->out_idx, (size_t)q * k * sizeof(int32_t), cudaMemcpyDeviceToHost, s->st));
   SERT_CUDA(cudaMemcpyAsync(out_score_host, s->out_score, (size_t)q * k * sizeof(float), cudaMemcpyDeviceToHost,
                             s->st));

@@ -47,7 +47,8 @@ int launch_normalise_rows(const float *in, float *out, int64_t rows, int d, cuda
 int topk_prepare(int cap);
 int topk_sweep(const TopkState &s, const float *queries_dev, int Q, int k, int32_t *out_idx, float *out_score,
                cudaStream_t st);
+// part p's lists start at idx + p * part_stride / score + p * part_stride (0 = Q * k: dense [part][q][k] arrays)
 int launch_topk_merge(const int32_t *idx, const float *score, int parts, int Q, int k, int32_t *out_idx,
-                      float *out_score, cudaStream_t st);
+                      float *out_score, cudaStream_t st, size_t part_stride = 0);
 
 }  // namespace sert

@@ -7,6 +7,7 @@
 #include <atomic>
 #include <vector>
 
+#include "comm.cuh"
 #include "kernels.cuh"
 #include "gemm_tc.cuh"
 #include "ll_kernels.cuh"
@@ -96,6 +97,7 @@ struct sert_model {
   int64_t e_begin = 0, e_total = 0;
   sert_exchange_fn exchange = nullptr;
   void *exchange_ctx = nullptr;
+  sert_comm *comm = nullptr;       // set: the exchanges are NCCL collectives issued by the library itself (comm.cu)
   float *xstats = nullptr;         // [kMaxShards][2][B*W] gathered (row max, row sum)
   float *smax = nullptr, *ssum = nullptr, *adot = nullptr, *racc = nullptr;
   // host-batch staging
@@ -857,6 +859,22 @@ int sert_model_set_entity_shard(sert_model *m, int32_t rank, int32_t world, int6
   for (int s = 0; s < m->nseg; ++s)
     if (m->seg[s].offset == m->off[SERT_PARAM_WORD_REPR]) m->seg[s].regularised = rank == 0 ? 1 : 2;
   return 0;
+}
+
+// the exchange "callback" of a model that shards over a library communicator: NCCL on the model's stream
+static int nccl_exchange(void *ctx, int32_t op, float *buf, size_t count) {
+  sert_model *m = static_cast<sert_model *>(ctx);
+  if (op == SERT_XCHG_ALLREDUCE_SUM) return comm_all_reduce_sum_f32(m->comm, buf, count, m->st);
+  if (op == SERT_XCHG_ALLGATHER)
+    return comm_all_gather(m->comm, buf + (size_t)m->comm->rank * count, buf, count * sizeof(float), m->st);
+  set_error("unknown exchange op");
+  return -1;
+}
+
+int sert_model_set_entity_shard_comm(sert_model *m, sert_comm *comm, int64_t entity_begin, int64_t entities_total) {
+  SERT_REQUIRE(m && comm, "null argument");
+  m->comm = comm;
+  return sert_model_set_entity_shard(m, comm->rank, comm->world, entity_begin, entities_total, nccl_exchange, m);
 }
 
 int sert_model_profile(sert_model *m, int enable) {

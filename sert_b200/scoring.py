@@ -1,8 +1,8 @@
 """Entity scoring on the device: query x all-entities inner products with a fused running top-k.
 
 Replaces the sklearn NearestNeighbors / cdist + argsort of VectorSpaceCallback.query
-(bin/query.py:280-318).  ``ShardedScorer`` row-shards the entity matrix over the ranks of a
-torch.distributed (NCCL) group and merges per-shard top-k lists after ONE all-gather.
+(bin/query.py:280-318).  ``ShardedScorer`` row-shards the entity matrix over one process per GPU; the ONE
+all-gather of per-shard top-k lists and the merge run inside the library (NCCL, csrc/comm.cu).
 """
 import numpy as np
 
@@ -113,7 +113,9 @@ def unpack_lists(gathered):
 
 
 def all_gather_lists(idx, score, group=None):
-    """The single exchange step of sharded scoring: every rank receives every rank's (ids, scores)[Q,k]."""
+    """The exchange step of sharded scoring restated over torch.distributed (gloo in the CPU tests of the host-side
+    merge logic; the product path does this all-gather inside the library): every rank receives every rank's
+    (ids, scores)[Q,k]."""
     import torch
     import torch.distributed as dist
     packed = pack_lists(idx, score)
@@ -134,42 +136,36 @@ def shard_bounds(num_rows, world_size, rank):
 
 
 class ShardedScorer(object):
-    """Row-sharded scoring over a torch.distributed group: local GEMM + top-k, ONE all-gather of the
-    per-shard (idx, score)[Q,k] lists, k-way merge on every rank."""
+    """Row-sharded scoring, one process per GPU: local GEMM + top-k, ONE all-gather of the per-shard
+    (idx, score)[Q,k] lists, k-way merge on every rank -- all three inside libsert_b200 on the scorer's stream
+    (``sert_scorer_set_comm``; the all-gather is an ncclAllGather the library issues itself).  ``comm`` is a
+    ``sert_b200.comm.Communicator``; by default one is built over the initialised torch.distributed group, which is
+    used for nothing but shipping the 128-byte NCCL unique id."""
 
     def __init__(self, entities_full_or_shard, num_rows_total, group=None, is_shard=False, normalise=False,
-                 max_queries=1024, max_k=128):
-        import torch.distributed as dist
-        self.dist = dist
-        self.group = group
-        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
-        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+                 max_queries=1024, max_k=128, comm=None):
+        if comm is None:
+            import torch.distributed as dist
+            if dist.is_initialized() and dist.get_world_size(group) > 1:
+                from sert_b200.comm import Communicator
+                comm = Communicator.from_torch_distributed(group)
+        self.comm = comm
+        self.world = comm.world if comm is not None else 1
+        self.rank = comm.rank if comm is not None else 0
         begin, end = shard_bounds(num_rows_total, self.world, self.rank)
         shard = entities_full_or_shard if is_shard else entities_full_or_shard[begin:end]
         assert shard.shape[0] == end - begin
         self.local = EntityScorer(shard, normalise=normalise, max_queries=max_queries, max_k=max_k, row_begin=begin)
+        if self.world > 1:
+            N.check(self.local.lib.sert_scorer_set_comm(self.local.handle, comm.handle))
 
     def topk_dev(self, queries_dev, k, normalise_queries=False):
-        torch = _torch()
-        idx, score = self.local.topk_dev(queries_dev, k, normalise_queries)
-        if self.world == 1:
-            return idx, score
-        Q = idx.shape[0]
-        g_idx, g_score = all_gather_lists(idx, score, self.group)
-        out_idx = torch.empty_like(idx)
-        out_score = torch.empty_like(score)
-        N.check(self.local.lib.sert_topk_merge_dev(N.dev_ptr(g_idx), N.dev_ptr(g_score), self.world, Q, k,
-                                                   N.dev_ptr(out_idx), N.dev_ptr(out_score),
-                                                   N.c_void_p(torch.cuda.current_stream().cuda_stream)))
-        return out_idx, out_score
+        """(idx, score) of the GLOBAL matrix on every rank; asynchronous on the scorer's stream."""
+        return self.local.topk_dev(queries_dev, k, normalise_queries)
 
     def topk(self, queries, k, normalise_queries=False):
-        torch = _torch()
-        queries = np.ascontiguousarray(queries, dtype=np.float32)
-        outs_i, outs_s = [], []
-        for done in range(0, queries.shape[0], self.local.max_queries):
-            q = torch.from_numpy(queries[done:done + self.local.max_queries]).to(self.local.device)
-            i, s = self.topk_dev(q, k, normalise_queries)
-            outs_i.append(i.cpu().numpy())
-            outs_s.append(s.cpu().numpy())
-        return np.concatenate(outs_i), np.concatenate(outs_s)
+        """Host in / host out through sert_scorer_topk_host (H2D of the queries, D2H of the merged lists)."""
+        return self.local.topk(queries, k, normalise_queries)
+
+    def close(self):
+        self.local.close()

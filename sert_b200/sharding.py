@@ -6,7 +6,9 @@ The reference trains on one device.  Here the dense layer ``W (dw,E), b (E,)`` o
 five exchange points of a step (include/sert_b200.h ``sert_exchange_fn``); the classes below implement that
 callback:
 
-* ``DistExchange``  -- ``torch.distributed`` (NCCL over NVLink on GPUs, gloo in the CPU tests);
+* ``CommExchange``  -- no callback at all: the library issues the NCCL collectives itself (csrc/comm.cu); the
+  product path on GPUs;
+* ``DistExchange``  -- ``torch.distributed`` through the callback (gloo in the CPU tests);
 * ``LocalExchange`` -- all shards in ONE process on ONE device, one host thread per shard (the C-ABI's threading
   contract), used to test the sharded arithmetic on a single GPU.
 
@@ -36,9 +38,12 @@ class Exchange(object):
     calls = 0
     floats = 0
 
-    def bind(self, arena):
+    def bind(self, arena, stream=None):
         """Returns the C callback for a model whose HBM arena is ``arena`` (one exchange may serve several
-        models of the same rank, e.g. a resumed copy)."""
+        models of the same rank, e.g. a resumed copy).  ``stream``: the model's torch stream -- the collectives are
+        issued under it, whatever stream is current when the library calls back (the library's kernels run on the
+        stream the model was created with; a collective ordered on another stream would race with them)."""
+        import contextlib
         import torch
         base, nbytes = arena.data_ptr(), arena.numel()
 
@@ -48,12 +53,14 @@ class Exchange(object):
                 off = int(buf) - base
                 assert 0 <= off and off + 4 * n <= nbytes, 'exchange buffer outside the arena'
                 view = arena[off:off + 4 * n].view(torch.float32)
-                if op == XCHG_ALLREDUCE_SUM:
-                    self.all_reduce_sum(view)
-                elif op == XCHG_ALLGATHER:
-                    self.all_gather(view, int(count))
-                else:
-                    raise ValueError('unknown exchange op %d' % op)
+                scope = torch.cuda.stream(stream) if (stream is not None and arena.is_cuda) else contextlib.nullcontext()
+                with scope:
+                    if op == XCHG_ALLREDUCE_SUM:
+                        self.all_reduce_sum(view)
+                    elif op == XCHG_ALLGATHER:
+                        self.all_gather(view, int(count))
+                    else:
+                        raise ValueError('unknown exchange op %d' % op)
                 self.calls += 1
                 self.floats += int(count)
                 return 0
@@ -103,6 +110,21 @@ class DistExchange(Exchange):
         out = np.concatenate(parts, axis=-1)
         assert out.shape[-1] == total
         return out
+
+
+class CommExchange(DistExchange):
+    """The five exchanges issued by libsert_b200 itself as NCCL collectives on the model's stream
+    (``sert_model_set_entity_shard_comm``): no callback, no torch collective on the step.  torch.distributed is
+    used to ship the unique id (``Communicator.from_torch_distributed``) and, off the hot path, to gather column
+    shards on the host for checkpoints / predict_fn (``gather_columns``)."""
+
+    def __init__(self, comm=None, group=None):
+        DistExchange.__init__(self, group)
+        if comm is None:
+            from sert_b200.comm import Communicator
+            comm = Communicator.from_torch_distributed(group)
+        assert (comm.rank, comm.world) == (self.rank, self.world)
+        self.comm = comm
 
 
 class LocalExchange(object):
@@ -161,7 +183,12 @@ class _LocalShard(Exchange):
 
 def attach(native_model, exchange, entity_begin, entities_total):
     """Registers ``exchange`` with a log-linear _NativeModel created over the shard's column count."""
-    cb = exchange.bind(native_model.arena)
+    if isinstance(exchange, CommExchange):
+        N.check(native_model.lib.sert_model_set_entity_shard_comm(
+            native_model.handle, exchange.comm.handle, int(entity_begin), int(entities_total)))
+        native_model.exchange = exchange
+        return
+    cb = exchange.bind(native_model.arena, getattr(native_model, 'stream', None))
     N.check(native_model.lib.sert_model_set_entity_shard(
         native_model.handle, exchange.rank, exchange.world, int(entity_begin), int(entities_total),
         ctypes.cast(cb, N.c_void_p), None))

@@ -157,7 +157,7 @@ p = H.ll_problem(41, V=3000, E=1003, dw=64, W=5, B=128, n_batches=4)
 kw = dict(batch_size=p['B'], window_size=p['W'], representations_init=p['R'], output_layer_size=p['E'],
           regularization_lambda=0.01, training_set=p['train'], validation_set=p['val'],
           dense_init=(p['Wd'], p['bd']))
-sharded = models.LanguageModel(entity_shard=sharding.DistExchange(), **kw)
+sharded = models.LanguageModel(entity_shard=sharding.CommExchange(), **kw)   # NCCL inside the library
 single = models.LanguageModel(**kw)
 order = [3, 1, 0, 2]
 n, mean = sharded.train(order=order)
@@ -167,9 +167,15 @@ H.close(mean, mean1, what='epoch mean loss')
 H.close(sharded.validation_error()[0], single.validation_error()[0], rtol=2e-4, what='validation error')
 H.close(sharded.get_representations(), single.get_representations(), rtol=2e-4, what='R')
 H.close(sharded.get_dense()[0], single.get_dense()[0], rtol=2e-4, what='Wd')
+info = sharded._native.exchange.comm.info()
+assert info['collectives'] > 0 and info['world'] == world, info
+# the callback form (torch.distributed collectives ordered on the model's stream) gives the same numbers
+legacy = models.LanguageModel(entity_shard=sharding.DistExchange(), **kw)
+n2, mean2 = legacy.train(order=order)
+H.close(mean2, mean, rtol=1e-5, what='callback exchange vs library exchange')
 dist.barrier()
 if rank == 0:
-    print('LL_SHARDED_OK world=%%d' %% world)
+    print('LL_SHARDED_OK world=%%d nccl=%%d collectives=%%d' %% (world, info['nccl_version'], info['collectives']))
 dist.destroy_process_group()
 '''
 

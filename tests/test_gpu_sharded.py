@@ -33,9 +33,16 @@ full = EntityScorer(E, max_queries=128, max_k=128)
 ref_idx, ref_score = full.topk(q, k)
 assert (idx == ref_idx).all(), (rank, np.argwhere(idx != ref_idx)[:5])
 np.testing.assert_array_equal(score, ref_score)
+info = sharded.comm.info()
+assert info['collectives'] >= 1 and info['world'] == world, info       # the all-gather ran inside the library
+qd = torch.from_numpy(q).cuda()
+di, ds = sharded.topk_dev(qd, k)
+torch.cuda.synchronize()
+assert (di.cpu().numpy() == ref_idx).all()
+np.testing.assert_array_equal(ds.cpu().numpy(), ref_score)
 dist.barrier()
 if rank == 0:
-    print('SHARDED_OK world=%%d' %% world)
+    print('SHARDED_OK world=%%d nccl=%%d' %% (world, info['nccl_version']))
 dist.destroy_process_group()
 '''
 
