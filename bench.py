@@ -30,6 +30,9 @@ CFG2 = dict(V=100000, E=50000, dw=128, de=128, W=10, B=4096, k=10, lam=0.01)
 CFG3 = dict(Q=10000, E=50000, d=128, k=100)
 CFG4 = dict(Q=10000, E=1000000, d=256, k=100)
 METRIC = '(word,entity) pairs/sec train'
+WORKLOAD = ('BASELINE.json configs[1]: VectorSpaceLanguageModel V=100k E=50k d=128 window=10 B=4096 k=10 lambda=0.01 '
+            '(Adam + dense L2, float32)')
+MIN_TIMED_S = 0.4           # the K timed steps are repeated as whole blocks until the timed region is at least this long
 UNIT = 'pairs/s'
 
 
@@ -162,24 +165,22 @@ def run_reference(args, rank, world):
         return
     from oracle import sert_oracle as O
     cfg = CFG2
-    steps, warm = args.steps, args.warmup
-    sample_steps = min(steps, 8)
-    p = make_problem(0, sample_steps + min(warm, 1))
+    sample_steps, warm = args.steps, args.warmup          # exactly what the driver asked for; one step = one full batch
+    p = make_problem(0, sample_steps + warm)
     orc = O.VectorSpaceOracle(cfg['B'], p['R'], p['Wp'], p['bp'], p['Eemb'], cfg['lam'], p['train'], p['val'])
-    for j in range(min(warm, 1)):
+    for j in range(warm):
         orc.train_batch(j, p['neg'][j])
     t0 = time.perf_counter()
     for j in range(sample_steps):
-        orc.train_batch(min(warm, 1) + j, p['neg'][min(warm, 1) + j])
+        orc.train_batch(warm + j, p['neg'][warm + j])
     dt = time.perf_counter() - t0
     value = sample_steps * cfg['B'] / dt
     cores = len(os.sched_getaffinity(0))
     line = {
         'impl': 'reference', 'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': args.gpus,
-        'steps': sample_steps, 'warmup': min(warm, 1), 'ms_per_step': 1e3 * dt / sample_steps,
+        'steps': sample_steps, 'warmup': warm, 'ms_per_step': 1e3 * dt / sample_steps,
         'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
-        'config': {'workload': 'BASELINE.json configs[1]: VectorSpaceLanguageModel V=100k E=50k d=128 window=10 '
-                               'B=4096 k=10 lambda=0.01', 'parallelism': 'cpu'},
+        'config': {'workload': WORKLOAD, 'parallelism': 'cpu'},
         'cpu_baseline': {'value': value, 'unit': UNIT, 'cores': cores, 'kind': 'port',
                          'sample': '%d training batches of 4096 pairs (numpy f32 oracle port of sert/models.py; '
                                    'BLAS uses %d threads, elementwise passes are single-threaded like '
@@ -224,14 +225,29 @@ def run_ours(args, rank, world, local_rank):
                                        N.c_void_p(neg_dev.data_ptr() + lo * cfg['B'] * cfg['k'] * 4), lo))
 
     # ---- device-resident throughput ("value") ----
+    # One block = the K timed steps (batches warm..warm+K-1).  A block of K=20 steps lasts 2.4 ms, too short for the
+    # clock sampler and for the driver's wall clock to vouch for, so the block is repeated R times back to back
+    # (further passes over the same K batches: the same kernels on the same shapes) until the timed region reaches
+    # MIN_TIMED_S; ms_per_step = region / (R * K).
     train(0, warm)
     barrier()
-    launches0 = N.launch_count()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    train(warm, n_batches)
+    ev1.record()
+    barrier()
+    first_losses = np.empty(n_batches, np.float32)
+    N.check(lib.sert_losses_fetch(nat.handle, 0, n_batches, N.host_ptr(first_losses)))
+    est = torch.tensor([max(ev0.elapsed_time(ev1), 1e-3)], dtype=torch.float64, device='cuda')
+    if world > 1:
+        dist.all_reduce(est, op=dist.ReduceOp.MAX)
+    repeats = max(1, int(np.ceil(MIN_TIMED_S * 1e3 / float(est.item()))))
+    launches0 = N.launch_count()
     with ClockSampler(local_rank) as clocks:
         barrier()
         ev0.record()
-        train(warm, n_batches)
+        for _ in range(repeats):
+            train(warm, n_batches)
         ev1.record()
         barrier()
     launches = N.launch_count() - launches0
@@ -242,7 +258,8 @@ def run_ours(args, rank, world, local_rank):
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms_max = float(t.item())
-    value = world * steps * cfg['B'] / (ms_max * 1e-3)
+    timed_steps = repeats * steps
+    value = world * timed_steps * cfg['B'] / (ms_max * 1e-3)
 
     # ---- roofline of the dominant kernel (dense Adam+L2 update), CUDA events around each launch ----
     N.check(lib.sert_model_profile(nat.handle, 1))
@@ -281,15 +298,17 @@ def run_ours(args, rank, world, local_rank):
     for b in range(warm):
         e2e_step(b)
     barrier()
+    sync_repeats = max(1, repeats // 4)
     t0 = time.perf_counter()
-    for b in range(warm, n_batches):
-        e2e_step(b)
+    for _ in range(sync_repeats):
+        for b in range(warm, n_batches):
+            e2e_step(b)
     torch.cuda.synchronize()
     e2e_sync_s = time.perf_counter() - t0
     te = torch.tensor([e2e_sync_s], dtype=torch.float64, device='cuda')
     if world > 1:
         dist.all_reduce(te, op=dist.ReduceOp.MAX)
-    e2e_sync_value = world * steps * B / float(te.item())
+    e2e_sync_value = world * sync_repeats * steps * B / float(te.item())
 
     # the same, pipelined: batch b is copied and enqueued before the loss of batch b-1 is waited for and checked
     ticket, prev, lossv = N.c_int64(0), None, N.ctypes.c_float(0)
@@ -313,18 +332,19 @@ def run_ours(args, rank, world, local_rank):
     prev = None
     barrier()
     t0 = time.perf_counter()
-    for b in range(warm, n_batches):
-        t = e2e_async_step(b)
-        if prev is not None:
-            e2e_wait(prev)
-        prev = t
+    for _ in range(repeats):
+        for b in range(warm, n_batches):
+            t = e2e_async_step(b)
+            if prev is not None:
+                e2e_wait(prev)
+            prev = t
     e2e_wait(prev)
     torch.cuda.synchronize()
     e2e_s = time.perf_counter() - t0
     te = torch.tensor([e2e_s], dtype=torch.float64, device='cuda')
     if world > 1:
         dist.all_reduce(te, op=dist.ReduceOp.MAX)
-    e2e_value = world * steps * B / float(te.item())
+    e2e_value = world * timed_steps * B / float(te.item())
     h2d = B * cfg['W'] * 4 + B * 4 + B * 4 + B * cfg['k'] * 4
     model._native.close()
     del model
@@ -346,13 +366,12 @@ def run_ours(args, rank, world, local_rank):
     loglinear_stress = None if os.environ.get('SERT_BENCH_SKIP_CFG5') else leg(run_loglinear_cfg5, rank, world, barrier)
 
     if rank == 0:
-        cpu = leg(cpu_baseline_sample)
+        cpu = leg(cpu_baseline_sample, p, first_losses)
         line = {
             'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': steps, 'warmup': warm,
-            'ms_per_step': ms_max / steps, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
+            'ms_per_step': ms_max / timed_steps, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
             'dtype': 'f32', 'data': 'synthetic',
-            'config': {'workload': 'BASELINE.json configs[1]: VectorSpaceLanguageModel V=100k E=50k d=128 window=10 '
-                                   'B=4096 k=10 lambda=0.01 (Adam + dense L2, float32)',
+            'config': {'workload': WORKLOAD,
                        'global_batch': world * B,
                        'parallelism': 'single' if world == 1 else 'replicas x%d (no training collective)' % world,
                        'l2_policy': 'working set (params+Adam state+grads = 307 MB) larger than L2; no flush',
@@ -370,10 +389,19 @@ def run_ours(args, rank, world, local_rank):
                          'achieved': achieved, 'peak': peak, 'unit': 'GB/s', 'frac': achieved / peak,
                          'traffic': traffic, 'peak_source': peak_src,
                          'algorithmic_bytes_per_launch': bpl.value, 'kernel_ms': upd_ms,
-                         'kernel_share_of_step': upd_ms / (ms_max / steps),
+                         'kernel_share_of_step': upd_ms / (ms_max / timed_steps),
                          'step_algorithmic_bytes': step_bytes,
-                         'step_frac_of_hbm_peak': step_bytes / (ms_max / steps * 1e-3) / 1e9 / peak},
+                         'step_frac_of_hbm_peak': step_bytes / (ms_max / timed_steps * 1e-3) / 1e9 / peak},
             'cpu_baseline': cpu,
+            'parity_rel_err': (cpu or {}).get('parity_rel_err'),
+            'timed_steps': timed_steps, 'timed_region_s': ms_max * 1e-3,
+            'scoring_ms': (scoring or {}).get('ms'),
+            'scoring_frac': ((scoring or {}).get('roofline') or {}).get('frac'),
+            'scoring_lists_identical': (scoring or {}).get('lists_identical'),
+            'scoring_small_ms': (scoring_small or {}).get('ms'),
+            'scoring_small_frac': ((scoring_small or {}).get('roofline') or {}).get('frac'),
+            'scoring_small_lists_identical': (scoring_small or {}).get('lists_identical'),
+            'loglinear_stress_ms': (loglinear_stress or {}).get('ms_per_step'),
             'loglinear': loglinear,
             'loglinear_stress': loglinear_stress,
             'scoring': scoring,
@@ -384,30 +412,39 @@ def run_ours(args, rank, world, local_rank):
         dist.destroy_process_group()
 
 
-def run_scoring(sc, label, rank, world, barrier, cpu):
-    """Scored entities/s for Q queries x E entities, top-k: rows sharded over the ranks (each rank builds only
-    its shard), ONE all-gather of the per-shard lists, merge on every rank."""
-    import torch
-    import torch.distributed as dist
-    from sert_b200.scoring import ShardedScorer, shard_bounds
+def scoring_shard(sc, world, rank):
+    """Rank `rank`'s rows of the synthetic entity matrix (unit-normalised N(0,1) rows)."""
+    from sert_b200.scoring import shard_bounds
     begin, end = shard_bounds(sc['E'], world, rank)
     rng = np.random.default_rng(20160816 + 3 + 7919 * rank)
     ent = rng.standard_normal((end - begin, sc['d']), dtype=np.float32)
     ent /= np.linalg.norm(ent, axis=1)[:, None]
+    return ent
+
+
+def run_scoring(sc, label, rank, world, barrier, cpu):
+    """Scored entities/s for Q queries x E entities, top-k: rows sharded over the ranks (each rank builds only
+    its shard), local sweep + ONE ncclAllGather of the per-shard lists + merge, all inside libsert_b200."""
+    import torch
+    import torch.distributed as dist
+    from sert_b200.scoring import EntityScorer, ShardedScorer
+    ent = scoring_shard(sc, world, rank)
     qs = np.random.default_rng(20160816 + 4).standard_normal((sc['Q'], sc['d']), dtype=np.float32)
     qs /= np.linalg.norm(qs, axis=1)[:, None]
     scorer = ShardedScorer(ent, sc['E'], is_shard=True, max_queries=sc['Q'], max_k=128)
     q_dev = torch.from_numpy(qs).cuda()
-    for _ in range(2):
-        scorer.topk_dev(q_dev, sc['k'])
+    for _ in range(3):
+        idx_dev, score_dev = scorer.topk_dev(q_dev, sc['k'])
     barrier()
     s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    reps = 3
+    reps = 10
+    launches0 = N_launches()
     s0.record()
     for _ in range(reps):
         scorer.topk_dev(q_dev, sc['k'])
     s1.record()
     barrier()
+    launches = (N_launches() - launches0) / reps
     sms = torch.tensor([s0.elapsed_time(s1) / reps], dtype=torch.float64, device='cuda')
     if world > 1:
         dist.all_reduce(sms, op=dist.ReduceOp.MAX)
@@ -415,32 +452,73 @@ def run_scoring(sc, label, rank, world, barrier, cpu):
     # e2e: host queries in, host lists out (H2D of the queries, D2H of the lists inside the timed region)
     barrier()
     t0 = time.perf_counter()
-    scorer.topk(qs, sc['k'])
+    idx_host, score_host = scorer.topk(qs, sc['k'])
     e2e_s = time.perf_counter() - t0
+    te = torch.tensor([e2e_s], dtype=torch.float64, device='cuda')
+    if world > 1:
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+    e2e_s = float(te.item())
+    seeded, fell_back = scorer.local.stats()
     out = {'metric': 'scored entities/sec', 'value': sc['Q'] * sc['E'] / (ms * 1e-3), 'unit': 'entities/s',
-           'workload': '%s: Q=%d x E=%d d=%d top-%d, float32 vectors, rows sharded over %d GPU(s), one all-gather'
-                       % (label, sc['Q'], sc['E'], sc['d'], sc['k'], world),
-           'ms': ms, 'e2e_value': sc['Q'] * sc['E'] / e2e_s,
+           'workload': '%s: Q=%d x E=%d d=%d top-%d, float32 vectors, rows sharded over %d GPU(s), one ncclAllGather '
+                       'issued by the library' % (label, sc['Q'], sc['E'], sc['d'], sc['k'], world),
+           'ms': ms, 'e2e_value': sc['Q'] * sc['E'] / e2e_s, 'e2e_ms': e2e_s * 1e3,
+           'e2e_h2d_bytes': int(qs.nbytes), 'e2e_d2h_bytes': int(idx_host.nbytes + score_host.nbytes),
+           'launches_per_call': launches, 'seeded_sweeps': seeded, 'fallback_sweeps': fell_back,
            'algorithmic_tflops': 2.0 * sc['Q'] * sc['E'] * sc['d'] / (ms * 1e-3) / 1e12,
-           'arithmetic': 'coarse-then-exact: one bf16 tcgen05 GEMM (2*Q*E*d flops) with a rigorous rounding-error '
-                         'margin, fp32 re-scoring of the survivors; returned lists are the exact fp32 top-k'}
+           'arithmetic': 'coarse-then-exact: one bf16 tcgen05 GEMM launch (2*Q*E*d flops) behind thresholds seeded from '
+                         'a strided row sample, rigorous rounding-error margin, fp32 re-scoring of the survivors; '
+                         'returned lists are the exact fp32 top-k'}
     tpeak, tsrc = measured_tensor_peak()
-    out['roofline'] = {'bound': 'tensor', 'kernel': 'gemm_tc_kernel + top-k epilogue (csrc/gemm_tc.cu), whole sweep',
-                       'achieved': out['algorithmic_tflops'], 'peak': tpeak, 'unit': 'TFLOP/s',
-                       'frac': out['algorithmic_tflops'] / tpeak, 'peak_source': tsrc, 'traffic': None}
+    # per-GPU fraction: the aggregate rate of the N shards against N times one GPU's measured peak
+    out['roofline'] = {'bound': 'tensor', 'kernel': 'gemm_tc_kernel + top-k epilogue (csrc/gemm_tc.cu), whole sweep '
+                                                    'incl. sample, finalize, all-gather and merge',
+                       'achieved': out['algorithmic_tflops'], 'peak': tpeak * world, 'unit': 'TFLOP/s',
+                       'frac': out['algorithmic_tflops'] / (tpeak * world), 'peak_source': tsrc + ' x %d GPUs' % world,
+                       'traffic': None}
+    # ---- verification at the benchmarked shape (outside the timed regions) ----
+    if world > 1:
+        out['comm'] = scorer.comm.info()
+    if rank == 0:
+        nv = min(512, sc['Q'])
+        got_idx, got_score = idx_host[:nv], score_host[:nv]
+        full = ent if world == 1 else np.concatenate([ent] + [scoring_shard(sc, world, r) for r in range(1, world)])
+        if world > 1:
+            single = EntityScorer(full, max_queries=nv, max_k=128)
+            ref_idx, ref_score = single.topk(qs[:nv], sc['k'])
+            single.close()
+            del single
+            out['lists_identical'] = bool((ref_idx == got_idx).all() and (ref_score == got_score).all())
+            out['lists_identical_what'] = ('merged (row id, score) lists of %d queries, bit for bit, against ONE single-GPU '
+                                           'scorer over all %d rows (rank 0)' % (nv, sc['E']))
+        ne = 16
+        exact = qs[:ne].astype(np.float64) @ full.astype(np.float64).T
+        order = np.argsort(-exact, axis=1, kind='stable')[:, :sc['k']]
+        ex_score = np.take_along_axis(exact, order, axis=1)
+        sep = np.abs(np.diff(ex_score, axis=1)).min(axis=1) > 1e-6
+        out['exact_check'] = {'queries': ne, 'max_abs_score_err': float(np.abs(got_score[:ne] - ex_score).max()),
+                              'lists_equal_float64_ranking': bool((got_idx[:ne][sep] == order[sep]).all()),
+                              'queries_with_separated_scores': int(sep.sum())}
+        del full
+    barrier()
     if cpu and world == 1:
         out['cpu_baseline'] = scoring_cpu_baseline(ent, qs, sc['k'])
-    scorer.local.close()
+    scorer.close()
     del scorer
     torch.cuda.empty_cache()
     return out
+
+
+def N_launches():
+    from sert_b200 import _native
+    return _native.launch_count()
 
 
 def scoring_cpu_baseline(ent, qs, k):
     """(i) the reference's literal path (bin/query.py:304-359): per-query kd-tree k-NN + per-candidate scoring,
     on a bounded sample of queries; (ii) a strong CPU baseline: batched sgemm + argpartition."""
     import sklearn.neighbors
-    n_lit = 8
+    n_lit = 100
     nn = sklearn.neighbors.NearestNeighbors(n_neighbors=k, algorithm='kd_tree', metric='euclidean')
     nn.fit(ent)                                    # index build is not timed (done once in the callback's __init__)
     t0 = time.perf_counter()
@@ -511,7 +589,7 @@ def run_loglinear_cfg5(rank, world, barrier, steps=4):
     rng = np.random.default_rng(20160816 + 5)                  # same seed on every rank: identical initial values
     train, val = synth.loglinear_corpus(20160821, V, E, W, B * nb, B)
     R, Wd, bd = synth.glorot(rng, (V, dw)), synth.glorot(rng, (dw, E)), np.zeros(E, np.float32)
-    exchange = sharding.DistExchange() if world > 1 else None
+    exchange = sharding.CommExchange() if world > 1 else None      # the five exchanges are NCCL calls of the library
     model = models.LanguageModel(batch_size=B, window_size=W, representations_init=R, output_layer_size=E,
                                  regularization_lambda=0.01, training_set=train, validation_set=val,
                                  dense_init=(Wd, bd), loss_slots=64, entity_shard=exchange)
@@ -538,24 +616,31 @@ def run_loglinear_cfg5(rank, world, barrier, steps=4):
                         'Adadelta + dense L2, exact per-word clipped path, E sharded over %d GPU(s)' % world,
             'value': B / (ms * 1e-3), 'unit': UNIT, 'ms_per_step': ms, 'scaling': 'strong',
             'algorithmic_tflops': 6.0 * B * W * dw * E / (ms * 1e-3) / 1e12,
-            'exchanges_per_step': 0 if world == 1 else 5, 'arena_gb_per_gpu': arena_gb,
+            'exchanges_per_step': 0 if world == 1 else 5, 'exchange': 'ncclAllReduce / ncclAllGather issued by libsert_b200', 'arena_gb_per_gpu': arena_gb,
             'losses': [float(v) for v in losses[:3]]}
 
 
-def cpu_baseline_sample():
-    """Oracle port timed on the host cores (rank 0, N=1 semantics): a bounded sample of the same workload."""
+def cpu_baseline_sample(p, gpu_losses):
+    """Oracle port timed on the host cores (rank 0, N=1 semantics): a bounded sample of the same workload -- the
+    first 7 batches of the very problem the GPU trained on (same initial values, batch order and negatives), so the
+    oracle's losses double as the parity check of the benchmarked shape."""
     from oracle import sert_oracle as O
     cfg = CFG2
-    n = 6
-    p = make_problem(0, n + 1)
+    n = max(1, min(6, len(gpu_losses) - 1))
     orc = O.VectorSpaceOracle(cfg['B'], p['R'], p['Wp'], p['bp'], p['Eemb'], cfg['lam'], p['train'], p['val'])
-    orc.train_batch(0, p['neg'][0])
+    ref = [orc.train_batch(0, p['neg'][0])]
     t0 = time.perf_counter()
     for j in range(1, n + 1):
-        orc.train_batch(j, p['neg'][j])
+        ref.append(orc.train_batch(j, p['neg'][j]))
     dt = time.perf_counter() - t0
+    ref = np.asarray(ref, np.float64)
+    got = np.asarray(gpu_losses[:n + 1], np.float64)
+    rel = float(np.max(np.abs(got - ref) / np.abs(ref)))
     return {'value': n * cfg['B'] / dt, 'unit': UNIT, 'cores': len(os.sched_getaffinity(0)), 'kind': 'port',
-            'sample': '%d training batches of 4096 pairs, numpy f32 oracle (oracle/sert_oracle.py)' % n}
+            'sample': '%d training batches of 4096 pairs, numpy f32 oracle (oracle/sert_oracle.py)' % n,
+            'parity_rel_err': rel, 'parity_what': 'max relative difference of the first %d per-batch training losses, '
+            'CUDA path vs oracle, at the benchmarked shape (tolerance 1e-4)' % (n + 1),
+            'parity_ok': bool(rel <= 1e-4)}
 
 
 def main():

@@ -30,8 +30,12 @@ constexpr int COLS_PER_WARP = BN / (EPI_WARPS / 4);
 static_assert(EPI_WARPS % 4 == 0 && COLS_PER_WARP % 32 == 0, "epilogue warps split the columns in 32-column chunks");
 constexpr int NUM_THREADS = 64 + 32 * EPI_WARPS;
 constexpr uint32_t TMEM_COLS = 512;
-constexpr int STASH = 64 / EPI_WARPS;     // survivors a lane can park in shared memory per tile (top-k epilogue)
-constexpr uint32_t STASH_BYTES = 2 * EPI_WARPS * 32 * STASH * 8;   // two buffers: this tile's and the previous one's
+// top-k epilogue: survivors of one tile that a WARP parks in shared memory (keys compacted across its 32 rows with
+// ballots; 8-byte key + 2-byte (owner lane, ordinal within the owner's row)), two buffers: this tile's and the
+// previous one's, whose list slots are being reserved
+constexpr int WSTASH = 96;
+constexpr uint32_t STASH_KEYS_BYTES = 2 * EPI_WARPS * WSTASH * 8;
+constexpr uint32_t STASH_BYTES = STASH_KEYS_BYTES + 2 * EPI_WARPS * WSTASH * 2;
 constexpr size_t SMEM_BYTES = 1024 /*align slack*/ + (size_t)STAGES * STAGE_BYTES + 256 /*barriers*/ + STASH_BYTES;
 
 struct alignas(64) TcMap {
@@ -276,20 +280,35 @@ gemm_tc_kernel(const __grid_constant__ TcMap map_a, const __grid_constant__ TcMa
     uint32_t acc_phase = 0;
     const TcEpilogue &ep = args.epi;
     // top-k epilogue: the keys parked by the PREVIOUS tile wait for their list slots (pend_pos is the result of an
-    // atomicAdd issued one tile ago: its ~1 us round trip runs under this tile's accumulator read)
-    int pend_total = 0, pend_pos = 0, pend_gm = 0, stash_buf = 0;
+    // atomicAdd issued one tile ago: its ~1 us round trip runs under this tile's accumulator read).  The warp's
+    // keys sit compacted in shared memory; entry i belongs to row (pend_m0 + quarter*32 + owner) and goes to slot
+    // pend_pos[owner] + ordinal of that row's list, so the copy-out is one coalesced loop over the entries.
+    int pend_wtotal = 0, pend_pos = 0, pend_m0 = 0, stash_buf = 0;
+    const uint32_t lane_lt = (1u << lane) - 1u;
+    auto stash_keys = [&](int buf) { return stash_base + (uint32_t)((buf * EPI_WARPS + (warp - 2)) * WSTASH) * 8u; };
+    auto stash_meta = [&](int buf) {
+      return stash_base + STASH_KEYS_BYTES + (uint32_t)((buf * EPI_WARPS + (warp - 2)) * WSTASH) * 2u;
+    };
     auto flush_pending = [&]() {
-      if (pend_total > 0) {
-        if (pend_pos + pend_total > ep.cap) *ep.overflow = 1;
-        unsigned long long *list = ep.cand + (size_t)pend_gm * ep.cap;
-        const uint32_t src = stash_base + (uint32_t)((((stash_buf ^ 1) * EPI_WARPS + (warp - 2)) * 32 + lane) * STASH) * 8u;
-        for (int i = 0; i < pend_total; ++i) {
-          unsigned long long key;
-          asm volatile("ld.shared.b64 %0, [%1];" : "=l"(key) : "r"(src + (uint32_t)i * 8u) : "memory");
-          if (pend_pos + i < ep.cap) list[pend_pos + i] = key;
+      if (pend_wtotal > 0) {                              // warp-uniform
+        const uint32_t keys = stash_keys(stash_buf ^ 1), meta = stash_meta(stash_buf ^ 1);
+        for (int i0 = 0; i0 < pend_wtotal; i0 += 32) {
+          const int i = i0 + lane;
+          unsigned long long key = 0ull;
+          uint32_t mt16 = 0u;
+          if (i < pend_wtotal) {
+            asm volatile("ld.shared.b64 %0, [%1];" : "=l"(key) : "r"(keys + (uint32_t)i * 8u) : "memory");
+            asm volatile("ld.shared.u16 %0, [%1];" : "=r"(mt16) : "r"(meta + (uint32_t)i * 2u) : "memory");
+          }
+          const int owner = (int)(mt16 >> 11), ord = (int)(mt16 & 0x7ffu);
+          const int pos = __shfl_sync(0xffffffffu, pend_pos, owner) + ord;
+          if (i < pend_wtotal) {
+            if (pos < ep.cap) ep.cand[(size_t)(pend_m0 + quarter * 32 + owner) * ep.cap + pos] = key;
+            else *ep.overflow = 1;
+          }
         }
       }
-      pend_total = 0;
+      pend_wtotal = 0;
     };
     int mt, nt, seq;
     for (int it = 0; cta_tile<BSTAT>(it, num_m_tiles, num_n_tiles, mt, nt, seq); ++it) {
@@ -364,56 +383,92 @@ gemm_tc_kernel(const __grid_constant__ TcMap map_a, const __grid_constant__ TcMa
         }
         if (ep.group != 8 && row_ok) ep.gmax[(size_t)gm * ep.gmax_ld + (size_t)nt * (BN / COLS_PER_WARP) + col_lo / COLS_PER_WARP] = mx;
       } else {
-        // ---- running top-k filter.  The chunk loops stay rolled: the epilogue's code must stay resident in
-        // the instruction caches (a fully unrolled two-pass version measured 6x slower: the warps sat in
-        // "no instruction" stalls).  Pass 1 counts this row's survivors, one compare per score, and parks the
-        // first STASH of them as keys in shared memory: reading the accumulator once is all the TMEM bandwidth
-        // a K = 256 tile leaves (a tile's 128 KB at 64 B/cycle = its 2048 cycles of MMA).
-        int total = 0;
+        // ---- running top-k filter.  The chunk loop stays rolled: the epilogue's code must stay resident in the
+        // instruction caches (a fully unrolled two-pass version measured 6x slower: the warps sat in "no
+        // instruction" stalls).  One read of the accumulator; per 32-column chunk a max tree (31 FMNMX) decides
+        // whether ANY of the warp's 32 rows has a survivor (one ballot); only then the four 8-column quarters that
+        // hold one are scanned, column by column with a ballot each, and the survivors are compacted into the warp's
+        // shared-memory stash.  Cost follows the number of survivors: ~40 instructions for a chunk without one.
+        // (Round 1 parked keys per LANE, 4 slots each: a row with a fifth survivor in 64 columns sent the whole warp
+        // to the two-pass path -- a quarter of the tiles at 500 survivors per query and 50 k rows -- and every lane
+        // with a hit ran the full 32-column scan.)
+        int total = 0;                                                   // this lane's survivors in the tile
+        int wcount = 0;                                                  // the warp's (uniform)
         uint32_t chunk_any = 0;                                          // warp-uniform: chunks with a survivor
-        const uint32_t my_stash = stash_base + (uint32_t)(((stash_buf * EPI_WARPS + (warp - 2)) * 32 + lane) * STASH) * 8u;
+        const uint32_t my_keys = stash_keys(stash_buf), my_meta = stash_meta(stash_buf);
 #pragma unroll 1
         for (int ci = 0; ci < CHUNKS; ++ci) {
           uint32_t v[32];
           tc_ld_32x32(t_row + (uint32_t)(col_lo + ci * 32), v);
           tc_wait_ld();
           const long long left = args.n_end - (n0 + col_lo + ci * 32);          // valid columns in this chunk
-          const int nv = left >= 32 ? 32 : (left <= 0 ? 0 : (int)left);
-          // One max-reduction per chunk instead of 32 compares feeding a dependent count: the two epilogue warps of
-          // a scheduler issue ~150 instead of ~1400 instructions per tile (ncu: the epilogue was issue-bound on
-          // dependent integer adds, 7 k cycles per tile against 2 k cycles of MMA at K = 256).
-          float mx = -INFINITY;
-          if (nv == 32) {
-            float m16[16];
-#pragma unroll
-            for (int j = 0; j < 16; ++j) m16[j] = fmaxf(__uint_as_float(v[2 * j]), __uint_as_float(v[2 * j + 1]));
-#pragma unroll
-            for (int j = 0; j < 8; ++j) m16[j] = fmaxf(m16[2 * j], m16[2 * j + 1]);
-#pragma unroll
-            for (int j = 0; j < 4; ++j) m16[j] = fmaxf(m16[2 * j], m16[2 * j + 1]);
-            mx = fmaxf(fmaxf(m16[0], m16[1]), fmaxf(m16[2], m16[3]));
-          } else {
+          if (left < 32) {                                                      // warp-uniform: the shard's last tile
 #pragma unroll
             for (int j = 0; j < 32; ++j)
-              if (j < nv) mx = fmaxf(mx, __uint_as_float(v[j]));
+              if (j >= left) v[j] = 0xff800000u;                                // -inf
           }
-          const bool hit = mx > tau_score;
-          if (hit) {                                                     // rare once tau has warmed up
+          float m4[4];
 #pragma unroll
-            for (int j = 0; j < 32; ++j) {
-              if (j < nv && __uint_as_float(v[j]) > tau_score) {
-                if (total < STASH) {
-                  const unsigned long long key = make_key(
-                      __uint_as_float(v[j]), (unsigned int)(n0 + col_lo + ci * 32 + j + ep.row_offset));
-                  asm volatile("st.shared.b64 [%0], %1;" ::"r"(my_stash + (uint32_t)total * 8u), "l"(key) : "memory");
+          for (int qd = 0; qd < 4; ++qd) {
+            const float a = fmaxf(fmaxf(__uint_as_float(v[8 * qd]), __uint_as_float(v[8 * qd + 1])),
+                                  fmaxf(__uint_as_float(v[8 * qd + 2]), __uint_as_float(v[8 * qd + 3])));
+            const float b = fmaxf(fmaxf(__uint_as_float(v[8 * qd + 4]), __uint_as_float(v[8 * qd + 5])),
+                                  fmaxf(__uint_as_float(v[8 * qd + 6]), __uint_as_float(v[8 * qd + 7])));
+            m4[qd] = fmaxf(a, b);
+          }
+          const float mx = fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3]));
+          if (__ballot_sync(0xffffffffu, mx > tau_score) == 0u) continue;        // nothing in this chunk (common)
+          chunk_any |= 1u << ci;
+          const unsigned int col_base = (unsigned int)(n0 + col_lo + ci * 32 + ep.row_offset);
+#pragma unroll
+          for (int qd = 0; qd < 4; ++qd) {
+            if (__ballot_sync(0xffffffffu, m4[qd] > tau_score) == 0u) continue;
+            // survivors of this lane among the quarter's 8 columns, and the column of the last one
+            int cnt = 0, idx = 0;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const bool hit = __uint_as_float(v[8 * qd + j]) > tau_score;
+              cnt += hit ? 1 : 0;
+              idx = hit ? j : idx;
+            }
+            const uint32_t h1 = __ballot_sync(0xffffffffu, cnt >= 1);
+            if (__ballot_sync(0xffffffffu, cnt >= 2) == 0u) {
+              // common case: no row has two survivors in these 8 columns, so a row's survivor IS its quarter maximum
+              if (cnt != 0) {
+                const int slot = wcount + __popc(h1 & lane_lt);
+                if (slot < WSTASH) {
+                  const unsigned long long key = make_key(m4[qd], col_base + (unsigned int)(8 * qd + idx));
+                  asm volatile("st.shared.b64 [%0], %1;" ::"r"(my_keys + (uint32_t)slot * 8u), "l"(key) : "memory");
+                  asm volatile("st.shared.u16 [%0], %1;" ::"r"(my_meta + (uint32_t)slot * 2u),
+                               "h"((unsigned short)((lane << 11) | (total & 0x7ff)))
+                               : "memory");
                 }
                 ++total;
               }
+              wcount += __popc(h1);
+              continue;
+            }
+#pragma unroll
+            for (int j = 8 * qd; j < 8 * qd + 8; ++j) {
+              const bool hit = __uint_as_float(v[j]) > tau_score;
+              const uint32_t hm = __ballot_sync(0xffffffffu, hit);
+              if (hm == 0u) continue;
+              if (hit) {
+                const int slot = wcount + __popc(hm & lane_lt);
+                if (slot < WSTASH) {
+                  const unsigned long long key = make_key(__uint_as_float(v[j]), col_base + (unsigned int)j);
+                  asm volatile("st.shared.b64 [%0], %1;" ::"r"(my_keys + (uint32_t)slot * 8u), "l"(key) : "memory");
+                  asm volatile("st.shared.u16 [%0], %1;" ::"r"(my_meta + (uint32_t)slot * 2u),
+                               "h"((unsigned short)((lane << 11) | (total & 0x7ff)))
+                               : "memory");
+                }
+                ++total;
+              }
+              wcount += __popc(hm);
             }
           }
-          chunk_any |= (__any_sync(0xffffffffu, hit) ? 1u : 0u) << ci;
         }
-        if (!__any_sync(0xffffffffu, total > STASH)) {
+        if (wcount <= WSTASH) {
           // Everything this warp keeps sits in shared memory: hand the accumulator back to the MMA warp, copy out
           // the previous tile's keys (their slots were reserved a tile ago), reserve this tile's slots.
           tc_fence_before();
@@ -421,11 +476,9 @@ gemm_tc_kernel(const __grid_constant__ TcMap map_a, const __grid_constant__ TcMa
           if (lane == 0) mbar_arrive(tempty_bar(acc));
           if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
           flush_pending();                                // previous tile's keys: buffer stash_buf ^ 1
-          if (total > 0) {
-            pend_pos = atomicAdd(ep.count + gm, total);
-            pend_total = total;
-            pend_gm = gm;
-          }
+          if (total > 0) pend_pos = atomicAdd(ep.count + gm, total);
+          pend_wtotal = wcount;
+          pend_m0 = m0;
           stash_buf ^= 1;                                 // this tile's keys now sit in the "previous" buffer
           continue;
         }

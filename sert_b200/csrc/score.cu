@@ -298,7 +298,9 @@ struct FinalizeArgs {
   int per_warp_bytes;
 };
 
-__global__ void __launch_bounds__(256) finalize_kernel(const FinalizeArgs a) {
+constexpr int kFinRegs = 32;      // keys per lane held in registers: lists of up to 1024 keys are read from L2 once
+
+__global__ void __launch_bounds__(256, 3) finalize_kernel(const FinalizeArgs a) {
   extern __shared__ __align__(16) unsigned char fin_smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int q = blockIdx.x * (blockDim.x >> 5) + warp;
@@ -322,23 +324,33 @@ __global__ void __launch_bounds__(256) finalize_kernel(const FinalizeArgs a) {
     for (int i = lane; i < a.k; i += 32) { oi[i] = -1; os[i] = -INFINITY; }
     return;
   }
+  // the query vector, for step (3); issued first so that it travels with the list
+  for (int cc = lane; cc < a.d; cc += 32) qs[cc] = a.Qm[(size_t)q * a.d + cc];
+  // The list: in registers when it fits (one coalesced sweep, every load in flight at once), else re-read per pass.
+  const bool inreg = n <= 32 * kFinRegs;
+  unsigned long long kreg[kFinRegs];
+  if (inreg) {
+#pragma unroll
+    for (int i = 0; i < kFinRegs; ++i) kreg[i] = (i * 32 + lane < n) ? list[i * 32 + lane] : 0ull;
+  }
+#define SERT_FOR_EACH_KEY(BODY)                                                   \
+  if (inreg) {                                                                    \
+    _Pragma("unroll") for (int i_ = 0; i_ < kFinRegs; ++i_) {                     \
+      if (i_ * 32 < n && i_ * 32 + lane < n) { const unsigned long long key = kreg[i_]; BODY }   \
+    }                                                                             \
+  } else {                                                                        \
+    for (int i_ = lane; i_ < n; i_ += 32) { const unsigned long long key = list[i_]; BODY }      \
+  }
   // (1) score range of the list, histogram, bin of the need-th best
   float hi = -INFINITY, lo = INFINITY;
-  for (int i = lane; i < n; i += 32) {
-    const float s = key_score(list[i]);
-    hi = fmaxf(hi, s);
-    lo = fminf(lo, s);
-  }
+  SERT_FOR_EACH_KEY({ const float s = key_score(key); hi = fmaxf(hi, s); lo = fminf(lo, s); })
   hi = warp_max(hi);
   lo = -warp_max(-lo);
   const float scale = hi > lo ? 255.9f / (hi - lo) : 0.f;
 #pragma unroll
   for (int i = 0; i < 8; ++i) hist[lane * 8 + i] = 0;
   __syncwarp();
-  for (int i = lane; i < n; i += 32) {
-    const int b = min(255, (int)((key_score(list[i]) - lo) * scale));
-    atomicAdd(&hist[b], 1);
-  }
+  SERT_FOR_EACH_KEY({ atomicAdd(&hist[min(255, (int)((key_score(key) - lo) * scale))], 1); })
   __syncwarp();
   int local[8], lsum = 0;
 #pragma unroll
@@ -362,10 +374,10 @@ __global__ void __launch_bounds__(256) finalize_kernel(const FinalizeArgs a) {
   bstar = __reduce_max_sync(0xffffffffu, bstar);
   // (2) Lf = smallest score at or above that bin; survivors = everything within the margin below it
   float lf = INFINITY;
-  for (int i = lane; i < n; i += 32) {
-    const float s = key_score(list[i]);
+  SERT_FOR_EACH_KEY({
+    const float s = key_score(key);
     if (min(255, (int)((s - lo) * scale)) >= bstar) lf = fminf(lf, s);
-  }
+  })
   lf = -warp_max(-lf);
   const float thr = lf - a.margin[q];
   if (tk != 0ull && !(thr > tau_s)) {
@@ -373,63 +385,112 @@ __global__ void __launch_bounds__(256) finalize_kernel(const FinalizeArgs a) {
     return;
   }
   int c = 0;
-  for (int i0 = 0; i0 < n; i0 += 32) {
-    const int i = i0 + lane;
-    unsigned long long key = 0ull;
-    bool keep = false;
-    if (i < n) {
-      key = list[i];
-      keep = key_score(key) >= thr;
+  if (inreg) {
+#pragma unroll
+    for (int i = 0; i < kFinRegs; ++i) {
+      if (i * 32 < n) {                                      // warp-uniform
+        const bool keep = (i * 32 + lane < n) && key_score(kreg[i]) >= thr;
+        const unsigned int m = __ballot_sync(0xffffffffu, keep);
+        const int pos = c + __popc(m & ((1u << lane) - 1u));
+        if (keep && pos < a.cmax) keys[pos] = kreg[i];
+        c += __popc(m);
+      }
     }
-    const unsigned int m = __ballot_sync(0xffffffffu, keep);
-    const int pos = c + __popc(m & ((1u << lane) - 1u));
-    if (keep && pos < a.cmax) keys[pos] = key;
-    c += __popc(m);
+  } else {
+    for (int i0 = 0; i0 < n; i0 += 32) {
+      const int i = i0 + lane;
+      unsigned long long key = 0ull;
+      bool keep = false;
+      if (i < n) {
+        key = list[i];
+        keep = key_score(key) >= thr;
+      }
+      const unsigned int m = __ballot_sync(0xffffffffu, keep);
+      const int pos = c + __popc(m & ((1u << lane) - 1u));
+      if (keep && pos < a.cmax) keys[pos] = key;
+      c += __popc(m);
+    }
   }
+#undef SERT_FOR_EACH_KEY
   if (c > a.cmax) {
     if (lane == 0) *a.flag = 1;
     return;
   }
-  // (3) exact fp32 scores of the survivors
-  for (int cc = lane; cc < a.d; cc += 32) qs[cc] = a.Qm[(size_t)q * a.d + cc];
   __syncwarp();
-  for (int j0 = 0; j0 < c; j0 += 4) {
-    unsigned int r[4];
-    float sc[4];
+  // (3) exact fp32 scores of the survivors, eight rows in flight per warp (a row is one or two 16-byte requests per
+  // lane: latency-bound on its own)
+  constexpr int RF = 8;
+  for (int j0 = 0; j0 < c; j0 += RF) {
+    unsigned int r[RF];
+    float sc[RF];
 #pragma unroll
-    for (int i = 0; i < 4; ++i) r[i] = key_row(keys[min(j0 + i, c - 1)]);
+    for (int i = 0; i < RF; ++i) r[i] = key_row(keys[min(j0 + i, c - 1)]);
     if ((a.d & 3) == 0) {
-      // four rows in flight: the loads of a row are one or two 16-byte requests per lane, latency-bound on their own
       const float4 *q4 = reinterpret_cast<const float4 *>(qs);
-      const float4 *e4[4];
+      const float4 *e4[RF];
 #pragma unroll
-      for (int i = 0; i < 4; ++i)
+      for (int i = 0; i < RF; ++i)
         e4[i] = reinterpret_cast<const float4 *>(a.En + (size_t)((long long)r[i] - a.row_begin) * a.d);
 #pragma unroll
-      for (int i = 0; i < 4; ++i) sc[i] = 0.f;
+      for (int i = 0; i < RF; ++i) sc[i] = 0.f;
       for (int cc = lane; cc < (a.d >> 2); cc += 32) {
         const float4 qv = q4[cc];
-        float4 ev[4];
+        float4 ev[RF];
 #pragma unroll
-        for (int i = 0; i < 4; ++i) ev[i] = __ldg(e4[i] + cc);
+        for (int i = 0; i < RF; ++i) ev[i] = __ldg(e4[i] + cc);
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
+        for (int i = 0; i < RF; ++i) {
           sc[i] = fmaf(ev[i].x, qv.x, sc[i]); sc[i] = fmaf(ev[i].y, qv.y, sc[i]);
           sc[i] = fmaf(ev[i].z, qv.z, sc[i]); sc[i] = fmaf(ev[i].w, qv.w, sc[i]);
         }
       }
-#pragma unroll
-      for (int i = 0; i < 4; ++i) sc[i] = warp_sum(sc[i]);
     } else {
 #pragma unroll
-      for (int i = 0; i < 4; ++i)
-        sc[i] = warp_dot(qs, a.En + (size_t)((long long)r[i] - a.row_begin) * a.d, a.d, lane);
+      for (int i = 0; i < RF; ++i) {
+        const float *e = a.En + (size_t)((long long)r[i] - a.row_begin) * a.d;
+        float s = 0.f;
+        for (int c0 = lane * 4; c0 < a.d; c0 += 128) {
+#pragma unroll
+          for (int j = 0; j < 4; ++j)
+            if (c0 + j < a.d) s = fmaf(__ldg(e + c0 + j), qs[c0 + j], s);
+        }
+        sc[i] = s;
+      }
     }
-    __syncwarp();
-    if (lane < 4 && j0 + lane < c) {
-      const float mine_s = lane == 0 ? sc[0] : (lane == 1 ? sc[1] : (lane == 2 ? sc[2] : sc[3]));
-      const unsigned int mine_r = lane == 0 ? r[0] : (lane == 1 ? r[1] : (lane == 2 ? r[2] : r[3]));
-      keys[j0 + lane] = make_key(mine_s, mine_r);
+    // Eight butterfly reductions at once, transposed: at the xor-16 / 8 / 4 steps a lane hands over the partial sums
+    // of the rows its partner keeps (4, 2, 1 exchanges instead of 8 each), the last two steps are plain.  Every row's
+    // sum is built by the SAME tree as warp_sum (pairs 16 apart, then 8, 4, 2, 1; fp addition commutes), so the
+    // result is bit-identical to warp_dot's.  Row i ends up in the lanes with (lane >> 2) & 7 == bitrev3(i).
+    {
+      const bool up16 = lane & 16, up8 = lane & 8, up4 = lane & 4;
+      float t4[4], t2[2], t1;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {          // keep rows i (lower half) or i + 4 (upper half)
+        const float give = up16 ? sc[i] : sc[i + 4];
+        const float keep = up16 ? sc[i + 4] : sc[i];
+        t4[i] = keep + __shfl_xor_sync(0xffffffffu, give, 16);
+      }
+#pragma unroll
+      for (int i = 0; i < 2; ++i) {
+        const float give = up8 ? t4[i] : t4[i + 2];
+        const float keep = up8 ? t4[i + 2] : t4[i];
+        t2[i] = keep + __shfl_xor_sync(0xffffffffu, give, 8);
+      }
+      {
+        const float give = up4 ? t2[0] : t2[1];
+        const float keep = up4 ? t2[1] : t2[0];
+        t1 = keep + __shfl_xor_sync(0xffffffffu, give, 4);
+      }
+      t1 += __shfl_xor_sync(0xffffffffu, t1, 2);
+      t1 += __shfl_xor_sync(0xffffffffu, t1, 1);
+      // this lane's row: bit 2 of i from lane bit 4, bit 1 from lane bit 3, bit 0 from lane bit 2
+      const int mine_i = ((lane >> 4) & 1) * 4 + ((lane >> 3) & 1) * 2 + ((lane >> 2) & 1);
+      unsigned int mine_r = r[0];
+#pragma unroll
+      for (int i = 1; i < RF; ++i)
+        if (mine_i == i) mine_r = r[i];
+      __syncwarp();
+      if ((lane & 3) == 0 && j0 + mine_i < c) keys[j0 + mine_i] = make_key(t1, mine_r);
     }
   }
   // (4) order the survivors (bitonic, descending, in the warp's shared-memory slots) and write the best `need`

@@ -29,5 +29,6 @@ for _ in range(reps):
 e1.record()
 torch.cuda.synchronize()
 ms = e0.elapsed_time(e1) / reps
+print('stats (seeded, fallback):', sc.stats())
 print('mode=%s Q=%d E=%d d=%d k=%d: %.3f ms  %.3e entities/s  %.1f TFLOP/s (x1 flops)' %
       (mode, Q, E, d, k, ms, Q * E / ms * 1e3, 2.0 * Q * E * d / ms / 1e9))
