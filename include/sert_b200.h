@@ -232,6 +232,25 @@ SERT_API int sert_ll_forward_host(sert_model *m, int split, int64_t batch_index,
 /* log-linear predict_fn(batch, mask) -> (rows,W,E) per-word softmax (sert/models.py:880-890; the mask is
  * accepted and unused there).  rows <= B. Host in, host out. */
 SERT_API int sert_predict_loglinear(sert_model *m, const int32_t *batch_host, int32_t rows, float *out_host);
+/* LogLinearCallback.process on the device (bin/query.py:204-233; aggregate_distribution(mode='product'),
+ * sert/inference.py:170-183).  `batch_host` is the WordBatcher's (rows, W) index array; query j occupies rows from
+ * query_first_row[j] with its query_terms[j] tokens laid out row-major (sert/inference.py:99-111).  For every query:
+ * per-term softmax over all E entities, sum over its terms of log p (exact zeros skipped, as np.ma.log(p).filled(0)),
+ * exp, renormalise, and the full descending order.  Returns the first `top` (<= E; E = rank everything, as the
+ * reference does) entity ids and relevances per query, the normalised entropy of every term's distribution in query
+ * order (compute_normalised_entropy, bin/query.py:370-376; NULL to skip), the normalised entropy of each query's final
+ * distribution and its mass after renormalisation (the reference's isclose(sum, 1) check).  Ties order by lower
+ * entity id.  Host in / host out; nothing of size (rows, W, E) leaves the device. */
+SERT_API int sert_ll_rank_queries(sert_model *m, const int32_t *batch_host, int32_t rows,
+                                  const int32_t *query_first_row_host, const int32_t *query_terms_host,
+                                  int32_t num_queries, int32_t top, int32_t *out_idx_host, float *out_rel_host,
+                                  float *out_term_entropy_host, float *out_entropy_host, float *out_mass_host);
+/* The same ranking from given per-term distributions (num_terms, entities) -- the callback's own input contract
+ * (bin/query.py:204: `distribution`): query j owns rows query_first_term[j] .. +query_terms[j].  No model needed. */
+SERT_API int sert_ll_rank_distributions(const float *dist_host, int32_t num_terms, int32_t entities,
+                                        const int32_t *query_first_term_host, const int32_t *query_terms_host,
+                                        int32_t num_queries, int32_t top, int32_t *out_idx_host, float *out_rel_host,
+                                        float *out_term_entropy_host, float *out_entropy_host, float *out_mass_host);
 /* vector-space predict_fn(avg) -> tanh(avg.W+b), no clip (sert/models.py:1107-1118), batched over q rows. */
 SERT_API int sert_project_queries(sert_model *m, const float *avg_host, int32_t q, float *out_host);
 

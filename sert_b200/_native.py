@@ -79,6 +79,10 @@ SIGNATURES = {
     'sert_ll_forward_host': (c_int, [c_void_p, c_int, c_int64, c_void_p, c_void_p, c_void_p]),
     'sert_predict_loglinear': (c_int, [c_void_p, c_void_p, c_int32, c_void_p]),
     'sert_project_queries': (c_int, [c_void_p, c_void_p, c_int32, c_void_p]),
+    'sert_ll_rank_queries': (c_int, [c_void_p, c_void_p, c_int32, c_void_p, c_void_p, c_int32, c_int32, c_void_p,
+                                     c_void_p, c_void_p, c_void_p, c_void_p]),
+    'sert_ll_rank_distributions': (c_int, [c_void_p, c_int32, c_int32, c_void_p, c_void_p, c_int32, c_int32, c_void_p,
+                                           c_void_p, c_void_p, c_void_p, c_void_p]),
     'sert_scorer_arena_bytes': (c_int, [c_int64, c_int32, c_int32, c_int32, ctypes.POINTER(c_size_t)]),
     'sert_scorer_create': (c_int, [c_void_p, c_int64, c_int32, c_int64, c_int32, c_int32, c_int32, c_void_p,
                                    c_size_t, c_void_p, ctypes.POINTER(c_void_p)]),

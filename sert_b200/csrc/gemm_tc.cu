@@ -401,12 +401,11 @@ gemm_tc_kernel(const __grid_constant__ TcMap map_a, const __grid_constant__ TcMa
           uint32_t v[32];
           tc_ld_32x32(t_row + (uint32_t)(col_lo + ci * 32), v);
           tc_wait_ld();
-          const long long left = args.n_end - (n0 + col_lo + ci * 32);          // valid columns in this chunk
-          if (left < 32) {                                                      // warp-uniform: the shard's last tile
-#pragma unroll
-            for (int j = 0; j < 32; ++j)
-              if (j >= left) v[j] = 0xff800000u;                                // -inf
-          }
+          // valid columns in this chunk: fewer than 32 only in the shard's last tile.  Columns beyond hold zeros (TMA
+          // fills out-of-bounds rows); they are excluded where survivors are picked, not by rewriting v[] -- the
+          // compiler turns such a fix-up into 64 compare/select pairs on every chunk.
+          const long long left = args.n_end - (n0 + col_lo + ci * 32);
+          const bool partial = left < 32;                                       // warp-uniform
           float m4[4];
 #pragma unroll
           for (int qd = 0; qd < 4; ++qd) {
@@ -432,7 +431,7 @@ gemm_tc_kernel(const __grid_constant__ TcMap map_a, const __grid_constant__ TcMa
               idx = hit ? j : idx;
             }
             const uint32_t h1 = __ballot_sync(0xffffffffu, cnt >= 1);
-            if (__ballot_sync(0xffffffffu, cnt >= 2) == 0u) {
+            if (!partial && __ballot_sync(0xffffffffu, cnt >= 2) == 0u) {
               // common case: no row has two survivors in these 8 columns, so a row's survivor IS its quarter maximum
               if (cnt != 0) {
                 const int slot = wcount + __popc(h1 & lane_lt);
@@ -450,7 +449,7 @@ gemm_tc_kernel(const __grid_constant__ TcMap map_a, const __grid_constant__ TcMa
             }
 #pragma unroll
             for (int j = 8 * qd; j < 8 * qd + 8; ++j) {
-              const bool hit = __uint_as_float(v[j]) > tau_score;
+              const bool hit = __uint_as_float(v[j]) > tau_score && j < left;
               const uint32_t hm = __ballot_sync(0xffffffffu, hit);
               if (hm == 0u) continue;
               if (hit) {

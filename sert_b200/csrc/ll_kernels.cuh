@@ -47,4 +47,11 @@ int launch_ll_shard_labels(const LlInstanceArgs &a, const float *smax, const flo
 int launch_ll_shard_ds(const LlInstanceArgs &a, const float *smax, const float *ssum, int e_begin,
                        const float *adot_all, cudaStream_t st);
 
+// ---- entity ranking of queries (ll_rank.cu): product of the terms' distributions, renormalised, ranked over all E ----
+size_t ll_rank_scratch_bytes(int nq, int E, int n_terms);
+int ll_rank(const float *Z, const float *rmax, const float *rsum, bool probs, long long ldz, int E,
+            const int32_t *first_host, const int32_t *nterms_host, int nq, int top, float *rel_dev, void *scratch,
+            size_t scratch_bytes, int32_t *out_idx_host, float *out_rel_host, float *out_term_entropy_host,
+            float *out_entropy_host, float *out_mass_host, cudaStream_t st);
+
 }  // namespace sert

@@ -98,6 +98,8 @@ struct sert_model {
   sert_exchange_fn exchange = nullptr;
   void *exchange_ctx = nullptr;
   sert_comm *comm = nullptr;       // set: the exchanges are NCCL collectives issued by the library itself (comm.cu)
+  void *rank_scratch = nullptr;    // sert_ll_rank_queries: sort keys and per-query sums (library-owned, grown on demand)
+  size_t rank_scratch_bytes = 0;
   float *xstats = nullptr;         // [kMaxShards][2][B*W] gathered (row max, row sum)
   float *smax = nullptr, *ssum = nullptr, *adot = nullptr, *racc = nullptr;
   // host-batch staging
@@ -764,6 +766,7 @@ int sert_model_destroy(sert_model *m) {
     for (int q = 0; q < sert_model::kPipe; ++q)
       if (m->ev_loss[q]) cudaEventDestroy(m->ev_loss[q]);
     if (m->pin_loss) cudaFreeHost(m->pin_loss);
+    if (m->rank_scratch) cudaFree(m->rank_scratch);
     delete m;
   }
   return 0;
@@ -1190,6 +1193,74 @@ int sert_predict_loglinear(sert_model *m, const int32_t *batch_host, int32_t row
   SERT_CUDA(cudaMemcpyAsync(out_host, m->Z, BW * E * sizeof(float), cudaMemcpyDeviceToHost, m->st));
   SERT_CUDA(cudaStreamSynchronize(m->st));
   return 0;
+}
+
+// scratch of the ranking calls: grown on demand, owned by the library
+static int rank_scratch(void **buf, size_t *cap, size_t need) {
+  if (*cap >= need) return 0;
+  if (*buf) SERT_CUDA(cudaFree(*buf));
+  *buf = nullptr; *cap = 0;
+  SERT_CUDA(cudaMalloc(buf, need));
+  *cap = need;
+  return 0;
+}
+
+int sert_ll_rank_queries(sert_model *m, const int32_t *batch_host, int32_t rows, const int32_t *query_first_row_host,
+                         const int32_t *query_terms_host, int32_t num_queries, int32_t top, int32_t *out_idx_host,
+                         float *out_rel_host, float *out_term_entropy_host, float *out_entropy_host,
+                         float *out_mass_host) {
+  SERT_REQUIRE(m && batch_host && query_first_row_host && query_terms_host && out_idx_host && out_rel_host,
+               "null argument");
+  SERT_REQUIRE(!is_vs(m->cfg), "log-linear model required");
+  const sert_config &c = m->cfg;
+  SERT_REQUIRE(rows >= 0 && rows <= c.batch, "more rows than the model's batch size");
+  SERT_REQUIRE(m->exchange == nullptr, "ranking needs the full entity axis: gather the shards first");
+  SERT_REQUIRE(num_queries >= 0 && num_queries <= rows, "more queries than rows");
+  if (num_queries == 0) return 0;
+  const int W = c.window, E = (int)c.entities;
+  std::vector<int32_t> first((size_t)num_queries);
+  long long n_terms = 0;
+  for (int j = 0; j < num_queries; ++j) {
+    const long long r0 = query_first_row_host[j], T = query_terms_host[j];
+    SERT_REQUIRE(r0 >= 0 && T >= 1 && r0 * W + T <= (long long)rows * W, "query outside the batch");
+    first[j] = (int32_t)(r0 * W);          // term t of the query is row first + t of the (rows*W, E) per-term matrix
+    n_terms += T;
+  }
+  const size_t BW = (size_t)rows * W;
+  SERT_CUDA(cudaMemcpyAsync(m->stage_x, batch_host, BW * sizeof(int32_t), cudaMemcpyHostToDevice, m->st));
+  if (ll_forward(*m, m->stage_x, rows, m->st)) return -1;
+  const size_t need = ll_rank_scratch_bytes(num_queries, E, (int)n_terms);
+  if (rank_scratch(&m->rank_scratch, &m->rank_scratch_bytes, need)) return -1;
+  return ll_rank(m->Z, m->rmax, m->rsum, false, E, E, first.data(), query_terms_host, num_queries, top, m->S,
+                 m->rank_scratch, m->rank_scratch_bytes, out_idx_host, out_rel_host, out_term_entropy_host,
+                 out_entropy_host, out_mass_host, m->st);
+}
+
+int sert_ll_rank_distributions(const float *dist_host, int32_t num_terms, int32_t entities,
+                               const int32_t *query_first_term_host, const int32_t *query_terms_host,
+                               int32_t num_queries, int32_t top, int32_t *out_idx_host, float *out_rel_host,
+                               float *out_term_entropy_host, float *out_entropy_host, float *out_mass_host) {
+  SERT_REQUIRE(dist_host && query_first_term_host && query_terms_host && out_idx_host && out_rel_host, "null argument");
+  SERT_REQUIRE(num_terms >= 1 && entities >= 1 && num_queries >= 0, "bad shape");
+  int ndev = 0;
+  SERT_CUDA(cudaGetDeviceCount(&ndev));
+  SERT_REQUIRE(ndev > 0, "no CUDA device: libsert_b200 has no CPU fallback");
+  if (num_queries == 0) return 0;
+  for (int j = 0; j < num_queries; ++j)
+    SERT_REQUIRE(query_first_term_host[j] >= 0 && query_terms_host[j] >= 1 &&
+                 query_first_term_host[j] + query_terms_host[j] <= num_terms, "query outside the term matrix");
+  float *dist = nullptr, *rel = nullptr;
+  void *scratch = nullptr;
+  const size_t need = ll_rank_scratch_bytes(num_queries, entities, num_terms);
+  SERT_CUDA(cudaMalloc(&dist, (size_t)num_terms * entities * sizeof(float)));
+  SERT_CUDA(cudaMalloc(&rel, (size_t)num_queries * entities * sizeof(float)));
+  SERT_CUDA(cudaMalloc(&scratch, need));
+  SERT_CUDA(cudaMemcpy(dist, dist_host, (size_t)num_terms * entities * sizeof(float), cudaMemcpyHostToDevice));
+  const int rc = ll_rank(dist, nullptr, nullptr, true, entities, entities, query_first_term_host, query_terms_host,
+                         num_queries, top, rel, scratch, need, out_idx_host, out_rel_host, out_term_entropy_host,
+                         out_entropy_host, out_mass_host, nullptr);
+  cudaFree(dist); cudaFree(rel); cudaFree(scratch);
+  return rc;
 }
 
 int sert_project_queries(sert_model *m, const float *avg_host, int32_t q, float *out_host) {

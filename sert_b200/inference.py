@@ -94,6 +94,19 @@ class WordBatcher(object):
         logging.debug('Processing batch (batch size=%d, current batch=%d).',
                       self.batch_size, self.num_used_instances)
 
+        if hasattr(self.predict_fn, 'rank') and hasattr(self.callback, 'process_ranked'):
+            # device path: per-term softmax, product of experts, renormalisation and the full ranking stay on the
+            # device; the callback receives (entity ids, relevances) instead of a (T, E) distribution
+            spans, row = [], 0
+            for num_instances, payload, kwargs in self.requests:
+                spans.append((row, len(payload)))
+                row += num_instances
+            ranked = self.predict_fn.rank(self.batch[:self.num_used_instances], spans)
+            for (num_instances, payload, kwargs), result in zip(self.requests, ranked):
+                self.callback.process_ranked(payload, *result, **kwargs)
+            self._empty_batch()
+            return
+
         results = self.predict_fn(self.batch, self.mask)
         logging.debug('Retrieved batch results %s.', results.shape)
 

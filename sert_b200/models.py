@@ -482,6 +482,41 @@ class LogLinearPredictFn(object):
         return out
 
 
+    def rank(self, batch, requests, top=None):
+        """LogLinearCallback.process for every query of a WordBatcher batch, on the device (bin/query.py:204-233):
+        ``requests`` = [(first_row, num_tokens), ...] in ``batch`` (rows, W).  Returns per query
+        (entity ids (top,), relevances (top,), per-term normalised entropies (T,), normalised entropy of the final
+        distribution, its mass); top=None ranks all E entities like the reference.  Only (queries, top) ids and
+        relevances cross PCIe -- not the (rows, W, E) tensor ``__call__`` returns."""
+        nat = self._ensure()
+        batch = np.ascontiguousarray(batch, dtype=np.int32)
+        assert batch.ndim == 2 and batch.shape[1] == self.window_size
+        E = self.dense_w.shape[1]
+        top = E if top is None else min(int(top), E)
+        results = []
+        for lo in range(0, len(requests), self.batch_size):
+            chunk = requests[lo:lo + self.batch_size]
+            row_lo = chunk[0][0]
+            row_hi = max(first + -(-n // self.window_size) for first, n in chunk)
+            assert row_hi - row_lo <= self.batch_size
+            first = np.array([f - row_lo for f, _ in chunk], np.int32)
+            terms = np.array([n for _, n in chunk], np.int32)
+            nq = len(chunk)
+            idx = np.empty((nq, top), np.int32)
+            rel = np.empty((nq, top), np.float32)
+            term_entropy = np.empty(int(terms.sum()), np.float32)
+            entropy = np.empty(nq, np.float32)
+            mass = np.empty(nq, np.float32)
+            N.check(nat.lib.sert_ll_rank_queries(
+                nat.handle, N.host_ptr(batch[row_lo:row_hi]), row_hi - row_lo, N.host_ptr(first), N.host_ptr(terms), nq,
+                top, N.host_ptr(idx), N.host_ptr(rel), N.host_ptr(term_entropy), N.host_ptr(entropy), N.host_ptr(mass)))
+            ends = np.cumsum(terms)
+            for j in range(nq):
+                results.append((idx[j], rel[j], term_entropy[ends[j] - terms[j]:ends[j]], float(entropy[j]),
+                                float(mass[j])))
+        return results
+
+
 class VectorSpacePredictFn(object):
     """Picklable predict_fn of the vector-space model: avg word embedding (dw,) -> tanh(avg.W+b) (de,),
     no clip (sert/models.py:1107-1118).  ``project`` is the batched form used by the GPU ranker."""

@@ -1,7 +1,9 @@
 """Ranking callbacks: drop-in for the callbacks of the reference's ``bin/query.py:165-382``.
 
-``LogLinearCallback`` is host arithmetic over the per-term distributions that the device ``predict_fn``
-returns (product of experts, renormalise, rank ALL entities; bin/query.py:204-233).
+``LogLinearCallback.process`` is the reference's host arithmetic over per-term distributions (product of experts,
+renormalise, rank ALL entities; bin/query.py:204-233), kept for callers that hand it a (T, E) array;
+``process_ranked`` takes the same ranking computed on the device (``sert_ll_rank_queries``: nothing of size
+(rows, W, E) crosses PCIe), which is what ``WordBatcher`` uses when ``predict_fn`` offers ``rank``.
 
 ``VectorSpaceCallback`` keeps the reference's observable behaviour (bin/query.py:241-367) but replaces
 the sklearn k-NN / scipy cdist search by the device scorer (``sert_b200.scoring``): the device returns the
@@ -81,8 +83,45 @@ class LogLinearCallback(Callback):
 
         self.rank_callback(topic_id, top_ranked_indices, distribution[top_ranked_indices])
 
+    def process_ranked(self, payload, top_ranked_indices, top_ranked_values, term_entropies, entropy, mass,
+                       topic_id):
+        """The same observable behaviour as ``process`` from a device ranking (``LogLinearPredictFn.rank`` /
+        ``rank_distributions``): the (T, E) per-term distributions never reach the host."""
+        assert topic_id not in self.topic_projections
+        self.topic_projections[topic_id] = None           # the reference keeps the raw (T, E) result; nothing reads it
+        terms = [self.tokens[token_id] for token_id in payload]
+
+        if not np.isclose(mass, 1.0):
+            logging.error('Encountered non-normalized distribution for topic "%s" (mass=%.10f).', topic_id, mass)
+
+        self.f_debug_out.write('Topic {0} {1}: {2}\n'.format(
+            topic_id, entropy, zip(terms, [float(v) for v in term_entropies])))
+
+        self.rank_callback(topic_id, np.asarray(top_ranked_indices, dtype=np.int64), np.asarray(top_ranked_values))
+
     def should_average_input(self):
         return False
+
+
+def rank_distributions(distributions, top=None):
+    """Device ranking of queries given their per-term distributions [(T_j, E) float32, ...] -- the input contract
+    of ``LogLinearCallback.process`` (bin/query.py:204).  Returns what ``LogLinearPredictFn.rank`` returns."""
+    from sert_b200 import _native as N
+    E = distributions[0].shape[1]
+    top = E if top is None else min(int(top), E)
+    terms = np.array([d.shape[0] for d in distributions], np.int32)
+    first = (np.cumsum(terms) - terms).astype(np.int32)
+    stacked = np.ascontiguousarray(np.concatenate(distributions, axis=0), dtype=np.float32)
+    nq = len(distributions)
+    idx = np.empty((nq, top), np.int32)
+    rel = np.empty((nq, top), np.float32)
+    term_entropy = np.empty(int(terms.sum()), np.float32)
+    entropy, mass = np.empty(nq, np.float32), np.empty(nq, np.float32)
+    N.check(N.load().sert_ll_rank_distributions(
+        N.host_ptr(stacked), stacked.shape[0], E, N.host_ptr(first), N.host_ptr(terms), nq, top, N.host_ptr(idx),
+        N.host_ptr(rel), N.host_ptr(term_entropy), N.host_ptr(entropy), N.host_ptr(mass)))
+    return [(idx[j], rel[j], term_entropy[first[j]:first[j] + terms[j]], float(entropy[j]), float(mass[j]))
+            for j in range(nq)]
 
 
 class VectorSpaceCallback(Callback):
