@@ -359,6 +359,7 @@ def run_ours(args, rank, world, local_rank):
             traceback.print_exc(file=sys.stderr)
             return {'error': '%s: %s' % (type(exc).__name__, exc)}
 
+    bf16_mode = leg(run_bf16_state_mode, p, cfg, steps, warm, repeats, first_losses, losses, rank, world, barrier)
     scoring = leg(run_scoring, CFG4, 'BASELINE.json configs[3]', rank, world, barrier, cpu=False)
     scoring_small = leg(run_scoring, CFG3, 'BASELINE.json configs[2]', rank, world, barrier, cpu=(rank == 0))
 
@@ -402,6 +403,7 @@ def run_ours(args, rank, world, local_rank):
             'scoring_small_frac': ((scoring_small or {}).get('roofline') or {}).get('frac'),
             'scoring_small_lists_identical': (scoring_small or {}).get('lists_identical'),
             'loglinear_stress_ms': (loglinear_stress or {}).get('ms_per_step'),
+            'bf16_state_mode': bf16_mode,
             'loglinear': loglinear,
             'loglinear_stress': loglinear_stress,
             'scoring': scoring,
@@ -410,6 +412,71 @@ def run_ours(args, rank, world, local_rank):
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
+
+
+def run_bf16_state_mode(p, cfg, steps, warm, repeats, f32_first_losses, f32_last_losses, rank, world, barrier):
+    """BASELINE.json configs[1] says "bf16": the perf mode next to the float32 parity headline.  Same model, same
+    batches, same step sequence, with Adam's m / v stored as bfloat16 (stochastic rounding) -- sert_config.dtype_mode 1:
+    the dense update streams 16 instead of 24 bytes per parameter.  Parameters, gradients, forward and backward stay
+    float32.  Reports the throughput, the roofline of its dense update and the measured deviation from the float32
+    run over the identical step sequence."""
+    import torch
+    import torch.distributed as dist
+    from sert_b200 import _native as N, models
+    n_batches = steps + warm
+    model = models.VectorSpaceLanguageModel(
+        batch_size=cfg['B'], window_size=cfg['W'], num_negative_samples=cfg['k'],
+        representations_init=p['R'], entity_representations_init=p['Eemb'], regularization_lambda=cfg['lam'],
+        training_set=p['train'], validation_set=p['val'], dense_init=(p['Wp'], p['bp']),
+        loss_slots=max(1024, n_batches), optimizer_state_dtype='bfloat16')
+    nat, lib = model._native, model._native.lib
+    neg_dev = torch.from_numpy(p['neg']).cuda()
+    order = np.arange(n_batches, dtype=np.int64)
+
+    def train(lo, hi):
+        N.check(lib.sert_train_batches(nat.handle, N.host_ptr(order[lo:hi]), hi - lo,
+                                       N.c_void_p(neg_dev.data_ptr() + lo * cfg['B'] * cfg['k'] * 4), lo))
+
+    train(0, n_batches)
+    first = np.empty(n_batches, np.float32)
+    N.check(lib.sert_losses_fetch(nat.handle, 0, n_batches, N.host_ptr(first)))
+    barrier()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    for _ in range(repeats):
+        train(warm, n_batches)
+    ev1.record()
+    barrier()
+    t = torch.tensor([ev0.elapsed_time(ev1)], dtype=torch.float64, device='cuda')
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item()) / (repeats * steps)
+    last = np.empty(n_batches, np.float32)
+    N.check(lib.sert_losses_fetch(nat.handle, 0, n_batches, N.host_ptr(last)))
+    N.check(lib.sert_model_profile(nat.handle, 1))
+    prof_steps = min(steps, 50)
+    N.check(lib.sert_train_batches(nat.handle, N.host_ptr(order[:prof_steps]), prof_steps,
+                                   N.c_void_p(neg_dev.data_ptr()), 0))
+    tot, cnt, bpl = N.ctypes.c_double(0), N.c_int64(0), N.ctypes.c_double(0)
+    N.check(lib.sert_model_profile_read(nat.handle, N.ctypes.byref(tot), N.ctypes.byref(cnt), N.ctypes.byref(bpl)))
+    upd_ms = tot.value / max(cnt.value, 1)
+    peak, peak_src = measured_peaks()
+    achieved = bpl.value / (upd_ms * 1e-3) / 1e9
+    arena_mb = nat.arena.numel() / 1e6
+    nat.close()
+    del model
+    torch.cuda.empty_cache()
+    rel = lambda a, b: float(np.max(np.abs(np.asarray(a, np.float64) - b) / np.abs(b)))
+    return {'workload': WORKLOAD.replace('float32', 'float32 parameters and gradients, bfloat16 Adam state (dtype_mode 1)'),
+            'value': world * cfg['B'] / (ms * 1e-3), 'unit': UNIT, 'ms_per_step': ms, 'dtype': 'f32 + bf16 optimiser state',
+            'roofline': {'bound': 'hbm', 'kernel': 'dense_update_kernel<Adam, tables, bf16 state>', 'achieved': achieved,
+                         'peak': peak, 'unit': 'GB/s', 'frac': achieved / peak, 'peak_source': peak_src,
+                         'algorithmic_bytes_per_launch': bpl.value, 'kernel_ms': upd_ms, 'traffic': None},
+            'deviation_rel': rel(first, f32_first_losses),
+            'deviation_rel_after_%d_steps' % (n_batches + repeats * steps): rel(last[warm:], f32_last_losses[warm:]),
+            'deviation_what': 'max relative difference of the per-batch training losses against the float32 run of '
+                              'the identical step sequence (first pass / last timed pass)',
+            'arena_mb': arena_mb}
 
 
 def scoring_shard(sc, world, rank):

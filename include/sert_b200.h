@@ -75,7 +75,11 @@ typedef struct sert_config {
   int32_t loss_slots;      /* capacity of the device-side per-batch loss buffer */
   uint64_t seed;           /* negative-sampler seed (reference: unseeded RandomStreams, sert/models.py:958-959) */
   int32_t inference_only;  /* 1: parameters + forward workspaces only (predict_fn models); training calls are refused */
-  int32_t reserved0;       /* must be 0 */
+  int32_t dtype_mode;      /* 0: float32 throughout -- the reference's arithmetic and the parity mode (float64 anywhere is
+                              a hard error there, sert/models.py:624-628).  1: perf mode of BASELINE.json configs[1] ("bf16"):
+                              the two optimiser-state arrays of every parameter (Adam m, v / Adadelta accu, delta_accu;
+                              sert/models.py:820,922) are stored as bfloat16 with stochastic rounding, parameters and
+                              gradients stay float32: the dense update streams 16 instead of 24 bytes per parameter */
   int64_t reserved1;       /* must be 0 */
 } sert_config;
 
@@ -119,6 +123,12 @@ SERT_API int sert_model_get_tensor(sert_model *m, int which, int slot, float *ho
 /* Adam's shared step counter t (lasagne.updates.adam t_prev; sert/models.py:922). */
 SERT_API int sert_model_set_step(sert_model *m, int64_t t);
 SERT_API int sert_model_get_step(sert_model *m, int64_t *t);
+
+/* State of the device-side negative sampler (sert/models.py:947-979 draws from an unseeded RandomStreams): the
+ * Philox seed and the number of draws made so far.  A checkpoint that carries both resumes with the negatives an
+ * uninterrupted run would have drawn. */
+SERT_API int sert_model_get_sampler(sert_model *m, uint64_t *seed, uint64_t *draws);
+SERT_API int sert_model_set_sampler(sert_model *m, uint64_t seed, uint64_t draws);
 
 /* Measurement hook (no reference counterpart): when enabled, every training step brackets its dense
  * optimiser kernel with CUDA events on the model's stream -- in the two-stream vector-space step that is the

@@ -28,7 +28,7 @@ class SertConfig(ctypes.Structure):
         ('word_dim', c_int32), ('entity_dim', c_int32),
         ('lambda_', c_float), ('loss_slots', c_int32),
         ('seed', ctypes.c_uint64),
-        ('inference_only', c_int32), ('reserved0', c_int32), ('reserved1', c_int64),
+        ('inference_only', c_int32), ('dtype_mode', c_int32), ('reserved1', c_int64),
     ]
 
 
@@ -48,6 +48,8 @@ SIGNATURES = {
     'sert_model_get_tensor': (c_int, [c_void_p, c_int, c_int, c_void_p, c_size_t]),
     'sert_model_set_step': (c_int, [c_void_p, c_int64]),
     'sert_model_get_step': (c_int, [c_void_p, ctypes.POINTER(c_int64)]),
+    'sert_model_get_sampler': (c_int, [c_void_p, ctypes.POINTER(ctypes.c_uint64), ctypes.POINTER(ctypes.c_uint64)]),
+    'sert_model_set_sampler': (c_int, [c_void_p, ctypes.c_uint64, ctypes.c_uint64]),
     'sert_model_set_entity_shard': (c_int, [c_void_p, c_int32, c_int32, c_int64, c_int64, c_void_p, c_void_p]),
     'sert_comm_unique_id': (c_int, [c_void_p, c_size_t]),
     'sert_comm_init': (c_int, [c_int32, c_int32, c_void_p, ctypes.POINTER(c_void_p)]),

@@ -130,6 +130,9 @@ struct OptimArgs {
   // phase 4, optional: segment `transposed_segment` ((rows, row_len) row-major) is also written transposed here
   float *transposed = nullptr;
   int transposed_segment = 0, transposed_rows = 0;
+  // 1: s1 / s2 are arrays of bfloat16 (sert_config.dtype_mode 1), written with stochastic rounding -- 16 instead of
+  // 24 bytes per parameter and step.  Element offsets are the same as for theta.
+  int state_bf16 = 0;
 };
 
 // Adam + L2 of the hot word rows (gradient = sum of the private copies), see opt_kernels.cu
@@ -143,6 +146,8 @@ struct HotUpdateArgs {
   float l2_scale, c0, c1, c2, c3;
   double *acc;                     // sum(theta^2) goes to acc[1 + slot]
   int counted;                     // 1: this rank reports the table's norm in the loss
+  int state_bf16 = 0;              // as OptimArgs::state_bf16
+  uint32_t stamp = 0;              // seeds the stochastic rounding
 };
 int launch_hot_update(const HotUpdateArgs &h, cudaStream_t st);
 // flags[hot_ids[s]] = value  (kHotRowMark to hand the rows to launch_hot_update, 0 to hand them back)

@@ -44,6 +44,48 @@ __device__ __forceinline__ void update_element(float &p, float &s1, float &s2, f
   }
 }
 
+// ---- optimiser state as bfloat16 (sert_config.dtype_mode 1; BASELINE.json configs[1] "bf16") ----------------------
+// Four consecutive state values = one 8-byte access.  Stores round stochastically: Adam's second moment moves by
+// 0.1 % per step (beta2 = 0.999), less than half a bf16 ulp (0.2-0.4 %), so round-to-nearest would freeze it; adding
+// 16 uniform random bits below the kept mantissa before truncating makes the stored value unbiased.  The bits come
+// from a hash of (element index, step): no state, reproducible.
+template <bool S16>
+__device__ __forceinline__ void load_state4(const float *base, long long i4, float (&v)[4]) {
+  if (S16) {
+    const uint2 u = reinterpret_cast<const uint2 *>(base)[i4];
+    v[0] = __uint_as_float(u.x << 16); v[1] = __uint_as_float(u.x & 0xffff0000u);
+    v[2] = __uint_as_float(u.y << 16); v[3] = __uint_as_float(u.y & 0xffff0000u);
+  } else {
+    const float4 x = reinterpret_cast<const float4 *>(base)[i4];
+    v[0] = x.x; v[1] = x.y; v[2] = x.z; v[3] = x.w;
+  }
+}
+__device__ __forceinline__ uint32_t sr_hash(uint32_t element, uint32_t step) {
+  uint32_t h = element * 0x9E3779B1u ^ step * 0x85EBCA77u;
+  h ^= h >> 15; h *= 0x2C1B3C6Du; h ^= h >> 12; h *= 0x297A2D39u; h ^= h >> 15;
+  return h;
+}
+// top 16 bits of (bits + 16 random bits): a value is rounded away from zero with probability = its discarded fraction
+__device__ __forceinline__ uint32_t bf16_sr(float x, uint32_t r16) { return (__float_as_uint(x) + r16) >> 16; }
+template <bool S16>
+__device__ __forceinline__ void store_state4(float *base, long long i4, const float (&v)[4], uint32_t element,
+                                             uint32_t step, uint32_t salt) {
+  if (S16) {
+    uint32_t r[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const uint32_t h = sr_hash(element + j, step);
+      r[j] = salt ? (h >> 16) : (h & 0xffffu);
+    }
+    uint2 u;
+    u.x = bf16_sr(v[0], r[0]) | (bf16_sr(v[1], r[1]) << 16);
+    u.y = bf16_sr(v[2], r[2]) | (bf16_sr(v[3], r[3]) << 16);
+    reinterpret_cast<uint2 *>(base)[i4] = u;
+  } else {
+    reinterpret_cast<float4 *>(base)[i4] = make_float4(v[0], v[1], v[2], v[3]);
+  }
+}
+
 // One 16-byte chunk of each stream per thread, one-shot grid (no grid-stride loop): measured on B200
 // (tools/bw_probe.cu) the in-place 3-stream read-modify-write reaches 6.50 TB/s this way vs 5.3-6.2 TB/s
 // for persistent grid-stride variants -- the block scheduler interleaves the load and store phases of
@@ -51,12 +93,10 @@ __device__ __forceinline__ void update_element(float &p, float &s1, float &s2, f
 // PHASE 0: everything.  PHASE 3: only the row-stamped tables (word / entity representations).  PHASE 4: only the
 // dense tensors (projection matrix, bias), whose gradients are produced by two small kernels that the caller
 // overlaps with phase 3 on a second stream.
-template <bool ADAM, int PHASE>
+template <bool ADAM, int PHASE, bool S16>
 __global__ void __launch_bounds__(256) dense_update_kernel(OptimArgs a) {
   const long long total4 = a.total >> 2;
   float4 *__restrict__ th4 = reinterpret_cast<float4 *>(a.theta);
-  float4 *__restrict__ s14 = reinterpret_cast<float4 *>(a.s1);
-  float4 *__restrict__ s24 = reinterpret_cast<float4 *>(a.s2);
   float4 *__restrict__ g4 = reinterpret_cast<float4 *>(a.grad);
   float sumsq = 0.f;
 
@@ -78,15 +118,14 @@ __global__ void __launch_bounds__(256) dense_update_kernel(OptimArgs a) {
     const bool mine = PHASE == 0 ? true : PHASE == 3 ? (sg.flags != nullptr) : (sg.flags == nullptr);
     if (live && mine && !skip) {
       const float4 p = th4[i4];
-      const float4 x1 = s14[i4];
-      const float4 x2 = s24[i4];
+      float v1[4], v2[4];
+      load_state4<S16>(a.s1, i4, v1);
+      load_state4<S16>(a.s2, i4, v2);
       float4 g = make_float4(0.f, 0.f, 0.f, 0.f);
       if (touched) g = __ldcg(g4 + i4);
       const float l2 = sg.regularised ? a.l2_scale : 0.0f;
       if (sg.regularised == 1) sumsq = p.x * p.x + p.y * p.y + p.z * p.z + p.w * p.w;
       float pv[4] = {p.x, p.y, p.z, p.w};
-      float v1[4] = {x1.x, x1.y, x1.z, x1.w};
-      float v2[4] = {x2.x, x2.y, x2.z, x2.w};
       const float gv[4] = {g.x, g.y, g.z, g.w};
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
@@ -100,8 +139,8 @@ __global__ void __launch_bounds__(256) dense_update_kernel(OptimArgs a) {
 #pragma unroll
         for (int j = 0; j < 4; ++j) a.transposed[(size_t)(c + j) * a.transposed_rows + r] = pv[j];
       }
-      s14[i4] = make_float4(v1[0], v1[1], v1[2], v1[3]);
-      s24[i4] = make_float4(v2[0], v2[1], v2[2], v2[3]);
+      store_state4<S16>(a.s1, i4, v1, (uint32_t)e, a.stamp, 0u);
+      store_state4<S16>(a.s2, i4, v2, (uint32_t)e, a.stamp, 1u);
       // The gradient row is zeroed only now, behind the stores that depend on its value: a store issued
       // right behind the load of the same address stalls the LSU until the load returns and costs 2.6x
       // (measured with tools/bw_probe.cu: 185 us vs 71 us for this stream on B200).
@@ -174,15 +213,15 @@ static int launch_update(const OptimArgs &a, bool adam, cudaStream_t st) {
   const long long blocks = std::max<long long>(1, (total4 - a.first4 + 255) / 256);
   SERT_REQUIRE(blocks < (1ll << 31), "parameter arena too large for one launch");
   const int g = (int)blocks;
-  if (adam) {
-    if (a.phase == 3) dense_update_kernel<true, 3><<<g, 256, 0, st>>>(a);
-    else if (a.phase == 4) dense_update_kernel<true, 4><<<g, 256, 0, st>>>(a);
-    else dense_update_kernel<true, 0><<<g, 256, 0, st>>>(a);
-  } else {
-    if (a.phase == 3) dense_update_kernel<false, 3><<<g, 256, 0, st>>>(a);
-    else if (a.phase == 4) dense_update_kernel<false, 4><<<g, 256, 0, st>>>(a);
-    else dense_update_kernel<false, 0><<<g, 256, 0, st>>>(a);
-  }
+#define SERT_UPD(ADAM_, S16_)                                                              \
+  do {                                                                                     \
+    if (a.phase == 3) dense_update_kernel<ADAM_, 3, S16_><<<g, 256, 0, st>>>(a);           \
+    else if (a.phase == 4) dense_update_kernel<ADAM_, 4, S16_><<<g, 256, 0, st>>>(a);      \
+    else dense_update_kernel<ADAM_, 0, S16_><<<g, 256, 0, st>>>(a);                        \
+  } while (0)
+  if (adam) { if (a.state_bf16) SERT_UPD(true, true); else SERT_UPD(true, false); }
+  else { if (a.state_bf16) SERT_UPD(false, true); else SERT_UPD(false, false); }
+#undef SERT_UPD
   SERT_LAUNCH_CHECK();
   if (a.phase == 0 && !a.no_finalize) {          // the loss is complete once the last phase of the step has run (phase 4 finalises itself)
     finalize_train_kernel<<<1, kSumsqSlots, 0, st>>>(a.acc, a.loss_out, a.inv_B, a.reg_coeff);
@@ -194,6 +233,7 @@ static int launch_update(const OptimArgs &a, bool adam, cudaStream_t st) {
 // Adam + L2 for the hot word rows of the fused tile kernel (kernels.cuh: VsFusedArgs::hot_slot): the gradient of hot
 // row s is the sum of its kHotReplicas private copies (plus whatever sits in the gradient row itself); the copies
 // are zeroed for the next step.  One CTA per hot row, one 16-byte chunk per thread, off the step's critical path.
+template <bool S16>
 __global__ void __launch_bounds__(128) hot_update_kernel(HotUpdateArgs h) {
   const int s = blockIdx.x;
   const int row = __ldg(h.hot_ids + s);
@@ -208,19 +248,18 @@ __global__ void __launch_bounds__(128) hot_update_kernel(HotUpdateArgs h) {
 #pragma unroll
     for (int r = 0; r < kHotReplicas; ++r) { g.x += v[r].x; g.y += v[r].y; g.z += v[r].z; g.w += v[r].w; }
     const float4 p = reinterpret_cast<float4 *>(h.theta)[i4];
-    const float4 x1 = reinterpret_cast<float4 *>(h.s1)[i4];
-    const float4 x2 = reinterpret_cast<float4 *>(h.s2)[i4];
+    float v1[4], v2[4];
+    load_state4<S16>(h.s1, (long long)i4, v1);
+    load_state4<S16>(h.s2, (long long)i4, v2);
     sumsq += p.x * p.x + p.y * p.y + p.z * p.z + p.w * p.w;
     float pv[4] = {p.x, p.y, p.z, p.w};
-    float v1[4] = {x1.x, x1.y, x1.z, x1.w};
-    float v2[4] = {x2.x, x2.y, x2.z, x2.w};
     const float gv[4] = {g.x, g.y, g.z, g.w};
 #pragma unroll
     for (int j = 0; j < 4; ++j)
       update_element<true>(pv[j], v1[j], v2[j], gv[j] + h.l2_scale * pv[j], h.c0, h.c1, h.c2, h.c3);
     reinterpret_cast<float4 *>(h.theta)[i4] = make_float4(pv[0], pv[1], pv[2], pv[3]);
-    reinterpret_cast<float4 *>(h.s1)[i4] = make_float4(v1[0], v1[1], v1[2], v1[3]);
-    reinterpret_cast<float4 *>(h.s2)[i4] = make_float4(v2[0], v2[1], v2[2], v2[3]);
+    store_state4<S16>(h.s1, (long long)i4, v1, (uint32_t)(i4 * 4), h.stamp, 0u);
+    store_state4<S16>(h.s2, (long long)i4, v2, (uint32_t)(i4 * 4), h.stamp, 1u);
     reinterpret_cast<float4 *>(h.grad)[i4] = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
     for (int r = 0; r < kHotReplicas; ++r)
@@ -241,7 +280,8 @@ int launch_hot_update(const HotUpdateArgs &h, cudaStream_t st) {
   if (h.n_hot <= 0) return 0;
   SERT_REQUIRE(h.d % 4 == 0 && h.table_offset % 4 == 0, "hot rows must be 16-byte aligned");
   const int threads = std::min(128, std::max(32, (h.d / 4 + 31) / 32 * 32));
-  hot_update_kernel<<<h.n_hot, threads, 0, st>>>(h);
+  if (h.state_bf16) hot_update_kernel<true><<<h.n_hot, threads, 0, st>>>(h);
+  else hot_update_kernel<false><<<h.n_hot, threads, 0, st>>>(h);
   SERT_LAUNCH_CHECK();
   return 0;
 }

@@ -156,7 +156,8 @@ static int validate(const sert_config &c) {
   SERT_REQUIRE(c.word_dim > 0 && c.word_dim % 4 == 0, "word representation size must be a positive multiple of 4");
   SERT_REQUIRE(c.loss_slots > 0, "loss_slots must be positive");
   SERT_REQUIRE(c.lambda >= 0.f, "regularization lambda must be >= 0");
-  SERT_REQUIRE(c.reserved0 == 0 && c.reserved1 == 0, "reserved config fields must be zero");
+  SERT_REQUIRE(c.dtype_mode == 0 || c.dtype_mode == 1, "dtype_mode must be 0 (float32) or 1 (bfloat16 optimiser state)");
+  SERT_REQUIRE(c.reserved1 == 0, "reserved config fields must be zero");
   if (is_vs(c)) {
     SERT_REQUIRE(c.entity_dim > 0 && c.entity_dim % 4 == 0,
                  "entity representation size must be a positive multiple of 4");
@@ -201,8 +202,13 @@ static size_t carve(sert_model &m, void *base) {
   m.total = o;
   const bool train = c.inference_only == 0;
   m.theta = b.take<float>(o);
-  m.s1 = train ? b.take<float>(o) : nullptr;
-  m.s2 = train ? b.take<float>(o) : nullptr;
+  if (c.dtype_mode == 1) {      // bfloat16 optimiser state: same element offsets, half the bytes
+    m.s1 = train ? reinterpret_cast<float *>(b.take<uint16_t>(o)) : nullptr;
+    m.s2 = train ? reinterpret_cast<float *>(b.take<uint16_t>(o)) : nullptr;
+  } else {
+    m.s1 = train ? b.take<float>(o) : nullptr;
+    m.s2 = train ? b.take<float>(o) : nullptr;
+  }
   m.grad = train ? b.take<float>(o) : nullptr;
   m.flagR = train ? b.take<uint32_t>(V) : nullptr;
   m.flagE = (train && is_vs(c)) ? b.take<uint32_t>(E) : nullptr;
@@ -279,6 +285,7 @@ static float adam_alpha_f32(int64_t t) {
 static OptimArgs optim_args(sert_model &m, float *loss_out) {
   OptimArgs a;
   a.theta = m.theta; a.s1 = m.s1; a.s2 = m.s2; a.grad = m.grad;
+  a.state_bf16 = m.cfg.dtype_mode == 1 ? 1 : 0;
   a.total = m.total;
   for (int s = 0; s < m.nseg; ++s) a.seg[s] = m.seg[s];
   for (int s = m.nseg; s < kMaxSegments; ++s) a.seg[s] = ParamSegment{0, 0, 1, 0, nullptr};
@@ -318,7 +325,7 @@ static int timed_update(sert_model &m, const OptimArgs &o, bool adam) {
   long long params = 0;
   for (int sg = 0; sg < o.num_segments; ++sg)
     if (o.phase == 0 || (o.phase == 3) == (o.seg[sg].flags != nullptr)) params += o.seg[sg].count;
-  m.prof_bytes = 24.0 * (double)params;
+  m.prof_bytes = (o.state_bf16 ? 16.0 : 24.0) * (double)params;   // theta rw + two state arrays rw
   if (rc || o.phase != 0) return rc;
   return launch_finalize_train(o.acc, o.loss_out, o.inv_B, o.reg_coeff, m.st);
 }
@@ -455,6 +462,7 @@ static int vs_train_step(sert_model &m, const int32_t *x, const int32_t *y, cons
       h.hot_acc = m.hot_acc; h.hot_ids = m.hot_ids; h.n_hot = m.n_hot;
       h.l2_scale = o.l2_scale; h.c0 = o.c0; h.c1 = o.c1; h.c2 = o.c2; h.c3 = o.c3;
       h.acc = acc; h.counted = 1;
+      h.state_bf16 = o.state_bf16; h.stamp = o.stamp;
       if (launch_hot_update(h, side)) return -1;
     }
     SERT_CUDA(cudaEventRecord(m.ev_join, side));
@@ -783,6 +791,19 @@ int sert_model_set_tensor(sert_model *m, int which, int slot, const float *host,
   SERT_REQUIRE(slot >= 0 && slot <= 2, "bad state slot");
   SERT_REQUIRE(slot == SERT_STATE_PARAM || m->cfg.inference_only == 0, "inference_only models keep no optimiser state");
   SERT_REQUIRE((long long)count == m->cnt[which], "tensor size mismatch");
+  if (slot != SERT_STATE_PARAM && m->cfg.dtype_mode == 1) {
+    // bfloat16 state: round to nearest even on the host (checkpoints written by this mode are exact in bf16)
+    std::vector<uint16_t> tmp(count);
+    for (size_t i = 0; i < count; ++i) {
+      uint32_t u;
+      memcpy(&u, host + i, 4);
+      tmp[i] = (uint16_t)((u + 0x7fffu + ((u >> 16) & 1u)) >> 16);
+    }
+    uint16_t *dst = reinterpret_cast<uint16_t *>(slot == SERT_STATE_S1 ? m->s1 : m->s2) + m->off[which];
+    SERT_CUDA(cudaMemcpyAsync(dst, tmp.data(), count * sizeof(uint16_t), cudaMemcpyHostToDevice, m->st));
+    SERT_CUDA(cudaStreamSynchronize(m->st));
+    return 0;
+  }
   SERT_CUDA(cudaMemcpyAsync(tensor_ptr(m, which, slot), host, count * sizeof(float), cudaMemcpyHostToDevice, m->st));
   SERT_CUDA(cudaStreamSynchronize(m->st));
   if (which == SERT_PARAM_DENSE_W && slot == SERT_STATE_PARAM) m->wpt_valid = false;
@@ -795,6 +816,17 @@ int sert_model_get_tensor(sert_model *m, int which, int slot, float *host, size_
   SERT_REQUIRE(slot >= 0 && slot <= 2, "bad state slot");
   SERT_REQUIRE(slot == SERT_STATE_PARAM || m->cfg.inference_only == 0, "inference_only models keep no optimiser state");
   SERT_REQUIRE((long long)count == m->cnt[which], "tensor size mismatch");
+  if (slot != SERT_STATE_PARAM && m->cfg.dtype_mode == 1) {
+    std::vector<uint16_t> tmp(count);
+    const uint16_t *src = reinterpret_cast<const uint16_t *>(slot == SERT_STATE_S1 ? m->s1 : m->s2) + m->off[which];
+    SERT_CUDA(cudaMemcpyAsync(tmp.data(), src, count * sizeof(uint16_t), cudaMemcpyDeviceToHost, m->st));
+    SERT_CUDA(cudaStreamSynchronize(m->st));
+    for (size_t i = 0; i < count; ++i) {
+      const uint32_t u = (uint32_t)tmp[i] << 16;
+      memcpy(host + i, &u, 4);
+    }
+    return 0;
+  }
   SERT_CUDA(cudaMemcpyAsync(host, tensor_ptr(m, which, slot), count * sizeof(float), cudaMemcpyDeviceToHost, m->st));
   SERT_CUDA(cudaStreamSynchronize(m->st));
   return 0;
@@ -808,6 +840,19 @@ int sert_model_set_step(sert_model *m, int64_t t) {
 int sert_model_get_step(sert_model *m, int64_t *t) {
   SERT_REQUIRE(m && t, "null argument");
   *t = m->step;
+  return 0;
+}
+
+int sert_model_get_sampler(sert_model *m, uint64_t *seed, uint64_t *draws) {
+  SERT_REQUIRE(m && seed && draws, "null argument");
+  *seed = m->cfg.seed;
+  *draws = m->sample_calls;
+  return 0;
+}
+int sert_model_set_sampler(sert_model *m, uint64_t seed, uint64_t draws) {
+  SERT_REQUIRE(m, "null model");
+  m->cfg.seed = seed;
+  m->sample_calls = draws;
   return 0;
 }
 

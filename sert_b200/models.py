@@ -38,17 +38,16 @@ def glorot_uniform(shape, rng=np.random):
     return rng.uniform(-a, a, size=shape).astype(np.float32)
 
 
-def l2_regularization(objects):
-    """Marker kept for signature compatibility (sert/models.py:92-120); the L2 term is fused into the
-    dense optimiser kernel (csrc/opt_kernels.cu)."""
-    raise NotImplementedError('the L2 term is evaluated on the device')
+# The reference passes a function here (sert/models.py:92-120); on this path the L2 term is evaluated inside the dense
+# optimiser kernel (csrc/opt_kernels.cu), so the attribute only names the regulariser.
+l2_regularization = 'l2'
 
 
 class _NativeModel(object):
     """Owns the HBM arena + the sert_model handle."""
 
     def __init__(self, kind, batch, window, vocab, entities, word_dim, entity_dim=0, num_negatives=0,
-                 lam=0.0, loss_slots=1 << 16, seed=None, device=None, inference_only=False):
+                 lam=0.0, loss_slots=1 << 16, seed=None, device=None, inference_only=False, dtype_mode=0):
         torch = _torch()
         self.lib = N.load()
         self.device = torch.device('cuda', torch.cuda.current_device() if device is None else device)
@@ -57,7 +56,7 @@ class _NativeModel(object):
         self.cfg = N.SertConfig(kind=kind, batch=batch, window=window, num_negatives=num_negatives or 0,
                                 vocab=vocab, entities=entities, word_dim=word_dim, entity_dim=entity_dim or 0,
                                 lambda_=lam, loss_slots=loss_slots, seed=seed,
-                                inference_only=int(bool(inference_only)), reserved0=0, reserved1=0)
+                                inference_only=int(bool(inference_only)), dtype_mode=int(dtype_mode), reserved1=0)
         nbytes = N.c_size_t(0)
         N.check(self.lib.sert_model_arena_bytes(N.ctypes.byref(self.cfg), N.ctypes.byref(nbytes)))
         with torch.cuda.device(self.device):
@@ -366,6 +365,9 @@ class ModelBase(ModelInterface):
     def get_checkpoint(self):
         """Every parameter tensor with both optimiser-state arrays plus the optimiser step, as host arrays."""
         ckpt = {'step': np.int64(self._native_step())}
+        seed, draws = N.ctypes.c_uint64(0), N.ctypes.c_uint64(0)
+        N.check(self._native.lib.sert_model_get_sampler(self._native.handle, N.ctypes.byref(seed), N.ctypes.byref(draws)))
+        ckpt['sampler_seed'], ckpt['sampler_draws'] = np.uint64(seed.value), np.uint64(draws.value)
         for name, (which, shape) in self._tensor_shapes().items():
             for slot, suffix in ((N.STATE_PARAM, ''), (N.STATE_S1, '/state1'), (N.STATE_S2, '/state2')):
                 ckpt[name + suffix] = self._gather_columns(name, self._native.get_tensor(which, shape, slot))
@@ -378,6 +380,9 @@ class ModelBase(ModelInterface):
                 assert array.shape == tuple(shape), (name + suffix, array.shape, shape)
                 self._native.set_tensor(which, array, slot)
         N.check(self._native.lib.sert_model_set_step(self._native.handle, int(ckpt['step'])))
+        if 'sampler_seed' in ckpt:       # the device negative sampler continues where the checkpointed run stood
+            N.check(self._native.lib.sert_model_set_sampler(self._native.handle, int(ckpt['sampler_seed']),
+                                                            int(ckpt['sampler_draws'])))
 
     # entity-sharded models (LanguageModel(entity_shard=...)) hold column slices of some tensors; checkpoints and
     # get_state() always carry the full tensors
@@ -680,7 +685,11 @@ class VectorSpaceLanguageModel(VectorSpaceLanguageModelBase):
                  regularization_lambda,
                  training_set,
                  validation_set,
-                 dense_init=None, device=None, seed=None, loss_slots=1 << 16):
+                 dense_init=None, device=None, seed=None, loss_slots=1 << 16, optimizer_state_dtype='float32'):
+        """``optimizer_state_dtype``: 'float32' (the reference's arithmetic; parity mode) or 'bfloat16' (perf mode of
+        BASELINE.json configs[1]: Adam's m and v stored as bfloat16 with stochastic rounding, 16 instead of 24 bytes
+        per parameter and step; parameters, gradients and every forward/backward value stay float32)."""
+        assert optimizer_state_dtype in ('float32', 'bfloat16')
         super(VectorSpaceLanguageModel, self).__init__(
             batch_size=batch_size,
             window_size=window_size,
@@ -706,7 +715,8 @@ class VectorSpaceLanguageModel(VectorSpaceLanguageModelBase):
             N.KIND_VECTORSPACE, self.batch_size, self.window_size, self.vocabulary_size, self.num_entities,
             self.representation_size, entity_dim=self.entity_representation_size,
             num_negatives=int(num_negative_samples), lam=float(regularization_lambda),
-            loss_slots=loss_slots, seed=seed, device=device)
+            loss_slots=loss_slots, seed=seed, device=device,
+            dtype_mode=1 if optimizer_state_dtype == 'bfloat16' else 0)
         self._native.set_tensor(N.PARAM_WORD_REPR, representations_init)
         self._native.set_tensor(N.PARAM_ENTITY_REPR, entity_representations_init)
         self._native.set_tensor(N.PARAM_DENSE_W, dense_init[0])

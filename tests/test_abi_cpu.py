@@ -30,7 +30,7 @@ def test_arena_size_and_config_validation(native_lib):
     from sert_b200 import _native as N
     cfg = N.SertConfig(kind=N.KIND_VECTORSPACE, batch=4096, window=10, num_negatives=10, vocab=100000,
                        entities=50000, word_dim=128, entity_dim=128, lambda_=0.01, loss_slots=1024, seed=1,
-                       inference_only=0, reserved0=0, reserved1=0)
+                       inference_only=0, dtype_mode=0, reserved1=0)
     nbytes = N.c_size_t(0)
     N.check(native_lib.sert_model_arena_bytes(ctypes.byref(cfg), ctypes.byref(nbytes)))
     params = 100000 * 128 + 50000 * 128 + 128 * 128 + 128

@@ -265,3 +265,54 @@ def test_checkpoint_resume_is_exact():
     Rb, Eb = b.get_representations()
     np.testing.assert_allclose(Ra, Rb, rtol=1e-6, atol=1e-9)     # atomics order may differ in the last bit
     np.testing.assert_allclose(Ea, Eb, rtol=1e-6, atol=1e-9)
+
+
+def test_bf16_optimizer_state_mode_tracks_the_float32_model():
+    """dtype_mode 1 (BASELINE.json configs[1] "bf16" perf mode): Adam's m / v live in bfloat16 with stochastic
+    rounding.  The forward pass is untouched (first loss identical), later losses and parameters follow the float32
+    oracle within the bf16 rounding of the state (stated deviation: 2e-3 relative on losses, 3 % of the parameter
+    change per step on parameters), the state reads back as bf16-representable values, and a checkpoint resumes."""
+    p = H.vs_problem(21, V=4000, E=1500, dw=128, de=128, W=10, B=256, k=10, n_batches=8)
+    model = make_model(p, 0.01, optimizer_state_dtype='bfloat16')
+    oracle = H.vs_oracle(p, 0.01)
+    R0 = p['R'].copy()
+    got, ref = [], []
+    for j in range(8):
+        got.append(model.train_fn(j, p['neg'][j]))
+        ref.append(oracle.train_batch(j, p['neg'][j]))
+    assert abs(got[0] - ref[0]) <= 1e-5 * abs(ref[0])
+    np.testing.assert_allclose(got, ref, rtol=2e-3)
+    R, Eemb = model.get_representations()
+    moved = np.abs(oracle.R - R0).mean()
+    assert np.abs(R - oracle.R).mean() < 0.03 * 8 * moved / 8 + 1e-7, (np.abs(R - oracle.R).mean(), moved)
+    ckpt = model.get_checkpoint()
+    state = ckpt['entity_representations/state2'] if 'entity_representations/state2' in ckpt else None
+    if state is not None:                     # what comes back is bf16-representable
+        assert (state.view(np.uint32) & 0xffff == 0).all()
+    other = make_model(p, 0.01, optimizer_state_dtype='bfloat16')
+    other.set_checkpoint(ckpt)
+    a, b = model.train_fn(0, p['neg'][0]), other.train_fn(0, p['neg'][0])
+    assert abs(a - b) <= 1e-6 * abs(a)
+    # the arena really is smaller: 16 instead of 24 bytes per parameter for (theta, m, v) + 4 for the gradient
+    full = make_model(p, 0.01)
+    assert model._native.arena.numel() < full._native.arena.numel() - 3 * (4000 + 1500) * 128
+
+
+def test_checkpoint_resumes_device_sampled_negatives():
+    """with negatives drawn on the device a resumed model must continue the Philox stream, not replay it."""
+    p = H.vs_problem(33, V=500, E=120, dw=32, de=32, W=4, B=64, k=4, n_batches=4)
+    a = make_model(p, 0.01, seed=1234)
+    for j in range(2):
+        a.train_fn(j)
+    ckpt = a.get_checkpoint()
+    assert int(ckpt['sampler_draws']) == 2 and int(ckpt['sampler_seed']) == 1234
+    tail_a = [a.train_fn(j) for j in (2, 3)]
+    b = make_model(p, 0.01, seed=99)
+    b.set_checkpoint(ckpt)
+    tail_b = [b.train_fn(j) for j in (2, 3)]
+    np.testing.assert_allclose(tail_a, tail_b, rtol=1e-6)
+    c = make_model(p, 0.01, seed=1234)          # same seed but a restarted stream: different negatives
+    ckpt2 = dict(ckpt)
+    ckpt2['sampler_draws'] = np.uint64(0)
+    c.set_checkpoint(ckpt2)
+    assert abs(c.train_fn(2) - tail_a[0]) > 1e-7
