@@ -360,6 +360,9 @@ def run_ours(args, rank, world, local_rank):
             return {'error': '%s: %s' % (type(exc).__name__, exc)}
 
     bf16_mode = leg(run_bf16_state_mode, p, cfg, steps, warm, repeats, first_losses, losses, rank, world, barrier)
+    if isinstance(bf16_mode, dict) and 'error' not in bf16_mode:
+        bf16_mode['float32_rerun_control'] = leg(run_bf16_state_mode, p, cfg, steps, warm, repeats, first_losses, losses,
+                                                 rank, world, barrier, state_dtype='float32')
     scoring = leg(run_scoring, CFG4, 'BASELINE.json configs[3]', rank, world, barrier, cpu=False)
     scoring_small = leg(run_scoring, CFG3, 'BASELINE.json configs[2]', rank, world, barrier, cpu=(rank == 0))
 
@@ -414,7 +417,8 @@ def run_ours(args, rank, world, local_rank):
         dist.destroy_process_group()
 
 
-def run_bf16_state_mode(p, cfg, steps, warm, repeats, f32_first_losses, f32_last_losses, rank, world, barrier):
+def run_bf16_state_mode(p, cfg, steps, warm, repeats, f32_first_losses, f32_last_losses, rank, world, barrier,
+                        state_dtype='bfloat16'):
     """BASELINE.json configs[1] says "bf16": the perf mode next to the float32 parity headline.  Same model, same
     batches, same step sequence, with Adam's m / v stored as bfloat16 (stochastic rounding) -- sert_config.dtype_mode 1:
     the dense update streams 16 instead of 24 bytes per parameter.  Parameters, gradients, forward and backward stay
@@ -428,7 +432,7 @@ def run_bf16_state_mode(p, cfg, steps, warm, repeats, f32_first_losses, f32_last
         batch_size=cfg['B'], window_size=cfg['W'], num_negative_samples=cfg['k'],
         representations_init=p['R'], entity_representations_init=p['Eemb'], regularization_lambda=cfg['lam'],
         training_set=p['train'], validation_set=p['val'], dense_init=(p['Wp'], p['bp']),
-        loss_slots=max(1024, n_batches), optimizer_state_dtype='bfloat16')
+        loss_slots=max(1024, n_batches), optimizer_state_dtype=state_dtype)
     nat, lib = model._native, model._native.lib
     neg_dev = torch.from_numpy(p['neg']).cuda()
     order = np.arange(n_batches, dtype=np.int64)
@@ -467,6 +471,11 @@ def run_bf16_state_mode(p, cfg, steps, warm, repeats, f32_first_losses, f32_last
     del model
     torch.cuda.empty_cache()
     rel = lambda a, b: float(np.max(np.abs(np.asarray(a, np.float64) - b) / np.abs(b)))
+    if state_dtype == 'float32':
+        # control: a second float32 run of the same sequence.  Its distance from the first one (float atomics order the
+        # gradient sums differently from run to run, and training amplifies that) is the yardstick for the bf16 figure.
+        return {'deviation_rel': rel(first, f32_first_losses),
+                'deviation_rel_last_pass': rel(last[warm:], f32_last_losses[warm:]), 'ms_per_step': ms}
     return {'workload': WORKLOAD.replace('float32', 'float32 parameters and gradients, bfloat16 Adam state (dtype_mode 1)'),
             'value': world * cfg['B'] / (ms * 1e-3), 'unit': UNIT, 'ms_per_step': ms, 'dtype': 'f32 + bf16 optimiser state',
             'roofline': {'bound': 'hbm', 'kernel': 'dense_update_kernel<Adam, tables, bf16 state>', 'achieved': achieved,

@@ -100,36 +100,63 @@ __global__ void __launch_bounds__(256) dense_update_kernel(OptimArgs a) {
   float4 *__restrict__ g4 = reinterpret_cast<float4 *>(a.grad);
   float sumsq = 0.f;
 
-  const long long i4 = a.first4 + (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i4 < total4) {
-    const long long e = i4 << 2;
-    int s = 0;
+  // One 16-byte chunk of theta / gradient per thread, whatever the state type: with bfloat16 state the 8-byte state
+  // accesses of a warp still fill whole 32-byte sectors, and tools/bf16_state_probe.cu measures 6.23 TB/s for this
+  // shape against 5.0-5.7 TB/s for 8 elements per thread (16-byte state accesses or two adjacent chunks).
+  constexpr int CH = 1;
+  const long long base4 = a.first4 + ((long long)blockIdx.x * blockDim.x + threadIdx.x) * CH;
+  // phase A: where each chunk lives, whether its row was touched, and every load of every chunk in flight at once
+  int sgi[CH];
+  bool act[CH], touched[CH];
+  float4 p[CH], g[CH];
+  float v1[CH][4], v2[CH][4];
 #pragma unroll
-    for (int q = 1; q < kMaxSegments; ++q) s += (q < a.num_segments && e >= a.seg[q].offset) ? 1 : 0;
-    const ParamSegment &sg = a.seg[s];
-    const bool live = (e - sg.offset) < sg.count;   // false only inside inter-segment padding
-    bool touched = true, skip = false;
-    if (live && sg.flags != nullptr) {
-      const unsigned int row = (unsigned int)(e - sg.offset) / (unsigned int)sg.row_len;
-      const uint32_t flag = __ldg(sg.flags + row);
-      touched = (flag == a.stamp);
-      skip = (flag == kHotRowMark);       // updated by hot_update_kernel on the side stream
+  for (int ch = 0; ch < CH; ++ch) {
+    const long long i4 = base4 + ch;
+    act[ch] = false; touched[ch] = false; sgi[ch] = 0;
+    g[ch] = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (i4 < total4) {
+      const long long e = i4 << 2;
+      int s = 0;
+#pragma unroll
+      for (int q = 1; q < kMaxSegments; ++q) s += (q < a.num_segments && e >= a.seg[q].offset) ? 1 : 0;
+      const ParamSegment &sg = a.seg[s];
+      const bool live = (e - sg.offset) < sg.count;   // false only inside inter-segment padding
+      bool tch = true, skip = false;
+      if (live && sg.flags != nullptr) {
+        const unsigned int row = (unsigned int)(e - sg.offset) / (unsigned int)sg.row_len;
+        const uint32_t flag = __ldg(sg.flags + row);
+        tch = (flag == a.stamp);
+        skip = (flag == kHotRowMark);       // updated by hot_update_kernel on the side stream
+      }
+      const bool mine = PHASE == 0 ? true : PHASE == 3 ? (sg.flags != nullptr) : (sg.flags == nullptr);
+      sgi[ch] = s;
+      act[ch] = live && mine && !skip;
+      touched[ch] = act[ch] && tch;
+      if (act[ch]) {
+        p[ch] = th4[i4];
+        load_state4<S16>(a.s1, i4, v1[ch]);
+        load_state4<S16>(a.s2, i4, v2[ch]);
+        if (touched[ch]) g[ch] = __ldcg(g4 + i4);
+      }
     }
-    const bool mine = PHASE == 0 ? true : PHASE == 3 ? (sg.flags != nullptr) : (sg.flags == nullptr);
-    if (live && mine && !skip) {
-      const float4 p = th4[i4];
-      float v1[4], v2[4];
-      load_state4<S16>(a.s1, i4, v1);
-      load_state4<S16>(a.s2, i4, v2);
-      float4 g = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (touched) g = __ldcg(g4 + i4);
+  }
+  // phase B: update and store
+#pragma unroll
+  for (int ch = 0; ch < CH; ++ch) {
+    if (act[ch]) {
+      const long long i4 = base4 + ch;
+      const long long e = i4 << 2;
+      const int s = sgi[ch];
+      const ParamSegment &sg = a.seg[s];
       const float l2 = sg.regularised ? a.l2_scale : 0.0f;
-      if (sg.regularised == 1) sumsq = p.x * p.x + p.y * p.y + p.z * p.z + p.w * p.w;
-      float pv[4] = {p.x, p.y, p.z, p.w};
-      const float gv[4] = {g.x, g.y, g.z, g.w};
+      if (sg.regularised == 1)
+        sumsq += p[ch].x * p[ch].x + p[ch].y * p[ch].y + p[ch].z * p[ch].z + p[ch].w * p[ch].w;
+      float pv[4] = {p[ch].x, p[ch].y, p[ch].z, p[ch].w};
+      const float gv[4] = {g[ch].x, g[ch].y, g[ch].z, g[ch].w};
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
-        update_element<ADAM>(pv[j], v1[j], v2[j], gv[j] + l2 * pv[j], a.c0, a.c1, a.c2, a.c3);
+        update_element<ADAM>(pv[j], v1[ch][j], v2[ch][j], gv[j] + l2 * pv[j], a.c0, a.c1, a.c2, a.c3);
       }
       th4[i4] = make_float4(pv[0], pv[1], pv[2], pv[3]);
       if (PHASE == 4 && a.transposed != nullptr && s == a.transposed_segment) {
@@ -139,12 +166,12 @@ __global__ void __launch_bounds__(256) dense_update_kernel(OptimArgs a) {
 #pragma unroll
         for (int j = 0; j < 4; ++j) a.transposed[(size_t)(c + j) * a.transposed_rows + r] = pv[j];
       }
-      store_state4<S16>(a.s1, i4, v1, (uint32_t)e, a.stamp, 0u);
-      store_state4<S16>(a.s2, i4, v2, (uint32_t)e, a.stamp, 1u);
+      store_state4<S16>(a.s1, i4, v1[ch], (uint32_t)e, a.stamp, 0u);
+      store_state4<S16>(a.s2, i4, v2[ch], (uint32_t)e, a.stamp, 1u);
       // The gradient row is zeroed only now, behind the stores that depend on its value: a store issued
       // right behind the load of the same address stalls the LSU until the load returns and costs 2.6x
       // (measured with tools/bw_probe.cu: 185 us vs 71 us for this stream on B200).
-      if (touched) g4[i4] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (touched[ch]) g4[i4] = make_float4(0.f, 0.f, 0.f, 0.f);
     }
   }
 
@@ -210,7 +237,8 @@ static int launch_update(const OptimArgs &a, bool adam, cudaStream_t st) {
   SERT_REQUIRE(a.transposed == nullptr || a.seg[a.transposed_segment].row_len % 4 == 0,
                "transposed copy needs rows of 4n floats");
   const long long total4 = a.total / 4;
-  const long long blocks = std::max<long long>(1, (total4 - a.first4 + 255) / 256);
+  const long long per_block = 256;                           // 16-byte chunks per block (dense_update_kernel: CH = 1)
+  const long long blocks = std::max<long long>(1, (total4 - a.first4 + per_block - 1) / per_block);
   SERT_REQUIRE(blocks < (1ll << 31), "parameter arena too large for one launch");
   const int g = (int)blocks;
 #define SERT_UPD(ADAM_, S16_)                                                              \
