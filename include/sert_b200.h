@@ -286,6 +286,12 @@ SERT_API int sert_scorer_set_mode(sert_scorer *s, int32_t mode);
 /* Host counters since creation: top-k calls answered by the seeded one-launch sweep / calls that fell back to the
  * chunked sweeps (measurement and tests; no reference counterpart). */
 SERT_API int sert_scorer_stats(sert_scorer *s, int64_t *seeded_sweeps, int64_t *fallback_sweeps);
+/* The threshold-seeding plan of a top-k call on this shard (tests, diagnostics): the sample is `groups` groups of
+ * `group_rows` consecutive rows, taken from every `tile_stride`-th tile of 256 rows; tau is seeded from the
+ * `rank`-th largest group maximum; about `expected_survivors` rows per query pass.  group_rows = 0: no seed (the
+ * shard fits a candidate list, or no sample small enough exists). */
+SERT_API int sert_scorer_plan(sert_scorer *s, int32_t k, int32_t *group_rows, int32_t *groups, int32_t *rank,
+                              int64_t *tile_stride, double *expected_survivors);
 /* Row-sharded scoring: this scorer holds rows [row_begin, row_begin+rows) of the global matrix and
  * `comm` joins the other shards.  Every top-k call then runs the local sweep, ONE ncclAllGather of the packed
  * (row id, score)[q,k] lists (q*k*8 bytes per rank) and a k-way merge on the scorer's stream, and returns the top k of

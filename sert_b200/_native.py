@@ -90,6 +90,8 @@ SIGNATURES = {
                                    c_size_t, c_void_p, ctypes.POINTER(c_void_p)]),
     'sert_scorer_destroy': (c_int, [c_void_p]),
     'sert_scorer_set_mode': (c_int, [c_void_p, c_int32]),
+    'sert_scorer_plan': (c_int, [c_void_p, c_int32, ctypes.POINTER(c_int32), ctypes.POINTER(c_int32),
+                                 ctypes.POINTER(c_int32), ctypes.POINTER(c_int64), ctypes.POINTER(ctypes.c_double)]),
     'sert_scorer_stats': (c_int, [c_void_p, ctypes.POINTER(c_int64), ctypes.POINTER(c_int64)]),
     'sert_scorer_topk_host': (c_int, [c_void_p, c_void_p, c_int32, c_int32, c_int32, c_void_p, c_void_p]),
     'sert_scorer_scores_host': (c_int, [c_void_p, c_void_p, c_int32, c_int32, c_void_p]),

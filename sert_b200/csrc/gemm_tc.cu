@@ -373,15 +373,19 @@ gemm_tc_kernel(const __grid_constant__ TcMap map_a, const __grid_constant__ TcMa
                                   fmaxf(__uint_as_float(v[8 * j + 6]), __uint_as_float(v[8 * j + 7])));
             m4[j] = fmaxf(a, b);
           }
+          float *dst = ep.gmax + (size_t)gm * ep.gmax_ld + (size_t)nt * (BN / ep.group) + (col_lo + ci * 32) / ep.group;
           if (ep.group == 8) {
-            if (row_ok)
-              *reinterpret_cast<float4 *>(ep.gmax + (size_t)gm * ep.gmax_ld + (size_t)nt * (BN / 8) +
-                                          (col_lo + ci * 32) / 8) = make_float4(m4[0], m4[1], m4[2], m4[3]);
+            if (row_ok) *reinterpret_cast<float4 *>(dst) = make_float4(m4[0], m4[1], m4[2], m4[3]);
+          } else if (ep.group == 16) {
+            if (row_ok) *reinterpret_cast<float2 *>(dst) = make_float2(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3]));
+          } else if (ep.group == 32) {
+            if (row_ok) *dst = fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3]));
           } else {
             mx = fmaxf(mx, fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3])));
           }
         }
-        if (ep.group != 8 && row_ok) ep.gmax[(size_t)gm * ep.gmax_ld + (size_t)nt * (BN / COLS_PER_WARP) + col_lo / COLS_PER_WARP] = mx;
+        if (ep.group == COLS_PER_WARP && row_ok)
+          ep.gmax[(size_t)gm * ep.gmax_ld + (size_t)nt * (BN / COLS_PER_WARP) + col_lo / COLS_PER_WARP] = mx;
       } else {
         // ---- running top-k filter.  The chunk loop stays rolled: the epilogue's code must stay resident in the
         // instruction caches (a fully unrolled two-pass version measured 6x slower: the warps sat in "no

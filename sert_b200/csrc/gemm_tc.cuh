@@ -29,7 +29,7 @@ struct TcEpilogue {
   long long row_offset = 0;     // global id of B row 0
   int *overflow = nullptr;      // set to 1 when a candidate list is full
   // TC_EPI_GROUPMAX (threshold seeding of the scoring sweep, score.cu): every n-tile must be full (256 valid rows).
-  // gmax[m * gmax_ld + tile * (256 / group) + c / group] = max over the `group` (8 or 64) columns around column c
+  // gmax[m * gmax_ld + tile * (256 / group) + c / group] = max over the `group` (8, 16, 32 or 64) columns around column c
   // of n-tile `tile`; nothing else is written.
   float *gmax = nullptr;
   int gmax_ld = 0;

@@ -16,6 +16,8 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <vector>
+
 #include "comm.cuh"
 #include "gemm_tc.cuh"
 #include "kernels.cuh"
@@ -762,50 +764,108 @@ static int topk_pass(const TopkState &s, const float *queries_dev, int Q, int k_
   return 0;
 }
 
+// ---- optional phase timing (SERT_SCORE_TRACE=1): CUDA events between the phases of a call, printed to stderr ------
+struct PhaseTrace {
+  static constexpr int kMax = 12;
+  cudaEvent_t ev[kMax];
+  const char *name[kMax];
+  int n = 0;
+  bool on = false;
+  cudaStream_t st = nullptr;
+  explicit PhaseTrace(cudaStream_t s) : st(s) {
+    static const bool enabled = getenv("SERT_SCORE_TRACE") != nullptr;
+    on = enabled;
+  }
+  void mark(const char *what) {
+    if (!on || n >= kMax) return;
+    cudaEventCreate(&ev[n]);
+    cudaEventRecord(ev[n], st);
+    name[n++] = what;
+  }
+  void report(const char *title) {
+    if (!on || n < 2) return;
+    cudaEventSynchronize(ev[n - 1]);
+    fprintf(stderr, "[sert trace] %s:", title);
+    for (int i = 1; i < n; ++i) {
+      float ms = 0.f;
+      cudaEventElapsedTime(&ms, ev[i - 1], ev[i]);
+      fprintf(stderr, " %s %.1f us |", name[i], ms * 1e3f);
+    }
+    float tot = 0.f;
+    cudaEventElapsedTime(&tot, ev[0], ev[n - 1]);
+    fprintf(stderr, " total %.1f us\n", tot * 1e3f);
+    for (int i = 0; i < n; ++i) cudaEventDestroy(ev[i]);
+    n = 0;
+  }
+};
+
 // ---- seeded sweep: plan ------------------------------------------------------------------------------------------
 // Picks the row sample (G groups of g rows = G*g/256 strided n-tiles) and the rank j of the group maximum that seeds
-// tau so that about T ~ 5k rows per query survive the one-launch sweep.  With x = g T / rows a group holds a row
-// above the T-th best score with probability 1 - exp(-x); j = that fraction of G.  j >= 16 keeps the survivor count
-// concentrated (relative spread ~ 1/sqrt(j)): P(fewer than k survive) ~ P(Gamma(j) < j k / T) < 1e-6 per query at
-// T = 5k; when the sample would have to exceed G = 256 groups T is raised instead.  Of the two group sizes the
-// epilogue offers, the smaller sample wins.  Shards of at most cap/2 rows need no seed (every row fits the list).
+// tau so that about T rows per query survive the one-launch sweep.  With x = g T / rows a group holds a row above the
+// T-th best score with probability 1 - exp(-x); j = that fraction of G.  The survivor count concentrates like
+// Gamma(j) / j: P(fewer than k survive) ~ P(Gamma(j) < j k / T) = P(Poisson(j k / T) >= j), so a smaller T needs a
+// larger j, i.e. a larger sample.  The epilogue and the finalize kernel cost in proportion to T (measured: the sweep
+// of 10 k queries over 50 k rows takes ~0.7 us per unit of T), the sample in proportion to G*g rows: the plan takes the
+// smallest T = r k, r in {3, 4, 5, 6, 8, 10, 16}, whose sample stays below a sixth of the shard and 512 groups, at a
+// failure probability below 1e-7 per query.  Shards of at most cap/2 rows need no seed (every row fits the list).
 struct SweepPlan {
   bool seeded = false;
   int g = 0, G = 0, j = 0;
   long long stride = 1;       // n-tiles between sample tiles
+  double T = 0;               // expected survivors per query
 };
+
+// smallest j with P(Poisson(j / r) >= j) <= eps
+static int seed_rank_for_ratio(double r, double eps) {
+  for (int j = 4; j <= 400; ++j) {
+    const double lam = j / r;
+    double term = exp(-lam), cdf = term;             // P(X <= j-1)
+    for (int i = 1; i < j; ++i) { term *= lam / i; cdf += term; }
+    if (1.0 - cdf <= eps) return j;
+  }
+  return 400;
+}
 
 static SweepPlan topk_plan(long long rows, int k, int cap) {
   SweepPlan best;
-  const double T0 = std::max(5.0 * k, 320.0);
-  for (int g : {8, 64}) {
-    const int unit = 256 / g;                                 // groups per n-tile
-    double x = T0 * g / (double)rows;
-    if (x > 1.0) continue;
-    double frac = 1.0 - exp(-x);
-    long long G = (long long)ceil(32.0 / frac);
-    G = std::min<long long>((G + unit - 1) / unit * unit, kSeedGroups);
-    int j = (int)floor(frac * (double)G);
-    if (j < 16) {
-      j = 16;                                                 // raises the expected survivors to rows * -ln(1 - j/G) / g
-      const double T = (double)rows * -log(1.0 - (double)j / (double)G) / g;
-      if (T > cap / 4) continue;
+  if (rows <= cap / 2) return best;
+  const double ratios[] = {3, 4, 5, 6, 8, 10, 16};
+  for (double r : ratios) {
+    const double T = std::max(r * k, 96.0);
+    if (T > cap / 4) break;
+    const int j = std::max(seed_rank_for_ratio(T / k, 1e-7), 8);
+    for (int g : {8, 16, 32, 64}) {
+      const int unit = 256 / g;                               // groups per n-tile
+      const double x = T * g / (double)rows;
+      if (x > 1.2) continue;
+      const double frac = 1.0 - exp(-x);
+      long long G = (long long)ceil(j / frac);
+      G = (G + unit - 1) / unit * unit;
+      if (G > kSeedGroups) continue;
+      const long long S = G * g;
+      if (S * 6 > rows) continue;
+      const int jj = std::max(j, (int)floor(frac * (double)G));   // rounding G up may only raise the rank, never T
+      if (!best.seeded || S < (long long)best.G * best.g) {
+        best.seeded = true;
+        best.g = g; best.G = (int)G; best.j = jj;
+        best.stride = ((rows + 255) / 256) / (S / 256);
+        best.T = (double)rows * -log(1.0 - (double)jj / (double)G) / g;
+      }
     }
-    const long long S = G * g;
-    if (S * 2 > rows) continue;
-    if (!best.seeded || S < (long long)best.G * best.g) {
-      best.seeded = true;
-      best.g = g; best.G = (int)G; best.j = j;
-      best.stride = ((rows + 255) / 256) / (S / 256);
-    }
+    if (best.seeded) return best;
   }
   return best;
 }
 
 static int finalize_per_warp_bytes(int cmax, int d) { return (int)align_up((size_t)cmax * 8 + 1024 + (size_t)d * 4, 16); }
 
+// `deferred`: non-null = the caller checks the seeded attempt itself.  If the seeded one-launch sweep applies, it is
+// only ENQUEUED (no host synchronisation): *deferred = 1 and the verdict is left in s.overflow on the device (non-zero
+// = the result is not valid; call again with deferred == nullptr).  Otherwise *deferred = 0 and the call completes as
+// usual.  `allow_seeded` = false skips the seeded attempt (the retry after a failed one).
 int topk_sweep(const TopkState &s, const float *queries_dev, int Q, int k, int32_t *out_idx, float *out_score,
-               cudaStream_t st) {
+               cudaStream_t st, int *deferred, bool allow_seeded) {
+  if (deferred) *deferred = 0;
   SERT_REQUIRE(k >= 1 && k <= s.cap / 2, "k exceeds the scorer's max_k");
   SERT_REQUIRE(Q >= 0 && Q <= s.max_queries, "more queries than the scorer's max_queries");
   if (Q == 0) return 0;
@@ -813,6 +873,8 @@ int topk_sweep(const TopkState &s, const float *queries_dev, int Q, int k, int32
   // tensor-core mode keeps a margin of candidates beyond k so that bf16x3 rounding at the k-th place
   // cannot drop a true top-k row before the exact re-scoring
   const int k_sel = tensor ? std::min(s.cap / 2, k + 16) : k;
+  PhaseTrace trace(st);
+  trace.mark("start");
   if (tensor) {
     // split rows [hi|hi|mid] of the queries, their coarse-score margins, list state reset
     prep_queries_kernel<<<cdiv(Q, 8), 256, 0, st>>>(queries_dev, Q, s.d, s.kt / s.terms, s.q_split, s.ent_norm_max,
@@ -829,9 +891,10 @@ int topk_sweep(const TopkState &s, const float *queries_dev, int Q, int k, int32
     const int per_warp = finalize_per_warp_bytes(cmax, s.d);
     const int warps = std::min(8, (200 * 1024) / per_warp);
     const SweepPlan plan = topk_plan(s.rows, k, s.cap);
-    if (s.seeded && warps >= 1 && s.rows > 0 && (plan.seeded || s.rows <= s.cap / 2)) {
+    if (allow_seeded && s.seeded && warps >= 1 && s.rows > 0 && (plan.seeded || s.rows <= s.cap / 2)) {
       // Seeded one-launch sweep: sample GEMM -> tau -> ONE GEMM over the shard -> finalize (select, re-score, sort).
       SERT_CUDA(cudaMemsetAsync(s.overflow, 0, sizeof(int), st));
+      trace.mark("prep");
       TcEpilogue ep;
       const int depth = s.kt / s.terms;     // first block of both split operands = the hi term
       if (plan.seeded) {
@@ -839,22 +902,32 @@ int topk_sweep(const TopkState &s, const float *queries_dev, int Q, int k, int32
         ep.gmax = s.gmax; ep.gmax_ld = kSeedGroups; ep.group = plan.g; ep.tile_stride = (int)plan.stride;
         const long long sample_rows = (long long)plan.G * plan.g;
         if (launch_gemm_tc_ld(s.q_split, s.kt, Q, s.ent_split, s.kt, s.rows, 0, sample_rows, depth, ep, st)) return -1;
+        trace.mark("sample");
         seed_tau_kernel<<<cdiv(Q, 8), 256, 0, st>>>(s.gmax, kSeedGroups, plan.G, plan.j, s.margin, s.tau, Q);
         SERT_LAUNCH_CHECK();
+        trace.mark("seed");
       }
       ep = TcEpilogue();
       ep.mode = TC_EPI_TOPK;
       ep.tau = s.tau; ep.count = s.count; ep.cand = s.cand; ep.cap = s.cap; ep.row_offset = s.row_begin;
       ep.overflow = s.overflow;
       if (launch_gemm_tc_ld(s.q_split, s.kt, Q, s.ent_split, s.kt, s.rows, 0, s.rows, depth, ep, st)) return -1;
+      trace.mark("sweep");
       FinalizeArgs fa;
       fa.Qm = queries_dev; fa.En = s.entities; fa.Q = Q; fa.d = s.d; fa.row_begin = s.row_begin; fa.rows = s.rows;
       fa.cand = s.cand; fa.count = s.count; fa.cap = s.cap; fa.tau = s.tau; fa.margin = s.margin; fa.k = k;
       fa.cmax = cmax; fa.out_idx = out_idx; fa.out_score = out_score; fa.flag = s.overflow; fa.per_warp_bytes = per_warp;
       finalize_kernel<<<cdiv(Q, warps), warps * 32, (size_t)warps * per_warp, st>>>(fa);
       SERT_LAUNCH_CHECK();
+      trace.mark("finalize");
+      if (deferred) {
+        *deferred = 1;
+        trace.report("seeded sweep (check deferred)");
+        return 0;
+      }
       SERT_CUDA(cudaMemcpyAsync(&overflow, s.overflow, sizeof(int), cudaMemcpyDeviceToHost, st));
       SERT_CUDA(cudaStreamSynchronize(st));
+      trace.report("seeded sweep");
       if (s.stats) ++s.stats[overflow ? 1 : 0];
       if (!overflow) return 0;
       // a list came up short, overflowed, or held too many near-ties: the multi-chunk sweeps below answer
@@ -949,25 +1022,136 @@ struct sert_scorer {
   float *out_score = nullptr;
   int max_k = 0;
   long long stats[2] = {0, 0};
+  long long retries = 0;        // sharded calls repeated with full-length lists
   // row-sharded scoring (sert_scorer_set_comm): gathered per-shard lists, world blocks of [ids (Q,k) | scores (Q,k)]
   sert_comm *comm = nullptr;
   int32_t *gathered = nullptr;
 };
 
-// Top k of the GLOBAL entity matrix on every rank: local sweep into this rank's block of the gather buffer, ONE
-// all-gather of the packed (row id, score)[Q,k] lists (Q k 8 bytes per rank), k-way merge.  Keys carry global row
-// ids and ties order by row id, so the merged list equals the single-device list.
-static int scorer_topk(sert_scorer *s, const float *q_dev, int q, int k, int32_t *out_idx, float *out_score) {
-  if (s->comm == nullptr || s->comm->world == 1) return sert::topk_sweep(s->s, q_dev, q, k, out_idx, out_score, s->st);
-  const size_t block = (size_t)2 * q * k;                    // 32-bit words per rank
-  int32_t *mine = s->gathered + (size_t)s->comm->rank * block;
-  if (sert::topk_sweep(s->s, q_dev, q, k, mine, reinterpret_cast<float *>(mine + (size_t)q * k), s->st)) return -1;
-  if (sert::comm_all_gather(s->comm, mine, s->gathered, block * 4, s->st)) return -1;
-  return sert::launch_topk_merge(s->gathered, reinterpret_cast<const float *>(s->gathered + (size_t)q * k), s->comm->world,
-                                 q, k, out_idx, out_score, s->st, block);
+// ---- merge of the gathered per-shard lists (row-sharded scoring), one warp per query -----------------------------
+// Every part's list is sorted (best first) and keys are unique, so an entry's place in the merged order is its place
+// in its own list plus, for every other part, the number of that part's keys above it -- one binary search each; no
+// sort.  Entries whose place is below k are written straight to their slot.  When the parts sent fewer than k
+// entries each (k_loc < k, scorer_topk), a part ALL of whose entries made the global top k may hold further rows that
+// belong there: that sets *flag and the call is repeated with full-length lists.
+namespace sert {
+__global__ void __launch_bounds__(256) merge_sorted_kernel(const int32_t *__restrict__ gathered, size_t part_stride,
+                                                           int parts, int Q, int k_loc, int k,
+                                                           int32_t *__restrict__ out_idx, float *__restrict__ out_score,
+                                                           int *__restrict__ flag) {
+  extern __shared__ unsigned long long mkeys[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int q = blockIdx.x * (blockDim.x >> 5) + warp;
+  if (q >= Q) return;
+  const int n = parts * k_loc;
+  unsigned long long *keys = mkeys + (size_t)warp * n;
+  int valid = 0;
+  for (int e = lane; e < n; e += 32) {
+    const int p = e / k_loc, i = e - p * k_loc;
+    const int32_t *blk = gathered + (size_t)p * part_stride;
+    const int32_t id = blk[(size_t)q * k_loc + i];
+    const float sc = reinterpret_cast<const float *>(blk + (size_t)Q * k_loc)[(size_t)q * k_loc + i];
+    keys[e] = id >= 0 ? make_key(sc, (unsigned int)id) : 0ull;
+    valid += id >= 0 ? 1 : 0;
+  }
+  valid = __reduce_add_sync(0xffffffffu, valid);
+  __syncwarp();
+  bool more = false;
+  for (int e = lane; e < n; e += 32) {
+    const unsigned long long key = keys[e];
+    if (key == 0ull) continue;
+    const int p = e / k_loc, i = e - p * k_loc;
+    int place = i;
+    for (int o = 0; o < parts; ++o) {
+      if (o == p) continue;
+      const unsigned long long *other = keys + o * k_loc;
+      int lo = 0, hi = k_loc;                                // first position of `other` holding a smaller key
+      while (lo < hi) {
+        const int mid = (lo + hi) >> 1;
+        if (other[mid] > key) lo = mid + 1; else hi = mid;
+      }
+      place += lo;
+    }
+    if (place < k) {
+      out_idx[(size_t)q * k + place] = (int32_t)key_row(key);
+      out_score[(size_t)q * k + place] = key_score(key);
+      if (i == k_loc - 1 && k_loc < k) more = true;         // this part's whole list is inside the global top k
+    }
+  }
+  for (int i = valid + lane; i < k; i += 32) {               // fewer than k rows in all shards together
+    out_idx[(size_t)q * k + i] = -1;
+    out_score[(size_t)q * k + i] = -INFINITY;
+  }
+  if (__any_sync(0xffffffffu, more) && lane == 0) *flag = 1;
+}
+}  // namespace sert
+
+static int parts_bytes(int world, int k_loc) { return (int)sert::align_up((size_t)world * k_loc * 8, 16); }
+
+// Entries a shard contributes to a global top k over `world` equal shards: mean k / world plus six standard
+// deviations of the binomial count, so that on rows spread evenly over the shards one attempt in ~1e8 (per query and
+// shard) is repeated; never more than k.
+static int shard_list_length(int k, int world) {
+  const double mean = (double)k / world;
+  const int k_loc = (int)ceil(mean + 6.0 * sqrt(mean * (1.0 - 1.0 / world)) + 2.0);
+  return std::min(k, std::max(k_loc, 8));
 }
 
-
+// Top k of the GLOBAL entity matrix on every rank: local sweep into this rank's block of the gather buffer, ONE
+// all-gather of the packed (row id, score)[Q, k_loc] lists, merge.  Keys carry global row ids and ties order by row
+// id, so the merged list equals the single-device list.  First attempt: every shard sends its best k_loc <= k rows
+// (shard_list_length) and the seeded local sweep is not checked on the host; the blocks carry each rank's verdict,
+// the merge adds its own, and ONE synchronisation at the end reads them.  All ranks see the same gathered data,
+// hence take the same decision: on any doubt the call is repeated with k rows per shard and checked local sweeps.
+static int scorer_topk(sert_scorer *s, const float *q_dev, int q, int k, int32_t *out_idx, float *out_score) {
+  if (s->comm == nullptr || s->comm->world == 1)
+    return sert::topk_sweep(s->s, q_dev, q, k, out_idx, out_score, s->st, nullptr, true);
+  if (q == 0) return 0;
+  const int world = s->comm->world;
+  bool seeded_ok = true;          // false once some rank's seeded sweep reported a failure: the retry uses chunked sweeps
+  for (int attempt = 0; attempt < 2; ++attempt) {
+    const int k_loc = attempt == 0 ? shard_list_length(k, world) : k;
+    const size_t block = (size_t)2 * q * k_loc + 4;           // 32-bit words per rank: ids, scores, verdict + padding
+    int32_t *mine = s->gathered + (size_t)s->comm->rank * block;
+    sert::PhaseTrace trace(s->st);
+    trace.mark("start");
+    int deferred = 0;
+    if (sert::topk_sweep(s->s, q_dev, q, k_loc, mine, reinterpret_cast<float *>(mine + (size_t)q * k_loc), s->st,
+                         attempt == 0 ? &deferred : nullptr, seeded_ok))
+      return -1;
+    if (deferred) {
+      SERT_CUDA(cudaMemcpyAsync(mine + (size_t)2 * q * k_loc, s->s.overflow, sizeof(int), cudaMemcpyDeviceToDevice, s->st));
+    } else {
+      SERT_CUDA(cudaMemsetAsync(mine + (size_t)2 * q * k_loc, 0, sizeof(int), s->st));
+    }
+    SERT_CUDA(cudaMemsetAsync(s->s.overflow + 3, 0, sizeof(int), s->st));      // the merge's verdict
+    trace.mark("local sweep");
+    if (sert::comm_all_gather(s->comm, mine, s->gathered, block * 4, s->st)) return -1;
+    trace.mark("all-gather");
+    const int per_warp = parts_bytes(world, k_loc);
+    const int warps = std::max(1, std::min(8, (96 * 1024) / per_warp));
+    sert::merge_sorted_kernel<<<sert::cdiv(q, warps), warps * 32, (size_t)warps * per_warp, s->st>>>(
+        s->gathered, block, world, q, k_loc, k, out_idx, out_score, s->s.overflow + 3);
+    SERT_LAUNCH_CHECK();
+    trace.mark("merge");
+    // verdicts: one word per rank inside the gathered blocks + the merge's
+    int merge_flag = 0;
+    std::vector<int> local_flags((size_t)world, 0);
+    SERT_CUDA(cudaMemcpyAsync(&merge_flag, s->s.overflow + 3, sizeof(int), cudaMemcpyDeviceToHost, s->st));
+    SERT_CUDA(cudaMemcpy2DAsync(local_flags.data(), sizeof(int), s->gathered + (size_t)2 * q * k_loc, block * 4,
+                                sizeof(int), world, cudaMemcpyDeviceToHost, s->st));
+    SERT_CUDA(cudaStreamSynchronize(s->st));
+    trace.report(attempt == 0 ? "sharded top-k" : "sharded top-k (full-length retry)");
+    bool redo = merge_flag != 0;
+    for (int r = 0; r < world; ++r)
+      if (local_flags[r] != 0) { redo = true; seeded_ok = false; }
+    if (deferred) ++s->stats[local_flags[s->comm->rank] ? 1 : 0];
+    if (!redo) return 0;
+    ++s->retries;
+  }
+  sert::set_error("sharded top-k: the full-length attempt reported a failure");
+  return -1;
+}
 
 namespace sert {
 static size_t carve_scorer(sert_scorer &sc, void *base, int64_t rows, int d, int max_queries, int max_k) {
@@ -1073,6 +1257,15 @@ int sert_scorer_set_mode(sert_scorer *s, int32_t mode) {
   return 0;
 }
 
+int sert_scorer_plan(sert_scorer *s, int32_t k, int32_t *group_rows, int32_t *groups, int32_t *rank,
+                     int64_t *tile_stride, double *expected_survivors) {
+  SERT_REQUIRE(s && group_rows && groups && rank && tile_stride && expected_survivors, "null argument");
+  const sert::SweepPlan p = sert::topk_plan(s->s.rows, k, s->s.cap);
+  *group_rows = p.seeded ? p.g : 0;
+  *groups = p.G; *rank = p.j; *tile_stride = p.stride; *expected_survivors = p.T;
+  return 0;
+}
+
 int sert_scorer_stats(sert_scorer *s, int64_t *seeded_sweeps, int64_t *fallback_sweeps) {
   SERT_REQUIRE(s && seeded_sweeps && fallback_sweeps, "null argument");
   *seeded_sweeps = s->stats[0];
@@ -1085,7 +1278,7 @@ int sert_scorer_set_comm(sert_scorer *s, sert_comm *comm) {
   if (s->gathered) { cudaStreamSynchronize(s->st); cudaFree(s->gathered); s->gathered = nullptr; }
   s->comm = comm;
   if (comm != nullptr && comm->world > 1)
-    SERT_CUDA(cudaMalloc(&s->gathered, (size_t)comm->world * 2 * s->s.max_queries * s->max_k * sizeof(int32_t)));
+    SERT_CUDA(cudaMalloc(&s->gathered, (size_t)comm->world * ((size_t)2 * s->s.max_queries * s->max_k + 4) * sizeof(int32_t)));
   return 0;
 }
 

@@ -41,12 +41,12 @@ struct TopkState {
   long long *stats = nullptr;           // host counters: [0] sweeps answered by the seeded path, [1] sweeps that fell back
 };
 
-constexpr int kSeedGroups = 256;        // most group maxima per query the threshold seed selects from
+constexpr int kSeedGroups = 512;        // most group maxima per query the threshold seed selects from
 
 int launch_normalise_rows(const float *in, float *out, int64_t rows, int d, cudaStream_t st);
 int topk_prepare(int cap);
 int topk_sweep(const TopkState &s, const float *queries_dev, int Q, int k, int32_t *out_idx, float *out_score,
-               cudaStream_t st);
+               cudaStream_t st, int *deferred = nullptr, bool allow_seeded = true);
 // part p's lists start at idx + p * part_stride / score + p * part_stride (0 = Q * k: dense [part][q][k] arrays)
 int launch_topk_merge(const int32_t *idx, const float *score, int parts, int Q, int k, int32_t *out_idx,
                       float *out_score, cudaStream_t st, size_t part_stride = 0);

@@ -46,6 +46,15 @@ class EntityScorer(object):
         re-scoring) or 'fma' (fp32 CUDA-core tiles)."""
         N.check(self.lib.sert_scorer_set_mode(self.handle, {'fma': 0, 'tensor': 1, 'tensor3': 2, 'tensor_chunked': 3}[mode]))
 
+    def plan(self, k):
+        """Threshold-seeding plan of a top-k call: dict(group_rows, groups, rank, tile_stride, expected_survivors)."""
+        g, G, j = N.c_int32(0), N.c_int32(0), N.c_int32(0)
+        stride, T = N.c_int64(0), N.ctypes.c_double(0)
+        N.check(self.lib.sert_scorer_plan(self.handle, int(k), N.ctypes.byref(g), N.ctypes.byref(G), N.ctypes.byref(j),
+                                          N.ctypes.byref(stride), N.ctypes.byref(T)))
+        return dict(group_rows=g.value, groups=G.value, rank=j.value, tile_stride=stride.value,
+                    expected_survivors=T.value)
+
     def stats(self):
         """(calls answered by the seeded one-launch sweep, calls that fell back to the chunked sweeps)."""
         a, b = N.c_int64(0), N.c_int64(0)

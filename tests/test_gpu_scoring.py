@@ -196,11 +196,14 @@ def test_seeded_sweep_falls_back_when_the_sample_misleads():
     rows, d, k = 20000, 64, 100
     E = O.normalise_rows(rng.standard_normal((rows, d))) * np.float32(0.5)
     q = O.normalise_rows(rng.standard_normal((3, d)))
-    # plan for (20000 rows, k=100): groups of 8 rows, 192 groups = 6 sample tiles, every 13th n-tile (score.cu: topk_plan)
-    n_tiles = (rows + 255) // 256
-    stride = n_tiles // 6
-    for i in range(50):
-        E[(i % 6) * stride * 256 + 8 * (i // 6)] = q[0] * np.float32(0.9)
+    sc = EntityScorer(E, max_queries=8, max_k=128)
+    plan = sc.plan(k)
+    assert plan['group_rows'] > 0 and plan['rank'] < 50 < k
+    per_tile = 256 // plan['group_rows']
+    for i in range(50):                      # one such row in each of 50 sample groups
+        tile, group = divmod(i, per_tile)
+        E[tile * plan['tile_stride'] * 256 + group * plan['group_rows']] = q[0] * np.float32(0.9)
+    sc.close()
     sc = EntityScorer(E, max_queries=8, max_k=128)
     idx, score = sc.topk(q, k)
     assert sc.stats() == (0, 1), sc.stats()
