@@ -8,10 +8,9 @@ sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), '..'
 from cvangysel import argparse_utils, logging_utils, trec_utils  # noqa: E402
 from sert import inference, models  # noqa: E402
 from sert_b200.ranking import (  # noqa: E402,F401
-    Callback, LogLinearCallback, VectorSpaceCallback, compute_normalised_entropy)
+    Callback, LogLinearCallback, RunCollector, VectorSpaceCallback, compute_normalised_entropy)
 
 import argparse  # noqa: E402
-import collections  # noqa: E402
 import io  # noqa: E402
 import logging  # noqa: E402
 import pickle  # noqa: E402
@@ -60,14 +59,9 @@ def main(argv=None):
 
     model_name = os.path.basename(args.model)
 
-    topics_per_entity = collections.defaultdict(list)     # entity profiling
-    entities_per_topic = collections.defaultdict(list)    # entity finding
-
-    def ranker_callback(topic_id, top_ranked_indices, top_ranked_values):
-        for entity_internal_id, relevance in zip(top_ranked_indices, top_ranked_values):
-            entity_id = entity_indices_inv[entity_internal_id]
-            topics_per_entity[entity_id].append((relevance, topic_id))
-            entities_per_topic[topic_id].append((relevance, entity_id))
+    # entity profiling / entity finding rankings, kept as arrays (sert_b200.ranking.RunCollector) instead of the
+    # reference's two dictionaries of (relevance, id) tuples (bin/query.py:80-92)
+    ranker_callback = RunCollector(entity_indices_inv)
 
     with open('{0}_debug'.format(args.run_out), 'w') as f_debug_out:
         if model_args.type == models.LanguageModel:
@@ -104,11 +98,9 @@ def main(argv=None):
 
         batcher.process()
 
-    with io.open('{0}_ep'.format(args.run_out), 'w', encoding='utf8') as out_ep_run:
-        trec_utils.write_run(model_name, topics_per_entity, out_ep_run)
-
-    with io.open('{0}_ef'.format(args.run_out), 'w', encoding='utf8') as out_ef_run:
-        trec_utils.write_run(model_name, entities_per_topic, out_ef_run)
+    with io.open('{0}_ep'.format(args.run_out), 'w', encoding='utf8') as out_ep_run, \
+            io.open('{0}_ef'.format(args.run_out), 'w', encoding='utf8') as out_ef_run:
+        ranker_callback.write(model_name, out_ep_run, out_ef_run)
 
     logging.info('Saved run to %s.', args.run_out)
 

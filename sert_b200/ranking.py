@@ -26,7 +26,10 @@ import numpy as np
 from cvangysel import trec_utils
 from sert_b200 import inference, math_utils
 
-CANDIDATE_MARGIN = 28       # extra device candidates re-ranked on the host (fp32 near-ties at the k-th place)
+# Extra device candidates fetched with the first request and re-ranked on the host.  NOT a correctness bound: query()
+# verifies every row's candidate set against a float32 rounding bound and asks again with more candidates (finally all
+# entities) until the set provably contains the k nearest entities by float64 distance.
+CANDIDATE_MARGIN = 28
 
 
 class Callback(object):
@@ -165,33 +168,77 @@ class VectorSpaceCallback(Callback):
         if scorer_factory is None:
             from sert_b200.scoring import EntityScorer
             scorer_factory = EntityScorer
+        # room to ask for more candidates when near-ties at the k-th place demand it (query())
+        self.max_candidates = min(num_entities, max(4 * (self.num_candidates or 1), 1024)) if n_neighbors else 1
         self.scorer = scorer_factory(entity_representations, normalise=False, max_queries=1024,
-                                     max_k=max(self.num_candidates or 1, 1))
+                                     max_k=max(self.max_candidates, 1))
         self.entity_neighbors = self.scorer if n_neighbors else None
 
     # -- candidate search -------------------------------------------------------------------------
     def query(self, centroids):
         """(distances, indices) with the reference's meaning: per row, the k nearest entities by Euclidean
-        distance in ascending order (k = --top), or all entities when --top is unset (bin/query.py:304-318)."""
+        distance in ascending order (k = --top), or all entities when --top is unset (bin/query.py:304-318).
+
+        The device ranks by float32 inner product; the reference's tree search ranks by float64 Euclidean distance
+        between the float32 vectors.  A candidate set of m rows (device order) provably contains the k nearest when
+        no row OUTSIDE it can be closer than the k-th nearest inside it: an outside row scores at most the m-th
+        device score s_m, so its squared distance is at least |e|^2_min + |q|^2 - 2 (s_m + eps) with eps the float32
+        summation error bound (d + 2) 2^-24 |q| |e|_max.  Rows for which that bound does not clear the k-th distance
+        (masses of near-ties around the k-th place) are asked again with four times the candidates, finally with the
+        dense scores of all entities."""
         centroids = np.ascontiguousarray(centroids, dtype=np.float32)
         E = self.entity_representations
-        if self.n_neighbors:
-            cand_idx, _ = self.scorer.topk(centroids, self.num_candidates)
-        else:
+        num_rows = centroids.shape[0]
+        k = self.n_neighbors or E.shape[0]
+        distances = np.full((num_rows, k), np.inf, dtype=np.float64)
+        indices = np.full((num_rows, k), -1, dtype=np.int64)
+        if not self.n_neighbors:
             scores = self.scorer.scores(centroids)
             cand_idx = np.argsort(-scores, axis=1, kind='stable')
-        k = self.n_neighbors or E.shape[0]
-        distances = np.empty((centroids.shape[0], k), dtype=np.float64)
-        indices = np.empty((centroids.shape[0], k), dtype=np.int64)
-        for row in range(centroids.shape[0]):
-            cands = cand_idx[row]
-            cands = cands[cands >= 0]
-            diff = E[cands].astype(np.float64) - centroids[row].astype(np.float64)
-            dist = np.sqrt(np.einsum('ij,ij->i', diff, diff))
-            order = np.argsort(dist, kind='stable')[:k]
-            indices[row, :len(order)] = cands[order]
-            distances[row, :len(order)] = dist[order]
+            for row in range(num_rows):
+                self._select(E, centroids[row], cand_idx[row], k, distances, indices, row)
+            return distances, indices
+        if not hasattr(self, '_norm_sq'):
+            sq = np.einsum('ij,ij->i', E.astype(np.float64), E.astype(np.float64))
+            self._norm_sq = (float(sq.min()), float(np.sqrt(sq.max())))
+        e_sq_min, e_norm_max = self._norm_sq
+        pending = np.arange(num_rows)
+        m = self.num_candidates
+        while pending.size:
+            if m >= E.shape[0]:                                # every entity is a candidate: nothing left to prove
+                scores = self.scorer.scores(centroids[pending])
+                order = np.argsort(-scores, axis=1, kind='stable')
+                for j, row in enumerate(pending):
+                    self._select(E, centroids[row], order[j], k, distances, indices, row)
+                break
+            cand_idx, cand_score = self.scorer.topk(centroids[pending], m)
+            unresolved = []
+            for j, row in enumerate(pending):
+                cands = cand_idx[j]
+                present = cands >= 0
+                kth = self._select(E, centroids[row], cands[present], k, distances, indices, row)
+                if not present.all():                          # the scorer ran out of rows: all of them are candidates
+                    continue
+                q64 = centroids[row].astype(np.float64)
+                q_sq = float(q64 @ q64)
+                eps = (E.shape[1] + 2) * 2.0 ** -24 * np.sqrt(q_sq) * e_norm_max
+                outside_sq = e_sq_min + q_sq - 2.0 * (float(cand_score[j, -1]) + eps)
+                if not outside_sq > kth * kth:
+                    unresolved.append(row)
+            pending = np.asarray(unresolved, dtype=np.int64)
+            m = min(4 * m, self.max_candidates) if m < self.max_candidates else E.shape[0]
         return distances, indices
+
+    @staticmethod
+    def _select(E, centroid, cands, k, distances, indices, row):
+        """The k nearest of `cands` by float64 distance, ascending, into row `row`; returns the k-th distance."""
+        diff = E[cands].astype(np.float64) - centroid.astype(np.float64)
+        dist = np.sqrt(np.einsum('ij,ij->i', diff, diff))
+        order = np.argsort(dist, kind='stable')[:k]
+        assert len(order) == k, 'the scorer returned fewer candidates than neighbours were asked for'
+        indices[row, :] = cands[order]
+        distances[row, :] = dist[order]
+        return float(dist[order[-1]])
 
     # -- ranking ----------------------------------------------------------------------------------
     def _normalise(self, term_projections):
@@ -306,3 +353,83 @@ def write_topk_run(model_name, topic_ids, top_indices, relevances, entity_indice
     if written < 0:
         N.check(int(written))
     out_f.write(out[:written].tobytes().decode('utf8'))
+
+
+class RunCollector(object):
+    """``ranker_callback`` of bin/query.py:83-92 without per-assessment tuples: keeps, per topic, the arrays the
+    ranking callback hands over, and writes both run files of bin/query.py:149-156 from flat arrays --
+    ``<run_out>_ef`` (entity finding: topics rank entities) and ``<run_out>_ep`` (entity profiling: entities rank
+    topics).  Same bytes as feeding ``trec_utils.write_run`` the two dictionaries the reference builds: subjects in
+    first-insertion order, assessments by descending (relevance, object id) (trec_utils.py:560-561), relevance
+    printed as '{0}'.format(value) (the float64 repr of the value, also for numpy.float32).  One lexsort per file and
+    the library's host-side formatter instead of Q x E tuples, two tuple sorts per subject and a str.format per line."""
+
+    def __init__(self, entity_indices_inv):
+        self.entity_indices_inv = entity_indices_inv
+        self.topic_ids, self.indices, self.values = [], [], []
+
+    def __call__(self, topic_id, top_ranked_indices, top_ranked_values):
+        self.topic_ids.append(topic_id)
+        self.indices.append(np.asarray(top_ranked_indices, dtype=np.int64).ravel())
+        self.values.append(np.asarray(top_ranked_values).ravel())
+
+    def _flat(self):
+        lengths = np.array([len(i) for i in self.indices], dtype=np.int64)
+        topic_of = np.repeat(np.arange(len(self.indices), dtype=np.int64), lengths)
+        entity = np.concatenate(self.indices) if self.indices else np.zeros(0, np.int64)
+        value = (np.concatenate([v.astype(np.float64) for v in self.values]) if self.values
+                 else np.zeros(0, np.float64))
+        return topic_of, entity, value
+
+    @staticmethod
+    def _string_rank(strings):
+        """Rank of every string in sorted order (ties share a rank): a numeric stand-in for string comparison."""
+        _, inverse = np.unique(np.asarray(strings, dtype=str), return_inverse=True)
+        return inverse.astype(np.int64)
+
+    def write(self, model_name, out_ep, out_ef, max_objects_per_query=sys.maxsize):
+        from sert_b200 import _native as N
+        topic_of, entity, value = self._flat()
+        if entity.size == 0:
+            return
+        entity_ids = sorted(set(entity.tolist()))
+        entity_pos = {e: i for i, e in enumerate(entity_ids)}
+        entity_names = [self.entity_indices_inv[e] for e in entity_ids]
+        entity_of = np.fromiter((entity_pos[e] for e in entity.tolist()), dtype=np.int64, count=entity.size)
+        topic_rank = self._string_rank(self.topic_ids)
+        entity_rank = self._string_rank(entity_names)
+        topic_blob, topic_off = _utf8_blob(self.topic_ids)
+        entity_blob, entity_off = _utf8_blob(entity_names)
+        model = str(model_name).encode('utf8')
+        lib = N.load()
+
+        def emit(subject_of, subject_order_key, object_of, object_rank, subject_blob, subject_off, object_blob,
+                 object_off, out_f):
+            # lines ordered by subject (insertion order), then descending (relevance, object id)
+            order = np.lexsort((-object_rank[object_of], -value, subject_order_key[subject_of]))
+            subj, obj, val = subject_of[order], object_of[order], value[order]
+            starts = np.flatnonzero(np.r_[True, subj[1:] != subj[:-1]])
+            rank = np.arange(subj.size) - np.repeat(starts, np.diff(np.r_[starts, subj.size])) + 1
+            keep = rank <= max_objects_per_query
+            subj, obj, val, rank = subj[keep], obj[keep], val[keep], rank[keep]
+            n = int(subj.size)
+            longest = int(np.diff(subject_off).max(initial=0) + np.diff(object_off).max(initial=0)) + len(model) + 64
+            out = np.empty(max(1, n * longest), dtype=np.uint8)
+            written = lib.sert_format_run(
+                N.host_ptr(subject_blob), N.host_ptr(subject_off), N.host_ptr(object_blob), N.host_ptr(object_off),
+                N.host_ptr(np.ascontiguousarray(subj, dtype=np.int32)), N.host_ptr(np.ascontiguousarray(obj, dtype=np.int32)),
+                N.host_ptr(np.ascontiguousarray(rank, dtype=np.int32)), N.host_ptr(np.ascontiguousarray(val)), n, model,
+                N.host_ptr(out), out.size)
+            if written < 0:
+                N.check(int(written))
+            out_f.write(out[:written].tobytes().decode('utf8'))
+
+        # entity profiling: subjects = entities in order of first appearance (dict insertion order of the reference)
+        first_seen = np.full(len(entity_ids), entity.size, dtype=np.int64)
+        np.minimum.at(first_seen, entity_of, np.arange(entity.size))
+        entity_order = np.empty(len(entity_ids), dtype=np.int64)
+        entity_order[np.argsort(first_seen, kind='stable')] = np.arange(len(entity_ids))
+        emit(entity_of, entity_order, topic_of, topic_rank, entity_blob, entity_off, topic_blob, topic_off, out_ep)
+        # entity finding: subjects = topics in call order
+        emit(topic_of, np.arange(len(self.topic_ids), dtype=np.int64), entity_of, entity_rank, topic_blob, topic_off,
+             entity_blob, entity_off, out_ef)

@@ -281,3 +281,81 @@ def test_write_topk_run_from_device_style_arrays():
     trec_utils.write_run('m.bin', data, a)
     ranking.write_topk_run('m.bin', topics, idx, rel, inv, b)
     assert a.getvalue() == b.getvalue() and a.getvalue().count('\n') == (idx >= 0).sum()
+
+
+def test_candidate_set_is_verified_and_grown_on_near_ties():
+    """more near-ties around the k-th place than the first request's candidate margin.  200 entities lie
+    within float32 noise of one another along the query direction, in an order the float32 inner product cannot
+    resolve; the k nearest by float64 distance (what the reference's tree search returns) must still come out, which
+    needs the second, larger request."""
+    import io
+    from sert_b200 import ranking
+    rng = np.random.default_rng(8)
+    d, n, k = 16, 3000, 10
+    q = rng.standard_normal(d).astype(np.float32)
+    q /= np.linalg.norm(q)
+    E = rng.standard_normal((n, d)).astype(np.float32)
+    E /= np.linalg.norm(E, axis=1)[:, None]
+    ties = rng.choice(n, 200, replace=False)
+    for j, row in enumerate(ties):                       # q plus a perturbation at the float32 rounding level
+        v = q.astype(np.float64) * (1.0 + 1e-8 * j)
+        v[j % d] += 3e-8 * ((j * 7919) % 13 - 6)
+        E[row] = v.astype(np.float32)
+
+    class Args(object):
+        top = k
+
+    class ModelArgs(object):
+        entity_representation_size = d
+
+    calls = []
+
+    class CountingScorer(NumpyScorer):
+        def topk(self, queries, kk):
+            calls.append(kk)
+            return NumpyScorer.topk(self, queries, kk)
+
+    cb = ranking.VectorSpaceCallback(E.copy(), Args(), ModelArgs(), ['w'], io.StringIO(), lambda *a: None,
+                                     scorer_factory=CountingScorer)
+    En = cb.entity_representations
+    dist, idx = cb.query(q.reshape(1, -1).copy())
+    diff = En.astype(np.float64) - q.astype(np.float64)
+    ref = np.sqrt(np.einsum('ij,ij->i', diff, diff))
+    ref_order = np.argsort(ref, kind='stable')[:k]
+    np.testing.assert_array_equal(np.sort(ref[idx[0]]), np.sort(ref[ref_order]))     # the same k distances
+    assert set(idx[0].tolist()) <= set(ties.tolist())
+    assert len(calls) >= 2 and calls[1] > calls[0], calls                              # it had to ask again
+
+
+def test_run_collector_writes_the_reference_run_files():
+    """bin/query.py's ranker_callback + two write_run calls (bin/query.py:83-92,149-156) against RunCollector: same
+    bytes for the entity-profiling and the entity-finding run, including relevance ties (broken by descending id),
+    float32 and float64 relevances, topics of different lengths and entities first seen late."""
+    import collections
+    import io
+    from cvangysel import trec_utils
+    from sert_b200.ranking import RunCollector
+    rng = np.random.default_rng(3)
+    inv = {i: 'ent-%03d' % ((i * 37) % 50) for i in range(50)}
+    calls = []
+    for t in range(12):
+        n = int(rng.integers(1, 30))
+        idx = rng.choice(50, n, replace=False)
+        val = (rng.integers(0, 6, n) / 5.0 + (rng.random(n) < 0.5) * rng.random(n) * 1e-3)
+        val = val.astype(np.float32) if t % 2 else val.astype(np.float64)
+        order = np.argsort(-val, kind='stable')
+        calls.append(('topic-%d' % (97 - 7 * t), idx[order], val[order]))
+    topics_per_entity, entities_per_topic = collections.defaultdict(list), collections.defaultdict(list)
+    collector = RunCollector(inv)
+    for topic_id, idx, val in calls:
+        collector(topic_id, idx, val)
+        for entity_internal_id, relevance in zip(idx, val):          # the reference's ranker_callback
+            entity_id = inv[entity_internal_id]
+            topics_per_entity[entity_id].append((relevance, topic_id))
+            entities_per_topic[topic_id].append((relevance, entity_id))
+    ref_ep, ref_ef, got_ep, got_ef = io.StringIO(), io.StringIO(), io.StringIO(), io.StringIO()
+    trec_utils.write_run('model', topics_per_entity, ref_ep)
+    trec_utils.write_run('model', entities_per_topic, ref_ef)
+    collector.write('model', got_ep, got_ef)
+    assert got_ef.getvalue() == ref_ef.getvalue()
+    assert got_ep.getvalue() == ref_ep.getvalue()
