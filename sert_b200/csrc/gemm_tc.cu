@@ -334,7 +334,7 @@ gemm_tc_kernel(const __grid_constant__ TcMap map_a, const __grid_constant__ TcMa
           tc_wait_ld();
           const long long gn0 = n0 + c0;
           if (row_ok && gn0 < args.n_end) {
-            float *dst = ep.C + (long long)gm * ep.ldc + gn0;
+            float *dst = gm == ep.extra_row ? ep.extra_dst + gn0 : ep.C + (long long)gm * ep.ldc + gn0;
             const bool full = (gn0 + 32 <= args.n_end) && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0);
             if (full) {
 #pragma unroll
@@ -342,8 +342,13 @@ gemm_tc_kernel(const __grid_constant__ TcMap map_a, const __grid_constant__ TcMa
                 float4 o = make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]), __uint_as_float(v[j + 2]),
                                        __uint_as_float(v[j + 3]));
                 if (ep.bias != nullptr) {
-                  o.x += ep.bias[gn0 + j]; o.y += ep.bias[gn0 + j + 1];
-                  o.z += ep.bias[gn0 + j + 2]; o.w += ep.bias[gn0 + j + 3];
+                  if ((reinterpret_cast<uintptr_t>(ep.bias + gn0) & 15) == 0) {        // one broadcast 16-byte load
+                    const float4 bv = __ldg(reinterpret_cast<const float4 *>(ep.bias + gn0 + j));
+                    o.x += bv.x; o.y += bv.y; o.z += bv.z; o.w += bv.w;
+                  } else {
+                    o.x += ep.bias[gn0 + j]; o.y += ep.bias[gn0 + j + 1];
+                    o.z += ep.bias[gn0 + j + 2]; o.w += ep.bias[gn0 + j + 3];
+                  }
                 }
                 *reinterpret_cast<float4 *>(dst + j) = o;
               }

@@ -21,6 +21,10 @@ struct TcEpilogue {
   float *C = nullptr;
   long long ldc = 0;
   const float *bias = nullptr;
+  // TC_EPI_STORE, optional: row `extra_row` of C goes to extra_dst[n] instead of C (a row of ones appended to A turns
+  // the GEMM's last output row into the column sums of B^T -- the bias gradient of the log-linear layer for free)
+  int extra_row = -1;
+  float *extra_dst = nullptr;
   // TC_EPI_TOPK: rows are queries, columns are entity rows [n_begin, n_end) of B
   const unsigned long long *tau = nullptr;
   int *count = nullptr;

@@ -6,6 +6,8 @@
 // reductions (warp shuffles + one smem hop).
 #include "ll_kernels.cuh"
 
+#include <cuda_bf16.h>
+
 namespace sert {
 
 __device__ __forceinline__ float block_max(float v, float *sm) {
@@ -80,27 +82,40 @@ int launch_ll_softmax_inplace(float *Z, int64_t rows, int E, int64_t ldz, const 
 }
 
 // ---- joint logits S[i,e] = sum_w log clip(p[i,w,e]) ------------------------------------------------
+__global__ void ll_log_kernel(const float *__restrict__ in, float *__restrict__ out, long long n) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = logf(in[i]);
+}
+
 __global__ void __launch_bounds__(256) ll_joint_kernel(const float *__restrict__ Z,
                                                        const float *__restrict__ rmax,
-                                                       const float *__restrict__ rsum, float *__restrict__ S,
+                                                       const float *__restrict__ lrsum, float *__restrict__ S,
                                                        int B, int W, int E, long long ldz, long long lds) {
   const int e = blockIdx.x * blockDim.x + threadIdx.x;
   const int i = blockIdx.y;
   if (e >= E) return;
+  // log clip(p, lo, hi) = clip(log p, log lo, log hi) (log is monotone), and log p = z - max - log(sum): the W terms
+  // of an entity cost a subtraction and two compares each instead of exp, divide and log (4.6 -> 1.6 ms at
+  // BASELINE configs[4], where this pass is pure streaming of the 8.2 GB logit matrix).  The two forms differ by the
+  // rounding of exp / divide / log (~1e-7 relative on log p), far inside the 1e-4 parity tolerance.
+  const float log_lo = logf(SERT_CLIP_LO), log_hi = logf(SERT_CLIP_HI);
   float acc = 0.f;
   for (int w = 0; w < W; ++w) {
     const long long r = (long long)i * W + w;
-    const float p = expf(Z[r * ldz + e] - rmax[r]) / rsum[r];
-    acc += logf(clipf_(p, SERT_CLIP_LO, SERT_CLIP_HI));
+    const float lp = (Z[r * ldz + e] - rmax[r]) - __ldg(lrsum + r);
+    acc += fminf(fmaxf(lp, log_lo), log_hi);
   }
   S[(long long)i * lds + e] = acc;
 }
 
 int launch_ll_joint(const float *Z, const float *rmax, const float *rsum, float *S, int B, int W, int E,
-                    int64_t ldz, int64_t lds, cudaStream_t st) {
+                    int64_t ldz, int64_t lds, cudaStream_t st, float *lrsum_scratch) {
   if (B == 0) return 0;
+  SERT_REQUIRE(lrsum_scratch != nullptr, "the joint pass needs B*W floats of scratch");
+  ll_log_kernel<<<cdiv((long long)B * W, 256), 256, 0, st>>>(rsum, lrsum_scratch, (long long)B * W);
+  SERT_LAUNCH_CHECK();
   dim3 grid(cdiv(E, 256), B);
-  ll_joint_kernel<<<grid, 256, 0, st>>>(Z, rmax, rsum, S, B, W, E, ldz, lds);
+  ll_joint_kernel<<<grid, 256, 0, st>>>(Z, rmax, lrsum_scratch, S, B, W, E, ldz, lds);
   SERT_LAUNCH_CHECK();
   return 0;
 }
@@ -202,6 +217,159 @@ int launch_ll_dz(float *Z, const float *rmax, const float *rsum, const float *DS
   if (mode == 0) ll_dz_kernel<0><<<grid, threads, 0, st>>>(Z, rmax, rsum, DS, rows, W, E, ldz, lds, racc);
   else if (mode == 1) ll_dz_kernel<1><<<grid, threads, 0, st>>>(Z, rmax, rsum, DS, rows, W, E, ldz, lds, racc);
   else ll_dz_kernel<2><<<grid, threads, 0, st>>>(Z, rmax, rsum, DS, rows, W, E, ldz, lds, racc);
+  SERT_LAUNCH_CHECK();
+  return 0;
+}
+
+// ---- fused backward tail of the tensor-core path ---------------------------------------------------------------
+// dZ = dpp - p * acc_r (acc_r = sum over the row's unclipped entries of ds) never exists in float32: pass A streams
+// Z once for acc_r, pass B streams it once more and writes dZ directly as the two bf16x3 split operands the gradient
+// GEMMs consume -- dZs (B*W, 3*E64), K-major A of dX = dZ . Wd^T, and dZT_s (E, 3*BW64), K-major B of gWd = X^T . dZ
+// (transposed through shared memory).  Replaces ll_dz (2 reads + 1 write of Z) + split_bf16 + split_bf16_t + colsum
+// (3 more reads of the float32 dZ): 30 ms -> 9 ms at BASELINE configs[4].  The clip mask is evaluated in the log
+// domain, log p = z - max - log(sum) against log(1e-7) / log(1 - 1e-7), like ll_joint_kernel.
+__global__ void __launch_bounds__(256) ll_racc_log_kernel(const float *__restrict__ Z, const float *__restrict__ rmax,
+                                                          const float *__restrict__ lrsum,
+                                                          const float *__restrict__ DS, long long rows, int W, int E,
+                                                          long long ldz, long long lds, float *__restrict__ racc) {
+  __shared__ float sm[32];
+  const float log_lo = logf(SERT_CLIP_LO), log_hi = logf(SERT_CLIP_HI);
+  for (long long r = blockIdx.x; r < rows; r += gridDim.x) {
+    const float *z = Z + r * ldz;
+    const float *ds = DS + (r / W) * lds;
+    const float off = rmax[r] + lrsum[r];
+    float acc = 0.f;
+    if ((E & 3) == 0 && (ldz & 3) == 0 && (lds & 3) == 0) {
+      const float4 *z4 = reinterpret_cast<const float4 *>(z);
+      const float4 *d4 = reinterpret_cast<const float4 *>(ds);
+      for (int e = threadIdx.x; e < (E >> 2); e += blockDim.x) {
+        const float4 zv = __ldcs(z4 + e);
+        const float4 dv = __ldg(d4 + e);
+        const float l0 = zv.x - off, l1 = zv.y - off, l2 = zv.z - off, l3 = zv.w - off;
+        acc += (l0 >= log_lo && l0 <= log_hi) ? dv.x : 0.f;
+        acc += (l1 >= log_lo && l1 <= log_hi) ? dv.y : 0.f;
+        acc += (l2 >= log_lo && l2 <= log_hi) ? dv.z : 0.f;
+        acc += (l3 >= log_lo && l3 <= log_hi) ? dv.w : 0.f;
+      }
+    } else {
+      for (int e = threadIdx.x; e < E; e += blockDim.x) {
+        const float lp = z[e] - off;
+        acc += (lp >= log_lo && lp <= log_hi) ? ds[e] : 0.f;
+      }
+    }
+    acc = block_sum(acc, sm);
+    if (threadIdx.x == 0) racc[r] = acc;
+  }
+}
+
+int launch_ll_racc_log(const float *Z, const float *rmax, const float *lrsum, const float *DS, int B, int W, int E,
+                       int64_t ldz, int64_t lds, float *racc, cudaStream_t st) {
+  const long long rows = (long long)B * W;
+  if (rows == 0) return 0;
+  ll_racc_log_kernel<<<(int)std::min<long long>(rows, 148 * 64), 256, 0, st>>>(Z, rmax, lrsum, DS, rows, W, E, ldz, lds,
+                                                                               racc);
+  SERT_LAUNCH_CHECK();
+  return 0;
+}
+
+constexpr int kDzTile = 64;      // rows x columns of Z per CTA in pass B
+
+__device__ __forceinline__ unsigned short bf16_bits(float x) {
+  return __bfloat16_as_ushort(__float2bfloat16_rn(x));
+}
+
+// grid (ceil(E64 / 64), ceil(BW64 / 64)); dZs row stride 3*E64, dZT_s row stride 3*BW64 (elements)
+__global__ void __launch_bounds__(256) ll_dz_split_kernel(const float *__restrict__ Z, const float *__restrict__ rmax,
+                                                          const float *__restrict__ lrsum,
+                                                          const float *__restrict__ racc,
+                                                          const float *__restrict__ DS, long long rows, int W, int E,
+                                                          long long ldz, long long lds, long long E64, long long BW64,
+                                                          __nv_bfloat16 *__restrict__ dZs,
+                                                          __nv_bfloat16 *__restrict__ dZT_s) {
+  __shared__ unsigned short t_hi[kDzTile][kDzTile + 2], t_mid[kDzTile][kDzTile + 2];   // [column][row]
+  const float log_lo = logf(SERT_CLIP_LO), log_hi = logf(SERT_CLIP_HI);
+  const long long c0 = (long long)blockIdx.x * kDzTile, r0 = (long long)blockIdx.y * kDzTile;
+  const int tc = (threadIdx.x & 15) * 4;          // 16 threads x 4 columns per row
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const int tr = (threadIdx.x >> 4) + 16 * k;
+    const long long r = r0 + tr, c = c0 + tc;
+    float dz[4] = {0.f, 0.f, 0.f, 0.f};
+    if (r < rows && c < E) {
+      const float off = rmax[r] + lrsum[r], acc = racc[r];
+      const float *z = Z + r * ldz + c;
+      const float *ds = DS + (r / W) * lds + c;
+      float zv[4], dv[4];
+      if (c + 3 < E && (ldz & 3) == 0 && (lds & 3) == 0) {
+        const float4 a = __ldcs(reinterpret_cast<const float4 *>(z));
+        const float4 b = __ldg(reinterpret_cast<const float4 *>(ds));
+        zv[0] = a.x; zv[1] = a.y; zv[2] = a.z; zv[3] = a.w;
+        dv[0] = b.x; dv[1] = b.y; dv[2] = b.z; dv[3] = b.w;
+      } else {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          zv[j] = c + j < E ? z[j] : 0.f;
+          dv[j] = c + j < E ? ds[j] : 0.f;
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float lp = zv[j] - off;
+        const float pj = __expf(lp);
+        const float dpp = (lp >= log_lo && lp <= log_hi) ? dv[j] : 0.f;
+        dz[j] = c + j < E ? dpp - pj * acc : 0.f;
+      }
+    }
+    unsigned short hi[4], mid[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const __nv_bfloat16 h = __float2bfloat16_rn(dz[j]);
+      hi[j] = __bfloat16_as_ushort(h);
+      mid[j] = bf16_bits(dz[j] - __bfloat162float(h));
+      t_hi[tc + j][tr] = hi[j];
+      t_mid[tc + j][tr] = mid[j];
+    }
+    if (r < BW64 && c < E64) {
+      // A operand rows [hi | hi | mid]
+      const uint2 h2 = make_uint2((unsigned)hi[0] | ((unsigned)hi[1] << 16), (unsigned)hi[2] | ((unsigned)hi[3] << 16));
+      const uint2 m2 = make_uint2((unsigned)mid[0] | ((unsigned)mid[1] << 16), (unsigned)mid[2] | ((unsigned)mid[3] << 16));
+      __nv_bfloat16 *row = dZs + r * 3 * E64 + c;
+      if (r < rows) {
+        *reinterpret_cast<uint2 *>(row) = h2;
+        *reinterpret_cast<uint2 *>(row + E64) = h2;
+        *reinterpret_cast<uint2 *>(row + 2 * E64) = m2;
+      }
+    }
+  }
+  __syncthreads();
+  // B operand rows [hi | mid | hi] of the transpose: thread = (column, 16-row chunk)
+  const int col = threadIdx.x >> 2, rc = (threadIdx.x & 3) * 16;
+  const long long c = c0 + col;
+  if (c < E && r0 + rc < BW64) {
+    unsigned int hw[8], mw[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      hw[j] = (unsigned)t_hi[col][rc + 2 * j] | ((unsigned)t_hi[col][rc + 2 * j + 1] << 16);
+      mw[j] = (unsigned)t_mid[col][rc + 2 * j] | ((unsigned)t_mid[col][rc + 2 * j + 1] << 16);
+    }
+    __nv_bfloat16 *dst = dZT_s + c * 3 * BW64 + r0 + rc;
+    uint4 *d0 = reinterpret_cast<uint4 *>(dst), *d1 = reinterpret_cast<uint4 *>(dst + BW64),
+          *d2 = reinterpret_cast<uint4 *>(dst + 2 * BW64);
+    d0[0] = make_uint4(hw[0], hw[1], hw[2], hw[3]); d0[1] = make_uint4(hw[4], hw[5], hw[6], hw[7]);
+    d1[0] = make_uint4(mw[0], mw[1], mw[2], mw[3]); d1[1] = make_uint4(mw[4], mw[5], mw[6], mw[7]);
+    d2[0] = make_uint4(hw[0], hw[1], hw[2], hw[3]); d2[1] = make_uint4(hw[4], hw[5], hw[6], hw[7]);
+  }
+}
+
+int launch_ll_dz_split(const float *Z, const float *rmax, const float *lrsum, const float *racc, const float *DS,
+                       int B, int W, int E, int64_t ldz, int64_t lds, __nv_bfloat16 *dZs, __nv_bfloat16 *dZT_s,
+                       cudaStream_t st) {
+  const long long rows = (long long)B * W;
+  if (rows == 0) return 0;
+  const long long E64 = (long long)align_up((size_t)E, 64), BW64 = (long long)align_up((size_t)rows, 64);
+  dim3 grid((unsigned)(E64 / kDzTile), (unsigned)(BW64 / kDzTile));
+  SERT_REQUIRE(grid.y < 65536, "too many rows for the dZ tile grid");
+  ll_dz_split_kernel<<<grid, 256, 0, st>>>(Z, rmax, lrsum, racc, DS, rows, W, E, ldz, lds, E64, BW64, dZs, dZT_s);
   SERT_LAUNCH_CHECK();
   return 0;
 }

@@ -1,6 +1,8 @@
 // Launchers for the log-linear row kernels (see ll_kernels.cu).
 #pragma once
 
+#include <cuda_bf16.h>
+
 #include <algorithm>
 
 #include "common.cuh"
@@ -12,7 +14,7 @@ int launch_ll_row_stats(const float *Z, int64_t rows, int E, int64_t ldz, float 
 int launch_ll_softmax_inplace(float *Z, int64_t rows, int E, int64_t ldz, const float *rmax,
                               const float *rsum, cudaStream_t st);
 int launch_ll_joint(const float *Z, const float *rmax, const float *rsum, float *S, int B, int W, int E,
-                    int64_t ldz, int64_t lds, cudaStream_t st);
+                    int64_t ldz, int64_t lds, cudaStream_t st, float *lrsum_scratch);
 
 struct LlInstanceArgs {
   const float *S;          // (B,E) joint logits
@@ -35,6 +37,14 @@ int launch_ll_instance(const LlInstanceArgs &a, cudaStream_t st);
 // mode 0: both halves; 1: racc[r] = partial row sum only; 2: apply with racc[r] given (entity-sharded step).
 int launch_ll_dz(float *Z, const float *rmax, const float *rsum, const float *DS, int B, int W, int E,
                  int64_t ldz, int64_t lds, cudaStream_t st, int mode = 0, float *racc = nullptr);
+
+// ---- fused backward tail of the tensor-core path: acc_r in the log domain, then dZ straight into the split bf16
+// operands of the two gradient GEMMs (see ll_kernels.cu).  lrsum = log(rsum) (launch_ll_joint leaves it in its scratch).
+int launch_ll_racc_log(const float *Z, const float *rmax, const float *lrsum, const float *DS, int B, int W, int E,
+                       int64_t ldz, int64_t lds, float *racc, cudaStream_t st);
+int launch_ll_dz_split(const float *Z, const float *rmax, const float *lrsum, const float *racc, const float *DS,
+                       int B, int W, int E, int64_t ldz, int64_t lds, __nv_bfloat16 *dZs, __nv_bfloat16 *dZT_s,
+                       cudaStream_t st);
 
 // ---- entity-sharded softmax pieces (columns [e_begin, e_begin+E) of the entity axis live on this rank) ----
 // parts [shard][2][rows] of gathered (row max, row sum) -> global statistics

@@ -83,6 +83,7 @@ struct sert_model {
   float *dbg_scores = nullptr, *dbg_u = nullptr, *dbg_ell = nullptr;
   // log-linear workspaces
   float *X = nullptr, *Z = nullptr, *S = nullptr, *DS = nullptr, *dX = nullptr, *rmax = nullptr, *rsum = nullptr;
+  float *lrsum = nullptr;          // log of rsum (joint pass in the log domain)
   // bf16x3 split operands of the three word x entity GEMMs (tcgen05 path, csrc/gemm_tc.cu), all K-major:
   __nv_bfloat16 *Xs = nullptr;     // (B*W, 3*dw64)   A of  Z  = X . Wd
   __nv_bfloat16 *WdT_s = nullptr;  // (E,   3*dw64)   B of  Z  (transposed split of Wd (dw,E))
@@ -245,6 +246,7 @@ static size_t carve(sert_model &m, void *base) {
     m.dX = train ? b.take<float>(B * W * dw) : nullptr;
     m.rmax = b.take<float>(B * W);
     m.rsum = b.take<float>(B * W);
+    m.lrsum = b.take<float>(B * W);
     m.xstats = b.take<float>(kMaxShards * 2 * B * W);
     m.smax = b.take<float>(B);
     m.ssum = b.take<float>(B);
@@ -256,7 +258,7 @@ static size_t carve(sert_model &m, void *base) {
     if (train) {
       m.dZs = b.take<__nv_bfloat16>(B * W * 3 * E64);
       m.Wd_s = b.take<__nv_bfloat16>(dw * 3 * E64);
-      m.XT_s = b.take<__nv_bfloat16>(dw * 3 * BW64);
+      m.XT_s = b.take<__nv_bfloat16>((dw + 1) * 3 * BW64);    // + a row of ones: the bias gradient falls out of gWd's GEMM
       m.dZT_s = b.take<__nv_bfloat16>(E * 3 * BW64);
     }
     m.dbg_ell = b.take<float>(B);
@@ -502,6 +504,11 @@ static int vs_eval_step(sert_model &m, const int32_t *x, const int32_t *y, const
   return launch_finalize_eval(m.acc, loss_out, 1.0f / (float)c.batch, st);
 }
 
+__global__ void fill_bf16_kernel(__nv_bfloat16 *dst, long long n, float value) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) dst[i] = __float2bfloat16_rn(value);
+}
+
 // ---- log-linear ---------------------------------------------------------------------------------
 // The tcgen05 kernel works on 128 x 256 output tiles with one persistent CTA per SM: it is used when the
 // output has enough tiles to occupy the chip, the fp32 FMA tiles (with split-K) otherwise.
@@ -573,6 +580,33 @@ static int ll_backward_gemms(sert_model &m, int BW, int E, int dw, float *Wd, cu
   return 0;
 }
 
+// Both gradient GEMMs on tensor cores: dZ is written once, directly as their split bf16 operands (ll_kernels.cu).
+static bool ll_fused_tail(const sert_model &m, long long BW, long long E, long long dw) {
+  return ll_tensor(m, dw, E) && ll_tensor(m, BW, dw);
+}
+
+// racc (complete over all shards) -> dZs / dZT_s -> gWd (+ gbd through the ones row of X^T) and dX
+static int ll_backward_fused(sert_model &m, int B, int W, int E, int dw, float *Wd, cudaStream_t st) {
+  const int BW = B * W;
+  if (launch_ll_dz_split(m.Z, m.rmax, m.lrsum, m.racc, m.DS, B, W, E, E, E, m.dZs, m.dZT_s, st)) return -1;
+  {
+    const int kt = 3 * tc_padded_k(BW);
+    if (launch_split_bf16_t(m.X, BW, dw, dw, 3, SPLIT_A, m.XT_s, st)) return -1;
+    TcEpilogue ep;
+    ep.mode = TC_EPI_STORE; ep.C = m.grad + m.off[SERT_PARAM_DENSE_W]; ep.ldc = E;   // overwrites the (zeroed) grads
+    ep.extra_row = dw; ep.extra_dst = m.grad + m.off[SERT_PARAM_DENSE_B];
+    if (launch_gemm_tc(m.XT_s, dw + 1, m.dZT_s, E, 0, E, kt, ep, st)) return -1;
+  }
+  {
+    const int kt = 3 * tc_padded_k(E);
+    if (launch_split_bf16(Wd, dw, E, E, 3, SPLIT_B, m.Wd_s, st)) return -1;
+    TcEpilogue ep;
+    ep.mode = TC_EPI_STORE; ep.C = m.dX; ep.ldc = dw;
+    if (launch_gemm_tc(m.dZs, BW, m.Wd_s, dw, 0, dw, kt, ep, st)) return -1;
+  }
+  return 0;
+}
+
 static int ll_train_step(sert_model &m, const int32_t *x, const int64_t *indptr, long long nnz_base,
                          const int32_t *indices, const float *data, const float *w, float *loss_out) {
   const sert_config &c = m.cfg;
@@ -582,10 +616,15 @@ static int ll_train_step(sert_model &m, const int32_t *x, const int64_t *indptr,
   float *Wd = m.theta + m.off[SERT_PARAM_DENSE_W];
   m.stamp += 1;
   if (ll_forward(m, x, B, st)) return -1;
-  if (launch_ll_joint(m.Z, m.rmax, m.rsum, m.S, B, W, E, E, E, st)) return -1;
+  if (launch_ll_joint(m.Z, m.rmax, m.rsum, m.S, B, W, E, E, E, st, m.lrsum)) return -1;
   if (launch_ll_instance(ll_instance_args(m, indptr, nnz_base, indices, data, w, true, nullptr), st)) return -1;
-  if (launch_ll_dz(m.Z, m.rmax, m.rsum, m.DS, B, W, E, E, E, st)) return -1;
-  if (ll_backward_gemms(m, BW, E, dw, Wd, st)) return -1;
+  if (ll_fused_tail(m, BW, E, dw)) {
+    if (launch_ll_racc_log(m.Z, m.rmax, m.lrsum, m.DS, B, W, E, E, E, m.racc, st)) return -1;
+    if (ll_backward_fused(m, B, W, E, dw, Wd, st)) return -1;
+  } else {
+    if (launch_ll_dz(m.Z, m.rmax, m.rsum, m.DS, B, W, E, E, E, st)) return -1;
+    if (ll_backward_gemms(m, BW, E, dw, Wd, st)) return -1;
+  }
   if (launch_scatter_rows(x, m.dX, m.grad + m.off[SERT_PARAM_WORD_REPR], m.flagR, m.stamp, BW, 1, dw, 1.0f, st))
     return -1;
   m.step += 1;
@@ -600,7 +639,7 @@ static int ll_eval_step(sert_model &m, const int32_t *x, const int64_t *indptr, 
   cudaStream_t st = m.st;
   const int B = c.batch, W = c.window, E = (int)c.entities;
   if (ll_forward(m, x, B, st)) return -1;
-  if (launch_ll_joint(m.Z, m.rmax, m.rsum, m.S, B, W, E, E, E, st)) return -1;
+  if (launch_ll_joint(m.Z, m.rmax, m.rsum, m.S, B, W, E, E, E, st, m.lrsum)) return -1;
   if (launch_ll_instance(ll_instance_args(m, indptr, nnz_base, indices, data, nullptr, false,
                                           debug ? m.dbg_ell : nullptr), st))
     return -1;
@@ -640,7 +679,7 @@ static int ll_shard_forward(sert_model &m, const int32_t *x, const int64_t *indp
   float *mine = ll_my_stats(m, BW);
   if (ll_forward(m, x, B, m.st, mine, mine + BW)) return -1;      // local columns of Z and their statistics
   if (ll_shard_combine(m, BW, m.rmax, m.rsum)) return -1;
-  if (launch_ll_joint(m.Z, m.rmax, m.rsum, m.S, B, W, E, E, E, m.st)) return -1;
+  if (launch_ll_joint(m.Z, m.rmax, m.rsum, m.S, B, W, E, E, E, m.st, m.lrsum)) return -1;
   mine = ll_my_stats(m, B);
   if (launch_ll_row_stats(m.S, B, E, E, mine, mine + B, m.st)) return -1;
   if (ll_shard_combine(m, B, m.smax, m.ssum)) return -1;
@@ -660,10 +699,16 @@ static int ll_train_step_sharded(sert_model &m, const int32_t *x, const int64_t 
   if (xchg(m, SERT_XCHG_ALLREDUCE_SUM, m.adot, (size_t)B)) return -1;
   LlInstanceArgs a = ll_instance_args(m, indptr, nnz_base, indices, data, w, true, nullptr);
   if (launch_ll_shard_ds(a, m.smax, m.ssum, (int)m.e_begin, m.adot, st)) return -1;
-  if (launch_ll_dz(m.Z, m.rmax, m.rsum, m.DS, B, W, E, E, E, st, 1, m.racc)) return -1;
-  if (xchg(m, SERT_XCHG_ALLREDUCE_SUM, m.racc, (size_t)BW)) return -1;
-  if (launch_ll_dz(m.Z, m.rmax, m.rsum, m.DS, B, W, E, E, E, st, 2, m.racc)) return -1;
-  if (ll_backward_gemms(m, BW, E, dw, Wd, st)) return -1;
+  if (ll_fused_tail(m, BW, E, dw)) {
+    if (launch_ll_racc_log(m.Z, m.rmax, m.lrsum, m.DS, B, W, E, E, E, m.racc, st)) return -1;
+    if (xchg(m, SERT_XCHG_ALLREDUCE_SUM, m.racc, (size_t)BW)) return -1;
+    if (ll_backward_fused(m, B, W, E, dw, Wd, st)) return -1;
+  } else {
+    if (launch_ll_dz(m.Z, m.rmax, m.rsum, m.DS, B, W, E, E, E, st, 1, m.racc)) return -1;
+    if (xchg(m, SERT_XCHG_ALLREDUCE_SUM, m.racc, (size_t)BW)) return -1;
+    if (launch_ll_dz(m.Z, m.rmax, m.rsum, m.DS, B, W, E, E, E, st, 2, m.racc)) return -1;
+    if (ll_backward_gemms(m, BW, E, dw, Wd, st)) return -1;
+  }
   if (xchg(m, SERT_XCHG_ALLREDUCE_SUM, m.dX, (size_t)BW * dw)) return -1;
   if (launch_scatter_rows(x, m.dX, m.grad + m.off[SERT_PARAM_WORD_REPR], m.flagR, m.stamp, BW, 1, dw, 1.0f, st))
     return -1;
@@ -740,6 +785,14 @@ int sert_model_create(const sert_config *cfg, void *arena_dev, size_t arena_byte
     delete m;
     set_error(std::string("cudaMemsetAsync: ") + cudaGetErrorString(e));
     return -1;
+  }
+  if (!is_vs(*cfg) && m->XT_s != nullptr) {
+    // the row of ones behind X^T (split [hi | hi | mid] = [1 | 1 | 0] over the B*W real rows): see ll_backward_fused
+    const long long BW = (long long)cfg->batch * cfg->window, BW64 = tc_padded_k((int)BW);
+    __nv_bfloat16 *row = m->XT_s + (size_t)cfg->word_dim * 3 * BW64;
+    fill_bf16_kernel<<<cdiv(BW, 256), 256, 0, m->st>>>(row, BW, 1.0f);
+    fill_bf16_kernel<<<cdiv(BW, 256), 256, 0, m->st>>>(row + BW64, BW, 1.0f);
+    count_launch(2);
   }
   if (is_vs(*cfg)) {
     int least = 0, greatest = 0;

@@ -125,6 +125,8 @@ def test_predict_fn_matches_oracle_and_pickles():
     (dict(V=3000, E=300, dw=64, W=10, B=512), 1),      # Z and dX on tcgen05 (40 tiles each), dWd on FMA tiles
     (dict(V=2000, E=4096, dw=256, W=4, B=64), 1),      # Z and dWd on tcgen05 (32 tiles each), dX on FMA tiles
     (dict(V=3000, E=300, dw=64, W=10, B=512), 0),      # same shapes, tensor cores off
+    (dict(V=3000, E=8200, dw=64, W=8, B=512), 1),      # all three on tcgen05: fused backward tail (dZ written once, as
+                                                       # the split operands; bias gradient through the ones row)
 ])
 def test_tensor_core_projection_matches_oracle(dims, tensor):
     """The word x entity GEMMs through the tcgen05 bf16x3 path: logits within 1e-4 relative, 3 Adadelta steps."""
@@ -166,3 +168,18 @@ def test_empty_validation_set_and_tail_drop():
     assert n == 2 and np.isfinite(loss)          # 2*16+5 instances -> 2 batches, 5 dropped
     with pytest.raises(RuntimeError, match='out of range'):
         model.train_fn(2)
+
+
+@pytest.mark.parametrize('gain', [25.0, 60.0])
+def test_fused_backward_tail_in_the_clipped_regime(gain):
+    """All three word x entity GEMMs on tensor cores with logits driven into the clips (log-domain clip masks of
+    ll_joint / ll_racc_log / ll_dz_split against the oracle's p-domain clips)."""
+    p = H.ll_problem(43, n_batches=2, gain=gain, V=1500, E=8192, dw=64, W=8, B=512)
+    model = make_model(p, 0.01)
+    oracle = H.ll_oracle(p, 0.01)
+    for j in range(2):
+        H.close(model.train_fn(j), oracle.train_batch(j), what='train loss step %d' % j)
+    Wd, bd = model.get_dense()
+    H.close(model.get_representations(), oracle.R, rtol=2e-4, what='R')
+    H.close(Wd, oracle.Wd, rtol=2e-4, what='Wd')
+    H.close(bd, oracle.bd, rtol=2e-4, atol_scale=1e-4, what='bd')
