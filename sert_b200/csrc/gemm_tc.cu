@@ -46,6 +46,8 @@ struct KernelArgs {
   int M;
   long long n_begin, n_end;
   int num_kb;          // Kt / 64
+  int k_slices;        // split-K: the K blocks are cut into this many slices, each a tile of its own (TC_EPI_STORE
+                       // with epi.accumulate: partial sums meet in C through float4 reductions)
   TcEpilogue epi;
 };
 
@@ -58,7 +60,9 @@ struct KernelArgs {
 // same moment queue up on the slices that hold its lines (measured: 10.3 k cycles per tile unstaggered).
 // seq = position inside the n-tile's sweep (0 = first, num_m_tiles - 1 = last).
 template <bool BSTAT>
-__device__ __forceinline__ bool cta_tile(int it, int num_m_tiles, int num_n_tiles, int &mt, int &nt, int &seq) {
+__device__ __forceinline__ bool cta_tile(int it, int num_m_tiles, int num_n_tiles, int k_slices, int &mt, int &nt,
+                                         int &seq, int &slice) {
+  slice = 0;
   if (BSTAT) {
     nt = blockIdx.x + (it / num_m_tiles) * gridDim.x;
     seq = it % num_m_tiles;
@@ -68,8 +72,16 @@ __device__ __forceinline__ bool cta_tile(int it, int num_m_tiles, int num_n_tile
   seq = 0;
   const long long t = blockIdx.x + (long long)it * gridDim.x;
   mt = (int)(t % num_m_tiles);
-  nt = (int)(t / num_m_tiles);
-  return t < (long long)num_m_tiles * num_n_tiles;
+  const long long rest = t / num_m_tiles;
+  nt = (int)(rest % num_n_tiles);
+  slice = (int)(rest / num_n_tiles);
+  return slice < k_slices;
+}
+// K blocks [kb0, kb0 + n) of slice `slice` (the last slice takes the remainder)
+__device__ __forceinline__ void slice_range(int num_kb, int k_slices, int slice, int &kb0, int &n) {
+  const int per = (num_kb + k_slices - 1) / k_slices;
+  kb0 = slice * per;
+  n = min(per, num_kb - kb0);
 }
 
 // ---- PTX wrappers -----------------------------------------------------------------------------
@@ -214,10 +226,12 @@ gemm_tc_kernel(const __grid_constant__ TcMap map_a, const __grid_constant__ TcMa
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0, bphase = 0;
-      int mt, nt, seq;
-      for (int it = 0; cta_tile<BSTAT>(it, num_m_tiles, num_n_tiles, mt, nt, seq); ++it) {
+      int mt, nt, seq, slice;
+      for (int it = 0; cta_tile<BSTAT>(it, num_m_tiles, num_n_tiles, args.k_slices, mt, nt, seq, slice); ++it) {
         const int m0 = mt * BM;
         const int n0 = (int)(args.n_begin + (long long)nt * BN * args.epi.tile_stride);
+        int kb0, nkb;
+        slice_range(args.num_kb, args.k_slices, slice, kb0, nkb);
         if (BSTAT && seq == 0) {
           mbar_wait(bempty_bar, bphase ^ 1u);            // the previous n-tile's MMAs no longer read the B slots
           mbar_expect_tx(bfull_bar, (uint32_t)args.num_kb * B_STAGE_BYTES);
@@ -225,7 +239,7 @@ gemm_tc_kernel(const __grid_constant__ TcMap map_a, const __grid_constant__ TcMa
             tma_load_2d(smem_b + kb * B_STAGE_BYTES, &map_b, bfull_bar, kb * BK, n0);
           bphase ^= 1u;
         }
-        for (int kb = 0; kb < args.num_kb; ++kb) {
+        for (int kb = kb0; kb < kb0 + nkb; ++kb) {
           mbar_wait(empty_bar(stage), phase ^ 1u);
           mbar_expect_tx(full_bar(stage), BSTAT ? A_STAGE_BYTES : STAGE_BYTES);
           tma_load_2d(smem_a + stage * A_STAGE_BYTES, &map_a, full_bar(stage), kb * BK, m0);
@@ -242,8 +256,10 @@ gemm_tc_kernel(const __grid_constant__ TcMap map_a, const __grid_constant__ TcMa
       uint32_t phase = 0;
       int acc = 0;
       uint32_t acc_phase = 0, bphase = 0;
-      int mt, nt, seq;
-      for (int it = 0; cta_tile<BSTAT>(it, num_m_tiles, num_n_tiles, mt, nt, seq); ++it) {
+      int mt, nt, seq, slice;
+      for (int it = 0; cta_tile<BSTAT>(it, num_m_tiles, num_n_tiles, args.k_slices, mt, nt, seq, slice); ++it) {
+        int kb0, nkb;
+        slice_range(args.num_kb, args.k_slices, slice, kb0, nkb);
         if (BSTAT && seq == 0) {
           mbar_wait(bfull_bar, bphase);                  // this n-tile's B blocks have landed
           bphase ^= 1u;
@@ -251,7 +267,7 @@ gemm_tc_kernel(const __grid_constant__ TcMap map_a, const __grid_constant__ TcMa
         mbar_wait(tempty_bar(acc), acc_phase ^ 1u);      // epilogue has drained this accumulator
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + (uint32_t)acc * BN;
-        for (int kb = 0; kb < args.num_kb; ++kb) {
+        for (int kb = 0; kb < nkb; ++kb) {
           mbar_wait(full_bar(stage), phase);             // TMA bytes have landed
           tc_fence_after();
           const uint32_t a_addr = smem_a + stage * A_STAGE_BYTES;
@@ -310,8 +326,8 @@ gemm_tc_kernel(const __grid_constant__ TcMap map_a, const __grid_constant__ TcMa
       }
       pend_wtotal = 0;
     };
-    int mt, nt, seq;
-    for (int it = 0; cta_tile<BSTAT>(it, num_m_tiles, num_n_tiles, mt, nt, seq); ++it) {
+    int mt, nt, seq, slice;
+    for (int it = 0; cta_tile<BSTAT>(it, num_m_tiles, num_n_tiles, args.k_slices, mt, nt, seq, slice); ++it) {
       const int m0 = mt * BM;
       const long long n0 = args.n_begin + (long long)nt * BN * args.epi.tile_stride;
       const int gm = m0 + row;
@@ -327,6 +343,7 @@ gemm_tc_kernel(const __grid_constant__ TcMap map_a, const __grid_constant__ TcMa
       tc_fence_after();
       const uint32_t t_row = tmem_base + (uint32_t)acc * BN + ((uint32_t)(quarter * 32) << 16);
       if (ep.mode == TC_EPI_STORE) {
+        float st_max = -INFINITY, st_sum = 0.f;             // running softmax statistics of this lane's 64 columns
 #pragma unroll 1
         for (int c0 = col_lo; c0 < col_lo + COLS_PER_WARP; c0 += 32) {
           uint32_t v[32];
@@ -334,32 +351,57 @@ gemm_tc_kernel(const __grid_constant__ TcMap map_a, const __grid_constant__ TcMa
           tc_wait_ld();
           const long long gn0 = n0 + c0;
           if (row_ok && gn0 < args.n_end) {
+            const int nv = (int)(args.n_end - gn0 < 32 ? args.n_end - gn0 : 32);
+            float w[32];
+#pragma unroll
+            for (int j = 0; j < 32; ++j) w[j] = __uint_as_float(v[j]);
+            if (ep.bias != nullptr) {
+              if (nv == 32 && (reinterpret_cast<uintptr_t>(ep.bias + gn0) & 15) == 0) {
+#pragma unroll
+                for (int j = 0; j < 32; j += 4) {              // broadcast 16-byte loads: every lane adds the same bias
+                  const float4 bv = __ldg(reinterpret_cast<const float4 *>(ep.bias + gn0 + j));
+                  w[j] += bv.x; w[j + 1] += bv.y; w[j + 2] += bv.z; w[j + 3] += bv.w;
+                }
+              } else {
+#pragma unroll
+                for (int j = 0; j < 32; ++j)
+                  if (j < nv) w[j] += __ldg(ep.bias + gn0 + j);
+              }
+            }
+            if (ep.row_stats != nullptr) {
+              float mx = -INFINITY;
+#pragma unroll
+              for (int j = 0; j < 32; ++j)
+                if (j < nv) mx = fmaxf(mx, w[j]);
+              const float m_new = fmaxf(st_max, mx);
+              float add = 0.f;
+#pragma unroll
+              for (int j = 0; j < 32; ++j)
+                if (j < nv) add += __expf(w[j] - m_new);
+              st_sum = st_sum * __expf(st_max - m_new) + add;
+              st_max = m_new;
+            }
             float *dst = gm == ep.extra_row ? ep.extra_dst + gn0 : ep.C + (long long)gm * ep.ldc + gn0;
-            const bool full = (gn0 + 32 <= args.n_end) && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0);
-            if (full) {
+            if (nv == 32 && (reinterpret_cast<uintptr_t>(dst) & 15) == 0) {
 #pragma unroll
               for (int j = 0; j < 32; j += 4) {
-                float4 o = make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]), __uint_as_float(v[j + 2]),
-                                       __uint_as_float(v[j + 3]));
-                if (ep.bias != nullptr) {
-                  if ((reinterpret_cast<uintptr_t>(ep.bias + gn0) & 15) == 0) {        // one broadcast 16-byte load
-                    const float4 bv = __ldg(reinterpret_cast<const float4 *>(ep.bias + gn0 + j));
-                    o.x += bv.x; o.y += bv.y; o.z += bv.z; o.w += bv.w;
-                  } else {
-                    o.x += ep.bias[gn0 + j]; o.y += ep.bias[gn0 + j + 1];
-                    o.z += ep.bias[gn0 + j + 2]; o.w += ep.bias[gn0 + j + 3];
-                  }
-                }
-                *reinterpret_cast<float4 *>(dst + j) = o;
+                const float4 o = make_float4(w[j], w[j + 1], w[j + 2], w[j + 3]);
+                if (ep.accumulate) red_add_f4(dst + j, o);
+                else *reinterpret_cast<float4 *>(dst + j) = o;
               }
             } else {
 #pragma unroll
               for (int j = 0; j < 32; ++j)
-                if (gn0 + j < args.n_end)
-                  dst[j] = __uint_as_float(v[j]) + (ep.bias != nullptr ? ep.bias[gn0 + j] : 0.f);
+                if (j < nv) {
+                  if (ep.accumulate) atomicAdd(dst + j, w[j]);
+                  else dst[j] = w[j];
+                }
             }
           }
         }
+        if (ep.row_stats != nullptr && row_ok && n0 + col_lo < args.n_end)
+          ep.row_stats[(size_t)gm * ep.stats_ld + (size_t)((n0 - args.n_begin) + col_lo) / COLS_PER_WARP] =
+              make_float2(st_max, st_sum);
       } else if (ep.mode == TC_EPI_GROUPMAX) {
         // ---- maxima over groups of 8 or 64 columns (full tiles only): the sample the scoring sweep seeds its
         // thresholds from (score.cu: seed_tau_kernel)
@@ -607,6 +649,7 @@ int launch_gemm_tc_ld(const __nv_bfloat16 *A, long long lda, int M, const __nv_b
   args.n_begin = n_begin;
   args.n_end = n_end;
   args.num_kb = Kt / BK;
+  args.k_slices = 1;
   args.epi = epi;
   const long long m_tiles = (M + BM - 1) / BM, n_tiles = (n_end - n_begin + BN - 1) / BN;
   const long long tiles = m_tiles * n_tiles;
@@ -622,7 +665,17 @@ int launch_gemm_tc_ld(const __nv_bfloat16 *A, long long lda, int M, const __nv_b
     SERT_LAUNCH_CHECK();
     return 0;
   }
-  const int grid = (int)std::min<long long>(tiles, sms);
+  long long work = tiles;
+  if (epi.mode == TC_EPI_STORE && epi.accumulate && epi.bias == nullptr) {
+    // split-K: few output tiles and a very deep K (dX = dZ . Wd^T of the log-linear model: 160 tiles, K = 600 k) leave
+    // the chip in two unequal waves; slices of the K range become tiles of their own and meet in C by reduction
+    int slices = 1;
+    while (tiles * slices < 4ll * sms && args.num_kb / (slices * 2) >= 32) slices *= 2;
+    const int per = (args.num_kb + slices - 1) / slices;
+    args.k_slices = (args.num_kb + per - 1) / per;       // no empty slice
+    work = tiles * args.k_slices;
+  }
+  const int grid = (int)std::min<long long>(work, sms);
   gemm_tc_kernel<false><<<grid, NUM_THREADS, SMEM_BYTES, st>>>(ma, mb, args);
   SERT_LAUNCH_CHECK();
   return 0;

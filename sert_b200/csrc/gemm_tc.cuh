@@ -25,6 +25,15 @@ struct TcEpilogue {
   // the GEMM's last output row into the column sums of B^T -- the bias gradient of the log-linear layer for free)
   int extra_row = -1;
   float *extra_dst = nullptr;
+  // TC_EPI_STORE: C += acc (float4 reductions) instead of C = acc; the launcher may then split a deep K range into
+  // slices that are scheduled as independent tiles.  C must hold the initial value (zeros) before the launch.
+  int accumulate = 0;
+  // TC_EPI_STORE, optional: softmax statistics of the stored values (after the bias), per row and per 64-column
+  // slice -- row_stats[m * stats_ld + slot] = (max, sum of exp(v - max)) with slot = (n - n_begin) / 64 -- so that the
+  // row-softmax of the log-linear logits needs no pass of its own over the (B*W, E) matrix
+  // (launch_ll_combine_slices folds the slices).  Slots of a row that lie beyond n_end are not written.
+  float2 *row_stats = nullptr;
+  int stats_ld = 0;
   // TC_EPI_TOPK: rows are queries, columns are entity rows [n_begin, n_end) of B
   const unsigned long long *tau = nullptr;
   int *count = nullptr;

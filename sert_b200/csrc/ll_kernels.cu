@@ -53,6 +53,34 @@ __global__ void __launch_bounds__(256) ll_row_stats_kernel(const float *__restri
   }
 }
 
+// folds the per-slice (max, sum exp) pairs the GEMM epilogue left (gemm_tc.cuh: row_stats), one warp per row
+__global__ void __launch_bounds__(256) ll_combine_slices_kernel(const float2 *__restrict__ stats, long long rows,
+                                                                int slots, long long ld, float *__restrict__ rmax,
+                                                                float *__restrict__ rsum) {
+  const long long r = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (r >= rows) return;
+  const float2 *row = stats + r * ld;
+  float m = -INFINITY;
+  for (int i = lane; i < slots; i += 32) m = fmaxf(m, row[i].x);
+  m = warp_max(m);
+  float s = 0.f;
+  for (int i = lane; i < slots; i += 32) {
+    const float2 v = row[i];
+    s += v.y * expf(v.x - m);
+  }
+  s = warp_sum(s);
+  if (lane == 0) { rmax[r] = m; rsum[r] = s; }
+}
+
+int launch_ll_combine_slices(const float2 *stats, int64_t rows, int slots, int64_t ld, float *rmax, float *rsum,
+                             cudaStream_t st) {
+  if (rows == 0) return 0;
+  ll_combine_slices_kernel<<<cdiv(rows, 8), 256, 0, st>>>(stats, rows, slots, ld, rmax, rsum);
+  SERT_LAUNCH_CHECK();
+  return 0;
+}
+
 int launch_ll_row_stats(const float *Z, int64_t rows, int E, int64_t ldz, float *rmax, float *rsum,
                         cudaStream_t st) {
   if (rows == 0) return 0;

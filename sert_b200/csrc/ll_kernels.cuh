@@ -38,6 +38,10 @@ int launch_ll_instance(const LlInstanceArgs &a, cudaStream_t st);
 int launch_ll_dz(float *Z, const float *rmax, const float *rsum, const float *DS, int B, int W, int E,
                  int64_t ldz, int64_t lds, cudaStream_t st, int mode = 0, float *racc = nullptr);
 
+// (rows, slots) pairs of (max, sum exp(v - max)) over 64-column slices -> per-row softmax statistics
+int launch_ll_combine_slices(const float2 *stats, int64_t rows, int slots, int64_t ld, float *rmax, float *rsum,
+                             cudaStream_t st);
+
 // ---- fused backward tail of the tensor-core path: acc_r in the log domain, then dZ straight into the split bf16
 // operands of the two gradient GEMMs (see ll_kernels.cu).  lrsum = log(rsum) (launch_ll_joint leaves it in its scratch).
 int launch_ll_racc_log(const float *Z, const float *rmax, const float *lrsum, const float *DS, int B, int W, int E,

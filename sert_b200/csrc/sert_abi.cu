@@ -84,6 +84,7 @@ struct sert_model {
   // log-linear workspaces
   float *X = nullptr, *Z = nullptr, *S = nullptr, *DS = nullptr, *dX = nullptr, *rmax = nullptr, *rsum = nullptr;
   float *lrsum = nullptr;          // log of rsum (joint pass in the log domain)
+  float2 *zstats = nullptr;        // (B*W, ceil(E/64)) per-slice softmax statistics from the GEMM epilogue
   // bf16x3 split operands of the three word x entity GEMMs (tcgen05 path, csrc/gemm_tc.cu), all K-major:
   __nv_bfloat16 *Xs = nullptr;     // (B*W, 3*dw64)   A of  Z  = X . Wd
   __nv_bfloat16 *WdT_s = nullptr;  // (E,   3*dw64)   B of  Z  (transposed split of Wd (dw,E))
@@ -247,6 +248,7 @@ static size_t carve(sert_model &m, void *base) {
     m.rmax = b.take<float>(B * W);
     m.rsum = b.take<float>(B * W);
     m.lrsum = b.take<float>(B * W);
+    m.zstats = b.take<float2>(B * W * ((E + 63) / 64));
     m.xstats = b.take<float>(kMaxShards * 2 * B * W);
     m.smax = b.take<float>(B);
     m.ssum = b.take<float>(B);
@@ -532,7 +534,12 @@ static int ll_forward(sert_model &m, const int32_t *x, int rows /* instances */,
     if (launch_split_bf16_t(Wd, dw, E, E, 3, SPLIT_B, m.WdT_s, st)) return -1;
     TcEpilogue ep;
     ep.mode = TC_EPI_STORE; ep.C = m.Z; ep.ldc = E; ep.bias = bd;
+    // the epilogue leaves per-slice softmax statistics: no pass over Z for the row maxima and sums
+    const int slots = cdiv(E, 64);
+    ep.row_stats = m.zstats; ep.stats_ld = slots;
     if (launch_gemm_tc(m.Xs, (int)BW, m.WdT_s, E, 0, E, kt, ep, st)) return -1;
+    return launch_ll_combine_slices(m.zstats, BW, slots, slots, rmax_out ? rmax_out : m.rmax,
+                                    rsum_out ? rsum_out : m.rsum, st);
   } else {
     if (launch_gemm_f32(m.X, Wd, m.Z, (int)BW, E, dw, false, false, dw, E, E, EPI_BIAS, bd, 1, st)) return -1;
   }
@@ -602,6 +609,8 @@ static int ll_backward_fused(sert_model &m, int B, int W, int E, int dw, float *
     if (launch_split_bf16(Wd, dw, E, E, 3, SPLIT_B, m.Wd_s, st)) return -1;
     TcEpilogue ep;
     ep.mode = TC_EPI_STORE; ep.C = m.dX; ep.ldc = dw;
+    ep.accumulate = 1;                                  // split-K over the entity axis (K = 3 E64)
+    SERT_CUDA(cudaMemsetAsync(m.dX, 0, (size_t)BW * dw * sizeof(float), st));
     if (launch_gemm_tc(m.dZs, BW, m.Wd_s, dw, 0, dw, kt, ep, st)) return -1;
   }
   return 0;
