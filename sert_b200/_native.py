@@ -10,7 +10,8 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, 'libsert_b200.so')
+# SERT_B200_LIB: another build of the same library (A/B measurements of two kernel variants in one GPU session)
+LIB_PATH = os.environ.get('SERT_B200_LIB') or os.path.join(_HERE, 'libsert_b200.so')
 
 KIND_LOGLINEAR, KIND_VECTORSPACE = 0, 1
 SPLIT_TRAIN, SPLIT_VALIDATE = 0, 1

@@ -154,6 +154,12 @@ __device__ __forceinline__ void tc_ld_32x32(uint32_t taddr, uint32_t (&r)[32]) {
       : "r"(taddr)
       : "memory");
 }
+__device__ __forceinline__ void tc_ld_32x8(uint32_t taddr, uint32_t (&r)[8]) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+               : "r"(taddr)
+               : "memory");
+}
 __device__ __forceinline__ void tc_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 // Shared-memory matrix descriptor of a K-major bf16 tile stored as rows of 64 elements (128 bytes) with the
@@ -175,7 +181,9 @@ constexpr uint32_t make_idesc(int m, int n) {
 }
 
 // ---- the kernel -----------------------------------------------------------------------------------
-template <bool BSTAT>
+// MODE = the epilogue (TcEpilogueMode): one kernel per epilogue keeps each kernel's code small enough for the
+// instruction caches (the epilogues are long unrolled register code; a warp only ever runs one of them).
+template <bool BSTAT, int MODE>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ TcMap map_a, const __grid_constant__ TcMap map_b, const KernelArgs args) {
   extern __shared__ unsigned char smem_raw[];
@@ -335,14 +343,14 @@ gemm_tc_kernel(const __grid_constant__ TcMap map_a, const __grid_constant__ TcMa
       // Rows are swept in increasing id order and tau only moves between launches, so a later row that
       // ties tau's score has a larger id (= a smaller key): `score > tau_score` is the exact key test.
       float tau_score = INFINITY;
-      if (ep.mode == TC_EPI_TOPK && row_ok) {
+      if (MODE == TC_EPI_TOPK && row_ok) {
         const unsigned long long tau_key = ep.tau[gm];
         tau_score = tau_key == 0ull ? -INFINITY : key_score(tau_key);
       }
       mbar_wait(tfull_bar(acc), acc_phase);
       tc_fence_after();
       const uint32_t t_row = tmem_base + (uint32_t)acc * BN + ((uint32_t)(quarter * 32) << 16);
-      if (ep.mode == TC_EPI_STORE) {
+      if (MODE == TC_EPI_STORE) {
         float st_max = -INFINITY, st_sum = 0.f;             // running softmax statistics of this lane's 64 columns
 #pragma unroll 1
         for (int c0 = col_lo; c0 < col_lo + COLS_PER_WARP; c0 += 32) {
@@ -402,7 +410,7 @@ gemm_tc_kernel(const __grid_constant__ TcMap map_a, const __grid_constant__ TcMa
         if (ep.row_stats != nullptr && row_ok && n0 + col_lo < args.n_end)
           ep.row_stats[(size_t)gm * ep.stats_ld + (size_t)((n0 - args.n_begin) + col_lo) / COLS_PER_WARP] =
               make_float2(st_max, st_sum);
-      } else if (ep.mode == TC_EPI_GROUPMAX) {
+      } else if (MODE == TC_EPI_GROUPMAX) {
         // ---- maxima over groups of 8 or 64 columns (full tiles only): the sample the scoring sweep seeds its
         // thresholds from (score.cu: seed_tau_kernel)
         float mx = -INFINITY;
@@ -434,90 +442,91 @@ gemm_tc_kernel(const __grid_constant__ TcMap map_a, const __grid_constant__ TcMa
         if (ep.group == COLS_PER_WARP && row_ok)
           ep.gmax[(size_t)gm * ep.gmax_ld + (size_t)nt * (BN / COLS_PER_WARP) + col_lo / COLS_PER_WARP] = mx;
       } else {
-        // ---- running top-k filter.  The chunk loop stays rolled: the epilogue's code must stay resident in the
-        // instruction caches (a fully unrolled two-pass version measured 6x slower: the warps sat in "no
-        // instruction" stalls).  One read of the accumulator; per 32-column chunk a max tree (31 FMNMX) decides
-        // whether ANY of the warp's 32 rows has a survivor (one ballot); only then the four 8-column quarters that
-        // hold one are scanned, column by column with a ballot each, and the survivors are compacted into the warp's
-        // shared-memory stash.  Cost follows the number of survivors: ~40 instructions for a chunk without one.
-        // (Round 1 parked keys per LANE, 4 slots each: a row with a fifth survivor in 64 columns sent the whole warp
-        // to the two-pass path -- a quarter of the tiles at 500 survivors per query and 50 k rows -- and every lane
-        // with a hit ran the full 32-column scan.)
+        // ---- running top-k filter.  The accumulator is read ONCE, eight columns at a time (tcgen05.ld x8, the next
+        // group in flight while the current one is examined), in a ROLLED loop: the epilogue's code must stay in the
+        // instruction caches -- a fully unrolled two-pass version measured 6x slower ("no instruction" stalls), and the
+        // 32-column form of this pass, with its four quarter bodies unrolled, still spent a quarter of its issue
+        // slots there (profiles/ncu_gemm_tc_r2c_*).  Per group: a max tree and ONE ballot decide whether any of the
+        // warp's 32 rows has a survivor (usually not); if so every lane counts its survivors and remembers the last
+        // one's column; when no row has two (a row's survivor then IS its group maximum) they are compacted into the
+        // warp's shared-memory stash with one more ballot, else the group is scanned column by column.
         int total = 0;                                                   // this lane's survivors in the tile
         int wcount = 0;                                                  // the warp's (uniform)
-        uint32_t chunk_any = 0;                                          // warp-uniform: chunks with a survivor
+        uint32_t group_any = 0;                                          // warp-uniform: 8-column groups with a survivor
         const uint32_t my_keys = stash_keys(stash_buf), my_meta = stash_meta(stash_buf);
-#pragma unroll 1
-        for (int ci = 0; ci < CHUNKS; ++ci) {
-          uint32_t v[32];
-          tc_ld_32x32(t_row + (uint32_t)(col_lo + ci * 32), v);
-          tc_wait_ld();
-          // valid columns in this chunk: fewer than 32 only in the shard's last tile.  Columns beyond hold zeros (TMA
-          // fills out-of-bounds rows); they are excluded where survivors are picked, not by rewriting v[] -- the
-          // compiler turns such a fix-up into 64 compare/select pairs on every chunk.
-          const long long left = args.n_end - (n0 + col_lo + ci * 32);
-          const bool partial = left < 32;                                       // warp-uniform
-          float m4[4];
+        const unsigned int col_base = (unsigned int)(n0 + col_lo + ep.row_offset);
+        const long long left_all = args.n_end - (n0 + col_lo);           // valid columns of this warp's slice
+        auto examine = [&](const uint32_t (&v)[8], int g) {
+          const float mA = fmaxf(fmaxf(__uint_as_float(v[0]), __uint_as_float(v[1])),
+                                 fmaxf(__uint_as_float(v[2]), __uint_as_float(v[3])));
+          const float mB = fmaxf(fmaxf(__uint_as_float(v[4]), __uint_as_float(v[5])),
+                                 fmaxf(__uint_as_float(v[6]), __uint_as_float(v[7])));
+          const float mx = fmaxf(mA, mB);
+          if (__ballot_sync(0xffffffffu, mx > tau_score) == 0u) return;          // nothing here (the common case)
+          const int left = (int)(left_all - g * 8 < 8 ? left_all - g * 8 : 8);   // < 8 only in the shard's last tile
+          int cnt = 0, idx = 0;
 #pragma unroll
-          for (int qd = 0; qd < 4; ++qd) {
-            const float a = fmaxf(fmaxf(__uint_as_float(v[8 * qd]), __uint_as_float(v[8 * qd + 1])),
-                                  fmaxf(__uint_as_float(v[8 * qd + 2]), __uint_as_float(v[8 * qd + 3])));
-            const float b = fmaxf(fmaxf(__uint_as_float(v[8 * qd + 4]), __uint_as_float(v[8 * qd + 5])),
-                                  fmaxf(__uint_as_float(v[8 * qd + 6]), __uint_as_float(v[8 * qd + 7])));
-            m4[qd] = fmaxf(a, b);
+          for (int j = 0; j < 8; ++j) {
+            const bool hit = __uint_as_float(v[j]) > tau_score && j < left;
+            cnt += hit ? 1 : 0;
+            idx = hit ? j : idx;
           }
-          const float mx = fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3]));
-          if (__ballot_sync(0xffffffffu, mx > tau_score) == 0u) continue;        // nothing in this chunk (common)
-          chunk_any |= 1u << ci;
-          const unsigned int col_base = (unsigned int)(n0 + col_lo + ci * 32 + ep.row_offset);
-#pragma unroll
-          for (int qd = 0; qd < 4; ++qd) {
-            if (__ballot_sync(0xffffffffu, m4[qd] > tau_score) == 0u) continue;
-            // survivors of this lane among the quarter's 8 columns, and the column of the last one
-            int cnt = 0, idx = 0;
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              const bool hit = __uint_as_float(v[8 * qd + j]) > tau_score;
-              cnt += hit ? 1 : 0;
-              idx = hit ? j : idx;
-            }
-            const uint32_t h1 = __ballot_sync(0xffffffffu, cnt >= 1);
-            if (!partial && __ballot_sync(0xffffffffu, cnt >= 2) == 0u) {
-              // common case: no row has two survivors in these 8 columns, so a row's survivor IS its quarter maximum
-              if (cnt != 0) {
-                const int slot = wcount + __popc(h1 & lane_lt);
-                if (slot < WSTASH) {
-                  const unsigned long long key = make_key(m4[qd], col_base + (unsigned int)(8 * qd + idx));
-                  asm volatile("st.shared.b64 [%0], %1;" ::"r"(my_keys + (uint32_t)slot * 8u), "l"(key) : "memory");
-                  asm volatile("st.shared.u16 [%0], %1;" ::"r"(my_meta + (uint32_t)slot * 2u),
-                               "h"((unsigned short)((lane << 11) | (total & 0x7ff)))
-                               : "memory");
-                }
-                ++total;
+          const uint32_t h1 = __ballot_sync(0xffffffffu, cnt >= 1);
+          if (h1 == 0u) return;                                                  // only padding columns beat tau
+          group_any |= 1u << g;
+          if (left == 8 && __ballot_sync(0xffffffffu, cnt >= 2) == 0u) {
+            if (cnt != 0) {
+              const int slot = wcount + __popc(h1 & lane_lt);
+              if (slot < WSTASH) {
+                const unsigned long long key = make_key(mx, col_base + (unsigned int)(g * 8 + idx));
+                asm volatile("st.shared.b64 [%0], %1;" ::"r"(my_keys + (uint32_t)slot * 8u), "l"(key) : "memory");
+                asm volatile("st.shared.u16 [%0], %1;" ::"r"(my_meta + (uint32_t)slot * 2u),
+                             "h"((unsigned short)((lane << 11) | (total & 0x7ff)))
+                             : "memory");
               }
-              wcount += __popc(h1);
-              continue;
+              ++total;
             }
+            wcount += __popc(h1);
+            return;
+          }
 #pragma unroll
-            for (int j = 8 * qd; j < 8 * qd + 8; ++j) {
-              const bool hit = __uint_as_float(v[j]) > tau_score && j < left;
-              const uint32_t hm = __ballot_sync(0xffffffffu, hit);
-              if (hm == 0u) continue;
-              if (hit) {
-                const int slot = wcount + __popc(hm & lane_lt);
-                if (slot < WSTASH) {
-                  const unsigned long long key = make_key(__uint_as_float(v[j]), col_base + (unsigned int)j);
-                  asm volatile("st.shared.b64 [%0], %1;" ::"r"(my_keys + (uint32_t)slot * 8u), "l"(key) : "memory");
-                  asm volatile("st.shared.u16 [%0], %1;" ::"r"(my_meta + (uint32_t)slot * 2u),
-                               "h"((unsigned short)((lane << 11) | (total & 0x7ff)))
-                               : "memory");
-                }
-                ++total;
+          for (int j = 0; j < 8; ++j) {
+            const bool hit = __uint_as_float(v[j]) > tau_score && j < left;
+            const uint32_t hm = __ballot_sync(0xffffffffu, hit);
+            if (hm == 0u) continue;
+            if (hit) {
+              const int slot = wcount + __popc(hm & lane_lt);
+              if (slot < WSTASH) {
+                const unsigned long long key = make_key(__uint_as_float(v[j]), col_base + (unsigned int)(g * 8 + j));
+                asm volatile("st.shared.b64 [%0], %1;" ::"r"(my_keys + (uint32_t)slot * 8u), "l"(key) : "memory");
+                asm volatile("st.shared.u16 [%0], %1;" ::"r"(my_meta + (uint32_t)slot * 2u),
+                             "h"((unsigned short)((lane << 11) | (total & 0x7ff)))
+                             : "memory");
               }
-              wcount += __popc(hm);
+              ++total;
             }
+            wcount += __popc(hm);
+          }
+        };
+        {
+          constexpr int GROUPS = COLS_PER_WARP / 8;
+          static_assert(GROUPS % 2 == 0, "the group loop is unrolled by two");
+          const uint32_t tbase = t_row + (uint32_t)col_lo;
+          uint32_t va[8], vb[8];
+          tc_ld_32x8(tbase, va);
+#pragma unroll 1
+          for (int g = 0; g < GROUPS; g += 2) {
+            tc_wait_ld();
+            tc_ld_32x8(tbase + (uint32_t)(g + 1) * 8u, vb);
+            examine(va, g);
+            tc_wait_ld();
+            if (g + 2 < GROUPS) tc_ld_32x8(tbase + (uint32_t)(g + 2) * 8u, va);
+            examine(vb, g + 1);
           }
         }
+        uint32_t chunk_any = 0;                                          // 32-column chunks with a survivor (two-pass path)
+#pragma unroll
+        for (int ci = 0; ci < CHUNKS; ++ci) chunk_any |= ((group_any >> (4 * ci)) & 0xfu) ? (1u << ci) : 0u;
         if (wcount <= WSTASH) {
           // Everything this warp keeps sits in shared memory: hand the accumulator back to the MMA warp, copy out
           // the previous tile's keys (their slots were reserved a tile ago), reserve this tile's slots.
@@ -638,8 +647,10 @@ int launch_gemm_tc_ld(const __nv_bfloat16 *A, long long lda, int M, const __nv_b
   if (make_map(B, N_total, Kt, ldb, BN, &mb)) return -1;
   static std::atomic<uint64_t> configured{0};
   if (first_use_on_device(configured)) {
-    SERT_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
-    SERT_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
+    SERT_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<false, TC_EPI_STORE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
+    SERT_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<false, TC_EPI_TOPK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
+    SERT_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<false, TC_EPI_GROUPMAX>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
+    SERT_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<true, TC_EPI_TOPK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
   }
   int dev = 0, sms = kNumSMs;
   SERT_CUDA(cudaGetDevice(&dev));
@@ -660,8 +671,8 @@ int launch_gemm_tc_ld(const __nv_bfloat16 *A, long long lda, int M, const __nv_b
   const long long per_cta = (n_tiles + sms - 1) / sms;
   const bool bstat = args.num_kb <= STAGES && m_tiles >= 8 && n_tiles >= sms &&
                      per_cta * sms * 10 <= n_tiles * 12 && getenv("SERT_GEMM_BSTAT") != nullptr;
-  if (bstat) {
-    gemm_tc_kernel<true><<<(int)std::min<long long>(n_tiles, sms), NUM_THREADS, SMEM_BYTES, st>>>(ma, mb, args);
+  if (bstat && epi.mode == TC_EPI_TOPK) {
+    gemm_tc_kernel<true, TC_EPI_TOPK><<<(int)std::min<long long>(n_tiles, sms), NUM_THREADS, SMEM_BYTES, st>>>(ma, mb, args);
     SERT_LAUNCH_CHECK();
     return 0;
   }
@@ -676,7 +687,9 @@ int launch_gemm_tc_ld(const __nv_bfloat16 *A, long long lda, int M, const __nv_b
     work = tiles * args.k_slices;
   }
   const int grid = (int)std::min<long long>(work, sms);
-  gemm_tc_kernel<false><<<grid, NUM_THREADS, SMEM_BYTES, st>>>(ma, mb, args);
+  if (epi.mode == TC_EPI_TOPK) gemm_tc_kernel<false, TC_EPI_TOPK><<<grid, NUM_THREADS, SMEM_BYTES, st>>>(ma, mb, args);
+  else if (epi.mode == TC_EPI_GROUPMAX) gemm_tc_kernel<false, TC_EPI_GROUPMAX><<<grid, NUM_THREADS, SMEM_BYTES, st>>>(ma, mb, args);
+  else gemm_tc_kernel<false, TC_EPI_STORE><<<grid, NUM_THREADS, SMEM_BYTES, st>>>(ma, mb, args);
   SERT_LAUNCH_CHECK();
   return 0;
 }
