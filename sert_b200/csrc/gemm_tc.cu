@@ -33,6 +33,11 @@ constexpr uint32_t TMEM_COLS = 512;
 // top-k epilogue: survivors of one tile that a WARP parks in shared memory (keys compacted across its 32 rows with
 // ballots; 8-byte key + 2-byte (owner lane, ordinal within the owner's row)), two buffers: this tile's and the
 // previous one's, whose list slots are being reserved
+#ifndef SERT_TC_GROUP
+#define SERT_TC_GROUP 16
+#endif
+constexpr int GW = SERT_TC_GROUP;         // columns of the accumulator the top-k epilogue examines at a time (8 or 16)
+static_assert(GW == 8 || GW == 16, "tcgen05.ld x8 / x16");
 constexpr int WSTASH = 96;
 constexpr uint32_t STASH_KEYS_BYTES = 2 * EPI_WARPS * WSTASH * 8;
 constexpr uint32_t STASH_BYTES = STASH_KEYS_BYTES + 2 * EPI_WARPS * WSTASH * 2;
@@ -60,8 +65,8 @@ struct KernelArgs {
 // same moment queue up on the slices that hold its lines (measured: 10.3 k cycles per tile unstaggered).
 // seq = position inside the n-tile's sweep (0 = first, num_m_tiles - 1 = last).
 template <bool BSTAT>
-__device__ __forceinline__ bool cta_tile(int it, int num_m_tiles, int num_n_tiles, int k_slices, int &mt, int &nt,
-                                         int &seq, int &slice) {
+__device__ __forceinline__ bool cta_tile(int it, int num_m_tiles, int num_n_tiles, int k_slices, int step_m, int step_n,
+                                         int &mt, int &nt, int &seq, int &slice) {
   slice = 0;
   if (BSTAT) {
     nt = blockIdx.x + (it / num_m_tiles) * gridDim.x;
@@ -70,13 +75,23 @@ __device__ __forceinline__ bool cta_tile(int it, int num_m_tiles, int num_n_tile
     return nt < num_n_tiles;
   }
   seq = 0;
-  const long long t = blockIdx.x + (long long)it * gridDim.x;
-  mt = (int)(t % num_m_tiles);
-  const long long rest = t / num_m_tiles;
-  nt = (int)(rest % num_n_tiles);
-  slice = (int)(rest / num_n_tiles);
+  // Incremental: every warp of the CTA walks its tiles with this function, and two 64-bit divisions per tile
+  // (~150 instructions) were a fifth of an epilogue warp's work on a tile without survivors.  `mt` and `nt` carry
+  // the previous tile's coordinates (nt counts n-tiles across all K slices); a step adds gridDim.x tiles.
+  if (it == 0) {
+    mt = (int)(blockIdx.x % (unsigned)num_m_tiles);
+    nt = (int)(blockIdx.x / (unsigned)num_m_tiles);
+  } else {
+    mt += step_m;
+    nt += step_n;
+    if (mt >= num_m_tiles) { mt -= num_m_tiles; ++nt; }
+  }
+  if (k_slices == 1) return nt < num_n_tiles;
+  slice = nt / num_n_tiles;
   return slice < k_slices;
 }
+// the n-tile inside its K slice (cta_tile leaves the running count over all slices in `nt`)
+__device__ __forceinline__ int slice_nt(int nt, int num_n_tiles, int slice) { return nt - slice * num_n_tiles; }
 // K blocks [kb0, kb0 + n) of slice `slice` (the last slice takes the remainder)
 __device__ __forceinline__ void slice_range(int num_kb, int k_slices, int slice, int &kb0, int &n) {
   const int per = (num_kb + k_slices - 1) / k_slices;
@@ -160,6 +175,20 @@ __device__ __forceinline__ void tc_ld_32x8(uint32_t taddr, uint32_t (&r)[8]) {
                : "r"(taddr)
                : "memory");
 }
+__device__ __forceinline__ void tc_ld_32x16(uint32_t taddr, uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr)
+      : "memory");
+}
+template <int N>
+__device__ __forceinline__ void tc_ld_group(uint32_t taddr, uint32_t (&r)[N]) {
+  if constexpr (N == 8) tc_ld_32x8(taddr, r);
+  else tc_ld_32x16(taddr, r);
+}
 __device__ __forceinline__ void tc_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 // Shared-memory matrix descriptor of a K-major bf16 tile stored as rows of 64 elements (128 bytes) with the
@@ -206,6 +235,7 @@ gemm_tc_kernel(const __grid_constant__ TcMap map_a, const __grid_constant__ TcMa
 
   const int num_m_tiles = (args.M + BM - 1) / BM;
   const int num_n_tiles = (int)((args.n_end - args.n_begin + BN - 1) / BN);
+  const int step_m = (int)(gridDim.x % (unsigned)num_m_tiles), step_n = (int)(gridDim.x / (unsigned)num_m_tiles);
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&map_a);
@@ -235,9 +265,9 @@ gemm_tc_kernel(const __grid_constant__ TcMap map_a, const __grid_constant__ TcMa
       int stage = 0;
       uint32_t phase = 0, bphase = 0;
       int mt, nt, seq, slice;
-      for (int it = 0; cta_tile<BSTAT>(it, num_m_tiles, num_n_tiles, args.k_slices, mt, nt, seq, slice); ++it) {
+      for (int it = 0; cta_tile<BSTAT>(it, num_m_tiles, num_n_tiles, args.k_slices, step_m, step_n, mt, nt, seq, slice); ++it) {
         const int m0 = mt * BM;
-        const int n0 = (int)(args.n_begin + (long long)nt * BN * args.epi.tile_stride);
+        const int n0 = (int)(args.n_begin + (long long)slice_nt(nt, num_n_tiles, slice) * BN * args.epi.tile_stride);
         int kb0, nkb;
         slice_range(args.num_kb, args.k_slices, slice, kb0, nkb);
         if (BSTAT && seq == 0) {
@@ -265,7 +295,7 @@ gemm_tc_kernel(const __grid_constant__ TcMap map_a, const __grid_constant__ TcMa
       int acc = 0;
       uint32_t acc_phase = 0, bphase = 0;
       int mt, nt, seq, slice;
-      for (int it = 0; cta_tile<BSTAT>(it, num_m_tiles, num_n_tiles, args.k_slices, mt, nt, seq, slice); ++it) {
+      for (int it = 0; cta_tile<BSTAT>(it, num_m_tiles, num_n_tiles, args.k_slices, step_m, step_n, mt, nt, seq, slice); ++it) {
         int kb0, nkb;
         slice_range(args.num_kb, args.k_slices, slice, kb0, nkb);
         if (BSTAT && seq == 0) {
@@ -335,9 +365,10 @@ gemm_tc_kernel(const __grid_constant__ TcMap map_a, const __grid_constant__ TcMa
       pend_wtotal = 0;
     };
     int mt, nt, seq, slice;
-    for (int it = 0; cta_tile<BSTAT>(it, num_m_tiles, num_n_tiles, args.k_slices, mt, nt, seq, slice); ++it) {
+    for (int it = 0; cta_tile<BSTAT>(it, num_m_tiles, num_n_tiles, args.k_slices, step_m, step_n, mt, nt, seq, slice); ++it) {
       const int m0 = mt * BM;
-      const long long n0 = args.n_begin + (long long)nt * BN * args.epi.tile_stride;
+      const int nt_in = slice_nt(nt, num_n_tiles, slice);
+      const long long n0 = args.n_begin + (long long)nt_in * BN * args.epi.tile_stride;
       const int gm = m0 + row;
       const bool row_ok = gm < args.M;
       // Rows are swept in increasing id order and tau only moves between launches, so a later row that
@@ -428,7 +459,7 @@ gemm_tc_kernel(const __grid_constant__ TcMap map_a, const __grid_constant__ TcMa
                                   fmaxf(__uint_as_float(v[8 * j + 6]), __uint_as_float(v[8 * j + 7])));
             m4[j] = fmaxf(a, b);
           }
-          float *dst = ep.gmax + (size_t)gm * ep.gmax_ld + (size_t)nt * (BN / ep.group) + (col_lo + ci * 32) / ep.group;
+          float *dst = ep.gmax + (size_t)gm * ep.gmax_ld + (size_t)nt_in * (BN / ep.group) + (col_lo + ci * 32) / ep.group;
           if (ep.group == 8) {
             if (row_ok) *reinterpret_cast<float4 *>(dst) = make_float4(m4[0], m4[1], m4[2], m4[3]);
           } else if (ep.group == 16) {
@@ -440,7 +471,7 @@ gemm_tc_kernel(const __grid_constant__ TcMap map_a, const __grid_constant__ TcMa
           }
         }
         if (ep.group == COLS_PER_WARP && row_ok)
-          ep.gmax[(size_t)gm * ep.gmax_ld + (size_t)nt * (BN / COLS_PER_WARP) + col_lo / COLS_PER_WARP] = mx;
+          ep.gmax[(size_t)gm * ep.gmax_ld + (size_t)nt_in * (BN / COLS_PER_WARP) + col_lo / COLS_PER_WARP] = mx;
       } else {
         // ---- running top-k filter.  The accumulator is read ONCE, eight columns at a time (tcgen05.ld x8, the next
         // group in flight while the current one is examined), in a ROLLED loop: the epilogue's code must stay in the
@@ -456,17 +487,15 @@ gemm_tc_kernel(const __grid_constant__ TcMap map_a, const __grid_constant__ TcMa
         const uint32_t my_keys = stash_keys(stash_buf), my_meta = stash_meta(stash_buf);
         const unsigned int col_base = (unsigned int)(n0 + col_lo + ep.row_offset);
         const long long left_all = args.n_end - (n0 + col_lo);           // valid columns of this warp's slice
-        auto examine = [&](const uint32_t (&v)[8], int g) {
-          const float mA = fmaxf(fmaxf(__uint_as_float(v[0]), __uint_as_float(v[1])),
-                                 fmaxf(__uint_as_float(v[2]), __uint_as_float(v[3])));
-          const float mB = fmaxf(fmaxf(__uint_as_float(v[4]), __uint_as_float(v[5])),
-                                 fmaxf(__uint_as_float(v[6]), __uint_as_float(v[7])));
-          const float mx = fmaxf(mA, mB);
+        auto examine = [&](const uint32_t (&v)[GW], int g) {
+          float mx = __uint_as_float(v[0]);
+#pragma unroll
+          for (int j = 1; j < GW; ++j) mx = fmaxf(mx, __uint_as_float(v[j]));
           if (__ballot_sync(0xffffffffu, mx > tau_score) == 0u) return;          // nothing here (the common case)
-          const int left = (int)(left_all - g * 8 < 8 ? left_all - g * 8 : 8);   // < 8 only in the shard's last tile
+          const int left = (int)(left_all - g * GW < GW ? left_all - g * GW : GW);   // < GW only in the shard's last tile
           int cnt = 0, idx = 0;
 #pragma unroll
-          for (int j = 0; j < 8; ++j) {
+          for (int j = 0; j < GW; ++j) {
             const bool hit = __uint_as_float(v[j]) > tau_score && j < left;
             cnt += hit ? 1 : 0;
             idx = hit ? j : idx;
@@ -474,11 +503,11 @@ gemm_tc_kernel(const __grid_constant__ TcMap map_a, const __grid_constant__ TcMa
           const uint32_t h1 = __ballot_sync(0xffffffffu, cnt >= 1);
           if (h1 == 0u) return;                                                  // only padding columns beat tau
           group_any |= 1u << g;
-          if (left == 8 && __ballot_sync(0xffffffffu, cnt >= 2) == 0u) {
+          if (left == GW && __ballot_sync(0xffffffffu, cnt >= 2) == 0u) {
             if (cnt != 0) {
               const int slot = wcount + __popc(h1 & lane_lt);
               if (slot < WSTASH) {
-                const unsigned long long key = make_key(mx, col_base + (unsigned int)(g * 8 + idx));
+                const unsigned long long key = make_key(mx, col_base + (unsigned int)(g * GW + idx));
                 asm volatile("st.shared.b64 [%0], %1;" ::"r"(my_keys + (uint32_t)slot * 8u), "l"(key) : "memory");
                 asm volatile("st.shared.u16 [%0], %1;" ::"r"(my_meta + (uint32_t)slot * 2u),
                              "h"((unsigned short)((lane << 11) | (total & 0x7ff)))
@@ -490,14 +519,14 @@ gemm_tc_kernel(const __grid_constant__ TcMap map_a, const __grid_constant__ TcMa
             return;
           }
 #pragma unroll
-          for (int j = 0; j < 8; ++j) {
+          for (int j = 0; j < GW; ++j) {
             const bool hit = __uint_as_float(v[j]) > tau_score && j < left;
             const uint32_t hm = __ballot_sync(0xffffffffu, hit);
             if (hm == 0u) continue;
             if (hit) {
               const int slot = wcount + __popc(hm & lane_lt);
               if (slot < WSTASH) {
-                const unsigned long long key = make_key(__uint_as_float(v[j]), col_base + (unsigned int)(g * 8 + j));
+                const unsigned long long key = make_key(__uint_as_float(v[j]), col_base + (unsigned int)(g * GW + j));
                 asm volatile("st.shared.b64 [%0], %1;" ::"r"(my_keys + (uint32_t)slot * 8u), "l"(key) : "memory");
                 asm volatile("st.shared.u16 [%0], %1;" ::"r"(my_meta + (uint32_t)slot * 2u),
                              "h"((unsigned short)((lane << 11) | (total & 0x7ff)))
@@ -509,24 +538,25 @@ gemm_tc_kernel(const __grid_constant__ TcMap map_a, const __grid_constant__ TcMa
           }
         };
         {
-          constexpr int GROUPS = COLS_PER_WARP / 8;
+          constexpr int GROUPS = COLS_PER_WARP / GW;
           static_assert(GROUPS % 2 == 0, "the group loop is unrolled by two");
           const uint32_t tbase = t_row + (uint32_t)col_lo;
-          uint32_t va[8], vb[8];
-          tc_ld_32x8(tbase, va);
+          uint32_t va[GW], vb[GW];
+          tc_ld_group<GW>(tbase, va);
 #pragma unroll 1
           for (int g = 0; g < GROUPS; g += 2) {
             tc_wait_ld();
-            tc_ld_32x8(tbase + (uint32_t)(g + 1) * 8u, vb);
+            tc_ld_group<GW>(tbase + (uint32_t)((g + 1) * GW), vb);
             examine(va, g);
             tc_wait_ld();
-            if (g + 2 < GROUPS) tc_ld_32x8(tbase + (uint32_t)(g + 2) * 8u, va);
+            if (g + 2 < GROUPS) tc_ld_group<GW>(tbase + (uint32_t)((g + 2) * GW), va);
             examine(vb, g + 1);
           }
         }
         uint32_t chunk_any = 0;                                          // 32-column chunks with a survivor (two-pass path)
 #pragma unroll
-        for (int ci = 0; ci < CHUNKS; ++ci) chunk_any |= ((group_any >> (4 * ci)) & 0xfu) ? (1u << ci) : 0u;
+        for (int ci = 0; ci < CHUNKS; ++ci)
+          chunk_any |= ((group_any >> ((32 / GW) * ci)) & ((1u << (32 / GW)) - 1u)) ? (1u << ci) : 0u;
         if (wcount <= WSTASH) {
           // Everything this warp keeps sits in shared memory: hand the accumulator back to the MMA warp, copy out
           // the previous tile's keys (their slots were reserved a tile ago), reserve this tile's slots.
