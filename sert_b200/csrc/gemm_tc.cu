@@ -69,9 +69,13 @@ __device__ __forceinline__ bool cta_tile(int it, int num_m_tiles, int num_n_tile
                                          int &mt, int &nt, int &seq, int &slice) {
   slice = 0;
   if (BSTAT) {
-    nt = blockIdx.x + (it / num_m_tiles) * gridDim.x;
-    seq = it % num_m_tiles;
-    mt = (seq + blockIdx.x) % num_m_tiles;
+    if (it == 0) {
+      nt = blockIdx.x; seq = 0;
+      mt = (int)(blockIdx.x % (unsigned)num_m_tiles);
+    } else {
+      if (++seq == num_m_tiles) { seq = 0; nt += gridDim.x; }
+      if (++mt == num_m_tiles) mt = 0;
+    }
     return nt < num_n_tiles;
   }
   seq = 0;
@@ -694,13 +698,15 @@ int launch_gemm_tc_ld(const __nv_bfloat16 *A, long long lda, int M, const __nv_b
   args.epi = epi;
   const long long m_tiles = (M + BM - 1) / BM, n_tiles = (n_end - n_begin + BN - 1) / BN;
   const long long tiles = m_tiles * n_tiles;
-  // B-stationary schedule (opt-in, SERT_GEMM_BSTAT=1): K fits the ring's B slots, every CTA gets an n-tile, enough
-  // m-tiles to amortise the load of B (one bubble per n-tile), and whole n-tiles balance at least as well as single
-  // tiles would.  Measured at BASELINE configs[3] it is 2-3 % SLOWER than the classic order (8.86 vs 8.62 ms): the
-  // top-k epilogue, not L2, paces the K = 256 tiles (ncu: tensor pipe 37 % active, L2 11 %), so it stays off.
+  // B-stationary schedule (top-k epilogue; SERT_GEMM_BSTAT=0 turns it off): K fits the ring's B slots, every CTA gets
+  // an n-tile, enough m-tiles to amortise the load of B (one bubble per n-tile), and whole n-tiles balance at least as
+  // well as single tiles would.  It cuts the operand traffic of a tile from 192 KB to 64 KB at K = 256.  Round 1
+  // measured it 2-3 % SLOWER (8.86 vs 8.62 ms at BASELINE configs[3]) because the top-k epilogue paced the tiles;
+  // with the round-2 epilogue it is 4 % faster (4.60 vs 4.79 ms, same box, same run), so it is on by default.
   const long long per_cta = (n_tiles + sms - 1) / sms;
+  const char *bstat_env = getenv("SERT_GEMM_BSTAT");
   const bool bstat = args.num_kb <= STAGES && m_tiles >= 8 && n_tiles >= sms &&
-                     per_cta * sms * 10 <= n_tiles * 12 && getenv("SERT_GEMM_BSTAT") != nullptr;
+                     per_cta * sms * 10 <= n_tiles * 12 && !(bstat_env != nullptr && bstat_env[0] == '0');
   if (bstat && epi.mode == TC_EPI_TOPK) {
     gemm_tc_kernel<true, TC_EPI_TOPK><<<(int)std::min<long long>(n_tiles, sms), NUM_THREADS, SMEM_BYTES, st>>>(ma, mb, args);
     SERT_LAUNCH_CHECK();
