@@ -367,6 +367,7 @@ def run_ours(args, rank, world, local_rank):
     scoring_small = leg(run_scoring, CFG3, 'BASELINE.json configs[2]', rank, world, barrier, cpu=(rank == 0))
 
     loglinear = leg(run_loglinear_cfg1, rank) if rank == 0 else None
+    product_search = leg(run_product_search_shape, rank) if rank == 0 else None
     loglinear_stress = None if os.environ.get('SERT_BENCH_SKIP_CFG5') else leg(run_loglinear_cfg5, rank, world, barrier)
 
     if rank == 0:
@@ -407,6 +408,7 @@ def run_ours(args, rank, world, local_rank):
             'scoring_small_lists_identical': (scoring_small or {}).get('lists_identical'),
             'loglinear_stress_ms': (loglinear_stress or {}).get('ms_per_step'),
             'bf16_state_mode': bf16_mode,
+            'product_search_shape': product_search,
             'loglinear': loglinear,
             'loglinear_stress': loglinear_stress,
             'scoring': scoring,
@@ -486,6 +488,50 @@ def run_bf16_state_mode(p, cfg, steps, warm, repeats, f32_first_losses, f32_last
             'deviation_what': 'max relative difference of the per-batch training losses against the float32 run of '
                               'the identical step sequence (first pass / last timed pass)',
             'arena_mb': arena_mb}
+
+
+def run_product_search_shape(rank, steps=200):
+    """The reference's canonical LSE recipe (product-search.sh:102-147): window 4, B = 4096, d_w = 300, d_e = 128, k = 10,
+    on the synthetic vocabulary / entity counts of configs[1].  One GPU, device-resident batches."""
+    import torch
+    from sert_b200 import _native as N, models, synth
+    cfg = dict(V=100000, E=50000, dw=300, de=128, W=4, B=4096, k=10, lam=0.01)
+    nb = 30
+    seed = 20160816 + 7
+    rng = np.random.default_rng(seed)
+    train, val = synth.vectorspace_corpus(seed, cfg['V'], cfg['E'], cfg['W'], cfg['B'] * nb, cfg['B'])
+    model = models.VectorSpaceLanguageModel(
+        batch_size=cfg['B'], window_size=cfg['W'], num_negative_samples=cfg['k'],
+        representations_init=synth.glorot(rng, (cfg['V'], cfg['dw'])),
+        entity_representations_init=synth.glorot(rng, (cfg['E'], cfg['de'])), regularization_lambda=cfg['lam'],
+        training_set=train, validation_set=val, loss_slots=1024)
+    nat, lib = model._native, model._native.lib
+    neg_dev = torch.from_numpy(rng.integers(0, cfg['E'], size=(nb, cfg['B'], cfg['k'])).astype(np.int32)).cuda()
+    order = np.arange(nb, dtype=np.int64)
+    run = lambda: N.check(lib.sert_train_batches(nat.handle, N.host_ptr(order), nb, N.c_void_p(neg_dev.data_ptr()), 0))
+    run()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    reps = max(1, steps // nb)
+    e0.record()
+    for _ in range(reps):
+        run()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / (reps * nb)
+    losses = np.empty(nb, np.float32)
+    N.check(lib.sert_losses_fetch(nat.handle, 0, nb, N.host_ptr(losses)))
+    P = cfg['V'] * cfg['dw'] + cfg['E'] * cfg['de'] + cfg['dw'] * cfg['de'] + cfg['de']
+    step_bytes = 24 * P + 2 * cfg['B'] * cfg['W'] * cfg['dw'] * 4 + 2 * cfg['B'] * (1 + cfg['k']) * cfg['de'] * 4
+    peak, _ = measured_peaks()
+    nat.close()
+    del model
+    torch.cuda.empty_cache()
+    return {'workload': 'product-search.sh recipe: VectorSpaceLanguageModel V=100k E=50k d_w=300 d_e=128 window=4 B=4096 '
+                        'k=10 lambda=0.01 (Adam + dense L2, float32)',
+            'value': cfg['B'] / (ms * 1e-3), 'unit': UNIT, 'ms_per_step': ms,
+            'step_algorithmic_bytes': step_bytes, 'step_frac_of_hbm_peak': step_bytes / (ms * 1e-3) / 1e9 / peak,
+            'final_loss': float(losses[-1])}
 
 
 def scoring_shard(sc, world, rank):

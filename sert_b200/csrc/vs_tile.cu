@@ -1,5 +1,6 @@
-// Vector-space training step, forward + backward, ONE CTA PER TILE OF 8 INSTANCES, d_w = d_e = 128
-// (BASELINE configs[1]; sert/models.py:1044-1098).  Same stages and arithmetic as csrc/vs_warp.cu, re-cut around
+// Vector-space training step, forward + backward, ONE CTA PER TILE OF 8 INSTANCES, d_e = 128 and d_w a multiple of 4 up to
+// 384 in NW = ceil(d_w / 128) chunks of 128 floats per lane (BASELINE configs[1]: 128 / 128, NW = 1;
+// product-search.sh:102-147: 300 / 128, NW = 3; sert/models.py:1044-1098).  Same stages and arithmetic as csrc/vs_warp.cu, re-cut around
 // what the profiles of that kernel and of the earlier versions of this one showed (profiles/ncu_vs_tile_r1*.txt,
 // tools/red_probe.cu):
 //   * warp g owns instance g for the gather, the loss and the two scatters (one 512-byte row per request);
@@ -29,9 +30,10 @@ namespace {
 
 constexpr int kT = 8;                 // instances per CTA == warps per CTA
 constexpr int kThreads = kT * 32;
-constexpr int kD = 128;               // word and entity representation size served by this kernel
+constexpr int kD = 128;               // entity representation size served by this kernel; also the column block of the products
 constexpr int kD4 = kD / 4;
-constexpr int kLd = kD + 4;           // padded staging rows
+constexpr int kLd = kD + 4;           // padded staging rows (entity-sized vectors)
+constexpr int kMaxNW = 3;             // word rows of up to 3 x 128 floats
 constexpr int kMaxRows = 16;          // 1 + k scores per instance handled by the butterfly
 constexpr int kMaxWindow = 32;
 constexpr int kRowsPerWarp = kD / kT; // matrix rows per warp in the K-split products
@@ -51,29 +53,56 @@ __device__ __forceinline__ void cp_async_16(void *smem_dst, const void *gmem_src
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 __device__ __forceinline__ void prefetch_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 
-// Row `warp` of  vec (8 x 128, shared, row stride kLd) . M (128 x 128, global, row-major), columns 4*lane..4*lane+3.
-// Every thread of the CTA must call.  `part` (kPartFloats floats of shared memory) is scratch; the barrier at the
-// start also publishes `vec`, the one at the end releases `part` for other uses.
-__device__ __forceinline__ float4 tile_matvec(const float *__restrict__ vec, float *part,
-                                              const float *__restrict__ M, int warp, int lane) {
+// Row `warp` of  vec (8 x K, shared, row stride ldv) . M[:, c0 .. c0 + 128) (K x ldm4*4, global, row-major), columns
+// c0 + 4*lane .. + 3; only the first ncol4 float4 columns of the block exist (lanes beyond return zeros).  K is split
+// over the 8 warps, rows_per_warp rows each (a multiple of 4; rows >= K are skipped).  Every thread of the CTA must
+// call.  `part` (kPartFloats floats of shared memory) is scratch; the barrier at the start also publishes `vec`, the
+// one at the end releases `part` for other uses.
+// SQUARE: the 128 x 128 case of BASELINE configs[1] (K = 128, 16 rows per warp, full columns) with every bound a
+// compile-time constant, as measured in round 1; the general form guards rows and columns.
+template <bool SQUARE>
+__device__ __forceinline__ float4 tile_matvec(const float *__restrict__ vec, int ldv, float *part,
+                                              const float *__restrict__ M, int K, int rows_per_warp, int ldm4, int c0_4,
+                                              int ncol4, int warp, int lane) {
   float4 acc[kT];
 #pragma unroll
   for (int g = 0; g < kT; ++g) acc[g] = f4_zero();
-  const float4 *m = reinterpret_cast<const float4 *>(M) + (size_t)warp * kRowsPerWarp * kD4 + lane;
-  __syncthreads();
+  if (SQUARE) {
+    const float4 *m = reinterpret_cast<const float4 *>(M) + (size_t)warp * kRowsPerWarp * kD4 + lane;
+    __syncthreads();
 #pragma unroll
-  for (int q = 0; q < kRowsPerWarp; q += 4) {
-    const float4 r0 = __ldg(m + (q + 0) * kD4);
-    const float4 r1 = __ldg(m + (q + 1) * kD4);
-    const float4 r2 = __ldg(m + (q + 2) * kD4);
-    const float4 r3 = __ldg(m + (q + 3) * kD4);
+    for (int q = 0; q < kRowsPerWarp; q += 4) {
+      const float4 r0 = __ldg(m + (q + 0) * kD4);
+      const float4 r1 = __ldg(m + (q + 1) * kD4);
+      const float4 r2 = __ldg(m + (q + 2) * kD4);
+      const float4 r3 = __ldg(m + (q + 3) * kD4);
 #pragma unroll
-    for (int g = 0; g < kT; ++g) {
-      const float4 s = *reinterpret_cast<const float4 *>(vec + g * kLd + warp * kRowsPerWarp + q);   // broadcast
-      f4_fma(acc[g], s.x, r0);
-      f4_fma(acc[g], s.y, r1);
-      f4_fma(acc[g], s.z, r2);
-      f4_fma(acc[g], s.w, r3);
+      for (int g = 0; g < kT; ++g) {
+        const float4 s = *reinterpret_cast<const float4 *>(vec + g * ldv + warp * kRowsPerWarp + q);   // broadcast
+        f4_fma(acc[g], s.x, r0);
+        f4_fma(acc[g], s.y, r1);
+        f4_fma(acc[g], s.z, r2);
+        f4_fma(acc[g], s.w, r3);
+      }
+    }
+  } else {
+    const bool col_ok = lane < ncol4;
+    const float4 *m = reinterpret_cast<const float4 *>(M) + (size_t)warp * rows_per_warp * ldm4 + c0_4 + lane;
+    __syncthreads();
+    const int row0 = warp * rows_per_warp;
+    for (int q = 0; q < rows_per_warp; q += 4) {
+      if (row0 + q >= K) break;                           // warp-uniform
+      float4 r[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) r[u] = (col_ok && row0 + q + u < K) ? __ldg(m + (size_t)(q + u) * ldm4) : f4_zero();
+#pragma unroll
+      for (int g = 0; g < kT; ++g) {
+        const float4 s = *reinterpret_cast<const float4 *>(vec + g * ldv + row0 + q);   // broadcast
+        f4_fma(acc[g], s.x, r[0]);
+        f4_fma(acc[g], s.y, r[1]);
+        f4_fma(acc[g], s.z, r[2]);
+        f4_fma(acc[g], s.w, r[3]);
+      }
     }
   }
 #pragma unroll
@@ -100,9 +129,13 @@ __device__ __forceinline__ void fold(float (&v)[kMaxRows], int lane, int o) {
   }
 }
 
-__global__ void __launch_bounds__(kThreads, 4) vs_tile_kernel(VsFusedArgs a, const float *__restrict__ WpT) {
+// NW = chunks of 128 floats in a word row; SQ = the word rows are exactly 128 floats (every bound constant)
+template <int NW, bool SQ>
+__global__ void __launch_bounds__(kThreads, NW == 1 ? 4 : 3) vs_tile_kernel(VsFusedArgs a, const float *__restrict__ WpT) {
   extern __shared__ __align__(16) float scratch[];      // partial products, then [kT][K1][kD] entity rows of the tile
-  __shared__ __align__(16) float hbuf[kT * kLd];        // h, later da
+  constexpr int kLdH = NW * kD + 4;                     // padded rows of the word-sized staging buffer
+  __shared__ __align__(16) float hbuf[kT * kLdH];       // h (word-sized rows), later da (entity-sized rows, stride kLd)
+  const int dw = SQ ? kD : a.dw, dw4 = SQ ? kD4 : (a.dw >> 2);
   __shared__ int xs[kT * kMaxWindow];
   __shared__ double s_loss[kT];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -150,19 +183,29 @@ __global__ void __launch_bounds__(kThreads, 4) vs_tile_kernel(VsFusedArgs a, con
   }
 
   // ---- B: gather + window mean (sert/models.py:180,226,1051) ------------------------------------------------
-  float4 h = f4_zero();
+  float4 h[NW];
+#pragma unroll
+  for (int u = 0; u < NW; ++u) h[u] = f4_zero();
 #pragma unroll 5
   for (int w = 0; w < W; ++w) {
     const int r = __shfl_sync(0xffffffffu, xi, w);
-    f4_add(h, __ldg(R4 + (size_t)r * kD4 + lane));
+#pragma unroll
+    for (int u = 0; u < NW; ++u)
+      if (lane + 32 * u < dw4) f4_add(h[u], __ldg(R4 + (size_t)r * dw4 + lane + 32 * u));
   }
   const float den = (float)W;
-  h.x = __fdiv_rn(h.x, den); h.y = __fdiv_rn(h.y, den); h.z = __fdiv_rn(h.z, den); h.w = __fdiv_rn(h.w, den);
-  reinterpret_cast<float4 *>(hbuf + warp * kLd)[lane] = h;
-  if (ok) reinterpret_cast<float4 *>(a.h)[(size_t)i * kD4 + lane] = h;
+#pragma unroll
+  for (int u = 0; u < NW; ++u) {
+    h[u].x = __fdiv_rn(h[u].x, den); h[u].y = __fdiv_rn(h[u].y, den);
+    h[u].z = __fdiv_rn(h[u].z, den); h[u].w = __fdiv_rn(h[u].w, den);
+    reinterpret_cast<float4 *>(hbuf + warp * kLdH)[lane + 32 * u] = h[u];          // chunks beyond dw hold zeros
+    if (ok && lane + 32 * u < dw4) reinterpret_cast<float4 *>(a.h)[(size_t)i * dw4 + lane + 32 * u] = h[u];
+  }
 
   // ---- C: t = tanh(h . Wp + bp) (sert/models.py:1055-1061) --------------------------------------------------
-  float4 t = tile_matvec(hbuf, scratch, a.Wp, warp, lane);
+  // K = dw rows of Wp (dw x 128) over the 8 warps, 4-row steps
+  const int rpw_c = ((dw + kT - 1) / kT + 3) & ~3;
+  float4 t = tile_matvec<SQ>(hbuf, kLdH, scratch, a.Wp, dw, rpw_c, kD4, 0, kD4, warp, lane);
   {
     const float4 b = __ldg(reinterpret_cast<const float4 *>(a.bp) + lane);
     t.x = tanhf(t.x + b.x); t.y = tanhf(t.y + b.y); t.z = tanhf(t.z + b.z); t.w = tanhf(t.w + b.w);
@@ -230,16 +273,25 @@ __global__ void __launch_bounds__(kThreads, 4) vs_tile_kernel(VsFusedArgs a, con
   // ---- E: dh = da . Wp^T, scatter-add of dh / W into the word-gradient rows (the entity rows are dead behind the
   //         first barrier of tile_matvec) ------------------------------------------------------------------------
   {
-    float4 dh = tile_matvec(hbuf, scratch, WpT, warp, lane);
-    dh.x = __fdiv_rn(dh.x, den); dh.y = __fdiv_rn(dh.y, den); dh.z = __fdiv_rn(dh.z, den); dh.w = __fdiv_rn(dh.w, den);
+    // WpT is (128 x dw): K = 128 rows, 16 per warp; the dw output columns in NW blocks of 128
+    float4 dh[NW];
+#pragma unroll
+    for (int u = 0; u < NW; ++u) {
+      const int ncol4 = min(kD4, dw4 - 32 * u);
+      dh[u] = tile_matvec<SQ>(hbuf, kLd, scratch, WpT, kD, kRowsPerWarp, dw4, 32 * u, ncol4, warp, lane);
+      dh[u].x = __fdiv_rn(dh[u].x, den); dh[u].y = __fdiv_rn(dh[u].y, den);
+      dh[u].z = __fdiv_rn(dh[u].z, den); dh[u].w = __fdiv_rn(dh[u].w, den);
+    }
     if (ok) {
-      float *dst = a.gR + lane * 4;
       float *hot = a.hot_slot == nullptr
                        ? nullptr
-                       : a.hot_acc + (size_t)(blockIdx.x & (a.hot_replicas - 1)) * kMaxHotRows * kD + lane * 4;
+                       : a.hot_acc + (size_t)(blockIdx.x & (a.hot_replicas - 1)) * kMaxHotRows * dw;
       for (int w = 0; w < W; ++w) {
         const int r = xs[warp * kMaxWindow + w];
-        red_add_f4(r >= 0 ? dst + (size_t)r * kD : hot + (size_t)(-1 - r) * kD, dh);
+        float *row = r >= 0 ? a.gR + (size_t)r * dw : hot + (size_t)(-1 - r) * dw;
+#pragma unroll
+        for (int u = 0; u < NW; ++u)
+          if (lane + 32 * u < dw4) red_add_f4(row + (lane + 32 * u) * 4, dh[u]);
       }
     }
   }
@@ -259,7 +311,7 @@ __global__ void __launch_bounds__(kThreads, 4) vs_tile_kernel(VsFusedArgs a, con
 }  // namespace
 
 bool vs_tile_supported(int dw, int de, int W, int k) {
-  return dw == kD && de == kD && W >= 1 && W <= kMaxWindow && k + 1 <= kMaxRows;
+  return dw >= 4 && dw % 4 == 0 && dw <= kMaxNW * kD && de == kD && W >= 1 && W <= kMaxWindow && k + 1 <= kMaxRows;
 }
 
 // returns 0 = launched, 1 = shape not served by this kernel
@@ -267,11 +319,20 @@ int launch_vs_tile(const VsFusedArgs &a, const float *WpT, cudaStream_t st) {
   if (!vs_tile_supported(a.dw, a.de, a.W, a.k)) return 1;
   const size_t smem = std::max((size_t)kT * (a.k + 1) * kD, (size_t)kPartFloats) * sizeof(float);
   static std::atomic<uint64_t> configured{0};
-  if (first_use_on_device(configured))
-    SERT_CUDA(cudaFuncSetAttribute(vs_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                   (int)(kT * kMaxRows * kD * sizeof(float))));
+  if (first_use_on_device(configured)) {
+    const int most = (int)(kT * kMaxRows * kD * sizeof(float));
+    SERT_CUDA(cudaFuncSetAttribute(vs_tile_kernel<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, most));
+    SERT_CUDA(cudaFuncSetAttribute(vs_tile_kernel<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, most));
+    SERT_CUDA(cudaFuncSetAttribute(vs_tile_kernel<2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, most));
+    SERT_CUDA(cudaFuncSetAttribute(vs_tile_kernel<3, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, most));
+  }
   static_assert(kSumsqSlots == 64, "the finalising CTA reads the slots with two warps");
-  vs_tile_kernel<<<cdiv(a.B, kT) + 1, kThreads, smem, st>>>(a, WpT);    // + 1: the CTA that finalises the previous loss
+  const int grid = cdiv(a.B, kT) + 1;                    // + 1: the CTA that finalises the previous loss
+  const int nw = (a.dw + kD - 1) / kD;
+  if (a.dw == kD) vs_tile_kernel<1, true><<<grid, kThreads, smem, st>>>(a, WpT);
+  else if (nw == 1) vs_tile_kernel<1, false><<<grid, kThreads, smem, st>>>(a, WpT);
+  else if (nw == 2) vs_tile_kernel<2, false><<<grid, kThreads, smem, st>>>(a, WpT);
+  else vs_tile_kernel<3, false><<<grid, kThreads, smem, st>>>(a, WpT);
   SERT_LAUNCH_CHECK();
   return 0;
 }

@@ -58,12 +58,15 @@ def test_forward_logits_match_oracle(dims):
     (1.0, False, dict(dw=128, de=128, W=32, B=40, k=1)),         # tile kernel, widest window / fewest negatives
     (1.0, True, dict(dw=128, de=128, W=3, B=64, k=16)),          # 17 scores: falls back to the warp kernel
     (40.0, True, dict(dw=64, de=48, W=5, B=128, k=6)),
-    (1.0, True, dict(dw=300, de=128, W=4, B=64, k=10)),          # product-search dims (unfused path)
+    (1.0, True, dict(dw=300, de=128, W=4, B=67, k=10)),          # product-search dims: tile kernel, 3 chunks per word row
+    (30.0, True, dict(dw=300, de=128, W=4, B=64, k=10)),         # ... into the clips
+    (1.0, False, dict(dw=200, de=128, W=6, B=40, k=5)),          # tile kernel, 2 chunks, ragged second chunk
+    (1.0, True, dict(dw=64, de=128, W=5, B=48, k=7)),            # tile kernel, word rows shorter than a chunk
     (3.0, True, dict(dw=32, de=32, W=40, B=96, k=3)),            # window > 32
 ])
 def test_training_steps_match_oracle(gain, weights, dims, fused, overlap):
-    """5 Adam steps + eval losses through the fused kernels (fused=1: tile kernel where d_w = d_e = 128, else the warp
-    kernel; fused=2: warp kernel) and the per-stage kernels (fused=0); gain >= 30 drives tanh / sigmoid into the
+    """5 Adam steps + eval losses through the fused kernels (fused=1: tile kernel where d_e = 128 and d_w <= 384, else
+    the warp kernel; fused=2: warp kernel) and the per-stage kernels (fused=0); gain >= 30 drives tanh / sigmoid into the
     1e-7 clips."""
     from sert_b200 import _native as N
     p = H.vs_problem(5, V=800, E=300, n_batches=5, gain=gain, weights=weights, **dims)
