@@ -192,7 +192,7 @@ __global__ void __launch_bounds__(256) rescore_kernel(const float *__restrict__ 
 // residual norms instead of assuming the worst case 2^-8 |q| roughly halves the band), plus d 2^-22 |qh| max|eh| for
 // the fp32 accumulation of the exact bf16 products inside the tensor core (truncating adds: one ulp each).  Two rows
 // whose exact scores order one way can order the other way in the coarse scores only within 2 eps_q: margin = 2 eps_q.
-__global__ void __launch_bounds__(256) prep_queries_kernel(const float *__restrict__ Qm, int Q, int d, int Kp,
+__global__ void __launch_bounds__(256) prep_queries_kernel(const float *__restrict__ Qm, int Q, int products, int d, int Kp,
                                                            __nv_bfloat16 *__restrict__ split, float ent_norm_max,
                                                            float ent_err_max, float *__restrict__ margin,
                                                            unsigned long long *__restrict__ tau, int *__restrict__ count) {
@@ -215,31 +215,37 @@ __global__ void __launch_bounds__(256) prep_queries_kernel(const float *__restri
   h2 = warp_sum(h2);
   if (lane == 0) {
     const float qh = sqrtf(h2);
-    const float eps = sqrtf(e2) * ent_norm_max + qh * ent_err_max + (float)d * 2.3841858e-7f * qh * ent_norm_max * 1.004f;
+    // ent_err_max is the residual of what the coarse GEMM keeps of an entity row (hi alone, or hi + mid); `d` counts the
+    // accumulated products (twice the dimension with two blocks)
+    const float eps = sqrtf(e2) * ent_norm_max + qh * ent_err_max + (float)products * 2.3841858e-7f * qh * ent_norm_max * 1.004f;
     margin[q] = 2.0f * eps * 1.02f + 1e-30f;
     tau[q] = 0ull;
     count[q] = 0;
   }
 }
 
-// largest row norm and largest bf16-rounding residual norm, as ordered uint bits (norms are >= 0): out[0], out[1]
+// largest row norm and largest residual norms after one / two bf16 terms, as ordered uint bits (norms are >= 0): out[0..2]
 __global__ void __launch_bounds__(256) row_norm_max_kernel(const float *__restrict__ E, long long rows, int d,
                                                            unsigned int *__restrict__ out) {
   const long long r = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (r >= rows) return;
-  float ss = 0.f, rr = 0.f;
+  float ss = 0.f, rr = 0.f, r2 = 0.f;
   for (int c = lane; c < d; c += 32) {
     const float v = E[(size_t)r * d + c];
     const float res = v - __bfloat162float(__float2bfloat16_rn(v));
+    const float res2 = res - __bfloat162float(__float2bfloat16_rn(res));
     ss = fmaf(v, v, ss);
     rr = fmaf(res, res, rr);
+    r2 = fmaf(res2, res2, r2);
   }
   ss = warp_sum(ss);
   rr = warp_sum(rr);
+  r2 = warp_sum(r2);
   if (lane == 0) {
     atomicMax(out, __float_as_uint(sqrtf(ss)));
     atomicMax(out + 1, __float_as_uint(sqrtf(rr)));
+    atomicMax(out + 2, __float_as_uint(sqrtf(r2)));
   }
 }
 
@@ -263,12 +269,17 @@ __global__ void __launch_bounds__(256) seed_tau_kernel(const float *__restrict__
   }
   unsigned int t = 0u;
 #pragma unroll 1
-  for (int bit = 31; bit >= 0; --bit) {
+  // 20 of the 32 bits: the result (low bits zero) is a lower bound of the exact j-th largest value, 2^-11 relative
+  // below it at most -- any lower bound seeds a valid threshold, and this one lets through well under 1 % more rows
+  for (int bit = 31; bit >= 12; --bit) {
     const unsigned int cand = t | (1u << bit);
     unsigned int c = 0u;
 #pragma unroll
     for (int i = 0; i < kSeedGroups / 32; ++i) c += v[i] >= cand ? 1u : 0u;
-    c = __reduce_add_sync(0xffffffffu, c);
+    // shuffle butterfly, not __reduce_add_sync: REDUX issues at a fraction of the shuffle rate, and 64 resident warps
+    // doing 32 of them each made this kernel 28 us for 10 k queries
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
     if (c >= (unsigned int)j) t = cand;
   }
   if (lane == 0) tau[q] = make_key(unorderable(t) - margin[q], 0xffffffffu);
@@ -741,7 +752,7 @@ static int topk_pass(const TopkState &s, const float *queries_dev, int Q, int k_
       ep.tau = s.tau; ep.count = s.count; ep.cand = s.cand; ep.cap = s.cap; ep.row_offset = s.row_begin;
       ep.overflow = s.overflow;
       // coarse: the first block of both operands is the hi term ([hi|hi|mid] x [hi|mid|hi]); same buffers, depth kt/3
-      const int depth = coarse ? s.kt / s.terms : s.kt;
+      const int depth = coarse ? s.coarse_blocks * (s.kt / s.terms) : s.kt;
       if (launch_gemm_tc_ld(s.q_split, s.kt, Q, s.ent_split, s.kt, s.rows, n0, n1, depth, ep, st)) return -1;
     } else {
       dim3 grid(cdiv(n1 - n0, TN), cdiv(Q, TQ));
@@ -877,8 +888,9 @@ int topk_sweep(const TopkState &s, const float *queries_dev, int Q, int k, int32
   trace.mark("start");
   if (tensor) {
     // split rows [hi|hi|mid] of the queries, their coarse-score margins, list state reset
-    prep_queries_kernel<<<cdiv(Q, 8), 256, 0, st>>>(queries_dev, Q, s.d, s.kt / s.terms, s.q_split, s.ent_norm_max,
-                                                    s.ent_err_max, s.margin, s.tau, s.count);
+    prep_queries_kernel<<<cdiv(Q, 8), 256, 0, st>>>(queries_dev, Q, s.d * s.coarse_blocks, s.d, s.kt / s.terms, s.q_split,
+                                                    s.ent_norm_max, s.coarse_blocks == 2 ? s.ent_err2_max : s.ent_err_max,
+                                                    s.margin, s.tau, s.count);
     SERT_LAUNCH_CHECK();
   }
   int overflow = 1;
@@ -896,7 +908,7 @@ int topk_sweep(const TopkState &s, const float *queries_dev, int Q, int k, int32
       SERT_CUDA(cudaMemsetAsync(s.overflow, 0, sizeof(int), st));
       trace.mark("prep");
       TcEpilogue ep;
-      const int depth = s.kt / s.terms;     // first block of both split operands = the hi term
+      const int depth = s.coarse_blocks * (s.kt / s.terms);     // leading block(s) of both split operands
       if (plan.seeded) {
         ep.mode = TC_EPI_GROUPMAX;
         ep.gmax = s.gmax; ep.gmax_ld = kSeedGroups; ep.group = plan.g; ep.tile_stride = (int)plan.stride;
@@ -1174,7 +1186,7 @@ static size_t carve_scorer(sert_scorer &sc, void *base, int64_t rows, int d, int
   sc.s.cand = reinterpret_cast<unsigned long long *>(take((size_t)max_queries * cap * sizeof(unsigned long long)));
   sc.s.tau = reinterpret_cast<unsigned long long *>(take((size_t)max_queries * sizeof(unsigned long long)));
   sc.s.count = reinterpret_cast<int *>(take((size_t)max_queries * sizeof(int)));
-  sc.s.overflow = reinterpret_cast<int *>(take(4 * sizeof(int)));      // [1], [2]: scratch of row_norm_max_kernel
+  sc.s.overflow = reinterpret_cast<int *>(take(8 * sizeof(int)));      // [3]: merge verdict; [4..6]: scratch of row_norm_max_kernel
   sc.s.margin = reinterpret_cast<float *>(take((size_t)max_queries * sizeof(float)));
   sc.s.gmax = reinterpret_cast<float *>(take((size_t)max_queries * kSeedGroups * sizeof(float)));
   sc.queries = reinterpret_cast<float *>(take((size_t)max_queries * d * sizeof(float)));
@@ -1231,19 +1243,21 @@ int sert_scorer_create(const float *entities_host, int64_t rows, int32_t d, int6
     }
   }
   sc->s.mode = SCORE_TENSOR;
-  unsigned int norm_bits[2] = {0u, 0u};
+  unsigned int norm_bits[3] = {0u, 0u, 0u};
   if (rows > 0) {
-    unsigned int *scratch = reinterpret_cast<unsigned int *>(sc->s.overflow + 1);
-    cudaMemsetAsync(scratch, 0, 2 * sizeof(unsigned int), sc->st);
+    unsigned int *scratch = reinterpret_cast<unsigned int *>(sc->s.overflow + 4);
+    cudaMemsetAsync(scratch, 0, 3 * sizeof(unsigned int), sc->st);
     row_norm_max_kernel<<<cdiv(rows, 8), 256, 0, sc->st>>>(sc->s.entities, rows, d, scratch);
     count_launch();
-    cudaMemcpyAsync(norm_bits, scratch, 2 * sizeof(unsigned int), cudaMemcpyDeviceToHost, sc->st);
+    cudaMemcpyAsync(norm_bits, scratch, 3 * sizeof(unsigned int), cudaMemcpyDeviceToHost, sc->st);
   }
   cudaError_t e = cudaStreamSynchronize(sc->st);
   if (e == cudaSuccess) e = cudaGetLastError();
   if (e != cudaSuccess) { delete sc; set_error(cudaGetErrorString(e)); return -1; }
   memcpy(&sc->s.ent_norm_max, &norm_bits[0], sizeof(float));
   memcpy(&sc->s.ent_err_max, &norm_bits[1], sizeof(float));
+  memcpy(&sc->s.ent_err2_max, &norm_bits[2], sizeof(float));
+  sc->s.coarse_blocks = (sc->s.kt / sc->s.terms <= 128 && getenv("SERT_COARSE_BLOCKS1") == nullptr) ? 2 : 1;
   *out = sc;
   return 0;
 }

@@ -35,6 +35,11 @@ struct TopkState {
   float *margin = nullptr;              // (max_queries,)
   float ent_norm_max = 0.f;             // largest L2 norm of an entity row
   float ent_err_max = 0.f;              // largest L2 norm of (row - bf16(row)): the rows' share of the coarse error
+  float ent_err2_max = 0.f;             // ... of (row - hi - mid): the rows' share when the coarse GEMM takes two blocks
+  // Blocks of the split operands the coarse GEMM multiplies: 1 = [hi].[hi]; 2 = [hi|hi].[hi|mid] = q_hi.(e_hi + e_mid),
+  // which removes the entity rows' rounding from the error (the margin band halves).  Two blocks double the MMA work;
+  // taken when one block is a K of 128 or less, where the epilogue paces the sweep and the extra MMAs are free.
+  int coarse_blocks = 1;
   // seeded single-launch sweep (score.cu: topk_sweep): group maxima of a strided row sample, (max_queries, kSeedGroups)
   float *gmax = nullptr;
   int seeded = 1;                       // 0: always the multi-chunk sweep (tests, diagnostics)
