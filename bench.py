@@ -482,7 +482,7 @@ def run_bf16_state_mode(p, cfg, steps, warm, repeats, f32_first_losses, f32_last
             'value': world * cfg['B'] / (ms * 1e-3), 'unit': UNIT, 'ms_per_step': ms, 'dtype': 'f32 + bf16 optimiser state',
             'roofline': {'bound': 'hbm', 'kernel': 'dense_update_kernel<Adam, tables, bf16 state>', 'achieved': achieved,
                          'peak': peak, 'unit': 'GB/s', 'frac': achieved / peak, 'peak_source': peak_src,
-                         'algorithmic_bytes_per_launch': bpl.value, 'kernel_ms': upd_ms, 'traffic': None},
+                         'algorithmic_bytes_per_launch': bpl.value, 'kernel_ms': upd_ms, 'traffic': bf16_traffic()},
             'deviation_rel': rel(first, f32_first_losses),
             'deviation_rel_after_%d_steps' % (n_batches + repeats * steps): rel(last[warm:], f32_last_losses[warm:]),
             'deviation_what': 'max relative difference of the per-batch training losses against the float32 run of '
@@ -532,6 +532,14 @@ def run_product_search_shape(rank, steps=200):
             'value': cfg['B'] / (ms * 1e-3), 'unit': UNIT, 'ms_per_step': ms,
             'step_algorithmic_bytes': step_bytes, 'step_frac_of_hbm_peak': step_bytes / (ms * 1e-3) / 1e9 / peak,
             'final_loss': float(losses[-1])}
+
+
+def bf16_traffic():
+    tpath = os.path.join(ROOT, 'profiles', 'dense_update_traffic.json')
+    if os.path.exists(tpath):
+        with open(tpath) as f:
+            return (json.load(f).get('bf16_state') or {}).get('dram_bytes_per_launch')
+    return None
 
 
 def scoring_shard(sc, world, rank):

@@ -23,7 +23,8 @@ for variant in variants:
     model = models.VectorSpaceLanguageModel(
         batch_size=cfg['B'], window_size=cfg['W'], num_negative_samples=cfg['k'],
         representations_init=p['R'], entity_representations_init=p['Eemb'], regularization_lambda=cfg['lam'],
-        training_set=p['train'], validation_set=p['val'], dense_init=(p['Wp'], p['bp']), loss_slots=max(1024, nb))
+        training_set=p['train'], validation_set=p['val'], dense_init=(p['Wp'], p['bp']), loss_slots=max(1024, nb),
+        optimizer_state_dtype='bfloat16' if os.environ.get('SERT_BENCH_BF16_STATE') else 'float32')
     nat = model._native
     N.check(nat.lib.sert_model_set_fused(nat.handle, variant))
     best = None
