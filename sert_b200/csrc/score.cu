@@ -955,7 +955,9 @@ int topk_sweep(const TopkState &s, const float *queries_dev, int Q, int k, int32
     if (overflow && topk_pass(s, queries_dev, Q, k_sel, false, st)) return -1;
   }
   if (tensor && s.rows > 0) {
-    rescore_kernel<<<Q, 256, (size_t)s.d * sizeof(float), st>>>(queries_dev, s.entities, s.d, s.row_begin, s.cand,
+    // the query's shared-memory copy is padded to whole 16-byte pieces: the compiler reads it in 16-byte loads even on
+    // the ragged path (compute-sanitizer flagged the last, partly unused piece when d is no multiple of 4)
+    rescore_kernel<<<Q, 256, align_up((size_t)s.d * sizeof(float), 16), st>>>(queries_dev, s.entities, s.d, s.row_begin, s.cand,
                                                                 s.count, s.cap);
     SERT_LAUNCH_CHECK();
   }
