@@ -64,16 +64,18 @@ struct KernelArgs {
 // The CTAs start their sweeps at different m-tiles (blockIdx.x apart): 148 SMs asking L2 for the same A tile at the
 // same moment queue up on the slices that hold its lines (measured: 10.3 k cycles per tile unstaggered).
 // seq = position inside the n-tile's sweep (0 = first, num_m_tiles - 1 = last).
+// bid / gdim: the CTA's place among the tile walkers -- blockIdx.x / gridDim.x, or the CLUSTER's index / count when two
+// CTAs walk the tiles as a pair (num_m_tiles then counts pairs of m-tiles).
 template <bool BSTAT>
-__device__ __forceinline__ bool cta_tile(int it, int num_m_tiles, int num_n_tiles, int k_slices, int step_m, int step_n,
-                                         int &mt, int &nt, int &seq, int &slice) {
+__device__ __forceinline__ bool cta_tile(int it, int bid, int gdim, int num_m_tiles, int num_n_tiles, int k_slices,
+                                         int step_m, int step_n, int &mt, int &nt, int &seq, int &slice) {
   slice = 0;
   if (BSTAT) {
     if (it == 0) {
-      nt = blockIdx.x; seq = 0;
-      mt = (int)(blockIdx.x % (unsigned)num_m_tiles);
+      nt = bid; seq = 0;
+      mt = bid % num_m_tiles;
     } else {
-      if (++seq == num_m_tiles) { seq = 0; nt += gridDim.x; }
+      if (++seq == num_m_tiles) { seq = 0; nt += gdim; }
       if (++mt == num_m_tiles) mt = 0;
     }
     return nt < num_n_tiles;
@@ -83,8 +85,8 @@ __device__ __forceinline__ bool cta_tile(int it, int num_m_tiles, int num_n_tile
   // (~150 instructions) were a fifth of an epilogue warp's work on a tile without survivors.  `mt` and `nt` carry
   // the previous tile's coordinates (nt counts n-tiles across all K slices); a step adds gridDim.x tiles.
   if (it == 0) {
-    mt = (int)(blockIdx.x % (unsigned)num_m_tiles);
-    nt = (int)(blockIdx.x / (unsigned)num_m_tiles);
+    mt = bid % num_m_tiles;
+    nt = bid / num_m_tiles;
   } else {
     mt += step_m;
     nt += step_n;
@@ -137,6 +139,23 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const void *map, uint3
       ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1)
       : "memory");
 }
+// the same load, delivered to the same shared-memory offset (and mbarrier offset) of every CTA in `cta_mask`
+__device__ __forceinline__ void tma_load_2d_multicast(uint32_t dst, const void *map, uint32_t bar, int c0, int c1,
+                                                      uint16_t cta_mask) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster "
+      "[%0], [%1, {%3, %4}], [%2], %5;"
+      ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "h"(cta_mask)
+      : "memory");
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ uint32_t cluster_cta_rank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_alloc(uint32_t smem_result, uint32_t cols) {
@@ -160,6 +179,13 @@ __device__ __forceinline__ void tc_mma_bf16(uint32_t d_tmem, uint64_t a_desc, ui
 // arrive on an mbarrier when all previously issued tcgen05.mma of this thread have completed
 __device__ __forceinline__ void tc_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+// ... on the mbarrier at this offset of every CTA in `cta_mask` (the peer's producer waits for both MMA warps)
+__device__ __forceinline__ void tc_commit_multicast(uint32_t bar, uint16_t cta_mask) {
+  asm volatile(
+      "tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar),
+      "h"(cta_mask)
+      : "memory");
 }
 __device__ __forceinline__ void tc_ld_32x32(uint32_t taddr, uint32_t (&r)[32]) {
   asm volatile(
@@ -216,7 +242,11 @@ constexpr uint32_t make_idesc(int m, int n) {
 // ---- the kernel -----------------------------------------------------------------------------------
 // MODE = the epilogue (TcEpilogueMode): one kernel per epilogue keeps each kernel's code small enough for the
 // instruction caches (the epilogues are long unrolled register code; a warp only ever runs one of them).
-template <bool BSTAT, int MODE>
+// CL = 2: the CTAs run in clusters of two that share an n-tile and take two adjacent m-tiles.  Each CTA loads its own
+// A tile and HALF of the B tile, multicast into both CTAs' shared memory (TMA .multicast::cluster), so a tile pair
+// pulls 16 + 16 + 16 + 16 = 64 KB per K block through L2 instead of 96 KB; a stage's slot is free for the next load
+// once BOTH MMA warps have retired their reads of it (tcgen05.commit multicast on the empty barriers).
+template <bool BSTAT, int MODE, int CL = 1>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ TcMap map_a, const __grid_constant__ TcMap map_b, const KernelArgs args) {
   extern __shared__ unsigned char smem_raw[];
@@ -239,14 +269,17 @@ gemm_tc_kernel(const __grid_constant__ TcMap map_a, const __grid_constant__ TcMa
 
   const int num_m_tiles = (args.M + BM - 1) / BM;
   const int num_n_tiles = (int)((args.n_end - args.n_begin + BN - 1) / BN);
-  const int step_m = (int)(gridDim.x % (unsigned)num_m_tiles), step_n = (int)(gridDim.x / (unsigned)num_m_tiles);
+  const uint32_t cta_rank = CL == 2 ? cluster_cta_rank() : 0u;
+  const int bid = (int)blockIdx.x / CL, gdim = (int)gridDim.x / CL;
+  const int walk_m_tiles = (num_m_tiles + CL - 1) / CL;                  // m-tiles, or pairs of m-tiles
+  const int step_m = gdim % walk_m_tiles, step_n = gdim / walk_m_tiles;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&map_a);
     tma_prefetch_desc(&map_b);
     for (int s = 0; s < STAGES; ++s) {
       mbar_init(full_bar(s), 1);
-      mbar_init(empty_bar(s), 1);
+      mbar_init(empty_bar(s), CL);            // one arrival per MMA warp that reads the slot
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(tfull_bar(a), 1);
@@ -259,6 +292,7 @@ gemm_tc_kernel(const __grid_constant__ TcMap map_a, const __grid_constant__ TcMa
   if (warp == 1) tc_alloc(tmem_ptr_smem, TMEM_COLS);
   tc_fence_before();
   __syncthreads();
+  if (CL == 2) cluster_sync_all();           // the peer's barriers exist before anything is multicast at them
   tc_fence_after();
   uint32_t tmem_base;
   asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_ptr_smem));
@@ -269,8 +303,8 @@ gemm_tc_kernel(const __grid_constant__ TcMap map_a, const __grid_constant__ TcMa
       int stage = 0;
       uint32_t phase = 0, bphase = 0;
       int mt, nt, seq, slice;
-      for (int it = 0; cta_tile<BSTAT>(it, num_m_tiles, num_n_tiles, args.k_slices, step_m, step_n, mt, nt, seq, slice); ++it) {
-        const int m0 = mt * BM;
+      for (int it = 0; cta_tile<BSTAT>(it, bid, gdim, walk_m_tiles, num_n_tiles, args.k_slices, step_m, step_n, mt, nt, seq, slice); ++it) {
+        const int m0 = (mt * CL + (int)cta_rank) * BM;
         const int n0 = (int)(args.n_begin + (long long)slice_nt(nt, num_n_tiles, slice) * BN * args.epi.tile_stride);
         int kb0, nkb;
         slice_range(args.num_kb, args.k_slices, slice, kb0, nkb);
@@ -285,7 +319,13 @@ gemm_tc_kernel(const __grid_constant__ TcMap map_a, const __grid_constant__ TcMa
           mbar_wait(empty_bar(stage), phase ^ 1u);
           mbar_expect_tx(full_bar(stage), BSTAT ? A_STAGE_BYTES : STAGE_BYTES);
           tma_load_2d(smem_a + stage * A_STAGE_BYTES, &map_a, full_bar(stage), kb * BK, m0);
-          if (!BSTAT) tma_load_2d(smem_b + stage * B_STAGE_BYTES, &map_b, full_bar(stage), kb * BK, n0);
+          if (CL == 2) {
+            // this CTA's half of the B tile (map_b's box is BN / 2 rows), into both CTAs
+            tma_load_2d_multicast(smem_b + stage * B_STAGE_BYTES + cta_rank * (B_STAGE_BYTES / 2), &map_b, full_bar(stage),
+                                  kb * BK, n0 + (int)cta_rank * (BN / 2), (uint16_t)0x3);
+          } else if (!BSTAT) {
+            tma_load_2d(smem_b + stage * B_STAGE_BYTES, &map_b, full_bar(stage), kb * BK, n0);
+          }
           if (++stage == STAGES) { stage = 0; phase ^= 1u; }
         }
       }
@@ -299,7 +339,7 @@ gemm_tc_kernel(const __grid_constant__ TcMap map_a, const __grid_constant__ TcMa
       int acc = 0;
       uint32_t acc_phase = 0, bphase = 0;
       int mt, nt, seq, slice;
-      for (int it = 0; cta_tile<BSTAT>(it, num_m_tiles, num_n_tiles, args.k_slices, step_m, step_n, mt, nt, seq, slice); ++it) {
+      for (int it = 0; cta_tile<BSTAT>(it, bid, gdim, walk_m_tiles, num_n_tiles, args.k_slices, step_m, step_n, mt, nt, seq, slice); ++it) {
         int kb0, nkb;
         slice_range(args.num_kb, args.k_slices, slice, kb0, nkb);
         if (BSTAT && seq == 0) {
@@ -320,7 +360,8 @@ gemm_tc_kernel(const __grid_constant__ TcMap map_a, const __grid_constant__ TcMa
             tc_mma_bf16(d_tmem, make_smem_desc(a_addr + k * UMMA_K * 2), make_smem_desc(b_addr + k * UMMA_K * 2),
                         idesc, (kb | k) != 0 ? 1u : 0u);
           }
-          tc_commit(empty_bar(stage));                   // frees the smem slot once those MMAs retire
+          if (CL == 2) tc_commit_multicast(empty_bar(stage), (uint16_t)0x3);   // ... in both CTAs: the peer's loads land here too
+          else tc_commit(empty_bar(stage));              // frees the smem slot once those MMAs retire
           if (++stage == STAGES) { stage = 0; phase ^= 1u; }
         }
         tc_commit(tfull_bar(acc));                       // accumulator complete -> epilogue
@@ -369,8 +410,8 @@ gemm_tc_kernel(const __grid_constant__ TcMap map_a, const __grid_constant__ TcMa
       pend_wtotal = 0;
     };
     int mt, nt, seq, slice;
-    for (int it = 0; cta_tile<BSTAT>(it, num_m_tiles, num_n_tiles, args.k_slices, step_m, step_n, mt, nt, seq, slice); ++it) {
-      const int m0 = mt * BM;
+    for (int it = 0; cta_tile<BSTAT>(it, bid, gdim, walk_m_tiles, num_n_tiles, args.k_slices, step_m, step_n, mt, nt, seq, slice); ++it) {
+      const int m0 = (mt * CL + (int)cta_rank) * BM;
       const int nt_in = slice_nt(nt, num_n_tiles, slice);
       const long long n0 = args.n_begin + (long long)nt_in * BN * args.epi.tile_stride;
       const int gm = m0 + row;
@@ -618,6 +659,7 @@ gemm_tc_kernel(const __grid_constant__ TcMap map_a, const __grid_constant__ TcMa
 
   tc_fence_before();
   __syncthreads();
+  if (CL == 2) cluster_sync_all();           // no CTA leaves while its peer may still signal its barriers
   if (warp == 1) {
     tc_fence_after();
     tc_dealloc(tmem_base, TMEM_COLS);
@@ -685,6 +727,7 @@ int launch_gemm_tc_ld(const __nv_bfloat16 *A, long long lda, int M, const __nv_b
     SERT_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<false, TC_EPI_TOPK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
     SERT_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<false, TC_EPI_GROUPMAX>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
     SERT_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<true, TC_EPI_TOPK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
+    SERT_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<false, TC_EPI_STORE, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
   }
   int dev = 0, sms = kNumSMs;
   SERT_CUDA(cudaGetDevice(&dev));
@@ -723,6 +766,31 @@ int launch_gemm_tc_ld(const __nv_bfloat16 *A, long long lda, int M, const __nv_b
     work = tiles * args.k_slices;
   }
   const int grid = (int)std::min<long long>(work, sms);
+  // Two-CTA clusters with a multicast B tile (store epilogue): a third less operand traffic through L2 for the GEMMs
+  // whose K is too deep for the B-stationary schedule (the log-linear projection and its gradients).  Needs an even
+  // number of SMs' worth of CTAs and enough m-tiles that pairing them wastes little (an odd count pads one tile).
+  const char *cl_env = getenv("SERT_GEMM_CLUSTER");
+  const bool cluster2 = epi.mode == TC_EPI_STORE && m_tiles >= 8 && (m_tiles % 2 == 0 || m_tiles >= 32) &&
+                        !(cl_env != nullptr && cl_env[0] == '0');
+  if (cluster2) {
+    TcMap mb_half;
+    if (make_map(B, N_total, Kt, ldb, BN / 2, &mb_half)) return -1;
+    const long long pair_work = ((m_tiles + 1) / 2) * n_tiles * args.k_slices;
+    const int clusters = (int)std::min<long long>(pair_work, sms / 2);
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(2 * clusters);
+    cfg.blockDim = dim3(NUM_THREADS);
+    cfg.dynamicSmemBytes = SMEM_BYTES;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    SERT_CUDA(cudaLaunchKernelEx(&cfg, gemm_tc_kernel<false, TC_EPI_STORE, 2>, ma, mb_half, args));
+    count_launch();
+    return 0;
+  }
   if (epi.mode == TC_EPI_TOPK) gemm_tc_kernel<false, TC_EPI_TOPK><<<grid, NUM_THREADS, SMEM_BYTES, st>>>(ma, mb, args);
   else if (epi.mode == TC_EPI_GROUPMAX) gemm_tc_kernel<false, TC_EPI_GROUPMAX><<<grid, NUM_THREADS, SMEM_BYTES, st>>>(ma, mb, args);
   else gemm_tc_kernel<false, TC_EPI_STORE><<<grid, NUM_THREADS, SMEM_BYTES, st>>>(ma, mb, args);

@@ -45,3 +45,40 @@ def test_identity_layout():
     ref = a.astype(np.float64) @ b.astype(np.float64).T
     got = run(a, b, 3)
     np.testing.assert_allclose(got, ref, rtol=1e-5, atol=1e-3)
+
+
+def test_cluster_multicast_layout_is_exact():
+    """Two-CTA clusters with a multicast B tile (m-tiles >= 8): every output column picks one B row and every output row
+    one A element, so a half-tile landing at the wrong offset, in the wrong CTA or with the wrong swizzle shows up
+    exactly; an odd number of m-tiles leaves the last cluster's second CTA without rows."""
+    for m in (1024, 1152, 4224):
+        n, k = 768, 128
+        a = np.zeros((m, k), np.float32)
+        b = np.zeros((n, k), np.float32)
+        for i in range(m):
+            a[i, i % k] = 1.0 + (i % 97)
+        for j in range(n):
+            b[j, (j * 5) % k] = 0.5 + (j % 89)
+        ref = a.astype(np.float64) @ b.astype(np.float64).T
+        got = run(a, b, 3)
+        np.testing.assert_allclose(got, ref, rtol=1e-5, atol=1e-3)
+
+
+@pytest.mark.parametrize('m,n,k', [(2048, 1000, 192), (4200, 300, 640), (1100, 513, 1000), (1024, 256, 64)])
+def test_cluster_multicast_equals_single_cta_tiles(m, n, k):
+    """The two-CTA cluster schedule changes where operand tiles come from, not the arithmetic: bit-identical outputs
+    with SERT_GEMM_CLUSTER=0 (even, odd (33) and few (8, 9) m-tiles; ragged n; K of 1, 3, 10, 16 blocks)."""
+    import os
+    rng = np.random.default_rng(m + n + k)
+    a = rng.standard_normal((m, k)).astype(np.float32)
+    b = rng.standard_normal((n, k)).astype(np.float32)
+    bias = rng.standard_normal(n).astype(np.float32)
+    got = run(a, b, 3, bias)
+    os.environ['SERT_GEMM_CLUSTER'] = '0'
+    try:
+        plain = run(a, b, 3, bias)
+    finally:
+        del os.environ['SERT_GEMM_CLUSTER']
+    np.testing.assert_array_equal(got, plain)
+    ref = a.astype(np.float64) @ b.astype(np.float64).T + bias
+    assert np.abs(got - ref).max() < 6e-5 * np.sqrt(k)
