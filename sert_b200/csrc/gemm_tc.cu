@@ -242,10 +242,11 @@ constexpr uint32_t make_idesc(int m, int n) {
 // ---- the kernel -----------------------------------------------------------------------------------
 // MODE = the epilogue (TcEpilogueMode): one kernel per epilogue keeps each kernel's code small enough for the
 // instruction caches (the epilogues are long unrolled register code; a warp only ever runs one of them).
-// CL = 2: the CTAs run in clusters of two that share an n-tile and take two adjacent m-tiles.  Each CTA loads its own
-// A tile and HALF of the B tile, multicast into both CTAs' shared memory (TMA .multicast::cluster), so a tile pair
-// pulls 16 + 16 + 16 + 16 = 64 KB per K block through L2 instead of 96 KB; a stage's slot is free for the next load
-// once BOTH MMA warps have retired their reads of it (tcgen05.commit multicast on the empty barriers).
+// CL = 2 or 4: the CTAs run in clusters that share an n-tile and take CL adjacent m-tiles.  Each CTA loads its own A
+// tile and 1/CL of the B tile, multicast into every CTA's shared memory (TMA .multicast::cluster), so a cluster pulls
+// CL*16 + 32 KB per K block through L2 instead of CL*48 KB (-33 % at CL = 2, -50 % at CL = 4); a stage's slot is free
+// for the next load once ALL the cluster's MMA warps have retired their reads of it (tcgen05.commit multicast on the
+// empty barriers).
 template <bool BSTAT, int MODE, int CL = 1>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ TcMap map_a, const __grid_constant__ TcMap map_b, const KernelArgs args) {
@@ -269,7 +270,7 @@ gemm_tc_kernel(const __grid_constant__ TcMap map_a, const __grid_constant__ TcMa
 
   const int num_m_tiles = (args.M + BM - 1) / BM;
   const int num_n_tiles = (int)((args.n_end - args.n_begin + BN - 1) / BN);
-  const uint32_t cta_rank = CL == 2 ? cluster_cta_rank() : 0u;
+  const uint32_t cta_rank = CL > 1 ? cluster_cta_rank() : 0u;
   const int bid = (int)blockIdx.x / CL, gdim = (int)gridDim.x / CL;
   const int walk_m_tiles = (num_m_tiles + CL - 1) / CL;                  // m-tiles, or pairs of m-tiles
   const int step_m = gdim % walk_m_tiles, step_n = gdim / walk_m_tiles;
@@ -292,7 +293,7 @@ gemm_tc_kernel(const __grid_constant__ TcMap map_a, const __grid_constant__ TcMa
   if (warp == 1) tc_alloc(tmem_ptr_smem, TMEM_COLS);
   tc_fence_before();
   __syncthreads();
-  if (CL == 2) cluster_sync_all();           // the peer's barriers exist before anything is multicast at them
+  if (CL > 1) cluster_sync_all();            // the peers' barriers exist before anything is multicast at them
   tc_fence_after();
   uint32_t tmem_base;
   asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_ptr_smem));
@@ -319,10 +320,10 @@ gemm_tc_kernel(const __grid_constant__ TcMap map_a, const __grid_constant__ TcMa
           mbar_wait(empty_bar(stage), phase ^ 1u);
           mbar_expect_tx(full_bar(stage), BSTAT ? A_STAGE_BYTES : STAGE_BYTES);
           tma_load_2d(smem_a + stage * A_STAGE_BYTES, &map_a, full_bar(stage), kb * BK, m0);
-          if (CL == 2) {
-            // this CTA's half of the B tile (map_b's box is BN / 2 rows), into both CTAs
-            tma_load_2d_multicast(smem_b + stage * B_STAGE_BYTES + cta_rank * (B_STAGE_BYTES / 2), &map_b, full_bar(stage),
-                                  kb * BK, n0 + (int)cta_rank * (BN / 2), (uint16_t)0x3);
+          if (CL > 1) {
+            // this CTA's share of the B tile (map_b's box is BN / CL rows), into every CTA of the cluster
+            tma_load_2d_multicast(smem_b + stage * B_STAGE_BYTES + cta_rank * (B_STAGE_BYTES / CL), &map_b, full_bar(stage),
+                                  kb * BK, n0 + (int)cta_rank * (BN / CL), (uint16_t)((1u << CL) - 1u));
           } else if (!BSTAT) {
             tma_load_2d(smem_b + stage * B_STAGE_BYTES, &map_b, full_bar(stage), kb * BK, n0);
           }
@@ -360,7 +361,7 @@ gemm_tc_kernel(const __grid_constant__ TcMap map_a, const __grid_constant__ TcMa
             tc_mma_bf16(d_tmem, make_smem_desc(a_addr + k * UMMA_K * 2), make_smem_desc(b_addr + k * UMMA_K * 2),
                         idesc, (kb | k) != 0 ? 1u : 0u);
           }
-          if (CL == 2) tc_commit_multicast(empty_bar(stage), (uint16_t)0x3);   // ... in both CTAs: the peer's loads land here too
+          if (CL > 1) tc_commit_multicast(empty_bar(stage), (uint16_t)((1u << CL) - 1u));   // ... in every CTA of the cluster: the peers' loads land here too
           else tc_commit(empty_bar(stage));              // frees the smem slot once those MMAs retire
           if (++stage == STAGES) { stage = 0; phase ^= 1u; }
         }
@@ -659,7 +660,7 @@ gemm_tc_kernel(const __grid_constant__ TcMap map_a, const __grid_constant__ TcMa
 
   tc_fence_before();
   __syncthreads();
-  if (CL == 2) cluster_sync_all();           // no CTA leaves while its peer may still signal its barriers
+  if (CL > 1) cluster_sync_all();            // no CTA leaves while a peer may still signal its barriers
   if (warp == 1) {
     tc_fence_after();
     tc_dealloc(tmem_base, TMEM_COLS);
@@ -728,6 +729,7 @@ int launch_gemm_tc_ld(const __nv_bfloat16 *A, long long lda, int M, const __nv_b
     SERT_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<false, TC_EPI_GROUPMAX>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
     SERT_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<true, TC_EPI_TOPK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
     SERT_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<false, TC_EPI_STORE, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
+    SERT_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<false, TC_EPI_STORE, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
   }
   int dev = 0, sms = kNumSMs;
   SERT_CUDA(cudaGetDevice(&dev));
@@ -766,28 +768,35 @@ int launch_gemm_tc_ld(const __nv_bfloat16 *A, long long lda, int M, const __nv_b
     work = tiles * args.k_slices;
   }
   const int grid = (int)std::min<long long>(work, sms);
-  // Two-CTA clusters with a multicast B tile (store epilogue): a third less operand traffic through L2 for the GEMMs
-  // whose K is too deep for the B-stationary schedule (the log-linear projection and its gradients).  Needs an even
-  // number of SMs' worth of CTAs and enough m-tiles that pairing them wastes little (an odd count pads one tile).
+  // Clusters of 2 or 4 CTAs with a multicast B tile (store epilogue): a third / half less operand traffic through L2
+  // for the GEMMs whose K is too deep for the B-stationary schedule (the log-linear projection and its gradients).
+  // Needs enough m-tiles that grouping them wastes little (a ragged count pads the last group).
+  // Measured at BASELINE configs[4] (one box, one session): step 29.9 ms without clusters, 27.9 ms with pairs, 32.7 ms
+  // with clusters of four (the lockstep of four CTAs costs more than the traffic saves), so pairs are the default.
+  // SERT_GEMM_CLUSTER = 0: off, 4: clusters of four where the m-tiles allow.
   const char *cl_env = getenv("SERT_GEMM_CLUSTER");
-  const bool cluster2 = epi.mode == TC_EPI_STORE && m_tiles >= 8 && (m_tiles % 2 == 0 || m_tiles >= 32) &&
-                        !(cl_env != nullptr && cl_env[0] == '0');
-  if (cluster2) {
-    TcMap mb_half;
-    if (make_map(B, N_total, Kt, ldb, BN / 2, &mb_half)) return -1;
-    const long long pair_work = ((m_tiles + 1) / 2) * n_tiles * args.k_slices;
-    const int clusters = (int)std::min<long long>(pair_work, sms / 2);
+  int cl = 1;
+  if (epi.mode == TC_EPI_STORE && m_tiles >= 8 && !(cl_env != nullptr && cl_env[0] == '0')) {
+    if (cl_env != nullptr && cl_env[0] == '4' && (m_tiles % 4 == 0 || m_tiles >= 64) && sms % 4 == 0) cl = 4;
+    else if (m_tiles % 2 == 0 || m_tiles >= 32) cl = 2;
+  }
+  if (cl > 1) {
+    TcMap mb_part;
+    if (make_map(B, N_total, Kt, ldb, BN / cl, &mb_part)) return -1;
+    const long long group_work = ((m_tiles + cl - 1) / cl) * n_tiles * args.k_slices;
+    const int clusters = (int)std::min<long long>(group_work, sms / cl);
     cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3(2 * clusters);
+    cfg.gridDim = dim3(cl * clusters);
     cfg.blockDim = dim3(NUM_THREADS);
     cfg.dynamicSmemBytes = SMEM_BYTES;
     cfg.stream = st;
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    attr[0].val.clusterDim.x = cl; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    SERT_CUDA(cudaLaunchKernelEx(&cfg, gemm_tc_kernel<false, TC_EPI_STORE, 2>, ma, mb_half, args));
+    if (cl == 4) SERT_CUDA(cudaLaunchKernelEx(&cfg, gemm_tc_kernel<false, TC_EPI_STORE, 4>, ma, mb_part, args));
+    else SERT_CUDA(cudaLaunchKernelEx(&cfg, gemm_tc_kernel<false, TC_EPI_STORE, 2>, ma, mb_part, args));
     count_launch();
     return 0;
   }

@@ -64,21 +64,26 @@ def test_cluster_multicast_layout_is_exact():
         np.testing.assert_allclose(got, ref, rtol=1e-5, atol=1e-3)
 
 
-@pytest.mark.parametrize('m,n,k', [(2048, 1000, 192), (4200, 300, 640), (1100, 513, 1000), (1024, 256, 64)])
+@pytest.mark.parametrize('m,n,k', [(2048, 1000, 192), (4200, 300, 640), (1100, 513, 1000), (1024, 256, 64),
+                                   (8300, 257, 128), (1280, 2000, 320)])
 def test_cluster_multicast_equals_single_cta_tiles(m, n, k):
-    """The two-CTA cluster schedule changes where operand tiles come from, not the arithmetic: bit-identical outputs
-    with SERT_GEMM_CLUSTER=0 (even, odd (33) and few (8, 9) m-tiles; ragged n; K of 1, 3, 10, 16 blocks)."""
+    """The cluster schedules (pairs by default, quads with SERT_GEMM_CLUSTER=4) change where operand tiles come
+    from, not the arithmetic: bit-identical outputs with SERT_GEMM_CLUSTER=0 (16 / 33 / 9 / 8 / 65 / 10 m-tiles; ragged
+    n; K of 1 to 16 blocks)."""
     import os
     rng = np.random.default_rng(m + n + k)
     a = rng.standard_normal((m, k)).astype(np.float32)
     b = rng.standard_normal((n, k)).astype(np.float32)
     bias = rng.standard_normal(n).astype(np.float32)
     got = run(a, b, 3, bias)
-    os.environ['SERT_GEMM_CLUSTER'] = '0'
     try:
+        os.environ['SERT_GEMM_CLUSTER'] = '0'
         plain = run(a, b, 3, bias)
+        os.environ['SERT_GEMM_CLUSTER'] = '4'
+        quads = run(a, b, 3, bias)
     finally:
         del os.environ['SERT_GEMM_CLUSTER']
     np.testing.assert_array_equal(got, plain)
+    np.testing.assert_array_equal(quads, plain)
     ref = a.astype(np.float64) @ b.astype(np.float64).T + bias
     assert np.abs(got - ref).max() < 6e-5 * np.sqrt(k)
