@@ -580,9 +580,15 @@ def run_scoring(sc, label, rank, world, barrier, cpu):
         dist.all_reduce(sms, op=dist.ReduceOp.MAX)
     ms = float(sms.item())
     # e2e: host queries in, host lists out (H2D of the queries, D2H of the lists inside the timed region)
+    # (page-locked host buffers, as the training e2e: the copies run at PCIe speed)
+    qs_pin = torch.from_numpy(qs).pin_memory()
+    out_pin = (torch.empty((sc['Q'], sc['k']), dtype=torch.int32).pin_memory(),
+               torch.empty((sc['Q'], sc['k']), dtype=torch.float32).pin_memory())
+    out_np = (out_pin[0].numpy(), out_pin[1].numpy())
+    scorer.topk(qs_pin.numpy(), sc['k'], out=out_np)
     barrier()
     t0 = time.perf_counter()
-    idx_host, score_host = scorer.topk(qs, sc['k'])
+    idx_host, score_host = scorer.topk(qs_pin.numpy(), sc['k'], out=out_np)
     e2e_s = time.perf_counter() - t0
     te = torch.tensor([e2e_s], dtype=torch.float64, device='cuda')
     if world > 1:

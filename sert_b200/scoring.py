@@ -72,13 +72,20 @@ class EntityScorer(object):
         except Exception:
             pass
 
-    def topk(self, queries, k, normalise_queries=False):
-        """queries (Q,d) host float32 -> (idx (Q,k) int32 global row ids, score (Q,k) float32), best first."""
+    def topk(self, queries, k, normalise_queries=False, out=None):
+        """queries (Q,d) host float32 -> (idx (Q,k) int32 global row ids, score (Q,k) float32), best first.
+        ``out`` = (idx, score) arrays to fill; with page-locked ``queries`` / ``out`` (e.g. numpy views of pinned torch
+        tensors) the two copies run at PCIe speed instead of through the driver's staging buffers."""
         queries = np.ascontiguousarray(queries, dtype=np.float32)
         assert queries.ndim == 2 and queries.shape[1] == self.d
         Q = queries.shape[0]
-        idx = np.empty((Q, k), dtype=np.int32)
-        score = np.empty((Q, k), dtype=np.float32)
+        if out is None:
+            idx = np.empty((Q, k), dtype=np.int32)
+            score = np.empty((Q, k), dtype=np.float32)
+        else:
+            idx, score = out
+            assert idx.shape == (Q, k) and idx.dtype == np.int32 and idx.flags['C_CONTIGUOUS']
+            assert score.shape == (Q, k) and score.dtype == np.float32 and score.flags['C_CONTIGUOUS']
         done = 0
         while done < Q:
             n = min(self.max_queries, Q - done)
@@ -172,9 +179,9 @@ class ShardedScorer(object):
         """(idx, score) of the GLOBAL matrix on every rank; asynchronous on the scorer's stream."""
         return self.local.topk_dev(queries_dev, k, normalise_queries)
 
-    def topk(self, queries, k, normalise_queries=False):
+    def topk(self, queries, k, normalise_queries=False, out=None):
         """Host in / host out through sert_scorer_topk_host (H2D of the queries, D2H of the merged lists)."""
-        return self.local.topk(queries, k, normalise_queries)
+        return self.local.topk(queries, k, normalise_queries, out=out)
 
     def close(self):
         self.local.close()
