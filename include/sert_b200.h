@@ -180,6 +180,25 @@ SERT_API int sert_model_set_entity_shard(sert_model *m, int32_t rank, int32_t wo
 SERT_API int sert_model_set_entity_shard_comm(sert_model *m, sert_comm *comm, int64_t entity_begin,
                                               int64_t entities_total);
 
+/* ---- table-sharded vector-space training ("shard rows of R and Eemb (+Adam state) across ranks") --
+ * One model at the global batch, `world` <= 8 ranks of one NVLink domain.  Every rank is fed the SAME batches (and
+ * draws the same negatives: same sert_config.seed) and computes the whole step's gradient, but streams the Adam
+ * update only over its own contiguous piece of the two representation tables, 1/world of the 24 B/parameter dense
+ * update (rank 0 also updates the projection matrix and bias).  The new parameters then reach every rank:
+ *   peer_stores = 0: in place, by grouped ncclBroadcast of the pieces behind the update kernels;
+ *   peer_stores = 1: by the update kernels' own stores into the next of two parameter buffers of every rank, mapped
+ *                    with CUDA IPC over NVLink (the update is the exchange; one 64-double ncclAllReduce of the loss's
+ *                    sum(theta^2) terms per step is also the barrier behind which the buffers swap).
+ * The reference trains on one device (sert/models.py:520-560 builds one update function); there is no counterpart.
+ * Collective: every rank calls it with its communicator; parameters and optimiser step are taken from rank 0.
+ * comm = NULL detaches.  The optimiser state of a rank is current only inside its piece:
+ * sert_model_gather_table_state makes it whole everywhere (checkpoints). */
+SERT_API int sert_model_set_table_shard_comm(sert_model *m, sert_comm *comm, int32_t peer_stores);
+SERT_API int sert_model_gather_table_state(sert_model *m);
+/* mode: 0 none, 1 broadcast, 2 peer stores; [own_begin, own_end): this rank's float range of the tables' table_floats */
+SERT_API int sert_model_table_shard_info(sert_model *m, int32_t *mode, int64_t *own_begin, int64_t *own_end,
+                                         int64_t *table_floats);
+
 /* ---- device-resident data set: replaces the theano.shared X/Y/W variables, sert/models.py:470-480 -- */
 /* x_dev (N,W) int32; labels either one-hot y_dev (N,) int32 (vector space, bin/train.py:186-245) or CSR
  * (indptr_dev int64 (N+1), indices_dev int32, data_dev f32; bin/prepare.py:593-597); w_dev (N,) f32 or NULL

@@ -14,6 +14,8 @@
 #include <string.h>
 
 #include <mutex>
+#include <string>
+#include <vector>
 
 namespace sert {
 
@@ -29,6 +31,7 @@ struct NcclApi {
                             cudaStream_t) = nullptr;
   ncclResult_t (*ReduceScatter)(const void *, void *, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t,
                                 cudaStream_t) = nullptr;
+  ncclResult_t (*Broadcast)(const void *, void *, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
   ncclResult_t (*GroupStart)() = nullptr;
   ncclResult_t (*GroupEnd)() = nullptr;
   ncclResult_t (*Send)(const void *, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
@@ -57,7 +60,7 @@ void load_nccl() {
   bool ok = bind(g_api.GetUniqueId, "ncclGetUniqueId") && bind(g_api.CommInitRank, "ncclCommInitRank") &&
             bind(g_api.CommDestroy, "ncclCommDestroy") && bind(g_api.AllGather, "ncclAllGather") &&
             bind(g_api.AllReduce, "ncclAllReduce") && bind(g_api.ReduceScatter, "ncclReduceScatter") &&
-            bind(g_api.GroupStart, "ncclGroupStart") && bind(g_api.GroupEnd, "ncclGroupEnd") &&
+            bind(g_api.Broadcast, "ncclBroadcast") && bind(g_api.GroupStart, "ncclGroupStart") && bind(g_api.GroupEnd, "ncclGroupEnd") &&
             bind(g_api.Send, "ncclSend") && bind(g_api.Recv, "ncclRecv") &&
             bind(g_api.GetErrorString, "ncclGetErrorString") && bind(g_api.GetVersion, "ncclGetVersion");
   if (!ok) g_api.handle = nullptr;
@@ -101,6 +104,90 @@ int comm_all_reduce_sum_f32(sert_comm *c, float *buf, size_t count, cudaStream_t
   SERT_NCCL(g_api.AllReduce(buf, buf, count, ncclFloat32, ncclSum, static_cast<ncclComm_t>(c->nccl), st));
   ++c->collectives;
   c->bytes += count * 4;
+  return 0;
+}
+
+int comm_all_reduce_sum_f64(sert_comm *c, double *buf, size_t count, cudaStream_t st) {
+  SERT_REQUIRE(c != nullptr, "null communicator");
+  if (c->world == 1) return 0;
+  SERT_NCCL(g_api.AllReduce(buf, buf, count, ncclFloat64, ncclSum, static_cast<ncclComm_t>(c->nccl), st));
+  ++c->collectives;
+  c->bytes += count * 8;
+  return 0;
+}
+
+// In-place all-gather of unequal pieces: rank r's bytes [off[r], off[r] + len[r]) of `base` reach every rank (one
+// grouped ncclBroadcast per piece: NCCL fuses the group into one launch).
+int comm_gather_pieces(sert_comm *c, void *base, const size_t *off, const size_t *len, cudaStream_t st) {
+  SERT_REQUIRE(c != nullptr, "null communicator");
+  if (c->world == 1) return 0;
+  ncclComm_t comm = static_cast<ncclComm_t>(c->nccl);
+  SERT_NCCL(g_api.GroupStart());
+  for (int r = 0; r < c->world; ++r) {
+    if (len[r] == 0) continue;
+    char *piece = static_cast<char *>(base) + off[r];
+    SERT_NCCL(g_api.Broadcast(piece, piece, len[r], ncclInt8, r, comm, st));
+    c->bytes += len[r];
+  }
+  SERT_NCCL(g_api.GroupEnd());
+  ++c->collectives;
+  return 0;
+}
+
+int comm_broadcast(sert_comm *c, void *buf, size_t bytes, int root, cudaStream_t st) {
+  SERT_REQUIRE(c != nullptr && root >= 0 && root < c->world, "bad broadcast");
+  if (c->world == 1 || bytes == 0) return 0;
+  SERT_NCCL(g_api.Broadcast(buf, buf, bytes, ncclInt8, root, static_cast<ncclComm_t>(c->nccl), st));
+  ++c->collectives;
+  c->bytes += bytes;
+  return 0;
+}
+
+// Peer mappings of a cudaMalloc'ed buffer of every rank (CUDA IPC; the ranks are processes of one node whose GPUs
+// reach each other over NVLink): peers[r] = this process's address of rank r's buffer, peers[rank] = local.  The
+// 64-byte handles travel through one ncclAllGather.  Collective: every rank of the communicator calls it.
+int comm_map_peers(sert_comm *c, void *local, void **peers, cudaStream_t st) {
+  SERT_REQUIRE(c != nullptr && local != nullptr && peers != nullptr, "null argument");
+  for (int r = 0; r < c->world; ++r) peers[r] = nullptr;
+  peers[c->rank] = local;
+  if (c->world == 1) return 0;
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "unexpected IPC handle size");
+  cudaIpcMemHandle_t mine;
+  SERT_CUDA(cudaIpcGetMemHandle(&mine, local));
+  char *dev = nullptr;
+  SERT_CUDA(cudaMalloc(&dev, (size_t)c->world * sizeof(mine)));
+  std::vector<cudaIpcMemHandle_t> all((size_t)c->world);
+  int rc = 0;
+  do {
+    if (cudaMemcpyAsync(dev + (size_t)c->rank * sizeof(mine), &mine, sizeof(mine), cudaMemcpyHostToDevice, st) != cudaSuccess ||
+        comm_all_gather(c, dev + (size_t)c->rank * sizeof(mine), dev, sizeof(mine), st) != 0 ||
+        cudaMemcpyAsync(all.data(), dev, all.size() * sizeof(mine), cudaMemcpyDeviceToHost, st) != cudaSuccess ||
+        cudaStreamSynchronize(st) != cudaSuccess) {
+      rc = -1;
+      break;
+    }
+    for (int r = 0; r < c->world && rc == 0; ++r) {
+      if (r == c->rank) continue;
+      const cudaError_t e = cudaIpcOpenMemHandle(&peers[r], all[(size_t)r], cudaIpcMemLazyEnablePeerAccess);
+      if (e != cudaSuccess) {
+        set_error(std::string("cudaIpcOpenMemHandle (rank ") + std::to_string(r) + "): " + cudaGetErrorString(e));
+        (void)cudaGetLastError();
+        rc = -1;
+      }
+    }
+  } while (false);
+  cudaFree(dev);
+  if (rc != 0) {
+    for (int r = 0; r < c->world; ++r)
+      if (r != c->rank && peers[r] != nullptr) { cudaIpcCloseMemHandle(peers[r]); peers[r] = nullptr; }
+  }
+  return rc;
+}
+
+int comm_unmap_peers(sert_comm *c, void **peers) {
+  if (c == nullptr || peers == nullptr) return 0;
+  for (int r = 0; r < c->world; ++r)
+    if (r != c->rank && peers[r] != nullptr) { cudaIpcCloseMemHandle(peers[r]); peers[r] = nullptr; }
   return 0;
 }
 

@@ -107,6 +107,7 @@ struct ParamSegment {
   const uint32_t *flags; // per-row touched stamps or nullptr (= always read the gradient)
 };
 constexpr int kMaxSegments = 4;
+constexpr int kMaxPeers = 7;        // other ranks of a table-shard group (one NVSwitch domain: 8 GPUs)
 constexpr int kSumsqSlots = 64;     // acc[0] = data-loss sum, acc[1..64] = partial sums of theta^2
 struct OptimArgs {
   float *theta, *s1, *s2, *grad;   // arena arrays of `total` floats
@@ -133,6 +134,16 @@ struct OptimArgs {
   // 1: s1 / s2 are arrays of bfloat16 (sert_config.dtype_mode 1), written with stochastic rounding -- 16 instead of
   // 24 bytes per parameter and step.  Element offsets are the same as for theta.
   int state_bf16 = 0;
+  // Table shards (vs_train_step with sert_model_set_table_shard_comm): every rank computes the whole batch's gradient,
+  // but updates only the 16-byte chunks [own_lo4, own_hi4) of the row-stamped tables (and the dense tensors iff
+  // own_dense); a touched chunk of another rank's shard only has its gradient zeroed.  The new theta goes to
+  // theta_out (nullptr: in place) and to the same offset of every peer_theta[p] -- the other ranks' copies, written
+  // over NVLink by this kernel's own stores, so the update IS the exchange.
+  long long own_lo4 = 0, own_hi4 = 0x7fffffffffffffffll;
+  int own_dense = 1;
+  float *theta_out = nullptr;
+  int n_peers = 0;
+  float *peer_theta[kMaxPeers] = {};
 };
 
 // Adam + L2 of the hot word rows (gradient = sum of the private copies), see opt_kernels.cu
@@ -148,6 +159,11 @@ struct HotUpdateArgs {
   int counted;                     // 1: this rank reports the table's norm in the loss
   int state_bf16 = 0;              // as OptimArgs::state_bf16
   uint32_t stamp = 0;              // seeds the stochastic rounding
+  // table shards, as in OptimArgs: rows outside [own_lo4, own_hi4) only have their gradient copies zeroed
+  long long own_lo4 = 0, own_hi4 = 0x7fffffffffffffffll;
+  float *theta_out = nullptr;
+  int n_peers = 0;
+  float *peer_theta[kMaxPeers] = {};
 };
 int launch_hot_update(const HotUpdateArgs &h, cudaStream_t st);
 // flags[hot_ids[s]] = value  (kHotRowMark to hand the rows to launch_hot_update, 0 to hand them back)

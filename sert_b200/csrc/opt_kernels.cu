@@ -96,7 +96,8 @@ __device__ __forceinline__ void store_state4(float *base, long long i4, const fl
 template <bool ADAM, int PHASE, bool S16>
 __global__ void __launch_bounds__(256) dense_update_kernel(OptimArgs a) {
   const long long total4 = a.total >> 2;
-  float4 *__restrict__ th4 = reinterpret_cast<float4 *>(a.theta);
+  const float4 *__restrict__ th4 = reinterpret_cast<const float4 *>(a.theta);
+  float4 *__restrict__ out4 = reinterpret_cast<float4 *>(a.theta_out != nullptr ? a.theta_out : a.theta);
   float4 *__restrict__ g4 = reinterpret_cast<float4 *>(a.grad);
   float sumsq = 0.f;
 
@@ -130,9 +131,13 @@ __global__ void __launch_bounds__(256) dense_update_kernel(OptimArgs a) {
         skip = (flag == kHotRowMark);       // updated by hot_update_kernel on the side stream
       }
       const bool mine = PHASE == 0 ? true : PHASE == 3 ? (sg.flags != nullptr) : (sg.flags == nullptr);
+      // table shards: this rank updates its own slice of the tables (and the dense tensors iff own_dense)
+      const bool owned = sg.flags != nullptr ? (i4 >= a.own_lo4 && i4 < a.own_hi4) : (a.own_dense != 0);
       sgi[ch] = s;
-      act[ch] = live && mine && !skip;
+      act[ch] = live && mine && !skip && owned;
       touched[ch] = act[ch] && tch;
+      // another rank's chunk: this replica's gradient of it is dropped (the owner computed the same one)
+      if (live && mine && !skip && !owned && tch) g4[i4] = make_float4(0.f, 0.f, 0.f, 0.f);
       if (act[ch]) {
         p[ch] = th4[i4];
         load_state4<S16>(a.s1, i4, v1[ch]);
@@ -158,7 +163,9 @@ __global__ void __launch_bounds__(256) dense_update_kernel(OptimArgs a) {
       for (int j = 0; j < 4; ++j) {
         update_element<ADAM>(pv[j], v1[ch][j], v2[ch][j], gv[j] + l2 * pv[j], a.c0, a.c1, a.c2, a.c3);
       }
-      th4[i4] = make_float4(pv[0], pv[1], pv[2], pv[3]);
+      const float4 fresh = make_float4(pv[0], pv[1], pv[2], pv[3]);
+      out4[i4] = fresh;
+      for (int pr = 0; pr < a.n_peers; ++pr) reinterpret_cast<float4 *>(a.peer_theta[pr])[i4] = fresh;   // NVLink stores
       if (PHASE == 4 && a.transposed != nullptr && s == a.transposed_segment) {
         // keep the (cols, rows) copy of the projection matrix current for the next step's back-projection
         const unsigned int el = (unsigned int)(e - sg.offset);
@@ -272,10 +279,18 @@ __global__ void __launch_bounds__(128) hot_update_kernel(HotUpdateArgs h) {
     for (int r = 0; r < kHotReplicas; ++r)
       v[r] = __ldcg(reinterpret_cast<const float4 *>(h.hot_acc + ((size_t)r * kMaxHotRows + s) * h.d) + c);
     const size_t i4 = ((size_t)h.table_offset + (size_t)row * h.d) / 4 + c;
+    if ((long long)i4 < h.own_lo4 || (long long)i4 >= h.own_hi4) {
+      // table shards: another rank updates this row; this replica's gradient copies are dropped
+      reinterpret_cast<float4 *>(h.grad)[i4] = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+      for (int r = 0; r < kHotReplicas; ++r)
+        reinterpret_cast<float4 *>(h.hot_acc + ((size_t)r * kMaxHotRows + s) * h.d)[c] = make_float4(0.f, 0.f, 0.f, 0.f);
+      continue;
+    }
     float4 g = __ldcg(reinterpret_cast<const float4 *>(h.grad) + i4);
 #pragma unroll
     for (int r = 0; r < kHotReplicas; ++r) { g.x += v[r].x; g.y += v[r].y; g.z += v[r].z; g.w += v[r].w; }
-    const float4 p = reinterpret_cast<float4 *>(h.theta)[i4];
+    const float4 p = reinterpret_cast<const float4 *>(h.theta)[i4];
     float v1[4], v2[4];
     load_state4<S16>(h.s1, (long long)i4, v1);
     load_state4<S16>(h.s2, (long long)i4, v2);
@@ -285,7 +300,9 @@ __global__ void __launch_bounds__(128) hot_update_kernel(HotUpdateArgs h) {
 #pragma unroll
     for (int j = 0; j < 4; ++j)
       update_element<true>(pv[j], v1[j], v2[j], gv[j] + h.l2_scale * pv[j], h.c0, h.c1, h.c2, h.c3);
-    reinterpret_cast<float4 *>(h.theta)[i4] = make_float4(pv[0], pv[1], pv[2], pv[3]);
+    const float4 fresh = make_float4(pv[0], pv[1], pv[2], pv[3]);
+    reinterpret_cast<float4 *>(h.theta_out != nullptr ? h.theta_out : h.theta)[i4] = fresh;
+    for (int pr = 0; pr < h.n_peers; ++pr) reinterpret_cast<float4 *>(h.peer_theta[pr])[i4] = fresh;
     store_state4<S16>(h.s1, (long long)i4, v1, (uint32_t)(i4 * 4), h.stamp, 0u);
     store_state4<S16>(h.s2, (long long)i4, v2, (uint32_t)(i4 * 4), h.stamp, 1u);
     reinterpret_cast<float4 *>(h.grad)[i4] = make_float4(0.f, 0.f, 0.f, 0.f);

@@ -195,8 +195,10 @@ __global__ void __launch_bounds__(256) rescore_kernel(const float *__restrict__ 
 __global__ void __launch_bounds__(256) prep_queries_kernel(const float *__restrict__ Qm, int Q, int products, int d, int Kp,
                                                            __nv_bfloat16 *__restrict__ split, float ent_norm_max,
                                                            float ent_err_max, float *__restrict__ margin,
-                                                           unsigned long long *__restrict__ tau, int *__restrict__ count) {
+                                                           unsigned long long *__restrict__ tau, int *__restrict__ count,
+                                                           int *__restrict__ flag) {
   const int q = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (blockIdx.x == 0 && threadIdx.x == 0) *flag = 0;        // the seeded sweep's verdict word (no memset node of its own)
   if (q >= Q) return;
   __nv_bfloat16 *row = split + (size_t)q * 3 * Kp;
   float e2 = 0.f, h2 = 0.f;
@@ -890,7 +892,7 @@ int topk_sweep(const TopkState &s, const float *queries_dev, int Q, int k, int32
     // split rows [hi|hi|mid] of the queries, their coarse-score margins, list state reset
     prep_queries_kernel<<<cdiv(Q, 8), 256, 0, st>>>(queries_dev, Q, s.d * s.coarse_blocks, s.d, s.kt / s.terms, s.q_split,
                                                     s.ent_norm_max, s.coarse_blocks == 2 ? s.ent_err2_max : s.ent_err_max,
-                                                    s.margin, s.tau, s.count);
+                                                    s.margin, s.tau, s.count, s.overflow);
     SERT_LAUNCH_CHECK();
   }
   int overflow = 1;
@@ -905,8 +907,7 @@ int topk_sweep(const TopkState &s, const float *queries_dev, int Q, int k, int32
     const SweepPlan plan = topk_plan(s.rows, k, s.cap);
     if (allow_seeded && s.seeded && warps >= 1 && s.rows > 0 && (plan.seeded || s.rows <= s.cap / 2)) {
       // Seeded one-launch sweep: sample GEMM -> tau -> ONE GEMM over the shard -> finalize (select, re-score, sort).
-      SERT_CUDA(cudaMemsetAsync(s.overflow, 0, sizeof(int), st));
-      trace.mark("prep");
+      trace.mark("prep");                   // prep_queries_kernel also cleared the verdict word
       TcEpilogue ep;
       const int depth = s.coarse_blocks * (s.kt / s.terms);     // leading block(s) of both split operands
       if (plan.seeded) {

@@ -100,6 +100,18 @@ struct sert_model {
   sert_exchange_fn exchange = nullptr;
   void *exchange_ctx = nullptr;
   sert_comm *comm = nullptr;       // set: the exchanges are NCCL collectives issued by the library itself (comm.cu)
+  // table-sharded vector-space step (sert_model_set_table_shard_comm): this rank updates the 16-byte chunks
+  // [table_lo4[rank], table_lo4[rank + 1]) of the two tables (rank 0 also the dense tensors) for the whole group.
+  // Mode 1: the updated pieces are broadcast in place by NCCL.  Mode 2: theta lives in two library-owned buffers that
+  // every rank maps (CUDA IPC); the update kernels store the new values into the NEXT buffer of every rank over
+  // NVLink, and the buffers swap behind the step's one all-reduce.
+  sert_comm *table_comm = nullptr;
+  int table_mode = 0;
+  long long table_lo4[kMaxPeers + 2] = {};
+  float *arena_theta = nullptr;    // theta's place in the arena (mode 2 moves m.theta out of it)
+  float *pp[2] = {nullptr, nullptr};
+  void *pp_peers[2][kMaxPeers + 1] = {};
+  int pp_cur = 0;
   void *rank_scratch = nullptr;    // sert_ll_rank_queries: sort keys and per-query sums (library-owned, grown on demand)
   size_t rank_scratch_bytes = 0;
   float *xstats = nullptr;         // [kMaxShards][2][B*W] gathered (row max, row sum)
@@ -300,7 +312,42 @@ static OptimArgs optim_args(sert_model &m, float *loss_out) {
   a.acc = m.acc; a.loss_out = loss_out;
   a.inv_B = 1.0f / B;
   a.reg_coeff = m.cfg.lambda > 0.f ? m.cfg.lambda / (2.0f * B) : 0.f;
+  if (m.table_comm != nullptr) {
+    const int r = m.table_comm->rank;
+    a.own_lo4 = m.table_lo4[r]; a.own_hi4 = m.table_lo4[r + 1];
+    a.own_dense = r == 0 ? 1 : 0;
+    if (m.table_mode == 2) {
+      const int next = m.pp_cur ^ 1;
+      a.theta_out = m.pp[next];
+      for (int p = 0; p < m.table_comm->world; ++p)
+        if (p != r) a.peer_theta[a.n_peers++] = static_cast<float *>(m.pp_peers[next][p]);
+    }
+  }
   return a;
+}
+
+// Table shards: what follows the update kernels of a step on the model's stream.  Mode 1 broadcasts every owner's
+// piece of theta in place.  Both modes sum the owners' partial sum(theta^2) (the loss is finalised after this), and
+// in mode 2 that all-reduce is also the step's barrier: it completes on a rank only after every rank has finished
+// its update kernels, i.e. after every store into this rank's next buffer has landed; then the buffers swap.
+static int table_exchange(sert_model &m, double *acc) {
+  sert_comm *c = m.table_comm;
+  if (m.table_mode == 1) {
+    size_t off[kMaxPeers + 1], len[kMaxPeers + 1];
+    for (int r = 0; r < c->world; ++r) {
+      off[r] = (size_t)m.table_lo4[r] * 16;
+      len[r] = (size_t)(m.table_lo4[r + 1] - m.table_lo4[r]) * 16;
+    }
+    if (comm_gather_pieces(c, m.theta, off, len, m.st)) return -1;
+    const long long dense0 = m.off[SERT_PARAM_DENSE_W];
+    if (comm_broadcast(c, m.theta + dense0, (size_t)(m.total - dense0) * sizeof(float), 0, m.st)) return -1;
+  }
+  if (comm_all_reduce_sum_f64(c, acc + 1, kSumsqSlots, m.st)) return -1;
+  if (m.table_mode == 2) {
+    m.pp_cur ^= 1;
+    m.theta = m.pp[m.pp_cur];
+  }
+  return 0;
 }
 
 static int pick_split_k(int M, int N, int K) {
@@ -330,7 +377,7 @@ static int timed_update(sert_model &m, const OptimArgs &o, bool adam) {
   for (int sg = 0; sg < o.num_segments; ++sg)
     if (o.phase == 0 || (o.phase == 3) == (o.seg[sg].flags != nullptr)) params += o.seg[sg].count;
   m.prof_bytes = (o.state_bf16 ? 16.0 : 24.0) * (double)params;   // theta rw + two state arrays rw
-  if (rc || o.phase != 0) return rc;
+  if (rc || o.phase != 0 || o.no_finalize) return rc;
   return launch_finalize_train(o.acc, o.loss_out, o.inv_B, o.reg_coeff, m.st);
 }
 
@@ -404,6 +451,9 @@ static int vs_train_step(sert_model &m, const int32_t *x, const int32_t *y, cons
   const int fused = m.use_fused ? launch_vs_fused(f, m.WpT, !m.wpt_valid, m.use_fused, st) : 1;
   if (fused == 0) m.wpt_valid = true;
   if (fused < 0) return -1;
+  const bool sharded = m.table_comm != nullptr;
+  // table shards: the projection matrix arrives from rank 0, so only rank 0's update can keep the transposed copy
+  if (sharded && m.table_comm->rank != 0) m.wpt_valid = false;
   if (m.want_fused_event) SERT_CUDA(cudaEventRecord(m.ev_fused, st));   // the previous step's loss is final here
   if (lazy) { m.pending_bank = -1; m.pending_loss = nullptr; }      // the tile kernel has taken care of it
   if (fused == 1) {
@@ -439,7 +489,10 @@ static int vs_train_step(sert_model &m, const int32_t *x, const int32_t *y, cons
   o.c0 = adam_alpha_f32(m.step); o.c1 = 0.9f; o.c2 = 0.999f; o.c3 = 1e-8f;
   if (!overlap) {
     m.wpt_valid = false;
-    return timed_update(m, o, true);
+    if (!sharded) return timed_update(m, o, true);
+    o.no_finalize = true;
+    if (timed_update(m, o, true) || table_exchange(m, acc)) return -1;
+    return launch_finalize_train(acc, loss_out, o.inv_B, o.reg_coeff, st);
   }
   OptimArgs dense = o;
   dense.phase = 4;
@@ -467,11 +520,14 @@ static int vs_train_step(sert_model &m, const int32_t *x, const int32_t *y, cons
       h.l2_scale = o.l2_scale; h.c0 = o.c0; h.c1 = o.c1; h.c2 = o.c2; h.c3 = o.c3;
       h.acc = acc; h.counted = 1;
       h.state_bf16 = o.state_bf16; h.stamp = o.stamp;
+      h.own_lo4 = o.own_lo4; h.own_hi4 = o.own_hi4; h.theta_out = o.theta_out; h.n_peers = o.n_peers;
+      for (int p = 0; p < o.n_peers; ++p) h.peer_theta[p] = o.peer_theta[p];
       if (launch_hot_update(h, side)) return -1;
     }
     SERT_CUDA(cudaEventRecord(m.ev_join, side));
     if (timed_update(m, tables, true)) return -1;     // profile mode: events around the table stream, in situ
     SERT_CUDA(cudaStreamWaitEvent(st, m.ev_join, 0));
+    if (sharded && table_exchange(m, acc)) return -1;
     m.pending_bank = bank;
     m.pending_loss = loss_out;
     return 0;
@@ -479,6 +535,11 @@ static int vs_train_step(sert_model &m, const int32_t *x, const int32_t *y, cons
   SERT_CUDA(cudaEventRecord(m.ev_join, side));
   if (timed_update(m, tables, true)) return -1;
   SERT_CUDA(cudaStreamWaitEvent(st, m.ev_join, 0));
+  if (sharded) {                  // the loss waits for the other ranks' share of sum(theta^2)
+    dense.loss_out = nullptr;
+    if (launch_adam(dense, st) || table_exchange(m, acc)) return -1;
+    return launch_finalize_train(acc, loss_out, o.inv_B, o.reg_coeff, st);
+  }
   dense.ticket = reinterpret_cast<unsigned int *>(m.acc + kAccDoubles - 4);
   return launch_adam(dense, st);
 }
@@ -817,6 +878,8 @@ int sert_model_create(const sert_config *cfg, void *arena_dev, size_t arena_byte
   return 0;
 }
 
+static void table_shard_release(sert_model *m);
+
 int sert_model_destroy(sert_model *m) {
   if (m) {
     cudaStreamSynchronize(m->st);
@@ -837,6 +900,7 @@ int sert_model_destroy(sert_model *m) {
       if (m->ev_loss[q]) cudaEventDestroy(m->ev_loss[q]);
     if (m->pin_loss) cudaFreeHost(m->pin_loss);
     if (m->rank_scratch) cudaFree(m->rank_scratch);
+    table_shard_release(m);
     delete m;
   }
   return 0;
@@ -985,6 +1049,119 @@ int sert_model_set_entity_shard_comm(sert_model *m, sert_comm *comm, int64_t ent
   SERT_REQUIRE(m && comm, "null argument");
   m->comm = comm;
   return sert_model_set_entity_shard(m, comm->rank, comm->world, entity_begin, entities_total, nccl_exchange, m);
+}
+
+static void table_shard_release(sert_model *m) {
+  if (m->table_comm == nullptr) return;
+  if (m->table_mode == 2) {
+    // theta returns to its place in the arena
+    cudaMemcpyAsync(m->arena_theta, m->theta, (size_t)m->total * sizeof(float), cudaMemcpyDeviceToDevice, m->st);
+    cudaStreamSynchronize(m->st);
+    m->theta = m->arena_theta;
+    for (int b = 0; b < 2; ++b) {
+      comm_unmap_peers(m->table_comm, m->pp_peers[b]);
+      if (m->pp[b]) cudaFree(m->pp[b]);
+      m->pp[b] = nullptr;
+    }
+  }
+  m->table_comm = nullptr;
+  m->table_mode = 0;
+}
+
+int sert_model_set_table_shard_comm(sert_model *m, sert_comm *comm, int32_t peer_stores) {
+  SERT_REQUIRE(m != nullptr, "null model");
+  SERT_REQUIRE(is_vs(m->cfg) && m->cfg.inference_only == 0, "table shards are for trainable vector-space models");
+  if (flush_pending(*m)) return -1;
+  SERT_CUDA(cudaStreamSynchronize(m->st));
+  if (m->st2) SERT_CUDA(cudaStreamSynchronize(m->st2));
+  table_shard_release(m);
+  if (comm == nullptr) return 0;
+  SERT_REQUIRE(comm->world <= kMaxPeers + 1, "table shards span at most 8 ranks (one NVLink domain)");
+  const long long tables4 = m->off[SERT_PARAM_DENSE_W] / 4;      // the two tables come first in the arena (carve)
+  SERT_REQUIRE(m->off[SERT_PARAM_ENTITY_REPR] < m->off[SERT_PARAM_DENSE_W] &&
+               m->off[SERT_PARAM_WORD_REPR] < m->off[SERT_PARAM_DENSE_W] &&
+               m->off[SERT_PARAM_DENSE_W] < m->off[SERT_PARAM_DENSE_B], "unexpected parameter layout");
+  for (int r = 0; r <= comm->world; ++r) {
+    long long b = tables4 * r / comm->world;
+    if (r != comm->world) b &= ~63ll;                            // 1 KB pieces
+    m->table_lo4[r] = b;
+  }
+  // one model: every rank starts from rank 0's parameters, optimiser state and step, and draws rank 0's negatives
+  if (comm_broadcast(comm, m->theta, (size_t)m->total * sizeof(float), 0, m->st)) return -1;
+  const size_t state_el = m->cfg.dtype_mode == 1 ? 2 : 4;
+  if (comm_broadcast(comm, m->s1, (size_t)m->total * state_el, 0, m->st)) return -1;
+  if (comm_broadcast(comm, m->s2, (size_t)m->total * state_el, 0, m->st)) return -1;
+  {
+    unsigned long long host[3] = {(unsigned long long)m->cfg.seed, (unsigned long long)m->sample_calls,
+                                  (unsigned long long)m->step};
+    unsigned long long *dev = nullptr;
+    SERT_CUDA(cudaMalloc(&dev, sizeof(host)));
+    const bool ok = cudaMemcpyAsync(dev, host, sizeof(host), cudaMemcpyHostToDevice, m->st) == cudaSuccess &&
+                    comm_broadcast(comm, dev, sizeof(host), 0, m->st) == 0 &&
+                    cudaMemcpyAsync(host, dev, sizeof(host), cudaMemcpyDeviceToHost, m->st) == cudaSuccess &&
+                    cudaStreamSynchronize(m->st) == cudaSuccess;
+    cudaFree(dev);
+    SERT_REQUIRE(ok, "table shards: could not broadcast the sampler state");
+    m->cfg.seed = (decltype(m->cfg.seed))host[0];
+    m->sample_calls = host[1];
+    m->step = (int64_t)host[2];
+  }
+  m->wpt_valid = false;
+  if (peer_stores) {
+    m->arena_theta = m->theta;
+    for (int b = 0; b < 2; ++b) {
+      SERT_CUDA(cudaMalloc(&m->pp[b], (size_t)m->total * sizeof(float)));
+      SERT_CUDA(cudaMemcpyAsync(m->pp[b], m->theta, (size_t)m->total * sizeof(float), cudaMemcpyDeviceToDevice, m->st));
+    }
+    int rc = 0;
+    for (int b = 0; b < 2 && rc == 0; ++b) rc = comm_map_peers(comm, m->pp[b], m->pp_peers[b], m->st);
+    if (rc) {
+      for (int b = 0; b < 2; ++b) {
+        comm_unmap_peers(comm, m->pp_peers[b]);
+        cudaFree(m->pp[b]);
+        m->pp[b] = nullptr;
+      }
+      return -1;
+    }
+    m->pp_cur = 0;
+    m->theta = m->pp[0];
+  }
+  m->table_comm = comm;
+  m->table_mode = peer_stores ? 2 : 1;
+  SERT_CUDA(cudaStreamSynchronize(m->st));
+  return 0;
+}
+
+// Table shards: each rank's optimiser state is current only inside its own piece; this makes s1 / s2 whole on every
+// rank (for a checkpoint).  Collective.
+int sert_model_gather_table_state(sert_model *m) {
+  SERT_REQUIRE(m != nullptr, "null model");
+  if (m->table_comm == nullptr) return 0;
+  if (flush_pending(*m)) return -1;
+  sert_comm *c = m->table_comm;
+  const size_t el = m->cfg.dtype_mode == 1 ? 2 : 4;
+  size_t off[kMaxPeers + 1], len[kMaxPeers + 1];
+  for (int r = 0; r < c->world; ++r) {
+    off[r] = (size_t)m->table_lo4[r] * 4 * el;
+    len[r] = (size_t)(m->table_lo4[r + 1] - m->table_lo4[r]) * 4 * el;
+  }
+  const size_t dense0 = (size_t)m->off[SERT_PARAM_DENSE_W];
+  for (float *state : {m->s1, m->s2}) {
+    if (comm_gather_pieces(c, state, off, len, m->st)) return -1;
+    if (comm_broadcast(c, reinterpret_cast<char *>(state) + dense0 * el, ((size_t)m->total - dense0) * el, 0, m->st)) return -1;
+  }
+  SERT_CUDA(cudaStreamSynchronize(m->st));
+  return 0;
+}
+
+int sert_model_table_shard_info(sert_model *m, int32_t *mode, int64_t *own_begin, int64_t *own_end, int64_t *table_floats) {
+  SERT_REQUIRE(m != nullptr, "null model");
+  if (mode) *mode = m->table_mode;
+  const int r = m->table_comm ? m->table_comm->rank : 0;
+  if (own_begin) *own_begin = m->table_comm ? m->table_lo4[r] * 4 : 0;
+  if (own_end) *own_end = m->table_comm ? m->table_lo4[r + 1] * 4 : m->off[SERT_PARAM_DENSE_W];
+  if (table_floats) *table_floats = m->off[SERT_PARAM_DENSE_W];
+  return 0;
 }
 
 int sert_model_profile(sert_model *m, int enable) {

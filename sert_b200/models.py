@@ -685,8 +685,15 @@ class VectorSpaceLanguageModel(VectorSpaceLanguageModelBase):
                  regularization_lambda,
                  training_set,
                  validation_set,
-                 dense_init=None, device=None, seed=None, loss_slots=1 << 16, optimizer_state_dtype='float32'):
-        """``optimizer_state_dtype``: 'float32' (the reference's arithmetic; parity mode) or 'bfloat16' (perf mode of
+                 dense_init=None, device=None, seed=None, loss_slots=1 << 16, optimizer_state_dtype='float32',
+                 table_shard=None, table_shard_peer_stores=True):
+        """``table_shard``: a ``sert_b200.comm.Communicator`` (one process per GPU of one NVLink domain): ONE model at
+        the global batch whose Adam stream over the two tables is split over the ranks (include/sert_b200.h:
+        sert_model_set_table_shard_comm).  Every rank must be fed the same batches; parameters, optimiser state and
+        the negative sampler are taken from rank 0.  ``table_shard_peer_stores``: the update kernels write the new
+        parameters into every rank's copy over NVLink (CUDA IPC); False = grouped NCCL broadcasts.
+
+        ``optimizer_state_dtype``: 'float32' (the reference's arithmetic; parity mode) or 'bfloat16' (perf mode of
         BASELINE.json configs[1]: Adam's m and v stored as bfloat16 with stochastic rounding, 16 instead of 24 bytes
         per parameter and step; parameters, gradients and every forward/backward value stay float32)."""
         assert optimizer_state_dtype in ('float32', 'bfloat16')
@@ -723,7 +730,24 @@ class VectorSpaceLanguageModel(VectorSpaceLanguageModelBase):
         self._native.set_tensor(N.PARAM_DENSE_B, dense_init[1])
         self._attach_datasets()
         self.set_hot_words(self.pick_hot_words())
+        self.table_shard = table_shard
+        if table_shard is not None:
+            N.check(self._native.lib.sert_model_set_table_shard_comm(
+                self._native.handle, table_shard.handle, int(bool(table_shard_peer_stores))))
         self._create_functions()
+
+    def table_shard_info(self):
+        """(mode, own_begin, own_end, table_floats): mode 0 none / 1 broadcast / 2 peer stores; this rank updates the
+        floats [own_begin, own_end) of the two tables' table_floats."""
+        mode, b, e, n = N.ctypes.c_int32(0), N.c_int64(0), N.c_int64(0), N.c_int64(0)
+        N.check(self._native.lib.sert_model_table_shard_info(self._native.handle, N.ctypes.byref(mode), N.ctypes.byref(b),
+                                                             N.ctypes.byref(e), N.ctypes.byref(n)))
+        return mode.value, b.value, e.value, n.value
+
+    def get_checkpoint(self):
+        if self.table_shard is not None:      # each rank's Adam state is current only inside its own piece
+            N.check(self._native.lib.sert_model_gather_table_state(self._native.handle))
+        return super(VectorSpaceLanguageModel, self).get_checkpoint()
 
     def pick_hot_words(self):
         """Word ids whose gradient row receives so many additions per batch that they serialise in L2
