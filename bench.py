@@ -363,6 +363,9 @@ def run_ours(args, rank, world, local_rank):
     if isinstance(bf16_mode, dict) and 'error' not in bf16_mode:
         bf16_mode['float32_rerun_control'] = leg(run_bf16_state_mode, p, cfg, steps, warm, repeats, first_losses, losses,
                                                  rank, world, barrier, state_dtype='float32')
+    table_shards = None
+    if world > 1:
+        table_shards = leg(run_table_shards, cfg, steps, warm, repeats, ms_max / timed_steps, first_losses, rank, world, barrier)
     scoring = leg(run_scoring, CFG4, 'BASELINE.json configs[3]', rank, world, barrier, cpu=False)
     scoring_small = leg(run_scoring, CFG3, 'BASELINE.json configs[2]', rank, world, barrier, cpu=(rank == 0))
 
@@ -407,6 +410,8 @@ def run_ours(args, rank, world, local_rank):
             'scoring_small_frac': ((scoring_small or {}).get('roofline') or {}).get('frac'),
             'scoring_small_lists_identical': (scoring_small or {}).get('lists_identical'),
             'loglinear_stress_ms': (loglinear_stress or {}).get('ms_per_step'),
+            'table_shards_ms': ((table_shards or {}).get('peer_stores') or {}).get('ms_per_step'),
+            'table_shards': table_shards,
             'bf16_state_mode': bf16_mode,
             'product_search_shape': product_search,
             'loglinear': loglinear,
@@ -488,6 +493,103 @@ def run_bf16_state_mode(p, cfg, steps, warm, repeats, f32_first_losses, f32_last
             'deviation_what': 'max relative difference of the per-batch training losses against the float32 run of '
                               'the identical step sequence (first pass / last timed pass)',
             'arena_mb': arena_mb}
+
+
+def run_table_shards(cfg, steps, warm, repeats, single_ms, single_first_losses, rank, world, barrier):
+    """SURVEY.md 8(e), vector-space training as ONE model over the N GPUs (strong scaling; the headline line stays N
+    independent replicas, weak).  Every rank is fed rank 0's batches and computes the step's gradient; the 24 B/param
+    Adam stream over the two tables is split into N pieces, and the new parameters reach the other ranks either through
+    the update kernels' own stores into every rank's next parameter buffer (CUDA IPC over NVLink: the update IS the
+    exchange, one 512-byte ncclAllReduce per step is the barrier) or through grouped ncclBroadcast calls."""
+    import torch
+    import torch.distributed as dist
+    from sert_b200 import _native as N, models
+    from sert_b200.comm import Communicator
+    n_batches = steps + warm
+    p = make_problem(0, n_batches)                       # the same batches, negatives and initial values on every rank
+    neg_dev = torch.from_numpy(p['neg']).cuda()
+    order = np.arange(n_batches, dtype=np.int64)
+    comm = Communicator.from_torch_distributed()
+    out = {'workload': WORKLOAD + '; ONE model, global batch %d, table pieces over %d ranks' % (cfg['B'], world),
+           'scaling': 'strong', 'single_gpu_ms_per_step': single_ms}
+    for label, peer in (('peer_stores', True), ('nccl_broadcast', False)):
+        model = models.VectorSpaceLanguageModel(
+            batch_size=cfg['B'], window_size=cfg['W'], num_negative_samples=cfg['k'],
+            representations_init=p['R'], entity_representations_init=p['Eemb'], regularization_lambda=cfg['lam'],
+            training_set=p['train'], validation_set=p['val'], dense_init=(p['Wp'], p['bp']),
+            loss_slots=max(1024, n_batches), table_shard=comm, table_shard_peer_stores=peer)
+        nat, lib = model._native, model._native.lib
+        mode, own_b, own_e, table_floats = model.table_shard_info()
+
+        def train(lo, hi):
+            N.check(lib.sert_train_batches(nat.handle, N.host_ptr(order[lo:hi]), hi - lo,
+                                           N.c_void_p(neg_dev.data_ptr() + lo * cfg['B'] * cfg['k'] * 4), lo))
+
+        train(0, n_batches)
+        first = np.empty(n_batches, np.float32)
+        N.check(lib.sert_losses_fetch(nat.handle, 0, n_batches, N.host_ptr(first)))
+        info0 = comm.info()
+        barrier()
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ev0.record()
+        for _ in range(repeats):
+            train(warm, n_batches)
+        ev1.record()
+        barrier()
+        t = torch.tensor([ev0.elapsed_time(ev1)], dtype=torch.float64, device='cuda')
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item()) / (repeats * steps)
+        info1 = comm.info()
+        # every rank must hold the same model: compare a checksum of the parameters with rank 0's
+        R, Eemb = model.get_representations()
+        digest = torch.tensor([float(np.sum(R, dtype=np.float64)), float(np.sum(Eemb, dtype=np.float64))],
+                              dtype=torch.float64, device='cuda')
+        ref = digest.clone()
+        dist.broadcast(ref, 0)
+        same = torch.tensor([1.0 if torch.equal(ref, digest) else 0.0], device='cuda')
+        dist.all_reduce(same, op=dist.ReduceOp.MIN)
+        own_bytes = (own_e - own_b) * 4
+        dense_tail = (cfg['dw'] * cfg['de'] + cfg['de']) * 4
+        leg = {'ms_per_step': ms, 'value': cfg['B'] / (ms * 1e-3), 'unit': UNIT,
+               'speedup_vs_single_gpu': single_ms / ms,
+               'replicas_identical': bool(same.item() == 1.0),
+               'nccl_collectives_per_step': (info1['collectives'] - info0['collectives']) / float(repeats * steps)}
+        if rank == 0:
+            rel = np.abs(first.astype(np.float64) - single_first_losses) / np.abs(single_first_losses)
+            leg['loss_rel_err_vs_single_gpu'] = float(rel.max())
+        if peer:
+            leg['exchange'] = ('dense_update_kernel / hot_update_kernel store each new 16-byte chunk into the next parameter '
+                               'buffer of all %d ranks (CUDA IPC mappings, NVLink); ncclAllReduce of 64 doubles per step '
+                               '(sum(theta^2) of the loss) doubles as the barrier' % world)
+            # sent by this rank per step: with look-ahead only the rows of its piece that the next batch reads (counted
+            # here from the batches themselves, mean over the timed ones), everything on the last step of a call
+            E_f = cfg['E'] * cfg['de']
+            e_lo, e_hi = min(own_b, E_f) // cfg['de'], min(own_e, E_f) // cfg['de']
+            r_lo, r_hi = max(own_b - E_f, 0) // cfg['dw'], max(own_e - E_f, 0) // cfg['dw']
+            x_all, y_all = p['train'][0], p['train'][1]
+            sent = []
+            for b in range(warm, min(n_batches, warm + 8)):
+                sl = slice(b * cfg['B'], (b + 1) * cfg['B'])
+                words = np.unique(x_all[sl])
+                ents = np.unique(np.concatenate([y_all[sl].ravel(), p['neg'][b].ravel()]))
+                rows_r = int(np.count_nonzero((words >= r_lo) & (words < r_hi)))
+                rows_e = int(np.count_nonzero((ents >= e_lo) & (ents < e_hi)))
+                sent.append((rows_r * cfg['dw'] + rows_e * cfg['de']) * 4 * (world - 1))
+            leg['nvlink_bytes_sent_per_step_this_rank'] = float(np.mean(sent))
+            leg['nvlink_bytes_sent_full_push_this_rank'] = (own_bytes + (dense_tail if rank == world - 1 else 0)) * (world - 1)
+            leg['nccl_bytes_per_step'] = 512
+        else:
+            leg['exchange'] = ('%d grouped ncclBroadcast (one table piece per owner) + ncclBroadcast of the projection from '
+                               'its owner + ncclAllReduce of 64 doubles, behind the update kernels' % world)
+            leg['nccl_bytes_per_step'] = table_floats * 4 + dense_tail + 512
+        leg['adam_stream_bytes_per_rank'] = 24 * (own_e - own_b)
+        out[label] = leg
+        nat.close()
+        del model
+        torch.cuda.empty_cache()
+        barrier()
+    comm.close()
+    return out
 
 
 def run_product_search_shape(rank, steps=200):

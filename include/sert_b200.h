@@ -184,7 +184,7 @@ SERT_API int sert_model_set_entity_shard_comm(sert_model *m, sert_comm *comm, in
  * One model at the global batch, `world` <= 8 ranks of one NVLink domain.  Every rank is fed the SAME batches (and
  * draws the same negatives: same sert_config.seed) and computes the whole step's gradient, but streams the Adam
  * update only over its own contiguous piece of the two representation tables, 1/world of the 24 B/parameter dense
- * update (rank 0 also updates the projection matrix and bias).  The new parameters then reach every rank:
+ * update (the last rank also updates the projection matrix and bias).  The new parameters then reach every rank:
  *   peer_stores = 0: in place, by grouped ncclBroadcast of the pieces behind the update kernels;
  *   peer_stores = 1: by the update kernels' own stores into the next of two parameter buffers of every rank, mapped
  *                    with CUDA IPC over NVLink (the update is the exchange; one 64-double ncclAllReduce of the loss's

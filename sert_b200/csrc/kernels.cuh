@@ -24,6 +24,15 @@ int launch_gemm_f32(const float *A, const float *Bm, float *C, int M, int N, int
 int launch_colsum_atomic(const float *A, float *out, int M, int N, cudaStream_t st);
 
 // ---- vector-space negative-sampling loss, forward + backward (sert/models.py:1072-1098,893-902) ---
+// Table shards (sert_model_set_table_shard_comm): every rank computes the whole batch, but accumulates gradient rows
+// (and stamps them touched) only for the rows of the two tables it updates itself.  Default: everything.
+struct RowOwner {
+  int e_lo = 0, e_hi = 0x7fffffff;    // entity rows [e_lo, e_hi)
+  int r_lo = 0, r_hi = 0x7fffffff;    // word rows
+  __host__ __device__ bool entity(int row) const { return row >= e_lo && row < e_hi; }
+  __host__ __device__ bool word(int row) const { return row >= r_lo && row < r_hi; }
+};
+
 struct VsNceArgs {
   const float *t;        // (B,de) tanh(h.Wp+bp), unclipped
   const float *Eemb;     // (E,de)
@@ -41,6 +50,7 @@ struct VsNceArgs {
   int B, k, de;
   float inv_B;
   bool train;
+  RowOwner own;
 };
 int launch_vs_nce(const VsNceArgs &a, cudaStream_t st);
 
@@ -76,6 +86,7 @@ struct VsFusedArgs {
   double *fin_acc = nullptr;
   float *fin_loss = nullptr;
   float fin_inv_B = 0.f, fin_reg_coeff = 0.f;
+  RowOwner own;
 };
 constexpr int kMaxHotRows = 32;
 constexpr int kHotReplicas = 16;
@@ -91,7 +102,11 @@ int launch_vs_tile(const VsFusedArgs &a, const float *WpT, cudaStream_t st);
 
 // scatter-add of dh/denom into the word-gradient rows (autodiff of the gather, AdvancedIncSubtensor)
 int launch_scatter_rows(const int32_t *x, const float *dh, float *gR, uint32_t *flagR, uint32_t stamp,
-                        int B, int W, int d, float denom, cudaStream_t st);
+                        int B, int W, int d, float denom, cudaStream_t st, int row_lo = 0, int row_hi = 0x7fffffff);
+// Table shards with look-ahead: need_e / need_r [row] = stamp for every row the NEXT batch (x, y, neg) will read, so
+// that the update kernels send only those rows' new values to the other ranks
+int launch_mark_needed(const int32_t *x, const int32_t *y, const int32_t *neg, int B, int W, int k, uint32_t *need_r,
+                       uint32_t *need_e, uint32_t stamp, cudaStream_t st);
 
 // uniform negatives with replacement over [0,E) (sert/models.py:956-973); Philox4x32-10
 int launch_sample_negatives(int32_t *out, int64_t n, int64_t E, uint64_t seed, uint64_t step,
@@ -134,16 +149,18 @@ struct OptimArgs {
   // 1: s1 / s2 are arrays of bfloat16 (sert_config.dtype_mode 1), written with stochastic rounding -- 16 instead of
   // 24 bytes per parameter and step.  Element offsets are the same as for theta.
   int state_bf16 = 0;
-  // Table shards (vs_train_step with sert_model_set_table_shard_comm): every rank computes the whole batch's gradient,
-  // but updates only the 16-byte chunks [own_lo4, own_hi4) of the row-stamped tables (and the dense tensors iff
-  // own_dense); a touched chunk of another rank's shard only has its gradient zeroed.  The new theta goes to
-  // theta_out (nullptr: in place) and to the same offset of every peer_theta[p] -- the other ranks' copies, written
-  // over NVLink by this kernel's own stores, so the update IS the exchange.
-  long long own_lo4 = 0, own_hi4 = 0x7fffffffffffffffll;
-  int own_dense = 1;
+  // Table shards (vs_train_step with sert_model_set_table_shard_comm): the launch covers the 16-byte chunks
+  // [first4, last4) only (this rank's piece of the tables; last4 < 0: to the end).  The new theta goes to theta_out
+  // (nullptr: in place) and to the same offset of every peer_theta[p] -- the other ranks' copies, written over NVLink
+  // by this kernel's own stores, so the update IS the exchange.  With look-ahead (push_all == 0) a chunk of a
+  // segment with need flags is sent only when its row is marked need_stamp (the next batch reads it).
+  long long last4 = -1;
   float *theta_out = nullptr;
   int n_peers = 0;
   float *peer_theta[kMaxPeers] = {};
+  const uint32_t *need[kMaxSegments] = {};
+  uint32_t need_stamp = 0;
+  int push_all = 1;
 };
 
 // Adam + L2 of the hot word rows (gradient = sum of the private copies), see opt_kernels.cu
@@ -159,7 +176,7 @@ struct HotUpdateArgs {
   int counted;                     // 1: this rank reports the table's norm in the loss
   int state_bf16 = 0;              // as OptimArgs::state_bf16
   uint32_t stamp = 0;              // seeds the stochastic rounding
-  // table shards, as in OptimArgs: rows outside [own_lo4, own_hi4) only have their gradient copies zeroed
+  // table shards: hot rows outside the chunks [own_lo4, own_hi4) belong to another rank (nothing to do here)
   long long own_lo4 = 0, own_hi4 = 0x7fffffffffffffffll;
   float *theta_out = nullptr;
   int n_peers = 0;

@@ -95,7 +95,7 @@ __device__ __forceinline__ void store_state4(float *base, long long i4, const fl
 // overlaps with phase 3 on a second stream.
 template <bool ADAM, int PHASE, bool S16>
 __global__ void __launch_bounds__(256) dense_update_kernel(OptimArgs a) {
-  const long long total4 = a.total >> 2;
+  const long long total4 = a.last4 >= 0 ? a.last4 : (a.total >> 2);
   const float4 *__restrict__ th4 = reinterpret_cast<const float4 *>(a.theta);
   float4 *__restrict__ out4 = reinterpret_cast<float4 *>(a.theta_out != nullptr ? a.theta_out : a.theta);
   float4 *__restrict__ g4 = reinterpret_cast<float4 *>(a.grad);
@@ -108,7 +108,7 @@ __global__ void __launch_bounds__(256) dense_update_kernel(OptimArgs a) {
   const long long base4 = a.first4 + ((long long)blockIdx.x * blockDim.x + threadIdx.x) * CH;
   // phase A: where each chunk lives, whether its row was touched, and every load of every chunk in flight at once
   int sgi[CH];
-  bool act[CH], touched[CH];
+  bool act[CH], touched[CH], push[CH];
   float4 p[CH], g[CH];
   float v1[CH][4], v2[CH][4];
 #pragma unroll
@@ -124,20 +124,19 @@ __global__ void __launch_bounds__(256) dense_update_kernel(OptimArgs a) {
       const ParamSegment &sg = a.seg[s];
       const bool live = (e - sg.offset) < sg.count;   // false only inside inter-segment padding
       bool tch = true, skip = false;
+      push[ch] = a.n_peers > 0;
       if (live && sg.flags != nullptr) {
         const unsigned int row = (unsigned int)(e - sg.offset) / (unsigned int)sg.row_len;
         const uint32_t flag = __ldg(sg.flags + row);
         tch = (flag == a.stamp);
         skip = (flag == kHotRowMark);       // updated by hot_update_kernel on the side stream
+        // table shards with look-ahead: the other ranks only need the rows their next batch reads
+        if (a.n_peers > 0 && a.push_all == 0 && a.need[s] != nullptr) push[ch] = __ldg(a.need[s] + row) == a.need_stamp;
       }
       const bool mine = PHASE == 0 ? true : PHASE == 3 ? (sg.flags != nullptr) : (sg.flags == nullptr);
-      // table shards: this rank updates its own slice of the tables (and the dense tensors iff own_dense)
-      const bool owned = sg.flags != nullptr ? (i4 >= a.own_lo4 && i4 < a.own_hi4) : (a.own_dense != 0);
       sgi[ch] = s;
-      act[ch] = live && mine && !skip && owned;
+      act[ch] = live && mine && !skip;
       touched[ch] = act[ch] && tch;
-      // another rank's chunk: this replica's gradient of it is dropped (the owner computed the same one)
-      if (live && mine && !skip && !owned && tch) g4[i4] = make_float4(0.f, 0.f, 0.f, 0.f);
       if (act[ch]) {
         p[ch] = th4[i4];
         load_state4<S16>(a.s1, i4, v1[ch]);
@@ -165,7 +164,8 @@ __global__ void __launch_bounds__(256) dense_update_kernel(OptimArgs a) {
       }
       const float4 fresh = make_float4(pv[0], pv[1], pv[2], pv[3]);
       out4[i4] = fresh;
-      for (int pr = 0; pr < a.n_peers; ++pr) reinterpret_cast<float4 *>(a.peer_theta[pr])[i4] = fresh;   // NVLink stores
+      if (push[ch])
+        for (int pr = 0; pr < a.n_peers; ++pr) reinterpret_cast<float4 *>(a.peer_theta[pr])[i4] = fresh;   // NVLink stores
       if (PHASE == 4 && a.transposed != nullptr && s == a.transposed_segment) {
         // keep the (cols, rows) copy of the projection matrix current for the next step's back-projection
         const unsigned int el = (unsigned int)(e - sg.offset);
@@ -243,7 +243,9 @@ static int launch_update(const OptimArgs &a, bool adam, cudaStream_t st) {
   SERT_REQUIRE(a.phase == 0 || a.phase == 3 || a.phase == 4, "bad update phase");
   SERT_REQUIRE(a.transposed == nullptr || a.seg[a.transposed_segment].row_len % 4 == 0,
                "transposed copy needs rows of 4n floats");
-  const long long total4 = a.total / 4;
+  const long long total4 = a.last4 >= 0 ? a.last4 : a.total / 4;
+  SERT_REQUIRE(total4 <= a.total / 4 && a.first4 <= total4, "bad chunk range");
+  if (a.first4 == total4) return 0;                          // an empty piece
   const long long per_block = 256;                           // 16-byte chunks per block (dense_update_kernel: CH = 1)
   const long long blocks = std::max<long long>(1, (total4 - a.first4 + per_block - 1) / per_block);
   SERT_REQUIRE(blocks < (1ll << 31), "parameter arena too large for one launch");
@@ -272,6 +274,8 @@ template <bool S16>
 __global__ void __launch_bounds__(128) hot_update_kernel(HotUpdateArgs h) {
   const int s = blockIdx.x;
   const int row = __ldg(h.hot_ids + s);
+  const long long row4 = (long long)(((size_t)h.table_offset + (size_t)row * h.d) / 4);
+  if (row4 < h.own_lo4 || row4 >= h.own_hi4) return;   // table shards: another rank's row (its gradient is not formed here)
   float sumsq = 0.f;
   for (int c = threadIdx.x; c < h.d / 4; c += blockDim.x) {
     float4 v[kHotReplicas];
@@ -279,14 +283,6 @@ __global__ void __launch_bounds__(128) hot_update_kernel(HotUpdateArgs h) {
     for (int r = 0; r < kHotReplicas; ++r)
       v[r] = __ldcg(reinterpret_cast<const float4 *>(h.hot_acc + ((size_t)r * kMaxHotRows + s) * h.d) + c);
     const size_t i4 = ((size_t)h.table_offset + (size_t)row * h.d) / 4 + c;
-    if ((long long)i4 < h.own_lo4 || (long long)i4 >= h.own_hi4) {
-      // table shards: another rank updates this row; this replica's gradient copies are dropped
-      reinterpret_cast<float4 *>(h.grad)[i4] = make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll
-      for (int r = 0; r < kHotReplicas; ++r)
-        reinterpret_cast<float4 *>(h.hot_acc + ((size_t)r * kMaxHotRows + s) * h.d)[c] = make_float4(0.f, 0.f, 0.f, 0.f);
-      continue;
-    }
     float4 g = __ldcg(reinterpret_cast<const float4 *>(h.grad) + i4);
 #pragma unroll
     for (int r = 0; r < kHotReplicas; ++r) { g.x += v[r].x; g.y += v[r].y; g.z += v[r].z; g.w += v[r].w; }

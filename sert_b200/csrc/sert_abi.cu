@@ -101,13 +101,17 @@ struct sert_model {
   void *exchange_ctx = nullptr;
   sert_comm *comm = nullptr;       // set: the exchanges are NCCL collectives issued by the library itself (comm.cu)
   // table-sharded vector-space step (sert_model_set_table_shard_comm): this rank updates the 16-byte chunks
-  // [table_lo4[rank], table_lo4[rank + 1]) of the two tables (rank 0 also the dense tensors) for the whole group.
+  // [table_lo4[rank], table_lo4[rank + 1]) of the two tables (the LAST rank also the dense tensors) for the whole group.
   // Mode 1: the updated pieces are broadcast in place by NCCL.  Mode 2: theta lives in two library-owned buffers that
   // every rank maps (CUDA IPC); the update kernels store the new values into the NEXT buffer of every rank over
   // NVLink, and the buffers swap behind the step's one all-reduce.
   sert_comm *table_comm = nullptr;
   int table_mode = 0;
   long long table_lo4[kMaxPeers + 2] = {};
+  RowOwner table_own;              // this rank's rows of the two tables (pieces end on row boundaries)
+  uint32_t *need_r = nullptr, *need_e = nullptr;   // (V,), (E,): rows the next batch reads (look-ahead, mode 2)
+  int32_t *neg_alt = nullptr;      // negatives of the next step, drawn one step ahead (look-ahead with device sampling)
+  bool neg_presampled = false;
   float *arena_theta = nullptr;    // theta's place in the arena (mode 2 moves m.theta out of it)
   float *pp[2] = {nullptr, nullptr};
   void *pp_peers[2][kMaxPeers + 1] = {};
@@ -312,19 +316,21 @@ static OptimArgs optim_args(sert_model &m, float *loss_out) {
   a.acc = m.acc; a.loss_out = loss_out;
   a.inv_B = 1.0f / B;
   a.reg_coeff = m.cfg.lambda > 0.f ? m.cfg.lambda / (2.0f * B) : 0.f;
-  if (m.table_comm != nullptr) {
-    const int r = m.table_comm->rank;
-    a.own_lo4 = m.table_lo4[r]; a.own_hi4 = m.table_lo4[r + 1];
-    a.own_dense = r == 0 ? 1 : 0;
-    if (m.table_mode == 2) {
-      const int next = m.pp_cur ^ 1;
-      a.theta_out = m.pp[next];
-      for (int p = 0; p < m.table_comm->world; ++p)
-        if (p != r) a.peer_theta[a.n_peers++] = static_cast<float *>(m.pp_peers[next][p]);
-    }
+  if (m.table_comm != nullptr && m.table_mode == 2) {
+    const int r = m.table_comm->rank, next = m.pp_cur ^ 1;
+    a.theta_out = m.pp[next];
+    for (int p = 0; p < m.table_comm->world; ++p)
+      if (p != r) a.peer_theta[a.n_peers++] = static_cast<float *>(m.pp_peers[next][p]);
+    static const char *dbg = getenv("SERT_TABLE_SHARD_DEBUG");
+    if (dbg && strchr(dbg, 'p')) a.n_peers = 0;
+    for (int sg = 0; sg < m.nseg; ++sg)
+      a.need[sg] = m.seg[sg].flags == m.flagR ? m.need_r : m.seg[sg].flags == m.flagE ? m.need_e : nullptr;
   }
   return a;
 }
+
+// stamp of the step after `stamp` (vs_train_step advances it the same way)
+static uint32_t next_stamp(uint32_t stamp) { return stamp + 1 == kHotRowMark ? 1u : stamp + 1; }
 
 // Table shards: what follows the update kernels of a step on the model's stream.  Mode 1 broadcasts every owner's
 // piece of theta in place.  Both modes sum the owners' partial sum(theta^2) (the loss is finalised after this), and
@@ -340,9 +346,12 @@ static int table_exchange(sert_model &m, double *acc) {
     }
     if (comm_gather_pieces(c, m.theta, off, len, m.st)) return -1;
     const long long dense0 = m.off[SERT_PARAM_DENSE_W];
-    if (comm_broadcast(c, m.theta + dense0, (size_t)(m.total - dense0) * sizeof(float), 0, m.st)) return -1;
+    if (comm_broadcast(c, m.theta + dense0, (size_t)(m.total - dense0) * sizeof(float), c->world - 1, m.st)) return -1;
   }
-  if (comm_all_reduce_sum_f64(c, acc + 1, kSumsqSlots, m.st)) return -1;
+  // diagnostic (timing only, results invalid): SERT_TABLE_SHARD_DEBUG containing 'a' skips the all-reduce, 'p' the
+  // peer stores, 'm' the look-ahead marks (every row is sent)
+  static const char *dbg = getenv("SERT_TABLE_SHARD_DEBUG");
+  if (!(dbg && strchr(dbg, 'a')) && comm_all_reduce_sum_f64(c, acc + 1, kSumsqSlots, m.st)) return -1;
   if (m.table_mode == 2) {
     m.pp_cur ^= 1;
     m.theta = m.pp[m.pp_cur];
@@ -410,8 +419,16 @@ static int set_hot_marks(sert_model &m, bool on) {
   return launch_hot_mark(m.flagR, m.hot_ids, m.n_hot, on ? kHotRowMark : 0u, m.st);
 }
 
+// The batch the NEXT vs_train_step call will be given (table shards with look-ahead: only the rows it reads are
+// sent to the other ranks by this step's update).  x == nullptr: unknown, every row is sent.
+struct NextBatch {
+  const int32_t *x = nullptr, *y = nullptr;
+  const int32_t *neg = nullptr;      // nullptr with sampled == true: its negatives are drawn now, one step ahead
+  bool sampled = false;
+};
+
 static int vs_train_step(sert_model &m, const int32_t *x, const int32_t *y, const float *w,
-                         const int32_t *neg, float *loss_out) {
+                         const int32_t *neg, float *loss_out, const NextBatch &next = NextBatch()) {
   const sert_config &c = m.cfg;
   cudaStream_t st = m.st;
   const int B = c.batch, dw = c.word_dim, de = c.entity_dim;
@@ -427,9 +444,36 @@ static int vs_train_step(sert_model &m, const int32_t *x, const int32_t *y, cons
   m.stamp += 1;
   if (m.stamp == kHotRowMark) m.stamp = 1;          // never collides in practice (2^32 steps); keeps the mark unique
   if (neg == nullptr) {
-    if (launch_sample_negatives(m.neg, (int64_t)B * c.num_negatives, c.entities, c.seed, m.sample_calls++, st))
+    if (m.neg_presampled) {                         // drawn by the previous step (look-ahead)
+      std::swap(m.neg, m.neg_alt);
+      m.neg_presampled = false;
+    } else if (launch_sample_negatives(m.neg, (int64_t)B * c.num_negatives, c.entities, c.seed, m.sample_calls++, st)) {
       return -1;
+    }
     neg = m.neg;
+  }
+  const bool sharded = m.table_comm != nullptr;
+  // table shards: the LAST rank updates projection and bias -- their gradient GEMM, column sum and update are a chain
+  // of small kernels beside the table update, and the hot word rows (the most frequent, lowest ids) sit in an earlier
+  // rank's piece
+  const bool dense_owner = !sharded || m.table_comm->rank == m.table_comm->world - 1;
+  // table shards, look-ahead: mark the rows the next batch reads; the update kernels send only those
+  bool push_all = true;
+  static const char *ts_dbg = getenv("SERT_TABLE_SHARD_DEBUG");
+  if (sharded && m.table_mode == 2 && next.x != nullptr && m.table_comm->world > 1 && !(ts_dbg && strchr(ts_dbg, 'm'))) {
+    const int32_t *next_neg = next.neg;
+    if (next_neg == nullptr && next.sampled) {
+      if (launch_sample_negatives(m.neg_alt, (int64_t)B * c.num_negatives, c.entities, c.seed, m.sample_calls++, st))
+        return -1;
+      m.neg_presampled = true;
+      next_neg = m.neg_alt;
+    }
+    if (next_neg != nullptr) {
+      if (launch_mark_needed(next.x, next.y, next_neg, B, c.window, c.num_negatives, m.need_r, m.need_e,
+                             next_stamp(m.stamp), st))
+        return -1;
+      push_all = false;
+    }
   }
   const int64_t t_next = m.step + 1;
   const int bank = lazy ? (m.pending_bank == 0 ? 1 : 0) : 0;
@@ -441,6 +485,7 @@ static int vs_train_step(sert_model &m, const int32_t *x, const int32_t *y, cons
   f.gR = m.grad + m.off[SERT_PARAM_WORD_REPR]; f.flagR = m.flagR; f.stamp = m.stamp;
   f.h = m.h; f.da = m.da; f.loss_acc = acc;
   f.B = B; f.W = c.window; f.k = c.num_negatives; f.dw = dw; f.de = de; f.inv_B = 1.0f / (float)B;
+  f.own = m.table_own;
   if (lazy && m.n_hot > 0) {
     f.hot_slot = m.hot_slot; f.hot_acc = m.hot_acc; f.hot_replicas = kHotReplicas;
   }
@@ -451,9 +496,8 @@ static int vs_train_step(sert_model &m, const int32_t *x, const int32_t *y, cons
   const int fused = m.use_fused ? launch_vs_fused(f, m.WpT, !m.wpt_valid, m.use_fused, st) : 1;
   if (fused == 0) m.wpt_valid = true;
   if (fused < 0) return -1;
-  const bool sharded = m.table_comm != nullptr;
-  // table shards: the projection matrix arrives from rank 0, so only rank 0's update can keep the transposed copy
-  if (sharded && m.table_comm->rank != 0) m.wpt_valid = false;
+  // table shards: the projection matrix arrives from its owner, whose update alone can keep the transposed copy
+  if (!dense_owner) m.wpt_valid = false;
   if (m.want_fused_event) SERT_CUDA(cudaEventRecord(m.ev_fused, st));   // the previous step's loss is final here
   if (lazy) { m.pending_bank = -1; m.pending_loss = nullptr; }      // the tile kernel has taken care of it
   if (fused == 1) {
@@ -464,11 +508,12 @@ static int vs_train_step(sert_model &m, const int32_t *x, const int32_t *y, cons
     a.gE = m.grad + m.off[SERT_PARAM_ENTITY_REPR]; a.flagE = m.flagE; a.stamp = m.stamp; a.da = m.da;
     a.loss_acc = acc; a.dbg_scores = nullptr; a.dbg_u = nullptr; a.dbg_ell = nullptr;
     a.B = B; a.k = c.num_negatives; a.de = de; a.inv_B = 1.0f / (float)B; a.train = true;
+    a.own = m.table_own;
     if (launch_vs_nce(a, st)) return -1;
     // dh = da . Wp^T
     if (launch_gemm_f32(m.da, Wp, m.dh, B, dw, de, false, true, de, de, dw, EPI_STORE, nullptr, 1, st)) return -1;
     if (launch_scatter_rows(x, m.dh, m.grad + m.off[SERT_PARAM_WORD_REPR], m.flagR, m.stamp, B, c.window, dw,
-                            (float)c.window, st))
+                            (float)c.window, st, m.table_own.r_lo, m.table_own.r_hi))
       return -1;
   }
   // The gradients of the dense tensors (gWp = h^T . da by split-K, gbp = colsum(da)) are only consumed by the
@@ -479,19 +524,36 @@ static int vs_train_step(sert_model &m, const int32_t *x, const int32_t *y, cons
     SERT_CUDA(cudaEventRecord(m.ev_fork, st));
     SERT_CUDA(cudaStreamWaitEvent(side, m.ev_fork, 0));
   }
-  if (launch_gemm_f32(m.h, m.da, m.grad + m.off[SERT_PARAM_DENSE_W], dw, de, B, true, false, dw, de, de,
-                      EPI_ATOMIC_ADD, nullptr, pick_split_k(dw, de, B), side))
-    return -1;
-  if (launch_colsum_atomic(m.da, m.grad + m.off[SERT_PARAM_DENSE_B], B, de, side)) return -1;
+  if (dense_owner) {
+    if (launch_gemm_f32(m.h, m.da, m.grad + m.off[SERT_PARAM_DENSE_W], dw, de, B, true, false, dw, de, de,
+                        EPI_ATOMIC_ADD, nullptr, pick_split_k(dw, de, B), side))
+      return -1;
+    if (launch_colsum_atomic(m.da, m.grad + m.off[SERT_PARAM_DENSE_B], B, de, side)) return -1;
+  }
   m.step = t_next;
   OptimArgs o = optim_args(m, loss_out);
   o.acc = acc;
   o.c0 = adam_alpha_f32(m.step); o.c1 = 0.9f; o.c2 = 0.999f; o.c3 = 1e-8f;
+  o.push_all = push_all ? 1 : 0;
+  o.need_stamp = next_stamp(m.stamp);
   if (!overlap) {
     m.wpt_valid = false;
     if (!sharded) return timed_update(m, o, true);
-    o.no_finalize = true;
-    if (timed_update(m, o, true) || table_exchange(m, acc)) return -1;
+    // table shards: this rank's piece of the tables, then (their owner) the dense tensors, then the exchange
+    OptimArgs piece = o;
+    piece.no_finalize = true;
+    piece.phase = 3;
+    piece.first4 = m.table_lo4[m.table_comm->rank];
+    piece.last4 = m.table_lo4[m.table_comm->rank + 1];
+    if (timed_update(m, piece, true)) return -1;
+    if (dense_owner) {
+      OptimArgs tail = o;
+      tail.phase = 4;
+      tail.first4 = m.off[SERT_PARAM_DENSE_W] / 4;
+      tail.loss_out = nullptr;
+      if (launch_adam(tail, st)) return -1;
+    }
+    if (table_exchange(m, acc)) return -1;
     return launch_finalize_train(acc, loss_out, o.inv_B, o.reg_coeff, st);
   }
   OptimArgs dense = o;
@@ -508,10 +570,14 @@ static int vs_train_step(sert_model &m, const int32_t *x, const int32_t *y, cons
   OptimArgs tables = o;
   tables.loss_out = nullptr;
   tables.phase = 3;
+  if (sharded) {
+    tables.first4 = m.table_lo4[m.table_comm->rank];
+    tables.last4 = m.table_lo4[m.table_comm->rank + 1];
+  }
   if (lazy) {
     // second stream: dense tensors and hot rows; first stream: the two tables; join; loss left pending
     dense.loss_out = nullptr;
-    if (launch_adam(dense, side)) return -1;
+    if (dense_owner && launch_adam(dense, side)) return -1;
     if (m.n_hot > 0) {
       HotUpdateArgs h;
       h.theta = m.theta; h.s1 = m.s1; h.s2 = m.s2; h.grad = m.grad;
@@ -520,7 +586,8 @@ static int vs_train_step(sert_model &m, const int32_t *x, const int32_t *y, cons
       h.l2_scale = o.l2_scale; h.c0 = o.c0; h.c1 = o.c1; h.c2 = o.c2; h.c3 = o.c3;
       h.acc = acc; h.counted = 1;
       h.state_bf16 = o.state_bf16; h.stamp = o.stamp;
-      h.own_lo4 = o.own_lo4; h.own_hi4 = o.own_hi4; h.theta_out = o.theta_out; h.n_peers = o.n_peers;
+      if (sharded) { h.own_lo4 = tables.first4; h.own_hi4 = tables.last4; }
+      h.theta_out = o.theta_out; h.n_peers = o.n_peers;
       for (int p = 0; p < o.n_peers; ++p) h.peer_theta[p] = o.peer_theta[p];
       if (launch_hot_update(h, side)) return -1;
     }
@@ -537,7 +604,7 @@ static int vs_train_step(sert_model &m, const int32_t *x, const int32_t *y, cons
   SERT_CUDA(cudaStreamWaitEvent(st, m.ev_join, 0));
   if (sharded) {                  // the loss waits for the other ranks' share of sum(theta^2)
     dense.loss_out = nullptr;
-    if (launch_adam(dense, st) || table_exchange(m, acc)) return -1;
+    if ((dense_owner && launch_adam(dense, st)) || table_exchange(m, acc)) return -1;
     return launch_finalize_train(acc, loss_out, o.inv_B, o.reg_coeff, st);
   }
   dense.ticket = reinterpret_cast<unsigned int *>(m.acc + kAccDoubles - 4);
@@ -1064,6 +1131,18 @@ static void table_shard_release(sert_model *m) {
       m->pp[b] = nullptr;
     }
   }
+  if (m->need_r) cudaFree(m->need_r);
+  if (m->need_e) cudaFree(m->need_e);
+  m->need_r = m->need_e = nullptr;
+  if (m->neg_alt) {
+    // m.neg and neg_alt swap roles (look-ahead): the arena's buffer must be the one that stays
+    const char *lo = m->arena, *hi = m->arena + m->arena_bytes;
+    if (!(reinterpret_cast<const char *>(m->neg) >= lo && reinterpret_cast<const char *>(m->neg) < hi)) std::swap(m->neg, m->neg_alt);
+    cudaFree(m->neg_alt);
+    m->neg_alt = nullptr;
+  }
+  m->neg_presampled = false;
+  m->table_own = RowOwner();
   m->table_comm = nullptr;
   m->table_mode = 0;
 }
@@ -1081,11 +1160,21 @@ int sert_model_set_table_shard_comm(sert_model *m, sert_comm *comm, int32_t peer
   SERT_REQUIRE(m->off[SERT_PARAM_ENTITY_REPR] < m->off[SERT_PARAM_DENSE_W] &&
                m->off[SERT_PARAM_WORD_REPR] < m->off[SERT_PARAM_DENSE_W] &&
                m->off[SERT_PARAM_DENSE_W] < m->off[SERT_PARAM_DENSE_B], "unexpected parameter layout");
+  // Pieces of (nearly) equal float counts that end on row boundaries (row index a multiple of 4: 16-byte chunks),
+  // so that a gradient row is formed by exactly one rank.  The entity table comes first in the arena (carve).
+  const long long E = m->cfg.entities, V = m->cfg.vocab, de = m->cfg.entity_dim, dw = m->cfg.word_dim;
+  const long long offE = m->off[SERT_PARAM_ENTITY_REPR], offR = m->off[SERT_PARAM_WORD_REPR];
+  SERT_REQUIRE(offE < offR, "unexpected parameter layout");
+  long long e_row[kMaxPeers + 2], r_row[kMaxPeers + 2];
   for (int r = 0; r <= comm->world; ++r) {
-    long long b = tables4 * r / comm->world;
-    if (r != comm->world) b &= ~63ll;                            // 1 KB pieces
-    m->table_lo4[r] = b;
+    const long long t = (E * de + V * dw) * r / comm->world;     // floats before the boundary
+    if (r == comm->world) { e_row[r] = E; r_row[r] = V; m->table_lo4[r] = tables4; }
+    else if (t < E * de) { e_row[r] = (t / de) & ~3ll; r_row[r] = 0; m->table_lo4[r] = (offE + e_row[r] * de) / 4; }
+    else { e_row[r] = E; r_row[r] = ((t - E * de) / dw) & ~3ll; m->table_lo4[r] = (offR + r_row[r] * dw) / 4; }
   }
+  m->table_lo4[0] = 0;
+  m->table_own.e_lo = (int)e_row[comm->rank]; m->table_own.e_hi = (int)e_row[comm->rank + 1];
+  m->table_own.r_lo = (int)r_row[comm->rank]; m->table_own.r_hi = (int)r_row[comm->rank + 1];
   // one model: every rank starts from rank 0's parameters, optimiser state and step, and draws rank 0's negatives
   if (comm_broadcast(comm, m->theta, (size_t)m->total * sizeof(float), 0, m->st)) return -1;
   const size_t state_el = m->cfg.dtype_mode == 1 ? 2 : 4;
@@ -1108,6 +1197,12 @@ int sert_model_set_table_shard_comm(sert_model *m, sert_comm *comm, int32_t peer
   }
   m->wpt_valid = false;
   if (peer_stores) {
+    SERT_CUDA(cudaMalloc(&m->need_r, (size_t)V * sizeof(uint32_t)));
+    SERT_CUDA(cudaMalloc(&m->need_e, (size_t)E * sizeof(uint32_t)));
+    SERT_CUDA(cudaMalloc(&m->neg_alt, (size_t)m->cfg.batch * m->cfg.num_negatives * sizeof(int32_t)));
+    SERT_CUDA(cudaMemsetAsync(m->need_r, 0, (size_t)V * sizeof(uint32_t), m->st));
+    SERT_CUDA(cudaMemsetAsync(m->need_e, 0, (size_t)E * sizeof(uint32_t), m->st));
+    m->neg_presampled = false;
     m->arena_theta = m->theta;
     for (int b = 0; b < 2; ++b) {
       SERT_CUDA(cudaMalloc(&m->pp[b], (size_t)m->total * sizeof(float)));
@@ -1148,7 +1243,7 @@ int sert_model_gather_table_state(sert_model *m) {
   const size_t dense0 = (size_t)m->off[SERT_PARAM_DENSE_W];
   for (float *state : {m->s1, m->s2}) {
     if (comm_gather_pieces(c, state, off, len, m->st)) return -1;
-    if (comm_broadcast(c, reinterpret_cast<char *>(state) + dense0 * el, ((size_t)m->total - dense0) * el, 0, m->st)) return -1;
+    if (comm_broadcast(c, reinterpret_cast<char *>(state) + dense0 * el, ((size_t)m->total - dense0) * el, c->world - 1, m->st)) return -1;
   }
   SERT_CUDA(cudaStreamSynchronize(m->st));
   return 0;
@@ -1223,7 +1318,16 @@ int sert_train_batches(sert_model *m, const int64_t *order_host, int64_t n, cons
     int rc;
     if (is_vs(c)) {
       const int32_t *neg = neg_dev ? neg_dev + j * (int64_t)c.batch * c.num_negatives : nullptr;
-      rc = vs_train_step(*m, d.x + r0 * c.window, d.y + r0, w, neg, loss);
+      NextBatch next;                      // table shards: the batch after this one is known here
+      if (m->table_comm != nullptr && j + 1 < n) {
+        if (check_batch(m, SERT_SPLIT_TRAIN, order_host[j + 1])) return -1;
+        const int64_t r1 = order_host[j + 1] * c.batch;
+        next.x = d.x + r1 * c.window;
+        next.y = d.y + r1;
+        next.neg = neg_dev ? neg_dev + (j + 1) * (int64_t)c.batch * c.num_negatives : nullptr;
+        next.sampled = neg_dev == nullptr;
+      }
+      rc = vs_train_step(*m, d.x + r0 * c.window, d.y + r0, w, neg, loss, next);
     } else {
       rc = (m->exchange ? ll_train_step_sharded : ll_train_step)(*m, d.x + r0 * c.window, d.indptr + r0, 0,
                                                                 d.indices, d.data, w, loss);

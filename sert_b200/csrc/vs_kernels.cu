@@ -84,7 +84,7 @@ __global__ void __launch_bounds__(256) scatter_rows_kernel(const int32_t *__rest
                                                            const float4 *__restrict__ dh,
                                                            float *__restrict__ gR,
                                                            uint32_t *__restrict__ flagR, uint32_t stamp,
-                                                           int B, int W, int d4, float denom) {
+                                                           int B, int W, int d4, float denom, int row_lo, int row_hi) {
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (warp >= B) return;
@@ -92,7 +92,7 @@ __global__ void __launch_bounds__(256) scatter_rows_kernel(const int32_t *__rest
   for (int w0 = 0; w0 < W; w0 += 32) {
     const int nw = min(32, W - w0);
     const int idx = (lane < nw) ? __ldg(xi + w0 + lane) : 0;
-    if (lane < nw) flagR[idx] = stamp;
+    if (lane < nw && idx >= row_lo && idx < row_hi) flagR[idx] = stamp;
     for (int c0 = 0; c0 < d4; c0 += 32) {
       const int c = c0 + lane;
       const bool active = c < d4;
@@ -103,18 +103,38 @@ __global__ void __launch_bounds__(256) scatter_rows_kernel(const int32_t *__rest
       }
       for (int w = 0; w < nw; ++w) {
         const int r = __shfl_sync(0xffffffffu, idx, w);
-        if (active) red_add_f4(gR + ((size_t)r * d4 + c) * 4, g);
+        if (active && r >= row_lo && r < row_hi) red_add_f4(gR + ((size_t)r * d4 + c) * 4, g);
       }
     }
   }
 }
 
+// table shards with look-ahead: stamps the rows the next batch reads (kernels.cuh: launch_mark_needed)
+__global__ void __launch_bounds__(256) mark_needed_kernel(const int32_t *__restrict__ x, const int32_t *__restrict__ y,
+                                                          const int32_t *__restrict__ neg, long long nx, long long ny,
+                                                          long long nn, uint32_t *__restrict__ need_r,
+                                                          uint32_t *__restrict__ need_e, uint32_t stamp) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < nx) need_r[__ldg(x + i)] = stamp;
+  else if (i < nx + ny) need_e[__ldg(y + (i - nx))] = stamp;
+  else if (i < nx + ny + nn) need_e[__ldg(neg + (i - nx - ny))] = stamp;
+}
+
+int launch_mark_needed(const int32_t *x, const int32_t *y, const int32_t *neg, int B, int W, int k, uint32_t *need_r,
+                       uint32_t *need_e, uint32_t stamp, cudaStream_t st) {
+  const long long nx = (long long)B * W, ny = B, nn = (long long)B * k;
+  if (nx + ny + nn == 0) return 0;
+  mark_needed_kernel<<<cdiv(nx + ny + nn, 256), 256, 0, st>>>(x, y, neg, nx, ny, nn, need_r, need_e, stamp);
+  SERT_LAUNCH_CHECK();
+  return 0;
+}
+
 int launch_scatter_rows(const int32_t *x, const float *dh, float *gR, uint32_t *flagR, uint32_t stamp,
-                        int B, int W, int d, float denom, cudaStream_t st) {
+                        int B, int W, int d, float denom, cudaStream_t st, int row_lo, int row_hi) {
   SERT_REQUIRE(d % 4 == 0, "representation size must be a multiple of 4");
   if (B == 0) return 0;
   scatter_rows_kernel<<<cdiv(B, 8), 256, 0, st>>>(x, reinterpret_cast<const float4 *>(dh), gR, flagR,
-                                                  stamp, B, W, d / 4, denom);
+                                                  stamp, B, W, d / 4, denom, row_lo, row_hi);
   SERT_LAUNCH_CHECK();
   return 0;
 }
@@ -196,13 +216,14 @@ __global__ void __launch_bounds__(256) vs_nce_kernel(VsNceArgs a) {
         }
         if (a.dbg_scores != nullptr && lane == 0) a.dbg_scores[(size_t)i * (a.k + 1) + j] = score;
         if (TRAIN) {
-          if (lane == 0) a.flagE[rows[g]] = a.stamp;
+          const bool mine = a.own.entity(rows[g]);     // table shards: another rank forms this row's gradient
+          if (lane == 0 && mine) a.flagE[rows[g]] = a.stamp;
 #pragma unroll
           for (int c = 0; c < MAXC; ++c) {
             const int ch = lane + 32 * c;
             du[c].x += coef * e[g][c].x; du[c].y += coef * e[g][c].y;
             du[c].z += coef * e[g][c].z; du[c].w += coef * e[g][c].w;
-            if (ch < d4)
+            if (ch < d4 && mine)
               red_add_f4(a.gE + ((size_t)rows[g] * d4 + ch) * 4,
                          make_float4(coef * u[c].x, coef * u[c].y, coef * u[c].z, coef * u[c].w));
           }

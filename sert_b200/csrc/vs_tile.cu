@@ -36,6 +36,7 @@ constexpr int kLd = kD + 4;           // padded staging rows (entity-sized vecto
 constexpr int kMaxNW = 3;             // word rows of up to 3 x 128 floats
 constexpr int kMaxRows = 16;          // 1 + k scores per instance handled by the butterfly
 constexpr int kMaxWindow = 32;
+constexpr int kSkipRow = (int)0x80000000;   // gradient destination of a row another rank updates (table shards)
 constexpr int kRowsPerWarp = kD / kT; // matrix rows per warp in the K-split products
 constexpr int kPartFloats = kT * kT * kD;   // 8 warps x 8 instances x 128 partial products (32 KB)
 
@@ -165,16 +166,23 @@ __global__ void __launch_bounds__(kThreads, NW == 1 ? 4 : 3) vs_tile_kernel(VsFu
   float *my_ent = scratch + (size_t)warp * K1 * kD;
 
   // ---- A: the instance's indices, touched stamps, entity rows on their way into L2 -------------------------
-  int xi = 0, ri = 0, xdst = 0;          // xdst: row id, or -1 - slot for a hot row (kernels.cuh: hot_slot)
+  // xdst: gradient row id, -1 - slot for a hot row (kernels.cuh: hot_slot), kSkipRow for a row another rank updates
+  // (table shards: its gradient is formed there); rdst: the same for the entity rows
+  int xi = 0, ri = 0, xdst = kSkipRow, rdst = kSkipRow;
   if (ok && lane < W) {
     xi = __ldg(a.x + (size_t)i * W + lane);
-    const int slot = a.hot_slot != nullptr ? (int)__ldg(a.hot_slot + xi) : -1;
-    xdst = slot < 0 ? xi : -1 - slot;
-    if (slot < 0) a.flagR[xi] = a.stamp;   // hot rows keep their kHotRowMark
+    if (a.own.word(xi)) {
+      const int slot = a.hot_slot != nullptr ? (int)__ldg(a.hot_slot + xi) : -1;
+      xdst = slot < 0 ? xi : -1 - slot;
+      if (slot < 0) a.flagR[xi] = a.stamp;   // hot rows keep their kHotRowMark
+    }
   }
   if (ok && lane < K1) {
     ri = lane == 0 ? __ldg(a.y + i) : __ldg(a.neg + (size_t)i * a.k + lane - 1);
-    a.flagE[ri] = a.stamp;
+    if (a.own.entity(ri)) {
+      a.flagE[ri] = a.stamp;
+      rdst = ri;
+    }
   }
   xs[warp * kMaxWindow + lane] = xdst;   // read back by this warp only
   for (int j = 0; j < K1; ++j) {
@@ -256,10 +264,10 @@ __global__ void __launch_bounds__(kThreads, NW == 1 ? 4 : 3) vs_tile_kernel(VsFu
     float4 du = f4_zero();
     for (int jj = 0; jj < K1; ++jj) {
       const float c = __shfl_sync(0xffffffffu, coef, 2 * jj);
-      const int r = __shfl_sync(0xffffffffu, ri, jj);
+      const int r = __shfl_sync(0xffffffffu, rdst, jj);
       const float4 e = reinterpret_cast<const float4 *>(my_ent + jj * kD)[lane];
       f4_fma(du, c, e);
-      if (ok) red_add_f4(a.gE + ((size_t)r * kD4 + lane) * 4, make_float4(c * u.x, c * u.y, c * u.z, c * u.w));
+      if (ok && r != kSkipRow) red_add_f4(a.gE + ((size_t)r * kD4 + lane) * 4, make_float4(c * u.x, c * u.y, c * u.z, c * u.w));
     }
     float4 da;
     da.x = (t.x >= SERT_TANH_LO && t.x <= SERT_TANH_HI) ? du.x * (1.0f - t.x * t.x) : 0.f;
@@ -288,6 +296,7 @@ __global__ void __launch_bounds__(kThreads, NW == 1 ? 4 : 3) vs_tile_kernel(VsFu
                        : a.hot_acc + (size_t)(blockIdx.x & (a.hot_replicas - 1)) * kMaxHotRows * dw;
       for (int w = 0; w < W; ++w) {
         const int r = xs[warp * kMaxWindow + w];
+        if (r == kSkipRow) continue;
         float *row = r >= 0 ? a.gR + (size_t)r * dw : hot + (size_t)(-1 - r) * dw;
 #pragma unroll
         for (int u = 0; u < NW; ++u)

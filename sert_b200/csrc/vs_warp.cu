@@ -189,12 +189,13 @@ __global__ void __launch_bounds__(kThreads, kInst == 1 ? 4 : 3) vs_warp_kernel(V
               ell -= logf(1.0f - cl);
               coef = inside ? (coef_scale / (1.0f - cl)) * sg * (1.0f - sg) : 0.0f;
             }
-            if (lane == 0) a.flagE[rows[q]] = a.stamp;
+            const bool mine = a.own.entity(rows[q]);     // table shards: another rank forms this row's gradient
+            if (lane == 0 && mine) a.flagE[rows[q]] = a.stamp;
 #pragma unroll
             for (int c = 0; c < CE; ++c) {
               const int ch = lane + 32 * c;
               f4_fma(du[c], coef, e[q][c]);
-              if (ch < de4)
+              if (ch < de4 && mine)
                 red_add_f4(a.gE + ((size_t)rows[q] * de4 + ch) * 4,
                            make_float4(coef * u[c].x, coef * u[c].y, coef * u[c].z, coef * u[c].w));
             }
@@ -237,9 +238,10 @@ __global__ void __launch_bounds__(kThreads, kInst == 1 ? 4 : 3) vs_warp_kernel(V
       for (int w0 = 0; w0 < W; w0 += 32) {
         const int nw = min(32, W - w0);
         const int idx = lane < nw ? __ldg(xi + w0 + lane) : 0;
-        if (lane < nw) a.flagR[idx] = a.stamp;
+        if (lane < nw && a.own.word(idx)) a.flagR[idx] = a.stamp;
         for (int w = 0; w < nw; ++w) {
           const int r = __shfl_sync(0xffffffffu, idx, w);
+          if (!a.own.word(r)) continue;
 #pragma unroll
           for (int c = 0; c < CW; ++c) {
             const int ch = lane + 32 * c;

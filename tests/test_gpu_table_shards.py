@@ -87,7 +87,10 @@ for case, dims in enumerate([dict(V=1500, E=700, dw=128, de=128, W=8, B=256, k=1
         spans = [None] * world
         dist.all_gather_object(spans, (b, e))
         assert spans[0][0] == 0 and spans[-1][1] == n and all(spans[i][1] == spans[i + 1][0] for i in range(world - 1)), spans
-        got = [model.train_fn(bi, p['neg'][j]) for j, bi in enumerate(order)]
+        # four steps in ONE call (look-ahead: with peer stores only the rows the next batch reads are sent; the call's
+        # last step sends everything), then single-step calls
+        got = list(model._native.run_batches('train', order[:4], np.stack([p['neg'][j] for j in range(4)])))
+        got += [model.train_fn(bi, p['neg'][j]) for j, bi in enumerate(order) if j >= 4]
         H.close(got, ref, what='train losses (rank %%d, peer_stores=%%s)' %% (rank, peer_stores))
         R, Eemb = model.get_representations()
         Wp, bp = model.get_dense()
@@ -106,6 +109,14 @@ for case, dims in enumerate([dict(V=1500, E=700, dw=128, de=128, W=8, B=256, k=1
         H.close(ckpt['entity_representations/state1'], oracle.state['Eemb'][0], rtol=2e-4, atol_scale=1e-4, what='Adam m (Eemb)')
         H.close(ckpt['representations/state2'], oracle.state['R'][1], rtol=2e-4, atol_scale=1e-4, what='Adam v (R)')
         H.close(ckpt['dense_w/state1'], oracle.state['Wp'][0], rtol=2e-4, atol_scale=1e-4, what='Adam m (Wp)')
+        # negatives drawn on the device (one step ahead under look-ahead): every rank must draw the same ones
+        sampled = model._native.run_batches('train', [1, 4, 0, 2, 5], None)
+        assert np.all(np.isfinite(sampled))
+        R2, E2 = model.get_representations()
+        mine = torch.from_numpy(np.concatenate([sampled, R2.ravel(), E2.ravel()])).cuda()
+        ref0 = mine.clone()
+        dist.broadcast(ref0, 0)
+        assert torch.equal(mine, ref0), 'rank %%d differs from rank 0 after device-sampled steps' %% rank
         model._native.close()
         dist.barrier()
         oracle = H.vs_oracle(p, lam)
