@@ -410,7 +410,8 @@ def run_ours(args, rank, world, local_rank):
             'scoring_small_frac': ((scoring_small or {}).get('roofline') or {}).get('frac'),
             'scoring_small_lists_identical': (scoring_small or {}).get('lists_identical'),
             'loglinear_stress_ms': (loglinear_stress or {}).get('ms_per_step'),
-            'table_shards_ms': ((table_shards or {}).get('peer_stores') or {}).get('ms_per_step'),
+            'table_shards_ms': min([v['ms_per_step'] for v in (table_shards or {}).values()
+                                    if isinstance(v, dict) and 'ms_per_step' in v] or [None]),
             'table_shards': table_shards,
             'bf16_state_mode': bf16_mode,
             'product_search_shape': product_search,
@@ -512,7 +513,7 @@ def run_table_shards(cfg, steps, warm, repeats, single_ms, single_first_losses, 
     comm = Communicator.from_torch_distributed()
     out = {'workload': WORKLOAD + '; ONE model, global batch %d, table pieces over %d ranks' % (cfg['B'], world),
            'scaling': 'strong', 'single_gpu_ms_per_step': single_ms}
-    for label, peer in (('peer_stores', True), ('nccl_broadcast', False)):
+    for label, peer in (('instance_shards', 'instances'), ('peer_stores', True), ('nccl_broadcast', False)):
         model = models.VectorSpaceLanguageModel(
             batch_size=cfg['B'], window_size=cfg['W'], num_negative_samples=cfg['k'],
             representations_init=p['R'], entity_representations_init=p['Eemb'], regularization_lambda=cfg['lam'],
@@ -559,8 +560,11 @@ def run_table_shards(cfg, steps, warm, repeats, single_ms, single_first_losses, 
             leg['loss_rel_err_vs_single_gpu'] = float(rel.max())
         if peer:
             leg['exchange'] = ('dense_update_kernel / hot_update_kernel store each new 16-byte chunk into the next parameter '
-                               'buffer of all %d ranks (CUDA IPC mappings, NVLink); ncclAllReduce of 64 doubles per step '
-                               '(sum(theta^2) of the loss) doubles as the barrier' % world)
+                               'buffer of all %d ranks (CUDA IPC mappings, NVLink); the partial sums of the loss cross in a '
+                               'barrier kernel over the same mappings (csrc/peer_sync.cu), no NCCL call on the step' % world)
+            if peer == 'instances':
+                leg['exchange'] = ('each rank runs the tile kernel over its %d instances and adds the gradient rows into their '
+                                   'owners\' arenas (red.global.add.v4.f32 over NVLink); ' % (cfg['B'] // world)) + leg['exchange']
             # sent by this rank per step: with look-ahead only the rows of its piece that the next batch reads (counted
             # here from the batches themselves, mean over the timed ones), everything on the last step of a call
             E_f = cfg['E'] * cfg['de']
@@ -575,9 +579,10 @@ def run_table_shards(cfg, steps, warm, repeats, single_ms, single_first_losses, 
                 rows_r = int(np.count_nonzero((words >= r_lo) & (words < r_hi)))
                 rows_e = int(np.count_nonzero((ents >= e_lo) & (ents < e_hi)))
                 sent.append((rows_r * cfg['dw'] + rows_e * cfg['de']) * 4 * (world - 1))
-            leg['nvlink_bytes_sent_per_step_this_rank'] = float(np.mean(sent))
+            if peer != 'instances':      # instance shards send a row only to the ranks whose instances read it (fewer bytes)
+                leg['nvlink_bytes_sent_per_step_this_rank'] = float(np.mean(sent))
             leg['nvlink_bytes_sent_full_push_this_rank'] = (own_bytes + (dense_tail if rank == world - 1 else 0)) * (world - 1)
-            leg['nccl_bytes_per_step'] = 512
+            leg['nccl_bytes_per_step'] = 0
         else:
             leg['exchange'] = ('%d grouped ncclBroadcast (one table piece per owner) + ncclBroadcast of the projection from '
                                'its owner + ncclAllReduce of 64 doubles, behind the update kernels' % world)

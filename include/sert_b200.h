@@ -187,15 +187,23 @@ SERT_API int sert_model_set_entity_shard_comm(sert_model *m, sert_comm *comm, in
  * update (the last rank also updates the projection matrix and bias).  The new parameters then reach every rank:
  *   peer_stores = 0: in place, by grouped ncclBroadcast of the pieces behind the update kernels;
  *   peer_stores = 1: by the update kernels' own stores into the next of two parameter buffers of every rank, mapped
- *                    with CUDA IPC over NVLink (the update is the exchange; one 64-double ncclAllReduce of the loss's
- *                    sum(theta^2) terms per step is also the barrier behind which the buffers swap).
+ *                    with CUDA IPC over NVLink (the update is the exchange); the 64 partial sums of theta^2 of the
+ *                    loss travel through a barrier kernel over the same peer mappings (csrc/peer_sync.cu) behind which
+ *                    the buffers swap -- no NCCL call on the step (SERT_TABLE_SHARD_BARRIER=nccl: one ncclAllReduce).
+ *   peer_stores = 2: "instance shards": as 1, and every rank runs the forward / backward of its own slice of the
+ *                    batch's instances only (fused tile kernel shapes: entity_dim 128, word_dim <= 384), adding each
+ *                    gradient row (red.global.add.v4.f32) and its touched stamp into the gradient arena of the rank
+ *                    that updates the row, over NVLink for the other ranks' rows; its share of the projection's
+ *                    gradient goes to the last rank the same way.  Two barrier kernels per step (gradients landed /
+ *                    parameters landed); a new parameter row is sent only to the ranks whose instances of the next
+ *                    batch read it.
  * The reference trains on one device (sert/models.py:520-560 builds one update function); there is no counterpart.
  * Collective: every rank calls it with its communicator; parameters and optimiser step are taken from rank 0.
  * comm = NULL detaches.  The optimiser state of a rank is current only inside its piece:
  * sert_model_gather_table_state makes it whole everywhere (checkpoints). */
 SERT_API int sert_model_set_table_shard_comm(sert_model *m, sert_comm *comm, int32_t peer_stores);
 SERT_API int sert_model_gather_table_state(sert_model *m);
-/* mode: 0 none, 1 broadcast, 2 peer stores; [own_begin, own_end): this rank's float range of the tables' table_floats */
+/* mode: 0 none, 1 broadcast, 2 peer stores, 3 instance shards; [own_begin, own_end): this rank's float range of the tables' table_floats */
 SERT_API int sert_model_table_shard_info(sert_model *m, int32_t *mode, int64_t *own_begin, int64_t *own_end,
                                          int64_t *table_floats);
 

@@ -33,6 +33,7 @@ struct RowOwner {
   __host__ __device__ bool word(int row) const { return row >= r_lo && row < r_hi; }
 };
 
+constexpr int kMaxOwners = 8;       // ranks of a table-shard group (kMaxPeers + 1, one NVSwitch domain)
 struct VsNceArgs {
   const float *t;        // (B,de) tanh(h.Wp+bp), unclipped
   const float *Eemb;     // (E,de)
@@ -87,6 +88,16 @@ struct VsFusedArgs {
   float *fin_loss = nullptr;
   float fin_inv_B = 0.f, fin_reg_coeff = 0.f;
   RowOwner own;
+  // Instance shards (table-shard mode 3, tile kernel only): this rank runs the instances [i0, B) of the batch -- h and
+  // da rows are written at i - i0 -- and adds every gradient row (and its touched stamp) straight into the arena of
+  // the rank that updates it, over NVLink for the other ranks' rows: rank o owns the entity rows
+  // [e_bound[o], e_bound[o + 1]) and the word rows [r_bound[o], r_bound[o + 1]).  n_owner == 0: gE / gR / flagE / flagR
+  // above are the only destination.  Row ids must stay below 2^28 (the owner travels in the bits above).
+  int i0 = 0;
+  int n_owner = 0;
+  int e_bound[kMaxOwners + 1] = {}, r_bound[kMaxOwners + 1] = {};
+  float *gE_peer[kMaxOwners] = {}, *gR_peer[kMaxOwners] = {};
+  uint32_t *flagE_peer[kMaxOwners] = {}, *flagR_peer[kMaxOwners] = {};
 };
 constexpr int kMaxHotRows = 32;
 constexpr int kHotReplicas = 16;
@@ -107,6 +118,11 @@ int launch_scatter_rows(const int32_t *x, const float *dh, float *gR, uint32_t *
 // that the update kernels send only those rows' new values to the other ranks
 int launch_mark_needed(const int32_t *x, const int32_t *y, const int32_t *neg, int B, int W, int k, uint32_t *need_r,
                        uint32_t *need_e, uint32_t stamp, cudaStream_t st);
+
+// Instance shards: need_*[row] |= 1 << r for every row that rank r's instances [i_bound[r], i_bound[r + 1]) of the NEXT
+// batch read (the arrays are zeroed first); the update kernels send a row only to the ranks whose bit is set
+int launch_mark_needed_by(const int32_t *x, const int32_t *y, const int32_t *neg, int B, int W, int k, uint32_t *need_r,
+                          uint32_t *need_e, const int *i_bound, int n_ranks, cudaStream_t st);
 
 // uniform negatives with replacement over [0,E) (sert/models.py:956-973); Philox4x32-10
 int launch_sample_negatives(int32_t *out, int64_t n, int64_t E, uint64_t seed, uint64_t step,
@@ -161,7 +177,44 @@ struct OptimArgs {
   const uint32_t *need[kMaxSegments] = {};
   uint32_t need_stamp = 0;
   int push_all = 1;
+  // instance shards: the need words are bit masks over the ranks (launch_mark_needed_by); peer_rank[p] = rank behind
+  // peer_theta[p]
+  int need_is_mask = 0;
+  int peer_rank[kMaxPeers] = {};
 };
+
+// Instance shards: the gradient of hot word row s gathered on this rank (sum of its private copies, zeroed here) is
+// added into the gradient row of the rank that updates it (grad_peer[o] = that rank's gradient arena, r_bound as in
+// VsFusedArgs); launch_hot_update on the owner then sees the sum over all ranks in the row itself.
+struct HotPushArgs {
+  float *hot_acc;                  // (kHotReplicas, kMaxHotRows, d)
+  const int32_t *hot_ids;
+  int n_hot, d;
+  long long table_offset;          // float offset of the word table inside the gradient arenas
+  int n_owner;
+  int r_bound[kMaxPeers + 2];
+  float *grad_peer[kMaxPeers + 1];
+};
+int launch_hot_push(const HotPushArgs &h, cudaStream_t st);
+// dst[0 .. n) += src[0 .. n); src <- 0 (n a multiple of 4, 16-byte aligned): a rank's share of the dense tensors'
+// gradient, accumulated locally, goes to the rank that updates them in one pass of vector reductions over NVLink
+int launch_push_add(float *src, float *dst, long long n, cudaStream_t st);
+
+// ---- barrier + accumulator exchange of a table-shard group over NVLink peer memory (csrc/peer_sync.cu) ----------
+constexpr int kAccSlots = 1 + kSumsqSlots;     // acc[0] = data-loss sum, acc[1..64] = partial sums of theta^2
+struct PeerSyncBlock {
+  uint32_t flag[kMaxPeers + 1][32];            // flag[r][0]: the last epoch rank r has reached (one 128-byte line each)
+  double inbox[2][kMaxPeers + 1][72];          // [epoch parity][writer rank][accumulator]
+};
+struct PeerBarrierArgs {
+  PeerSyncBlock *blk[kMaxPeers + 1] = {};      // rank r's block as mapped in this process (blk[rank] = the local one)
+  int rank = 0, world = 1;
+  uint32_t epoch = 0;                          // 1, 2, 3, ... (the same sequence on every rank)
+  double *acc = nullptr;                       // kAccSlots local accumulators, replaced by the sum over the ranks
+  int acc_first = 0;                           // accumulators below this index are left alone
+  unsigned int *error = nullptr;               // page-locked host word, set when a peer never arrives
+};
+int launch_peer_barrier(const PeerBarrierArgs &a, cudaStream_t st);
 
 // Adam + L2 of the hot word rows (gradient = sum of the private copies), see opt_kernels.cu
 struct HotUpdateArgs {

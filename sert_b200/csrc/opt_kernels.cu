@@ -108,7 +108,8 @@ __global__ void __launch_bounds__(256) dense_update_kernel(OptimArgs a) {
   const long long base4 = a.first4 + ((long long)blockIdx.x * blockDim.x + threadIdx.x) * CH;
   // phase A: where each chunk lives, whether its row was touched, and every load of every chunk in flight at once
   int sgi[CH];
-  bool act[CH], touched[CH], push[CH];
+  bool act[CH], touched[CH];
+  uint32_t push[CH];               // ranks the new chunk is sent to (bit r = rank r)
   float4 p[CH], g[CH];
   float v1[CH][4], v2[CH][4];
 #pragma unroll
@@ -124,14 +125,18 @@ __global__ void __launch_bounds__(256) dense_update_kernel(OptimArgs a) {
       const ParamSegment &sg = a.seg[s];
       const bool live = (e - sg.offset) < sg.count;   // false only inside inter-segment padding
       bool tch = true, skip = false;
-      push[ch] = a.n_peers > 0;
+      push[ch] = a.n_peers > 0 ? 0xffffffffu : 0u;
       if (live && sg.flags != nullptr) {
         const unsigned int row = (unsigned int)(e - sg.offset) / (unsigned int)sg.row_len;
         const uint32_t flag = __ldg(sg.flags + row);
         tch = (flag == a.stamp);
         skip = (flag == kHotRowMark);       // updated by hot_update_kernel on the side stream
         // table shards with look-ahead: the other ranks only need the rows their next batch reads
-        if (a.n_peers > 0 && a.push_all == 0 && a.need[s] != nullptr) push[ch] = __ldg(a.need[s] + row) == a.need_stamp;
+        // (instance shards: the need word is the mask of the ranks whose instances read the row)
+        if (a.n_peers > 0 && a.push_all == 0 && a.need[s] != nullptr) {
+          const uint32_t nd = __ldg(a.need[s] + row);
+          push[ch] = a.need_is_mask ? nd : (nd == a.need_stamp ? 0xffffffffu : 0u);
+        }
       }
       const bool mine = PHASE == 0 ? true : PHASE == 3 ? (sg.flags != nullptr) : (sg.flags == nullptr);
       sgi[ch] = s;
@@ -165,7 +170,8 @@ __global__ void __launch_bounds__(256) dense_update_kernel(OptimArgs a) {
       const float4 fresh = make_float4(pv[0], pv[1], pv[2], pv[3]);
       out4[i4] = fresh;
       if (push[ch])
-        for (int pr = 0; pr < a.n_peers; ++pr) reinterpret_cast<float4 *>(a.peer_theta[pr])[i4] = fresh;   // NVLink stores
+        for (int pr = 0; pr < a.n_peers; ++pr)
+          if ((push[ch] >> a.peer_rank[pr]) & 1u) reinterpret_cast<float4 *>(a.peer_theta[pr])[i4] = fresh;   // NVLink stores
       if (PHASE == 4 && a.transposed != nullptr && s == a.transposed_segment) {
         // keep the (cols, rows) copy of the projection matrix current for the next step's back-projection
         const unsigned int el = (unsigned int)(e - sg.offset);
@@ -315,6 +321,52 @@ __global__ void __launch_bounds__(128) hot_update_kernel(HotUpdateArgs h) {
     for (int w = 0; w < (int)(blockDim.x >> 5); ++w) tot += s_part[w];
     if (tot != 0.0) atomicAdd(h.acc + 1 + (s & (kSumsqSlots - 1)), tot);
   }
+}
+
+// Instance shards: this rank's share of a hot row's gradient -> the row's owner (kernels.cuh: HotPushArgs)
+__global__ void __launch_bounds__(128) hot_push_kernel(HotPushArgs h) {
+  const int s = blockIdx.x;
+  const int row = __ldg(h.hot_ids + s);
+  int o = 0;
+  for (int q = 1; q < h.n_owner; ++q) o += row >= h.r_bound[q] ? 1 : 0;
+  float *dst = h.grad_peer[o] + (size_t)h.table_offset + (size_t)row * h.d;
+  for (int c = threadIdx.x; c < h.d / 4; c += blockDim.x) {
+    float4 g = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int r = 0; r < kHotReplicas; ++r) {
+      float4 *src = reinterpret_cast<float4 *>(h.hot_acc + ((size_t)r * kMaxHotRows + s) * h.d) + c;
+      const float4 v = __ldcg(src);
+      g.x += v.x; g.y += v.y; g.z += v.z; g.w += v.w;
+      *src = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    red_add_f4(dst + c * 4, g);
+  }
+}
+
+int launch_hot_push(const HotPushArgs &h, cudaStream_t st) {
+  if (h.n_hot <= 0) return 0;
+  SERT_REQUIRE(h.d % 4 == 0 && h.table_offset % 4 == 0, "hot rows must be 16-byte aligned");
+  SERT_REQUIRE(h.n_owner >= 1 && h.n_owner <= kMaxPeers + 1, "bad owner table");
+  const int threads = std::min(128, std::max(32, (h.d / 4 + 31) / 32 * 32));
+  hot_push_kernel<<<h.n_hot, threads, 0, st>>>(h);
+  SERT_LAUNCH_CHECK();
+  return 0;
+}
+
+__global__ void __launch_bounds__(256) push_add_kernel(float4 *__restrict__ src, float *__restrict__ dst, long long n4) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n4) return;
+  const float4 v = __ldcg(src + i);
+  src[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+  red_add_f4(dst + i * 4, v);
+}
+
+int launch_push_add(float *src, float *dst, long long n, cudaStream_t st) {
+  SERT_REQUIRE(n % 4 == 0, "push_add: the range must be a multiple of 4 floats");
+  if (n == 0) return 0;
+  push_add_kernel<<<cdiv(n / 4, 256), 256, 0, st>>>(reinterpret_cast<float4 *>(src), dst, n / 4);
+  SERT_LAUNCH_CHECK();
+  return 0;
 }
 
 int launch_hot_update(const HotUpdateArgs &h, cudaStream_t st) {

@@ -116,6 +116,25 @@ struct sert_model {
   float *pp[2] = {nullptr, nullptr};
   void *pp_peers[2][kMaxPeers + 1] = {};
   int pp_cur = 0;
+  // barrier + sum(theta^2) exchange of the group over NVLink peer memory (csrc/peer_sync.cu); replaces the step's one
+  // ncclAllReduce in mode 2 unless SERT_TABLE_SHARD_BARRIER=nccl
+  PeerSyncBlock *sync_blk = nullptr;
+  void *sync_peers[kMaxPeers + 1] = {};
+  uint32_t sync_epoch = 0;
+  unsigned int *sync_error = nullptr;   // page-locked host word
+  // Mode 3 (instance shards): on top of mode 2, every rank runs the forward / backward of its own instances
+  // [inst_bound[rank], inst_bound[rank + 1]) only and adds the gradient rows into the arena of the rank that updates
+  // them: gradients and touched stamps live in one library-owned block [grad (total) | flagE (E) | flagR (V)] that all
+  // ranks map (gsh_peers); m.grad / m.flagE / m.flagR point into it while the shard is attached.
+  // SERT_TABLE_SHARD_TRACE=1: CUDA events at the phase boundaries of the sharded step on the model's stream; the mean
+  // phase durations are printed to stderr when the shard is released (diagnostic)
+  std::vector<std::vector<cudaEvent_t>> trace;
+  float *gsh = nullptr;
+  void *gsh_peers[kMaxPeers + 1] = {};
+  float *arena_grad = nullptr;
+  uint32_t *arena_flagE = nullptr, *arena_flagR = nullptr;
+  int inst_bound[kMaxPeers + 2] = {};
+  int e_bound[kMaxPeers + 2] = {}, r_bound[kMaxPeers + 2] = {};
   void *rank_scratch = nullptr;    // sert_ll_rank_queries: sort keys and per-query sums (library-owned, grown on demand)
   size_t rank_scratch_bytes = 0;
   float *xstats = nullptr;         // [kMaxShards][2][B*W] gathered (row max, row sum)
@@ -316,11 +335,12 @@ static OptimArgs optim_args(sert_model &m, float *loss_out) {
   a.acc = m.acc; a.loss_out = loss_out;
   a.inv_B = 1.0f / B;
   a.reg_coeff = m.cfg.lambda > 0.f ? m.cfg.lambda / (2.0f * B) : 0.f;
-  if (m.table_comm != nullptr && m.table_mode == 2) {
+  if (m.table_comm != nullptr && m.table_mode >= 2) {
     const int r = m.table_comm->rank, next = m.pp_cur ^ 1;
     a.theta_out = m.pp[next];
     for (int p = 0; p < m.table_comm->world; ++p)
-      if (p != r) a.peer_theta[a.n_peers++] = static_cast<float *>(m.pp_peers[next][p]);
+      if (p != r) { a.peer_rank[a.n_peers] = p; a.peer_theta[a.n_peers++] = static_cast<float *>(m.pp_peers[next][p]); }
+    a.need_is_mask = m.table_mode == 3 ? 1 : 0;
     static const char *dbg = getenv("SERT_TABLE_SHARD_DEBUG");
     if (dbg && strchr(dbg, 'p')) a.n_peers = 0;
     for (int sg = 0; sg < m.nseg; ++sg)
@@ -331,6 +351,68 @@ static OptimArgs optim_args(sert_model &m, float *loss_out) {
 
 // stamp of the step after `stamp` (vs_train_step advances it the same way)
 static uint32_t next_stamp(uint32_t stamp) { return stamp + 1 == kHotRowMark ? 1u : stamp + 1; }
+
+constexpr int kTracePhases = 6;   // step start | tile kernel | side stream joined | barrier A | table update | barrier B
+static bool trace_on() {
+  static const char *e = getenv("SERT_TABLE_SHARD_TRACE");
+  return e != nullptr && e[0] == '1';
+}
+static void trace_mark(sert_model &m, int phase) {
+  if (!trace_on() || m.table_comm == nullptr || m.trace.size() > 400) return;
+  if (phase == 0) m.trace.emplace_back();
+  if (m.trace.empty()) return;
+  cudaEvent_t e;
+  if (cudaEventCreate(&e) != cudaSuccess) return;
+  cudaEventRecord(e, m.st);
+  m.trace.back().push_back(e);
+}
+static void trace_report(sert_model &m) {
+  if (m.trace.empty()) return;
+  cudaStreamSynchronize(m.st);
+  double sum[kTracePhases] = {}, gap = 0.0;
+  int n = 0, ngap = 0;
+  for (size_t i = 20; i < m.trace.size(); ++i) {
+    const auto &ev = m.trace[i];
+    if ((int)ev.size() != kTracePhases) continue;
+    for (int p = 1; p < kTracePhases; ++p) {
+      float ms = 0.f;
+      if (cudaEventElapsedTime(&ms, ev[p - 1], ev[p]) == cudaSuccess) sum[p] += ms;
+    }
+    if (i + 1 < m.trace.size() && (int)m.trace[i + 1].size() == kTracePhases) {
+      float ms = 0.f;
+      if (cudaEventElapsedTime(&ms, ev[kTracePhases - 1], m.trace[i + 1][0]) == cudaSuccess) { gap += ms; ++ngap; }
+    }
+    ++n;
+  }
+  if (n > 0)
+    fprintf(stderr, "[table shard trace] rank %d mode %d steps %d: mark %.1f us | tile %.1f | side join %.1f | barrier A %.1f | "
+            "table update %.1f | join + barrier B %.1f | gap to next step %.1f\n", m.table_comm->rank, m.table_mode, n,
+            0.0, 1e3 * sum[1] / n, 1e3 * sum[2] / n, 1e3 * sum[3] / n, 1e3 * sum[4] / n, 1e3 * sum[5] / n,
+            ngap ? 1e3 * gap / ngap : 0.0);
+  for (auto &ev : m.trace)
+    for (cudaEvent_t e : ev) cudaEventDestroy(e);
+  m.trace.clear();
+}
+
+// One barrier of the table-shard group on the model's stream; acc[acc_first .. 64] become their sums over the ranks.
+static int peer_barrier(sert_model &m, double *acc, int acc_first) {
+  PeerBarrierArgs b;
+  for (int r = 0; r < m.table_comm->world; ++r) b.blk[r] = static_cast<PeerSyncBlock *>(m.sync_peers[r]);
+  b.rank = m.table_comm->rank; b.world = m.table_comm->world;
+  b.epoch = ++m.sync_epoch;
+  b.acc = acc; b.acc_first = acc_first;
+  b.error = m.sync_error;
+  return launch_peer_barrier(b, m.st);
+}
+
+// A peer that never reached a barrier (peer_sync.cu: kTimeoutNs) leaves the parameters of this rank undefined.
+static int peer_barrier_check(sert_model &m) {
+  if (m.sync_error != nullptr && *static_cast<volatile unsigned int *>(m.sync_error) != 0u) {
+    set_error("table shards: a rank of the group did not reach the step's barrier (timeout); the model is invalid");
+    return -1;
+  }
+  return 0;
+}
 
 // Table shards: what follows the update kernels of a step on the model's stream.  Mode 1 broadcasts every owner's
 // piece of theta in place.  Both modes sum the owners' partial sum(theta^2) (the loss is finalised after this), and
@@ -351,8 +433,13 @@ static int table_exchange(sert_model &m, double *acc) {
   // diagnostic (timing only, results invalid): SERT_TABLE_SHARD_DEBUG containing 'a' skips the all-reduce, 'p' the
   // peer stores, 'm' the look-ahead marks (every row is sent)
   static const char *dbg = getenv("SERT_TABLE_SHARD_DEBUG");
-  if (!(dbg && strchr(dbg, 'a')) && comm_all_reduce_sum_f64(c, acc + 1, kSumsqSlots, m.st)) return -1;
-  if (m.table_mode == 2) {
+  if (dbg && strchr(dbg, 'a')) {
+  } else if (m.sync_blk != nullptr) {
+    if (peer_barrier(m, acc, m.table_mode == 3 ? 0 : 1)) return -1;   // instance shards: the data loss is partial too
+  } else if (comm_all_reduce_sum_f64(c, acc + 1, kSumsqSlots, m.st)) {
+    return -1;
+  }
+  if (m.table_mode >= 2) {
     m.pp_cur ^= 1;
     m.theta = m.pp[m.pp_cur];
   }
@@ -439,6 +526,9 @@ static int vs_train_step(sert_model &m, const int32_t *x, const int32_t *y, cons
   // update of the hot word rows -- runs on the second stream under the table update, and the scalar loss is
   // written by the NEXT step's tile kernel (or by flush_pending when no step follows).
   const bool lazy = overlap && m.use_fused == 1 && m.WpT != nullptr && vs_tile_supported(dw, de, c.window, c.num_negatives);
+  // instance shards (table-shard mode 3) exist on the lazy path only
+  const bool inst = m.table_comm != nullptr && m.table_mode == 3;
+  SERT_REQUIRE(!inst || lazy, "instance shards need the fused tile kernel and the second stream (sert_model_set_fused / _overlap)");
   if (!lazy && flush_pending(m)) return -1;
   if (set_hot_marks(m, lazy)) return -1;
   m.stamp += 1;
@@ -460,7 +550,9 @@ static int vs_train_step(sert_model &m, const int32_t *x, const int32_t *y, cons
   // table shards, look-ahead: mark the rows the next batch reads; the update kernels send only those
   bool push_all = true;
   static const char *ts_dbg = getenv("SERT_TABLE_SHARD_DEBUG");
-  if (sharded && m.table_mode == 2 && next.x != nullptr && m.table_comm->world > 1 && !(ts_dbg && strchr(ts_dbg, 'm'))) {
+  const bool traced = sharded && lazy;
+  if (traced) trace_mark(m, 0);
+  if (sharded && m.table_mode >= 2 && next.x != nullptr && m.table_comm->world > 1 && !(ts_dbg && strchr(ts_dbg, 'm'))) {
     const int32_t *next_neg = next.neg;
     if (next_neg == nullptr && next.sampled) {
       if (launch_sample_negatives(m.neg_alt, (int64_t)B * c.num_negatives, c.entities, c.seed, m.sample_calls++, st))
@@ -469,9 +561,16 @@ static int vs_train_step(sert_model &m, const int32_t *x, const int32_t *y, cons
       next_neg = m.neg_alt;
     }
     if (next_neg != nullptr) {
-      if (launch_mark_needed(next.x, next.y, next_neg, B, c.window, c.num_negatives, m.need_r, m.need_e,
-                             next_stamp(m.stamp), st))
+      if (inst) {
+        // one block (V + E words): which ranks' instances of the next batch read each row
+        SERT_CUDA(cudaMemsetAsync(m.need_r, 0, ((size_t)c.vocab + (size_t)c.entities) * sizeof(uint32_t), st));
+        if (launch_mark_needed_by(next.x, next.y, next_neg, B, c.window, c.num_negatives, m.need_r, m.need_e,
+                                  m.inst_bound, m.table_comm->world, st))
+          return -1;
+      } else if (launch_mark_needed(next.x, next.y, next_neg, B, c.window, c.num_negatives, m.need_r, m.need_e,
+                                    next_stamp(m.stamp), st)) {
         return -1;
+      }
       push_all = false;
     }
   }
@@ -486,6 +585,21 @@ static int vs_train_step(sert_model &m, const int32_t *x, const int32_t *y, cons
   f.h = m.h; f.da = m.da; f.loss_acc = acc;
   f.B = B; f.W = c.window; f.k = c.num_negatives; f.dw = dw; f.de = de; f.inv_B = 1.0f / (float)B;
   f.own = m.table_own;
+  if (inst) {
+    const int world = m.table_comm->world;
+    f.i0 = m.inst_bound[m.table_comm->rank];
+    f.B = m.inst_bound[m.table_comm->rank + 1];
+    f.n_owner = world;
+    for (int r = 0; r <= world; ++r) { f.e_bound[r] = m.e_bound[r]; f.r_bound[r] = m.r_bound[r]; }
+    for (int r = 0; r < world; ++r) {
+      float *g = static_cast<float *>(m.gsh_peers[r]);
+      uint32_t *fl = reinterpret_cast<uint32_t *>(g + m.total);
+      f.gE_peer[r] = g + m.off[SERT_PARAM_ENTITY_REPR];
+      f.gR_peer[r] = g + m.off[SERT_PARAM_WORD_REPR];
+      f.flagE_peer[r] = fl;
+      f.flagR_peer[r] = fl + c.entities;
+    }
+  }
   if (lazy && m.n_hot > 0) {
     f.hot_slot = m.hot_slot; f.hot_acc = m.hot_acc; f.hot_replicas = kHotReplicas;
   }
@@ -496,6 +610,7 @@ static int vs_train_step(sert_model &m, const int32_t *x, const int32_t *y, cons
   const int fused = m.use_fused ? launch_vs_fused(f, m.WpT, !m.wpt_valid, m.use_fused, st) : 1;
   if (fused == 0) m.wpt_valid = true;
   if (fused < 0) return -1;
+  if (traced) trace_mark(m, 1);
   // table shards: the projection matrix arrives from its owner, whose update alone can keep the transposed copy
   if (!dense_owner) m.wpt_valid = false;
   if (m.want_fused_event) SERT_CUDA(cudaEventRecord(m.ev_fused, st));   // the previous step's loss is final here
@@ -524,7 +639,43 @@ static int vs_train_step(sert_model &m, const int32_t *x, const int32_t *y, cons
     SERT_CUDA(cudaEventRecord(m.ev_fork, st));
     SERT_CUDA(cudaStreamWaitEvent(side, m.ev_fork, 0));
   }
-  if (dense_owner) {
+  if (inst) {
+    // this rank's instances' share of the dense gradients goes straight into the arena of the rank that updates the
+    // projection (float atomics over NVLink), its share of the hot rows' gradients to their owners
+    const int world = m.table_comm->world, Bl = f.B - f.i0;
+    // (accumulated in this rank's own -- otherwise unused -- dense gradient rows first: the split-K GEMM's scalar atomics
+    // are local, one pass of vector reductions carries the sum over NVLink)
+    if (launch_gemm_f32(m.h, m.da, m.grad + m.off[SERT_PARAM_DENSE_W], dw, de, Bl, true, false, dw, de, de,
+                        EPI_ATOMIC_ADD, nullptr, pick_split_k(dw, de, Bl), side))
+      return -1;
+    if (launch_colsum_atomic(m.da, m.grad + m.off[SERT_PARAM_DENSE_B], Bl, de, side)) return -1;
+    if (!dense_owner) {
+      const long long dense0 = m.off[SERT_PARAM_DENSE_W];
+      if (launch_push_add(m.grad + dense0, static_cast<float *>(m.gsh_peers[world - 1]) + dense0, m.total - dense0, side))
+        return -1;
+    }
+    if (m.n_hot > 0) {
+      HotPushArgs hp;
+      hp.hot_acc = m.hot_acc; hp.hot_ids = m.hot_ids; hp.n_hot = m.n_hot; hp.d = dw;
+      hp.table_offset = m.off[SERT_PARAM_WORD_REPR];
+      hp.n_owner = world;
+      for (int r = 0; r <= world; ++r) hp.r_bound[r] = m.r_bound[r];
+      for (int r = 0; r < world; ++r) hp.grad_peer[r] = static_cast<float *>(m.gsh_peers[r]);
+      if (launch_hot_push(hp, side)) return -1;
+    }
+    // every rank's gradient rows must have landed in their owners' arenas before any update reads them
+    SERT_CUDA(cudaEventRecord(m.ev_join, side));
+    SERT_CUDA(cudaStreamWaitEvent(st, m.ev_join, 0));
+    if (traced) trace_mark(m, 2);
+    if (!(ts_dbg && strchr(ts_dbg, 'a')) && peer_barrier(m, nullptr, 0)) return -1;
+    if (traced) trace_mark(m, 3);
+    SERT_CUDA(cudaEventRecord(m.ev_fork, st));
+    SERT_CUDA(cudaStreamWaitEvent(side, m.ev_fork, 0));
+  } else if (traced) {
+    trace_mark(m, 2);
+    trace_mark(m, 3);
+  }
+  if (!inst && dense_owner) {
     if (launch_gemm_f32(m.h, m.da, m.grad + m.off[SERT_PARAM_DENSE_W], dw, de, B, true, false, dw, de, de,
                         EPI_ATOMIC_ADD, nullptr, pick_split_k(dw, de, B), side))
       return -1;
@@ -593,8 +744,10 @@ static int vs_train_step(sert_model &m, const int32_t *x, const int32_t *y, cons
     }
     SERT_CUDA(cudaEventRecord(m.ev_join, side));
     if (timed_update(m, tables, true)) return -1;     // profile mode: events around the table stream, in situ
+    if (traced) trace_mark(m, 4);
     SERT_CUDA(cudaStreamWaitEvent(st, m.ev_join, 0));
     if (sharded && table_exchange(m, acc)) return -1;
+    if (traced) trace_mark(m, 5);
     m.pending_bank = bank;
     m.pending_loss = loss_out;
     return 0;
@@ -1120,7 +1273,22 @@ int sert_model_set_entity_shard_comm(sert_model *m, sert_comm *comm, int64_t ent
 
 static void table_shard_release(sert_model *m) {
   if (m->table_comm == nullptr) return;
-  if (m->table_mode == 2) {
+  trace_report(*m);
+  if (m->gsh != nullptr) {
+    // gradients (zero between steps) and touched stamps return to the arena
+    cudaMemcpyAsync(m->arena_flagE, m->flagE, (size_t)m->cfg.entities * sizeof(uint32_t), cudaMemcpyDeviceToDevice, m->st);
+    cudaMemcpyAsync(m->arena_flagR, m->flagR, (size_t)m->cfg.vocab * sizeof(uint32_t), cudaMemcpyDeviceToDevice, m->st);
+    cudaStreamSynchronize(m->st);
+    for (int sg = 0; sg < m->nseg; ++sg) {
+      if (m->seg[sg].flags == m->flagR) m->seg[sg].flags = m->arena_flagR;
+      else if (m->seg[sg].flags == m->flagE) m->seg[sg].flags = m->arena_flagE;
+    }
+    m->grad = m->arena_grad; m->flagE = m->arena_flagE; m->flagR = m->arena_flagR;
+    comm_unmap_peers(m->table_comm, m->gsh_peers);
+    cudaFree(m->gsh);
+    m->gsh = nullptr;
+  }
+  if (m->table_mode >= 2) {
     // theta returns to its place in the arena
     cudaMemcpyAsync(m->arena_theta, m->theta, (size_t)m->total * sizeof(float), cudaMemcpyDeviceToDevice, m->st);
     cudaStreamSynchronize(m->st);
@@ -1131,8 +1299,14 @@ static void table_shard_release(sert_model *m) {
       m->pp[b] = nullptr;
     }
   }
-  if (m->need_r) cudaFree(m->need_r);
-  if (m->need_e) cudaFree(m->need_e);
+  if (m->sync_blk) {
+    comm_unmap_peers(m->table_comm, m->sync_peers);
+    cudaFree(m->sync_blk);
+    m->sync_blk = nullptr;
+  }
+  if (m->sync_error) { cudaFreeHost(m->sync_error); m->sync_error = nullptr; }
+  m->sync_epoch = 0;
+  if (m->need_r) cudaFree(m->need_r);      // one block: need_r (V words), then need_e (E words)
   m->need_r = m->need_e = nullptr;
   if (m->neg_alt) {
     // m.neg and neg_alt swap roles (look-ahead): the arena's buffer must be the one that stays
@@ -1156,6 +1330,14 @@ int sert_model_set_table_shard_comm(sert_model *m, sert_comm *comm, int32_t peer
   table_shard_release(m);
   if (comm == nullptr) return 0;
   SERT_REQUIRE(comm->world <= kMaxPeers + 1, "table shards span at most 8 ranks (one NVLink domain)");
+  SERT_REQUIRE(peer_stores >= 0 && peer_stores <= 2, "peer_stores: 0 = NCCL broadcasts, 1 = peer stores, 2 = instance shards");
+  if (peer_stores == 2) {
+    const sert_config &c = m->cfg;
+    SERT_REQUIRE(vs_tile_supported(c.word_dim, c.entity_dim, c.window, c.num_negatives) && m->WpT != nullptr && m->st2 != nullptr,
+                 "instance shards need the fused tile kernel (entity_dim 128, word_dim <= 384, window <= 32, <= 15 negatives)");
+    SERT_REQUIRE(c.batch >= 8 * comm->world, "instance shards need at least one tile of 8 instances per rank");
+    SERT_REQUIRE(c.vocab < (1 << 28) && c.entities < (1 << 28), "instance shards: row ids must stay below 2^28");
+  }
   const long long tables4 = m->off[SERT_PARAM_DENSE_W] / 4;      // the two tables come first in the arena (carve)
   SERT_REQUIRE(m->off[SERT_PARAM_ENTITY_REPR] < m->off[SERT_PARAM_DENSE_W] &&
                m->off[SERT_PARAM_WORD_REPR] < m->off[SERT_PARAM_DENSE_W] &&
@@ -1197,11 +1379,10 @@ int sert_model_set_table_shard_comm(sert_model *m, sert_comm *comm, int32_t peer
   }
   m->wpt_valid = false;
   if (peer_stores) {
-    SERT_CUDA(cudaMalloc(&m->need_r, (size_t)V * sizeof(uint32_t)));
-    SERT_CUDA(cudaMalloc(&m->need_e, (size_t)E * sizeof(uint32_t)));
+    SERT_CUDA(cudaMalloc(&m->need_r, (size_t)(V + E) * sizeof(uint32_t)));
+    m->need_e = m->need_r + V;
     SERT_CUDA(cudaMalloc(&m->neg_alt, (size_t)m->cfg.batch * m->cfg.num_negatives * sizeof(int32_t)));
-    SERT_CUDA(cudaMemsetAsync(m->need_r, 0, (size_t)V * sizeof(uint32_t), m->st));
-    SERT_CUDA(cudaMemsetAsync(m->need_e, 0, (size_t)E * sizeof(uint32_t), m->st));
+    SERT_CUDA(cudaMemsetAsync(m->need_r, 0, (size_t)(V + E) * sizeof(uint32_t), m->st));
     m->neg_presampled = false;
     m->arena_theta = m->theta;
     for (int b = 0; b < 2; ++b) {
@@ -1220,9 +1401,50 @@ int sert_model_set_table_shard_comm(sert_model *m, sert_comm *comm, int32_t peer
     }
     m->pp_cur = 0;
     m->theta = m->pp[0];
+    const char *how = getenv("SERT_TABLE_SHARD_BARRIER");
+    SERT_REQUIRE(peer_stores != 2 || !(how && strcmp(how, "nccl") == 0), "instance shards use the peer-memory barrier");
+    if (!(how && strcmp(how, "nccl") == 0)) {
+      SERT_CUDA(cudaMalloc(&m->sync_blk, sizeof(PeerSyncBlock)));
+      SERT_CUDA(cudaMemsetAsync(m->sync_blk, 0, sizeof(PeerSyncBlock), m->st));
+      SERT_CUDA(cudaHostAlloc(&m->sync_error, sizeof(unsigned int), cudaHostAllocMapped | cudaHostAllocPortable));
+      *m->sync_error = 0u;
+      m->sync_epoch = 0;
+      // the all-gather inside comm_map_peers orders every rank's memset before any peer's first flag store
+      if (comm_map_peers(comm, m->sync_blk, m->sync_peers, m->st)) {
+        cudaFree(m->sync_blk);
+        m->sync_blk = nullptr;
+        return -1;
+      }
+    }
+  }
+  if (peer_stores == 2) {
+    // instance shards: gradients and touched stamps move into one block that every rank maps
+    const size_t bytes = (size_t)m->total * sizeof(float) + (size_t)(E + V) * sizeof(uint32_t);
+    SERT_CUDA(cudaMalloc(&m->gsh, bytes));
+    uint32_t *fl = reinterpret_cast<uint32_t *>(m->gsh + m->total);
+    SERT_CUDA(cudaMemcpyAsync(m->gsh, m->grad, (size_t)m->total * sizeof(float), cudaMemcpyDeviceToDevice, m->st));
+    SERT_CUDA(cudaMemcpyAsync(fl, m->flagE, (size_t)E * sizeof(uint32_t), cudaMemcpyDeviceToDevice, m->st));
+    SERT_CUDA(cudaMemcpyAsync(fl + E, m->flagR, (size_t)V * sizeof(uint32_t), cudaMemcpyDeviceToDevice, m->st));
+    if (comm_map_peers(comm, m->gsh, m->gsh_peers, m->st)) {
+      cudaFree(m->gsh);
+      m->gsh = nullptr;
+      return -1;
+    }
+    m->arena_grad = m->grad; m->arena_flagE = m->flagE; m->arena_flagR = m->flagR;
+    for (int sg = 0; sg < m->nseg; ++sg) {
+      if (m->seg[sg].flags == m->flagR) m->seg[sg].flags = fl + E;
+      else if (m->seg[sg].flags == m->flagE) m->seg[sg].flags = fl;
+    }
+    m->grad = m->gsh; m->flagE = fl; m->flagR = fl + E;
+    const int tiles = cdiv(m->cfg.batch, 8);
+    for (int r = 0; r <= comm->world; ++r) {
+      m->inst_bound[r] = std::min<long long>(m->cfg.batch, (long long)tiles * r / comm->world * 8);
+      m->e_bound[r] = (int)e_row[r];
+      m->r_bound[r] = (int)r_row[r];
+    }
   }
   m->table_comm = comm;
-  m->table_mode = peer_stores ? 2 : 1;
+  m->table_mode = peer_stores == 2 ? 3 : peer_stores ? 2 : 1;
   SERT_CUDA(cudaStreamSynchronize(m->st));
   return 0;
 }
@@ -1370,6 +1592,7 @@ int sert_losses_fetch(sert_model *m, int32_t first_slot, int64_t n, float *out_h
   if (n > 0)
     SERT_CUDA(cudaMemcpyAsync(out_host, m->losses + first_slot, n * sizeof(float), cudaMemcpyDeviceToHost, m->st));
   SERT_CUDA(cudaStreamSynchronize(m->st));
+  if (peer_barrier_check(*m)) return -1;
   for (int64_t j = 0; j < n; ++j) {
     if (!isfinite(out_host[j])) {
       // message mirrors sert/models.py:372-379

@@ -129,6 +129,37 @@ int launch_mark_needed(const int32_t *x, const int32_t *y, const int32_t *neg, i
   return 0;
 }
 
+// instance shards: which ranks' instances of the next batch read a row (kernels.cuh: launch_mark_needed_by)
+struct InstanceBounds { int b[kMaxOwners + 1]; };
+__global__ void __launch_bounds__(256) mark_needed_by_kernel(const int32_t *__restrict__ x, const int32_t *__restrict__ y,
+                                                             const int32_t *__restrict__ neg, long long nx, long long ny,
+                                                             long long nn, int W, int k, uint32_t *__restrict__ need_r,
+                                                             uint32_t *__restrict__ need_e, InstanceBounds ib, int n_ranks) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  int inst, row;
+  uint32_t *dst;
+  if (i < nx) { inst = (int)(i / W); row = __ldg(x + i); dst = need_r; }
+  else if (i < nx + ny) { inst = (int)(i - nx); row = __ldg(y + inst); dst = need_e; }
+  else if (i < nx + ny + nn) { inst = (int)((i - nx - ny) / k); row = __ldg(neg + (i - nx - ny)); dst = need_e; }
+  else return;
+  int r = 0;
+  for (int q = 1; q < n_ranks; ++q) r += inst >= ib.b[q] ? 1 : 0;
+  const uint32_t bit = 1u << r;
+  if ((__ldcg(dst + row) & bit) == 0u) atomicOr(dst + row, bit);
+}
+
+int launch_mark_needed_by(const int32_t *x, const int32_t *y, const int32_t *neg, int B, int W, int k, uint32_t *need_r,
+                          uint32_t *need_e, const int *i_bound, int n_ranks, cudaStream_t st) {
+  SERT_REQUIRE(n_ranks >= 1 && n_ranks <= kMaxOwners, "bad rank count");
+  const long long nx = (long long)B * W, ny = B, nn = (long long)B * k;
+  if (nx + ny + nn == 0) return 0;
+  InstanceBounds ib;
+  for (int r = 0; r <= n_ranks; ++r) ib.b[r] = i_bound[r];
+  mark_needed_by_kernel<<<cdiv(nx + ny + nn, 256), 256, 0, st>>>(x, y, neg, nx, ny, nn, W, k, need_r, need_e, ib, n_ranks);
+  SERT_LAUNCH_CHECK();
+  return 0;
+}
+
 int launch_scatter_rows(const int32_t *x, const float *dh, float *gR, uint32_t *flagR, uint32_t stamp,
                         int B, int W, int d, float denom, cudaStream_t st, int row_lo, int row_hi) {
   SERT_REQUIRE(d % 4 == 0, "representation size must be a multiple of 4");

@@ -37,6 +37,8 @@ constexpr int kMaxNW = 3;             // word rows of up to 3 x 128 floats
 constexpr int kMaxRows = 16;          // 1 + k scores per instance handled by the butterfly
 constexpr int kMaxWindow = 32;
 constexpr int kSkipRow = (int)0x80000000;   // gradient destination of a row another rank updates (table shards)
+constexpr int kOwnerShift = 28;             // instance shards: destination = row | owner << 28 (VsFusedArgs::n_owner)
+constexpr int kRowMask = (1 << kOwnerShift) - 1;
 constexpr int kRowsPerWarp = kD / kT; // matrix rows per warp in the K-split products
 constexpr int kPartFloats = kT * kT * kD;   // 8 warps x 8 instances x 128 partial products (32 KB)
 
@@ -159,8 +161,9 @@ __global__ void __launch_bounds__(kThreads, NW == 1 ? 4 : 3) vs_tile_kernel(VsFu
     return;
   }
   const int W = a.W, K1 = a.k + 1;
-  const int i = blockIdx.x * kT + warp;  // warp == instance, everywhere but inside tile_matvec
+  const int i = a.i0 + blockIdx.x * kT + warp;  // warp == instance, everywhere but inside tile_matvec
   const bool ok = i < a.B;
+  const size_t il = (size_t)(i - a.i0);         // row of the instance in h / da (instance shards start at i0)
   const float4 *R4 = reinterpret_cast<const float4 *>(a.R);
   const float4 *E4 = reinterpret_cast<const float4 *>(a.Eemb);
   float *my_ent = scratch + (size_t)warp * K1 * kD;
@@ -171,7 +174,18 @@ __global__ void __launch_bounds__(kThreads, NW == 1 ? 4 : 3) vs_tile_kernel(VsFu
   int xi = 0, ri = 0, xdst = kSkipRow, rdst = kSkipRow;
   if (ok && lane < W) {
     xi = __ldg(a.x + (size_t)i * W + lane);
-    if (a.own.word(xi)) {
+    if (a.n_owner > 0) {
+      // instance shards: the row's gradient is formed in the arena of the rank that updates it
+      const int slot = a.hot_slot != nullptr ? (int)__ldg(a.hot_slot + xi) : -1;
+      if (slot >= 0) {
+        xdst = -1 - slot;
+      } else {
+        int o = 0;
+        for (int q = 1; q < a.n_owner; ++q) o += xi >= a.r_bound[q] ? 1 : 0;
+        a.flagR_peer[o][xi] = a.stamp;
+        xdst = xi | (o << kOwnerShift);
+      }
+    } else if (a.own.word(xi)) {
       const int slot = a.hot_slot != nullptr ? (int)__ldg(a.hot_slot + xi) : -1;
       xdst = slot < 0 ? xi : -1 - slot;
       if (slot < 0) a.flagR[xi] = a.stamp;   // hot rows keep their kHotRowMark
@@ -179,7 +193,12 @@ __global__ void __launch_bounds__(kThreads, NW == 1 ? 4 : 3) vs_tile_kernel(VsFu
   }
   if (ok && lane < K1) {
     ri = lane == 0 ? __ldg(a.y + i) : __ldg(a.neg + (size_t)i * a.k + lane - 1);
-    if (a.own.entity(ri)) {
+    if (a.n_owner > 0) {
+      int o = 0;
+      for (int q = 1; q < a.n_owner; ++q) o += ri >= a.e_bound[q] ? 1 : 0;
+      a.flagE_peer[o][ri] = a.stamp;
+      rdst = ri | (o << kOwnerShift);
+    } else if (a.own.entity(ri)) {
       a.flagE[ri] = a.stamp;
       rdst = ri;
     }
@@ -207,7 +226,7 @@ __global__ void __launch_bounds__(kThreads, NW == 1 ? 4 : 3) vs_tile_kernel(VsFu
     h[u].x = __fdiv_rn(h[u].x, den); h[u].y = __fdiv_rn(h[u].y, den);
     h[u].z = __fdiv_rn(h[u].z, den); h[u].w = __fdiv_rn(h[u].w, den);
     reinterpret_cast<float4 *>(hbuf + warp * kLdH)[lane + 32 * u] = h[u];          // chunks beyond dw hold zeros
-    if (ok && lane + 32 * u < dw4) reinterpret_cast<float4 *>(a.h)[(size_t)i * dw4 + lane + 32 * u] = h[u];
+    if (ok && lane + 32 * u < dw4) reinterpret_cast<float4 *>(a.h)[il * dw4 + lane + 32 * u] = h[u];
   }
 
   // ---- C: t = tanh(h . Wp + bp) (sert/models.py:1055-1061) --------------------------------------------------
@@ -267,7 +286,9 @@ __global__ void __launch_bounds__(kThreads, NW == 1 ? 4 : 3) vs_tile_kernel(VsFu
       const int r = __shfl_sync(0xffffffffu, rdst, jj);
       const float4 e = reinterpret_cast<const float4 *>(my_ent + jj * kD)[lane];
       f4_fma(du, c, e);
-      if (ok && r != kSkipRow) red_add_f4(a.gE + ((size_t)r * kD4 + lane) * 4, make_float4(c * u.x, c * u.y, c * u.z, c * u.w));
+      if (ok && r != kSkipRow)
+        red_add_f4(a.gE_peer[r >> kOwnerShift] + ((size_t)(r & kRowMask) * kD4 + lane) * 4,
+                   make_float4(c * u.x, c * u.y, c * u.z, c * u.w));
     }
     float4 da;
     da.x = (t.x >= SERT_TANH_LO && t.x <= SERT_TANH_HI) ? du.x * (1.0f - t.x * t.x) : 0.f;
@@ -275,7 +296,7 @@ __global__ void __launch_bounds__(kThreads, NW == 1 ? 4 : 3) vs_tile_kernel(VsFu
     da.z = (t.z >= SERT_TANH_LO && t.z <= SERT_TANH_HI) ? du.z * (1.0f - t.z * t.z) : 0.f;
     da.w = (t.w >= SERT_TANH_LO && t.w <= SERT_TANH_HI) ? du.w * (1.0f - t.w * t.w) : 0.f;
     reinterpret_cast<float4 *>(hbuf + warp * kLd)[lane] = da;     // h is dead since the barriers of C
-    if (ok) reinterpret_cast<float4 *>(a.da)[(size_t)i * kD4 + lane] = da;
+    if (ok) reinterpret_cast<float4 *>(a.da)[il * kD4 + lane] = da;
   }
 
   // ---- E: dh = da . Wp^T, scatter-add of dh / W into the word-gradient rows (the entity rows are dead behind the
@@ -297,7 +318,7 @@ __global__ void __launch_bounds__(kThreads, NW == 1 ? 4 : 3) vs_tile_kernel(VsFu
       for (int w = 0; w < W; ++w) {
         const int r = xs[warp * kMaxWindow + w];
         if (r == kSkipRow) continue;
-        float *row = r >= 0 ? a.gR + (size_t)r * dw : hot + (size_t)(-1 - r) * dw;
+        float *row = r >= 0 ? a.gR_peer[r >> kOwnerShift] + (size_t)(r & kRowMask) * dw : hot + (size_t)(-1 - r) * dw;
 #pragma unroll
         for (int u = 0; u < NW; ++u)
           if (lane + 32 * u < dw4) red_add_f4(row + (lane + 32 * u) * 4, dh[u]);
@@ -324,8 +345,14 @@ bool vs_tile_supported(int dw, int de, int W, int k) {
 }
 
 // returns 0 = launched, 1 = shape not served by this kernel
-int launch_vs_tile(const VsFusedArgs &a, const float *WpT, cudaStream_t st) {
-  if (!vs_tile_supported(a.dw, a.de, a.W, a.k)) return 1;
+int launch_vs_tile(const VsFusedArgs &a_in, const float *WpT, cudaStream_t st) {
+  if (!vs_tile_supported(a_in.dw, a_in.de, a_in.W, a_in.k)) return 1;
+  VsFusedArgs a = a_in;
+  if (a.n_owner == 0) {                 // one destination: the kernel always goes through the owner table
+    a.gE_peer[0] = a.gE; a.gR_peer[0] = a.gR;
+  } else {
+    SERT_REQUIRE(a.n_owner <= kMaxOwners && a.i0 >= 0 && a.i0 <= a.B, "bad instance shard");
+  }
   const size_t smem = std::max((size_t)kT * (a.k + 1) * kD, (size_t)kPartFloats) * sizeof(float);
   static std::atomic<uint64_t> configured{0};
   if (first_use_on_device(configured)) {
@@ -336,7 +363,7 @@ int launch_vs_tile(const VsFusedArgs &a, const float *WpT, cudaStream_t st) {
     SERT_CUDA(cudaFuncSetAttribute(vs_tile_kernel<3, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, most));
   }
   static_assert(kSumsqSlots == 64, "the finalising CTA reads the slots with two warps");
-  const int grid = cdiv(a.B, kT) + 1;                    // + 1: the CTA that finalises the previous loss
+  const int grid = cdiv(a.B - a.i0, kT) + 1;             // + 1: the CTA that finalises the previous loss
   const int nw = (a.dw + kD - 1) / kD;
   if (a.dw == kD) vs_tile_kernel<1, true><<<grid, kThreads, smem, st>>>(a, WpT);
   else if (nw == 1) vs_tile_kernel<1, false><<<grid, kThreads, smem, st>>>(a, WpT);

@@ -690,8 +690,10 @@ class VectorSpaceLanguageModel(VectorSpaceLanguageModelBase):
         """``table_shard``: a ``sert_b200.comm.Communicator`` (one process per GPU of one NVLink domain): ONE model at
         the global batch whose Adam stream over the two tables is split over the ranks (include/sert_b200.h:
         sert_model_set_table_shard_comm).  Every rank must be fed the same batches; parameters, optimiser state and
-        the negative sampler are taken from rank 0.  ``table_shard_peer_stores``: the update kernels write the new
-        parameters into every rank's copy over NVLink (CUDA IPC); False = grouped NCCL broadcasts.
+        the negative sampler are taken from rank 0.  ``table_shard_peer_stores``: True = the update kernels write the
+        new parameters into every rank's copy over NVLink (CUDA IPC); False = grouped NCCL broadcasts;
+        ``'instances'`` (or 2) = peer stores AND each rank runs the forward / backward of its own slice of the batch's
+        instances only, adding the gradient rows into their owners' arenas over NVLink (no NCCL call on the step).
 
         ``optimizer_state_dtype``: 'float32' (the reference's arithmetic; parity mode) or 'bfloat16' (perf mode of
         BASELINE.json configs[1]: Adam's m and v stored as bfloat16 with stochastic rounding, 16 instead of 24 bytes
@@ -733,11 +735,12 @@ class VectorSpaceLanguageModel(VectorSpaceLanguageModelBase):
         self.table_shard = table_shard
         if table_shard is not None:
             N.check(self._native.lib.sert_model_set_table_shard_comm(
-                self._native.handle, table_shard.handle, int(bool(table_shard_peer_stores))))
+                self._native.handle, table_shard.handle,
+                2 if table_shard_peer_stores in ('instances', 2) else int(bool(table_shard_peer_stores))))
         self._create_functions()
 
     def table_shard_info(self):
-        """(mode, own_begin, own_end, table_floats): mode 0 none / 1 broadcast / 2 peer stores; this rank updates the
+        """(mode, own_begin, own_end, table_floats): mode 0 none / 1 broadcast / 2 peer stores / 3 instance shards; this rank updates the
         floats [own_begin, own_end) of the two tables' table_floats."""
         mode, b, e, n = N.ctypes.c_int32(0), N.c_int64(0), N.c_int64(0), N.c_int64(0)
         N.check(self._native.lib.sert_model_table_shard_info(self._native.handle, N.ctypes.byref(mode), N.ctypes.byref(b),

@@ -1,4 +1,6 @@
 """Table-sharded vector-space training (include/sert_b200.h: sert_model_set_table_shard_comm).
+Mode 3 ("instance shards") additionally splits the batch's instances over the ranks: gradient rows are added into
+their owners' arenas over NVLink and the step carries no NCCL call (two barrier kernels over peer memory).
 
 One model at the global batch: every rank computes the step's gradient, each rank streams the Adam update over its
 own piece of the two tables, the new parameters reach the other ranks either by grouped NCCL broadcasts (mode 1) or
@@ -28,8 +30,11 @@ def make_model(p, lam, **kw):
         dense_init=(p['Wp'], p['bp']), **kw)
 
 
-@pytest.mark.parametrize('peer_stores', [True, False])
-@pytest.mark.parametrize('fused,overlap', [(1, 1), (1, 0), (0, 1)])
+MODES = {False: 1, True: 2, 'instances': 3}
+
+
+@pytest.mark.parametrize('peer_stores,fused,overlap', [(ps, f, o) for ps in (True, False) for f, o in ((1, 1), (1, 0), (0, 1))] +
+                         [('instances', 1, 1)])
 def test_world_of_one_matches_oracle(peer_stores, fused, overlap):
     from sert_b200 import _native as N
     from sert_b200.comm import Communicator
@@ -39,7 +44,7 @@ def test_world_of_one_matches_oracle(peer_stores, fused, overlap):
     N.check(model._native.lib.sert_model_set_fused(model._native.handle, fused))
     N.check(model._native.lib.sert_model_set_overlap(model._native.handle, overlap))
     mode, b, e, n = model.table_shard_info()
-    assert mode == (2 if peer_stores else 1) and (b, e) == (0, n) and n == (900 + 300) * 128
+    assert mode == MODES[peer_stores] and (b, e) == (0, n) and n == (900 + 300) * 128
     oracle = H.vs_oracle(p, lam)
     for j, bi in enumerate([3, 0, 4, 1, 2]):
         H.close(model.train_fn(bi, p['neg'][j]), oracle.train_batch(bi, p['neg'][j]), what='train loss step %d' % j)
@@ -76,14 +81,15 @@ for case, dims in enumerate([dict(V=1500, E=700, dw=128, de=128, W=8, B=256, k=1
     kw = dict(batch_size=p['B'], window_size=p['W'], num_negative_samples=p['k'], representations_init=p['R'],
               entity_representations_init=p['Eemb'], regularization_lambda=lam, training_set=p['train'],
               validation_set=p['val'], dense_init=(p['Wp'], p['bp']))
-    for peer_stores in (True, False):
+    # instance shards (each rank runs its own slice of the batch) serve the tile kernel's shapes
+    for peer_stores in (('instances', True, False) if case == 0 else (True, False)):
         # ranks other than 0 start from DIFFERENT parameters: the attach call must bring rank 0's everywhere
         init = dict(kw)
         if rank != 0:
             init['representations_init'] = p['R'] * 0.5
         model = models.VectorSpaceLanguageModel(table_shard=comm, table_shard_peer_stores=peer_stores, **init)
         mode, b, e, n = model.table_shard_info()
-        assert mode == (2 if peer_stores else 1) and 0 <= b < e <= n, (mode, b, e, n)
+        assert mode == {False: 1, True: 2, 'instances': 3}[peer_stores] and 0 <= b < e <= n, (mode, b, e, n)
         spans = [None] * world
         dist.all_gather_object(spans, (b, e))
         assert spans[0][0] == 0 and spans[-1][1] == n and all(spans[i][1] == spans[i + 1][0] for i in range(world - 1)), spans
