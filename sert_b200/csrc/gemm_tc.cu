@@ -53,6 +53,11 @@ struct KernelArgs {
   int num_kb;          // Kt / 64
   int k_slices;        // split-K: the K blocks are cut into this many slices, each a tile of its own (TC_EPI_STORE
                        // with epi.accumulate: partial sums meet in C through float4 reductions)
+  int pair_kp;         // > 0: "pair" operands [hi | mid] (two blocks of pair_kp columns, launch_gemm_tc_pair); num_kb
+                       // then counts 64-column blocks of ONE term, and each takes two ring stages: (A_hi, B_hi) and
+                       // (A_mid, B_mid), from which the MMA warp forms hi.hi + hi.mid + mid.hi -- the three products of
+                       // the bf16x3 split from 96 KB of operands instead of the 144 KB of the [hi|hi|mid] x [hi|mid|hi]
+                       // layout
   TcEpilogue epi;
 };
 
@@ -316,16 +321,19 @@ gemm_tc_kernel(const __grid_constant__ TcMap map_a, const __grid_constant__ TcMa
             tma_load_2d(smem_b + kb * B_STAGE_BYTES, &map_b, bfull_bar, kb * BK, n0);
           bphase ^= 1u;
         }
-        for (int kb = kb0; kb < kb0 + nkb; ++kb) {
+        // ring steps: one per K block, or two (the hi and the mid columns of the block) for pair operands
+        const int per_kb = args.pair_kp > 0 ? 2 : 1;
+        for (int step = kb0 * per_kb; step < (kb0 + nkb) * per_kb; ++step) {
+          const int kc = args.pair_kp > 0 ? (step >> 1) * BK + (step & 1) * args.pair_kp : step * BK;
           mbar_wait(empty_bar(stage), phase ^ 1u);
           mbar_expect_tx(full_bar(stage), BSTAT ? A_STAGE_BYTES : STAGE_BYTES);
-          tma_load_2d(smem_a + stage * A_STAGE_BYTES, &map_a, full_bar(stage), kb * BK, m0);
+          tma_load_2d(smem_a + stage * A_STAGE_BYTES, &map_a, full_bar(stage), kc, m0);
           if (CL > 1) {
             // this CTA's share of the B tile (map_b's box is BN / CL rows), into every CTA of the cluster
             tma_load_2d_multicast(smem_b + stage * B_STAGE_BYTES + cta_rank * (B_STAGE_BYTES / CL), &map_b, full_bar(stage),
-                                  kb * BK, n0 + (int)cta_rank * (BN / CL), (uint16_t)((1u << CL) - 1u));
+                                  kc, n0 + (int)cta_rank * (BN / CL), (uint16_t)((1u << CL) - 1u));
           } else if (!BSTAT) {
-            tma_load_2d(smem_b + stage * B_STAGE_BYTES, &map_b, full_bar(stage), kb * BK, n0);
+            tma_load_2d(smem_b + stage * B_STAGE_BYTES, &map_b, full_bar(stage), kc, n0);
           }
           if (++stage == STAGES) { stage = 0; phase ^= 1u; }
         }
@@ -350,6 +358,37 @@ gemm_tc_kernel(const __grid_constant__ TcMap map_a, const __grid_constant__ TcMa
         mbar_wait(tempty_bar(acc), acc_phase ^ 1u);      // epilogue has drained this accumulator
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + (uint32_t)acc * BN;
+        if (!BSTAT && args.pair_kp > 0) {
+          // pair operands: stage s holds (A_hi, B_hi), stage s + 1 (A_mid, B_mid) of one 64-column block (s is even:
+          // every block takes two steps of the 4-stage ring)
+          static_assert(STAGES % 2 == 0, "pair operands take the ring's stages two at a time");
+          for (int kb = 0; kb < nkb; ++kb) {
+            mbar_wait(full_bar(stage), phase);
+            mbar_wait(full_bar(stage + 1), phase);
+            tc_fence_after();
+            const uint32_t a_hi = smem_a + stage * A_STAGE_BYTES, a_mid = a_hi + A_STAGE_BYTES;
+            const uint32_t b_hi = smem_b + stage * B_STAGE_BYTES, b_mid = b_hi + B_STAGE_BYTES;
+#pragma unroll
+            for (int k = 0; k < BK / UMMA_K; ++k)
+              tc_mma_bf16(d_tmem, make_smem_desc(a_hi + k * UMMA_K * 2), make_smem_desc(b_hi + k * UMMA_K * 2), idesc,
+                          (kb | k) != 0 ? 1u : 0u);
+#pragma unroll
+            for (int k = 0; k < BK / UMMA_K; ++k)
+              tc_mma_bf16(d_tmem, make_smem_desc(a_hi + k * UMMA_K * 2), make_smem_desc(b_mid + k * UMMA_K * 2), idesc, 1u);
+#pragma unroll
+            for (int k = 0; k < BK / UMMA_K; ++k)
+              tc_mma_bf16(d_tmem, make_smem_desc(a_mid + k * UMMA_K * 2), make_smem_desc(b_hi + k * UMMA_K * 2), idesc, 1u);
+            if (CL > 1) {
+              tc_commit_multicast(empty_bar(stage), (uint16_t)((1u << CL) - 1u));
+              tc_commit_multicast(empty_bar(stage + 1), (uint16_t)((1u << CL) - 1u));
+            } else {
+              tc_commit(empty_bar(stage));
+              tc_commit(empty_bar(stage + 1));
+            }
+            stage += 2;
+            if (stage == STAGES) { stage = 0; phase ^= 1u; }
+          }
+        } else
         for (int kb = 0; kb < nkb; ++kb) {
           mbar_wait(full_bar(stage), phase);             // TMA bytes have landed
           tc_fence_after();
@@ -713,10 +752,28 @@ int launch_gemm_tc(const __nv_bfloat16 *A, int M, const __nv_bfloat16 *B, long l
   return launch_gemm_tc_ld(A, Kt, M, B, Kt, N_total, n_begin, n_end, Kt, epi, st);
 }
 
+static int launch_gemm_tc_impl(const __nv_bfloat16 *A, long long lda, int M, const __nv_bfloat16 *B, long long ldb,
+                               long long N_total, long long n_begin, long long n_end, int Kt, int pair_kp,
+                               const TcEpilogue &epi, cudaStream_t st);
+
 int launch_gemm_tc_ld(const __nv_bfloat16 *A, long long lda, int M, const __nv_bfloat16 *B, long long ldb,
                       long long N_total, long long n_begin, long long n_end, int Kt, const TcEpilogue &epi,
                       cudaStream_t st) {
+  return launch_gemm_tc_impl(A, lda, M, B, ldb, N_total, n_begin, n_end, Kt, 0, epi, st);
+}
+
+int launch_gemm_tc_pair(const __nv_bfloat16 *A, int M, const __nv_bfloat16 *B, long long N_total, long long n_begin,
+                        long long n_end, int Kp, const TcEpilogue &epi, cudaStream_t st) {
+  SERT_REQUIRE(epi.mode == TC_EPI_STORE, "pair operands serve the store epilogue");
+  return launch_gemm_tc_impl(A, 2ll * Kp, M, B, 2ll * Kp, N_total, n_begin, n_end, 2 * Kp, Kp, epi, st);
+}
+
+// Kt = columns of the operands the tensor maps cover; pair_kp > 0: [hi | mid] operands of 2 * pair_kp columns
+static int launch_gemm_tc_impl(const __nv_bfloat16 *A, long long lda, int M, const __nv_bfloat16 *B, long long ldb,
+                               long long N_total, long long n_begin, long long n_end, int Kt, int pair_kp,
+                               const TcEpilogue &epi, cudaStream_t st) {
   if (M == 0 || n_end <= n_begin) return 0;
+  SERT_REQUIRE(pair_kp == 0 || (pair_kp % BK == 0 && Kt == 2 * pair_kp), "pair operands: two blocks of Kp columns");
   SERT_REQUIRE(n_begin >= 0 && n_end <= N_total && N_total < (1ll << 31), "bad column range");
   SERT_REQUIRE(Kt > 0 && Kt % BK == 0, "K must be a positive multiple of 64");
   TcMap ma, mb;
@@ -738,8 +795,9 @@ int launch_gemm_tc_ld(const __nv_bfloat16 *A, long long lda, int M, const __nv_b
   args.M = M;
   args.n_begin = n_begin;
   args.n_end = n_end;
-  args.num_kb = Kt / BK;
+  args.num_kb = (pair_kp > 0 ? pair_kp : Kt) / BK;
   args.k_slices = 1;
+  args.pair_kp = pair_kp;
   args.epi = epi;
   const long long m_tiles = (M + BM - 1) / BM, n_tiles = (n_end - n_begin + BN - 1) / BN;
   const long long tiles = m_tiles * n_tiles;
@@ -750,7 +808,7 @@ int launch_gemm_tc_ld(const __nv_bfloat16 *A, long long lda, int M, const __nv_b
   // with the round-2 epilogue it is 4 % faster (4.60 vs 4.79 ms, same box, same run), so it is on by default.
   const long long per_cta = (n_tiles + sms - 1) / sms;
   const char *bstat_env = getenv("SERT_GEMM_BSTAT");
-  const bool bstat = args.num_kb <= STAGES && m_tiles >= 8 && n_tiles >= sms &&
+  const bool bstat = pair_kp == 0 && args.num_kb <= STAGES && m_tiles >= 8 && n_tiles >= sms &&
                      per_cta * sms * 10 <= n_tiles * 12 && !(bstat_env != nullptr && bstat_env[0] == '0');
   if (bstat && epi.mode == TC_EPI_TOPK) {
     gemm_tc_kernel<true, TC_EPI_TOPK><<<(int)std::min<long long>(n_tiles, sms), NUM_THREADS, SMEM_BYTES, st>>>(ma, mb, args);
@@ -762,7 +820,8 @@ int launch_gemm_tc_ld(const __nv_bfloat16 *A, long long lda, int M, const __nv_b
     // split-K: few output tiles and a very deep K (dX = dZ . Wd^T of the log-linear model: 160 tiles, K = 600 k) leave
     // the chip in two unequal waves; slices of the K range become tiles of their own and meet in C by reduction
     int slices = 1;
-    while (tiles * slices < 4ll * sms && args.num_kb / (slices * 2) >= 32) slices *= 2;
+    const int kb_weight = pair_kp > 0 ? 3 : 1;           // a pair block carries three blocks' worth of MMAs
+    while (tiles * slices < 4ll * sms && args.num_kb * kb_weight / (slices * 2) >= 32) slices *= 2;
     const int per = (args.num_kb + slices - 1) / slices;
     args.k_slices = (args.num_kb + per - 1) / per;       // no empty slice
     work = tiles * args.k_slices;
@@ -824,17 +883,21 @@ __global__ void __launch_bounds__(256) split_bf16_kernel(const float *__restrict
       d[0] = hi;
     } else {
       const __nv_bfloat16 mid = __float2bfloat16_rn(x - __bfloat162float(hi));
-      // A'' = [hi | hi | mid],  B'' = [hi | mid | hi]
+      // terms 3: A'' = [hi | hi | mid],  B'' = [hi | mid | hi];  terms 2 (pair operands): [hi | mid]
       d[0] = hi;
-      d[Kp] = role == SPLIT_A ? hi : mid;
-      d[2 * (long long)Kp] = role == SPLIT_A ? mid : hi;
+      if (terms == 2) {
+        d[Kp] = mid;
+      } else {
+        d[Kp] = role == SPLIT_A ? hi : mid;
+        d[2 * (long long)Kp] = role == SPLIT_A ? mid : hi;
+      }
     }
   }
 }
 
 int launch_split_bf16(const float *src, long long rows, int K, long long ld_src, int terms, SplitRole role,
                       __nv_bfloat16 *dst, cudaStream_t st) {
-  SERT_REQUIRE(terms == 1 || terms == 3, "split terms must be 1 or 3");
+  SERT_REQUIRE(terms >= 1 && terms <= 3, "split terms must be 1, 2 (pair operands) or 3");
   if (rows == 0) return 0;
   const int Kp = tc_padded_k(K);
   const long long total = rows * Kp;
@@ -874,7 +937,8 @@ extern "C" SERT_API int sert_debug_gemm_tc(const float *a_host, const float *b_h
   ep.C = dC;
   ep.ldc = n;
   ep.bias = dbias;
-  if (!rc) rc = launch_gemm_tc(sA, m, sB, n, 0, n, Kt, ep, nullptr);
+  if (!rc) rc = terms == 2 ? launch_gemm_tc_pair(sA, m, sB, n, 0, n, Kp, ep, nullptr)
+                           : launch_gemm_tc(sA, m, sB, n, 0, n, Kt, ep, nullptr);
   cudaError_t e = cudaDeviceSynchronize();
   if (!rc && e != cudaSuccess) {
     set_error(std::string("gemm_tc: ") + cudaGetErrorString(e));
@@ -956,8 +1020,12 @@ __global__ void __launch_bounds__(256) split_bf16_t_kernel(const float *__restri
         } else {
           const __nv_bfloat16 mid = __float2bfloat16_rn(x - __bfloat162float(hi));
           d[0] = hi;
-          d[Rp] = role == SPLIT_A ? hi : mid;
-          d[2 * Rp] = role == SPLIT_A ? mid : hi;
+          if (terms == 2) {
+            d[Rp] = mid;
+          } else {
+            d[Rp] = role == SPLIT_A ? hi : mid;
+            d[2 * Rp] = role == SPLIT_A ? mid : hi;
+          }
         }
       }
     }
@@ -967,7 +1035,7 @@ __global__ void __launch_bounds__(256) split_bf16_t_kernel(const float *__restri
 
 int launch_split_bf16_t(const float *src, long long R, long long C, long long ld_src, int terms, SplitRole role,
                         __nv_bfloat16 *dst, cudaStream_t st) {
-  SERT_REQUIRE(terms == 1 || terms == 3, "split terms must be 1 or 3");
+  SERT_REQUIRE(terms >= 1 && terms <= 3, "split terms must be 1, 2 (pair operands) or 3");
   if (R == 0 || C == 0) return 0;
   const long long Rp = tc_padded_k((int)R);
   const long long tiles = ((C + 31) / 32) * (Rp / 32);

@@ -56,7 +56,8 @@ enum SplitRole { SPLIT_A = 0, SPLIT_B = 1 };
 // K padded to a multiple of 64 (one 128-byte swizzle row of bf16); returns the padded K of ONE term.
 static inline int tc_padded_k(int K) { return (int)align_up((size_t)K, 64); }
 
-// dst (rows, terms * Kp) bf16 <- split of src (rows, K) f32 (row stride ld_src); terms in {1, 3}.
+// dst (rows, terms * Kp) bf16 <- split of src (rows, K) f32 (row stride ld_src); terms in {1, 2, 3}
+// (2 = [hi | mid] for launch_gemm_tc_pair, role ignored).
 int launch_split_bf16(const float *src, long long rows, int K, long long ld_src, int terms, SplitRole role,
                       __nv_bfloat16 *dst, cudaStream_t st);
 
@@ -68,6 +69,11 @@ int launch_split_bf16_t(const float *src, long long R, long long C, long long ld
 // Kt = terms * Kp a multiple of 64.  For TC_EPI_STORE column n of C is B row n.
 int launch_gemm_tc(const __nv_bfloat16 *A, int M, const __nv_bfloat16 *B, long long N_total, long long n_begin,
                    long long n_end, int Kt, const TcEpilogue &epi, cudaStream_t st);
+// Pair operands: A (M, 2 Kp) and B (N_total, 2 Kp) hold [hi | mid] (split terms = 2); the kernel forms
+// hi.hi + hi.mid + mid.hi itself from two ring stages per 64-column block -- the same three products as the 3-term
+// layout from two thirds of the operand traffic and storage.  Store epilogue only.
+int launch_gemm_tc_pair(const __nv_bfloat16 *A, int M, const __nv_bfloat16 *B, long long N_total, long long n_begin,
+                        long long n_end, int Kp, const TcEpilogue &epi, cudaStream_t st);
 // Same with explicit row strides (elements): the first Kt columns of wider operands, e.g. the hi.hi term alone of
 // 3-term split operands (Kt = Kp, lda = ldb = 3 Kp).
 int launch_gemm_tc_ld(const __nv_bfloat16 *A, long long lda, int M, const __nv_bfloat16 *B, long long ldb,

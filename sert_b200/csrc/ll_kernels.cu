@@ -306,13 +306,14 @@ __device__ __forceinline__ unsigned short bf16_bits(float x) {
   return __bfloat16_as_ushort(__float2bfloat16_rn(x));
 }
 
-// grid (ceil(E64 / 64), ceil(BW64 / 64)); dZs row stride 3*E64, dZT_s row stride 3*BW64 (elements)
+// grid (ceil(E64 / 64), ceil(BW64 / 64)); dZs row stride terms*E64, dZT_s row stride terms*BW64 (elements);
+// terms 3: A rows [hi | hi | mid], B rows [hi | mid | hi]; terms 2 (pair operands, gemm_tc.cuh): [hi | mid] for both
 __global__ void __launch_bounds__(256) ll_dz_split_kernel(const float *__restrict__ Z, const float *__restrict__ rmax,
                                                           const float *__restrict__ lrsum,
                                                           const float *__restrict__ racc,
                                                           const float *__restrict__ DS, long long rows, int W, int E,
                                                           long long ldz, long long lds, long long E64, long long BW64,
-                                                          __nv_bfloat16 *__restrict__ dZs,
+                                                          int terms, __nv_bfloat16 *__restrict__ dZs,
                                                           __nv_bfloat16 *__restrict__ dZT_s) {
   __shared__ unsigned short t_hi[kDzTile][kDzTile + 2], t_mid[kDzTile][kDzTile + 2];   // [column][row]
   const float log_lo = logf(SERT_CLIP_LO), log_hi = logf(SERT_CLIP_HI);
@@ -361,11 +362,15 @@ __global__ void __launch_bounds__(256) ll_dz_split_kernel(const float *__restric
       // A operand rows [hi | hi | mid]
       const uint2 h2 = make_uint2((unsigned)hi[0] | ((unsigned)hi[1] << 16), (unsigned)hi[2] | ((unsigned)hi[3] << 16));
       const uint2 m2 = make_uint2((unsigned)mid[0] | ((unsigned)mid[1] << 16), (unsigned)mid[2] | ((unsigned)mid[3] << 16));
-      __nv_bfloat16 *row = dZs + r * 3 * E64 + c;
+      __nv_bfloat16 *row = dZs + r * terms * E64 + c;
       if (r < rows) {
         *reinterpret_cast<uint2 *>(row) = h2;
-        *reinterpret_cast<uint2 *>(row + E64) = h2;
-        *reinterpret_cast<uint2 *>(row + 2 * E64) = m2;
+        if (terms == 2) {
+          *reinterpret_cast<uint2 *>(row + E64) = m2;
+        } else {
+          *reinterpret_cast<uint2 *>(row + E64) = h2;
+          *reinterpret_cast<uint2 *>(row + 2 * E64) = m2;
+        }
       }
     }
   }
@@ -380,24 +385,27 @@ __global__ void __launch_bounds__(256) ll_dz_split_kernel(const float *__restric
       hw[j] = (unsigned)t_hi[col][rc + 2 * j] | ((unsigned)t_hi[col][rc + 2 * j + 1] << 16);
       mw[j] = (unsigned)t_mid[col][rc + 2 * j] | ((unsigned)t_mid[col][rc + 2 * j + 1] << 16);
     }
-    __nv_bfloat16 *dst = dZT_s + c * 3 * BW64 + r0 + rc;
-    uint4 *d0 = reinterpret_cast<uint4 *>(dst), *d1 = reinterpret_cast<uint4 *>(dst + BW64),
-          *d2 = reinterpret_cast<uint4 *>(dst + 2 * BW64);
+    __nv_bfloat16 *dst = dZT_s + c * terms * BW64 + r0 + rc;
+    uint4 *d0 = reinterpret_cast<uint4 *>(dst), *d1 = reinterpret_cast<uint4 *>(dst + BW64);
     d0[0] = make_uint4(hw[0], hw[1], hw[2], hw[3]); d0[1] = make_uint4(hw[4], hw[5], hw[6], hw[7]);
     d1[0] = make_uint4(mw[0], mw[1], mw[2], mw[3]); d1[1] = make_uint4(mw[4], mw[5], mw[6], mw[7]);
-    d2[0] = make_uint4(hw[0], hw[1], hw[2], hw[3]); d2[1] = make_uint4(hw[4], hw[5], hw[6], hw[7]);
+    if (terms == 3) {
+      uint4 *d2 = reinterpret_cast<uint4 *>(dst + 2 * BW64);
+      d2[0] = make_uint4(hw[0], hw[1], hw[2], hw[3]); d2[1] = make_uint4(hw[4], hw[5], hw[6], hw[7]);
+    }
   }
 }
 
 int launch_ll_dz_split(const float *Z, const float *rmax, const float *lrsum, const float *racc, const float *DS,
-                       int B, int W, int E, int64_t ldz, int64_t lds, __nv_bfloat16 *dZs, __nv_bfloat16 *dZT_s,
+                       int B, int W, int E, int64_t ldz, int64_t lds, int terms, __nv_bfloat16 *dZs, __nv_bfloat16 *dZT_s,
                        cudaStream_t st) {
+  SERT_REQUIRE(terms == 2 || terms == 3, "dZ operands: 2 (pair) or 3 blocks");
   const long long rows = (long long)B * W;
   if (rows == 0) return 0;
   const long long E64 = (long long)align_up((size_t)E, 64), BW64 = (long long)align_up((size_t)rows, 64);
   dim3 grid((unsigned)(E64 / kDzTile), (unsigned)(BW64 / kDzTile));
   SERT_REQUIRE(grid.y < 65536, "too many rows for the dZ tile grid");
-  ll_dz_split_kernel<<<grid, 256, 0, st>>>(Z, rmax, lrsum, racc, DS, rows, W, E, ldz, lds, E64, BW64, dZs, dZT_s);
+  ll_dz_split_kernel<<<grid, 256, 0, st>>>(Z, rmax, lrsum, racc, DS, rows, W, E, ldz, lds, E64, BW64, terms, dZs, dZT_s);
   SERT_LAUNCH_CHECK();
   return 0;
 }

@@ -47,8 +47,8 @@ int launch_ll_combine_slices(const float2 *stats, int64_t rows, int slots, int64
 int launch_ll_racc_log(const float *Z, const float *rmax, const float *lrsum, const float *DS, int B, int W, int E,
                        int64_t ldz, int64_t lds, float *racc, cudaStream_t st);
 int launch_ll_dz_split(const float *Z, const float *rmax, const float *lrsum, const float *racc, const float *DS,
-                       int B, int W, int E, int64_t ldz, int64_t lds, __nv_bfloat16 *dZs, __nv_bfloat16 *dZT_s,
-                       cudaStream_t st);
+                       int B, int W, int E, int64_t ldz, int64_t lds, int terms, __nv_bfloat16 *dZs, __nv_bfloat16 *dZT_s,
+                       cudaStream_t st);   // terms: 3 = [hi|hi|mid] / [hi|mid|hi] rows, 2 = [hi|mid] (pair operands)
 
 // ---- entity-sharded softmax pieces (columns [e_begin, e_begin+E) of the entity axis live on this rank) ----
 // parts [shard][2][rows] of gathered (row max, row sum) -> global statistics

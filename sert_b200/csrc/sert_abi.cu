@@ -53,6 +53,16 @@ struct Dataset {
 
 using namespace sert;
 
+// Blocks per split operand of the log-linear GEMMs: 2 = pair operands [hi | mid] (gemm_tc.cuh: launch_gemm_tc_pair,
+// default), 3 = the [hi|hi|mid] x [hi|mid|hi] layout (SERT_LL_TERMS=3, for A/B runs).  Read once per process.
+static int ll_terms() {
+  static const int t = [] {
+    const char *e = getenv("SERT_LL_TERMS");
+    return e != nullptr && e[0] == '3' ? 3 : 2;
+  }();
+  return t;
+}
+
 struct sert_model {
   sert_config cfg;
   cudaStream_t st = nullptr;
@@ -290,13 +300,14 @@ static size_t carve(sert_model &m, void *base) {
     m.adot = b.take<float>(B);
     m.racc = b.take<float>(B * W);
     const long long dw64 = tc_padded_k((int)dw), E64 = tc_padded_k((int)E), BW64 = tc_padded_k((int)(B * W));
-    m.Xs = b.take<__nv_bfloat16>(B * W * 3 * dw64);
-    m.WdT_s = b.take<__nv_bfloat16>(E * 3 * dw64);
+    const long long T = ll_terms();      // blocks per split operand
+    m.Xs = b.take<__nv_bfloat16>(B * W * T * dw64);
+    m.WdT_s = b.take<__nv_bfloat16>(E * T * dw64);
     if (train) {
-      m.dZs = b.take<__nv_bfloat16>(B * W * 3 * E64);
-      m.Wd_s = b.take<__nv_bfloat16>(dw * 3 * E64);
-      m.XT_s = b.take<__nv_bfloat16>((dw + 1) * 3 * BW64);    // + a row of ones: the bias gradient falls out of gWd's GEMM
-      m.dZT_s = b.take<__nv_bfloat16>(E * 3 * BW64);
+      m.dZs = b.take<__nv_bfloat16>(B * W * T * E64);
+      m.Wd_s = b.take<__nv_bfloat16>(dw * T * E64);
+      m.XT_s = b.take<__nv_bfloat16>((dw + 1) * T * BW64);    // + a row of ones: the bias gradient falls out of gWd's GEMM
+      m.dZT_s = b.take<__nv_bfloat16>(E * T * BW64);
     }
     m.dbg_ell = b.take<float>(B);
     m.stage_indptr = b.take<int64_t>(B + 1);
@@ -799,6 +810,13 @@ static bool ll_tensor(const sert_model &m, long long M, long long N) {
   return m.use_tensor && ((M + 127) / 128) * ((N + 255) / 256) >= 32;
 }
 
+// C = A . B^T over split operands of ll_terms() blocks of Kp columns
+static int ll_gemm(const __nv_bfloat16 *A, int M, const __nv_bfloat16 *B, long long N_total, long long n_begin,
+                   long long n_end, int Kp, const TcEpilogue &ep, cudaStream_t st) {
+  return ll_terms() == 2 ? launch_gemm_tc_pair(A, M, B, N_total, n_begin, n_end, Kp, ep, st)
+                         : launch_gemm_tc(A, M, B, N_total, n_begin, n_end, 3 * Kp, ep, st);
+}
+
 static int ll_forward(sert_model &m, const int32_t *x, int rows /* instances */, cudaStream_t st,
                       float *rmax_out = nullptr, float *rsum_out = nullptr) {
   const sert_config &c = m.cfg;
@@ -810,15 +828,15 @@ static int ll_forward(sert_model &m, const int32_t *x, int rows /* instances */,
   if (launch_gather_rows(x, R, m.X, BW, dw, st)) return -1;
   if (ll_tensor(m, BW, E)) {
     // Z = X . Wd + bd on the tensor cores: bf16x3 split of X (A) and of Wd^T (B), fp32 accumulation
-    const int kt = 3 * tc_padded_k(dw);
-    if (launch_split_bf16(m.X, BW, dw, dw, 3, SPLIT_A, m.Xs, st)) return -1;
-    if (launch_split_bf16_t(Wd, dw, E, E, 3, SPLIT_B, m.WdT_s, st)) return -1;
+    const int T = ll_terms();
+    if (launch_split_bf16(m.X, BW, dw, dw, T, SPLIT_A, m.Xs, st)) return -1;
+    if (launch_split_bf16_t(Wd, dw, E, E, T, SPLIT_B, m.WdT_s, st)) return -1;
     TcEpilogue ep;
     ep.mode = TC_EPI_STORE; ep.C = m.Z; ep.ldc = E; ep.bias = bd;
     // the epilogue leaves per-slice softmax statistics: no pass over Z for the row maxima and sums
     const int slots = cdiv(E, 64);
     ep.row_stats = m.zstats; ep.stats_ld = slots;
-    if (launch_gemm_tc(m.Xs, (int)BW, m.WdT_s, E, 0, E, kt, ep, st)) return -1;
+    if (ll_gemm(m.Xs, (int)BW, m.WdT_s, E, 0, E, tc_padded_k(dw), ep, st)) return -1;
     return launch_ll_combine_slices(m.zstats, BW, slots, slots, rmax_out ? rmax_out : m.rmax,
                                     rsum_out ? rsum_out : m.rsum, st);
   } else {
@@ -842,12 +860,12 @@ static LlInstanceArgs ll_instance_args(sert_model &m, const int64_t *indptr, lon
 static int ll_backward_gemms(sert_model &m, int BW, int E, int dw, float *Wd, cudaStream_t st) {
   if (ll_tensor(m, dw, E)) {
     // gWd = X^T . dZ : A = X^T (dw, B*W), B = dZ^T (E, B*W), both as transposed bf16x3 splits
-    const int kt = 3 * tc_padded_k(BW);
-    if (launch_split_bf16_t(m.X, BW, dw, dw, 3, SPLIT_A, m.XT_s, st)) return -1;
-    if (launch_split_bf16_t(m.Z, BW, E, E, 3, SPLIT_B, m.dZT_s, st)) return -1;
+    const int T = ll_terms();
+    if (launch_split_bf16_t(m.X, BW, dw, dw, T, SPLIT_A, m.XT_s, st)) return -1;
+    if (launch_split_bf16_t(m.Z, BW, E, E, T, SPLIT_B, m.dZT_s, st)) return -1;
     TcEpilogue ep;
     ep.mode = TC_EPI_STORE; ep.C = m.grad + m.off[SERT_PARAM_DENSE_W]; ep.ldc = E;   // overwrites the (zeroed) grad
-    if (launch_gemm_tc(m.XT_s, dw, m.dZT_s, E, 0, E, kt, ep, st)) return -1;
+    if (ll_gemm(m.XT_s, dw, m.dZT_s, E, 0, E, tc_padded_k(BW), ep, st)) return -1;
   } else {
     if (launch_gemm_f32(m.X, m.Z, m.grad + m.off[SERT_PARAM_DENSE_W], dw, E, BW, true, false, dw, E, E,
                         EPI_ATOMIC_ADD, nullptr, pick_split_k(dw, E, BW), st))
@@ -856,12 +874,12 @@ static int ll_backward_gemms(sert_model &m, int BW, int E, int dw, float *Wd, cu
   if (launch_colsum_atomic(m.Z, m.grad + m.off[SERT_PARAM_DENSE_B], BW, E, st)) return -1;
   if (ll_tensor(m, BW, dw)) {
     // dX = dZ . Wd^T : A = dZ (B*W, E), B = Wd (dw, E)
-    const int kt = 3 * tc_padded_k(E);
-    if (launch_split_bf16(m.Z, BW, E, E, 3, SPLIT_A, m.dZs, st)) return -1;
-    if (launch_split_bf16(Wd, dw, E, E, 3, SPLIT_B, m.Wd_s, st)) return -1;
+    const int T = ll_terms();
+    if (launch_split_bf16(m.Z, BW, E, E, T, SPLIT_A, m.dZs, st)) return -1;
+    if (launch_split_bf16(Wd, dw, E, E, T, SPLIT_B, m.Wd_s, st)) return -1;
     TcEpilogue ep;
     ep.mode = TC_EPI_STORE; ep.C = m.dX; ep.ldc = dw;
-    if (launch_gemm_tc(m.dZs, BW, m.Wd_s, dw, 0, dw, kt, ep, st)) return -1;
+    if (ll_gemm(m.dZs, BW, m.Wd_s, dw, 0, dw, tc_padded_k(E), ep, st)) return -1;
   } else {
     if (launch_gemm_f32(m.Z, Wd, m.dX, BW, dw, E, false, true, E, E, dw, EPI_STORE, nullptr, 1, st)) return -1;
   }
@@ -876,23 +894,22 @@ static bool ll_fused_tail(const sert_model &m, long long BW, long long E, long l
 // racc (complete over all shards) -> dZs / dZT_s -> gWd (+ gbd through the ones row of X^T) and dX
 static int ll_backward_fused(sert_model &m, int B, int W, int E, int dw, float *Wd, cudaStream_t st) {
   const int BW = B * W;
-  if (launch_ll_dz_split(m.Z, m.rmax, m.lrsum, m.racc, m.DS, B, W, E, E, E, m.dZs, m.dZT_s, st)) return -1;
+  const int T = ll_terms();
+  if (launch_ll_dz_split(m.Z, m.rmax, m.lrsum, m.racc, m.DS, B, W, E, E, E, T, m.dZs, m.dZT_s, st)) return -1;
   {
-    const int kt = 3 * tc_padded_k(BW);
-    if (launch_split_bf16_t(m.X, BW, dw, dw, 3, SPLIT_A, m.XT_s, st)) return -1;
+    if (launch_split_bf16_t(m.X, BW, dw, dw, T, SPLIT_A, m.XT_s, st)) return -1;
     TcEpilogue ep;
     ep.mode = TC_EPI_STORE; ep.C = m.grad + m.off[SERT_PARAM_DENSE_W]; ep.ldc = E;   // overwrites the (zeroed) grads
     ep.extra_row = dw; ep.extra_dst = m.grad + m.off[SERT_PARAM_DENSE_B];
-    if (launch_gemm_tc(m.XT_s, dw + 1, m.dZT_s, E, 0, E, kt, ep, st)) return -1;
+    if (ll_gemm(m.XT_s, dw + 1, m.dZT_s, E, 0, E, tc_padded_k(BW), ep, st)) return -1;
   }
   {
-    const int kt = 3 * tc_padded_k(E);
-    if (launch_split_bf16(Wd, dw, E, E, 3, SPLIT_B, m.Wd_s, st)) return -1;
+    if (launch_split_bf16(Wd, dw, E, E, T, SPLIT_B, m.Wd_s, st)) return -1;
     TcEpilogue ep;
     ep.mode = TC_EPI_STORE; ep.C = m.dX; ep.ldc = dw;
     ep.accumulate = 1;                                  // split-K over the entity axis (K = 3 E64)
     SERT_CUDA(cudaMemsetAsync(m.dX, 0, (size_t)BW * dw * sizeof(float), st));
-    if (launch_gemm_tc(m.dZs, BW, m.Wd_s, dw, 0, dw, kt, ep, st)) return -1;
+    if (ll_gemm(m.dZs, BW, m.Wd_s, dw, 0, dw, tc_padded_k(E), ep, st)) return -1;
   }
   return 0;
 }
@@ -1077,11 +1094,12 @@ int sert_model_create(const sert_config *cfg, void *arena_dev, size_t arena_byte
     return -1;
   }
   if (!is_vs(*cfg) && m->XT_s != nullptr) {
-    // the row of ones behind X^T (split [hi | hi | mid] = [1 | 1 | 0] over the B*W real rows): see ll_backward_fused
+    // the row of ones behind X^T (split [hi | hi | mid] = [1 | 1 | 0], or [hi | mid] = [1 | 0] for pair operands, over
+    // the B*W real rows): see ll_backward_fused
     const long long BW = (long long)cfg->batch * cfg->window, BW64 = tc_padded_k((int)BW);
-    __nv_bfloat16 *row = m->XT_s + (size_t)cfg->word_dim * 3 * BW64;
+    __nv_bfloat16 *row = m->XT_s + (size_t)cfg->word_dim * ll_terms() * BW64;
     fill_bf16_kernel<<<cdiv(BW, 256), 256, 0, m->st>>>(row, BW, 1.0f);
-    fill_bf16_kernel<<<cdiv(BW, 256), 256, 0, m->st>>>(row + BW64, BW, 1.0f);
+    if (ll_terms() == 3) fill_bf16_kernel<<<cdiv(BW, 256), 256, 0, m->st>>>(row + BW64, BW, 1.0f);
     count_launch(2);
   }
   if (is_vs(*cfg)) {

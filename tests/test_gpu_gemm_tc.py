@@ -33,6 +33,43 @@ def test_split3_matches_float64(m, n, k):
     assert err1 < 2e-2 * scale, err1          # plain bf16: ~2^-8 relative per product
 
 
+@pytest.mark.parametrize('m,n,k', [(128, 256, 64), (256, 512, 128), (100, 300, 70), (1, 9, 5), (1000, 2000, 128),
+                                   (333, 715, 300), (4096, 777, 256), (2048, 1000, 192), (1152, 513, 1000),
+                                   (8300, 257, 128), (1280, 2000, 320)])
+def test_pair_operands_match_float64_and_the_three_block_layout(m, n, k):
+    """Pair operands [hi | mid] (launch_gemm_tc_pair: two ring stages per 64-column block, hi.hi + hi.mid + mid.hi
+    formed by the MMA warp) compute the same three products as the [hi|hi|mid] x [hi|mid|hi] layout: same error
+    against float64, and the two agree to summation-order noise; single-CTA tiles and clusters (m-tiles >= 8), ragged
+    M / N / K, K of 1 to 16 blocks."""
+    rng = np.random.default_rng(m * 13 + n * 5 + k)
+    a = rng.standard_normal((m, k)).astype(np.float32)
+    b = rng.standard_normal((n, k)).astype(np.float32)
+    bias = rng.standard_normal(n).astype(np.float32)
+    ref = a.astype(np.float64) @ b.astype(np.float64).T + bias
+    got2 = run(a, b, 2, bias)
+    got3 = run(a, b, 3, bias)
+    scale = np.sqrt(k)
+    assert np.abs(got2 - ref).max() < 3e-5 * scale
+    assert np.abs(got2 - got3).max() < 3e-5 * scale      # (a missing cross term would show as ~2e-3 * scale)
+
+
+def test_pair_operands_identity_layout():
+    """Exact check of the pair path's operand placement (hi stage / mid stage, clusters): values whose bf16 split has
+    a non-zero mid term, one non-zero per row, so every output is a single product hi.hi + hi.mid + mid.hi."""
+    for m in (256, 1152):
+        n, k = 768, 192
+        a = np.zeros((m, k), np.float32)
+        b = np.zeros((n, k), np.float32)
+        for i in range(m):
+            a[i, i % k] = np.float32(1.0 + (i % 97) / 1024.0 + 2.0 ** -12)
+        for j in range(n):
+            b[j, (j * 5) % k] = np.float32(0.5 + (j % 89) / 512.0 + 2.0 ** -11)
+        ref = a.astype(np.float64) @ b.astype(np.float64).T
+        got = run(a, b, 2)
+        np.testing.assert_allclose(got, ref, rtol=3e-5, atol=0)
+        assert np.array_equal(got == 0, ref == 0)
+
+
 def test_identity_layout():
     """Each output column picks one B row: catches swizzle / descriptor / TMEM lane mistakes exactly."""
     m, n, k = 256, 512, 128
