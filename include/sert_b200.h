@@ -342,10 +342,12 @@ SERT_API int sert_topk_merge_dev(const int32_t *idx_dev, const float *score_dev,
                         int32_t *out_idx_dev, float *out_score_dev, void *stream);
 
 /* ---- test hook -------------------------------------------------------------------------------- */
-/* C (m,n) = A (m,k) . B (n,k)^T (+ bias (n,)) through the tcgen05/TMEM/TMA GEMM with `terms` (1 or 3) bf16
- * split terms per operand; host in / host out.  Used by tests/test_gpu_gemm_tc.py only. */
+/* C (m,n) = A (m,k) . B (n,k)^T (+ bias (n,)) through the tcgen05/TMEM/TMA GEMM with `terms` bf16 split terms per
+ * operand (1; 3 = [hi|hi|mid] x [hi|mid|hi]; 2 = pair operands [hi|mid], the log-linear path); host in / host out.  Used by tests/test_gpu_gemm_tc.py only. */
 SERT_API int sert_debug_gemm_tc(const float *a_host, const float *b_host, int m, int n, int k, int terms,
                                 const float *bias_host, float *c_host);
+/* the same product with B given transposed, bt_host (k, n) row-major: the N-major B operand of the pair path */
+SERT_API int sert_debug_gemm_tc_bn(const float *a_host, const float *bt_host, int m, int n, int k, float *c_host);
 /* Raw throughput of the tcgen05 kernel on zero operands (mode 0: store epilogue into one aliased row, mode 1:
  * top-k filter that rejects everything); mean launch time in ms.  Used by tools/gemm_bench.py only. */
 SERT_API int sert_debug_gemm_tc_bench(int m, int n, int kt, int reps, int mode, float *ms_out);

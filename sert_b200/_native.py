@@ -102,6 +102,7 @@ SIGNATURES = {
     'sert_scorer_scores_host': (c_int, [c_void_p, c_void_p, c_int32, c_int32, c_void_p]),
     'sert_scorer_topk_dev': (c_int, [c_void_p, c_void_p, c_int32, c_int32, c_int32, c_void_p, c_void_p]),
     'sert_debug_gemm_tc': (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
+    'sert_debug_gemm_tc_bn': (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
     'sert_topk_merge_dev': (c_int, [c_void_p, c_void_p, c_int32, c_int32, c_int32, c_void_p, c_void_p, c_void_p]),
 }
 

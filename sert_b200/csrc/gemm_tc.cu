@@ -53,6 +53,11 @@ struct KernelArgs {
   int num_kb;          // Kt / 64
   int k_slices;        // split-K: the K blocks are cut into this many slices, each a tile of its own (TC_EPI_STORE
                        // with epi.accumulate: partial sums meet in C through float4 reductions)
+  int b_nmajor;        // 1 (pair operands, single-CTA tiles): B lies N-major in global memory -- rows = K, columns = N, the
+                       // hi block behind map_b and the mid block behind map_b2 (boxes of 64 N x 64 K); the MMA reads it
+                       // through an MN-major descriptor.  Lets gWd = X^T . dZ of the log-linear model consume the same
+                       // split dZ rows as dX = dZ . Wd^T, so no transposed copy of dZ is ever written.
+  int n_fast;          // 1: tiles are numbered n-fastest inside a K slice (cta_tile)
   int pair_kp;         // > 0: "pair" operands [hi | mid] (two blocks of pair_kp columns, launch_gemm_tc_pair); num_kb
                        // then counts 64-column blocks of ONE term, and each takes two ring stages: (A_hi, B_hi) and
                        // (A_mid, B_mid), from which the MMA warp forms hi.hi + hi.mid + mid.hi -- the three products of
@@ -73,7 +78,28 @@ struct KernelArgs {
 // CTAs walk the tiles as a pair (num_m_tiles then counts pairs of m-tiles).
 template <bool BSTAT>
 __device__ __forceinline__ bool cta_tile(int it, int bid, int gdim, int num_m_tiles, int num_n_tiles, int k_slices,
-                                         int step_m, int step_n, int &mt, int &nt, int &seq, int &slice) {
+                                         int step_m, int step_n, int &mt, int &nt, int &seq, int &slice,
+                                         bool n_fast = false) {
+  if (!BSTAT && n_fast) {
+    // n-fastest numbering inside a K slice (store epilogue with a handful of n-tiles and a huge A operand -- dX of the
+    // log-linear model): the n-tiles that share an A tile are neighbours in the tile order, so the CTAs working on
+    // them run side by side and the second read of the A blocks hits L2.  step_m / step_n are then the steps of the
+    // (n, slice * m-tiles + m) numbering.
+    int fast, slow;
+    if (it == 0) {
+      fast = bid % num_n_tiles;
+      slow = bid / num_n_tiles;
+    } else {
+      fast = nt - slice * num_n_tiles + step_m;
+      slow = slice * num_m_tiles + mt + step_n;
+      if (fast >= num_n_tiles) { fast -= num_n_tiles; ++slow; }
+    }
+    seq = 0;
+    slice = slow / num_m_tiles;
+    mt = slow - slice * num_m_tiles;
+    nt = slice * num_n_tiles + fast;
+    return slice < k_slices;
+  }
   slice = 0;
   if (BSTAT) {
     if (it == 0) {
@@ -238,6 +264,20 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr) {
   d |= (uint64_t)2 << 61;
   return d;
 }
+// The same for an MN-major operand (tile stored [K rows][64 MN elements] in 128-byte swizzled rows, 64 K rows = 8 KB per
+// group of 64 MN elements, as four TMA boxes of 64 x 64 leave it): canonical layout ((8,n),(8,k)):((1,LBO),(8,SBO)) in
+// 16-byte units -- LBO = distance between groups of 64 MN elements (8192 B), SBO = distance between groups of 8 K rows
+// (1024 B).  One MMA step (K = 16) advances the start address by 16 rows = 2048 B.
+__device__ __forceinline__ uint64_t make_smem_desc_mn(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr & 0x3ffffu) >> 4);
+  d |= (uint64_t)(8192 >> 4) << 16;
+  d |= (uint64_t)(1024 >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+constexpr uint32_t IDESC_B_MN_MAJOR = 1u << 16;   // instruction descriptor bit 16: B is MN-major
 // Instruction descriptor (kind::f16): D fp32 (bits 4-5 = 1), A/B bf16 (bits 7-9, 10-12 = 1), both K-major,
 // N >> 3 at [17,23), M >> 4 at [24,29).
 constexpr uint32_t make_idesc(int m, int n) {
@@ -254,7 +294,8 @@ constexpr uint32_t make_idesc(int m, int n) {
 // empty barriers).
 template <bool BSTAT, int MODE, int CL = 1>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
-gemm_tc_kernel(const __grid_constant__ TcMap map_a, const __grid_constant__ TcMap map_b, const KernelArgs args) {
+gemm_tc_kernel(const __grid_constant__ TcMap map_a, const __grid_constant__ TcMap map_b, const __grid_constant__ TcMap map_b2,
+               const KernelArgs args) {
   extern __shared__ unsigned char smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;   // SWIZZLE_128B needs 1024-byte alignment
   const uint32_t smem_a = smem_base;
@@ -278,11 +319,14 @@ gemm_tc_kernel(const __grid_constant__ TcMap map_a, const __grid_constant__ TcMa
   const uint32_t cta_rank = CL > 1 ? cluster_cta_rank() : 0u;
   const int bid = (int)blockIdx.x / CL, gdim = (int)gridDim.x / CL;
   const int walk_m_tiles = (num_m_tiles + CL - 1) / CL;                  // m-tiles, or pairs of m-tiles
-  const int step_m = gdim % walk_m_tiles, step_n = gdim / walk_m_tiles;
+  const bool n_fast = !BSTAT && args.n_fast != 0;
+  const int walk_fast = n_fast ? num_n_tiles : walk_m_tiles;
+  const int step_m = gdim % walk_fast, step_n = gdim / walk_fast;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&map_a);
     tma_prefetch_desc(&map_b);
+    tma_prefetch_desc(&map_b2);
     for (int s = 0; s < STAGES; ++s) {
       mbar_init(full_bar(s), 1);
       mbar_init(empty_bar(s), CL);            // one arrival per MMA warp that reads the slot
@@ -309,7 +353,7 @@ gemm_tc_kernel(const __grid_constant__ TcMap map_a, const __grid_constant__ TcMa
       int stage = 0;
       uint32_t phase = 0, bphase = 0;
       int mt, nt, seq, slice;
-      for (int it = 0; cta_tile<BSTAT>(it, bid, gdim, walk_m_tiles, num_n_tiles, args.k_slices, step_m, step_n, mt, nt, seq, slice); ++it) {
+      for (int it = 0; cta_tile<BSTAT>(it, bid, gdim, walk_m_tiles, num_n_tiles, args.k_slices, step_m, step_n, mt, nt, seq, slice, n_fast); ++it) {
         const int m0 = (mt * CL + (int)cta_rank) * BM;
         const int n0 = (int)(args.n_begin + (long long)slice_nt(nt, num_n_tiles, slice) * BN * args.epi.tile_stride);
         int kb0, nkb;
@@ -332,6 +376,12 @@ gemm_tc_kernel(const __grid_constant__ TcMap map_a, const __grid_constant__ TcMa
             // this CTA's share of the B tile (map_b's box is BN / CL rows), into every CTA of the cluster
             tma_load_2d_multicast(smem_b + stage * B_STAGE_BYTES + cta_rank * (B_STAGE_BYTES / CL), &map_b, full_bar(stage),
                                   kc, n0 + (int)cta_rank * (BN / CL), (uint16_t)((1u << CL) - 1u));
+          } else if (!BSTAT && args.b_nmajor) {
+            // N-major B: K rows [block * 64, +64) of the hi (even step) or mid (odd step) block, four boxes of 64 columns
+            const TcMap *mb = (step & 1) ? &map_b2 : &map_b;
+#pragma unroll
+            for (int g = 0; g < BN / 64; ++g)
+              tma_load_2d(smem_b + stage * B_STAGE_BYTES + g * (64 * BK * 2), mb, full_bar(stage), n0 + g * 64, (step >> 1) * BK);
           } else if (!BSTAT) {
             tma_load_2d(smem_b + stage * B_STAGE_BYTES, &map_b, full_bar(stage), kc, n0);
           }
@@ -342,18 +392,25 @@ gemm_tc_kernel(const __grid_constant__ TcMap map_a, const __grid_constant__ TcMa
   } else if (warp == 1) {
     // ================= MMA issuer =================
     if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc(BM, BN);
+      constexpr uint32_t idesc_full = make_idesc(BM, BN);
       int stage = 0;
       uint32_t phase = 0;
       int acc = 0;
       uint32_t acc_phase = 0, bphase = 0;
       int mt, nt, seq, slice;
-      for (int it = 0; cta_tile<BSTAT>(it, bid, gdim, walk_m_tiles, num_n_tiles, args.k_slices, step_m, step_n, mt, nt, seq, slice); ++it) {
+      for (int it = 0; cta_tile<BSTAT>(it, bid, gdim, walk_m_tiles, num_n_tiles, args.k_slices, step_m, step_n, mt, nt, seq, slice, n_fast); ++it) {
         int kb0, nkb;
         slice_range(args.num_kb, args.k_slices, slice, kb0, nkb);
         if (BSTAT && seq == 0) {
           mbar_wait(bfull_bar, bphase);                  // this n-tile's B blocks have landed
           bphase ^= 1u;
+        }
+        // Store epilogue: a ragged last n-tile only multiplies the columns that exist (N rounded up to 16) -- dX of the
+        // log-linear model has 320 columns, and a full-width second tile spent 37 % of the GEMM's MMA time on padding
+        uint32_t idesc = idesc_full;
+        if (MODE == TC_EPI_STORE) {
+          const long long n_left = args.n_end - (args.n_begin + (long long)slice_nt(nt, num_n_tiles, slice) * BN * args.epi.tile_stride);
+          if (n_left < BN) idesc = make_idesc(BM, (int)((n_left + 15) / 16 * 16));
         }
         mbar_wait(tempty_bar(acc), acc_phase ^ 1u);      // epilogue has drained this accumulator
         tc_fence_after();
@@ -368,6 +425,19 @@ gemm_tc_kernel(const __grid_constant__ TcMap map_a, const __grid_constant__ TcMa
             tc_fence_after();
             const uint32_t a_hi = smem_a + stage * A_STAGE_BYTES, a_mid = a_hi + A_STAGE_BYTES;
             const uint32_t b_hi = smem_b + stage * B_STAGE_BYTES, b_mid = b_hi + B_STAGE_BYTES;
+            if (args.b_nmajor) {
+              const uint32_t idn = idesc | IDESC_B_MN_MAJOR;
+#pragma unroll
+              for (int k = 0; k < BK / UMMA_K; ++k)
+                tc_mma_bf16(d_tmem, make_smem_desc(a_hi + k * UMMA_K * 2), make_smem_desc_mn(b_hi + k * UMMA_K * 128), idn,
+                            (kb | k) != 0 ? 1u : 0u);
+#pragma unroll
+              for (int k = 0; k < BK / UMMA_K; ++k)
+                tc_mma_bf16(d_tmem, make_smem_desc(a_hi + k * UMMA_K * 2), make_smem_desc_mn(b_mid + k * UMMA_K * 128), idn, 1u);
+#pragma unroll
+              for (int k = 0; k < BK / UMMA_K; ++k)
+                tc_mma_bf16(d_tmem, make_smem_desc(a_mid + k * UMMA_K * 2), make_smem_desc_mn(b_hi + k * UMMA_K * 128), idn, 1u);
+            } else {
 #pragma unroll
             for (int k = 0; k < BK / UMMA_K; ++k)
               tc_mma_bf16(d_tmem, make_smem_desc(a_hi + k * UMMA_K * 2), make_smem_desc(b_hi + k * UMMA_K * 2), idesc,
@@ -378,6 +448,7 @@ gemm_tc_kernel(const __grid_constant__ TcMap map_a, const __grid_constant__ TcMa
 #pragma unroll
             for (int k = 0; k < BK / UMMA_K; ++k)
               tc_mma_bf16(d_tmem, make_smem_desc(a_mid + k * UMMA_K * 2), make_smem_desc(b_hi + k * UMMA_K * 2), idesc, 1u);
+            }
             if (CL > 1) {
               tc_commit_multicast(empty_bar(stage), (uint16_t)((1u << CL) - 1u));
               tc_commit_multicast(empty_bar(stage + 1), (uint16_t)((1u << CL) - 1u));
@@ -450,7 +521,7 @@ gemm_tc_kernel(const __grid_constant__ TcMap map_a, const __grid_constant__ TcMa
       pend_wtotal = 0;
     };
     int mt, nt, seq, slice;
-    for (int it = 0; cta_tile<BSTAT>(it, bid, gdim, walk_m_tiles, num_n_tiles, args.k_slices, step_m, step_n, mt, nt, seq, slice); ++it) {
+    for (int it = 0; cta_tile<BSTAT>(it, bid, gdim, walk_m_tiles, num_n_tiles, args.k_slices, step_m, step_n, mt, nt, seq, slice, n_fast); ++it) {
       const int m0 = (mt * CL + (int)cta_rank) * BM;
       const int nt_in = slice_nt(nt, num_n_tiles, slice);
       const long long n0 = args.n_begin + (long long)nt_in * BN * args.epi.tile_stride;
@@ -726,7 +797,7 @@ int get_encode_fn(EncodeTiledFn *out) {
 
 // 2-D bf16 tensor (rows, Kt) row-major with row stride ld elements; box = (64 elements of K) x box_rows, 128-byte
 // swizzle, zero OOB fill.
-int make_map(const __nv_bfloat16 *base, long long rows, int Kt, long long ld, int box_rows, TcMap *out) {
+int make_map(const __nv_bfloat16 *base, long long rows, long long Kt, long long ld, int box_rows, TcMap *out) {
   static_assert(sizeof(CUtensorMap) <= sizeof(TcMap), "CUtensorMap does not fit");
   EncodeTiledFn encode;
   if (get_encode_fn(&encode)) return -1;
@@ -754,7 +825,7 @@ int launch_gemm_tc(const __nv_bfloat16 *A, int M, const __nv_bfloat16 *B, long l
 
 static int launch_gemm_tc_impl(const __nv_bfloat16 *A, long long lda, int M, const __nv_bfloat16 *B, long long ldb,
                                long long N_total, long long n_begin, long long n_end, int Kt, int pair_kp,
-                               const TcEpilogue &epi, cudaStream_t st);
+                               const TcEpilogue &epi, cudaStream_t st, long long bn_rows = -1, long long bn_cols = 0);
 
 int launch_gemm_tc_ld(const __nv_bfloat16 *A, long long lda, int M, const __nv_bfloat16 *B, long long ldb,
                       long long N_total, long long n_begin, long long n_end, int Kt, const TcEpilogue &epi,
@@ -768,17 +839,35 @@ int launch_gemm_tc_pair(const __nv_bfloat16 *A, int M, const __nv_bfloat16 *B, l
   return launch_gemm_tc_impl(A, 2ll * Kp, M, B, 2ll * Kp, N_total, n_begin, n_end, 2 * Kp, Kp, epi, st);
 }
 
-// Kt = columns of the operands the tensor maps cover; pair_kp > 0: [hi | mid] operands of 2 * pair_kp columns
+int launch_gemm_tc_pair_bn(const __nv_bfloat16 *A, int M, const __nv_bfloat16 *Bn, long long k_rows, long long n_pad,
+                           long long N_total, long long n_begin, long long n_end, int Kp, const TcEpilogue &epi,
+                           cudaStream_t st) {
+  SERT_REQUIRE(epi.mode == TC_EPI_STORE, "pair operands serve the store epilogue");
+  SERT_REQUIRE(n_pad % 64 == 0 && N_total <= n_pad && k_rows <= Kp, "N-major B: blocks of n_pad columns, K rows within Kp");
+  return launch_gemm_tc_impl(A, 2ll * Kp, M, Bn, 2 * n_pad, N_total, n_begin, n_end, 2 * Kp, Kp, epi, st, k_rows, n_pad);
+}
+
+// Kt = columns of the operands the tensor maps cover; pair_kp > 0: [hi | mid] operands of 2 * pair_kp columns;
+// bn_rows >= 0: B is N-major, bn_rows K rows of [hi | mid] blocks of bn_cols columns (row stride ldb)
 static int launch_gemm_tc_impl(const __nv_bfloat16 *A, long long lda, int M, const __nv_bfloat16 *B, long long ldb,
                                long long N_total, long long n_begin, long long n_end, int Kt, int pair_kp,
-                               const TcEpilogue &epi, cudaStream_t st) {
+                               const TcEpilogue &epi, cudaStream_t st, long long bn_rows, long long bn_cols) {
   if (M == 0 || n_end <= n_begin) return 0;
   SERT_REQUIRE(pair_kp == 0 || (pair_kp % BK == 0 && Kt == 2 * pair_kp), "pair operands: two blocks of Kp columns");
   SERT_REQUIRE(n_begin >= 0 && n_end <= N_total && N_total < (1ll << 31), "bad column range");
   SERT_REQUIRE(Kt > 0 && Kt % BK == 0, "K must be a positive multiple of 64");
-  TcMap ma, mb;
+  const bool b_nmajor = bn_rows >= 0;
+  SERT_REQUIRE(!b_nmajor || pair_kp > 0, "N-major B needs pair operands");
+  TcMap ma, mb, mb2;
   if (make_map(A, M, Kt, lda, BM, &ma)) return -1;
-  if (make_map(B, N_total, Kt, ldb, BN, &mb)) return -1;
+  if (b_nmajor) {
+    // boxes of 64 N columns x 64 K rows over the hi block (columns [0, bn_cols)) and the mid block behind it
+    if (make_map(B, bn_rows, bn_cols, ldb, 64, &mb)) return -1;
+    if (make_map(B + bn_cols, bn_rows, bn_cols, ldb, 64, &mb2)) return -1;
+  } else {
+    if (make_map(B, N_total, Kt, ldb, BN, &mb)) return -1;
+    mb2 = mb;
+  }
   static std::atomic<uint64_t> configured{0};
   if (first_use_on_device(configured)) {
     SERT_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<false, TC_EPI_STORE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
@@ -798,6 +887,8 @@ static int launch_gemm_tc_impl(const __nv_bfloat16 *A, long long lda, int M, con
   args.num_kb = (pair_kp > 0 ? pair_kp : Kt) / BK;
   args.k_slices = 1;
   args.pair_kp = pair_kp;
+  args.n_fast = 0;
+  args.b_nmajor = b_nmajor ? 1 : 0;
   args.epi = epi;
   const long long m_tiles = (M + BM - 1) / BM, n_tiles = (n_end - n_begin + BN - 1) / BN;
   const long long tiles = m_tiles * n_tiles;
@@ -811,7 +902,7 @@ static int launch_gemm_tc_impl(const __nv_bfloat16 *A, long long lda, int M, con
   const bool bstat = pair_kp == 0 && args.num_kb <= STAGES && m_tiles >= 8 && n_tiles >= sms &&
                      per_cta * sms * 10 <= n_tiles * 12 && !(bstat_env != nullptr && bstat_env[0] == '0');
   if (bstat && epi.mode == TC_EPI_TOPK) {
-    gemm_tc_kernel<true, TC_EPI_TOPK><<<(int)std::min<long long>(n_tiles, sms), NUM_THREADS, SMEM_BYTES, st>>>(ma, mb, args);
+    gemm_tc_kernel<true, TC_EPI_TOPK><<<(int)std::min<long long>(n_tiles, sms), NUM_THREADS, SMEM_BYTES, st>>>(ma, mb, mb2, args);
     SERT_LAUNCH_CHECK();
     return 0;
   }
@@ -826,6 +917,12 @@ static int launch_gemm_tc_impl(const __nv_bfloat16 *A, long long lda, int M, con
     args.k_slices = (args.num_kb + per - 1) / per;       // no empty slice
     work = tiles * args.k_slices;
   }
+  {
+    // few n-tiles over a deep, tall A (dX = dZ . Wd^T: 2 n-tiles, A = 8 GB): keep the n-tiles of an A tile together
+    const char *nf = getenv("SERT_GEMM_NFAST");
+    if (epi.mode == TC_EPI_STORE && n_tiles >= 2 && n_tiles <= 4 && m_tiles >= 8 && !(nf != nullptr && nf[0] == '0'))
+      args.n_fast = 1;
+  }
   const int grid = (int)std::min<long long>(work, sms);
   // Clusters of 2 or 4 CTAs with a multicast B tile (store epilogue): a third / half less operand traffic through L2
   // for the GEMMs whose K is too deep for the B-stationary schedule (the log-linear projection and its gradients).
@@ -835,7 +932,7 @@ static int launch_gemm_tc_impl(const __nv_bfloat16 *A, long long lda, int M, con
   // SERT_GEMM_CLUSTER = 0: off, 4: clusters of four where the m-tiles allow.
   const char *cl_env = getenv("SERT_GEMM_CLUSTER");
   int cl = 1;
-  if (epi.mode == TC_EPI_STORE && m_tiles >= 8 && !(cl_env != nullptr && cl_env[0] == '0')) {
+  if (epi.mode == TC_EPI_STORE && m_tiles >= 8 && !b_nmajor && !(cl_env != nullptr && cl_env[0] == '0')) {
     if (cl_env != nullptr && cl_env[0] == '4' && (m_tiles % 4 == 0 || m_tiles >= 64) && sms % 4 == 0) cl = 4;
     else if (m_tiles % 2 == 0 || m_tiles >= 32) cl = 2;
   }
@@ -854,14 +951,14 @@ static int launch_gemm_tc_impl(const __nv_bfloat16 *A, long long lda, int M, con
     attr[0].val.clusterDim.x = cl; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    if (cl == 4) SERT_CUDA(cudaLaunchKernelEx(&cfg, gemm_tc_kernel<false, TC_EPI_STORE, 4>, ma, mb_part, args));
-    else SERT_CUDA(cudaLaunchKernelEx(&cfg, gemm_tc_kernel<false, TC_EPI_STORE, 2>, ma, mb_part, args));
+    if (cl == 4) SERT_CUDA(cudaLaunchKernelEx(&cfg, gemm_tc_kernel<false, TC_EPI_STORE, 4>, ma, mb_part, mb_part, args));
+    else SERT_CUDA(cudaLaunchKernelEx(&cfg, gemm_tc_kernel<false, TC_EPI_STORE, 2>, ma, mb_part, mb_part, args));
     count_launch();
     return 0;
   }
-  if (epi.mode == TC_EPI_TOPK) gemm_tc_kernel<false, TC_EPI_TOPK><<<grid, NUM_THREADS, SMEM_BYTES, st>>>(ma, mb, args);
-  else if (epi.mode == TC_EPI_GROUPMAX) gemm_tc_kernel<false, TC_EPI_GROUPMAX><<<grid, NUM_THREADS, SMEM_BYTES, st>>>(ma, mb, args);
-  else gemm_tc_kernel<false, TC_EPI_STORE><<<grid, NUM_THREADS, SMEM_BYTES, st>>>(ma, mb, args);
+  if (epi.mode == TC_EPI_TOPK) gemm_tc_kernel<false, TC_EPI_TOPK><<<grid, NUM_THREADS, SMEM_BYTES, st>>>(ma, mb, mb2, args);
+  else if (epi.mode == TC_EPI_GROUPMAX) gemm_tc_kernel<false, TC_EPI_GROUPMAX><<<grid, NUM_THREADS, SMEM_BYTES, st>>>(ma, mb, mb2, args);
+  else gemm_tc_kernel<false, TC_EPI_STORE><<<grid, NUM_THREADS, SMEM_BYTES, st>>>(ma, mb, mb2, args);
   SERT_LAUNCH_CHECK();
   return 0;
 }
@@ -946,6 +1043,38 @@ extern "C" SERT_API int sert_debug_gemm_tc(const float *a_host, const float *b_h
   }
   if (!rc) SERT_CUDA(cudaMemcpy(c_host, dC, (size_t)m * n * 4, cudaMemcpyDeviceToHost));
   cudaFree(dA); cudaFree(dB); cudaFree(dC); cudaFree(sA); cudaFree(sB); cudaFree(dbias);
+  return rc;
+}
+
+// ---- test hook: C = A . Bt with Bt given (k, n) row-major -- the N-major B operand of the pair path ------------------
+extern "C" SERT_API int sert_debug_gemm_tc_bn(const float *a_host, const float *bt_host, int m, int n, int k, float *c_host) {
+  using namespace sert;
+  SERT_REQUIRE(a_host && bt_host && c_host && m > 0 && n > 0 && k > 0, "bad argument");
+  const int Kp = tc_padded_k(k), Np = tc_padded_k(n);
+  float *dA = nullptr, *dB = nullptr, *dC = nullptr;
+  __nv_bfloat16 *sA = nullptr, *sB = nullptr;
+  SERT_CUDA(cudaMalloc(&dA, (size_t)m * k * 4));
+  SERT_CUDA(cudaMalloc(&dB, (size_t)n * k * 4));
+  SERT_CUDA(cudaMalloc(&dC, (size_t)m * n * 4));
+  SERT_CUDA(cudaMalloc(&sA, (size_t)m * 2 * Kp * 2));
+  SERT_CUDA(cudaMalloc(&sB, (size_t)k * 2 * Np * 2));
+  SERT_CUDA(cudaMemcpy(dA, a_host, (size_t)m * k * 4, cudaMemcpyHostToDevice));
+  SERT_CUDA(cudaMemcpy(dB, bt_host, (size_t)n * k * 4, cudaMemcpyHostToDevice));
+  SERT_CUDA(cudaMemset(dC, 0xff, (size_t)m * n * 4));
+  int rc = launch_split_bf16(dA, m, k, k, 2, SPLIT_A, sA, nullptr);
+  if (!rc) rc = launch_split_bf16(dB, k, n, n, 2, SPLIT_B, sB, nullptr);     // rows = K, [hi | mid] blocks of Np columns
+  TcEpilogue ep;
+  ep.mode = TC_EPI_STORE;
+  ep.C = dC;
+  ep.ldc = n;
+  if (!rc) rc = launch_gemm_tc_pair_bn(sA, m, sB, k, Np, n, 0, n, Kp, ep, nullptr);
+  cudaError_t e = cudaDeviceSynchronize();
+  if (!rc && e != cudaSuccess) {
+    set_error(std::string("gemm_tc (N-major B): ") + cudaGetErrorString(e));
+    rc = -1;
+  }
+  if (!rc) SERT_CUDA(cudaMemcpy(c_host, dC, (size_t)m * n * 4, cudaMemcpyDeviceToHost));
+  cudaFree(dA); cudaFree(dB); cudaFree(dC); cudaFree(sA); cudaFree(sB);
   return rc;
 }
 

@@ -74,6 +74,14 @@ int launch_gemm_tc(const __nv_bfloat16 *A, int M, const __nv_bfloat16 *B, long l
 // layout from two thirds of the operand traffic and storage.  Store epilogue only.
 int launch_gemm_tc_pair(const __nv_bfloat16 *A, int M, const __nv_bfloat16 *B, long long N_total, long long n_begin,
                         long long n_end, int Kp, const TcEpilogue &epi, cudaStream_t st);
+// Pair operands with an N-MAJOR B: Bn holds k_rows rows (the K index) of [hi | mid] blocks of n_pad columns (the N
+// index; row stride 2 * n_pad) -- e.g. the rows of a matrix whose TRANSPOSE is the B operand.  The kernel loads
+// 64 x 64 boxes and multiplies through an MN-major shared-memory descriptor, so no transposed copy is needed.
+// A: (M, 2 Kp) K-major pair operand with Kp >= k_rows (columns beyond k_rows must be zero or meet zero rows of Bn:
+// rows >= k_rows of Bn read as zeros).
+int launch_gemm_tc_pair_bn(const __nv_bfloat16 *A, int M, const __nv_bfloat16 *Bn, long long k_rows, long long n_pad,
+                           long long N_total, long long n_begin, long long n_end, int Kp, const TcEpilogue &epi,
+                           cudaStream_t st);
 // Same with explicit row strides (elements): the first Kt columns of wider operands, e.g. the hi.hi term alone of
 // 3-term split operands (Kt = Kp, lda = ldb = 3 Kp).
 int launch_gemm_tc_ld(const __nv_bfloat16 *A, long long lda, int M, const __nv_bfloat16 *B, long long ldb,

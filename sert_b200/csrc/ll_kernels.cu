@@ -136,12 +136,57 @@ __global__ void __launch_bounds__(256) ll_joint_kernel(const float *__restrict__
   S[(long long)i * lds + e] = acc;
 }
 
+// The same pass, four entities per thread (16-byte streaming loads of Z, every row of the window in flight), one CTA
+// per (instance, slot of kJointSlot entities); optionally leaves the slot's (max, sum exp) of the joint logits.
+__global__ void __launch_bounds__(256) ll_joint4_kernel(const float *__restrict__ Z, const float *__restrict__ rmax,
+                                                        const float *__restrict__ lrsum, float *__restrict__ S,
+                                                        int W, int E, long long ldz, long long lds,
+                                                        float2 *__restrict__ sstats, int slots) {
+  __shared__ float sm[32];
+  const int e = (blockIdx.x * 256 + threadIdx.x) * 4;
+  const int i = blockIdx.y;
+  const float log_lo = logf(SERT_CLIP_LO), log_hi = logf(SERT_CLIP_HI);
+  const bool ok = e < E;
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (ok) {
+    const float4 *z = reinterpret_cast<const float4 *>(Z + (long long)i * W * ldz + e);
+    const long long ld4 = ldz >> 2;
+#pragma unroll 5
+    for (int w = 0; w < W; ++w) {
+      const long long r = (long long)i * W + w;
+      const float4 v = __ldcs(z + w * ld4);
+      const float mx = __ldg(rmax + r), ls = __ldg(lrsum + r);
+      acc.x += fminf(fmaxf((v.x - mx) - ls, log_lo), log_hi);
+      acc.y += fminf(fmaxf((v.y - mx) - ls, log_lo), log_hi);
+      acc.z += fminf(fmaxf((v.z - mx) - ls, log_lo), log_hi);
+      acc.w += fminf(fmaxf((v.w - mx) - ls, log_lo), log_hi);
+    }
+    *reinterpret_cast<float4 *>(S + (long long)i * lds + e) = acc;
+  }
+  if (sstats != nullptr) {
+    float m = ok ? fmaxf(fmaxf(acc.x, acc.y), fmaxf(acc.z, acc.w)) : -INFINITY;
+    m = block_bcast(block_max(m, sm), sm);
+    float sum = ok ? expf(acc.x - m) + expf(acc.y - m) + expf(acc.z - m) + expf(acc.w - m) : 0.f;
+    sum = block_sum(sum, sm);
+    if (threadIdx.x == 0) sstats[(long long)i * slots + blockIdx.x] = make_float2(m, sum);
+  }
+}
+
 int launch_ll_joint(const float *Z, const float *rmax, const float *rsum, float *S, int B, int W, int E,
-                    int64_t ldz, int64_t lds, cudaStream_t st, float *lrsum_scratch) {
+                    int64_t ldz, int64_t lds, cudaStream_t st, float *lrsum_scratch, float2 *sstats) {
   if (B == 0) return 0;
   SERT_REQUIRE(lrsum_scratch != nullptr, "the joint pass needs B*W floats of scratch");
   ll_log_kernel<<<cdiv((long long)B * W, 256), 256, 0, st>>>(rsum, lrsum_scratch, (long long)B * W);
   SERT_LAUNCH_CHECK();
+  if ((E & 3) == 0 && (ldz & 3) == 0 && (lds & 3) == 0 && (reinterpret_cast<uintptr_t>(Z) & 15) == 0 &&
+      (reinterpret_cast<uintptr_t>(S) & 15) == 0) {
+    static_assert(kJointSlot == 256 * 4, "one CTA of 256 threads x 4 entities per slot");
+    const int slots = ll_joint_slots(E);
+    dim3 grid4(slots, B);
+    ll_joint4_kernel<<<grid4, 256, 0, st>>>(Z, rmax, lrsum_scratch, S, W, E, ldz, lds, sstats, slots);
+    SERT_LAUNCH_CHECK();
+    return sstats != nullptr ? 1 : 0;
+  }
   dim3 grid(cdiv(E, 256), B);
   ll_joint_kernel<<<grid, 256, 0, st>>>(Z, rmax, lrsum_scratch, S, B, W, E, ldz, lds);
   SERT_LAUNCH_CHECK();
@@ -153,12 +198,23 @@ __global__ void __launch_bounds__(256) ll_instance_kernel(LlInstanceArgs a) {
   __shared__ float sm[32];
   const int i = blockIdx.x;
   const float *s = a.S + (long long)i * a.lds;
-  float m = -INFINITY;
-  for (int e = threadIdx.x; e < a.E; e += blockDim.x) m = fmaxf(m, s[e]);
-  m = block_bcast(block_max(m, sm), sm);
-  float sum = 0.f;
-  for (int e = threadIdx.x; e < a.E; e += blockDim.x) sum += expf(s[e] - m);
-  sum = block_bcast(block_sum(sum, sm), sm);
+  float m = -INFINITY, sum = 0.f;
+  if (a.sstats != nullptr) {
+    // the joint pass left (max, sum exp) per slot of the row: fold them instead of reading the row twice
+    const float2 *st = a.sstats + (long long)i * a.slots;
+    for (int b = threadIdx.x; b < a.slots; b += blockDim.x) m = fmaxf(m, st[b].x);
+    m = block_bcast(block_max(m, sm), sm);
+    for (int b = threadIdx.x; b < a.slots; b += blockDim.x) {
+      const float2 v = st[b];
+      sum += v.y * expf(v.x - m);
+    }
+    sum = block_bcast(block_sum(sum, sm), sm);
+  } else {
+    for (int e = threadIdx.x; e < a.E; e += blockDim.x) m = fmaxf(m, s[e]);
+    m = block_bcast(block_max(m, sm), sm);
+    for (int e = threadIdx.x; e < a.E; e += blockDim.x) sum += expf(s[e] - m);
+    sum = block_bcast(block_sum(sum, sm), sm);
+  }
 
   const long long p0 = a.indptr[i] - a.nnz_base, p1 = a.indptr[i + 1] - a.nnz_base;
   const float wi = a.w ? a.w[i] : 1.0f;
@@ -181,7 +237,18 @@ __global__ void __launch_bounds__(256) ll_instance_kernel(LlInstanceArgs a) {
   if (!a.train) return;
   // ds = o * (do - sum_e do*o); do is non-zero only on the label columns
   float *ds = a.DS + (long long)i * a.lds;
-  for (int e = threadIdx.x; e < a.E; e += blockDim.x) ds[e] = -(expf(s[e] - m) / sum) * adot;
+  if ((a.E & 3) == 0 && (a.lds & 3) == 0 && (reinterpret_cast<uintptr_t>(a.S) & 15) == 0 &&
+      (reinterpret_cast<uintptr_t>(a.DS) & 15) == 0) {
+    const float4 *s4 = reinterpret_cast<const float4 *>(s);
+    float4 *d4 = reinterpret_cast<float4 *>(ds);
+    for (int e = threadIdx.x; e < (a.E >> 2); e += blockDim.x) {
+      const float4 v = __ldcs(s4 + e);
+      d4[e] = make_float4(-(expf(v.x - m) / sum) * adot, -(expf(v.y - m) / sum) * adot, -(expf(v.z - m) / sum) * adot,
+                          -(expf(v.w - m) / sum) * adot);
+    }
+  } else {
+    for (int e = threadIdx.x; e < a.E; e += blockDim.x) ds[e] = -(expf(s[e] - m) / sum) * adot;
+  }
   __syncthreads();
   for (long long p = p0 + threadIdx.x; p < p1; p += blockDim.x) {
     const int e = a.indices[p];
@@ -355,8 +422,10 @@ __global__ void __launch_bounds__(256) ll_dz_split_kernel(const float *__restric
       const __nv_bfloat16 h = __float2bfloat16_rn(dz[j]);
       hi[j] = __bfloat16_as_ushort(h);
       mid[j] = bf16_bits(dz[j] - __bfloat162float(h));
-      t_hi[tc + j][tr] = hi[j];
-      t_mid[tc + j][tr] = mid[j];
+      if (dZT_s != nullptr) {
+        t_hi[tc + j][tr] = hi[j];
+        t_mid[tc + j][tr] = mid[j];
+      }
     }
     if (r < BW64 && c < E64) {
       // A operand rows [hi | hi | mid]
@@ -374,6 +443,7 @@ __global__ void __launch_bounds__(256) ll_dz_split_kernel(const float *__restric
       }
     }
   }
+  if (dZT_s == nullptr) return;      // the gradient GEMM reads dZs N-major (launch_gemm_tc_pair_bn): no transposed copy
   __syncthreads();
   // B operand rows [hi | mid | hi] of the transpose: thread = (column, 16-row chunk)
   const int col = threadIdx.x >> 2, rc = (threadIdx.x & 3) * 16;

@@ -14,7 +14,13 @@ int launch_ll_row_stats(const float *Z, int64_t rows, int E, int64_t ldz, float 
 int launch_ll_softmax_inplace(float *Z, int64_t rows, int E, int64_t ldz, const float *rmax,
                               const float *rsum, cudaStream_t st);
 int launch_ll_joint(const float *Z, const float *rmax, const float *rsum, float *S, int B, int W, int E,
-                    int64_t ldz, int64_t lds, cudaStream_t st, float *lrsum_scratch);
+                    int64_t ldz, int64_t lds, cudaStream_t st, float *lrsum_scratch, float2 *sstats = nullptr);
+// sstats (optional, (B, ll_joint_slots(E)) float2): per instance and slot of kJointSlot entities, (max, sum of
+// exp(S - max)) of the joint logits the pass has just written -- launch_ll_instance then needs no pass of its own over
+// S for the softmax statistics.  Written only when E and the row strides are multiples of 4 (the vector path);
+// launch_ll_joint returns 1 (instead of 0) when it has written them.
+constexpr int kJointSlot = 1024;
+static inline int ll_joint_slots(long long E) { return (int)((E + kJointSlot - 1) / kJointSlot); }
 
 struct LlInstanceArgs {
   const float *S;          // (B,E) joint logits
@@ -30,6 +36,8 @@ struct LlInstanceArgs {
   float *ell_out;          // (B,) or nullptr
   double *loss_acc;
   bool train;
+  const float2 *sstats = nullptr;   // per-slot softmax statistics of S left by launch_ll_joint, or nullptr
+  int slots = 0;
 };
 int launch_ll_instance(const LlInstanceArgs &a, cudaStream_t st);
 

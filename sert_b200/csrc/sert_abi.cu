@@ -147,6 +147,7 @@ struct sert_model {
   int e_bound[kMaxPeers + 2] = {}, r_bound[kMaxPeers + 2] = {};
   void *rank_scratch = nullptr;    // sert_ll_rank_queries: sort keys and per-query sums (library-owned, grown on demand)
   size_t rank_scratch_bytes = 0;
+  float2 *sstats = nullptr;        // (B, ll_joint_slots(E)) softmax statistics of S per slot, left by the joint pass
   float *xstats = nullptr;         // [kMaxShards][2][B*W] gathered (row max, row sum)
   float *smax = nullptr, *ssum = nullptr, *adot = nullptr, *racc = nullptr;
   // host-batch staging
@@ -294,6 +295,7 @@ static size_t carve(sert_model &m, void *base) {
     m.rsum = b.take<float>(B * W);
     m.lrsum = b.take<float>(B * W);
     m.zstats = b.take<float2>(B * W * ((E + 63) / 64));
+    m.sstats = b.take<float2>(B * ll_joint_slots(E));
     m.xstats = b.take<float>(kMaxShards * 2 * B * W);
     m.smax = b.take<float>(B);
     m.ssum = b.take<float>(B);
@@ -895,13 +897,21 @@ static bool ll_fused_tail(const sert_model &m, long long BW, long long E, long l
 static int ll_backward_fused(sert_model &m, int B, int W, int E, int dw, float *Wd, cudaStream_t st) {
   const int BW = B * W;
   const int T = ll_terms();
-  if (launch_ll_dz_split(m.Z, m.rmax, m.lrsum, m.racc, m.DS, B, W, E, E, E, T, m.dZs, m.dZT_s, st)) return -1;
+  // Pair operands: gWd = X^T . dZ reads the rows of dZs as an N-major B operand, so dZ is written ONCE (8 instead of
+  // 16 GB of operand writes at BASELINE configs[4]).  SERT_LL_BN=0: the transposed copy dZT_s as K-major B.
+  static const char *bn_env = getenv("SERT_LL_BN");
+  const bool bn = T == 2 && !(bn_env != nullptr && bn_env[0] == '0');
+  if (launch_ll_dz_split(m.Z, m.rmax, m.lrsum, m.racc, m.DS, B, W, E, E, E, T, m.dZs, bn ? nullptr : m.dZT_s, st)) return -1;
   {
     if (launch_split_bf16_t(m.X, BW, dw, dw, T, SPLIT_A, m.XT_s, st)) return -1;
     TcEpilogue ep;
     ep.mode = TC_EPI_STORE; ep.C = m.grad + m.off[SERT_PARAM_DENSE_W]; ep.ldc = E;   // overwrites the (zeroed) grads
     ep.extra_row = dw; ep.extra_dst = m.grad + m.off[SERT_PARAM_DENSE_B];
-    if (ll_gemm(m.XT_s, dw + 1, m.dZT_s, E, 0, E, tc_padded_k(BW), ep, st)) return -1;
+    if (bn) {
+      if (launch_gemm_tc_pair_bn(m.XT_s, dw + 1, m.dZs, BW, tc_padded_k(E), E, 0, E, tc_padded_k(BW), ep, st)) return -1;
+    } else if (ll_gemm(m.XT_s, dw + 1, m.dZT_s, E, 0, E, tc_padded_k(BW), ep, st)) {
+      return -1;
+    }
   }
   {
     if (launch_split_bf16(Wd, dw, E, E, T, SPLIT_B, m.Wd_s, st)) return -1;
@@ -923,8 +933,13 @@ static int ll_train_step(sert_model &m, const int32_t *x, const int64_t *indptr,
   float *Wd = m.theta + m.off[SERT_PARAM_DENSE_W];
   m.stamp += 1;
   if (ll_forward(m, x, B, st)) return -1;
-  if (launch_ll_joint(m.Z, m.rmax, m.rsum, m.S, B, W, E, E, E, st, m.lrsum)) return -1;
-  if (launch_ll_instance(ll_instance_args(m, indptr, nnz_base, indices, data, w, true, nullptr), st)) return -1;
+  {
+    const int have = launch_ll_joint(m.Z, m.rmax, m.rsum, m.S, B, W, E, E, E, st, m.lrsum, m.sstats);
+    if (have < 0) return -1;
+    LlInstanceArgs ia = ll_instance_args(m, indptr, nnz_base, indices, data, w, true, nullptr);
+    if (have == 1) { ia.sstats = m.sstats; ia.slots = ll_joint_slots(E); }
+    if (launch_ll_instance(ia, st)) return -1;
+  }
   if (ll_fused_tail(m, BW, E, dw)) {
     if (launch_ll_racc_log(m.Z, m.rmax, m.lrsum, m.DS, B, W, E, E, E, m.racc, st)) return -1;
     if (ll_backward_fused(m, B, W, E, dw, Wd, st)) return -1;
@@ -946,10 +961,13 @@ static int ll_eval_step(sert_model &m, const int32_t *x, const int64_t *indptr, 
   cudaStream_t st = m.st;
   const int B = c.batch, W = c.window, E = (int)c.entities;
   if (ll_forward(m, x, B, st)) return -1;
-  if (launch_ll_joint(m.Z, m.rmax, m.rsum, m.S, B, W, E, E, E, st, m.lrsum)) return -1;
-  if (launch_ll_instance(ll_instance_args(m, indptr, nnz_base, indices, data, nullptr, false,
-                                          debug ? m.dbg_ell : nullptr), st))
-    return -1;
+  {
+    const int have = launch_ll_joint(m.Z, m.rmax, m.rsum, m.S, B, W, E, E, E, st, m.lrsum, m.sstats);
+    if (have < 0) return -1;
+    LlInstanceArgs ia = ll_instance_args(m, indptr, nnz_base, indices, data, nullptr, false, debug ? m.dbg_ell : nullptr);
+    if (have == 1) { ia.sstats = m.sstats; ia.slots = ll_joint_slots(E); }
+    if (launch_ll_instance(ia, st)) return -1;
+  }
   return launch_finalize_eval(m.acc, loss_out, 1.0f / (float)B, st);
 }
 
@@ -986,7 +1004,7 @@ static int ll_shard_forward(sert_model &m, const int32_t *x, const int64_t *indp
   float *mine = ll_my_stats(m, BW);
   if (ll_forward(m, x, B, m.st, mine, mine + BW)) return -1;      // local columns of Z and their statistics
   if (ll_shard_combine(m, BW, m.rmax, m.rsum)) return -1;
-  if (launch_ll_joint(m.Z, m.rmax, m.rsum, m.S, B, W, E, E, E, m.st, m.lrsum)) return -1;
+  if (launch_ll_joint(m.Z, m.rmax, m.rsum, m.S, B, W, E, E, E, m.st, m.lrsum) < 0) return -1;
   mine = ll_my_stats(m, B);
   if (launch_ll_row_stats(m.S, B, E, E, mine, mine + B, m.st)) return -1;
   if (ll_shard_combine(m, B, m.smax, m.ssum)) return -1;

@@ -70,6 +70,49 @@ def test_pair_operands_identity_layout():
         assert np.array_equal(got == 0, ref == 0)
 
 
+def run_bn(a, bt):
+    from sert_b200 import _native as N
+    lib = N.load()
+    m, k = a.shape
+    n = bt.shape[1]
+    c = np.empty((m, n), np.float32)
+    N.check(lib.sert_debug_gemm_tc_bn(N.host_ptr(a), N.host_ptr(bt), m, n, k, N.host_ptr(c)))
+    return c
+
+
+@pytest.mark.parametrize('m,n,k', [(128, 256, 64), (301, 2000, 1024), (100, 300, 70), (1, 9, 5), (301, 715, 10240),
+                                   (64, 777, 256), (301, 64, 128), (129, 513, 192)])
+def test_n_major_b_operand_matches_float64(m, n, k):
+    """B given as its transpose (k, n): the kernel loads 64 x 64 boxes of the row-major (K, N) matrix and multiplies
+    through an MN-major shared-memory descriptor (launch_gemm_tc_pair_bn -- how gWd = X^T . dZ reads dZ's rows without a
+    transposed copy).  Same bound as the K-major pair path; ragged M, N (last tile narrower than 256) and K."""
+    rng = np.random.default_rng(m * 3 + n * 11 + k)
+    a = rng.standard_normal((m, k)).astype(np.float32)
+    bt = rng.standard_normal((k, n)).astype(np.float32)
+    ref = a.astype(np.float64) @ bt.astype(np.float64)
+    got = run_bn(a, bt)
+    # (at K = 10240 the fp32 accumulation of 30 k products adds its own ~1e-3 on sums of magnitude 100)
+    assert np.abs(got - ref).max() < 5e-5 * np.sqrt(k)
+    got_k = run(a, np.ascontiguousarray(bt.T), 2)
+    assert np.abs(got - got_k).max() < 1e-5 * np.sqrt(k)      # same products in the same order: only the operand path differs
+
+
+def test_n_major_b_identity_layout():
+    """One non-zero per row of A and per column of B^T with a non-zero mid term: every output is a single product, so
+    a box landing at the wrong offset or a wrong descriptor stride shows up exactly."""
+    m, n, k = 256, 768, 192
+    a = np.zeros((m, k), np.float32)
+    bt = np.zeros((k, n), np.float32)
+    for i in range(m):
+        a[i, i % k] = np.float32(1.0 + (i % 97) / 1024.0 + 2.0 ** -12)
+    for j in range(n):
+        bt[(j * 5) % k, j] = np.float32(0.5 + (j % 89) / 512.0 + 2.0 ** -11)
+    ref = a.astype(np.float64) @ bt.astype(np.float64)
+    got = run_bn(a, bt)
+    np.testing.assert_allclose(got, ref, rtol=3e-5, atol=0)
+    assert np.array_equal(got == 0, ref == 0)
+
+
 def test_identity_layout():
     """Each output column picks one B row: catches swizzle / descriptor / TMEM lane mistakes exactly."""
     m, n, k = 256, 512, 128
