@@ -33,6 +33,9 @@ constexpr uint32_t TMEM_COLS = 512;
 // top-k epilogue: survivors of one tile that a WARP parks in shared memory (keys compacted across its 32 rows with
 // ballots; 8-byte key + 2-byte (owner lane, ordinal within the owner's row)), two buffers: this tile's and the
 // previous one's, whose list slots are being reserved
+#ifndef SERT_TC_TSTORE
+#define SERT_TC_TSTORE 1          // store epilogue: transposed 128-byte row stores (0: one row per lane)
+#endif
 #ifndef SERT_TC_GROUP
 #define SERT_TC_GROUP 16
 #endif
@@ -545,7 +548,14 @@ gemm_tc_kernel(const __grid_constant__ TcMap map_a, const __grid_constant__ TcMa
           tc_ld_32x32(t_row + (uint32_t)c0, v);
           tc_wait_ld();
           const long long gn0 = n0 + c0;
-          if (row_ok && gn0 < args.n_end) {
+          // Whole chunks of a 16-byte-aligned C go out TRANSPOSED inside groups of 8 lanes (warp-uniform condition):
+          // with one row per lane, a 16-byte store instruction touches 32 different 128-byte lines (32 L1 wavefronts:
+          // ~8 k cycles of store issue per 128 x 256 tile, the whole MMA time of the log-linear projection, whose
+          // epilogue writes the 8 GB logit matrix); after an 8 x 8 transpose of 16-byte pieces, 8 lanes write one
+          // row's 128 contiguous bytes and an instruction touches 4 lines.
+          const bool t_store = SERT_TC_TSTORE && gn0 + 32 <= args.n_end && ep.extra_row < 0 && (ep.ldc & 3) == 0 &&
+                               (reinterpret_cast<uintptr_t>(ep.C) & 15) == 0;
+          if ((row_ok || t_store) && gn0 < args.n_end) {
             const int nv = (int)(args.n_end - gn0 < 32 ? args.n_end - gn0 : 32);
             float w[32];
 #pragma unroll
@@ -563,7 +573,7 @@ gemm_tc_kernel(const __grid_constant__ TcMap map_a, const __grid_constant__ TcMa
                   if (j < nv) w[j] += __ldg(ep.bias + gn0 + j);
               }
             }
-            if (ep.row_stats != nullptr) {
+            if (ep.row_stats != nullptr && row_ok) {
               float mx = -INFINITY;
 #pragma unroll
               for (int j = 0; j < 32; ++j)
@@ -577,7 +587,37 @@ gemm_tc_kernel(const __grid_constant__ TcMap map_a, const __grid_constant__ TcMa
               st_max = m_new;
             }
             float *dst = gm == ep.extra_row ? ep.extra_dst + gn0 : ep.C + (long long)gm * ep.ldc + gn0;
-            if (nv == 32 && (reinterpret_cast<uintptr_t>(dst) & 15) == 0) {
+            if (t_store) {
+              float4 f[8];
+#pragma unroll
+              for (int j = 0; j < 8; ++j) f[j] = make_float4(w[4 * j], w[4 * j + 1], w[4 * j + 2], w[4 * j + 3]);
+#pragma unroll
+              for (int mk = 1; mk < 8; mk <<= 1) {
+                const bool upper = (lane & mk) != 0;
+#pragma unroll
+                for (int sl = 0; sl < 8; ++sl) {
+                  if (sl & mk) continue;
+                  const float4 send = upper ? f[sl] : f[sl | mk];
+                  float4 recv;
+                  recv.x = __shfl_xor_sync(0xffffffffu, send.x, mk);
+                  recv.y = __shfl_xor_sync(0xffffffffu, send.y, mk);
+                  recv.z = __shfl_xor_sync(0xffffffffu, send.z, mk);
+                  recv.w = __shfl_xor_sync(0xffffffffu, send.w, mk);
+                  if (upper) f[sl] = recv; else f[sl | mk] = recv;
+                }
+              }
+              // lane 8g + j now holds, in f[i], columns [4j, 4j + 4) of the row lane 8g + i read from TMEM
+              const int r0 = m0 + quarter * 32 + (lane & ~7);
+              float *base = ep.C + (long long)r0 * ep.ldc + gn0 + 4 * (lane & 7);
+#pragma unroll
+              for (int i = 0; i < 8; ++i) {
+                if (r0 + i < args.M) {
+                  if (ep.accumulate) red_add_f4(base + (long long)i * ep.ldc, f[i]);
+                  else *reinterpret_cast<float4 *>(base + (long long)i * ep.ldc) = f[i];
+                }
+              }
+            } else if (!row_ok) {
+            } else if (nv == 32 && (reinterpret_cast<uintptr_t>(dst) & 15) == 0) {
 #pragma unroll
               for (int j = 0; j < 32; j += 4) {
                 const float4 o = make_float4(w[j], w[j + 1], w[j + 2], w[j + 3]);
