@@ -60,6 +60,10 @@ struct KernelArgs {
                        // hi block behind map_b and the mid block behind map_b2 (boxes of 64 N x 64 K); the MMA reads it
                        // through an MN-major descriptor.  Lets gWd = X^T . dZ of the log-linear model consume the same
                        // split dZ rows as dX = dZ . Wd^T, so no transposed copy of dZ is ever written.
+  int tile_n;          // columns of C per n-tile: BN, or less (a multiple of 16, store epilogue) to cut a narrow C into
+                       // n-tiles of EQUAL width -- dX of the log-linear model is 300 columns: 256 + 44 left the CTAs of the
+                       // narrow tiles four times faster than their neighbours, and the A blocks both need (8 GB of split
+                       // dZ) came from HBM twice; 160 + 140 keeps the pairs in step, so the second read hits L2
   int n_fast;          // 1: tiles are numbered n-fastest inside a K slice (cta_tile)
   int pair_kp;         // > 0: "pair" operands [hi | mid] (two blocks of pair_kp columns, launch_gemm_tc_pair); num_kb
                        // then counts 64-column blocks of ONE term, and each takes two ring stages: (A_hi, B_hi) and
@@ -318,7 +322,8 @@ gemm_tc_kernel(const __grid_constant__ TcMap map_a, const __grid_constant__ TcMa
   const int lane = threadIdx.x & 31;
 
   const int num_m_tiles = (args.M + BM - 1) / BM;
-  const int num_n_tiles = (int)((args.n_end - args.n_begin + BN - 1) / BN);
+  const int TN = MODE == TC_EPI_STORE ? args.tile_n : BN;               // columns of C per n-tile
+  const int num_n_tiles = (int)((args.n_end - args.n_begin + TN - 1) / TN);
   const uint32_t cta_rank = CL > 1 ? cluster_cta_rank() : 0u;
   const int bid = (int)blockIdx.x / CL, gdim = (int)gridDim.x / CL;
   const int walk_m_tiles = (num_m_tiles + CL - 1) / CL;                  // m-tiles, or pairs of m-tiles
@@ -358,7 +363,7 @@ gemm_tc_kernel(const __grid_constant__ TcMap map_a, const __grid_constant__ TcMa
       int mt, nt, seq, slice;
       for (int it = 0; cta_tile<BSTAT>(it, bid, gdim, walk_m_tiles, num_n_tiles, args.k_slices, step_m, step_n, mt, nt, seq, slice, n_fast); ++it) {
         const int m0 = (mt * CL + (int)cta_rank) * BM;
-        const int n0 = (int)(args.n_begin + (long long)slice_nt(nt, num_n_tiles, slice) * BN * args.epi.tile_stride);
+        const int n0 = (int)(args.n_begin + (long long)slice_nt(nt, num_n_tiles, slice) * TN * args.epi.tile_stride);
         int kb0, nkb;
         slice_range(args.num_kb, args.k_slices, slice, kb0, nkb);
         if (BSTAT && seq == 0) {
@@ -412,7 +417,8 @@ gemm_tc_kernel(const __grid_constant__ TcMap map_a, const __grid_constant__ TcMa
         // log-linear model has 320 columns, and a full-width second tile spent 37 % of the GEMM's MMA time on padding
         uint32_t idesc = idesc_full;
         if (MODE == TC_EPI_STORE) {
-          const long long n_left = args.n_end - (args.n_begin + (long long)slice_nt(nt, num_n_tiles, slice) * BN * args.epi.tile_stride);
+          long long n_left = args.n_end - (args.n_begin + (long long)slice_nt(nt, num_n_tiles, slice) * TN * args.epi.tile_stride);
+          if (n_left > TN) n_left = TN;
           if (n_left < BN) idesc = make_idesc(BM, (int)((n_left + 15) / 16 * 16));
         }
         mbar_wait(tempty_bar(acc), acc_phase ^ 1u);      // epilogue has drained this accumulator
@@ -527,7 +533,9 @@ gemm_tc_kernel(const __grid_constant__ TcMap map_a, const __grid_constant__ TcMa
     for (int it = 0; cta_tile<BSTAT>(it, bid, gdim, walk_m_tiles, num_n_tiles, args.k_slices, step_m, step_n, mt, nt, seq, slice, n_fast); ++it) {
       const int m0 = (mt * CL + (int)cta_rank) * BM;
       const int nt_in = slice_nt(nt, num_n_tiles, slice);
-      const long long n0 = args.n_begin + (long long)nt_in * BN * args.epi.tile_stride;
+      const long long n0 = args.n_begin + (long long)nt_in * TN * args.epi.tile_stride;
+      // store epilogue: the tile's columns end at tile_end (tile_n may be narrower than the 256 accumulator columns)
+      const long long tile_end = MODE == TC_EPI_STORE && n0 + TN < args.n_end ? n0 + TN : args.n_end;
       const int gm = m0 + row;
       const bool row_ok = gm < args.M;
       // Rows are swept in increasing id order and tau only moves between launches, so a later row that
@@ -553,10 +561,10 @@ gemm_tc_kernel(const __grid_constant__ TcMap map_a, const __grid_constant__ TcMa
           // ~8 k cycles of store issue per 128 x 256 tile, the whole MMA time of the log-linear projection, whose
           // epilogue writes the 8 GB logit matrix); after an 8 x 8 transpose of 16-byte pieces, 8 lanes write one
           // row's 128 contiguous bytes and an instruction touches 4 lines.
-          const bool t_store = SERT_TC_TSTORE && gn0 + 32 <= args.n_end && ep.extra_row < 0 && (ep.ldc & 3) == 0 &&
+          const bool t_store = SERT_TC_TSTORE && gn0 + 32 <= tile_end && ep.extra_row < 0 && (ep.ldc & 3) == 0 &&
                                (reinterpret_cast<uintptr_t>(ep.C) & 15) == 0;
-          if ((row_ok || t_store) && gn0 < args.n_end) {
-            const int nv = (int)(args.n_end - gn0 < 32 ? args.n_end - gn0 : 32);
+          if ((row_ok || t_store) && gn0 < tile_end) {
+            const int nv = (int)(tile_end - gn0 < 32 ? tile_end - gn0 : 32);
             float w[32];
 #pragma unroll
             for (int j = 0; j < 32; ++j) w[j] = __uint_as_float(v[j]);
@@ -928,9 +936,20 @@ static int launch_gemm_tc_impl(const __nv_bfloat16 *A, long long lda, int M, con
   args.k_slices = 1;
   args.pair_kp = pair_kp;
   args.n_fast = 0;
+  args.tile_n = BN;
   args.b_nmajor = b_nmajor ? 1 : 0;
   args.epi = epi;
-  const long long m_tiles = (M + BM - 1) / BM, n_tiles = (n_end - n_begin + BN - 1) / BN;
+  const long long m_tiles = (M + BM - 1) / BM;
+  long long n_tiles = (n_end - n_begin + BN - 1) / BN;
+  {
+    // a narrow, ragged C (2-4 n-tiles) over many m-tiles: n-tiles of equal width (KernelArgs::tile_n)
+    const char *tn = getenv("SERT_GEMM_EQUAL_TILES");
+    if (epi.mode == TC_EPI_STORE && epi.row_stats == nullptr && epi.tile_stride == 1 && n_tiles >= 2 && n_tiles <= 4 &&
+        m_tiles >= 8 && (n_end - n_begin) % BN != 0 && !(tn != nullptr && tn[0] == '0')) {
+      const long long even = ((n_end - n_begin + n_tiles - 1) / n_tiles + 15) / 16 * 16;
+      if ((n_end - n_begin + even - 1) / even == n_tiles) args.tile_n = (int)even;
+    }
+  }
   const long long tiles = m_tiles * n_tiles;
   // B-stationary schedule (top-k epilogue; SERT_GEMM_BSTAT=0 turns it off): K fits the ring's B slots, every CTA gets
   // an n-tile, enough m-tiles to amortise the load of B (one bubble per n-tile), and whole n-tiles balance at least as

@@ -127,6 +127,10 @@ def test_predict_fn_matches_oracle_and_pickles():
     (dict(V=3000, E=300, dw=64, W=10, B=512), 0),      # same shapes, tensor cores off
     (dict(V=3000, E=8200, dw=64, W=8, B=512), 1),      # all three on tcgen05: fused backward tail (dZ written once, as
                                                        # the split operands; bias gradient through the ones row)
+    (dict(V=20000, E=8200, dw=300, W=10, B=256), 1),   # configs[4]'s row width over a ragged entity axis: pair operands
+                                                       # over 5 K blocks (projection, 20 x 33 tiles in clusters), 129
+                                                       # (dX: split-K, second n-tile 44 columns wide) and 40 (gWd: dZ's
+                                                       # rows as the N-major B operand, 301 rows with the ones row)
 ])
 def test_tensor_core_projection_matches_oracle(dims, tensor):
     """The word x entity GEMMs through the tcgen05 bf16x3 path: logits within 1e-4 relative, 3 Adadelta steps."""
