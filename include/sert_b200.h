@@ -207,6 +207,13 @@ SERT_API int sert_model_gather_table_state(sert_model *m);
 SERT_API int sert_model_table_shard_info(sert_model *m, int32_t *mode, int64_t *own_begin, int64_t *own_end,
                                          int64_t *table_floats);
 
+/* Host only (no device needed): the cut sert_model_set_table_shard_comm makes for this configuration over `world`
+ * ranks; every array has world + 1 entries.  Rank r updates entity rows [entity_row_bounds[r], [r + 1]), word rows
+ * [word_row_bounds[r], [r + 1]) = floats [float_bounds[r], [r + 1]) of the parameter arrays (pieces end on rows whose
+ * index is a multiple of 4), and with instance shards runs instances [instance_bounds[r], [r + 1]) of a batch. */
+SERT_API int sert_table_shard_plan(const sert_config *cfg, int32_t world, int64_t *entity_row_bounds,
+                                   int64_t *word_row_bounds, int64_t *float_bounds, int32_t *instance_bounds);
+
 /* ---- device-resident data set: replaces the theano.shared X/Y/W variables, sert/models.py:470-480 -- */
 /* x_dev (N,W) int32; labels either one-hot y_dev (N,) int32 (vector space, bin/train.py:186-245) or CSR
  * (indptr_dev int64 (N+1), indices_dev int32, data_dev f32; bin/prepare.py:593-597); w_dev (N,) f32 or NULL

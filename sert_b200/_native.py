@@ -60,6 +60,7 @@ SIGNATURES = {
     'sert_model_set_entity_shard_comm': (c_int, [c_void_p, c_void_p, c_int64, c_int64]),
     'sert_model_set_table_shard_comm': (c_int, [c_void_p, c_void_p, c_int32]),
     'sert_model_gather_table_state': (c_int, [c_void_p]),
+    'sert_table_shard_plan': (c_int, [c_void_p, c_int32, c_void_p, c_void_p, c_void_p, c_void_p]),
     'sert_model_table_shard_info': (c_int, [c_void_p, ctypes.POINTER(c_int32), ctypes.POINTER(c_int64),
                                             ctypes.POINTER(c_int64), ctypes.POINTER(c_int64)]),
     'sert_scorer_set_comm': (c_int, [c_void_p, c_void_p]),

@@ -1086,6 +1086,31 @@ int sert_model_arena_bytes(const sert_config *cfg, size_t *bytes) {
   return 0;
 }
 
+static int table_shard_partition(const sert_model &m, int world, long long *e_row, long long *r_row, long long *lo4,
+                                 int *inst);
+
+// Host only (no device needed): how sert_model_set_table_shard_comm would cut a model of this configuration over `world`
+// ranks.  Arrays of world + 1 entries.
+int sert_table_shard_plan(const sert_config *cfg, int32_t world, int64_t *entity_row_bounds, int64_t *word_row_bounds,
+                          int64_t *float_bounds, int32_t *instance_bounds) {
+  SERT_REQUIRE(cfg && entity_row_bounds && word_row_bounds && float_bounds && instance_bounds, "null argument");
+  if (validate(*cfg)) return -1;
+  SERT_REQUIRE(is_vs(*cfg), "table shards are for vector-space models");
+  sert_model tmp;
+  tmp.cfg = *cfg;
+  carve(tmp, nullptr);
+  long long e_row[kMaxPeers + 2], r_row[kMaxPeers + 2], lo4[kMaxPeers + 2];
+  int inst[kMaxPeers + 2];
+  if (table_shard_partition(tmp, world, e_row, r_row, lo4, inst)) return -1;
+  for (int r = 0; r <= world; ++r) {
+    entity_row_bounds[r] = e_row[r];
+    word_row_bounds[r] = r_row[r];
+    float_bounds[r] = lo4[r] * 4;
+    instance_bounds[r] = inst[r];
+  }
+  return 0;
+}
+
 int sert_model_create(const sert_config *cfg, void *arena_dev, size_t arena_bytes, void *stream,
                       sert_model **out) {
   SERT_REQUIRE(cfg && arena_dev && out, "null argument");
@@ -1307,6 +1332,31 @@ int sert_model_set_entity_shard_comm(sert_model *m, sert_comm *comm, int64_t ent
   return sert_model_set_entity_shard(m, comm->rank, comm->world, entity_begin, entities_total, nccl_exchange, m);
 }
 
+// Table shards: pieces of (nearly) equal float counts that end on row boundaries (row index a multiple of 4: whole
+// 16-byte chunks), so that a gradient row is formed and updated by exactly one rank.  The entity table comes first in
+// the arena (carve).  e_row / r_row [r], [r + 1] = rank r's entity / word rows, lo4 [r], [r + 1] = its 16-byte chunks of
+// the arena arrays, inst [r], [r + 1] = its instances of a batch (tiles of 8) for instance shards.
+static int table_shard_partition(const sert_model &m, int world, long long *e_row, long long *r_row, long long *lo4,
+                                 int *inst) {
+  SERT_REQUIRE(world >= 1 && world <= kMaxPeers + 1, "table shards span at most 8 ranks (one NVLink domain)");
+  SERT_REQUIRE(m.off[SERT_PARAM_ENTITY_REPR] < m.off[SERT_PARAM_WORD_REPR] &&
+               m.off[SERT_PARAM_WORD_REPR] < m.off[SERT_PARAM_DENSE_W] &&
+               m.off[SERT_PARAM_DENSE_W] < m.off[SERT_PARAM_DENSE_B], "unexpected parameter layout");
+  const long long tables4 = m.off[SERT_PARAM_DENSE_W] / 4;      // the two tables come first in the arena (carve)
+  const long long E = m.cfg.entities, V = m.cfg.vocab, de = m.cfg.entity_dim, dw = m.cfg.word_dim;
+  const long long offE = m.off[SERT_PARAM_ENTITY_REPR], offR = m.off[SERT_PARAM_WORD_REPR];
+  for (int r = 0; r <= world; ++r) {
+    const long long t = (E * de + V * dw) * r / world;     // floats before the boundary
+    if (r == world) { e_row[r] = E; r_row[r] = V; lo4[r] = tables4; }
+    else if (t < E * de) { e_row[r] = (t / de) & ~3ll; r_row[r] = 0; lo4[r] = (offE + e_row[r] * de) / 4; }
+    else { e_row[r] = E; r_row[r] = ((t - E * de) / dw) & ~3ll; lo4[r] = (offR + r_row[r] * dw) / 4; }
+  }
+  lo4[0] = 0;
+  const int tiles = cdiv(m.cfg.batch, 8);
+  for (int r = 0; r <= world; ++r) inst[r] = (int)std::min<long long>(m.cfg.batch, (long long)tiles * r / world * 8);
+  return 0;
+}
+
 static void table_shard_release(sert_model *m) {
   if (m->table_comm == nullptr) return;
   trace_report(*m);
@@ -1374,23 +1424,10 @@ int sert_model_set_table_shard_comm(sert_model *m, sert_comm *comm, int32_t peer
     SERT_REQUIRE(c.batch >= 8 * comm->world, "instance shards need at least one tile of 8 instances per rank");
     SERT_REQUIRE(c.vocab < (1 << 28) && c.entities < (1 << 28), "instance shards: row ids must stay below 2^28");
   }
-  const long long tables4 = m->off[SERT_PARAM_DENSE_W] / 4;      // the two tables come first in the arena (carve)
-  SERT_REQUIRE(m->off[SERT_PARAM_ENTITY_REPR] < m->off[SERT_PARAM_DENSE_W] &&
-               m->off[SERT_PARAM_WORD_REPR] < m->off[SERT_PARAM_DENSE_W] &&
-               m->off[SERT_PARAM_DENSE_W] < m->off[SERT_PARAM_DENSE_B], "unexpected parameter layout");
-  // Pieces of (nearly) equal float counts that end on row boundaries (row index a multiple of 4: 16-byte chunks),
-  // so that a gradient row is formed by exactly one rank.  The entity table comes first in the arena (carve).
-  const long long E = m->cfg.entities, V = m->cfg.vocab, de = m->cfg.entity_dim, dw = m->cfg.word_dim;
-  const long long offE = m->off[SERT_PARAM_ENTITY_REPR], offR = m->off[SERT_PARAM_WORD_REPR];
-  SERT_REQUIRE(offE < offR, "unexpected parameter layout");
+  const long long E = m->cfg.entities, V = m->cfg.vocab;
   long long e_row[kMaxPeers + 2], r_row[kMaxPeers + 2];
-  for (int r = 0; r <= comm->world; ++r) {
-    const long long t = (E * de + V * dw) * r / comm->world;     // floats before the boundary
-    if (r == comm->world) { e_row[r] = E; r_row[r] = V; m->table_lo4[r] = tables4; }
-    else if (t < E * de) { e_row[r] = (t / de) & ~3ll; r_row[r] = 0; m->table_lo4[r] = (offE + e_row[r] * de) / 4; }
-    else { e_row[r] = E; r_row[r] = ((t - E * de) / dw) & ~3ll; m->table_lo4[r] = (offR + r_row[r] * dw) / 4; }
-  }
-  m->table_lo4[0] = 0;
+  int inst_rows[kMaxPeers + 2];
+  if (table_shard_partition(*m, comm->world, e_row, r_row, m->table_lo4, inst_rows)) return -1;
   m->table_own.e_lo = (int)e_row[comm->rank]; m->table_own.e_hi = (int)e_row[comm->rank + 1];
   m->table_own.r_lo = (int)r_row[comm->rank]; m->table_own.r_hi = (int)r_row[comm->rank + 1];
   // one model: every rank starts from rank 0's parameters, optimiser state and step, and draws rank 0's negatives
@@ -1472,9 +1509,8 @@ int sert_model_set_table_shard_comm(sert_model *m, sert_comm *comm, int32_t peer
       else if (m->seg[sg].flags == m->flagE) m->seg[sg].flags = fl;
     }
     m->grad = m->gsh; m->flagE = fl; m->flagR = fl + E;
-    const int tiles = cdiv(m->cfg.batch, 8);
     for (int r = 0; r <= comm->world; ++r) {
-      m->inst_bound[r] = std::min<long long>(m->cfg.batch, (long long)tiles * r / comm->world * 8);
+      m->inst_bound[r] = inst_rows[r];
       m->e_bound[r] = (int)e_row[r];
       m->r_bound[r] = (int)r_row[r];
     }

@@ -5,6 +5,8 @@ import os
 import re
 import subprocess
 
+import numpy as np
+
 import pytest
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -49,6 +51,40 @@ def test_arena_size_and_config_validation(native_lib):
     sbytes = N.c_size_t(0)
     N.check(native_lib.sert_scorer_arena_bytes(1000000, 256, 10000, 128, ctypes.byref(sbytes)))
     assert sbytes.value >= 1000000 * 256 * 4
+
+
+@pytest.mark.parametrize('V,E,dw,de,B', [(100000, 50000, 128, 128, 4096), (1500, 700, 128, 128, 256),
+                                         (801, 333, 64, 48, 128), (40, 9000, 300, 128, 64), (5, 3, 4, 4, 8)])
+def test_table_shard_plan_partitions_the_tables(native_lib, V, E, dw, de, B):
+    """sert_table_shard_plan (host only): the pieces of sert_model_set_table_shard_comm tile the two tables without
+    gaps, end on rows whose index is a multiple of 4, are nearly equal in floats, agree between the row view and the
+    float view, and the instance bounds cut the batch into whole tiles of 8."""
+    from sert_b200 import _native as N
+    cfg = N.SertConfig(kind=N.KIND_VECTORSPACE, batch=B, window=5, num_negatives=4, vocab=V, entities=E, word_dim=dw,
+                       entity_dim=de, lambda_=0.01, loss_slots=64, seed=1, inference_only=0, dtype_mode=0, reserved1=0)
+    for world in range(1, 9):
+        e = np.zeros(world + 1, np.int64)
+        r = np.zeros(world + 1, np.int64)
+        f = np.zeros(world + 1, np.int64)
+        inst = np.zeros(world + 1, np.int32)
+        N.check(native_lib.sert_table_shard_plan(ctypes.byref(cfg), world, N.host_ptr(e), N.host_ptr(r), N.host_ptr(f),
+                                                 N.host_ptr(inst)))
+        assert e[0] == 0 and r[0] == 0 and f[0] == 0 and e[-1] == E and r[-1] == V
+        assert np.all(np.diff(e) >= 0) and np.all(np.diff(r) >= 0) and np.all(np.diff(f) >= 0)
+        assert np.all((e % 4 == 0) | (e == E)) and np.all((r % 4 == 0) | (r == V))      # inside a table: whole 16-byte chunks
+        owned = np.diff(e) * de + np.diff(r) * dw                     # floats of table rows per rank
+        assert owned.sum() == E * de + V * dw
+        # the float view covers the same rows (the arena pads each table to 64 floats: the pads ride with a neighbour)
+        assert np.all(np.abs(np.diff(f) - owned) <= 128)
+        ideal = (E * de + V * dw) / world
+        assert np.all(np.abs(owned - ideal) <= 4 * max(dw, de))
+        # a word-row piece starts only once the entity table is exhausted
+        assert np.all((r[:-1] == 0) | (e[:-1] == E))
+        assert inst[0] == 0 and inst[-1] == B and np.all(np.diff(inst) >= 0) and np.all(inst[:-1] % 8 == 0)
+    with pytest.raises(RuntimeError, match='at most 8 ranks'):
+        N.check(native_lib.sert_table_shard_plan(ctypes.byref(cfg), 9, N.host_ptr(np.zeros(10, np.int64)),
+                                                 N.host_ptr(np.zeros(10, np.int64)), N.host_ptr(np.zeros(10, np.int64)),
+                                                 N.host_ptr(np.zeros(10, np.int32))))
 
 
 def test_no_cpu_fallback_without_device(native_lib):
