@@ -214,6 +214,51 @@ __device__ __forceinline__ void tc_mma_bf16(uint32_t d_tmem, uint64_t a_desc, ui
       ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// ---- two-SM MMA (cta_group::2): the CTA pair of a cluster multiplies ONE 256 x N tile; CTA r holds rows [128 r, +128)
+// of A and rows [N/2 r, +N/2) of B in its own shared memory and the matching 128 rows of the accumulator in its own TMEM;
+// the leader (rank 0) issues the MMAs, both CTAs' TMA loads complete on the LEADER's barrier.
+__device__ __forceinline__ uint32_t mapa_cluster(uint32_t addr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ void tma_load_2d_cg2(uint32_t dst, const void *map, uint32_t leader_bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(dst), "l"(map), "r"(leader_bar), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_bar) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_bar) : "memory");
+}
+__device__ __forceinline__ void tc_alloc_cg2(uint32_t smem_result, uint32_t cols) {
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_result), "r"(cols)
+               : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tc_dealloc_cg2(uint32_t taddr, uint32_t cols) {
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(cols) : "memory");
+}
+__device__ __forceinline__ void tc_mma_bf16_cg2(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
+                                                uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void tc_commit_cg2(uint32_t bar, uint16_t cta_mask) {
+  asm volatile(
+      "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar),
+      "h"(cta_mask)
+      : "memory");
+}
+__device__ __forceinline__ float fast_exp2(float x) {
+  float r;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
 // arrive on an mbarrier when all previously issued tcgen05.mma of this thread have completed
 __device__ __forceinline__ void tc_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
@@ -299,10 +344,19 @@ constexpr uint32_t make_idesc(int m, int n) {
 // CL*16 + 32 KB per K block through L2 instead of CL*48 KB (-33 % at CL = 2, -50 % at CL = 4); a stage's slot is free
 // for the next load once ALL the cluster's MMA warps have retired their reads of it (tcgen05.commit multicast on the
 // empty barriers).
-template <bool BSTAT, int MODE, int CL = 1>
+// CG2 (with CL = 2, store epilogue): the pair runs as ONE two-SM MMA (cta_group::2, M = 256) instead of two single-SM MMAs
+// over a multicast B tile.  Each CTA then stages only its own 128 rows of A and its own half of B -- 32 instead of 48 KB
+// per ring step, so the 192 KB ring holds SIX steps (three blocks of pair operands in flight instead of two), and the
+// shared-memory write traffic of the B tile halves.
+template <bool BSTAT, int MODE, int CL = 1, bool CG2 = false>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ TcMap map_a, const __grid_constant__ TcMap map_b, const __grid_constant__ TcMap map_b2,
                const KernelArgs args) {
+  static_assert(!CG2 || (CL == 2 && !BSTAT && MODE == TC_EPI_STORE), "the two-SM MMA serves the clustered store kernels");
+  constexpr int STAGES = CG2 ? 6 : sert::STAGES;
+  constexpr uint32_t B_STAGE_BYTES = CG2 ? sert::B_STAGE_BYTES / 2 : sert::B_STAGE_BYTES;
+  constexpr uint32_t STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
+  static_assert(STAGES * STAGE_BYTES == sert::STAGES * sert::STAGE_BYTES, "the ring keeps its 192 KB");
   extern __shared__ unsigned char smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;   // SWIZZLE_128B needs 1024-byte alignment
   const uint32_t smem_a = smem_base;
@@ -337,17 +391,23 @@ gemm_tc_kernel(const __grid_constant__ TcMap map_a, const __grid_constant__ TcMa
     tma_prefetch_desc(&map_b2);
     for (int s = 0; s < STAGES; ++s) {
       mbar_init(full_bar(s), 1);
-      mbar_init(empty_bar(s), CL);            // one arrival per MMA warp that reads the slot
+      mbar_init(empty_bar(s), CG2 ? 1 : CL);  // one arrival per MMA warp that reads the slot (CG2: the leader's commit)
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(tfull_bar(a), 1);
-      mbar_init(tempty_bar(a), EPI_WARPS);   // one arrive per epilogue warp
+      mbar_init(tempty_bar(a), CG2 ? 2 * EPI_WARPS : EPI_WARPS);   // one arrive per epilogue warp (CG2: of both CTAs, at the leader)
     }
     mbar_init(bfull_bar, 1);
     mbar_init(bempty_bar, 1);
     fence_barrier_init();
   }
-  if (warp == 1) tc_alloc(tmem_ptr_smem, TMEM_COLS);
+  if (CG2) {
+    __syncthreads();
+    cluster_sync_all();                      // both CTAs are resident before the pair allocates its tensor memory
+    if (warp == 1) tc_alloc_cg2(tmem_ptr_smem, TMEM_COLS);
+  } else if (warp == 1) {
+    tc_alloc(tmem_ptr_smem, TMEM_COLS);
+  }
   tc_fence_before();
   __syncthreads();
   if (CL > 1) cluster_sync_all();            // the peers' barriers exist before anything is multicast at them
@@ -378,6 +438,19 @@ gemm_tc_kernel(const __grid_constant__ TcMap map_a, const __grid_constant__ TcMa
         for (int step = kb0 * per_kb; step < (kb0 + nkb) * per_kb; ++step) {
           const int kc = args.pair_kp > 0 ? (step >> 1) * BK + (step & 1) * args.pair_kp : step * BK;
           mbar_wait(empty_bar(stage), phase ^ 1u);
+          if (CG2) {
+            // both CTAs' bytes complete on the leader's barrier; each CTA stages its own A rows and its half of the
+            // B rows the MMA multiplies (N/2 rows from n0 + rank * N/2; the box is 128 rows, the rest is ignored)
+            const uint32_t lead_full = mapa_cluster(full_bar(stage), 0u);
+            if (cta_rank == 0) mbar_expect_tx(full_bar(stage), 2u * STAGE_BYTES);
+            long long n_left = args.n_end - n0;
+            if (n_left > TN) n_left = TN;
+            const int n_mma = n_left < BN ? (int)((n_left + 15) / 16 * 16) : BN;
+            tma_load_2d_cg2(smem_a + stage * A_STAGE_BYTES, &map_a, lead_full, kc, m0);
+            tma_load_2d_cg2(smem_b + stage * B_STAGE_BYTES, &map_b, lead_full, kc, n0 + (int)cta_rank * (n_mma / 2));
+            if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+            continue;
+          }
           mbar_expect_tx(full_bar(stage), BSTAT ? A_STAGE_BYTES : STAGE_BYTES);
           tma_load_2d(smem_a + stage * A_STAGE_BYTES, &map_a, full_bar(stage), kc, m0);
           if (CL > 1) {
@@ -399,8 +472,18 @@ gemm_tc_kernel(const __grid_constant__ TcMap map_a, const __grid_constant__ TcMa
     }
   } else if (warp == 1) {
     // ================= MMA issuer =================
-    if (lane == 0) {
+    if (lane == 0 && (!CG2 || cta_rank == 0)) {
       constexpr uint32_t idesc_full = make_idesc(BM, BN);
+      auto mma = [&](uint32_t d, uint64_t ad, uint64_t bd, uint32_t id, uint32_t accum) {
+        if (CG2) tc_mma_bf16_cg2(d, ad, bd, id, accum);
+        else tc_mma_bf16(d, ad, bd, id, accum);
+      };
+      // the ring slot is free once the MMAs reading it have retired: in every CTA whose loads land there
+      auto release_stage = [&](int st) {
+        if (CG2) tc_commit_cg2(empty_bar(st), (uint16_t)0x3);
+        else if (CL > 1) tc_commit_multicast(empty_bar(st), (uint16_t)((1u << CL) - 1u));
+        else tc_commit(empty_bar(st));
+      };
       int stage = 0;
       uint32_t phase = 0;
       int acc = 0;
@@ -421,6 +504,7 @@ gemm_tc_kernel(const __grid_constant__ TcMap map_a, const __grid_constant__ TcMa
           if (n_left > TN) n_left = TN;
           if (n_left < BN) idesc = make_idesc(BM, (int)((n_left + 15) / 16 * 16));
         }
+        if (CG2) idesc = (idesc & ~(0x1fu << 24)) | ((uint32_t)(2 * BM >> 4) << 24);   // M = 256 over the pair
         mbar_wait(tempty_bar(acc), acc_phase ^ 1u);      // epilogue has drained this accumulator
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + (uint32_t)acc * BN;
@@ -438,33 +522,28 @@ gemm_tc_kernel(const __grid_constant__ TcMap map_a, const __grid_constant__ TcMa
               const uint32_t idn = idesc | IDESC_B_MN_MAJOR;
 #pragma unroll
               for (int k = 0; k < BK / UMMA_K; ++k)
-                tc_mma_bf16(d_tmem, make_smem_desc(a_hi + k * UMMA_K * 2), make_smem_desc_mn(b_hi + k * UMMA_K * 128), idn,
+                mma(d_tmem, make_smem_desc(a_hi + k * UMMA_K * 2), make_smem_desc_mn(b_hi + k * UMMA_K * 128), idn,
                             (kb | k) != 0 ? 1u : 0u);
 #pragma unroll
               for (int k = 0; k < BK / UMMA_K; ++k)
-                tc_mma_bf16(d_tmem, make_smem_desc(a_hi + k * UMMA_K * 2), make_smem_desc_mn(b_mid + k * UMMA_K * 128), idn, 1u);
+                mma(d_tmem, make_smem_desc(a_hi + k * UMMA_K * 2), make_smem_desc_mn(b_mid + k * UMMA_K * 128), idn, 1u);
 #pragma unroll
               for (int k = 0; k < BK / UMMA_K; ++k)
-                tc_mma_bf16(d_tmem, make_smem_desc(a_mid + k * UMMA_K * 2), make_smem_desc_mn(b_hi + k * UMMA_K * 128), idn, 1u);
+                mma(d_tmem, make_smem_desc(a_mid + k * UMMA_K * 2), make_smem_desc_mn(b_hi + k * UMMA_K * 128), idn, 1u);
             } else {
 #pragma unroll
             for (int k = 0; k < BK / UMMA_K; ++k)
-              tc_mma_bf16(d_tmem, make_smem_desc(a_hi + k * UMMA_K * 2), make_smem_desc(b_hi + k * UMMA_K * 2), idesc,
+              mma(d_tmem, make_smem_desc(a_hi + k * UMMA_K * 2), make_smem_desc(b_hi + k * UMMA_K * 2), idesc,
                           (kb | k) != 0 ? 1u : 0u);
 #pragma unroll
             for (int k = 0; k < BK / UMMA_K; ++k)
-              tc_mma_bf16(d_tmem, make_smem_desc(a_hi + k * UMMA_K * 2), make_smem_desc(b_mid + k * UMMA_K * 2), idesc, 1u);
+              mma(d_tmem, make_smem_desc(a_hi + k * UMMA_K * 2), make_smem_desc(b_mid + k * UMMA_K * 2), idesc, 1u);
 #pragma unroll
             for (int k = 0; k < BK / UMMA_K; ++k)
-              tc_mma_bf16(d_tmem, make_smem_desc(a_mid + k * UMMA_K * 2), make_smem_desc(b_hi + k * UMMA_K * 2), idesc, 1u);
+              mma(d_tmem, make_smem_desc(a_mid + k * UMMA_K * 2), make_smem_desc(b_hi + k * UMMA_K * 2), idesc, 1u);
             }
-            if (CL > 1) {
-              tc_commit_multicast(empty_bar(stage), (uint16_t)((1u << CL) - 1u));
-              tc_commit_multicast(empty_bar(stage + 1), (uint16_t)((1u << CL) - 1u));
-            } else {
-              tc_commit(empty_bar(stage));
-              tc_commit(empty_bar(stage + 1));
-            }
+            release_stage(stage);
+            release_stage(stage + 1);
             stage += 2;
             if (stage == STAGES) { stage = 0; phase ^= 1u; }
           }
@@ -477,14 +556,14 @@ gemm_tc_kernel(const __grid_constant__ TcMap map_a, const __grid_constant__ TcMa
 #pragma unroll
           for (int k = 0; k < BK / UMMA_K; ++k) {
             // advancing K by 16 bf16 = 32 bytes inside the 128-byte swizzled row
-            tc_mma_bf16(d_tmem, make_smem_desc(a_addr + k * UMMA_K * 2), make_smem_desc(b_addr + k * UMMA_K * 2),
+            mma(d_tmem, make_smem_desc(a_addr + k * UMMA_K * 2), make_smem_desc(b_addr + k * UMMA_K * 2),
                         idesc, (kb | k) != 0 ? 1u : 0u);
           }
-          if (CL > 1) tc_commit_multicast(empty_bar(stage), (uint16_t)((1u << CL) - 1u));   // ... in every CTA of the cluster: the peers' loads land here too
-          else tc_commit(empty_bar(stage));              // frees the smem slot once those MMAs retire
+          release_stage(stage);                          // frees the smem slot once those MMAs retire
           if (++stage == STAGES) { stage = 0; phase ^= 1u; }
         }
-        tc_commit(tfull_bar(acc));                       // accumulator complete -> epilogue
+        if (CG2) tc_commit_cg2(tfull_bar(acc), (uint16_t)0x3);   // both CTAs' epilogues read their halves
+        else tc_commit(tfull_bar(acc));                  // accumulator complete -> epilogue
         if (BSTAT && seq == num_m_tiles - 1) tc_commit(bempty_bar);   // ... and the B slots are free once it is
         if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
       }
@@ -563,7 +642,68 @@ gemm_tc_kernel(const __grid_constant__ TcMap map_a, const __grid_constant__ TcMa
           // row's 128 contiguous bytes and an instruction touches 4 lines.
           const bool t_store = SERT_TC_TSTORE && gn0 + 32 <= tile_end && ep.extra_row < 0 && (ep.ldc & 3) == 0 &&
                                (reinterpret_cast<uintptr_t>(ep.C) & 15) == 0;
-          if ((row_ok || t_store) && gn0 < tile_end) {
+          if (t_store) {
+            // ---- whole chunk, every lane takes part (rows beyond M carry garbage that is never stored): no per-element
+            // or per-lane predicates anywhere, so the shuffles below sit in warp-uniform code
+            float w[32];
+#pragma unroll
+            for (int j = 0; j < 32; ++j) w[j] = __uint_as_float(v[j]);
+            if (ep.bias != nullptr) {
+              if ((reinterpret_cast<uintptr_t>(ep.bias + gn0) & 15) == 0) {
+#pragma unroll
+                for (int j = 0; j < 32; j += 4) {              // broadcast 16-byte loads: every lane adds the same bias
+                  const float4 bv = __ldg(reinterpret_cast<const float4 *>(ep.bias + gn0 + j));
+                  w[j] += bv.x; w[j + 1] += bv.y; w[j + 2] += bv.z; w[j + 3] += bv.w;
+                }
+              } else {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) w[j] += __ldg(ep.bias + gn0 + j);
+              }
+            }
+            if (ep.row_stats != nullptr) {
+              float mx = w[0];
+#pragma unroll
+              for (int j = 1; j < 32; ++j) mx = fmaxf(mx, w[j]);
+              const float m_new = fmaxf(st_max, mx);
+              // exp(w - m) = 2^(w log2e - m log2e): one FFMA and one MUFU per value
+              const float kLog2e = 1.4426950408889634f;
+              const float ml = m_new * kLog2e;
+              float add = 0.f;
+#pragma unroll
+              for (int j = 0; j < 32; ++j) add += fast_exp2(fmaf(w[j], kLog2e, -ml));
+              st_sum = st_sum * __expf(st_max - m_new) + add;
+              st_max = m_new;
+            }
+            float4 f[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) f[j] = make_float4(w[4 * j], w[4 * j + 1], w[4 * j + 2], w[4 * j + 3]);
+#pragma unroll
+            for (int mk = 1; mk < 8; mk <<= 1) {
+              const bool upper = (lane & mk) != 0;
+#pragma unroll
+              for (int sl = 0; sl < 8; ++sl) {
+                if (sl & mk) continue;
+                const float4 send = upper ? f[sl] : f[sl | mk];
+                float4 recv;
+                recv.x = __shfl_xor_sync(0xffffffffu, send.x, mk);
+                recv.y = __shfl_xor_sync(0xffffffffu, send.y, mk);
+                recv.z = __shfl_xor_sync(0xffffffffu, send.z, mk);
+                recv.w = __shfl_xor_sync(0xffffffffu, send.w, mk);
+                if (upper) f[sl] = recv; else f[sl | mk] = recv;
+              }
+            }
+            // lane 8g + j now holds, in f[i], columns [4j, 4j + 4) of the row lane 8g + i read from TMEM
+            const int r0 = m0 + quarter * 32 + (lane & ~7);
+            float *base = ep.C + (long long)r0 * ep.ldc + gn0 + 4 * (lane & 7);
+            const int rows_here = args.M - r0;               // the same for the 8 lanes of a group
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              if (i < rows_here) {
+                if (ep.accumulate) red_add_f4(base + (long long)i * ep.ldc, f[i]);
+                else *reinterpret_cast<float4 *>(base + (long long)i * ep.ldc) = f[i];
+              }
+            }
+          } else if (row_ok && gn0 < tile_end) {
             const int nv = (int)(tile_end - gn0 < 32 ? tile_end - gn0 : 32);
             float w[32];
 #pragma unroll
@@ -581,7 +721,7 @@ gemm_tc_kernel(const __grid_constant__ TcMap map_a, const __grid_constant__ TcMa
                   if (j < nv) w[j] += __ldg(ep.bias + gn0 + j);
               }
             }
-            if (ep.row_stats != nullptr && row_ok) {
+            if (ep.row_stats != nullptr) {
               float mx = -INFINITY;
 #pragma unroll
               for (int j = 0; j < 32; ++j)
@@ -595,37 +735,7 @@ gemm_tc_kernel(const __grid_constant__ TcMap map_a, const __grid_constant__ TcMa
               st_max = m_new;
             }
             float *dst = gm == ep.extra_row ? ep.extra_dst + gn0 : ep.C + (long long)gm * ep.ldc + gn0;
-            if (t_store) {
-              float4 f[8];
-#pragma unroll
-              for (int j = 0; j < 8; ++j) f[j] = make_float4(w[4 * j], w[4 * j + 1], w[4 * j + 2], w[4 * j + 3]);
-#pragma unroll
-              for (int mk = 1; mk < 8; mk <<= 1) {
-                const bool upper = (lane & mk) != 0;
-#pragma unroll
-                for (int sl = 0; sl < 8; ++sl) {
-                  if (sl & mk) continue;
-                  const float4 send = upper ? f[sl] : f[sl | mk];
-                  float4 recv;
-                  recv.x = __shfl_xor_sync(0xffffffffu, send.x, mk);
-                  recv.y = __shfl_xor_sync(0xffffffffu, send.y, mk);
-                  recv.z = __shfl_xor_sync(0xffffffffu, send.z, mk);
-                  recv.w = __shfl_xor_sync(0xffffffffu, send.w, mk);
-                  if (upper) f[sl] = recv; else f[sl | mk] = recv;
-                }
-              }
-              // lane 8g + j now holds, in f[i], columns [4j, 4j + 4) of the row lane 8g + i read from TMEM
-              const int r0 = m0 + quarter * 32 + (lane & ~7);
-              float *base = ep.C + (long long)r0 * ep.ldc + gn0 + 4 * (lane & 7);
-#pragma unroll
-              for (int i = 0; i < 8; ++i) {
-                if (r0 + i < args.M) {
-                  if (ep.accumulate) red_add_f4(base + (long long)i * ep.ldc, f[i]);
-                  else *reinterpret_cast<float4 *>(base + (long long)i * ep.ldc) = f[i];
-                }
-              }
-            } else if (!row_ok) {
-            } else if (nv == 32 && (reinterpret_cast<uintptr_t>(dst) & 15) == 0) {
+            if (nv == 32 && (reinterpret_cast<uintptr_t>(dst) & 15) == 0) {
 #pragma unroll
               for (int j = 0; j < 32; j += 4) {
                 const float4 o = make_float4(w[j], w[j + 1], w[j + 2], w[j + 3]);
@@ -810,7 +920,10 @@ gemm_tc_kernel(const __grid_constant__ TcMap map_a, const __grid_constant__ TcMa
       }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(tempty_bar(acc));
+      if (lane == 0) {
+        if (CG2) mbar_arrive_cluster(mapa_cluster(tempty_bar(acc), 0u));   // the leader's MMA warp waits for both CTAs
+        else mbar_arrive(tempty_bar(acc));
+      }
       if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
     }
     flush_pending();
@@ -821,7 +934,8 @@ gemm_tc_kernel(const __grid_constant__ TcMap map_a, const __grid_constant__ TcMa
   if (CL > 1) cluster_sync_all();            // no CTA leaves while a peer may still signal its barriers
   if (warp == 1) {
     tc_fence_after();
-    tc_dealloc(tmem_base, TMEM_COLS);
+    if (CG2) tc_dealloc_cg2(tmem_base, TMEM_COLS);
+    else tc_dealloc(tmem_base, TMEM_COLS);
   }
 }
 
@@ -924,6 +1038,7 @@ static int launch_gemm_tc_impl(const __nv_bfloat16 *A, long long lda, int M, con
     SERT_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<true, TC_EPI_TOPK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
     SERT_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<false, TC_EPI_STORE, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
     SERT_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<false, TC_EPI_STORE, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
+    SERT_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<false, TC_EPI_STORE, 2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
   }
   int dev = 0, sms = kNumSMs;
   SERT_CUDA(cudaGetDevice(&dev));
@@ -1010,7 +1125,10 @@ static int launch_gemm_tc_impl(const __nv_bfloat16 *A, long long lda, int M, con
     attr[0].val.clusterDim.x = cl; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    if (cl == 4) SERT_CUDA(cudaLaunchKernelEx(&cfg, gemm_tc_kernel<false, TC_EPI_STORE, 4>, ma, mb_part, mb_part, args));
+    static const char *cg2_env = getenv("SERT_GEMM_CG2");
+    const bool cg2 = cl == 2 && !(cg2_env != nullptr && cg2_env[0] == '0');   // two-SM MMA for the pairs (SERT_GEMM_CG2=0: two single-SM MMAs over a multicast B tile)
+    if (cg2) SERT_CUDA(cudaLaunchKernelEx(&cfg, gemm_tc_kernel<false, TC_EPI_STORE, 2, true>, ma, mb_part, mb_part, args));
+    else if (cl == 4) SERT_CUDA(cudaLaunchKernelEx(&cfg, gemm_tc_kernel<false, TC_EPI_STORE, 4>, ma, mb_part, mb_part, args));
     else SERT_CUDA(cudaLaunchKernelEx(&cfg, gemm_tc_kernel<false, TC_EPI_STORE, 2>, ma, mb_part, mb_part, args));
     count_launch();
     return 0;
